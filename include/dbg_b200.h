@@ -1,0 +1,154 @@
+/*
+ * dbg_b200.h  --  C ABI of the B200-native de Bruijn assembly hot path.
+ *
+ * This is the drop-in boundary for the path `II_assembleFromReads.py:58-63` drives in the
+ * reference (`debruijn.construct_graph` + `debruijn.output_contigs`).  The reference is pure
+ * Python, so "the FFI a maintainer would bind" is ctypes: INTEGRATION.md shows the stub, and
+ * `py-debruijn_b200/_native.py` is that stub in full.  Plain pointers and sizes only; no
+ * torch / CUDA types in any signature (a stream is passed as void*).
+ *
+ * Conventions
+ *   - every call returns DBG_OK (0) or a negative dbg_status; dbg_last_error() gives text
+ *   - the caller owns every buffer it passes; the handle owns all device memory
+ *   - one handle per host thread / stream; the library starts no host threads
+ *   - node ids are table-slot indices, valid until the next dbg_build* on the handle
+ *   - alphabet: DNA, exactly the bytes 'A','C','G','T' (2-bit codes 0..3 in that order)
+ *   - k-mers ("nodes", debruijn.py:127) are 2k-bit integers, first base most significant:
+ *     k <= 31 uses 64-bit keys, k <= 63 uses 128-bit keys (key_hi is 0 for k <= 31)
+ *   - a tag is (global read index << 32 | position in read) of a node's FIRST occurrence
+ *     in the reference's iteration order (debruijn.py:123-126); sorting by tag reproduces
+ *     the reference's dict order
+ */
+#ifndef DBG_B200_H
+#define DBG_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dbg_handle dbg_t;
+
+typedef enum {
+    DBG_OK = 0,
+    DBG_ERR_CUDA = -1,       /* CUDA runtime error, or no usable device                    */
+    DBG_ERR_ARG = -2,        /* bad argument (k out of range, null pointer, ...)            */
+    DBG_ERR_ALPHABET = -3,   /* a read holds a byte other than A/C/G/T                      */
+    DBG_ERR_NOMEM = -4,      /* device or host allocation failed                            */
+    DBG_ERR_STATE = -5,      /* call out of order (e.g. dbg_walk before dbg_build)          */
+    DBG_ERR_ZERODIV = -6,    /* threshold == 0 with a multi-successor node (debruijn.py:163
+                                raises ZeroDivisionError there)                             */
+    DBG_ERR_OVERFLOW = -7    /* read index / position / node count exceeds 32 bits          */
+} dbg_status;
+
+/* dbg_build flags */
+#define DBG_FINAL        1u  /* construct_graph(..., final=True), debruijn.py:281-283        */
+#define DBG_EXACT_ORDER  2u  /* also compute first-appearance order of each node's successors
+                                (Counter.most_common tie order, debruijn.py:159-164); costs a
+                                second pass over the reads only when multi-successor nodes exist */
+#define DBG_NO_PULL_READS 4u /* skip pull_out_read (debruijn.py:274-278)                      */
+
+/* node flag bits (dbg_export_nodes) */
+#define DBG_NODE_START   0x02u  /* reference indegree == 0 (debruijn.py:137-143 quirk)       */
+#define DBG_NODE_BRANCH  0x04u  /* > 1 successor survives pruningEdges (debruijn.py:230-236) */
+#define DBG_NODE_DEADEND 0x08u  /* reference outdegree == 0                                   */
+#define DBG_NODE_PULLED  0x10u  /* in already_pull_out (debruijn.py:249-254)                  */
+#define DBG_NODE_MULTI   0x20u  /* > 1 distinct successor before pruning                      */
+
+/* contig terminal kinds (debruijn.py:288-316) */
+#define DBG_TERM_DEADEND 0u  /* stopped at a node without successors; node is on the path     */
+#define DBG_TERM_BRANCH  1u  /* stopped at a branch node; node is on the path                 */
+#define DBG_TERM_PULLED  2u  /* stopped in front of a pulled node; node is NOT on the path    */
+
+typedef struct {
+    uint64_t n_reads;
+    uint64_t n_bases;
+    uint64_t n_windows;      /* (k+1)-mer instances = iterations of debruijn.py:126-144       */
+    uint64_t n_nodes;        /* distinct k-mers        -> "number of {k}mer:"                 */
+    uint64_t n_edges;        /* distinct (k+1)-mers    = len(edge_count_table)                */
+    uint64_t n_multi;        /* nodes with > 1 distinct successor                             */
+    uint64_t n_branch;       /* -> "branch number:" (before `final` empties the list)         */
+    uint64_t n_starts;       /* -> "Number of kmers have no income edges:"                    */
+    uint64_t n_pulled;       /* len(already_pull_out)                                         */
+    uint64_t n_pull_reads;   /* len(pull_out_read) (0 when DBG_FINAL)                         */
+    uint64_t n_contigs;      /* after dbg_walk                                                */
+    uint64_t n_cycle_starts; /* starts whose walk hits a cycle and emits nothing (:289)       */
+    uint64_t table_slots;
+    uint64_t table_bytes;
+    uint64_t hll_estimate;   /* distinct-node estimate used to size the table                 */
+    uint32_t key_words;      /* 1 (k <= 31) or 2                                              */
+    uint32_t jump_rounds;    /* pointer-jumping rounds run by dbg_walk                        */
+    /* device time per stage, CUDA events on the handle's stream, milliseconds */
+    float ms_h2d, ms_pack, ms_estimate, ms_table_init, ms_insert, ms_finalize, ms_order,
+          ms_lists, ms_tips, ms_pull_reads, ms_build_total, ms_walk_rank, ms_walk_emit,
+          ms_walk_total;
+} dbg_stats_t;
+
+typedef struct {
+    uint32_t start;          /* node id of the first node on the path                          */
+    uint32_t n_nodes;        /* nodes on the path; contig length = k + n_nodes - 1             */
+    uint32_t terminal;       /* node id at which the walk stopped                              */
+    uint32_t kind;           /* DBG_TERM_*                                                     */
+    uint64_t seg_begin;      /* [seg_begin, seg_end) into the segment list: > 1 segment only   */
+    uint64_t seg_end;        /*   for final=True paths that run through multi-successor nodes  */
+} dbg_contig_t;
+
+typedef struct {
+    uint32_t entry;          /* node id at which the segment starts                            */
+    uint32_t n_nodes;        /* nodes taken from this segment                                  */
+} dbg_segment_t;
+
+/* ---- lifetime ---- */
+int  dbg_create(dbg_t **out, int device, int k);
+void dbg_destroy(dbg_t *h);
+const char *dbg_last_error(const dbg_t *h);          /* h may be NULL: error of a failed create */
+int  dbg_set_stream(dbg_t *h, void *cuda_stream);    /* cudaStream_t; NULL = handle's own stream */
+int  dbg_version(void);
+
+/* ---- construct_graph (debruijn.py:206-285) ----
+ * reads = concatenated ASCII bases + n_reads+1 offsets; read i is bases[off[i] .. off[i+1]).
+ * read_idx_base is added to every read index in the tags (multi-GPU / batched callers).
+ * threshold is pruningEdges' divisor (debruijn.py:163), as a double.
+ * dbg_build takes HOST pointers (copies are part of the call); dbg_build_device takes
+ * DEVICE pointers already resident in HBM.  Both run the whole graph stage: pack, table
+ * build, degrees/prune/branch flags, tip pruning, pull-out read flags.                      */
+int dbg_build(dbg_t *h, const uint8_t *bases, const uint64_t *read_off, uint64_t n_reads,
+              uint64_t read_idx_base, double threshold, uint32_t flags);
+int dbg_build_device(dbg_t *h, const uint8_t *d_bases, const uint64_t *d_read_off,
+                     uint64_t n_reads, uint64_t n_bases, uint64_t read_idx_base,
+                     double threshold, uint32_t flags);
+int dbg_stats(dbg_t *h, dbg_stats_t *out);
+
+/* nodes, unordered (sort by first_tag for the reference's dict order).  Any pointer may be
+ * NULL.  succ_cnt: 4 per node = edge_count_table[node + "ACGT"[c]]; kept: low 8 bits = kept
+ * successor bases in E order (2 bits each, first in bits 0-1), bits 8-10 = how many are kept
+ * (pruningEdges result, debruijn.py:150-166).                                               */
+int dbg_export_nodes(dbg_t *h, uint32_t *node_id, uint64_t *key_lo, uint64_t *key_hi,
+                     uint64_t *first_tag, uint32_t *succ_cnt, uint8_t *flags, uint16_t *kept);
+int dbg_branch_nodes(dbg_t *h, uint32_t *node_id);   /* n_branch ids, reference order        */
+int dbg_pulled_nodes(dbg_t *h, uint32_t *node_id);   /* n_pulled ids, reference order        */
+int dbg_pull_reads(dbg_t *h, uint8_t *read_flags);   /* n_reads bytes, 1 = in pull_out_read  */
+int dbg_node_keys(dbg_t *h, const uint32_t *node_id, uint64_t n, uint64_t *key_lo, uint64_t *key_hi);
+
+/* edge_count_table[(k+1)-mer] for n ASCII (k+1)-mers laid back to back; 0 = absent
+ * (II_assembleFromReads.py:17 indexes it per contig window)                                 */
+int dbg_lookup_edges(dbg_t *h, const uint8_t *kplus1mers, uint64_t n, uint32_t *counts);
+
+/* ---- output_contigs (debruijn.py:326-347) ----
+ * stop_at_branch = 1 when branch_kmer is the list construct_graph returned with final=False,
+ * 0 when it is empty (final=True).  Contigs come out in the reference's order.             */
+int dbg_walk(dbg_t *h, int stop_at_branch, uint64_t *n_contigs);
+int dbg_contigs(dbg_t *h, dbg_contig_t *out);                      /* n_contigs entries      */
+int dbg_segments(dbg_t *h, dbg_segment_t *out, uint64_t *n_segments); /* out may be NULL      */
+/* contig strings idx[0..n) written back to back into buf at off[i] (host pointers);
+ * string i has length k + n_nodes - 1, no terminator                                        */
+int dbg_materialize(dbg_t *h, const uint64_t *idx, uint64_t n, char *buf, const uint64_t *off);
+/* getScore (II_assembleFromReads.py:14-18) of contigs idx[0..n): sum of edge counts along
+ * the path                                                                                  */
+int dbg_contig_scores(dbg_t *h, const uint64_t *idx, uint64_t n, uint64_t *scores);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DBG_B200_H */

@@ -1,0 +1,939 @@
+// dbg_b200.cu -- host side of the C ABI declared in include/dbg_b200.h.
+//
+// One handle = one graph on one device.  dbg_build* runs the construct_graph stages
+// (debruijn.py:206-285), dbg_walk the output_contigs stage (debruijn.py:326-347); every stage is a
+// kernel in dbg_kernels.cuh.  The only work done on the host is what the reference defines
+// sequentially and what is tiny: the branch-order conflict resolution of tip pruning
+// (debruijn.py:241-254, over the candidate paths the device enumerated) and the path enumeration
+// of final=True through surviving multi-successor nodes (debruijn.py:314, over the junction table
+// the device ranked).  There is no CPU implementation of any stage behind this ABI: without a
+// CUDA device dbg_create fails.
+//
+// tests/emu builds this same file with g++ and tests/emu/cuda_emu.h (-DDBG_EMU) so that the CPU
+// test-suite can run the host logic and kernel bodies; that library is test infrastructure and is
+// never loaded by the product.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <unordered_set>
+#include <utility>
+#include <vector>
+
+#ifdef DBG_EMU
+#define LAUNCH(kernel, grid, block, stream, ...) \
+    emu::launch(dim3((unsigned)(grid)), dim3((unsigned)(block)), 0, [&]() { kernel(__VA_ARGS__); })
+#else
+#include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
+#define LAUNCH(kernel, grid, block, stream, ...) kernel<<<(unsigned)(grid), (unsigned)(block), 0, stream>>>(__VA_ARGS__)
+#endif
+
+#include "../../include/dbg_b200.h"
+#include "dbg_kernels.cuh"
+
+#define DBG_ABI_VERSION 1
+#define MAX_ENUM_CONTIGS (1ull << 26)
+#define MAX_ENUM_STEPS (1ull << 32)
+
+// -------------------------------------------------------------------------------------------------
+// handle
+// -------------------------------------------------------------------------------------------------
+struct DevBuf {                 // grow-only device buffer: repeated builds on one handle reuse HBM
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+enum { EV_MAX = 24 };
+
+struct dbg_handle {
+    int device = 0;
+    int k = 0;
+    int W = 1;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    std::string err;
+    bool built = false, walked = false;
+    uint32_t build_flags = 0;
+    double threshold = 3.0;
+    uint64_t n_reads = 0, n_bases = 0, n_words = 0, n_tiles = 0, n_slots = 0, read_idx_base = 0;
+    float pending_h2d = 0;
+    const uint64_t *d_off = nullptr;          // offsets in use (caller's for build_device, ours for build)
+    DevBuf b_bases, b_off, b_packed, b_tile, b_table, b_flags, b_kept, b_succ, b_link, b_ctr, b_hll,
+           b_order, b_tag, b_tag2, b_slot, b_slot2, b_sorttmp, b_branch, b_starts, b_pulled, b_readflags,
+           b_recs, b_cnt32, b_off64, b_contig, b_junction, b_scratch[6];
+    DevCounters ctr;
+    dbg_stats_t st;
+    std::vector<uint32_t> branch, pulled;     // reference order
+    std::vector<uint8_t> read_flags;
+    bool read_flags_valid = false;
+    std::vector<dbg_contig_t> contigs;
+    std::vector<dbg_segment_t> segments;
+    cudaEvent_t ev[EV_MAX];
+    int n_ev = 0;
+};
+
+static std::string g_create_error;
+
+static int fail(dbg_t *h, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(h, e_ == cudaErrorMemoryAllocation ? DBG_ERR_NOMEM : DBG_ERR_CUDA,        \
+                        "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));       \
+    } while (0)
+#define CKK() CK(cudaGetLastError())
+#define TRY(expr) do { int r_ = (expr); if (r_ != DBG_OK) return r_; } while (0)
+
+static int reserve(dbg_t *h, DevBuf &b, size_t bytes) {
+    if (bytes == 0) bytes = 16;
+    if (b.cap >= bytes) return DBG_OK;
+    if (b.p) { cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+    size_t want = bytes + bytes / 16 + 256;
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) {
+        b.p = nullptr;
+        return fail(h, DBG_ERR_NOMEM, "device allocation of %zu bytes failed: %s", want, cudaGetErrorString(e));
+    }
+    b.cap = want;
+    return DBG_OK;
+}
+template <typename T> static T *ptr(DevBuf &b) { return (T *)b.p; }
+
+static inline uint64_t cdiv(uint64_t a, uint64_t b) { return (a + b - 1) / b; }
+static inline uint64_t blocks_for(uint64_t n) { return n ? cdiv(n, DBG_BLOCK) : 1; }
+
+static int ev_mark(dbg_t *h) {                       // returns the event index
+    int i = h->n_ev++;
+    cudaEventRecord(h->ev[i], h->stream);
+    return i;
+}
+static float ev_ms(dbg_t *h, int a, int b) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, h->ev[a], h->ev[b]);
+    return ms;
+}
+
+// -------------------------------------------------------------------------------------------------
+// sort (tag, slot) pairs by tag: the reference's dict order is first-occurrence order
+// -------------------------------------------------------------------------------------------------
+static int sort_by_tag(dbg_t *h, uint64_t n, u32 *d_sorted_slots_out) {
+    // input pairs are in b_tag / b_slot; sorted slots land in d_sorted_slots_out
+    if (n == 0) return DBG_OK;
+#ifdef DBG_EMU
+    std::vector<std::pair<u64, u32>> v(n);
+    u64 *t = ptr<u64>(h->b_tag);
+    u32 *s = ptr<u32>(h->b_slot);
+    for (uint64_t i = 0; i < n; i++) v[i] = std::make_pair(t[i], s[i]);
+    std::sort(v.begin(), v.end());
+    for (uint64_t i = 0; i < n; i++) d_sorted_slots_out[i] = v[i].second;
+#else
+    TRY(reserve(h, h->b_tag2, n * 8));
+    size_t tmp = 0;
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, ptr<u64>(h->b_tag), ptr<u64>(h->b_tag2), ptr<u32>(h->b_slot),
+                                       d_sorted_slots_out, (int64_t)n, 0, 64, h->stream));
+    TRY(reserve(h, h->b_sorttmp, tmp));
+    CK(cub::DeviceRadixSort::SortPairs(h->b_sorttmp.p, tmp, ptr<u64>(h->b_tag), ptr<u64>(h->b_tag2),
+                                       ptr<u32>(h->b_slot), d_sorted_slots_out, (int64_t)n, 0, 64, h->stream));
+#endif
+    return DBG_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// templated stage drivers
+// -------------------------------------------------------------------------------------------------
+static double hll_estimate(const std::vector<u32> &regs) {
+    const double m = (double)HLL_M;
+    double sum = 0;
+    int zeros = 0;
+    for (u32 r : regs) { sum += ldexp(1.0, -(int)r); zeros += (r == 0); }
+    double alpha = 0.7213 / (1.0 + 1.079 / m);
+    double e = alpha * m * m / sum;
+    if (e <= 2.5 * m && zeros) e = m * log(m / (double)zeros);      // small-range correction
+    return e;
+}
+
+static int fetch_counters(dbg_t *h) {
+    CK(cudaMemcpyAsync(&h->ctr, h->b_ctr.p, sizeof(DevCounters), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return DBG_OK;
+}
+
+template <int W>
+static int collect_sorted(dbg_t *h, u32 want, uint64_t expect, DevBuf &out, u64 *cursor) {
+    // slots whose flags hit `want`, sorted by first-occurrence tag
+    TRY(reserve(h, out, (expect + 1) * 4));
+    if (expect == 0) return DBG_OK;
+    TRY(reserve(h, h->b_tag, expect * 8));
+    TRY(reserve(h, h->b_slot, expect * 4));
+    CK(cudaMemsetAsync(cursor, 0, 8, h->stream));
+    LAUNCH(k_collect<W>, blocks_for(h->n_slots), DBG_BLOCK, h->stream, ptr<const Slot<W>>(h->b_table), h->n_slots,
+           ptr<const u8>(h->b_flags), want, ptr<u64>(h->b_tag), ptr<u32>(h->b_slot), cursor);
+    CKK();
+    return sort_by_tag(h, expect, ptr<u32>(out));
+}
+
+template <int W>
+static int tip_prune(dbg_t *h) {
+    // debruijn.py:241-254.  Device: every candidate path of every branch node (k_tip_paths).
+    // Host: walk the branch nodes in reference order and drop candidates that run into a node an
+    // earlier branch already pulled (debruijn.py:184) -- the one order-dependent step.
+    const uint64_t nb = h->branch.size();
+    h->pulled.clear();
+    if (nb == 0) return DBG_OK;
+    TRY(reserve(h, h->b_cnt32, nb * 4));
+    TRY(reserve(h, h->b_off64, (nb + 1) * 8));
+    LAUNCH(k_tip_paths<W>, blocks_for(nb), DBG_BLOCK, h->stream, ptr<const Slot<W>>(h->b_table), h->n_slots, h->k,
+           ptr<const u8>(h->b_flags), ptr<const u16>(h->b_kept), ptr<const u32>(h->b_branch), nb, 0,
+           ptr<u32>(h->b_cnt32), (const u64 *)nullptr, (u32 *)nullptr);
+    CKK();
+    std::vector<u32> counts(nb);
+    CK(cudaMemcpyAsync(counts.data(), h->b_cnt32.p, nb * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    std::vector<u64> offs(nb + 1, 0);
+    for (uint64_t i = 0; i < nb; i++) offs[i + 1] = offs[i] + counts[i];
+    const uint64_t total = offs[nb];
+    if (total == 0) return DBG_OK;
+    TRY(reserve(h, h->b_recs, total * 6 * 4));
+    CK(cudaMemcpyAsync(h->b_off64.p, offs.data(), (nb + 1) * 8, cudaMemcpyHostToDevice, h->stream));
+    LAUNCH(k_tip_paths<W>, blocks_for(nb), DBG_BLOCK, h->stream, ptr<const Slot<W>>(h->b_table), h->n_slots, h->k,
+           ptr<const u8>(h->b_flags), ptr<const u16>(h->b_kept), ptr<const u32>(h->b_branch), nb, 1,
+           ptr<u32>(h->b_cnt32), ptr<const u64>(h->b_off64), ptr<u32>(h->b_recs));
+    CKK();
+    std::vector<u32> recs(total * 6);
+    CK(cudaMemcpyAsync(recs.data(), h->b_recs.p, total * 6 * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    std::unordered_set<u32> pulled_set;
+    std::vector<u32> fresh;
+    for (uint64_t b = 0; b < nb; b++) {
+        fresh.clear();                                  // already_pull_out is fixed while b's DFS runs
+        for (uint64_t r = offs[b]; r < offs[b + 1]; r++) {
+            const u32 *rec = &recs[r * 6];
+            const int len = (int)(rec[0] & 0xFF);
+            const u32 bm = rec[0] >> 8;
+            bool blocked = false;                       // runs into a node an EARLIER branch pulled (:184)
+            for (int j = 1; j < len && !blocked; j++) blocked = pulled_set.count(rec[1 + j]) != 0;
+            if (blocked) continue;
+            for (int j = 0; j < len; j++) {
+                const u32 v = rec[1 + j];
+                if ((bm >> j) & 1) continue;                           // `item not in branch_kmer`
+                if (std::find(fresh.begin(), fresh.end(), v) == fresh.end()) fresh.push_back(v);
+            }
+        }
+        for (u32 v : fresh) { pulled_set.insert(v); h->pulled.push_back(v); }
+    }
+    const uint64_t np = h->pulled.size();
+    if (np) {
+        TRY(reserve(h, h->b_pulled, np * 4));
+        CK(cudaMemcpyAsync(h->b_pulled.p, h->pulled.data(), np * 4, cudaMemcpyHostToDevice, h->stream));
+        LAUNCH(k_mark_pulled, blocks_for(np), DBG_BLOCK, h->stream, ptr<const u32>(h->b_pulled), np,
+               ptr<u8>(h->b_flags));
+        CKK();
+        CK(cudaStreamSynchronize(h->stream));          // h->pulled is host memory of this handle; keep it simple
+    }
+    return DBG_OK;
+}
+
+template <int W>
+static int build_impl(dbg_t *h, const u8 *d_bases, const u64 *d_off) {
+    typedef Slot<W> S;
+    const int k = h->k;
+    dbg_stats_t &st = h->st;
+    DevCounters *d_ctr = ptr<DevCounters>(h->b_ctr);
+    const int e0 = ev_mark(h);
+
+    // ---- read packing (kernel 1) ----
+    h->n_words = cdiv(h->n_bases, 32);
+    TRY(reserve(h, h->b_packed, (h->n_words + 4) * 8));
+    CK(cudaMemsetAsync(ptr<u64>(h->b_packed) + h->n_words, 0, 4 * 8, h->stream));
+    h->n_tiles = cdiv(h->n_bases, DBG_TILE);
+    TRY(reserve(h, h->b_tile, (h->n_tiles + 2) * 4));
+    if (h->n_bases) {
+        LAUNCH(k_pack, blocks_for(h->n_words), DBG_BLOCK, h->stream, d_bases, h->n_bases, ptr<u64>(h->b_packed),
+               h->n_words, (int)(((uintptr_t)d_bases & 15) == 0), d_ctr);
+        CKK();
+    }
+    if (h->n_reads) {
+        LAUNCH(k_read_stats, blocks_for(h->n_reads), DBG_BLOCK, h->stream, d_off, h->n_reads, k, d_ctr);
+        CKK();
+    }
+    if (h->n_bases) {
+        LAUNCH(k_tile_first, blocks_for(h->n_tiles + 1), DBG_BLOCK, h->stream, d_off, h->n_reads, h->n_bases,
+               h->n_tiles, ptr<u32>(h->b_tile));
+        CKK();
+    }
+    const int e1 = ev_mark(h);
+
+    // ---- table sizing: HyperLogLog estimate of the distinct node count ----
+    uint64_t est = 0;
+    if (h->n_bases) {
+        TRY(reserve(h, h->b_hll, HLL_M * 4));
+        CK(cudaMemsetAsync(h->b_hll.p, 0, HLL_M * 4, h->stream));
+        LAUNCH(k_estimate<W>, h->n_tiles, DBG_BLOCK, h->stream, ptr<const u64>(h->b_packed), d_off,
+               ptr<const u32>(h->b_tile), h->n_bases, k, ptr<u32>(h->b_hll));
+        CKK();
+        std::vector<u32> regs(HLL_M);
+        CK(cudaMemcpyAsync(regs.data(), h->b_hll.p, HLL_M * 4, cudaMemcpyDeviceToHost, h->stream));
+        TRY(fetch_counters(h));
+        est = (uint64_t)hll_estimate(regs);
+    } else {
+        TRY(fetch_counters(h));
+    }
+    if (h->ctr.bad_alphabet) return fail(h, DBG_ERR_ALPHABET, "a read holds a byte other than A/C/G/T");
+    if (h->ctr.too_long) return fail(h, DBG_ERR_OVERFLOW, "a read is longer than 2^32-1 bases");
+    st.n_windows = h->ctr.n_windows;
+    st.hll_estimate = est;
+    const int e2 = ev_mark(h);
+
+    // ---- node table (kernel 3): upsert every node occurrence ----
+    const uint64_t max_nodes = st.n_windows + h->n_reads;             // every window + last k-mer per read
+    uint64_t want = (uint64_t)((double)est * 1.06) + 64;              // HLL std error at 2^12 registers: 1.6 %
+    if (want > max_nodes) want = max_nodes;
+    uint64_t n_slots = want * 2 + 1024;                               // load factor <= 0.5
+    float ms_init = 0, ms_insert = 0;
+    for (int attempt = 0;; attempt++) {
+        if (n_slots >= 0xFFFFFFF0ull) return fail(h, DBG_ERR_OVERFLOW, "node table would exceed 2^32 slots");
+        h->n_slots = n_slots;
+        TRY(reserve(h, h->b_table, n_slots * sizeof(S)));
+        const int a = ev_mark(h);
+        LAUNCH(k_table_init<W>, blocks_for(n_slots), DBG_BLOCK, h->stream, ptr<S>(h->b_table), n_slots);
+        CKK();
+        const int b = ev_mark(h);
+        if (st.n_windows) {
+            LAUNCH(k_insert<W>, h->n_tiles, DBG_BLOCK, h->stream, ptr<const u64>(h->b_packed), d_off,
+                   ptr<const u32>(h->b_tile), h->n_bases, k, ptr<S>(h->b_table), n_slots, h->read_idx_base, d_ctr);
+            CKK();
+        }
+        const int c = ev_mark(h);
+        TRY(fetch_counters(h));
+        ms_init += ev_ms(h, a, b);
+        ms_insert += ev_ms(h, b, c);
+        if (!h->ctr.overflow) break;
+        if (attempt >= 6) return fail(h, DBG_ERR_NOMEM, "node table overflowed repeatedly");
+        n_slots *= 2;                                                  // estimate was low: rebuild larger
+        CK(cudaMemsetAsync(&d_ctr->overflow, 0, 4, h->stream));
+        h->n_ev -= 3;
+    }
+    const int e3 = ev_mark(h);
+
+    // ---- degrees, pruningEdges, branch flags, successor links (kernel 4) ----
+    TRY(reserve(h, h->b_flags, n_slots));
+    TRY(reserve(h, h->b_kept, n_slots * 2));
+    TRY(reserve(h, h->b_succ, n_slots * 4));
+    LAUNCH(k_finalize<W>, blocks_for(n_slots), DBG_BLOCK, h->stream, ptr<const S>(h->b_table), n_slots, k,
+           h->threshold, ptr<u8>(h->b_flags), ptr<u16>(h->b_kept), ptr<u32>(h->b_succ), d_ctr);
+    CKK();
+    TRY(fetch_counters(h));
+    st.n_nodes = h->ctr.n_nodes;
+    st.n_edges = h->ctr.n_edges;
+    st.n_multi = h->ctr.n_multi;
+    st.n_branch = h->ctr.n_branch;
+    st.n_starts = h->ctr.n_starts;
+    if (st.n_multi && h->threshold == 0.0)
+        return fail(h, DBG_ERR_ZERODIV, "threshold == 0 with a multi-successor node (debruijn.py:163)");
+    const int e4 = ev_mark(h);
+
+    // ---- Counter.most_common tie order (debruijn.py:159-164) ----
+    if ((h->build_flags & DBG_EXACT_ORDER) && st.n_multi) {
+        const uint64_t cap = st.n_multi * 2 + 32;
+        TRY(reserve(h, h->b_order, cap * sizeof(OrderEntry)));
+        CK(cudaMemsetAsync(h->b_order.p, 0xFF, cap * sizeof(OrderEntry), h->stream));
+        LAUNCH(k_order_fill, blocks_for(n_slots), DBG_BLOCK, h->stream, ptr<const u8>(h->b_flags), n_slots,
+               ptr<OrderEntry>(h->b_order), cap);
+        CKK();
+        LAUNCH(k_order_scan<W>, h->n_tiles, DBG_BLOCK, h->stream, ptr<const u64>(h->b_packed), d_off,
+               ptr<const u32>(h->b_tile), h->n_bases, k, ptr<const S>(h->b_table), n_slots,
+               ptr<const u8>(h->b_flags), h->read_idx_base, ptr<OrderEntry>(h->b_order), cap);
+        CKK();
+        LAUNCH(k_order_apply<W>, blocks_for(cap), DBG_BLOCK, h->stream, ptr<const S>(h->b_table), n_slots, k,
+               h->threshold, ptr<const OrderEntry>(h->b_order), cap, ptr<u16>(h->b_kept), ptr<u32>(h->b_succ));
+        CKK();
+    }
+    const int e5 = ev_mark(h);
+
+    // ---- branch_kmer and starts, in first-occurrence order ----
+    TRY(collect_sorted<W>(h, F_BRANCH, st.n_branch, h->b_branch, &d_ctr->n_list_a));
+    TRY(collect_sorted<W>(h, F_START, st.n_starts, h->b_starts, &d_ctr->n_list_b));
+    h->branch.resize(st.n_branch);
+    if (st.n_branch) {
+        CK(cudaMemcpyAsync(h->branch.data(), h->b_branch.p, st.n_branch * 4, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    const int e6 = ev_mark(h);
+
+    // ---- tip pruning (debruijn.py:241-254) ----
+    TRY(tip_prune<W>(h));
+    st.n_pulled = h->pulled.size();
+    const int e7 = ev_mark(h);
+
+    // ---- pull_out_read (debruijn.py:274-283) ----
+    h->read_flags_valid = false;
+    st.n_pull_reads = 0;
+    const bool want_reads = !(h->build_flags & (DBG_FINAL | DBG_NO_PULL_READS));
+    if (want_reads) {
+        h->read_flags.assign(h->n_reads, 0);
+        if (st.n_branch && h->n_reads) {
+            TRY(reserve(h, h->b_readflags, h->n_reads));
+            CK(cudaMemsetAsync(h->b_readflags.p, 0, h->n_reads, h->stream));
+            LAUNCH(k_pull_reads<W>, h->n_tiles, DBG_BLOCK, h->stream, ptr<const u64>(h->b_packed), d_off,
+                   ptr<const u32>(h->b_tile), h->n_bases, k, ptr<const S>(h->b_table), n_slots,
+                   ptr<const u8>(h->b_flags), ptr<u8>(h->b_readflags));
+            CKK();
+            CK(cudaMemcpyAsync(h->read_flags.data(), h->b_readflags.p, h->n_reads, cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+            uint64_t n = 0;
+            for (uint8_t f : h->read_flags) n += f;
+            st.n_pull_reads = n;
+        }
+        h->read_flags_valid = true;
+    }
+    const int e8 = ev_mark(h);
+    CK(cudaStreamSynchronize(h->stream));
+
+    st.ms_pack = ev_ms(h, e0, e1);
+    st.ms_estimate = ev_ms(h, e1, e2);
+    st.ms_table_init = ms_init;
+    st.ms_insert = ms_insert;
+    st.ms_finalize = ev_ms(h, e3, e4);
+    st.ms_order = ev_ms(h, e4, e5);
+    st.ms_lists = ev_ms(h, e5, e6);
+    st.ms_tips = ev_ms(h, e6, e7);
+    st.ms_pull_reads = ev_ms(h, e7, e8);
+    st.ms_build_total = ev_ms(h, e0, e8);
+    st.table_slots = n_slots;
+    st.table_bytes = n_slots * sizeof(S);
+    return DBG_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// walk
+// -------------------------------------------------------------------------------------------------
+struct EnumFrame {
+    u32 junction_index;     // index into the branch list
+    int next_child;
+};
+
+template <int W>
+static int walk_impl(dbg_t *h, int stop_at_branch) {
+    typedef Slot<W> S;
+    dbg_stats_t &st = h->st;
+    const uint64_t n_slots = h->n_slots;
+    DevCounters *d_ctr = ptr<DevCounters>(h->b_ctr);
+    h->contigs.clear();
+    h->segments.clear();
+    st.n_contigs = 0;
+    st.n_cycle_starts = 0;
+    st.jump_rounds = 0;
+    const int e0 = ev_mark(h);
+
+    // ---- list ranking over the pruned successor array ----
+    TRY(reserve(h, h->b_link, n_slots * 8));
+    LAUNCH(k_link_init, blocks_for(n_slots), DBG_BLOCK, h->stream, ptr<const u8>(h->b_flags),
+           ptr<const u16>(h->b_kept), ptr<const u32>(h->b_succ), n_slots, ptr<u64>(h->b_link));
+    CKK();
+    int max_rounds = 2;
+    for (uint64_t n = st.n_nodes; n > 1; n >>= 1) max_rounds++;
+    for (int r = 0; r < max_rounds; r++) {
+        CK(cudaMemsetAsync(&d_ctr->changed, 0, 4, h->stream));
+        LAUNCH(k_jump, blocks_for(n_slots), DBG_BLOCK, h->stream, ptr<u64>(h->b_link), n_slots, d_ctr);
+        CKK();
+        st.jump_rounds++;
+        u32 changed = 0;
+        CK(cudaMemcpyAsync(&changed, &d_ctr->changed, 4, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        if (!changed) break;
+    }
+    const int e1 = ev_mark(h);
+
+    // ---- one record per start (debruijn.py:331-345) ----
+    const uint64_t ns = st.n_starts;
+    std::vector<ContigRec> recs(ns);
+    if (ns) {
+        TRY(reserve(h, h->b_contig, ns * sizeof(ContigRec)));
+        LAUNCH(k_emit, blocks_for(ns), DBG_BLOCK, h->stream, ptr<const u32>(h->b_starts), ns,
+               ptr<const u64>(h->b_link), ptr<const u8>(h->b_flags), ptr<ContigRec>(h->b_contig));
+        CKK();
+        CK(cudaMemcpyAsync(recs.data(), h->b_contig.p, ns * sizeof(ContigRec), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+
+    const uint64_t nb = h->branch.size();
+    const bool enumerate = !stop_at_branch && nb > 0;
+    std::vector<JunctionSucc> junc;
+    std::vector<std::pair<u32, u32>> jindex;           // (slot, index in branch list), sorted by slot
+    if (enumerate) {
+        TRY(reserve(h, h->b_junction, nb * 4 * sizeof(JunctionSucc)));
+        LAUNCH(k_junctions<W>, blocks_for(nb), DBG_BLOCK, h->stream, ptr<const S>(h->b_table), n_slots, h->k,
+               ptr<const u8>(h->b_flags), ptr<const u16>(h->b_kept), ptr<const u64>(h->b_link),
+               ptr<const u32>(h->b_branch), nb, ptr<JunctionSucc>(h->b_junction));
+        CKK();
+        junc.resize(nb * 4);
+        CK(cudaMemcpyAsync(junc.data(), h->b_junction.p, nb * 4 * sizeof(JunctionSucc), cudaMemcpyDeviceToHost,
+                           h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        jindex.resize(nb);
+        for (uint64_t i = 0; i < nb; i++) jindex[i] = std::make_pair(h->branch[i], (u32)i);
+        std::sort(jindex.begin(), jindex.end());
+    }
+    auto junction_of = [&](u32 slot) -> u32 {
+        auto it = std::lower_bound(jindex.begin(), jindex.end(), std::make_pair(slot, (u32)0));
+        return it->second;
+    };
+
+    uint64_t enum_steps = 0;
+    for (uint64_t i = 0; i < ns; i++) {
+        const ContigRec &c = recs[i];
+        if (c.kind == T_CYCLE) { st.n_cycle_starts++; continue; }      // debruijn.py:289
+        if (!(enumerate && c.kind == T_BRANCH)) {
+            if (c.n_nodes == 0) continue;                              // the start itself is pulled (:293-295)
+            dbg_contig_t d;
+            d.start = c.start; d.n_nodes = c.n_nodes; d.terminal = c.terminal; d.kind = c.kind;
+            d.seg_begin = d.seg_end = 0;
+            h->contigs.push_back(d);
+            continue;
+        }
+        // final=True: the walk continues through multi-successor nodes (debruijn.py:314), one
+        // contig per distinct root-to-stop path, paths that revisit a node emit nothing (:289).
+        const uint64_t first_contig = h->contigs.size();
+        std::vector<dbg_segment_t> segs;                               // current path as chain segments
+        std::vector<u32> on_path;                                      // junction indices on the path
+        std::vector<EnumFrame> stack;
+        uint64_t total_nodes = c.n_nodes;
+        segs.push_back(dbg_segment_t{c.start, c.n_nodes});
+        u32 j0 = junction_of(c.terminal);
+        on_path.push_back(j0);
+        stack.push_back(EnumFrame{j0, 0});
+        std::vector<uint64_t> node_stack;                              // total_nodes before each pushed segment
+        while (!stack.empty()) {
+            if (++enum_steps > MAX_ENUM_STEPS)
+                return fail(h, DBG_ERR_OVERFLOW, "final=True path enumeration exceeded %llu steps (it is "
+                            "exponential in the reference too, debruijn.py:314)", (unsigned long long)MAX_ENUM_STEPS);
+            EnumFrame &fr = stack.back();
+            const u32 jv = fr.junction_index;
+            if (fr.next_child >= 4 || junc[(uint64_t)jv * 4 + fr.next_child].entry == NONE32) {
+                stack.pop_back();
+                on_path.pop_back();
+                if (!node_stack.empty()) { total_nodes = node_stack.back(); node_stack.pop_back(); }
+                segs.pop_back();
+                continue;
+            }
+            const JunctionSucc js = junc[(uint64_t)jv * 4 + fr.next_child];
+            fr.next_child++;
+            if (js.kind == T_CYCLE) continue;
+            if (js.kind == T_BRANCH) {
+                const u32 jn = junction_of(js.terminal);
+                if (std::find(on_path.begin(), on_path.end(), jn) != on_path.end()) continue;   // revisit
+                node_stack.push_back(total_nodes);
+                segs.push_back(dbg_segment_t{js.entry, js.n_hops + 1});
+                total_nodes += js.n_hops + 1;
+                on_path.push_back(jn);
+                stack.push_back(EnumFrame{jn, 0});
+                continue;
+            }
+            // the path stops: at a dead end (terminal included) or in front of a pulled node
+            const u32 add = js.kind == T_PULLED ? js.n_hops : js.n_hops + 1;
+            dbg_contig_t d;
+            d.start = c.start; d.terminal = js.terminal; d.kind = js.kind;
+            d.n_nodes = (u32)(total_nodes + add);
+            // per-start dedup of identical paths (debruijn.py:297): only paths that stop directly in
+            // front of pulled successors of the same junction can coincide
+            bool dup = false;
+            if (add == 0) {
+                for (uint64_t q = first_contig; q < h->contigs.size() && !dup; q++) {
+                    const dbg_contig_t &o = h->contigs[q];
+                    if (o.n_nodes != d.n_nodes || o.seg_end - o.seg_begin != segs.size()) continue;
+                    bool same = true;
+                    for (size_t s = 0; s < segs.size() && same; s++)
+                        same = h->segments[o.seg_begin + s].entry == segs[s].entry &&
+                               h->segments[o.seg_begin + s].n_nodes == segs[s].n_nodes;
+                    dup = same;
+                }
+            }
+            if (dup) continue;
+            d.seg_begin = h->segments.size();
+            for (const dbg_segment_t &s : segs) h->segments.push_back(s);
+            if (add) h->segments.push_back(dbg_segment_t{js.entry, add});
+            d.seg_end = h->segments.size();
+            h->contigs.push_back(d);
+            if (h->contigs.size() > MAX_ENUM_CONTIGS)
+                return fail(h, DBG_ERR_OVERFLOW, "final=True path enumeration exceeded %llu contigs",
+                            (unsigned long long)MAX_ENUM_CONTIGS);
+        }
+    }
+    st.n_contigs = h->contigs.size();
+    const int e2 = ev_mark(h);
+    CK(cudaStreamSynchronize(h->stream));
+    st.ms_walk_rank = ev_ms(h, e0, e1);
+    st.ms_walk_emit = ev_ms(h, e1, e2);
+    st.ms_walk_total = ev_ms(h, e0, e2);
+    return DBG_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// C ABI
+// -------------------------------------------------------------------------------------------------
+#define DISPATCH(fn, ...) (h->W == 1 ? fn<1>(__VA_ARGS__) : fn<2>(__VA_ARGS__))
+
+#define DBG_API extern "C" __attribute__((visibility("default")))
+
+DBG_API int dbg_version(void) { return DBG_ABI_VERSION; }
+
+DBG_API const char *dbg_last_error(const dbg_t *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+DBG_API int dbg_create(dbg_t **out, int device, int k) {
+    dbg_t *h = nullptr;
+    if (!out) return fail(nullptr, DBG_ERR_ARG, "dbg_create: out is NULL");
+    *out = nullptr;
+    if (k < 1 || k > 63) return fail(nullptr, DBG_ERR_ARG, "k = %d out of range (1..63)", k);
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0)
+        return fail(nullptr, DBG_ERR_CUDA, "no CUDA device: %s (this library has no CPU path)",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0 || device >= n_dev) return fail(nullptr, DBG_ERR_ARG, "device %d out of range (0..%d)", device, n_dev - 1);
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) return fail(nullptr, DBG_ERR_CUDA, "cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
+    h = new dbg_handle();
+    h->device = device;
+    h->k = k;
+    h->W = k <= 31 ? 1 : 2;
+    memset(&h->st, 0, sizeof h->st);
+    memset(&h->ctr, 0, sizeof h->ctr);
+    h->st.key_words = (uint32_t)h->W;
+    e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete h; return fail(nullptr, DBG_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+    h->stream = h->own_stream;
+    for (int i = 0; i < EV_MAX; i++) cudaEventCreate(&h->ev[i]);
+    if (reserve(h, h->b_ctr, sizeof(DevCounters)) != DBG_OK) {
+        g_create_error = h->err;
+        dbg_destroy(h);
+        return DBG_ERR_NOMEM;
+    }
+    *out = h;
+    return DBG_OK;
+}
+
+DBG_API void dbg_destroy(dbg_t *h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    DevBuf *all[] = {&h->b_bases, &h->b_off, &h->b_packed, &h->b_tile, &h->b_table, &h->b_flags, &h->b_kept,
+                     &h->b_succ, &h->b_link, &h->b_ctr, &h->b_hll, &h->b_order, &h->b_tag, &h->b_tag2, &h->b_slot,
+                     &h->b_slot2, &h->b_sorttmp, &h->b_branch, &h->b_starts, &h->b_pulled, &h->b_readflags,
+                     &h->b_recs, &h->b_cnt32, &h->b_off64, &h->b_contig, &h->b_junction, &h->b_scratch[0],
+                     &h->b_scratch[1], &h->b_scratch[2], &h->b_scratch[3], &h->b_scratch[4], &h->b_scratch[5]};
+    for (DevBuf *b : all) if (b->p) cudaFree(b->p);
+    for (int i = 0; i < EV_MAX; i++) cudaEventDestroy(h->ev[i]);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+}
+
+DBG_API int dbg_set_stream(dbg_t *h, void *cuda_stream) {
+    if (!h) return DBG_ERR_ARG;
+    h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+    return DBG_OK;
+}
+
+DBG_API int dbg_build_device(dbg_t *h, const uint8_t *d_bases, const uint64_t *d_read_off, uint64_t n_reads,
+                     uint64_t n_bases, uint64_t read_idx_base, double threshold, uint32_t flags) {
+    if (!h) return DBG_ERR_ARG;
+    if ((n_bases && !d_bases) || !d_read_off) return fail(h, DBG_ERR_ARG, "dbg_build_device: NULL input");
+    if (n_reads + read_idx_base >= 0xFFFFFFFFull)
+        return fail(h, DBG_ERR_OVERFLOW, "read index exceeds 32 bits");
+    if (threshold != threshold) return fail(h, DBG_ERR_ARG, "threshold is NaN");
+    CK(cudaSetDevice(h->device));
+    h->built = h->walked = false;
+    h->n_ev = 0;
+    h->n_reads = n_reads;
+    h->n_bases = n_bases;
+    h->read_idx_base = read_idx_base;
+    h->threshold = threshold;
+    h->build_flags = flags;
+    h->d_off = d_read_off;
+    memset(&h->st, 0, sizeof h->st);
+    h->st.ms_h2d = h->pending_h2d;
+    h->pending_h2d = 0;
+    h->st.key_words = (uint32_t)h->W;
+    h->st.n_reads = n_reads;
+    h->st.n_bases = n_bases;
+    h->contigs.clear();
+    h->segments.clear();
+    CK(cudaMemsetAsync(h->b_ctr.p, 0, sizeof(DevCounters), h->stream));
+    TRY(DISPATCH(build_impl, h, (const u8 *)d_bases, (const u64 *)d_read_off));
+    h->built = true;
+    return DBG_OK;
+}
+
+DBG_API int dbg_build(dbg_t *h, const uint8_t *bases, const uint64_t *read_off, uint64_t n_reads,
+              uint64_t read_idx_base, double threshold, uint32_t flags) {
+    if (!h) return DBG_ERR_ARG;
+    if (!read_off) return fail(h, DBG_ERR_ARG, "dbg_build: read_off is NULL");
+    const uint64_t n_bases = read_off[n_reads];
+    if (n_bases && !bases) return fail(h, DBG_ERR_ARG, "dbg_build: bases is NULL");
+    CK(cudaSetDevice(h->device));
+    h->n_ev = 0;
+    TRY(reserve(h, h->b_bases, n_bases + 32));
+    TRY(reserve(h, h->b_off, (n_reads + 1) * 8));
+    const int a = ev_mark(h);
+    if (n_bases) CK(cudaMemcpyAsync(h->b_bases.p, bases, n_bases, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->b_off.p, read_off, (n_reads + 1) * 8, cudaMemcpyHostToDevice, h->stream));
+    const int b = ev_mark(h);
+    CK(cudaStreamSynchronize(h->stream));
+    h->pending_h2d = ev_ms(h, a, b);
+    return dbg_build_device(h, ptr<const uint8_t>(h->b_bases), ptr<const uint64_t>(h->b_off), n_reads, n_bases,
+                            read_idx_base, threshold, flags);
+}
+
+DBG_API int dbg_stats(dbg_t *h, dbg_stats_t *out) {
+    if (!h || !out) return DBG_ERR_ARG;
+    *out = h->st;
+    return DBG_OK;
+}
+
+#define NEED_BUILT() do { if (!h) return DBG_ERR_ARG; if (!h->built) return fail(h, DBG_ERR_STATE, "%s before a successful dbg_build", __func__); } while (0)
+
+template <int W>
+static int export_impl(dbg_t *h, uint32_t *node_id, uint64_t *key_lo, uint64_t *key_hi, uint64_t *first_tag,
+                       uint32_t *succ_cnt, uint8_t *flags, uint16_t *kept) {
+    const uint64_t n = h->st.n_nodes;
+    if (n == 0) return DBG_OK;
+    DevBuf *s = h->b_scratch;
+    TRY(reserve(h, s[0], n * 4));
+    TRY(reserve(h, s[1], n * 8));
+    TRY(reserve(h, s[2], n * 8));
+    TRY(reserve(h, s[3], n * 8));
+    TRY(reserve(h, s[4], n * 16));
+    TRY(reserve(h, s[5], n * 4));        // flags (n bytes) then kept (2n bytes) at offset n rounded to 2
+    u8 *d_flags = ptr<u8>(s[5]);
+    u16 *d_kept = (u16 *)(ptr<u8>(s[5]) + ((n + 1) & ~1ull));
+    DevCounters *d_ctr = ptr<DevCounters>(h->b_ctr);
+    CK(cudaMemsetAsync(&d_ctr->n_list_a, 0, 8, h->stream));
+    LAUNCH(k_export<W>, blocks_for(h->n_slots), DBG_BLOCK, h->stream, ptr<const Slot<W>>(h->b_table), h->n_slots,
+           ptr<const u8>(h->b_flags), ptr<const u16>(h->b_kept), &d_ctr->n_list_a, ptr<u32>(s[0]), ptr<u64>(s[1]),
+           ptr<u64>(s[2]), ptr<u64>(s[3]), ptr<u32>(s[4]), d_flags, d_kept);
+    CKK();
+    if (node_id) CK(cudaMemcpyAsync(node_id, s[0].p, n * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (key_lo) CK(cudaMemcpyAsync(key_lo, s[1].p, n * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (key_hi) CK(cudaMemcpyAsync(key_hi, s[2].p, n * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (first_tag) CK(cudaMemcpyAsync(first_tag, s[3].p, n * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (succ_cnt) CK(cudaMemcpyAsync(succ_cnt, s[4].p, n * 16, cudaMemcpyDeviceToHost, h->stream));
+    if (flags) CK(cudaMemcpyAsync(flags, d_flags, n, cudaMemcpyDeviceToHost, h->stream));
+    if (kept) CK(cudaMemcpyAsync(kept, d_kept, n * 2, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return DBG_OK;
+}
+
+DBG_API int dbg_export_nodes(dbg_t *h, uint32_t *node_id, uint64_t *key_lo, uint64_t *key_hi, uint64_t *first_tag,
+                     uint32_t *succ_cnt, uint8_t *flags, uint16_t *kept) {
+    NEED_BUILT();
+    CK(cudaSetDevice(h->device));
+    return DISPATCH(export_impl, h, node_id, key_lo, key_hi, first_tag, succ_cnt, flags, kept);
+}
+
+DBG_API int dbg_branch_nodes(dbg_t *h, uint32_t *node_id) {
+    NEED_BUILT();
+    if (h->branch.size() && !node_id) return fail(h, DBG_ERR_ARG, "NULL output");
+    if (h->branch.size()) memcpy(node_id, h->branch.data(), h->branch.size() * 4);
+    return DBG_OK;
+}
+
+DBG_API int dbg_pulled_nodes(dbg_t *h, uint32_t *node_id) {
+    NEED_BUILT();
+    if (h->pulled.size() && !node_id) return fail(h, DBG_ERR_ARG, "NULL output");
+    if (h->pulled.size()) memcpy(node_id, h->pulled.data(), h->pulled.size() * 4);
+    return DBG_OK;
+}
+
+DBG_API int dbg_pull_reads(dbg_t *h, uint8_t *read_flags) {
+    NEED_BUILT();
+    if (h->n_reads && !read_flags) return fail(h, DBG_ERR_ARG, "NULL output");
+    if (!h->read_flags_valid) {                         // DBG_FINAL / DBG_NO_PULL_READS: the list is empty
+        memset(read_flags, 0, h->n_reads);
+        return DBG_OK;
+    }
+    if (h->n_reads) memcpy(read_flags, h->read_flags.data(), h->n_reads);
+    return DBG_OK;
+}
+
+template <int W>
+static int node_keys_impl(dbg_t *h, const uint32_t *node_id, uint64_t n, uint64_t *key_lo, uint64_t *key_hi) {
+    DevBuf *s = h->b_scratch;
+    TRY(reserve(h, s[0], n * 4));
+    TRY(reserve(h, s[1], n * 8));
+    TRY(reserve(h, s[2], n * 8));
+    CK(cudaMemcpyAsync(s[0].p, node_id, n * 4, cudaMemcpyHostToDevice, h->stream));
+    LAUNCH(k_gather_keys<W>, blocks_for(n), DBG_BLOCK, h->stream, ptr<const Slot<W>>(h->b_table), ptr<const u32>(s[0]),
+           n, ptr<u64>(s[1]), ptr<u64>(s[2]));
+    CKK();
+    if (key_lo) CK(cudaMemcpyAsync(key_lo, s[1].p, n * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (key_hi) CK(cudaMemcpyAsync(key_hi, s[2].p, n * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return DBG_OK;
+}
+
+DBG_API int dbg_node_keys(dbg_t *h, const uint32_t *node_id, uint64_t n, uint64_t *key_lo, uint64_t *key_hi) {
+    NEED_BUILT();
+    if (n == 0) return DBG_OK;
+    if (!node_id) return fail(h, DBG_ERR_ARG, "NULL input");
+    for (uint64_t i = 0; i < n; i++)
+        if (node_id[i] >= h->n_slots) return fail(h, DBG_ERR_ARG, "node id %u out of range", node_id[i]);
+    CK(cudaSetDevice(h->device));
+    return DISPATCH(node_keys_impl, h, node_id, n, key_lo, key_hi);
+}
+
+template <int W>
+static int lookup_impl(dbg_t *h, const uint8_t *q, uint64_t n, uint32_t *counts) {
+    DevBuf *s = h->b_scratch;
+    const uint64_t bytes = n * (uint64_t)(h->k + 1);
+    TRY(reserve(h, s[0], bytes));
+    TRY(reserve(h, s[1], n * 4));
+    CK(cudaMemcpyAsync(s[0].p, q, bytes, cudaMemcpyHostToDevice, h->stream));
+    LAUNCH(k_lookup_edges<W>, blocks_for(n), DBG_BLOCK, h->stream, ptr<const Slot<W>>(h->b_table), h->n_slots, h->k,
+           ptr<const u8>(s[0]), n, ptr<u32>(s[1]));
+    CKK();
+    CK(cudaMemcpyAsync(counts, s[1].p, n * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return DBG_OK;
+}
+
+DBG_API int dbg_lookup_edges(dbg_t *h, const uint8_t *kplus1mers, uint64_t n, uint32_t *counts) {
+    NEED_BUILT();
+    if (n == 0) return DBG_OK;
+    if (!kplus1mers || !counts) return fail(h, DBG_ERR_ARG, "NULL argument");
+    CK(cudaSetDevice(h->device));
+    return DISPATCH(lookup_impl, h, kplus1mers, n, counts);
+}
+
+DBG_API int dbg_walk(dbg_t *h, int stop_at_branch, uint64_t *n_contigs) {
+    NEED_BUILT();
+    CK(cudaSetDevice(h->device));
+    h->walked = false;
+    h->n_ev = 0;
+    TRY(DISPATCH(walk_impl, h, stop_at_branch));
+    h->walked = true;
+    if (n_contigs) *n_contigs = h->contigs.size();
+    return DBG_OK;
+}
+
+#define NEED_WALKED() do { if (!h) return DBG_ERR_ARG; if (!h->walked) return fail(h, DBG_ERR_STATE, "%s before a successful dbg_walk", __func__); } while (0)
+
+DBG_API int dbg_contigs(dbg_t *h, dbg_contig_t *out) {
+    NEED_WALKED();
+    if (h->contigs.size() && !out) return fail(h, DBG_ERR_ARG, "NULL output");
+    if (h->contigs.size()) memcpy(out, h->contigs.data(), h->contigs.size() * sizeof(dbg_contig_t));
+    return DBG_OK;
+}
+
+DBG_API int dbg_segments(dbg_t *h, dbg_segment_t *out, uint64_t *n_segments) {
+    NEED_WALKED();
+    if (n_segments) *n_segments = h->segments.size();
+    if (out && h->segments.size()) memcpy(out, h->segments.data(), h->segments.size() * sizeof(dbg_segment_t));
+    return DBG_OK;
+}
+
+// segment list of contig c: its own segments, or the single chain (start, n_nodes)
+static void contig_segments(const dbg_t *h, const dbg_contig_t &c, std::vector<dbg_segment_t> &out) {
+    if (c.seg_end > c.seg_begin)
+        for (uint64_t s = c.seg_begin; s < c.seg_end; s++) out.push_back(h->segments[s]);
+    else
+        out.push_back(dbg_segment_t{c.start, c.n_nodes});
+}
+
+template <int W>
+static int materialize_impl(dbg_t *h, const uint64_t *idx, uint64_t n, char *buf, const uint64_t *off) {
+    std::vector<SegJob> jobs;
+    std::vector<dbg_segment_t> segs;
+    uint64_t total = 0;
+    for (uint64_t i = 0; i < n; i++) {
+        const dbg_contig_t &c = h->contigs[idx[i]];
+        segs.clear();
+        contig_segments(h, c, segs);
+        uint64_t o = off[i];
+        bool first = true;
+        for (const dbg_segment_t &s : segs) {
+            if (s.n_nodes == 0) continue;
+            SegJob j;
+            j.entry = s.entry; j.n_nodes = s.n_nodes; j.out = o; j.first = first ? 1u : 0u; j.pad = 0;
+            jobs.push_back(j);
+            o += first ? (uint64_t)h->k + s.n_nodes - 1 : s.n_nodes;
+            first = false;
+        }
+        total = std::max(total, o);
+    }
+    if (jobs.empty()) return DBG_OK;
+    DevBuf *s = h->b_scratch;
+    TRY(reserve(h, s[0], jobs.size() * sizeof(SegJob)));
+    TRY(reserve(h, s[1], total));
+    CK(cudaMemcpyAsync(s[0].p, jobs.data(), jobs.size() * sizeof(SegJob), cudaMemcpyHostToDevice, h->stream));
+    LAUNCH(k_materialize<W>, blocks_for(jobs.size()), DBG_BLOCK, h->stream, ptr<const Slot<W>>(h->b_table), h->k,
+           ptr<const u32>(h->b_succ), ptr<const SegJob>(s[0]), (u64)jobs.size(), ptr<char>(s[1]));
+    CKK();
+    // strings may be requested with gaps between them: copy each back to where the caller wants it
+    uint64_t lo = off[0], hi = 0;
+    for (uint64_t i = 0; i < n; i++) { lo = std::min(lo, off[i]); }
+    hi = total;
+    CK(cudaMemcpyAsync(buf + lo, ptr<char>(s[1]) + lo, hi - lo, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return DBG_OK;
+}
+
+DBG_API int dbg_materialize(dbg_t *h, const uint64_t *idx, uint64_t n, char *buf, const uint64_t *off) {
+    NEED_WALKED();
+    if (n == 0) return DBG_OK;
+    if (!idx || !buf || !off) return fail(h, DBG_ERR_ARG, "NULL argument");
+    for (uint64_t i = 0; i < n; i++)
+        if (idx[i] >= h->contigs.size()) return fail(h, DBG_ERR_ARG, "contig index out of range");
+    CK(cudaSetDevice(h->device));
+    return DISPATCH(materialize_impl, h, idx, n, buf, off);
+}
+
+template <int W>
+static int scores_impl(dbg_t *h, const uint64_t *idx, uint64_t n, uint64_t *scores) {
+    std::vector<u32> entry, nodes;
+    std::vector<ScoreJob> jobs(n);
+    std::vector<dbg_segment_t> segs;
+    for (uint64_t i = 0; i < n; i++) {
+        segs.clear();
+        contig_segments(h, h->contigs[idx[i]], segs);
+        jobs[i].seg_begin = entry.size();
+        for (const dbg_segment_t &s : segs) { entry.push_back(s.entry); nodes.push_back(s.n_nodes); }
+        jobs[i].seg_end = entry.size();
+    }
+    DevBuf *s = h->b_scratch;
+    TRY(reserve(h, s[0], entry.size() * 4));
+    TRY(reserve(h, s[1], nodes.size() * 4));
+    TRY(reserve(h, s[2], n * sizeof(ScoreJob)));
+    TRY(reserve(h, s[3], n * 8));
+    CK(cudaMemcpyAsync(s[0].p, entry.data(), entry.size() * 4, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(s[1].p, nodes.data(), nodes.size() * 4, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(s[2].p, jobs.data(), n * sizeof(ScoreJob), cudaMemcpyHostToDevice, h->stream));
+    LAUNCH(k_scores<W>, blocks_for(n), DBG_BLOCK, h->stream, ptr<const Slot<W>>(h->b_table), ptr<const u32>(h->b_succ),
+           ptr<const u32>(s[0]), ptr<const u32>(s[1]), ptr<const ScoreJob>(s[2]), n, ptr<u64>(s[3]));
+    CKK();
+    CK(cudaMemcpyAsync(scores, s[3].p, n * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return DBG_OK;
+}
+
+DBG_API int dbg_contig_scores(dbg_t *h, const uint64_t *idx, uint64_t n, uint64_t *scores) {
+    NEED_WALKED();
+    if (n == 0) return DBG_OK;
+    if (!idx || !scores) return fail(h, DBG_ERR_ARG, "NULL argument");
+    for (uint64_t i = 0; i < n; i++)
+        if (idx[i] >= h->contigs.size()) return fail(h, DBG_ERR_ARG, "contig index out of range");
+    CK(cudaSetDevice(h->device));
+    return DISPATCH(scores_impl, h, idx, n, scores);
+}
+

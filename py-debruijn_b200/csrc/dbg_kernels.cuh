@@ -1,0 +1,636 @@
+// dbg_kernels.cuh -- device kernels of the assembly hot path (sm_100a).
+//
+// Stage map (reference file:line -> kernel):
+//   read packing                       (new: 2-bit stream)          k_pack
+//   window loop   debruijn.py:123-144  (nodes, successor counts)    k_insert  (+ k_estimate sizing)
+//   degrees/prune debruijn.py:129-143, 150-166, 230-236             k_finalize
+//   tie order     debruijn.py:159-164  (Counter.most_common)        k_order_fill/scan/apply
+//   tip pruning   debruijn.py:169-186  (candidate paths)            k_tip_paths
+//   pull-out      debruijn.py:274-278                                k_pull_reads
+//   contig walk   debruijn.py:288-316, 326-347                      k_link_init, k_jump, k_emit
+//   strings       debruijn.py:298-300                                k_materialize
+//   getScore      II_assembleFromReads.py:14-18                      k_scores, k_lookup_edges
+#pragma once
+#include "dbg_common.cuh"
+
+#define DBG_BLOCK 256
+#define DBG_WPT 8                          // consecutive windows per thread
+#define DBG_TILE (DBG_BLOCK * DBG_WPT)     // base positions per block
+#define HLL_P 12
+#define HLL_M (1 << HLL_P)
+
+// internal terminal kinds (0..2 are the public DBG_TERM_*)
+#define T_DEADEND 0u
+#define T_BRANCH 1u
+#define T_PULLED 2u
+#define T_CYCLE 3u
+
+struct DevCounters {
+    u64 n_windows;
+    u64 n_nodes;
+    u64 n_edges;
+    u64 n_multi;
+    u64 n_branch;
+    u64 n_starts;
+    u64 n_list_a;       // append cursors for k_collect
+    u64 n_list_b;
+    u32 bad_alphabet;
+    u32 overflow;       // table full
+    u32 too_long;       // read longer than 2^32-1
+    u32 changed;        // pointer jumping made progress
+};
+
+// ---------------------------------------------------------------------------------------------
+// k_pack: ASCII -> 2-bit, 32 bases per u64 word, 128-bit loads (2 x uint4 per thread).
+// A=0 C=1 G=2 T=3 via ((c>>1)&3) ^ ((c>>2)&1); every byte is checked against "ACGT"[code].
+// ---------------------------------------------------------------------------------------------
+DBG_D u32 pack4(u32 x, bool &bad) {
+    u32 t = ((x >> 1) & 0x03030303u) ^ ((x >> 2) & 0x01010101u);
+    u32 sel = (t & 3u) | (((t >> 8) & 3u) << 4) | (((t >> 16) & 3u) << 8) | (((t >> 24) & 3u) << 12);
+    bad |= (__byte_perm(0x54474341u, 0u, sel) != x);
+    return ((t & 3u) << 6) | (((t >> 8) & 3u) << 4) | (((t >> 16) & 3u) << 2) | ((t >> 24) & 3u);
+}
+DBG_D u32 pack16(uint4 v, bool &bad) {
+    return (pack4(v.x, bad) << 24) | (pack4(v.y, bad) << 16) | (pack4(v.z, bad) << 8) | pack4(v.w, bad);
+}
+
+__global__ void __launch_bounds__(DBG_BLOCK) k_pack(const u8 *__restrict__ bases, u64 n_bases,
+                                                    u64 *__restrict__ packed, u64 n_words,
+                                                    int aligned16, DevCounters *ctr) {
+    u64 w = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_words) return;
+    u64 b0 = w * 32;
+    u64 word = 0;
+    bool bad = false;
+    if (aligned16 && b0 + 32 <= n_bases) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(bases + b0);
+        uint4 a = __ldg(src), b = __ldg(src + 1);
+        word = ((u64)pack16(a, bad) << 32) | pack16(b, bad);
+    } else {
+        for (int j = 0; j < 32; j++) {
+            u64 i = b0 + j;
+            u32 code = 0;
+            if (i < n_bases) {
+                u32 c = bases[i];
+                code = ((c >> 1) & 3u) ^ ((c >> 2) & 1u);
+                bad |= (c != ((0x54474341u >> (8 * code)) & 0xFFu));
+            }
+            word = (word << 2) | code;
+        }
+    }
+    packed[w] = word;
+    if (bad) ctr->bad_alphabet = 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_read_stats: n_windows = sum(max(0, len - k)) and the 32-bit position guard.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(DBG_BLOCK) k_read_stats(const u64 *__restrict__ off, u64 n_reads, int k,
+                                                          DevCounters *ctr) {
+    u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    u64 win = 0;
+    bool too_long = false;
+    if (r < n_reads) {
+        u64 len = __ldg(off + r + 1) - __ldg(off + r);
+        if (len > (u64)k) win = len - k;
+        too_long = len > 0xFFFFFFFFULL;
+    }
+    for (int d = 16; d > 0; d >>= 1) win += __shfl_down_sync(0xFFFFFFFFu, win, d);
+    if ((threadIdx.x & 31) == 0 && win) atomicAdd(&ctr->n_windows, win);
+    if (too_long) ctr->too_long = 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_tile_first: tile t covers base positions [t*TILE, (t+1)*TILE); first[t] = index of the read
+// holding its first position (last r with off[r] <= p).  n_tiles + 1 entries.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(DBG_BLOCK) k_tile_first(const u64 *__restrict__ off, u64 n_reads, u64 n_bases,
+                                                          u64 n_tiles, u32 *__restrict__ first) {
+    u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > n_tiles) return;
+    u64 p = t * DBG_TILE;
+    if (p > n_bases - 1) p = n_bases - 1;
+    u64 lo = 0, hi = n_reads - 1;
+    while (lo < hi) {
+        u64 mid = (lo + hi + 1) >> 1;
+        if (__ldg(off + mid) <= p) lo = mid; else hi = mid - 1;
+    }
+    first[t] = (u32)lo;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Window iteration.  Each thread owns DBG_WPT consecutive base positions of the concatenated
+// read stream and rolls the key along them (key = (key << 2 | next) & mask).  For every
+// position that is a node occurrence of its read it calls f(key, read, pos, has_next, next):
+//   BUILD  : reads longer than k, pos <= len - k            (debruijn.py:126-128)
+//   !BUILD : reads of length >= k (substring test of pull_out_read, debruijn.py:274-278)
+// has_next is false only for the last k-mer of a read (a node occurrence without an edge).
+// ---------------------------------------------------------------------------------------------
+template <int W, bool BUILD, typename F>
+DBG_D void for_windows(const u64 *__restrict__ packed, const u64 *__restrict__ off,
+                       const u32 *__restrict__ tile_first, u64 n_bases, int k, F f) {
+    typedef typename KeyOf<W>::type K;
+    u64 tile = blockIdx.x;
+    u64 p0 = tile * DBG_TILE + (u64)threadIdx.x * DBG_WPT;
+    if (p0 >= n_bases) return;
+    u32 rlo = __ldg(tile_first + tile), rhi = __ldg(tile_first + tile + 1);
+    while (rlo < rhi) {
+        u32 mid = rlo + ((rhi - rlo + 1) >> 1);
+        if (__ldg(off + mid) <= p0) rlo = mid; else rhi = mid - 1;
+    }
+    u32 r = rlo;
+    u64 rs = __ldg(off + r), re = __ldg(off + r + 1);
+    const K mask = key_mask<W>(k);
+    K key = extract_key<W>(packed, p0, k);
+#pragma unroll
+    for (int j = 0; j < DBG_WPT; j++) {
+        u64 p = p0 + j;
+        if (p >= n_bases) break;
+        while (p >= re) { r++; rs = re; re = __ldg(off + r + 1); }      // also skips empty reads
+        u64 len = re - rs, pos = p - rs;
+        u32 nb = base_at(packed, p + k);
+        bool ok = BUILD ? (len > (u64)k && pos + k <= len) : (pos + k <= len);
+        if (ok) f(key, r, pos, pos + k < len, nb);
+        key = ((key << 2) | (K)nb) & mask;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_estimate: HyperLogLog over node keys (2^12 registers) -> distinct-node estimate that sizes
+// the table.  Registers saturate after a few thousand keys, so almost every window is a plain
+// load and no atomic.
+// ---------------------------------------------------------------------------------------------
+template <int W>
+__global__ void __launch_bounds__(DBG_BLOCK) k_estimate(const u64 *__restrict__ packed, const u64 *__restrict__ off,
+                                                        const u32 *__restrict__ tile_first, u64 n_bases, int k,
+                                                        u32 *regs) {
+    typedef typename KeyOf<W>::type K;
+    for_windows<W, true>(packed, off, tile_first, n_bases, k,
+        [&](K key, u32, u64, bool, u32) {
+            u64 h = hash_key(key);
+            u32 idx = (u32)(h >> (64 - HLL_P));
+            u32 rank = (u32)__clzll((long long)((h << HLL_P) | (1ULL << (HLL_P - 1)))) + 1;
+            if (regs[idx] < rank) atomicMax(&regs[idx], rank);
+        });
+}
+
+// ---------------------------------------------------------------------------------------------
+// table init + insert
+// ---------------------------------------------------------------------------------------------
+template <int W>
+__global__ void __launch_bounds__(DBG_BLOCK) k_table_init(Slot<W> *table, u64 n_slots) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_slots) return;
+    Slot<W> s;
+    s.key = empty_key<W>();
+    s.tag = ~0ULL;
+    s.cnt[0] = s.cnt[1] = s.cnt[2] = s.cnt[3] = 0;
+    table[i] = s;
+}
+
+template <int W>
+__global__ void __launch_bounds__(DBG_BLOCK) k_insert(const u64 *__restrict__ packed, const u64 *__restrict__ off,
+                                                      const u32 *__restrict__ tile_first, u64 n_bases, int k,
+                                                      Slot<W> *table, u64 n_slots, u64 read_idx_base,
+                                                      DevCounters *ctr) {
+    typedef typename KeyOf<W>::type K;
+    for_windows<W, true>(packed, off, tile_first, n_bases, k,
+        [&](K key, u32 r, u64 pos, bool has_next, u32 nb) {
+            u64 idx = table_upsert<W>(table, n_slots, key);
+            if (idx == NONE64) { ctr->overflow = 1; return; }
+            Slot<W> *s = &table[idx];
+            u64 tag = ((read_idx_base + r) << 32) | pos;
+            if (tag < __ldcg(&s->tag)) atomicMin(&s->tag, tag);          // first occurrence
+            if (has_next) atomicAdd(&s->cnt[nb], 1u);                    // debruijn.py:132/136
+        });
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_finalize: per slot, degrees + pruningEdges + branch flag + the single surviving successor.
+// ---------------------------------------------------------------------------------------------
+template <int W>
+__global__ void __launch_bounds__(DBG_BLOCK) k_finalize(const Slot<W> *__restrict__ table, u64 n_slots, int k,
+                                                        double threshold, u8 *__restrict__ flags,
+                                                        u16 *__restrict__ kept, u32 *__restrict__ succ,
+                                                        DevCounters *ctr) {
+    typedef typename KeyOf<W>::type K;
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    bool occ = false;
+    u32 f = 0, word = 0, sx = NONE32;
+    if (i < n_slots) {
+        K key = table[i].key;
+        occ = key != empty_key<W>();
+        if (occ) {
+            u32 cnt[4] = { table[i].cnt[0], table[i].cnt[1], table[i].cnt[2], table[i].cnt[3] };
+            u64 tag = table[i].tag;
+            word = prune_successors(cnt, (const u64 *)0, threshold);
+            int nk = kept_count(word), m = distinct_count(word);
+            f = F_OCC | ((u32)tag == 0 ? F_START : 0) | (nk > 1 ? F_BRANCH : 0) |
+                (m == 0 ? F_DEADEND : 0) | (m > 1 ? F_MULTI : 0);
+            if (nk == 1) {
+                K sk = ((key << 2) | (K)kept_base(word, 0)) & key_mask<W>(k);
+                sx = (u32)table_find<W>(table, n_slots, sk);
+            }
+        }
+        flags[i] = (u8)f;
+        kept[i] = (u16)word;
+        succ[i] = sx;
+    }
+    u32 lane = threadIdx.x & 31;
+    u32 b_occ = __ballot_sync(0xFFFFFFFFu, occ);
+    u32 b_start = __ballot_sync(0xFFFFFFFFu, f & F_START);
+    u32 b_branch = __ballot_sync(0xFFFFFFFFu, f & F_BRANCH);
+    u32 b_multi = __ballot_sync(0xFFFFFFFFu, f & F_MULTI);
+    u32 e = (u32)distinct_count(word);
+    for (int d = 16; d > 0; d >>= 1) e += __shfl_down_sync(0xFFFFFFFFu, e, d);
+    if (lane == 0 && b_occ) {
+        atomicAdd(&ctr->n_nodes, (u64)__popc(b_occ));
+        if (e) atomicAdd(&ctr->n_edges, (u64)e);
+        if (b_start) atomicAdd(&ctr->n_starts, (u64)__popc(b_start));
+        if (b_branch) atomicAdd(&ctr->n_branch, (u64)__popc(b_branch));
+        if (b_multi) atomicAdd(&ctr->n_multi, (u64)__popc(b_multi));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Exact successor order (DBG_EXACT_ORDER): a side table keyed by slot index holds, for every
+// multi-successor node, the first-appearance tag of each successor base.
+// ---------------------------------------------------------------------------------------------
+struct OrderEntry {
+    u64 slot;          // ~0 = empty
+    u64 first[4];      // ~0 = never
+};
+
+DBG_D u64 order_locate(OrderEntry *ot, u64 cap, u64 slot, bool insert) {
+    u64 idx = mulhi64(fmix64(slot + 0x632be59bd9b4e019ULL), cap);
+    for (u64 probes = 0; probes < cap; ++probes) {
+        u64 cur = __ldcg(&ot[idx].slot);
+        if (cur == slot) return idx;
+        if (cur == ~0ULL) {
+            if (!insert) return NONE64;
+            u64 old = atomicCAS(&ot[idx].slot, ~0ULL, slot);
+            if (old == ~0ULL || old == slot) return idx;
+        }
+        if (++idx == cap) idx = 0;
+    }
+    return NONE64;
+}
+
+__global__ void __launch_bounds__(DBG_BLOCK) k_order_fill(const u8 *__restrict__ flags, u64 n_slots,
+                                                          OrderEntry *ot, u64 cap) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_slots) return;
+    if (flags[i] & F_MULTI) order_locate(ot, cap, i, true);
+}
+
+template <int W>
+__global__ void __launch_bounds__(DBG_BLOCK) k_order_scan(const u64 *__restrict__ packed, const u64 *__restrict__ off,
+                                                          const u32 *__restrict__ tile_first, u64 n_bases, int k,
+                                                          const Slot<W> *__restrict__ table, u64 n_slots,
+                                                          const u8 *__restrict__ flags, u64 read_idx_base,
+                                                          OrderEntry *ot, u64 cap) {
+    typedef typename KeyOf<W>::type K;
+    for_windows<W, true>(packed, off, tile_first, n_bases, k,
+        [&](K key, u32 r, u64 pos, bool has_next, u32 nb) {
+            if (!has_next) return;
+            u64 idx = table_find<W>(table, n_slots, key);
+            if (idx == NONE64 || !(flags[idx] & F_MULTI)) return;
+            u64 e = order_locate(ot, cap, idx, false);
+            if (e == NONE64) return;
+            u64 tag = ((read_idx_base + r) << 32) | pos;
+            if (tag < __ldcg(&ot[e].first[nb])) atomicMin(&ot[e].first[nb], tag);
+        });
+}
+
+template <int W>
+__global__ void __launch_bounds__(DBG_BLOCK) k_order_apply(const Slot<W> *__restrict__ table, u64 n_slots, int k,
+                                                           double threshold, const OrderEntry *__restrict__ ot,
+                                                           u64 cap, u16 *__restrict__ kept, u32 *__restrict__ succ) {
+    typedef typename KeyOf<W>::type K;
+    u64 e = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= cap) return;
+    u64 i = ot[e].slot;
+    if (i == ~0ULL) return;
+    u32 cnt[4] = { table[i].cnt[0], table[i].cnt[1], table[i].cnt[2], table[i].cnt[3] };
+    u64 first[4] = { ot[e].first[0], ot[e].first[1], ot[e].first[2], ot[e].first[3] };
+    u32 word = prune_successors(cnt, first, threshold);
+    kept[i] = (u16)word;
+    if (kept_count(word) == 1) {        // threshold < 1: the tie decides WHICH successor survives
+        K sk = ((table[i].key << 2) | (K)kept_base(word, 0)) & key_mask<W>(k);
+        succ[i] = (u32)table_find<W>(table, n_slots, sk);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_collect: append (tag, slot) of every slot whose flags hit `want` (starts / branch nodes).
+// ---------------------------------------------------------------------------------------------
+template <int W>
+__global__ void __launch_bounds__(DBG_BLOCK) k_collect(const Slot<W> *__restrict__ table, u64 n_slots,
+                                                       const u8 *__restrict__ flags, u32 want,
+                                                       u64 *__restrict__ out_tag, u32 *__restrict__ out_slot,
+                                                       u64 *cursor) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    bool hit = i < n_slots && (flags[i] & want);
+    u32 b = __ballot_sync(0xFFFFFFFFu, hit);
+    if (!b) return;
+    u32 lane = threadIdx.x & 31;
+    u64 base = 0;
+    if (lane == 0) base = atomicAdd(cursor, (u64)__popc(b));
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    if (hit) {
+        u64 o = base + __popc(b & ((1u << lane) - 1));
+        out_tag[o] = table[i].tag;
+        out_slot[o] = (u32)i;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_tip_paths: candidate paths of pruningErrorContigFromBranch (debruijn.py:169-186) for every
+// branch node, ignoring already_pull_out (the host applies that filter in branch order, which
+// is the only sequential part).  Record = 6 words: len | branch-bitmask << 8, then <= 5 slots.
+// mode 0 counts, mode 1 fills at offs[b].
+// ---------------------------------------------------------------------------------------------
+template <int W>
+__global__ void __launch_bounds__(DBG_BLOCK) k_tip_paths(const Slot<W> *__restrict__ table, u64 n_slots, int k,
+                                                         const u8 *__restrict__ flags, const u16 *__restrict__ kept,
+                                                         const u32 *__restrict__ branch, u64 n_branch, int mode,
+                                                         u32 *__restrict__ counts, const u64 *__restrict__ offs,
+                                                         u32 *__restrict__ recs) {
+    typedef typename KeyOf<W>::type K;
+    u64 b = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_branch) return;
+    const K mask = key_mask<W>(k);
+    u32 vec[5], word[5], child[5];
+    K keyv[5];
+    u32 n = 0;
+    vec[0] = branch[b]; word[0] = kept[vec[0]]; child[0] = 0; keyv[0] = table[vec[0]].key;
+    int depth = 1;
+    while (depth > 0) {
+        int d = depth - 1;
+        u32 ci = child[d];
+        if ((int)ci >= kept_count(word[d])) { depth--; continue; }
+        child[d] = ci + 1;
+        if (depth == 5) continue;                                   // callee would see depth == 0
+        K sk = ((keyv[d] << 2) | (K)kept_base(word[d], (int)ci)) & mask;
+        u32 nx = (u32)table_find<W>(table, n_slots, sk);
+        vec[depth] = nx;
+        u32 fl = flags[nx];
+        if (fl & F_DEADEND) {                                       // debruijn.py:173
+            if (mode == 1) {
+                u32 *rec = recs + (offs[b] + n) * 6;
+                u32 bm = 0;
+                for (int j = 0; j <= depth; j++) {
+                    rec[1 + j] = vec[j];
+                    if (flags[vec[j]] & F_BRANCH) bm |= 1u << j;
+                }
+                rec[0] = (u32)(depth + 1) | (bm << 8);
+            }
+            n++;
+            continue;
+        }
+        word[depth] = kept[nx]; child[depth] = 0; keyv[depth] = table[nx].key;
+        depth++;
+    }
+    if (mode == 0) counts[b] = n;
+}
+
+__global__ void __launch_bounds__(DBG_BLOCK) k_mark_pulled(const u32 *__restrict__ pulled, u64 n, u8 *flags) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flags[pulled[i]] |= (u8)F_PULLED;
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_pull_reads: read r is pulled out iff any of its k-mers is a branch node (debruijn.py:274-278)
+// ---------------------------------------------------------------------------------------------
+template <int W>
+__global__ void __launch_bounds__(DBG_BLOCK) k_pull_reads(const u64 *__restrict__ packed, const u64 *__restrict__ off,
+                                                          const u32 *__restrict__ tile_first, u64 n_bases, int k,
+                                                          const Slot<W> *__restrict__ table, u64 n_slots,
+                                                          const u8 *__restrict__ flags, u8 *read_flags) {
+    typedef typename KeyOf<W>::type K;
+    for_windows<W, false>(packed, off, tile_first, n_bases, k,
+        [&](K key, u32 r, u64, bool, u32) {
+            u64 idx = table_find<W>(table, n_slots, key);
+            if (idx != NONE64 && (flags[idx] & F_BRANCH)) read_flags[r] = 1;
+        });
+}
+
+// ---------------------------------------------------------------------------------------------
+// Contig walk as list ranking.  link[v] = (dist << 32 | next): next == v marks a root.  Roots
+// are the nodes at which the reference's DFS stops (debruijn.py:292, :304): pulled nodes,
+// nodes without successor, nodes with > 1 kept successor.  Every other node has exactly one
+// kept successor.  k_jump halves the remaining distance per round (pointer jumping, in place:
+// the 64-bit (next, dist) pair is read and written as one word, so any interleaving is a
+// valid earlier or later state of the same chain).  A node that still does not point at a
+// root after ceil(log2(n)) + 1 rounds sits on, or leads into, a cycle (debruijn.py:289); a
+// self-loop (AAAA -> AAAA) has next == self but dist 1, so "root" always means link == (v, 0).
+// ---------------------------------------------------------------------------------------------
+DBG_HD u64 link_pack(u32 next, u32 dist) { return ((u64)dist << 32) | next; }
+DBG_HD u32 link_next(u64 l) { return (u32)l; }
+DBG_HD u32 link_dist(u64 l) { return (u32)(l >> 32); }
+DBG_HD bool link_is_root(u64 l, u32 v) { return l == (u64)v; }
+
+__global__ void __launch_bounds__(DBG_BLOCK) k_link_init(const u8 *__restrict__ flags, const u16 *__restrict__ kept,
+                                                         const u32 *__restrict__ succ, u64 n_slots, u64 *link) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_slots) return;
+    u32 f = flags[i];
+    bool chain = (f & F_OCC) && !(f & F_PULLED) && kept_count(kept[i]) == 1;
+    link[i] = chain ? link_pack(succ[i], 1) : link_pack((u32)i, 0);
+}
+
+__global__ void __launch_bounds__(DBG_BLOCK) k_jump(u64 *link, u64 n_slots, DevCounters *ctr) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_slots) return;
+    u64 l = __ldcg(&link[i]);
+    u32 nx = link_next(l);
+    if (nx == (u32)i) return;                       // root (dist 0) or a self-loop (dist > 0)
+    u64 ln = __ldcg(&link[nx]);
+    u32 nn = link_next(ln);
+    if (nn == nx) return;                           // points at a root / self-loop: final
+    __stcg(&link[i], link_pack(nn, link_dist(l) + link_dist(ln)));
+    ctr->changed = 1;
+}
+
+struct ContigRec {          // one per start, in start order; kind T_CYCLE / n_nodes 0 = nothing emitted
+    u32 start, n_nodes, terminal, kind;
+};
+
+__global__ void __launch_bounds__(DBG_BLOCK) k_emit(const u32 *__restrict__ starts, u64 n_starts,
+                                                    const u64 *__restrict__ link, const u8 *__restrict__ flags,
+                                                    ContigRec *__restrict__ out) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_starts) return;
+    u32 s = starts[i];
+    u64 l = link[s];
+    u32 t = link_next(l), d = link_dist(l);
+    ContigRec c;
+    c.start = s; c.terminal = t;
+    if (!link_is_root(link[t], t)) { c.kind = T_CYCLE; c.n_nodes = 0; }
+    else {
+        u32 f = flags[t];
+        if (f & F_PULLED) { c.kind = T_PULLED; c.n_nodes = d; }          // path stops in front of t
+        else { c.kind = (f & F_DEADEND) ? T_DEADEND : T_BRANCH; c.n_nodes = d + 1; }
+    }
+    out[i] = c;
+}
+
+// junction table for the final=True enumeration: for every branch node and each kept successor,
+// where that successor's chain ends.
+struct JunctionSucc {
+    u32 entry, n_hops, terminal, kind;      // kind as above; n_hops = distance entry -> terminal
+};
+template <int W>
+__global__ void __launch_bounds__(DBG_BLOCK) k_junctions(const Slot<W> *__restrict__ table, u64 n_slots, int k,
+                                                         const u8 *__restrict__ flags, const u16 *__restrict__ kept,
+                                                         const u64 *__restrict__ link, const u32 *__restrict__ branch,
+                                                         u64 n_branch, JunctionSucc *__restrict__ out) {
+    typedef typename KeyOf<W>::type K;
+    u64 b = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_branch) return;
+    u32 v = branch[b];
+    u32 word = kept[v];
+    K key = table[v].key;
+    for (int j = 0; j < 4; j++) {
+        JunctionSucc js;
+        js.entry = NONE32; js.n_hops = 0; js.terminal = NONE32; js.kind = T_CYCLE;
+        if (j < kept_count(word)) {
+            K sk = ((key << 2) | (K)kept_base(word, j)) & key_mask<W>(k);
+            u32 s = (u32)table_find<W>(table, n_slots, sk);
+            u64 l = link[s];
+            u32 t = link_next(l);
+            js.entry = s; js.n_hops = link_dist(l); js.terminal = t;
+            if (!link_is_root(link[t], t)) js.kind = T_CYCLE;
+            else {
+                u32 f = flags[t];
+                js.kind = (f & F_PULLED) ? T_PULLED : (f & F_DEADEND) ? T_DEADEND : T_BRANCH;
+            }
+        }
+        out[b * 4 + j] = js;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// strings and scores: one thread per segment walks succ[] (debruijn.py:298-300: first node's
+// label, then the last base of every later node).
+// ---------------------------------------------------------------------------------------------
+struct SegJob {
+    u32 entry, n_nodes;
+    u64 out;            // offset into the char buffer
+    u32 first;          // 1 = first segment of its contig: write the whole entry label
+    u32 pad;
+};
+
+template <int W>
+__global__ void __launch_bounds__(DBG_BLOCK) k_materialize(const Slot<W> *__restrict__ table, int k,
+                                                           const u32 *__restrict__ succ,
+                                                           const SegJob *__restrict__ jobs, u64 n_jobs,
+                                                           char *__restrict__ buf) {
+    typedef typename KeyOf<W>::type K;
+    u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_jobs) return;
+    SegJob job = jobs[j];
+    if (job.n_nodes == 0) return;
+    const u32 ALPHA = 0x54474341u;
+    u32 v = job.entry;
+    char *o = buf + job.out;
+    K key = table[v].key;
+    if (job.first) {
+        for (int i = 0; i < k; i++) *o++ = (char)((ALPHA >> (8 * (u32)((key >> (2 * (k - 1 - i))) & 3))) & 0xFF);
+    } else {
+        *o++ = (char)((ALPHA >> (8 * (u32)(key & 3))) & 0xFF);
+    }
+    for (u32 i = 1; i < job.n_nodes; i++) {
+        v = succ[v];
+        *o++ = (char)((ALPHA >> (8 * (u32)(table[v].key & 3))) & 0xFF);
+    }
+}
+
+struct ScoreJob {
+    u64 seg_begin, seg_end;     // into the uploaded segment array
+};
+template <int W>
+__global__ void __launch_bounds__(DBG_BLOCK) k_scores(const Slot<W> *__restrict__ table,
+                                                      const u32 *__restrict__ succ,
+                                                      const u32 *__restrict__ seg_entry,
+                                                      const u32 *__restrict__ seg_nodes,
+                                                      const ScoreJob *__restrict__ jobs, u64 n_jobs,
+                                                      u64 *__restrict__ scores) {
+    u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_jobs) return;
+    ScoreJob job = jobs[j];
+    u64 total = 0;
+    u32 prev = NONE32;
+    for (u64 s = job.seg_begin; s < job.seg_end; s++) {
+        u32 v = seg_entry[s];
+        for (u32 i = 0; i < seg_nodes[s]; i++) {
+            if (i) v = succ[v];
+            if (prev != NONE32) total += table[prev].cnt[(u32)(table[v].key & 3)];
+            prev = v;
+        }
+    }
+    scores[j] = total;
+}
+
+template <int W>
+__global__ void __launch_bounds__(DBG_BLOCK) k_lookup_edges(const Slot<W> *__restrict__ table, u64 n_slots, int k,
+                                                            const u8 *__restrict__ q, u64 n, u32 *__restrict__ out) {
+    typedef typename KeyOf<W>::type K;
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const u8 *s = q + i * (u64)(k + 1);
+    K key = 0;
+    bool bad = false;
+    u32 code = 0;
+    for (int j = 0; j <= k; j++) {
+        u32 c = s[j];
+        code = ((c >> 1) & 3u) ^ ((c >> 2) & 1u);
+        bad |= (c != ((0x54474341u >> (8 * code)) & 0xFFu));
+        if (j < k) key = (key << 2) | (K)code;
+    }
+    u32 res = 0;
+    if (!bad) {
+        u64 idx = table_find<W>(table, n_slots, key);
+        if (idx != NONE64) res = table[idx].cnt[code];
+    }
+    out[i] = res;
+}
+
+template <int W>
+__global__ void __launch_bounds__(DBG_BLOCK) k_gather_keys(const Slot<W> *__restrict__ table,
+                                                           const u32 *__restrict__ ids, u64 n,
+                                                           u64 *__restrict__ lo, u64 *__restrict__ hi) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    typename KeyOf<W>::type key = table[ids[i]].key;
+    lo[i] = (u64)key;
+    hi[i] = W == 2 ? (u64)((u128)key >> 64) : 0;
+}
+
+// export: compact occupied slots (unordered)
+template <int W>
+__global__ void __launch_bounds__(DBG_BLOCK) k_export(const Slot<W> *__restrict__ table, u64 n_slots,
+                                                      const u8 *__restrict__ flags, const u16 *__restrict__ kept,
+                                                      u64 *cursor, u32 *__restrict__ o_id, u64 *__restrict__ o_lo,
+                                                      u64 *__restrict__ o_hi, u64 *__restrict__ o_tag,
+                                                      u32 *__restrict__ o_cnt, u8 *__restrict__ o_flags,
+                                                      u16 *__restrict__ o_kept) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    bool occ = i < n_slots && (flags[i] & F_OCC);
+    u32 b = __ballot_sync(0xFFFFFFFFu, occ);
+    if (!b) return;
+    u32 lane = threadIdx.x & 31;
+    u64 base = 0;
+    if (lane == 0) base = atomicAdd(cursor, (u64)__popc(b));
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    if (!occ) return;
+    u64 o = base + __popc(b & ((1u << lane) - 1));
+    typename KeyOf<W>::type key = table[i].key;
+    o_id[o] = (u32)i;
+    o_lo[o] = (u64)key;
+    o_hi[o] = W == 2 ? (u64)((u128)key >> 64) : 0;
+    o_tag[o] = table[i].tag;
+    for (int c = 0; c < 4; c++) o_cnt[4 * o + c] = table[i].cnt[c];
+    o_flags[o] = flags[i];
+    o_kept[o] = kept[i];
+}

@@ -1,0 +1,374 @@
+"""Host-side graph handle over the C ABI, plus the lazy Python views that stand in for the
+reference's ``vertices`` / ``edges`` / ``edge_count_table`` dicts (debruijn.py:285).
+
+Everything here is plumbing: packing ``list[str]`` into one byte buffer + offsets, calling the
+library, and decoding 2-bit keys back to strings when somebody looks.  No stage of the
+algorithm is computed in Python.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from collections.abc import Mapping
+
+import numpy as np
+
+from . import _native as N
+
+_ALPHA = np.frombuffer(b'ACGT', dtype=np.uint8)
+MAX_STRING_BYTES = 8 << 30          # refuse to materialise more contig characters than this at once
+
+
+class Node:
+    """debruijn.py:8-14."""
+
+    __slots__ = ('label', 'indegree', 'outdegree')
+
+    def __init__(self, lab):
+        self.label = lab
+        self.indegree = 0
+        self.outdegree = 0
+
+
+def pack_reads(reads):
+    """list[str] -> (uint8[n_bases] ASCII, uint64[n+1] offsets); II hands over a plain list."""
+    n = len(reads)
+    lens = np.fromiter((len(r) for r in reads), dtype=np.uint64, count=n)
+    off = np.zeros(n + 1, dtype=np.uint64)
+    np.cumsum(lens, out=off[1:])
+    try:
+        data = ''.join(reads).encode('ascii')
+    except UnicodeEncodeError as e:
+        raise ValueError('dbg_b200: only the DNA alphabet ACGT is supported on the B200 path') from e
+    bases = np.frombuffer(data, dtype=np.uint8)
+    return bases, off
+
+
+def decode_keys(key_lo, key_hi, k):
+    """2-bit keys (first base most significant) -> list[str]."""
+    n = len(key_lo)
+    if n == 0:
+        return []
+    shifts = 2 * (k - 1 - np.arange(k, dtype=np.int64))
+    lo = np.asarray(key_lo, dtype=np.uint64)[:, None]
+    codes = np.empty((n, k), dtype=np.uint8)
+    low = shifts < 64
+    codes[:, low] = ((lo >> shifts[low].astype(np.uint64)) & np.uint64(3)).astype(np.uint8)
+    if not low.all():
+        hi = np.asarray(key_hi, dtype=np.uint64)[:, None]
+        codes[:, ~low] = ((hi >> (shifts[~low] - 64).astype(np.uint64)) & np.uint64(3)).astype(np.uint8)
+    chars = _ALPHA[codes]
+    return chars.view('S%d' % k).ravel().astype('U%d' % k).tolist()
+
+
+def _default_device():
+    for var in ('DBG_B200_DEVICE', 'LOCAL_RANK'):
+        v = os.environ.get(var)
+        if v is not None and v != '':
+            return int(v)
+    return 0
+
+
+class Graph:
+    """One de Bruijn graph resident on one GPU (one ``dbg_t``).  Re-usable: ``build`` may be
+    called again with new reads and keeps its HBM."""
+
+    def __init__(self, k, device=None, lib=None):
+        self.lib = lib or N.get()
+        self.k = int(k)
+        self.device = _default_device() if device is None else int(device)
+        h = C.c_void_p()
+        rc = self.lib.dbg_create(C.byref(h), self.device, self.k)
+        if rc != N.DBG_OK:
+            msg = self.lib.dbg_last_error(None)
+            N._raise(rc, msg.decode() if msg else '')
+        self.h = h
+        self.reads = None
+        self.final = False
+        self._reset_cache()
+
+    def _reset_cache(self):
+        self._nodes = None
+        self._labels = None
+        self._contigs = None
+        self._stats = None
+
+    def close(self):
+        if getattr(self, 'h', None):
+            self.lib.dbg_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:       # noqa: BLE001 - interpreter shutdown
+            pass
+
+    # ---- construct_graph -----------------------------------------------------------------
+    def build(self, reads, threshold=3, final=False, exact_order=True, pull_reads=True,
+              packed=None, read_idx_base=0):
+        """Host entry: `reads` is a list[str] (or pass packed=(uint8 bases, uint64 offsets))."""
+        bases, off = packed if packed is not None else pack_reads(reads)
+        self.reads = reads
+        self.final = bool(final)
+        self._reset_cache()
+        flags = (N.DBG_FINAL if final else 0) | (N.DBG_EXACT_ORDER if exact_order else 0) | \
+                (0 if pull_reads else N.DBG_NO_PULL_READS)
+        self._keep = (bases, off)                      # keep the buffers alive during the call
+        self.n_reads = len(off) - 1
+        rc = self.lib.dbg_build(self.h, bases.ctypes.data if len(bases) else None, off.ctypes.data,
+                                self.n_reads, int(read_idx_base), float(threshold), flags)
+        self.lib.check(self.h, rc)
+        return self
+
+    def build_device(self, d_bases_ptr, d_off_ptr, n_reads, n_bases, threshold=3, final=False,
+                     exact_order=True, pull_reads=True, read_idx_base=0):
+        """Device entry: raw device pointers (e.g. torch tensors' data_ptr()) already in HBM."""
+        self.reads = None
+        self.final = bool(final)
+        self._reset_cache()
+        flags = (N.DBG_FINAL if final else 0) | (N.DBG_EXACT_ORDER if exact_order else 0) | \
+                (0 if pull_reads else N.DBG_NO_PULL_READS)
+        self.n_reads = int(n_reads)
+        rc = self.lib.dbg_build_device(self.h, d_bases_ptr, d_off_ptr, int(n_reads), int(n_bases),
+                                       int(read_idx_base), float(threshold), flags)
+        self.lib.check(self.h, rc)
+        return self
+
+    def set_stream(self, cuda_stream_ptr):
+        self.lib.check(self.h, self.lib.dbg_set_stream(self.h, cuda_stream_ptr))
+
+    def stats(self):
+        s = N.Stats()
+        self.lib.check(self.h, self.lib.dbg_stats(self.h, C.byref(s)))
+        return s
+
+    # ---- exports -------------------------------------------------------------------------
+    def nodes(self):
+        """Arrays of every node, sorted by first-occurrence tag (= the reference's dict order)."""
+        if self._nodes is None:
+            n = self.stats().n_nodes
+            a = {
+                'id': np.zeros(n, np.uint32), 'key_lo': np.zeros(n, np.uint64), 'key_hi': np.zeros(n, np.uint64),
+                'tag': np.zeros(n, np.uint64), 'cnt': np.zeros((n, 4), np.uint32),
+                'flags': np.zeros(n, np.uint8), 'kept': np.zeros(n, np.uint16),
+            }
+            rc = self.lib.dbg_export_nodes(self.h, *(a[f].ctypes.data for f in
+                                                     ('id', 'key_lo', 'key_hi', 'tag', 'cnt', 'flags', 'kept')))
+            self.lib.check(self.h, rc)
+            order = np.argsort(a['tag'], kind='stable')
+            self._nodes = {f: v[order] for f, v in a.items()}
+        return self._nodes
+
+    def labels(self):
+        if self._labels is None:
+            nd = self.nodes()
+            self._labels = decode_keys(nd['key_lo'], nd['key_hi'], self.k)
+        return self._labels
+
+    def label_of_ids(self, ids):
+        ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        n = len(ids)
+        lo = np.zeros(n, np.uint64)
+        hi = np.zeros(n, np.uint64)
+        if n:
+            self.lib.check(self.h, self.lib.dbg_node_keys(self.h, ids.ctypes.data, n, lo.ctypes.data, hi.ctypes.data))
+        return decode_keys(lo, hi, self.k)
+
+    def branch_ids(self):
+        n = self.stats().n_branch
+        out = np.zeros(n, np.uint32)
+        self.lib.check(self.h, self.lib.dbg_branch_nodes(self.h, out.ctypes.data if n else None))
+        return out
+
+    def pulled_ids(self):
+        n = self.stats().n_pulled
+        out = np.zeros(n, np.uint32)
+        self.lib.check(self.h, self.lib.dbg_pulled_nodes(self.h, out.ctypes.data if n else None))
+        return out
+
+    def pull_read_flags(self):
+        out = np.zeros(self.n_reads, np.uint8)
+        self.lib.check(self.h, self.lib.dbg_pull_reads(self.h, out.ctypes.data if self.n_reads else None))
+        return out
+
+    def lookup_edges(self, kplus1mers):
+        """edge_count_table values for a list of (k+1)-mer strings; 0 = absent."""
+        n = len(kplus1mers)
+        out = np.zeros(n, np.uint32)
+        if n == 0:
+            return out
+        buf = ''.join(kplus1mers).encode('ascii', 'replace')
+        if len(buf) != n * (self.k + 1):
+            raise ValueError('every query must have length k+1')
+        self.lib.check(self.h, self.lib.dbg_lookup_edges(self.h, buf, n, out.ctypes.data))
+        return out
+
+    # ---- output_contigs ------------------------------------------------------------------
+    def walk(self, stop_at_branch=True):
+        n = C.c_uint64()
+        self.lib.check(self.h, self.lib.dbg_walk(self.h, 1 if stop_at_branch else 0, C.byref(n)))
+        arr = (N.Contig * n.value)()
+        self.lib.check(self.h, self.lib.dbg_contigs(self.h, arr))
+        self._contigs = np.frombuffer(arr, dtype=np.dtype([
+            ('start', np.uint32), ('n_nodes', np.uint32), ('terminal', np.uint32), ('kind', np.uint32),
+            ('seg_begin', np.uint64), ('seg_end', np.uint64)]), count=n.value).copy() if n.value else \
+            np.zeros(0, dtype=[('start', np.uint32), ('n_nodes', np.uint32), ('terminal', np.uint32),
+                               ('kind', np.uint32), ('seg_begin', np.uint64), ('seg_end', np.uint64)])
+        return self._contigs
+
+    def contig_descriptors(self):
+        return self._contigs
+
+    def contig_lengths(self):
+        return self._contigs['n_nodes'].astype(np.int64) + (self.k - 1)
+
+    def contig_strings(self, idx=None):
+        """Materialise contig strings (all of them by default)."""
+        if idx is None:
+            idx = np.arange(len(self._contigs), dtype=np.uint64)
+        idx = np.ascontiguousarray(idx, dtype=np.uint64)
+        if len(idx) == 0:
+            return []
+        lens = self._contigs['n_nodes'][idx].astype(np.uint64) + np.uint64(self.k - 1)
+        off = np.zeros(len(idx) + 1, np.uint64)
+        np.cumsum(lens, out=off[1:])
+        total = int(off[-1])
+        if total > MAX_STRING_BYTES:
+            raise MemoryError('dbg_b200: %d contig characters requested at once; use '
+                              'contig_descriptors() / contig_strings(idx) in batches' % total)
+        buf = np.empty(total, np.uint8)
+        self.lib.check(self.h, self.lib.dbg_materialize(self.h, idx.ctypes.data, len(idx), buf.ctypes.data,
+                                                        off.ctypes.data))
+        raw = buf.tobytes().decode('ascii')
+        o = off.tolist()
+        return [raw[o[i]:o[i + 1]] for i in range(len(idx))]
+
+    def contig_scores(self, idx=None):
+        """getScore (II_assembleFromReads.py:14-18) of contigs, computed on the device."""
+        if idx is None:
+            idx = np.arange(len(self._contigs), dtype=np.uint64)
+        idx = np.ascontiguousarray(idx, dtype=np.uint64)
+        out = np.zeros(len(idx), np.uint64)
+        if len(idx):
+            self.lib.check(self.h, self.lib.dbg_contig_scores(self.h, idx.ctypes.data, len(idx), out.ctypes.data))
+        return out
+
+
+# ---------------------------------------------------------------------------------------------
+# lazy views handed back through the reference's return tuple (debruijn.py:285)
+# ---------------------------------------------------------------------------------------------
+class _View(Mapping):
+    def __init__(self, graph):
+        self._graph = graph
+        self._d = None
+
+    def _dict(self):
+        if self._d is None:
+            self._d = self._materialise()
+        return self._d
+
+    def __getitem__(self, key):
+        return self._dict()[key]
+
+    def __iter__(self):
+        return iter(self._dict())
+
+    def __len__(self):
+        return int(self._graph.stats().n_nodes)
+
+    def __repr__(self):
+        return '<%s of %d entries on cuda:%d>' % (type(self).__name__, len(self), self._graph.device)
+
+
+class Vertices(_View):
+    """label -> Node, first-occurrence order (debruijn.py:121-143)."""
+
+    def _materialise(self):
+        g = self._graph
+        nd = g.nodes()
+        labels = g.labels()
+        indeg = ((nd['flags'] & N.NODE_START) == 0).astype(np.int64).tolist()
+        outdeg = ((nd['kept'] >> 12) & 7).tolist()
+        d = {}
+        for lab, i, o in zip(labels, indeg, outdeg):
+            node = Node(lab)
+            node.indegree = i
+            node.outdegree = o
+            d[lab] = node
+        return d
+
+
+class Edges(_View):
+    """label -> kept successors in E order; pulled nodes are absent (debruijn.py:150-166, 254)."""
+
+    def _materialise(self):
+        g = self._graph
+        nd = g.nodes()
+        labels = g.labels()
+        kept = nd['kept'].tolist()
+        pulled = (nd['flags'] & N.NODE_PULLED).tolist()
+        d = {}
+        for lab, w, p in zip(labels, kept, pulled):
+            if p:
+                continue
+            tail = lab[1:]
+            d[lab] = [tail + 'ACGT'[(w >> (2 * j)) & 3] for j in range((w >> 8) & 7)]
+        return d
+
+    def __len__(self):
+        s = self._graph.stats()
+        return int(s.n_nodes - s.n_pulled)
+
+
+class EdgeCountTable(Mapping):
+    """(k+1)-mer -> multiplicity (debruijn.py:213-222).  Small tables are pulled to the host
+    once; large ones answer ``[]`` through dbg_lookup_edges."""
+
+    HOST_LIMIT = 4_000_000
+
+    def __init__(self, graph):
+        self._graph = graph
+        self._d = None
+
+    def _dict(self):
+        if self._d is None:
+            g = self._graph
+            nd = g.nodes()
+            labels = g.labels()
+            cnt = nd['cnt']
+            d = {}
+            rows, cols = np.nonzero(cnt)
+            vals = cnt[rows, cols].tolist()
+            for r, c, v in zip(rows.tolist(), cols.tolist(), vals):
+                d[labels[r] + 'ACGT'[c]] = v
+            self._d = d
+        return self._d
+
+    def __getitem__(self, key):
+        g = self._graph
+        if self._d is not None or g.stats().n_edges <= self.HOST_LIMIT:
+            return self._dict()[key]
+        if not isinstance(key, str) or len(key) != g.k + 1:
+            raise KeyError(key)
+        v = int(g.lookup_edges([key])[0])
+        if v == 0:
+            raise KeyError(key)
+        return v
+
+    def __iter__(self):
+        return iter(self._dict())
+
+    def __len__(self):
+        return int(self._graph.stats().n_edges)
+
+    def __repr__(self):
+        return '<EdgeCountTable of %d entries on cuda:%d>' % (len(self), self._graph.device)
+
+
+class KmerList(list):
+    """A plain list of k-mer strings (branch_kmer / already_pull_out) that remembers its graph."""
+
+    def __init__(self, items=(), graph=None):
+        super().__init__(items)
+        self._graph = graph

@@ -1,0 +1,190 @@
+"""Parity of the product (CUDA path behind include/dbg_b200.h, driven through the drop-in
+``debruijn`` module) against the oracle and the golden vectors of the literal reference.
+
+Bit-exact: all of this is integer / string work (BASELINE.json north_star).  Every test runs
+on the ``backend`` fixture: ``gpu`` = the real library on a B200 (-m gpu), ``emu`` = the same
+sources under the CPU emulator (see tests/conftest.py)."""
+import hashlib
+import json
+import random
+
+import numpy as np
+import pytest
+
+import util
+from oracle import c_oracle, dbg_oracle
+
+
+def digest(obj):
+    return hashlib.sha256(json.dumps(obj, separators=(',', ':')).encode()).hexdigest()
+
+
+def test_golden_fuzz_corpus(backend):
+    """Outputs of /root/reference/debruijn.py itself (DNA-alphabet cases of the corpus)."""
+    cases = util.load_golden('fuzz.json.gz')
+    n = 0
+    for i, case in enumerate(cases):
+        if not util.is_dna(case['reads']):
+            continue
+        got = util.product_snapshot(case['reads'], case['k'], case['threshold'], case['final'])
+        util.assert_same(got, case['expect'], 'golden fuzz %d' % i)
+        n += 1
+    assert n > 400
+
+
+def test_non_dna_input_raises(backend):
+    """No CPU fallback: the peptide example at II_assembleFromReads.py:55 must raise."""
+    import debruijn as db
+    with pytest.raises(ValueError):
+        db.construct_graph(['EVQLVE', 'QLVAPG', 'LVESGGAL', 'LVESGGGL'], 3, 2)
+    with pytest.raises(ValueError):
+        db.construct_graph(['ACGTN', 'ACGTA'], 3, 2)
+    with pytest.raises(ValueError):
+        db.construct_graph(['acgta', 'ACGTA'], 3, 2)
+
+
+def test_kat2_config1_shape(backend):
+    """KAT-2 = BASELINE.json configs[0]: 10 kb genome, 100 bp x 20x, k=31, threshold 2."""
+    from test_oracle_golden import _kat2_reads
+    kat2 = util.load_golden('kat2.json.gz')
+    reads = _kat2_reads(kat2['generator'])
+    for case in kat2['cases']:
+        got = util.product_snapshot(reads, kat2['k'], kat2['threshold'], case['final'])
+        assert got['stdout'] == case['stdout']
+        assert [len(c) for c in got['contigs']] == case['contig_lengths']
+        for f in util.FIELDS:
+            assert digest(got[f]) == case['sha256'][f], (case['final'], f)
+
+
+@pytest.mark.parametrize('seed,big', [(1, False), (2, False), (3, True)])
+def test_random_vs_oracle(backend, seed, big):
+    r = random.Random(1000 + seed)
+    n = 0
+    while n < (150 if not big else 40):
+        reads, k, thr, final = util.random_dna_case(r, big=big)
+        try:
+            exp = dbg_oracle.snapshot(reads, k, thr, final, max_paths=200)
+        except RuntimeError:
+            continue
+        got = util.product_snapshot(reads, k, thr, final)
+        util.assert_same(got, exp, 'random seed %d case %d: %r' % (seed, n, (reads, k, thr, final)))
+        n += 1
+
+
+def test_edge_cases(backend):
+    import debruijn as db
+    cases = [
+        ([], 5, 2, False),                                  # no reads at all
+        ([''], 5, 2, False),                                # one empty read
+        (['ACG', 'AC', ''], 3, 2, False),                   # every read has len <= k (debruijn.py:126)
+        (['ACGT'], 3, 2, False),                            # exactly one window
+        (['AAAAAAAAAA'], 3, 2, False),                      # self loop: the only start is on a cycle (:289)
+        (['ACGTACGTACGTACGT'], 4, 2, False),                # pure cycle
+        (['ACGTACGTACGTACGTT'], 4, 2, True),                # cycle with an exit
+        (['ACGTTGCA'] * 5, 4, 2, False),                    # duplicates kept (II dedups, the module must not)
+        (['A' * 70 + 'C', 'A' * 69 + 'CG'], 63, 2, False),  # k = 63: 126-bit keys
+        (['ACGT' * 40], 33, 2, True),                       # 128-bit keys, cyclic
+        (['ACGTAGCTAGCTAGGATCGATCGTAGCTAGCATCGA'], 31, 2, False),  # k = 31: 62-bit keys
+        (['ACGTAGCTAGCTAGGATCGATCGTAGCTAGCATCGA'], 32, 2, False),  # k = 32: first 128-bit k
+        (['ACGTA', 'ACGTC', 'ACGTG', 'ACGTT'], 4, 1, True),  # four-way tie at threshold 1
+        (['ACGTA', 'ACGTC', 'ACGTC', 'ACGTG'], 4, 0.5, False),  # threshold < 1 drops ties
+    ]
+    for reads, k, thr, final in cases:
+        exp = dbg_oracle.snapshot(reads, k, thr, final)
+        got = util.product_snapshot(reads, k, thr, final)
+        util.assert_same(got, exp, repr((reads, k, thr, final)))
+    for bad_k in (0, 64, -1):
+        with pytest.raises(ValueError):
+            db.construct_graph(['ACGTACGT'], bad_k, 2)
+
+
+def test_threshold_zero_raises_like_reference(backend):
+    """debruijn.py:163 divides by threshold: ZeroDivisionError as soon as one node has two successors."""
+    import debruijn as db
+    with pytest.raises(ZeroDivisionError):
+        db.construct_graph(['ACGTA', 'ACGTC'], 4, 0)
+    g, pull, br, pulled, ect = db.construct_graph(['ACGTA'], 4, 0)     # no multi-successor node: fine
+    assert db.output_contigs(g, br, pulled) == ['ACGTA']
+
+
+def test_reads_not_mutated_and_repeatable(backend):
+    import debruijn as db
+    _, reads = util.synth_reads(7, 2000, 60, 12, err=0.02)
+    before = list(reads)
+    a = util.product_snapshot(reads, 15, 2, False)
+    b = util.product_snapshot(reads, 15, 2, False)
+    assert reads == before
+    for f in util.FIELDS:
+        assert a[f] == b[f]
+
+
+def test_ii_multi_k_loop(backend):
+    """The caller's loop, II_assembleFromReads.py:52-75: dedup, k loop, getScore sort,
+    extend(pull_out_read), final=True on the last k."""
+    import contextlib
+    import io
+    import debruijn as db
+    _, reads = util.synth_reads(11, 1500, 50, 15, err=0.01)
+
+    def run(mod, get_score):
+        seqs = list(dict.fromkeys(reads))
+        out = None
+        with contextlib.redirect_stdout(io.StringIO()):
+            for k in range(12, 16):
+                final = k == 15
+                g, pull, branch, pulled, ect = mod.construct_graph(seqs, k, threshold=2, final=final)
+                contigs = mod.output_contigs(g, branch, pulled)
+                contigs.sort(key=lambda x: get_score(ect, x, k), reverse=True)
+                if final:
+                    out = contigs
+                    break
+                seqs = contigs
+                seqs.extend(pull)
+        return out
+
+    def ref_score(ect, contig, k):                          # II_assembleFromReads.py:14-18 verbatim semantics
+        return sum(ect[contig[i:i + k + 1]] for i in range(len(contig) - k))
+
+    class OracleMod:
+        construct_graph = staticmethod(lambda r, k, threshold, final: dbg_oracle.construct_graph(r, k, threshold, final, verbose=False))
+        output_contigs = staticmethod(lambda g, b, p: dbg_oracle.output_contigs(g, b, p, verbose=False))
+
+    exp = run(OracleMod, ref_score)
+    got = run(db, ref_score)
+    assert got == exp
+    got2 = run(db, db.get_score)                            # batched device lookup gives the same order
+    assert got2 == exp
+
+
+def test_descriptors_scores_and_lookup(backend):
+    """C-ABI level: descriptors, device getScore and edge lookups against the C oracle."""
+    from dbg_b200 import Graph
+    _, reads = util.synth_reads(5, 3000, 80, 15, err=0.01)
+    k = 21
+    g = Graph(k)
+    g.build(reads, threshold=2, final=False)
+    g.walk(stop_at_branch=True)
+    res = c_oracle.run(reads, k, 2, False)
+    st = g.stats()
+    assert (st.n_nodes, st.n_windows, st.n_starts) == (res.n_nodes, res.n_windows, res.n_starts)
+    assert st.n_branch == res.n_branch_internal and st.n_pulled == len(res.pulled)
+    nd = g.nodes()
+    assert np.array_equal(nd['tag'], res.tag)
+    assert np.array_equal(nd['key_lo'], res.key_lo) and np.array_equal(nd['key_hi'], res.key_hi)
+    assert np.array_equal(nd['cnt'], res.cnt)
+    desc = g.contig_descriptors()
+    assert len(desc) == len(res.contigs)
+    id_of_slot = {int(s): i for i, s in enumerate(nd['id'])}
+    assert [id_of_slot[int(s)] for s in desc['start']] == res.contigs[:, 0].tolist()
+    assert desc['n_nodes'].tolist() == res.contigs[:, 1].tolist()
+    assert [id_of_slot[int(s)] for s in desc['terminal']] == res.contigs[:, 2].tolist()
+    assert desc['kind'].tolist() == res.contigs[:, 3].tolist()
+    strings = g.contig_strings()
+    assert strings == res.contig_strings
+    ect = {lab + 'ACGT'[c]: int(res.cnt[v, c]) for v, lab in enumerate(g.labels()) for c in range(4) if res.cnt[v, c]}
+    exp_scores = [sum(ect[s[i:i + k + 1]] for i in range(len(s) - k)) for s in strings]
+    assert g.contig_scores().tolist() == exp_scores
+    qs = list(ect)[:500] + ['A' * (k + 1), 'ACGT' * 5 + 'AC']
+    got = g.lookup_edges(qs).tolist()
+    assert got == [ect.get(q, 0) for q in qs]
+    g.close()
