@@ -77,6 +77,7 @@ typedef struct {
     uint64_t table_slots;
     uint64_t table_bytes;
     uint64_t hll_estimate;   /* distinct-node estimate used to size the table                 */
+    uint64_t n_launches;     /* kernels this library launched in the last dbg_build* + dbg_walk */
     uint32_t key_words;      /* 1 (k <= 31) or 2                                              */
     uint32_t jump_rounds;    /* pointer-jumping rounds run by dbg_walk                        */
     /* device time per stage, CUDA events on the handle's stream, milliseconds */

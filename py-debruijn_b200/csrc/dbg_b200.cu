@@ -26,11 +26,12 @@
 
 #ifdef DBG_EMU
 #define LAUNCH(kernel, grid, block, stream, ...) \
-    emu::launch(dim3((unsigned)(grid)), dim3((unsigned)(block)), 0, [&]() { kernel(__VA_ARGS__); })
+    (h->st.n_launches++, emu::launch(dim3((unsigned)(grid)), dim3((unsigned)(block)), 0, [&]() { kernel(__VA_ARGS__); }))
 #else
 #include <cuda_runtime.h>
 #include <cub/device/device_radix_sort.cuh>
-#define LAUNCH(kernel, grid, block, stream, ...) kernel<<<(unsigned)(grid), (unsigned)(block), 0, stream>>>(__VA_ARGS__)
+#define LAUNCH(kernel, grid, block, stream, ...) \
+    (h->st.n_launches++, kernel<<<(unsigned)(grid), (unsigned)(block), 0, stream>>>(__VA_ARGS__))
 #endif
 
 #include "../../include/dbg_b200.h"
@@ -146,6 +147,7 @@ static int sort_by_tag(dbg_t *h, uint64_t n, u32 *d_sorted_slots_out) {
     CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, ptr<u64>(h->b_tag), ptr<u64>(h->b_tag2), ptr<u32>(h->b_slot),
                                        d_sorted_slots_out, (int64_t)n, 0, 64, h->stream));
     TRY(reserve(h, h->b_sorttmp, tmp));
+    h->st.n_launches++;                                   // cub launches several kernels; counted as one
     CK(cub::DeviceRadixSort::SortPairs(h->b_sorttmp.p, tmp, ptr<u64>(h->b_tag), ptr<u64>(h->b_tag2),
                                        ptr<u32>(h->b_slot), d_sorted_slots_out, (int64_t)n, 0, 64, h->stream));
 #endif
