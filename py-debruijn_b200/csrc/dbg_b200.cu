@@ -174,6 +174,14 @@ static int fetch_counters(dbg_t *h) {
     return DBG_OK;
 }
 
+static int check_fault(dbg_t *h, const char *where) {
+    TRY(fetch_counters(h));
+    if (h->ctr.fault && !getenv("DBG_B200_IGNORE_FAULT"))
+        return fail(h, DBG_ERR_STATE, "internal consistency fault %u (info %u) in %s", h->ctr.fault,
+                    h->ctr.fault_info, where);
+    return DBG_OK;
+}
+
 template <int W>
 static int collect_sorted(dbg_t *h, u32 want, uint64_t expect, DevBuf &out, u64 *cursor) {
     // slots whose flags hit `want`, sorted by first-occurrence tag
@@ -200,11 +208,12 @@ static int tip_prune(dbg_t *h) {
     TRY(reserve(h, h->b_off64, (nb + 1) * 8));
     LAUNCH(k_tip_paths<W>, blocks_for(nb), DBG_BLOCK, h->stream, ptr<const Slot<W>>(h->b_table), h->n_slots, h->k,
            ptr<const u8>(h->b_flags), ptr<const u16>(h->b_kept), ptr<const u32>(h->b_branch), nb, 0,
-           ptr<u32>(h->b_cnt32), (const u64 *)nullptr, (u32 *)nullptr);
+           ptr<u32>(h->b_cnt32), (const u64 *)nullptr, (u32 *)nullptr, ptr<DevCounters>(h->b_ctr));
     CKK();
     std::vector<u32> counts(nb);
     CK(cudaMemcpyAsync(counts.data(), h->b_cnt32.p, nb * 4, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    TRY(check_fault(h, "k_tip_paths"));
     std::vector<u64> offs(nb + 1, 0);
     for (uint64_t i = 0; i < nb; i++) offs[i + 1] = offs[i] + counts[i];
     const uint64_t total = offs[nb];
@@ -213,7 +222,7 @@ static int tip_prune(dbg_t *h) {
     CK(cudaMemcpyAsync(h->b_off64.p, offs.data(), (nb + 1) * 8, cudaMemcpyHostToDevice, h->stream));
     LAUNCH(k_tip_paths<W>, blocks_for(nb), DBG_BLOCK, h->stream, ptr<const Slot<W>>(h->b_table), h->n_slots, h->k,
            ptr<const u8>(h->b_flags), ptr<const u16>(h->b_kept), ptr<const u32>(h->b_branch), nb, 1,
-           ptr<u32>(h->b_cnt32), ptr<const u64>(h->b_off64), ptr<u32>(h->b_recs));
+           ptr<u32>(h->b_cnt32), ptr<const u64>(h->b_off64), ptr<u32>(h->b_recs), ptr<DevCounters>(h->b_ctr));
     CKK();
     std::vector<u32> recs(total * 6);
     CK(cudaMemcpyAsync(recs.data(), h->b_recs.p, total * 6 * 4, cudaMemcpyDeviceToHost, h->stream));
@@ -344,6 +353,9 @@ static int build_impl(dbg_t *h, const u8 *d_bases, const u64 *d_off) {
     st.n_multi = h->ctr.n_multi;
     st.n_branch = h->ctr.n_branch;
     st.n_starts = h->ctr.n_starts;
+    if (h->ctr.fault && !getenv("DBG_B200_IGNORE_FAULT"))
+        return fail(h, DBG_ERR_STATE, "internal consistency fault %u (info %u) in k_finalize", h->ctr.fault,
+                    h->ctr.fault_info);
     if (st.n_multi && h->threshold == 0.0)
         return fail(h, DBG_ERR_ZERODIV, "threshold == 0 with a multi-successor node (debruijn.py:163)");
     const int e4 = ev_mark(h);
@@ -358,11 +370,12 @@ static int build_impl(dbg_t *h, const u8 *d_bases, const u64 *d_off) {
         CKK();
         LAUNCH(k_order_scan<W>, h->n_tiles, DBG_BLOCK, h->stream, ptr<const u64>(h->b_packed), d_off,
                ptr<const u32>(h->b_tile), h->n_bases, k, ptr<const S>(h->b_table), n_slots,
-               ptr<const u8>(h->b_flags), h->read_idx_base, ptr<OrderEntry>(h->b_order), cap);
+               ptr<const u8>(h->b_flags), h->read_idx_base, ptr<OrderEntry>(h->b_order), cap, d_ctr);
         CKK();
         LAUNCH(k_order_apply<W>, blocks_for(cap), DBG_BLOCK, h->stream, ptr<const S>(h->b_table), n_slots, k,
-               h->threshold, ptr<const OrderEntry>(h->b_order), cap, ptr<u16>(h->b_kept), ptr<u32>(h->b_succ));
+               h->threshold, ptr<const OrderEntry>(h->b_order), cap, ptr<u16>(h->b_kept), ptr<u32>(h->b_succ), d_ctr);
         CKK();
+        TRY(check_fault(h, "k_order_*"));
     }
     const int e5 = ev_mark(h);
 
@@ -453,10 +466,8 @@ static int walk_impl(dbg_t *h, int stop_at_branch) {
         LAUNCH(k_jump, blocks_for(n_slots), DBG_BLOCK, h->stream, ptr<u64>(h->b_link), n_slots, d_ctr);
         CKK();
         st.jump_rounds++;
-        u32 changed = 0;
-        CK(cudaMemcpyAsync(&changed, &d_ctr->changed, 4, cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaStreamSynchronize(h->stream));
-        if (!changed) break;
+        TRY(check_fault(h, "k_jump"));
+        if (!h->ctr.changed) break;
     }
     const int e1 = ev_mark(h);
 
@@ -480,8 +491,9 @@ static int walk_impl(dbg_t *h, int stop_at_branch) {
         TRY(reserve(h, h->b_junction, nb * 4 * sizeof(JunctionSucc)));
         LAUNCH(k_junctions<W>, blocks_for(nb), DBG_BLOCK, h->stream, ptr<const S>(h->b_table), n_slots, h->k,
                ptr<const u8>(h->b_flags), ptr<const u16>(h->b_kept), ptr<const u64>(h->b_link),
-               ptr<const u32>(h->b_branch), nb, ptr<JunctionSucc>(h->b_junction));
+               ptr<const u32>(h->b_branch), nb, ptr<JunctionSucc>(h->b_junction), d_ctr);
         CKK();
+        TRY(check_fault(h, "k_junctions"));
         junc.resize(nb * 4);
         CK(cudaMemcpyAsync(junc.data(), h->b_junction.p, nb * 4 * sizeof(JunctionSucc), cudaMemcpyDeviceToHost,
                            h->stream));

@@ -16,8 +16,6 @@ typedef unsigned long long u64;
 typedef unsigned int u32;
 typedef unsigned short u16;
 typedef unsigned char u8;
-typedef unsigned __int128 u128;
-
 #define DBG_HD __host__ __device__ __forceinline__
 #define DBG_D __device__ __forceinline__
 
@@ -31,9 +29,19 @@ typedef unsigned __int128 u128;
 
 #define NONE32 0xFFFFFFFFu
 
+// 128-bit keys are two explicit 64-bit words with hand-written shifts.  (nvcc 12.9 miscompiles
+// rolling `unsigned __int128` shifts inside the unrolled window loop for sm_100a -- bits carried
+// from the low into the high word were lost on the B200 -- so no __int128 arithmetic is used in
+// device code.)
+struct __align__(16) K128 {
+    u64 lo, hi;
+};
+DBG_HD bool operator==(K128 a, K128 b) { return ((a.lo ^ b.lo) | (a.hi ^ b.hi)) == 0; }
+DBG_HD bool operator!=(K128 a, K128 b) { return ((a.lo ^ b.lo) | (a.hi ^ b.hi)) != 0; }
+
 template <int W> struct KeyOf;
 template <> struct KeyOf<1> { typedef u64 type; };
-template <> struct KeyOf<2> { typedef u128 type; };
+template <> struct KeyOf<2> { typedef K128 type; };
 
 template <int W> struct Slot;
 template <> struct __align__(32) Slot<1> {
@@ -42,18 +50,60 @@ template <> struct __align__(32) Slot<1> {
     u32 cnt[4];
 };
 template <> struct __align__(16) Slot<2> {
-    u128 key;
+    K128 key;
     u64 tag;
     u64 pad;
     u32 cnt[4];
 };
 
-template <int W> DBG_HD typename KeyOf<W>::type empty_key() { return ~(typename KeyOf<W>::type)0; }
+template <int W> DBG_HD typename KeyOf<W>::type empty_key();
+template <> DBG_HD u64 empty_key<1>() { return ~0ULL; }
+template <> DBG_HD K128 empty_key<2>() { K128 r; r.lo = ~0ULL; r.hi = ~0ULL; return r; }
 
-template <int W> DBG_HD typename KeyOf<W>::type key_mask(int k) {
-    typedef typename KeyOf<W>::type K;
-    return (((K)1) << (2 * k)) - 1;          // 2k <= 62 (W=1) or <= 126 (W=2): never the full word
+// mask of the low 2k bits: 2k <= 62 (W=1) or <= 126 (W=2), never the full key, so the all-ones
+// pattern is free for EMPTY
+template <int W> DBG_HD typename KeyOf<W>::type key_mask(int k);
+template <> DBG_HD u64 key_mask<1>(int k) { return (1ULL << (2 * k)) - 1; }
+template <> DBG_HD K128 key_mask<2>(int k) {
+    K128 r;
+    const int b = 2 * k;
+    if (b >= 64) { r.lo = ~0ULL; r.hi = (1ULL << (b - 64)) - 1; }
+    else { r.lo = (1ULL << b) - 1; r.hi = 0; }
+    return r;
 }
+
+// successor key: drop the first base, append `nb` (debruijn.py:128: read[i+1:i+k+1])
+DBG_HD u64 key_roll(u64 key, u32 nb, u64 mask) { return ((key << 2) | (u64)nb) & mask; }
+DBG_HD K128 key_roll(K128 key, u32 nb, K128 mask) {
+    K128 r;
+    r.hi = ((key.hi << 2) | (key.lo >> 62)) & mask.hi;
+    r.lo = ((key.lo << 2) | (u64)nb) & mask.lo;
+    return r;
+}
+// append without masking (building a key base by base)
+DBG_HD u64 key_push(u64 key, u32 nb) { return (key << 2) | (u64)nb; }
+DBG_HD K128 key_push(K128 key, u32 nb) {
+    K128 r;
+    r.hi = (key.hi << 2) | (key.lo >> 62);
+    r.lo = (key.lo << 2) | (u64)nb;
+    return r;
+}
+template <int W> DBG_HD typename KeyOf<W>::type zero_key();
+template <> DBG_HD u64 zero_key<1>() { return 0; }
+template <> DBG_HD K128 zero_key<2>() { K128 r; r.lo = 0; r.hi = 0; return r; }
+
+DBG_HD u32 key_last_base(u64 key) { return (u32)(key & 3); }
+DBG_HD u32 key_last_base(K128 key) { return (u32)(key.lo & 3); }
+// base j (0 = first) of a k-mer key
+DBG_HD u32 key_base(u64 key, int k, int j) { return (u32)(key >> (2 * (k - 1 - j))) & 3u; }
+DBG_HD u32 key_base(K128 key, int k, int j) {
+    const int sh = 2 * (k - 1 - j);
+    return (u32)(sh >= 64 ? key.hi >> (sh - 64) : key.lo >> sh) & 3u;
+}
+DBG_HD u64 key_lo64(u64 key) { return key; }
+DBG_HD u64 key_lo64(K128 key) { return key.lo; }
+DBG_HD u64 key_hi64(u64) { return 0; }
+DBG_HD u64 key_hi64(K128 key) { return key.hi; }
 
 DBG_HD u64 fmix64(u64 x) {
     x ^= x >> 33; x *= 0xff51afd7ed558ccdULL;
@@ -62,13 +112,13 @@ DBG_HD u64 fmix64(u64 x) {
     return x;
 }
 DBG_HD u64 hash_key(u64 k) { return fmix64(k + 0x9e3779b97f4a7c15ULL); }
-DBG_HD u64 hash_key(u128 k) { return fmix64((u64)k ^ fmix64((u64)(k >> 64) + 0x9e3779b97f4a7c15ULL)); }
+DBG_HD u64 hash_key(K128 k) { return fmix64(k.lo ^ fmix64(k.hi + 0x9e3779b97f4a7c15ULL)); }
 
 DBG_HD u64 mulhi64(u64 a, u64 b) {
 #if defined(__CUDA_ARCH__) || defined(DBG_EMU)
     return __umul64hi(a, b);
 #else
-    return (u64)(((u128)a * b) >> 64);
+    return (u64)(((unsigned __int128)a * b) >> 64);
 #endif
 }
 
@@ -90,14 +140,17 @@ template <> DBG_D u64 extract_key<1>(const u64 *__restrict__ packed, u64 p, int 
     u64 top = s ? ((w0 << s) | (w1 >> (64 - s))) : w0;       // 64 bits starting at base p
     return top >> (64 - 2 * k);
 }
-template <> DBG_D u128 extract_key<2>(const u64 *__restrict__ packed, u64 p, int k) {
+template <> DBG_D K128 extract_key<2>(const u64 *__restrict__ packed, u64 p, int k) {
     u64 w = p >> 5;
     int s = 2 * (int)(p & 31);
     u64 w0 = __ldg(packed + w), w1 = __ldg(packed + w + 1), w2 = __ldg(packed + w + 2);
-    u64 hi = s ? ((w0 << s) | (w1 >> (64 - s))) : w0;
+    u64 hi = s ? ((w0 << s) | (w1 >> (64 - s))) : w0;        // 128 bits starting at base p
     u64 lo = s ? ((w1 << s) | (w2 >> (64 - s))) : w1;
-    u128 top = ((u128)hi << 64) | lo;                        // 128 bits starting at base p
-    return top >> (128 - 2 * k);
+    const int sh = 128 - 2 * k;                              // right-align: 2 <= sh <= 126
+    K128 r;
+    if (sh >= 64) { r.lo = sh == 64 ? hi : hi >> (sh - 64); r.hi = 0; }
+    else { r.lo = (lo >> sh) | (hi << (64 - sh)); r.hi = hi >> sh; }
+    return r;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -106,9 +159,27 @@ template <> DBG_D u128 extract_key<2>(const u64 *__restrict__ packed, u64 p, int
 // for an occupied slot, which the CAS then corrects.
 // ---------------------------------------------------------------------------------------------
 DBG_D u64 load_key(const Slot<1> *s) { return __ldcg(&s->key); }
-DBG_D u128 load_key(const Slot<2> *s) {
+DBG_D K128 load_key(const Slot<2> *s) {
     ulonglong2 v = __ldcg(reinterpret_cast<const ulonglong2 *>(&s->key));
-    return ((u128)v.y << 64) | v.x;
+    K128 r; r.lo = v.x; r.hi = v.y;
+    return r;
+}
+
+// compare-and-swap of a whole key; returns the previous value
+DBG_D u64 cas_key(u64 *addr, u64 expect, u64 val) { return atomicCAS(addr, expect, val); }
+DBG_D K128 cas_key(K128 *addr, K128 expect, K128 val) {
+    K128 old;
+#ifdef DBG_EMU
+    old = *addr;
+    if (old == expect) *addr = val;
+#else
+    asm volatile("{\n\t.reg .b128 c, v, d;\n\tmov.b128 c, {%2, %3};\n\tmov.b128 v, {%4, %5};\n\t"
+                 "atom.global.cas.b128 d, [%6], c, v;\n\tmov.b128 {%0, %1}, d;\n\t}"
+                 : "=l"(old.lo), "=l"(old.hi)
+                 : "l"(expect.lo), "l"(expect.hi), "l"(val.lo), "l"(val.hi), "l"(addr)
+                 : "memory");
+#endif
+    return old;
 }
 
 // find-or-insert; returns slot index or NONE64 when the table is full
@@ -122,7 +193,7 @@ DBG_D u64 table_upsert(Slot<W> *table, u64 n_slots, typename KeyOf<W>::type key)
         K cur = load_key(&table[idx]);
         if (cur == key) return idx;
         if (cur == EMPTY) {
-            K old = atomicCAS(&table[idx].key, EMPTY, key);
+            K old = cas_key(&table[idx].key, EMPTY, key);
             if (old == EMPTY || old == key) return idx;
         }
         if (++idx == n_slots) idx = 0;

@@ -38,7 +38,19 @@ struct DevCounters {
     u32 overflow;       // table full
     u32 too_long;       // read longer than 2^32-1
     u32 changed;        // pointer jumping made progress
+    u32 fault;          // first internal-consistency failure seen by a kernel (FAULT_* code), 0 = none
+    u32 fault_info;
 };
+
+// internal-consistency guards: a kernel that would index out of range records a code instead
+#define FAULT_SUCC_MISSING 1u     // k_finalize / k_order_apply: a kept successor is not in the table
+#define FAULT_TIP_MISSING 2u      // k_tip_paths: ditto
+#define FAULT_JUMP_RANGE 3u       // k_jump / k_emit: link points outside the table
+#define FAULT_JUNCTION_MISSING 4u // k_junctions
+#define FAULT_ORDER_MISSING 5u    // k_order_scan: multi-successor node without an order entry
+DBG_D void raise_fault(DevCounters *ctr, u32 code, u32 info) {
+    if (atomicCAS(&ctr->fault, 0u, code) == 0u) ctr->fault_info = info;
+}
 
 // ---------------------------------------------------------------------------------------------
 // k_pack: ASCII -> 2-bit, 32 bases per u64 word, 128-bit loads (2 x uint4 per thread).
@@ -151,7 +163,7 @@ DBG_D void for_windows(const u64 *__restrict__ packed, const u64 *__restrict__ o
         u32 nb = base_at(packed, p + k);
         bool ok = BUILD ? (len > (u64)k && pos + k <= len) : (pos + k <= len);
         if (ok) f(key, r, pos, pos + k < len, nb);
-        key = ((key << 2) | (K)nb) & mask;
+        key = key_roll(key, nb, mask);
     }
 }
 
@@ -228,8 +240,10 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_finalize(const Slot<W> *__restric
             f = F_OCC | ((u32)tag == 0 ? F_START : 0) | (nk > 1 ? F_BRANCH : 0) |
                 (m == 0 ? F_DEADEND : 0) | (m > 1 ? F_MULTI : 0);
             if (nk == 1) {
-                K sk = ((key << 2) | (K)kept_base(word, 0)) & key_mask<W>(k);
-                sx = (u32)table_find<W>(table, n_slots, sk);
+                K sk = key_roll(key, (u32)kept_base(word, 0), key_mask<W>(k));
+                u64 fi = table_find<W>(table, n_slots, sk);
+                if (fi == NONE64) raise_fault(ctr, FAULT_SUCC_MISSING, (u32)i);
+                sx = (u32)fi;
             }
         }
         flags[i] = (u8)f;
@@ -288,7 +302,7 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_order_scan(const u64 *__restrict_
                                                           const u32 *__restrict__ tile_first, u64 n_bases, int k,
                                                           const Slot<W> *__restrict__ table, u64 n_slots,
                                                           const u8 *__restrict__ flags, u64 read_idx_base,
-                                                          OrderEntry *ot, u64 cap) {
+                                                          OrderEntry *ot, u64 cap, DevCounters *ctr) {
     typedef typename KeyOf<W>::type K;
     for_windows<W, true>(packed, off, tile_first, n_bases, k,
         [&](K key, u32 r, u64 pos, bool has_next, u32 nb) {
@@ -296,7 +310,7 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_order_scan(const u64 *__restrict_
             u64 idx = table_find<W>(table, n_slots, key);
             if (idx == NONE64 || !(flags[idx] & F_MULTI)) return;
             u64 e = order_locate(ot, cap, idx, false);
-            if (e == NONE64) return;
+            if (e == NONE64) { raise_fault(ctr, FAULT_ORDER_MISSING, (u32)idx); return; }
             u64 tag = ((read_idx_base + r) << 32) | pos;
             if (tag < __ldcg(&ot[e].first[nb])) atomicMin(&ot[e].first[nb], tag);
         });
@@ -305,7 +319,8 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_order_scan(const u64 *__restrict_
 template <int W>
 __global__ void __launch_bounds__(DBG_BLOCK) k_order_apply(const Slot<W> *__restrict__ table, u64 n_slots, int k,
                                                            double threshold, const OrderEntry *__restrict__ ot,
-                                                           u64 cap, u16 *__restrict__ kept, u32 *__restrict__ succ) {
+                                                           u64 cap, u16 *__restrict__ kept, u32 *__restrict__ succ,
+                                                           DevCounters *ctr) {
     typedef typename KeyOf<W>::type K;
     u64 e = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= cap) return;
@@ -316,8 +331,10 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_order_apply(const Slot<W> *__rest
     u32 word = prune_successors(cnt, first, threshold);
     kept[i] = (u16)word;
     if (kept_count(word) == 1) {        // threshold < 1: the tie decides WHICH successor survives
-        K sk = ((table[i].key << 2) | (K)kept_base(word, 0)) & key_mask<W>(k);
-        succ[i] = (u32)table_find<W>(table, n_slots, sk);
+        K sk = key_roll(table[i].key, (u32)kept_base(word, 0), key_mask<W>(k));
+        u64 fi = table_find<W>(table, n_slots, sk);
+        if (fi == NONE64) raise_fault(ctr, FAULT_SUCC_MISSING, (u32)i);
+        succ[i] = (u32)fi;
     }
 }
 
@@ -355,7 +372,7 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_tip_paths(const Slot<W> *__restri
                                                          const u8 *__restrict__ flags, const u16 *__restrict__ kept,
                                                          const u32 *__restrict__ branch, u64 n_branch, int mode,
                                                          u32 *__restrict__ counts, const u64 *__restrict__ offs,
-                                                         u32 *__restrict__ recs) {
+                                                         u32 *__restrict__ recs, DevCounters *ctr) {
     typedef typename KeyOf<W>::type K;
     u64 b = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= n_branch) return;
@@ -371,8 +388,10 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_tip_paths(const Slot<W> *__restri
         if ((int)ci >= kept_count(word[d])) { depth--; continue; }
         child[d] = ci + 1;
         if (depth == 5) continue;                                   // callee would see depth == 0
-        K sk = ((keyv[d] << 2) | (K)kept_base(word[d], (int)ci)) & mask;
-        u32 nx = (u32)table_find<W>(table, n_slots, sk);
+        K sk = key_roll(keyv[d], (u32)kept_base(word[d], (int)ci), mask);
+        u64 fi = table_find<W>(table, n_slots, sk);
+        if (fi == NONE64) { raise_fault(ctr, FAULT_TIP_MISSING, vec[d]); continue; }
+        u32 nx = (u32)fi;
         vec[depth] = nx;
         u32 fl = flags[nx];
         if (fl & F_DEADEND) {                                       // debruijn.py:173
@@ -445,6 +464,7 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_jump(u64 *link, u64 n_slots, DevC
     u64 l = __ldcg(&link[i]);
     u32 nx = link_next(l);
     if (nx == (u32)i) return;                       // root (dist 0) or a self-loop (dist > 0)
+    if (nx >= n_slots) { raise_fault(ctr, FAULT_JUMP_RANGE, (u32)i); return; }
     u64 ln = __ldcg(&link[nx]);
     u32 nn = link_next(ln);
     if (nn == nx) return;                           // points at a root / self-loop: final
@@ -484,7 +504,7 @@ template <int W>
 __global__ void __launch_bounds__(DBG_BLOCK) k_junctions(const Slot<W> *__restrict__ table, u64 n_slots, int k,
                                                          const u8 *__restrict__ flags, const u16 *__restrict__ kept,
                                                          const u64 *__restrict__ link, const u32 *__restrict__ branch,
-                                                         u64 n_branch, JunctionSucc *__restrict__ out) {
+                                                         u64 n_branch, JunctionSucc *__restrict__ out, DevCounters *ctr) {
     typedef typename KeyOf<W>::type K;
     u64 b = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= n_branch) return;
@@ -495,8 +515,10 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_junctions(const Slot<W> *__restri
         JunctionSucc js;
         js.entry = NONE32; js.n_hops = 0; js.terminal = NONE32; js.kind = T_CYCLE;
         if (j < kept_count(word)) {
-            K sk = ((key << 2) | (K)kept_base(word, j)) & key_mask<W>(k);
-            u32 s = (u32)table_find<W>(table, n_slots, sk);
+            K sk = key_roll(key, (u32)kept_base(word, j), key_mask<W>(k));
+            u64 fi = table_find<W>(table, n_slots, sk);
+            if (fi == NONE64) { raise_fault(ctr, FAULT_JUNCTION_MISSING, v); out[b * 4 + j] = js; continue; }
+            u32 s = (u32)fi;
             u64 l = link[s];
             u32 t = link_next(l);
             js.entry = s; js.n_hops = link_dist(l); js.terminal = t;
@@ -536,13 +558,13 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_materialize(const Slot<W> *__rest
     char *o = buf + job.out;
     K key = table[v].key;
     if (job.first) {
-        for (int i = 0; i < k; i++) *o++ = (char)((ALPHA >> (8 * (u32)((key >> (2 * (k - 1 - i))) & 3))) & 0xFF);
+        for (int i = 0; i < k; i++) *o++ = (char)((ALPHA >> (8 * key_base(key, k, i))) & 0xFF);
     } else {
-        *o++ = (char)((ALPHA >> (8 * (u32)(key & 3))) & 0xFF);
+        *o++ = (char)((ALPHA >> (8 * key_last_base(key))) & 0xFF);
     }
     for (u32 i = 1; i < job.n_nodes; i++) {
         v = succ[v];
-        *o++ = (char)((ALPHA >> (8 * (u32)(table[v].key & 3))) & 0xFF);
+        *o++ = (char)((ALPHA >> (8 * key_last_base(table[v].key))) & 0xFF);
     }
 }
 
@@ -565,7 +587,7 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_scores(const Slot<W> *__restrict_
         u32 v = seg_entry[s];
         for (u32 i = 0; i < seg_nodes[s]; i++) {
             if (i) v = succ[v];
-            if (prev != NONE32) total += table[prev].cnt[(u32)(table[v].key & 3)];
+            if (prev != NONE32) total += table[prev].cnt[key_last_base(table[v].key)];
             prev = v;
         }
     }
@@ -579,14 +601,14 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_lookup_edges(const Slot<W> *__res
     u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const u8 *s = q + i * (u64)(k + 1);
-    K key = 0;
+    K key = zero_key<W>();
     bool bad = false;
     u32 code = 0;
     for (int j = 0; j <= k; j++) {
         u32 c = s[j];
         code = ((c >> 1) & 3u) ^ ((c >> 2) & 1u);
         bad |= (c != ((0x54474341u >> (8 * code)) & 0xFFu));
-        if (j < k) key = (key << 2) | (K)code;
+        if (j < k) key = key_push(key, code);
     }
     u32 res = 0;
     if (!bad) {
@@ -603,8 +625,8 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_gather_keys(const Slot<W> *__rest
     u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     typename KeyOf<W>::type key = table[ids[i]].key;
-    lo[i] = (u64)key;
-    hi[i] = W == 2 ? (u64)((u128)key >> 64) : 0;
+    lo[i] = key_lo64(key);
+    hi[i] = key_hi64(key);
 }
 
 // export: compact occupied slots (unordered)
@@ -627,8 +649,8 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_export(const Slot<W> *__restrict_
     u64 o = base + __popc(b & ((1u << lane) - 1));
     typename KeyOf<W>::type key = table[i].key;
     o_id[o] = (u32)i;
-    o_lo[o] = (u64)key;
-    o_hi[o] = W == 2 ? (u64)((u128)key >> 64) : 0;
+    o_lo[o] = key_lo64(key);
+    o_hi[o] = key_hi64(key);
     o_tag[o] = table[i].tag;
     for (int c = 0; c < 4; c++) o_cnt[4 * o + c] = table[i].cnt[c];
     o_flags[o] = flags[i];

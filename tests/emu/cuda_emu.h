@@ -262,7 +262,8 @@ static inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 static inline cudaError_t cudaGetDevice(int *d) { *d = 0; return cudaSuccess; }
 static inline cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return cudaSuccess; }
 static inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
-template <typename T> static inline cudaError_t cudaMalloc(T **p, size_t n) { *p = (T *)aligned_alloc(256, (n + 255) / 256 * 256 + 256); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+/* device memory comes back full of garbage, as on a real GPU, so reads of never-written memory show up */
+template <typename T> static inline cudaError_t cudaMalloc(T **p, size_t n) { size_t m = (n + 255) / 256 * 256 + 256; *p = (T *)aligned_alloc(256, m); if (*p) memset((void *)*p, 0xA5, m); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
 template <typename T> static inline cudaError_t cudaMallocHost(T **p, size_t n) { *p = (T *)aligned_alloc(256, (n + 255) / 256 * 256 + 256); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
 static inline cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
 static inline cudaError_t cudaFreeHost(void *p) { free(p); return cudaSuccess; }
