@@ -65,7 +65,7 @@ struct dbg_handle {
     const uint64_t *d_off = nullptr;          // offsets in use (caller's for build_device, ours for build)
     DevBuf b_bases, b_off, b_packed, b_tile, b_table, b_flags, b_kept, b_succ, b_link, b_ctr, b_hll,
            b_order, b_tag, b_tag2, b_slot, b_slot2, b_sorttmp, b_branch, b_starts, b_pulled, b_readflags,
-           b_recs, b_cnt32, b_off64, b_contig, b_junction, b_scratch[6];
+           b_recs, b_cnt32, b_off64, b_contig, b_junction, b_split, b_scratch[6];
     DevCounters ctr;
     dbg_stats_t st;
     std::vector<uint32_t> branch, pulled;     // reference order
@@ -454,20 +454,37 @@ static int walk_impl(dbg_t *h, int stop_at_branch) {
     st.jump_rounds = 0;
     const int e0 = ev_mark(h);
 
-    // ---- list ranking over the pruned successor array ----
+    // ---- list ranking over the pruned successor array, cut at splitters ----
     TRY(reserve(h, h->b_link, n_slots * 8));
+    const uint64_t split_cap = (n_slots >> WALK_SPLIT_LOG2) * 3 / 2 + st.n_starts + 4096;
+    TRY(reserve(h, h->b_split, split_cap * 4));
+    CK(cudaMemsetAsync(&d_ctr->n_list_a, 0, 8, h->stream));
     LAUNCH(k_link_init, blocks_for(n_slots), DBG_BLOCK, h->stream, ptr<const u8>(h->b_flags),
-           ptr<const u16>(h->b_kept), ptr<const u32>(h->b_succ), n_slots, ptr<u64>(h->b_link));
+           ptr<const u16>(h->b_kept), ptr<const u32>(h->b_succ), n_slots, ptr<u64>(h->b_link), ptr<u32>(h->b_split),
+           split_cap, &d_ctr->n_list_a);
     CKK();
-    int max_rounds = 2;
-    for (uint64_t n = st.n_nodes; n > 1; n >>= 1) max_rounds++;
-    for (int r = 0; r < max_rounds; r++) {
-        CK(cudaMemsetAsync(&d_ctr->changed, 0, 4, h->stream));
-        LAUNCH(k_jump, blocks_for(n_slots), DBG_BLOCK, h->stream, ptr<u64>(h->b_link), n_slots, d_ctr);
+    TRY(fetch_counters(h));
+    const uint64_t n_split = h->ctr.n_list_a;
+    if (n_split > split_cap) return fail(h, DBG_ERR_STATE, "splitter list overflow (%llu > %llu)",
+                                         (unsigned long long)n_split, (unsigned long long)split_cap);
+    if (n_split) {
+        LAUNCH(k_sublist, blocks_for(n_split), DBG_BLOCK, h->stream, ptr<u64>(h->b_link), ptr<const u32>(h->b_split),
+               n_split);
         CKK();
-        st.jump_rounds++;
-        TRY(check_fault(h, "k_jump"));
-        if (!h->ctr.changed) break;
+        int max_rounds = 2;
+        for (uint64_t n = n_split; n > 1; n >>= 1) max_rounds++;
+        CK(cudaMemsetAsync(&d_ctr->changed, 0, 4, h->stream));
+        for (int r = 0; r < max_rounds; r++) {              // no host round trip per round: the list is small
+            LAUNCH(k_jump, blocks_for(n_split), DBG_BLOCK, h->stream, ptr<u64>(h->b_link),
+                   ptr<const u32>(h->b_split), n_split, n_slots, d_ctr);
+            CKK();
+            st.jump_rounds++;
+            if ((r & 7) == 7 || r == max_rounds - 1) {      // look every 8 rounds whether it has converged
+                TRY(check_fault(h, "k_jump"));
+                if (!h->ctr.changed) break;
+                CK(cudaMemsetAsync(&d_ctr->changed, 0, 4, h->stream));
+            }
+        }
     }
     const int e1 = ev_mark(h);
 
@@ -646,7 +663,7 @@ DBG_API void dbg_destroy(dbg_t *h) {
     DevBuf *all[] = {&h->b_bases, &h->b_off, &h->b_packed, &h->b_tile, &h->b_table, &h->b_flags, &h->b_kept,
                      &h->b_succ, &h->b_link, &h->b_ctr, &h->b_hll, &h->b_order, &h->b_tag, &h->b_tag2, &h->b_slot,
                      &h->b_slot2, &h->b_sorttmp, &h->b_branch, &h->b_starts, &h->b_pulled, &h->b_readflags,
-                     &h->b_recs, &h->b_cnt32, &h->b_off64, &h->b_contig, &h->b_junction, &h->b_scratch[0],
+                     &h->b_recs, &h->b_cnt32, &h->b_off64, &h->b_contig, &h->b_junction, &h->b_split, &h->b_scratch[0],
                      &h->b_scratch[1], &h->b_scratch[2], &h->b_scratch[3], &h->b_scratch[4], &h->b_scratch[5]};
     for (DevBuf *b : all) if (b->p) cudaFree(b->p);
     for (int i = 0; i < EV_MAX; i++) cudaEventDestroy(h->ev[i]);

@@ -7,7 +7,7 @@
 //   tie order     debruijn.py:159-164  (Counter.most_common)        k_order_fill/scan/apply
 //   tip pruning   debruijn.py:169-186  (candidate paths)            k_tip_paths
 //   pull-out      debruijn.py:274-278                                k_pull_reads
-//   contig walk   debruijn.py:288-316, 326-347                      k_link_init, k_jump, k_emit
+//   contig walk   debruijn.py:288-316, 326-347                      k_link_init, k_sublist, k_jump, k_emit
 //   strings       debruijn.py:298-300                                k_materialize
 //   getScore      II_assembleFromReads.py:14-18                      k_scores, k_lookup_edges
 #pragma once
@@ -435,41 +435,124 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_pull_reads(const u64 *__restrict_
 }
 
 // ---------------------------------------------------------------------------------------------
-// Contig walk as list ranking.  link[v] = (dist << 32 | next): next == v marks a root.  Roots
-// are the nodes at which the reference's DFS stops (debruijn.py:292, :304): pulled nodes,
-// nodes without successor, nodes with > 1 kept successor.  Every other node has exactly one
-// kept successor.  k_jump halves the remaining distance per round (pointer jumping, in place:
-// the 64-bit (next, dist) pair is read and written as one word, so any interleaving is a
-// valid earlier or later state of the same chain).  A node that still does not point at a
-// root after ceil(log2(n)) + 1 rounds sits on, or leads into, a cycle (debruijn.py:289); a
-// self-loop (AAAA -> AAAA) has next == self but dist 1, so "root" always means link == (v, 0).
+// Contig walk as list ranking (debruijn.py:288-316 without the recursion).
+//
+// link[v] = SPLIT | dist << 32 | next, "dist hops from v lead to next".  Roots are the nodes at
+// which the reference's DFS stops (debruijn.py:292, :304): pulled nodes, nodes without successor,
+// nodes with > 1 kept successor; a root is link == (v, 0).  Every other node ("chain node") has
+// exactly one kept successor.  Only the START nodes need an answer (one contig per start,
+// debruijn.py:331-345), so instead of pointer-jumping all n nodes for log n rounds (O(n log n)
+// sector traffic) the chain is cut at SPLITTERS -- every start plus a 1/2^WALK_SPLIT_LOG2 hash
+// sample of the chain nodes:
+//   k_link_init  writes the links, flags splitters, compacts them into a list
+//   k_sublist    one thread per splitter walks to the next splitter or root (expected 2^LOG2 hops,
+//                L2-resident 8-byte reads) and stores (that node, hops) in its own link
+//   k_jump       pointer jumping over the splitter list only (n / 2^LOG2 + starts elements)
+// The 64-bit (next, dist) pair is read and written as one word, so in k_jump any interleaving
+// reads a valid earlier or later state of the same chain.  A start that never reaches a root sits
+// on, or leads into, a cycle (debruijn.py:289: nothing is emitted): k_sublist finds splitter-free
+// cycles with Brent's checkpointing and marks the splitter as its own target; cycles through
+// splitters are what is left not pointing at a root after ceil(log2(m)) + 2 rounds.
 // ---------------------------------------------------------------------------------------------
+#define WALK_SPLIT_LOG2 5
+#define LINK_SPLIT 0x8000000000000000ULL
+#define LINK_DIST_MAX 0x7FFFFFFFu
 DBG_HD u64 link_pack(u32 next, u32 dist) { return ((u64)dist << 32) | next; }
 DBG_HD u32 link_next(u64 l) { return (u32)l; }
-DBG_HD u32 link_dist(u64 l) { return (u32)(l >> 32); }
+DBG_HD u32 link_dist(u64 l) { return (u32)(l >> 32) & LINK_DIST_MAX; }
 DBG_HD bool link_is_root(u64 l, u32 v) { return l == (u64)v; }
+DBG_HD u32 link_dist_add(u32 a, u32 b) { u64 s = (u64)a + b; return s > LINK_DIST_MAX ? LINK_DIST_MAX : (u32)s; }
+DBG_HD u32 hash32(u32 x) { x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16; return x; }
 
 __global__ void __launch_bounds__(DBG_BLOCK) k_link_init(const u8 *__restrict__ flags, const u16 *__restrict__ kept,
-                                                         const u32 *__restrict__ succ, u64 n_slots, u64 *link) {
+                                                         const u32 *__restrict__ succ, u64 n_slots, u64 *link,
+                                                         u32 *__restrict__ split_list, u64 split_cap, u64 *cursor) {
     u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_slots) return;
-    u32 f = flags[i];
-    bool chain = (f & F_OCC) && !(f & F_PULLED) && kept_count(kept[i]) == 1;
-    link[i] = chain ? link_pack(succ[i], 1) : link_pack((u32)i, 0);
+    bool split = false;
+    if (i < n_slots) {
+        u32 f = flags[i];
+        bool chain = (f & F_OCC) && !(f & F_PULLED) && kept_count(kept[i]) == 1;
+        split = chain && ((f & F_START) || (hash32((u32)i) & ((1u << WALK_SPLIT_LOG2) - 1)) == 0);
+        link[i] = chain ? (link_pack(succ[i], 1) | (split ? LINK_SPLIT : 0)) : link_pack((u32)i, 0);
+    }
+    u32 b = __ballot_sync(0xFFFFFFFFu, split);
+    if (!b) return;
+    u32 lane = threadIdx.x & 31;
+    u64 base = 0;
+    if (lane == 0) base = atomicAdd(cursor, (u64)__popc(b));
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    if (split) {
+        u64 o = base + __popc(b & ((1u << lane) - 1));
+        if (o < split_cap) split_list[o] = (u32)i;
+    }
 }
 
-__global__ void __launch_bounds__(DBG_BLOCK) k_jump(u64 *link, u64 n_slots, DevCounters *ctr) {
-    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_slots) return;
-    u64 l = __ldcg(&link[i]);
-    u32 nx = link_next(l);
-    if (nx == (u32)i) return;                       // root (dist 0) or a self-loop (dist > 0)
-    if (nx >= n_slots) { raise_fault(ctr, FAULT_JUMP_RANGE, (u32)i); return; }
-    u64 ln = __ldcg(&link[nx]);
-    u32 nn = link_next(ln);
-    if (nn == nx) return;                           // points at a root / self-loop: final
-    __stcg(&link[i], link_pack(nn, link_dist(l) + link_dist(ln)));
-    ctr->changed = 1;
+// walk from chain node `from` (exclusive) to the first splitter or root; returns that node and
+// the hop count, or NONE32 when the walk is caught in a splitter-free cycle
+DBG_D u32 walk_to_splitter(const u64 *link, u32 from_next, u32 *hops) {
+    u32 cur = from_next, d = 1;
+    u32 check = cur, power = 1, lam = 0;              // Brent: checkpoint every power of two
+    for (;;) {
+        u64 l = __ldcg(&link[cur]);
+        if ((l & LINK_SPLIT) || link_is_root(l, cur)) { *hops = d; return cur; }
+        cur = link_next(l);
+        d = link_dist_add(d, 1);
+        if (cur == check) return NONE32;
+        if (++lam == power) { check = cur; power <<= 1; lam = 0; }
+    }
+}
+
+__global__ void __launch_bounds__(DBG_BLOCK) k_sublist(u64 *link, const u32 *__restrict__ split_list, u64 n_split) {
+    u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_split) return;
+    u32 v = split_list[j];
+    u32 first = link_next(__ldcg(&link[v]));
+    u32 hops = 0;
+    u32 t = first == v ? NONE32 : walk_to_splitter(link, first, &hops);     // first == v: self loop
+    // only this thread writes link[v]; walkers that pass by only look at its SPLIT bit
+    __stcg(&link[v], t == NONE32 ? (LINK_SPLIT | link_pack(v, LINK_DIST_MAX)) : (LINK_SPLIT | link_pack(t, hops)));
+}
+
+__global__ void __launch_bounds__(DBG_BLOCK) k_jump(u64 *link, const u32 *__restrict__ split_list, u64 n_split,
+                                                    u64 n_slots, DevCounters *ctr) {
+    u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    bool changed = false;
+    if (j < n_split) {
+        u32 v = split_list[j];
+        u64 l = __ldcg(&link[v]);
+        u32 nx = link_next(l);
+        if (nx != v) {                                  // nx == v: marked cycle
+            if (nx >= n_slots) raise_fault(ctr, FAULT_JUMP_RANGE, v);
+            else {
+                u64 ln = __ldcg(&link[nx]);
+                u32 nn = link_next(ln);
+                if ((ln & LINK_SPLIT) && nn != nx) {    // else nx is a root (final) or a marked cycle
+                    __stcg(&link[v], LINK_SPLIT | link_pack(nn, link_dist_add(link_dist(l), link_dist(ln))));
+                    changed = true;
+                }
+            }
+        }
+    }
+    // one store per warp: a store per thread to the same word serialises in L2
+    if (__any_sync(0xFFFFFFFFu, changed) && (threadIdx.x & 31) == 0) ctr->changed = 1;
+}
+
+// (terminal, hops) of an arbitrary node after k_jump has converged
+DBG_D bool resolve_chain(const u64 *link, u32 v, u32 *terminal, u32 *hops) {
+    u64 l = __ldcg(&link[v]);
+    u32 d = 0, w = v;
+    if (!link_is_root(l, v) && !(l & LINK_SPLIT)) {          // plain chain node: reach a splitter first
+        u32 first = link_next(l);
+        if (first == v) return false;
+        w = walk_to_splitter(link, first, &d);
+        if (w == NONE32) return false;
+        l = __ldcg(&link[w]);
+    }
+    if (link_is_root(l, w)) { *terminal = w; *hops = d; return true; }
+    u32 t = link_next(l);
+    if (!link_is_root(__ldcg(&link[t]), t)) return false;    // cycle
+    *terminal = t; *hops = link_dist_add(d, link_dist(l));
+    return true;
 }
 
 struct ContigRec {          // one per start, in start order; kind T_CYCLE / n_nodes 0 = nothing emitted
@@ -482,12 +565,12 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_emit(const u32 *__restrict__ star
     u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_starts) return;
     u32 s = starts[i];
-    u64 l = link[s];
-    u32 t = link_next(l), d = link_dist(l);
+    u32 t = s, d = 0;
     ContigRec c;
-    c.start = s; c.terminal = t;
-    if (!link_is_root(link[t], t)) { c.kind = T_CYCLE; c.n_nodes = 0; }
+    c.start = s;
+    if (!resolve_chain(link, s, &t, &d)) { c.terminal = t; c.kind = T_CYCLE; c.n_nodes = 0; }
     else {
+        c.terminal = t;
         u32 f = flags[t];
         if (f & F_PULLED) { c.kind = T_PULLED; c.n_nodes = d; }          // path stops in front of t
         else { c.kind = (f & F_DEADEND) ? T_DEADEND : T_BRANCH; c.n_nodes = d + 1; }
@@ -518,13 +601,12 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_junctions(const Slot<W> *__restri
             K sk = key_roll(key, (u32)kept_base(word, j), key_mask<W>(k));
             u64 fi = table_find<W>(table, n_slots, sk);
             if (fi == NONE64) { raise_fault(ctr, FAULT_JUNCTION_MISSING, v); out[b * 4 + j] = js; continue; }
-            u32 s = (u32)fi;
-            u64 l = link[s];
-            u32 t = link_next(l);
-            js.entry = s; js.n_hops = link_dist(l); js.terminal = t;
-            if (!link_is_root(link[t], t)) js.kind = T_CYCLE;
+            u32 s = (u32)fi, t = s, d = 0;
+            js.entry = s;
+            if (!resolve_chain(link, s, &t, &d)) js.kind = T_CYCLE;
             else {
                 u32 f = flags[t];
+                js.n_hops = d; js.terminal = t;
                 js.kind = (f & F_PULLED) ? T_PULLED : (f & F_DEADEND) ? T_DEADEND : T_BRANCH;
             }
         }
