@@ -80,6 +80,8 @@ typedef struct {
     uint64_t n_launches;     /* kernels this library launched in the last dbg_build* + dbg_walk */
     uint32_t key_words;      /* 1 (k <= 31) or 2                                              */
     uint32_t jump_rounds;    /* pointer-jumping rounds run by dbg_walk                        */
+    uint32_t n_insert_passes;/* L2-resident partition passes of the table build               */
+    uint32_t reserved0;
     /* device time per stage, CUDA events on the handle's stream, milliseconds */
     float ms_h2d, ms_pack, ms_estimate, ms_table_init, ms_insert, ms_finalize, ms_order,
           ms_lists, ms_tips, ms_pull_reads, ms_build_total, ms_walk_rank, ms_walk_emit,

@@ -40,6 +40,7 @@
 #define DBG_ABI_VERSION 1
 #define MAX_ENUM_CONTIGS (1ull << 26)
 #define MAX_ENUM_STEPS (1ull << 32)
+#define L2_REGION_BYTES (72ull << 20)        // table bytes one insert pass may touch (B200 L2: 126 MB)
 
 // -------------------------------------------------------------------------------------------------
 // handle
@@ -324,9 +325,24 @@ static int build_impl(dbg_t *h, const u8 *d_bases, const u64 *d_off) {
         CKK();
         const int b = ev_mark(h);
         if (st.n_windows) {
-            LAUNCH(k_insert<W>, h->n_tiles, DBG_BLOCK, h->stream, ptr<const u64>(h->b_packed), d_off,
-                   ptr<const u32>(h->b_tile), h->n_bases, k, ptr<S>(h->b_table), n_slots, h->read_idx_base, d_ctr);
-            CKK();
+            // partition passes: each pass owns a hash range whose table region stays L2-resident
+            uint64_t region = (uint64_t)L2_REGION_BYTES;
+            if (const char *e = getenv("DBG_B200_L2_REGION_BYTES")) {     // tuning / tests: force more passes
+                const unsigned long long v = strtoull(e, nullptr, 10);
+                if (v >= 64) region = v;
+            }
+            uint32_t n_parts = (uint32_t)cdiv(n_slots * sizeof(S), region);
+            if (n_parts < 1) n_parts = 1;
+            if (n_parts > 64) n_parts = 64;
+            st.n_insert_passes = n_parts;
+            for (uint32_t part = 0; part < n_parts; part++) {
+                const uint32_t h_lo = (uint32_t)(((uint64_t)part << 32) / n_parts);
+                const uint32_t h_hi = part + 1 == n_parts ? 0xFFFFFFFFu : (uint32_t)((((uint64_t)(part + 1)) << 32) / n_parts) - 1;
+                LAUNCH(k_insert<W>, h->n_tiles, DBG_BLOCK, h->stream, ptr<const u64>(h->b_packed), d_off,
+                       ptr<const u32>(h->b_tile), h->n_bases, k, ptr<S>(h->b_table), n_slots, h->read_idx_base,
+                       h_lo, h_hi, d_ctr);
+                CKK();
+            }
         }
         const int c = ev_mark(h);
         TRY(fetch_counters(h));

@@ -28,6 +28,7 @@ typedef unsigned char u8;
 #define F_MULTI   0x20u
 
 #define NONE32 0xFFFFFFFFu
+#define NONE64 0xFFFFFFFFFFFFFFFFULL
 
 // 128-bit keys are two explicit 64-bit words with hand-written shifts.  (nvcc 12.9 miscompiles
 // rolling `unsigned __int128` shifts inside the unrolled window loop for sm_100a -- bits carried
@@ -114,6 +115,12 @@ DBG_HD u64 fmix64(u64 x) {
 DBG_HD u64 hash_key(u64 k) { return fmix64(k + 0x9e3779b97f4a7c15ULL); }
 DBG_HD u64 hash_key(K128 k) { return fmix64(k.lo ^ fmix64(k.hi + 0x9e3779b97f4a7c15ULL)); }
 
+// slot hash: multiply-shift, top 32 bits of a 64-bit product (3 IMADs for 64-bit keys); the home
+// slot is (h * n_slots) >> 32, one IMAD.WIDE, so n_slots must stay below 2^32 (node ids are 32 bit)
+DBG_HD u32 hash32_key(u64 k) { return (u32)((k * 0x9E3779B97F4A7C15ULL) >> 32); }
+DBG_HD u32 hash32_key(K128 k) { return (u32)((k.lo * 0x9E3779B97F4A7C15ULL + k.hi * 0xC2B2AE3D27D4EB4FULL) >> 32); }
+DBG_HD u64 slot_home(u32 h, u64 n_slots) { return ((u64)h * n_slots) >> 32; }
+
 DBG_HD u64 mulhi64(u64 a, u64 b) {
 #if defined(__CUDA_ARCH__) || defined(DBG_EMU)
     return __umul64hi(a, b);
@@ -128,6 +135,15 @@ DBG_HD u64 mulhi64(u64 a, u64 b) {
 // ---------------------------------------------------------------------------------------------
 DBG_D u32 base_at(const u64 *__restrict__ packed, u64 i) {
     return (u32)(__ldg(packed + (i >> 5)) >> (62 - 2 * (i & 31))) & 3u;
+}
+
+// n <= 16 bases starting at base index p, right-aligned in 32 bits (first base most significant)
+DBG_D u32 extract_bases(const u64 *__restrict__ packed, u64 p, int n) {
+    u64 w = p >> 5;
+    int s = 2 * (int)(p & 31);
+    u64 w0 = __ldg(packed + w), w1 = __ldg(packed + w + 1);
+    u64 top = s ? ((w0 << s) | (w1 >> (64 - s))) : w0;
+    return (u32)(top >> (64 - 2 * n));
 }
 
 // k bases starting at base index p, as a right-aligned integer
@@ -182,13 +198,45 @@ DBG_D K128 cas_key(K128 *addr, K128 expect, K128 val) {
     return old;
 }
 
+// key and first-occurrence tag of a slot in ONE 16-byte L2 request (k <= 31), or key then tag
+DBG_D u64 load_key_tag(const Slot<1> *s, u64 *tag) {
+    ulonglong2 v = __ldcg(reinterpret_cast<const ulonglong2 *>(s));
+    *tag = v.y;
+    return v.x;
+}
+DBG_D K128 load_key_tag(const Slot<2> *s, u64 *tag) {
+    K128 r = load_key(s);
+    *tag = __ldcg(&s->tag);
+    return r;
+}
+
+// find-or-insert starting at the key's home slot; also returns the tag the slot held when it was
+// read (~0 for a slot this call created).  NONE64 when the table is full.
+template <int W>
+DBG_D u64 table_upsert_tag(Slot<W> *table, u64 n_slots, u64 home, typename KeyOf<W>::type key, u64 *tag_seen) {
+    typedef typename KeyOf<W>::type K;
+    const K EMPTY = empty_key<W>();
+    u64 idx = home;
+    for (u64 probes = 0; probes < n_slots; ++probes) {
+        u64 t;
+        K cur = load_key_tag(&table[idx], &t);
+        if (cur == key) { *tag_seen = t; return idx; }
+        if (cur == EMPTY) {
+            K old = cas_key(&table[idx].key, EMPTY, key);
+            if (old == EMPTY) { *tag_seen = ~0ULL; return idx; }
+            if (old == key) { *tag_seen = __ldcg(&table[idx].tag); return idx; }
+        }
+        if (++idx == n_slots) idx = 0;
+    }
+    return NONE64;
+}
+
 // find-or-insert; returns slot index or NONE64 when the table is full
-#define NONE64 0xFFFFFFFFFFFFFFFFULL
 template <int W>
 DBG_D u64 table_upsert(Slot<W> *table, u64 n_slots, typename KeyOf<W>::type key) {
     typedef typename KeyOf<W>::type K;
     const K EMPTY = empty_key<W>();
-    u64 idx = mulhi64(hash_key(key), n_slots);
+    u64 idx = slot_home(hash32_key(key), n_slots);
     for (u64 probes = 0; probes < n_slots; ++probes) {
         K cur = load_key(&table[idx]);
         if (cur == key) return idx;
@@ -205,7 +253,7 @@ template <int W>
 DBG_D u64 table_find(const Slot<W> *table, u64 n_slots, typename KeyOf<W>::type key) {
     typedef typename KeyOf<W>::type K;
     const K EMPTY = empty_key<W>();
-    u64 idx = mulhi64(hash_key(key), n_slots);
+    u64 idx = slot_home(hash32_key(key), n_slots);
     for (u64 probes = 0; probes < n_slots; ++probes) {
         K cur = load_key(&table[idx]);
         if (cur == key) return idx;

@@ -14,7 +14,7 @@
 #include "dbg_common.cuh"
 
 #define DBG_BLOCK 256
-#define DBG_WPT 8                          // consecutive windows per thread
+#define DBG_WPT 16                         // consecutive windows per thread
 #define DBG_TILE (DBG_BLOCK * DBG_WPT)     // base positions per block
 #define HLL_P 12
 #define HLL_M (1 << HLL_P)
@@ -142,8 +142,8 @@ template <int W, bool BUILD, typename F>
 DBG_D void for_windows(const u64 *__restrict__ packed, const u64 *__restrict__ off,
                        const u32 *__restrict__ tile_first, u64 n_bases, int k, F f) {
     typedef typename KeyOf<W>::type K;
-    u64 tile = blockIdx.x;
-    u64 p0 = tile * DBG_TILE + (u64)threadIdx.x * DBG_WPT;
+    const u64 tile = blockIdx.x;
+    const u64 p0 = tile * DBG_TILE + (u64)threadIdx.x * DBG_WPT;
     if (p0 >= n_bases) return;
     u32 rlo = __ldg(tile_first + tile), rhi = __ldg(tile_first + tile + 1);
     while (rlo < rhi) {
@@ -154,15 +154,26 @@ DBG_D void for_windows(const u64 *__restrict__ packed, const u64 *__restrict__ o
     u64 rs = __ldg(off + r), re = __ldg(off + r + 1);
     const K mask = key_mask<W>(k);
     K key = extract_key<W>(packed, p0, k);
+    const u32 nbw = extract_bases(packed, p0 + k, DBG_WPT);      // the DBG_WPT bases that follow the first k-mer
+    // everything below is 32-bit arithmetic relative to p0
+    const int n_here = (int)(n_bases - p0 < (u64)DBG_WPT ? n_bases - p0 : (u64)DBG_WPT);
+    int end = (int)(re - p0 < (u64)(1 << 30) ? re - p0 : (u64)(1 << 30));      // read end, relative
+    u32 pos0 = (u32)(p0 - rs);                                   // position in read of relative 0 (wraps if the
+    bool long_enough = re - rs > (u64)k;                         // read starts later: fixed when it does)
 #pragma unroll
     for (int j = 0; j < DBG_WPT; j++) {
-        u64 p = p0 + j;
-        if (p >= n_bases) break;
-        while (p >= re) { r++; rs = re; re = __ldg(off + r + 1); }      // also skips empty reads
-        u64 len = re - rs, pos = p - rs;
-        u32 nb = base_at(packed, p + k);
-        bool ok = BUILD ? (len > (u64)k && pos + k <= len) : (pos + k <= len);
-        if (ok) f(key, r, pos, pos + k < len, nb);
+        if (j >= n_here) break;
+        while (j >= end) {                                       // next read (also skips empty reads)
+            r++;
+            const u64 ne = __ldg(off + r + 1);
+            long_enough = ne - re > (u64)k;
+            pos0 = (u32)0 - (u32)end;                            // read starts at relative `end`
+            end = (int)(ne - p0 < (u64)(1 << 30) ? ne - p0 : (u64)(1 << 30));
+            re = ne;
+        }
+        const u32 nb = (nbw >> (2 * (DBG_WPT - 1 - j))) & 3u;
+        const bool ok = BUILD ? (long_enough && j + k <= end) : (j + k <= end);
+        if (ok) f(key, r, pos0 + (u32)j, j + k < end, nb);
         key = key_roll(key, nb, mask);
     }
 }
@@ -178,10 +189,10 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_estimate(const u64 *__restrict__ 
                                                         u32 *regs) {
     typedef typename KeyOf<W>::type K;
     for_windows<W, true>(packed, off, tile_first, n_bases, k,
-        [&](K key, u32, u64, bool, u32) {
-            u64 h = hash_key(key);
-            u32 idx = (u32)(h >> (64 - HLL_P));
-            u32 rank = (u32)__clzll((long long)((h << HLL_P) | (1ULL << (HLL_P - 1)))) + 1;
+        [&](K key, u32, u32, bool, u32) {
+            u32 h = hash32_key(key);
+            u32 idx = h >> (32 - HLL_P);
+            u32 rank = (u32)__clz((int)((h << HLL_P) | (1u << (HLL_P - 1)))) + 1;
             if (regs[idx] < rank) atomicMax(&regs[idx], rank);
         });
 }
@@ -200,19 +211,28 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_table_init(Slot<W> *table, u64 n_
     table[i] = s;
 }
 
+// Partition passes: the table (32 B x 2 slots per node) is larger than the 126 MB L2 for any
+// genome above ~2 Mb, and a random 32-byte slot touch that misses L2 costs a 64-byte DRAM burst in
+// and, later, a dirty sector out (measured: 9.7 GB of DRAM traffic for 99 M windows, 2.2 TB/s).
+// So the windows are replayed n_parts times; pass `part` only touches keys whose home slot lies in
+// [part, part + 1) * n_slots / n_parts, a region sized to stay L2-resident, and the rolling key +
+// multiply-shift hash of the other windows (about 25 instructions) is all those cost.
 template <int W>
 __global__ void __launch_bounds__(DBG_BLOCK) k_insert(const u64 *__restrict__ packed, const u64 *__restrict__ off,
                                                       const u32 *__restrict__ tile_first, u64 n_bases, int k,
                                                       Slot<W> *table, u64 n_slots, u64 read_idx_base,
-                                                      DevCounters *ctr) {
+                                                      u32 h_lo, u32 h_hi, DevCounters *ctr) {
     typedef typename KeyOf<W>::type K;
     for_windows<W, true>(packed, off, tile_first, n_bases, k,
-        [&](K key, u32 r, u64 pos, bool has_next, u32 nb) {
-            u64 idx = table_upsert<W>(table, n_slots, key);
+        [&](K key, u32 r, u32 pos, bool has_next, u32 nb) {
+            const u32 h = hash32_key(key);
+            if (h < h_lo || h > h_hi) return;                            // another pass owns this key
+            u64 seen;
+            u64 idx = table_upsert_tag<W>(table, n_slots, slot_home(h, n_slots), key, &seen);
             if (idx == NONE64) { ctr->overflow = 1; return; }
             Slot<W> *s = &table[idx];
             u64 tag = ((read_idx_base + r) << 32) | pos;
-            if (tag < __ldcg(&s->tag)) atomicMin(&s->tag, tag);          // first occurrence
+            if (tag < seen) atomicMin(&s->tag, tag);                     // first occurrence
             if (has_next) atomicAdd(&s->cnt[nb], 1u);                    // debruijn.py:132/136
         });
 }
@@ -305,7 +325,7 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_order_scan(const u64 *__restrict_
                                                           OrderEntry *ot, u64 cap, DevCounters *ctr) {
     typedef typename KeyOf<W>::type K;
     for_windows<W, true>(packed, off, tile_first, n_bases, k,
-        [&](K key, u32 r, u64 pos, bool has_next, u32 nb) {
+        [&](K key, u32 r, u32 pos, bool has_next, u32 nb) {
             if (!has_next) return;
             u64 idx = table_find<W>(table, n_slots, key);
             if (idx == NONE64 || !(flags[idx] & F_MULTI)) return;
@@ -428,7 +448,7 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_pull_reads(const u64 *__restrict_
                                                           const u8 *__restrict__ flags, u8 *read_flags) {
     typedef typename KeyOf<W>::type K;
     for_windows<W, false>(packed, off, tile_first, n_bases, k,
-        [&](K key, u32 r, u64, bool, u32) {
+        [&](K key, u32 r, u32, bool, u32) {
             u64 idx = table_find<W>(table, n_slots, key);
             if (idx != NONE64 && (flags[idx] & F_BRANCH)) read_flags[r] = 1;
         });

@@ -39,7 +39,8 @@ class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         'n_reads', 'n_bases', 'n_windows', 'n_nodes', 'n_edges', 'n_multi', 'n_branch', 'n_starts',
         'n_pulled', 'n_pull_reads', 'n_contigs', 'n_cycle_starts', 'table_slots', 'table_bytes',
-        'hll_estimate', 'n_launches')] + [('key_words', C.c_uint32), ('jump_rounds', C.c_uint32)] + [
+        'hll_estimate', 'n_launches')] + [('key_words', C.c_uint32), ('jump_rounds', C.c_uint32), ('n_insert_passes', C.c_uint32),
+                                           ('reserved0', C.c_uint32)] + [
         (n, C.c_float) for n in (
             'ms_h2d', 'ms_pack', 'ms_estimate', 'ms_table_init', 'ms_insert', 'ms_finalize',
             'ms_order', 'ms_lists', 'ms_tips', 'ms_pull_reads', 'ms_build_total', 'ms_walk_rank',

@@ -33,7 +33,7 @@ def test_cuda_library_exports_every_symbol():
 def test_struct_layouts_match_header():
     assert ctypes.sizeof(_native.Contig) == 32
     assert ctypes.sizeof(_native.Segment) == 8
-    assert ctypes.sizeof(_native.Stats) == 16 * 8 + 2 * 4 + 14 * 4
+    assert ctypes.sizeof(_native.Stats) == 16 * 8 + 4 * 4 + 14 * 4
 
 
 def test_product_refuses_to_run_without_a_gpu():

@@ -188,3 +188,18 @@ def test_descriptors_scores_and_lookup(backend):
     got = g.lookup_edges(qs).tolist()
     assert got == [ect.get(q, 0) for q in qs]
     g.close()
+
+
+def test_partition_passes(backend, monkeypatch):
+    """The table build replays the windows once per L2-sized table region; force many passes."""
+    from dbg_b200 import Graph
+    monkeypatch.setenv('DBG_B200_L2_REGION_BYTES', '4096')
+    _, reads = util.synth_reads(21, 4000, 70, 12, err=0.01)
+    for k in (19, 41):
+        exp = dbg_oracle.snapshot(reads, k, 2, False)
+        got = util.product_snapshot(reads, k, 2, False)
+        util.assert_same(got, exp, 'partition passes k=%d' % k)
+        g = Graph(k)
+        g.build(reads, threshold=2)
+        assert g.stats().n_insert_passes > 8
+        g.close()
