@@ -338,9 +338,10 @@ static int build_impl(dbg_t *h, const u8 *d_bases, const u64 *d_off) {
             for (uint32_t part = 0; part < n_parts; part++) {
                 const uint32_t h_lo = (uint32_t)(((uint64_t)part << 32) / n_parts);
                 const uint32_t h_hi = part + 1 == n_parts ? 0xFFFFFFFFu : (uint32_t)((((uint64_t)(part + 1)) << 32) / n_parts) - 1;
+                const uint32_t h_span = h_hi - h_lo;
                 LAUNCH(k_insert<W>, h->n_tiles, DBG_BLOCK, h->stream, ptr<const u64>(h->b_packed), d_off,
                        ptr<const u32>(h->b_tile), h->n_bases, k, ptr<S>(h->b_table), n_slots, h->read_idx_base,
-                       h_lo, h_hi, d_ctr);
+                       h_lo, h_span, d_ctr);
                 CKK();
             }
         }

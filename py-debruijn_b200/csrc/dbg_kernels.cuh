@@ -178,6 +178,54 @@ DBG_D void for_windows(const u64 *__restrict__ packed, const u64 *__restrict__ o
     }
 }
 
+// Warp-uniform variant for the hot kernels: every lane calls f for all DBG_WPT steps, with
+// `valid` false where the position is not a node occurrence, so f may use warp collectives.
+// The read-boundary bookkeeping is 32-bit and relative to the thread's first position.
+template <int W, typename F>
+DBG_D void for_windows_uniform(const u64 *__restrict__ packed, const u64 *__restrict__ off,
+                               const u32 *__restrict__ tile_first, u64 n_bases, int k, F f) {
+    typedef typename KeyOf<W>::type K;
+    const u64 tile = blockIdx.x;
+    u64 p0 = tile * DBG_TILE + (u64)threadIdx.x * DBG_WPT;
+    int n_here = 0;                                               // positions of this thread inside the stream
+    if (p0 < n_bases) n_here = (int)(n_bases - p0 < (u64)DBG_WPT ? n_bases - p0 : (u64)DBG_WPT);
+    else p0 = 0;                                                  // idle lane: harmless loads, never valid
+    u32 rlo = __ldg(tile_first + tile), rhi = __ldg(tile_first + tile + 1);
+    if (n_here == 0) rlo = rhi = 0;
+    while (rlo < rhi) {
+        u32 mid = rlo + ((rhi - rlo + 1) >> 1);
+        if (__ldg(off + mid) <= p0) rlo = mid; else rhi = mid - 1;
+    }
+    u32 r = rlo;
+    const u64 rs = __ldg(off + r);
+    u64 re = __ldg(off + r + 1);
+    const K mask = key_mask<W>(k);
+    K key = extract_key<W>(packed, p0, k);
+    const u32 nbw = extract_bases(packed, p0 + k, DBG_WPT);
+    const u64 CLAMP = 1u << 30;
+    int end = (int)(re - p0 < CLAMP ? re - p0 : CLAMP);           // read end, relative to p0
+    u32 pos0 = (u32)(p0 - rs);
+    bool long_enough = re - rs > (u64)k;
+    int lim = long_enough ? end - k : -1;                         // node occurrence iff j <= lim; edge iff j < lim
+#pragma unroll
+    for (int j = 0; j < DBG_WPT; j++) {
+        if (j == end && j < n_here) {                             // rare: a read ends inside this thread's span
+            do {
+                r++;
+                const u64 ne = __ldg(off + r + 1);
+                long_enough = ne - re > (u64)k;
+                pos0 = (u32)0 - (u32)end;
+                end = (int)(ne - p0 < CLAMP ? ne - p0 : CLAMP);
+                re = ne;
+            } while (j >= end);                                   // skips empty reads
+            lim = long_enough ? end - k : -1;
+        }
+        const u32 nb = (nbw >> (2 * (DBG_WPT - 1 - j))) & 3u;
+        f(j, j <= lim && j < n_here, key, r, pos0 + (u32)j, j < lim, nb);
+        key = key_roll(key, nb, mask);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // k_estimate: HyperLogLog over node keys (2^12 registers) -> distinct-node estimate that sizes
 // the table.  Registers saturate after a few thousand keys, so almost every window is a plain
@@ -188,12 +236,12 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_estimate(const u64 *__restrict__ 
                                                         const u32 *__restrict__ tile_first, u64 n_bases, int k,
                                                         u32 *regs) {
     typedef typename KeyOf<W>::type K;
-    for_windows<W, true>(packed, off, tile_first, n_bases, k,
-        [&](K key, u32, u32, bool, u32) {
+    for_windows_uniform<W>(packed, off, tile_first, n_bases, k,
+        [&](int, bool valid, K key, u32, u32, bool, u32) {
             u32 h = hash32_key(key);
             u32 idx = h >> (32 - HLL_P);
             u32 rank = (u32)__clz((int)((h << HLL_P) | (1u << (HLL_P - 1)))) + 1;
-            if (regs[idx] < rank) atomicMax(&regs[idx], rank);
+            if (valid && regs[idx] < rank) atomicMax(&regs[idx], rank);
         });
 }
 
@@ -217,24 +265,63 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_table_init(Slot<W> *table, u64 n_
 // So the windows are replayed n_parts times; pass `part` only touches keys whose home slot lies in
 // [part, part + 1) * n_slots / n_parts, a region sized to stay L2-resident, and the rolling key +
 // multiply-shift hash of the other windows (about 25 instructions) is all those cost.
+// Each warp compacts the windows the pass owns into a 64-entry shared-memory ring and drains it
+// 32 at a time, so the table probes and atomics always run with all 32 lanes busy no matter how
+// few windows of a given iteration the pass owns.
+#define DBG_WARPS (DBG_BLOCK / 32)
+#define DBG_QCAP 64
+template <int W> struct WarpQueue {
+    typename KeyOf<W>::type key[DBG_WARPS][DBG_QCAP];
+    u64 tag[DBG_WARPS][DBG_QCAP];
+    u8 meta[DBG_WARPS][DBG_QCAP];          // has_next << 2 | next base
+};
+
+template <int W>
+DBG_D void insert_one(Slot<W> *table, u64 n_slots, typename KeyOf<W>::type key, u64 tag, u32 meta, DevCounters *ctr) {
+    u64 seen;
+    u64 idx = table_upsert_tag<W>(table, n_slots, slot_home(hash32_key(key), n_slots), key, &seen);
+    if (idx == NONE64) { ctr->overflow = 1; return; }
+    Slot<W> *s = &table[idx];
+    if (tag < seen) atomicMin(&s->tag, tag);                             // first occurrence
+    if (meta & 4u) atomicAdd(&s->cnt[meta & 3u], 1u);                    // debruijn.py:132/136
+}
+
 template <int W>
 __global__ void __launch_bounds__(DBG_BLOCK) k_insert(const u64 *__restrict__ packed, const u64 *__restrict__ off,
                                                       const u32 *__restrict__ tile_first, u64 n_bases, int k,
                                                       Slot<W> *table, u64 n_slots, u64 read_idx_base,
-                                                      u32 h_lo, u32 h_hi, DevCounters *ctr) {
+                                                      u32 h_lo, u32 h_span, DevCounters *ctr) {
     typedef typename KeyOf<W>::type K;
-    for_windows<W, true>(packed, off, tile_first, n_bases, k,
-        [&](K key, u32 r, u32 pos, bool has_next, u32 nb) {
-            const u32 h = hash32_key(key);
-            if (h < h_lo || h > h_hi) return;                            // another pass owns this key
-            u64 seen;
-            u64 idx = table_upsert_tag<W>(table, n_slots, slot_home(h, n_slots), key, &seen);
-            if (idx == NONE64) { ctr->overflow = 1; return; }
-            Slot<W> *s = &table[idx];
-            u64 tag = ((read_idx_base + r) << 32) | pos;
-            if (tag < seen) atomicMin(&s->tag, tag);                     // first occurrence
-            if (has_next) atomicAdd(&s->cnt[nb], 1u);                    // debruijn.py:132/136
+    __shared__ WarpQueue<W> q;
+    const u32 lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const u32 lt = (1u << lane) - 1;
+    u32 head = 0, count = 0;                                             // warp-uniform
+    for_windows_uniform<W>(packed, off, tile_first, n_bases, k,
+        [&](int, bool valid, K key, u32 r, u32 pos, bool has_next, u32 nb) {
+            const bool sel = valid && (hash32_key(key) - h_lo) <= h_span;     // this pass owns the key
+            const u32 m = __ballot_sync(0xFFFFFFFFu, sel);
+            if (m == 0) return;
+            if (sel) {
+                const u32 e = (head + count + __popc(m & lt)) & (DBG_QCAP - 1);
+                q.key[w][e] = key;
+                q.tag[w][e] = ((read_idx_base + r) << 32) | pos;
+                q.meta[w][e] = (u8)((has_next ? 4u : 0u) | nb);
+            }
+            count += __popc(m);
+            if (count >= 32) {
+                __syncwarp();
+                const u32 e = (head + lane) & (DBG_QCAP - 1);
+                insert_one<W>(table, n_slots, q.key[w][e], q.tag[w][e], q.meta[w][e], ctr);
+                head = (head + 32) & (DBG_QCAP - 1);
+                count -= 32;
+                __syncwarp();
+            }
         });
+    __syncwarp();
+    if (lane < count) {
+        const u32 e = (head + lane) & (DBG_QCAP - 1);
+        insert_one<W>(table, n_slots, q.key[w][e], q.tag[w][e], q.meta[w][e], ctr);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
