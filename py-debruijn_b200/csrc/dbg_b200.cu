@@ -66,7 +66,7 @@ struct dbg_handle {
     const uint64_t *d_off = nullptr;          // offsets in use (caller's for build_device, ours for build)
     DevBuf b_bases, b_off, b_packed, b_tile, b_table, b_flags, b_kept, b_succ, b_link, b_ctr, b_hll,
            b_order, b_tag, b_tag2, b_slot, b_slot2, b_sorttmp, b_branch, b_starts, b_pulled, b_readflags,
-           b_recs, b_cnt32, b_off64, b_contig, b_junction, b_split, b_scratch[6];
+           b_recs, b_cnt32, b_off64, b_contig, b_junction, b_split, b_h8, b_chunk, b_scratch[6];
     DevCounters ctr;
     dbg_stats_t st;
     std::vector<uint32_t> branch, pulled;     // reference order
@@ -294,8 +294,10 @@ static int build_impl(dbg_t *h, const u8 *d_bases, const u64 *d_off) {
     if (h->n_bases) {
         TRY(reserve(h, h->b_hll, HLL_M * 4));
         CK(cudaMemsetAsync(h->b_hll.p, 0, HLL_M * 4, h->stream));
+        TRY(reserve(h, h->b_h8, h->n_tiles * DBG_TILE));
+        TRY(reserve(h, h->b_chunk, h->n_tiles * (DBG_TILE / DBG_WPT) * 4));
         LAUNCH(k_estimate<W>, h->n_tiles, DBG_BLOCK, h->stream, ptr<const u64>(h->b_packed), d_off,
-               ptr<const u32>(h->b_tile), h->n_bases, k, ptr<u32>(h->b_hll));
+               ptr<const u32>(h->b_tile), h->n_bases, k, ptr<u32>(h->b_hll), ptr<u8>(h->b_h8), ptr<u32>(h->b_chunk));
         CKK();
         std::vector<u32> regs(HLL_M);
         CK(cudaMemcpyAsync(regs.data(), h->b_hll.p, HLL_M * 4, cudaMemcpyDeviceToHost, h->stream));
@@ -333,15 +335,26 @@ static int build_impl(dbg_t *h, const u8 *d_bases, const u64 *d_off) {
             }
             uint32_t n_parts = (uint32_t)cdiv(n_slots * sizeof(S), region);
             if (n_parts < 1) n_parts = 1;
-            if (n_parts > 64) n_parts = 64;
             st.n_insert_passes = n_parts;
+            if (n_parts > 255) n_parts = 255;
+            // persistent-style grid: each block owns a contiguous run of tiles
+            int sms = 148;
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+            uint64_t grid = (uint64_t)sms * 32;
+            if (const char *e = getenv("DBG_B200_INSERT_GRID")) {        // tuning / tests
+                const unsigned long long v = strtoull(e, nullptr, 10);
+                if (v >= 1) grid = v;
+            }
+            if (grid > h->n_tiles) grid = h->n_tiles;
+            const uint64_t tiles_per_block = cdiv(h->n_tiles, grid);
+            grid = cdiv(h->n_tiles, tiles_per_block);
             for (uint32_t part = 0; part < n_parts; part++) {
-                const uint32_t h_lo = (uint32_t)(((uint64_t)part << 32) / n_parts);
-                const uint32_t h_hi = part + 1 == n_parts ? 0xFFFFFFFFu : (uint32_t)((((uint64_t)(part + 1)) << 32) / n_parts) - 1;
-                const uint32_t h_span = h_hi - h_lo;
-                LAUNCH(k_insert<W>, h->n_tiles, DBG_BLOCK, h->stream, ptr<const u64>(h->b_packed), d_off,
-                       ptr<const u32>(h->b_tile), h->n_bases, k, ptr<S>(h->b_table), n_slots, h->read_idx_base,
-                       h_lo, h_span, d_ctr);
+                // hash bytes 0..254 (255 = not a window) split evenly over the passes
+                const uint32_t lo8 = part * 255u / n_parts;
+                const uint32_t hi8 = (part + 1) * 255u / n_parts - 1;
+                LAUNCH(k_insert<W>, grid, DBG_BLOCK, h->stream, ptr<const u64>(h->b_packed), d_off,
+                       ptr<const u32>(h->b_chunk), ptr<const u8>(h->b_h8), h->n_bases, h->n_tiles, tiles_per_block, k,
+                       ptr<S>(h->b_table), (u32)n_slots, h->read_idx_base, lo8, hi8 - lo8, d_ctr);
                 CKK();
             }
         }
@@ -680,7 +693,7 @@ DBG_API void dbg_destroy(dbg_t *h) {
     DevBuf *all[] = {&h->b_bases, &h->b_off, &h->b_packed, &h->b_tile, &h->b_table, &h->b_flags, &h->b_kept,
                      &h->b_succ, &h->b_link, &h->b_ctr, &h->b_hll, &h->b_order, &h->b_tag, &h->b_tag2, &h->b_slot,
                      &h->b_slot2, &h->b_sorttmp, &h->b_branch, &h->b_starts, &h->b_pulled, &h->b_readflags,
-                     &h->b_recs, &h->b_cnt32, &h->b_off64, &h->b_contig, &h->b_junction, &h->b_split, &h->b_scratch[0],
+                     &h->b_recs, &h->b_cnt32, &h->b_off64, &h->b_contig, &h->b_junction, &h->b_split, &h->b_h8, &h->b_chunk, &h->b_scratch[0],
                      &h->b_scratch[1], &h->b_scratch[2], &h->b_scratch[3], &h->b_scratch[4], &h->b_scratch[5]};
     for (DevBuf *b : all) if (b->p) cudaFree(b->p);
     for (int i = 0; i < EV_MAX; i++) cudaEventDestroy(h->ev[i]);

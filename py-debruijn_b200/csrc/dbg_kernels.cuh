@@ -231,18 +231,37 @@ DBG_D void for_windows_uniform(const u64 *__restrict__ packed, const u64 *__rest
 // the table.  Registers saturate after a few thousand keys, so almost every window is a plain
 // load and no atomic.
 // ---------------------------------------------------------------------------------------------
+// Pass 0 of the table build.  Besides the HLL registers it leaves, for every stream position, one
+// byte = top 8 bits of the node key's slot hash (255 = "not a node occurrence", 254 = hash bytes
+// 254 and 255), and for every 16-position chunk the index of the read holding its first position.
+// The insert passes select their windows from those bytes instead of re-rolling every key.
 template <int W>
 __global__ void __launch_bounds__(DBG_BLOCK) k_estimate(const u64 *__restrict__ packed, const u64 *__restrict__ off,
                                                         const u32 *__restrict__ tile_first, u64 n_bases, int k,
-                                                        u32 *regs) {
+                                                        u32 *regs, u8 *__restrict__ h8, u32 *__restrict__ chunk_read) {
     typedef typename KeyOf<W>::type K;
+    u32 acc[DBG_WPT / 4];
+#pragma unroll
+    for (int i = 0; i < DBG_WPT / 4; i++) acc[i] = 0;
+    u32 r0 = 0;
     for_windows_uniform<W>(packed, off, tile_first, n_bases, k,
-        [&](int, bool valid, K key, u32, u32, bool, u32) {
+        [&](int j, bool valid, K key, u32 r, u32, bool, u32) {
+            if (j == 0) r0 = r;
             u32 h = hash32_key(key);
             u32 idx = h >> (32 - HLL_P);
             u32 rank = (u32)__clz((int)((h << HLL_P) | (1u << (HLL_P - 1)))) + 1;
             if (valid && regs[idx] < rank) atomicMax(&regs[idx], rank);
+            u32 b = h >> 24;
+            b = valid ? (b > 254u ? 254u : b) : 255u;
+            acc[j >> 2] |= b << (8 * (j & 3));
         });
+    const u64 p0 = (u64)blockIdx.x * DBG_TILE + (u64)threadIdx.x * DBG_WPT;
+    if (p0 < n_bases) {
+        uint4 *dst = reinterpret_cast<uint4 *>(h8 + p0);                 // h8 is padded to whole tiles
+#pragma unroll
+        for (int i = 0; i < DBG_WPT / 16; i++) dst[i] = make_uint4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
+        chunk_read[p0 / DBG_WPT] = r0;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -265,63 +284,166 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_table_init(Slot<W> *table, u64 n_
 // So the windows are replayed n_parts times; pass `part` only touches keys whose home slot lies in
 // [part, part + 1) * n_slots / n_parts, a region sized to stay L2-resident, and the rolling key +
 // multiply-shift hash of the other windows (about 25 instructions) is all those cost.
-// Each warp compacts the windows the pass owns into a 64-entry shared-memory ring and drains it
-// 32 at a time, so the table probes and atomics always run with all 32 lanes busy no matter how
-// few windows of a given iteration the pass owns.
+// Insert pass.  A pass owns the keys whose hash byte lies in [lo8, lo8 + span8]; their home slots
+// form a contiguous table region small enough to stay L2-resident while every read is replayed.
+// Per warp, per tile:
+//   select  each lane loads the 16 hash bytes of its chunk (one 128-bit load), and the positions of
+//           the bytes in range are compacted into ring Q1 (a warp prefix sum gives the offsets)
+//   expand  32 positions at a time, one per lane: read index / position / key / next base are
+//           re-derived from the packed stream, the home slot is hashed, and ONE probe is made
+//   probe   a lane whose slot holds another key does not loop: it re-queues (key, tag, slot + 1)
+//           in ring Q2, which is drained 32 at a time the same way
+// so the table traffic always runs with (close to) 32 busy lanes and no divergent probe loops.
 #define DBG_WARPS (DBG_BLOCK / 32)
-#define DBG_QCAP 64
-template <int W> struct WarpQueue {
-    typename KeyOf<W>::type key[DBG_WARPS][DBG_QCAP];
-    u64 tag[DBG_WARPS][DBG_QCAP];
-    u8 meta[DBG_WARPS][DBG_QCAP];          // has_next << 2 | next base
+#define DBG_Q1CAP 512
+#define DBG_Q2CAP 64
+#define DBG_MAX_PROBES 4096u
+template <int W> struct InsertQueues {
+    u32 pos[DBG_WARPS][DBG_Q1CAP];         // (tile - first tile of the block) << 12 | position inside the tile
+    typename KeyOf<W>::type key[DBG_WARPS][DBG_Q2CAP];
+    u64 tag[DBG_WARPS][DBG_Q2CAP];
+    u32 idx[DBG_WARPS][DBG_Q2CAP];
+    u16 meta[DBG_WARPS][DBG_Q2CAP];        // probes so far << 3 | has_next << 2 | next base
 };
 
+// one probe of slot idx.  true = done (inserted / counted, or dropped on overflow)
 template <int W>
-DBG_D void insert_one(Slot<W> *table, u64 n_slots, typename KeyOf<W>::type key, u64 tag, u32 meta, DevCounters *ctr) {
-    u64 seen;
-    u64 idx = table_upsert_tag<W>(table, n_slots, slot_home(hash32_key(key), n_slots), key, &seen);
-    if (idx == NONE64) { ctr->overflow = 1; return; }
+DBG_D bool probe_once(Slot<W> *table, u32 idx, typename KeyOf<W>::type key, u64 tag, u32 meta) {
+    typedef typename KeyOf<W>::type K;
     Slot<W> *s = &table[idx];
+    u64 seen;
+    K cur = load_key_tag(s, &seen);
+    if (cur != key) {
+        if (cur != empty_key<W>()) return false;
+        K old = cas_key(&s->key, empty_key<W>(), key);
+        if (old == empty_key<W>()) seen = ~0ULL;
+        else if (old == key) seen = __ldcg(&s->tag);
+        else return false;
+    }
     if (tag < seen) atomicMin(&s->tag, tag);                             // first occurrence
     if (meta & 4u) atomicAdd(&s->cnt[meta & 3u], 1u);                    // debruijn.py:132/136
+    return true;
 }
 
 template <int W>
 __global__ void __launch_bounds__(DBG_BLOCK) k_insert(const u64 *__restrict__ packed, const u64 *__restrict__ off,
-                                                      const u32 *__restrict__ tile_first, u64 n_bases, int k,
-                                                      Slot<W> *table, u64 n_slots, u64 read_idx_base,
-                                                      u32 h_lo, u32 h_span, DevCounters *ctr) {
+                                                      const u32 *__restrict__ chunk_read, const u8 *__restrict__ h8,
+                                                      u64 n_bases, u64 n_tiles, u64 tiles_per_block, int k,
+                                                      Slot<W> *table, u32 n_slots, u64 read_idx_base,
+                                                      u32 lo8, u32 span8, DevCounters *ctr) {
     typedef typename KeyOf<W>::type K;
-    __shared__ WarpQueue<W> q;
+    __shared__ InsertQueues<W> q;
     const u32 lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const u32 lt = (1u << lane) - 1;
-    u32 head = 0, count = 0;                                             // warp-uniform
-    for_windows_uniform<W>(packed, off, tile_first, n_bases, k,
-        [&](int, bool valid, K key, u32 r, u32 pos, bool has_next, u32 nb) {
-            const bool sel = valid && (hash32_key(key) - h_lo) <= h_span;     // this pass owns the key
-            const u32 m = __ballot_sync(0xFFFFFFFFu, sel);
-            if (m == 0) return;
-            if (sel) {
-                const u32 e = (head + count + __popc(m & lt)) & (DBG_QCAP - 1);
-                q.key[w][e] = key;
-                q.tag[w][e] = ((read_idx_base + r) << 32) | pos;
-                q.meta[w][e] = (u8)((has_next ? 4u : 0u) | nb);
+    u32 head1 = 0, n1 = 0, head2 = 0, n2 = 0;                            // warp-uniform ring state
+    bool overflow = false;
+
+    // requeue lane's entry in Q2 (all lanes call; `again` says which need it)
+    auto requeue = [&](bool again, K key, u64 tag, u32 idx, u32 meta) {
+        const u32 m = __ballot_sync(0xFFFFFFFFu, again);
+        if (again) {
+            const u32 e = (head2 + n2 + __popc(m & lt)) & (DBG_Q2CAP - 1);
+            q.key[w][e] = key; q.tag[w][e] = tag; q.idx[w][e] = idx; q.meta[w][e] = (u16)meta;
+        }
+        n2 += __popc(m);
+    };
+    auto drain2 = [&]() {                                                // up to 32 retries, one probe each
+        __syncwarp();
+        const u32 take = n2 < 32u ? n2 : 32u;
+        const bool act = lane < take;
+        const u32 e = (head2 + lane) & (DBG_Q2CAP - 1);
+        K key = q.key[w][e]; u64 tag = q.tag[w][e]; u32 idx = q.idx[w][e]; u32 meta = q.meta[w][e];
+        __syncwarp();
+        head2 = (head2 + take) & (DBG_Q2CAP - 1);
+        n2 -= take;
+        bool again = false;
+        if (act) {
+            again = !probe_once<W>(table, idx, key, tag, meta);
+            if (again) {
+                idx = idx + 1 == n_slots ? 0 : idx + 1;
+                meta += 8u;
+                if ((meta >> 3) >= DBG_MAX_PROBES) { overflow = true; again = false; }
             }
-            count += __popc(m);
-            if (count >= 32) {
-                __syncwarp();
-                const u32 e = (head + lane) & (DBG_QCAP - 1);
-                insert_one<W>(table, n_slots, q.key[w][e], q.tag[w][e], q.meta[w][e], ctr);
-                head = (head + 32) & (DBG_QCAP - 1);
-                count -= 32;
-                __syncwarp();
+        }
+        requeue(again, key, tag, idx, meta);
+    };
+    const u64 tile_begin = (u64)blockIdx.x * tiles_per_block;
+    auto drain1 = [&]() {                                                // up to 32 fresh positions
+        __syncwarp();
+        const u32 take = n1 < 32u ? n1 : 32u;
+        const bool act = lane < take;
+        const u32 e = q.pos[w][(head1 + lane) & (DBG_Q1CAP - 1)];
+        __syncwarp();
+        head1 = (head1 + take) & (DBG_Q1CAP - 1);
+        n1 -= take;
+        bool again = false;
+        K key = zero_key<W>(); u64 tag = 0; u32 idx = 0, meta = 0;
+        if (act) {
+            const u64 p = (tile_begin + (e >> 12)) * DBG_TILE + (e & 0xFFFu);
+            u32 r = __ldg(chunk_read + p / DBG_WPT);
+            u64 rs = __ldg(off + r), re = __ldg(off + r + 1);
+            while (p >= re) { r++; rs = re; re = __ldg(off + r + 1); }  // a read ends inside the chunk
+            const u32 pos = (u32)(p - rs);
+            const bool has_next = (u64)pos + (u64)k < re - rs;
+            key = extract_key<W>(packed, p, k);
+            meta = (has_next ? 4u : 0u) | base_at(packed, p + k);
+            tag = ((read_idx_base + r) << 32) | pos;
+            idx = (u32)slot_home(hash32_key(key), n_slots);
+            again = !probe_once<W>(table, idx, key, tag, meta);
+            if (again) { idx = idx + 1 == n_slots ? 0 : idx + 1; meta += 8u; }
+        }
+        requeue(again, key, tag, idx, meta);
+    };
+
+    u64 tile_end = tile_begin + tiles_per_block;
+    if (tile_end > n_tiles) tile_end = n_tiles;
+    for (u64 tile = tile_begin; tile < tile_end; tile++) {
+        // ---- select: which of my 16 positions does this pass own?
+        const u32 rel0 = threadIdx.x * DBG_WPT;
+        const u64 p0 = tile * DBG_TILE + rel0;
+        u32 mask = 0;
+        if (p0 < n_bases) {
+#pragma unroll
+            for (int i = 0; i < DBG_WPT / 16; i++) {
+                const uint4 v = __ldg(reinterpret_cast<const uint4 *>(h8 + p0) + i);
+                const u32 wv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int c = 0; c < 4; c++)
+#pragma unroll
+                    for (int bb = 0; bb < 4; bb++)
+                        if ((((wv[c] >> (8 * bb)) & 0xFFu) - lo8) <= span8) mask |= 1u << (16 * i + 4 * c + bb);
             }
-        });
-    __syncwarp();
-    if (lane < count) {
-        const u32 e = (head + lane) & (DBG_QCAP - 1);
-        insert_one<W>(table, n_slots, q.key[w][e], q.tag[w][e], q.meta[w][e], ctr);
+        }
+        const u32 tbits = (u32)(tile - tile_begin) << 12;
+        // two halves of 8 positions, so that Q1 never has to take more than 256 entries at once
+#pragma unroll
+        for (int half = 0; half < 2; half++) {
+            u32 m8 = (mask >> (8 * half)) & 0xFFu;
+            u32 cnt = __popc(m8), incl = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const u32 t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                if (lane >= (u32)d) incl += t;
+            }
+            const u32 total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+            u32 o = head1 + n1 + incl - cnt;
+            while (m8) {
+                const u32 j = (u32)__ffs((int)m8) - 1;
+                m8 &= m8 - 1;
+                q.pos[w][o & (DBG_Q1CAP - 1)] = tbits | (rel0 + 8 * half + j);
+                o++;
+            }
+            n1 += total;
+            // ---- expand + probe, 32 at a time
+            while (n1 >= 32) {
+                drain1();
+                while (n2 >= 32) drain2();
+            }
+        }
     }
+    if (n1) drain1();
+    while (n2) drain2();
+    if (overflow) ctr->overflow = 1;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -190,11 +190,15 @@ def test_descriptors_scores_and_lookup(backend):
     g.close()
 
 
-def test_partition_passes(backend, monkeypatch):
-    """The table build replays the windows once per L2-sized table region; force many passes."""
+@pytest.mark.parametrize('grid', ['1', '3', ''])
+def test_partition_passes(backend, monkeypatch, grid):
+    """The table build replays the windows once per L2-sized table region; force many passes,
+    and few blocks so that every warp carries its queues across many tiles."""
     from dbg_b200 import Graph
     monkeypatch.setenv('DBG_B200_L2_REGION_BYTES', '4096')
-    _, reads = util.synth_reads(21, 4000, 70, 12, err=0.01)
+    if grid:
+        monkeypatch.setenv('DBG_B200_INSERT_GRID', grid)
+    _, reads = util.synth_reads(21, 12000, 70, 12, err=0.01)
     for k in (19, 41):
         exp = dbg_oracle.snapshot(reads, k, 2, False)
         got = util.product_snapshot(reads, k, 2, False)
