@@ -27,11 +27,14 @@
 #ifdef DBG_EMU
 #define LAUNCH(kernel, grid, block, stream, ...) \
     (h->st.n_launches++, emu::launch(dim3((unsigned)(grid)), dim3((unsigned)(block)), 0, [&]() { kernel(__VA_ARGS__); }))
+#define LAUNCH_SMEM(kernel, grid, block, smem, stream, ...) LAUNCH(kernel, grid, block, stream, __VA_ARGS__)
 #else
 #include <cuda_runtime.h>
 #include <cub/device/device_radix_sort.cuh>
 #define LAUNCH(kernel, grid, block, stream, ...) \
     (h->st.n_launches++, kernel<<<(unsigned)(grid), (unsigned)(block), 0, stream>>>(__VA_ARGS__))
+#define LAUNCH_SMEM(kernel, grid, block, smem, stream, ...) \
+    (h->st.n_launches++, kernel<<<(unsigned)(grid), (unsigned)(block), (smem), stream>>>(__VA_ARGS__))
 #endif
 
 #include "../../include/dbg_b200.h"
@@ -340,20 +343,28 @@ static int build_impl(dbg_t *h, const u8 *d_bases, const u64 *d_off) {
             // persistent-style grid: each block owns a contiguous run of tiles
             int sms = 148;
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
-            uint64_t grid = (uint64_t)sms * 32;
+            // persistent-style grid: each block owns a contiguous run of warp units
+            const uint64_t n_units = cdiv(h->n_bases, DBG_UNIT);
+            uint64_t grid = (uint64_t)sms * 16;
+            size_t smem_pad = 0;                                         // tuning: extra smem = fewer blocks, more L1
+            if (const char *e = getenv("DBG_B200_INSERT_SMEM_PAD")) smem_pad = (size_t)strtoull(e, nullptr, 10);
+#ifndef DBG_EMU
+            if (const char *e = getenv("DBG_B200_INSERT_CARVEOUT"))       // tuning: % of the unified L1 given to smem
+                cudaFuncSetAttribute(k_insert<W>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e));
+#endif
             if (const char *e = getenv("DBG_B200_INSERT_GRID")) {        // tuning / tests
                 const unsigned long long v = strtoull(e, nullptr, 10);
                 if (v >= 1) grid = v;
             }
-            if (grid > h->n_tiles) grid = h->n_tiles;
-            const uint64_t tiles_per_block = cdiv(h->n_tiles, grid);
-            grid = cdiv(h->n_tiles, tiles_per_block);
+            if (grid > cdiv(n_units, DBG_WARPS)) grid = cdiv(n_units, DBG_WARPS);
+            const uint64_t units_per_block = cdiv(n_units, grid);
+            grid = cdiv(n_units, units_per_block);
             for (uint32_t part = 0; part < n_parts; part++) {
                 // hash bytes 0..254 (255 = not a window) split evenly over the passes
                 const uint32_t lo8 = part * 255u / n_parts;
                 const uint32_t hi8 = (part + 1) * 255u / n_parts - 1;
-                LAUNCH(k_insert<W>, grid, DBG_BLOCK, h->stream, ptr<const u64>(h->b_packed), d_off,
-                       ptr<const u32>(h->b_chunk), ptr<const u8>(h->b_h8), h->n_bases, h->n_tiles, tiles_per_block, k,
+                LAUNCH_SMEM(k_insert<W>, grid, DBG_BLOCK, smem_pad, h->stream, ptr<const u64>(h->b_packed), h->n_words + 4,
+                       d_off, ptr<const u32>(h->b_chunk), ptr<const u8>(h->b_h8), h->n_bases, n_units, units_per_block, k,
                        ptr<S>(h->b_table), (u32)n_slots, h->read_idx_base, lo8, hi8 - lo8, d_ctr);
                 CKK();
             }

@@ -286,27 +286,60 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_table_init(Slot<W> *table, u64 n_
 // multiply-shift hash of the other windows (about 25 instructions) is all those cost.
 // Insert pass.  A pass owns the keys whose hash byte lies in [lo8, lo8 + span8]; their home slots
 // form a contiguous table region small enough to stay L2-resident while every read is replayed.
-// Per warp, per tile:
-//   select  each lane loads the 16 hash bytes of its chunk (one 128-bit load), and the positions of
-//           the bytes in range are compacted into ring Q1 (a warp prefix sum gives the offsets)
-//   expand  32 positions at a time, one per lane: read index / position / key / next base are
-//           re-derived from the packed stream, the home slot is hashed, and ONE probe is made
+// Each warp works through units of DBG_UNIT = 1024 stream positions on its own (no block barrier):
+//   stage   the unit's 2-bit words (+ k bases of overhang) and, per 16-position chunk, the read
+//           index / position-in-read / distance to the read's end go to shared memory with
+//           coalesced loads, so nothing below touches L2 except the table itself
+//   select  each lane loads the 16 hash bytes of its chunks (128-bit loads) and the positions of
+//           the bytes in range are compacted into ring Q1 (warp prefix sum for the offsets)
+//   expand  32 positions at a time, one per lane: key, next base and tag are rebuilt from the
+//           staged words, the home slot is hashed, and ONE probe is made
 //   probe   a lane whose slot holds another key does not loop: it re-queues (key, tag, slot + 1)
 //           in ring Q2, which is drained 32 at a time the same way
-// so the table traffic always runs with (close to) 32 busy lanes and no divergent probe loops.
+// so table traffic always runs with (close to) 32 busy lanes, without divergent probe loops, and
+// costs two L2 sector accesses per window (slot load, counter RED) plus the retries.
 #define DBG_WARPS (DBG_BLOCK / 32)
+#define DBG_UNIT 1024                     // positions per warp work unit
+#define DBG_UNIT_CHUNKS (DBG_UNIT / DBG_WPT)
+#define DBG_UNIT_WORDS (DBG_UNIT / 32 + 4) // staged 2-bit words: the unit + 63 + 16 bases of overhang
 #define DBG_Q1CAP 512
 #define DBG_Q2CAP 64
 #define DBG_MAX_PROBES 4096u
-template <int W> struct InsertQueues {
-    u32 pos[DBG_WARPS][DBG_Q1CAP];         // (tile - first tile of the block) << 12 | position inside the tile
+template <int W> struct InsertShared {
+    u64 words[DBG_WARPS][DBG_UNIT_WORDS];
+    u32 c_read[DBG_WARPS][DBG_UNIT_CHUNKS];   // read index at the chunk's first position
+    u32 c_pos[DBG_WARPS][DBG_UNIT_CHUNKS];    // position in that read
+    u32 c_end[DBG_WARPS][DBG_UNIT_CHUNKS];    // distance to the read's end (clamped)
+    u16 pos[DBG_WARPS][DBG_Q1CAP];            // Q1: position inside the unit
     typename KeyOf<W>::type key[DBG_WARPS][DBG_Q2CAP];
     u64 tag[DBG_WARPS][DBG_Q2CAP];
     u32 idx[DBG_WARPS][DBG_Q2CAP];
-    u16 meta[DBG_WARPS][DBG_Q2CAP];        // probes so far << 3 | has_next << 2 | next base
+    u16 meta[DBG_WARPS][DBG_Q2CAP];           // probes so far << 3 | has_next << 2 | next base
 };
 
-// one probe of slot idx.  true = done (inserted / counted, or dropped on overflow)
+// k bases starting at base `rel` of a staged word array (same layout as extract_key)
+template <int W> DBG_D typename KeyOf<W>::type staged_key(const u64 *words, u32 rel, int k);
+template <> DBG_D u64 staged_key<1>(const u64 *words, u32 rel, int k) {
+    const u32 w = rel >> 5;
+    const int s = 2 * (int)(rel & 31);
+    const u64 w0 = words[w], w1 = words[w + 1];
+    const u64 top = s ? ((w0 << s) | (w1 >> (64 - s))) : w0;
+    return top >> (64 - 2 * k);
+}
+template <> DBG_D K128 staged_key<2>(const u64 *words, u32 rel, int k) {
+    const u32 w = rel >> 5;
+    const int s = 2 * (int)(rel & 31);
+    const u64 w0 = words[w], w1 = words[w + 1], w2 = words[w + 2];
+    const u64 hi = s ? ((w0 << s) | (w1 >> (64 - s))) : w0;
+    const u64 lo = s ? ((w1 << s) | (w2 >> (64 - s))) : w1;
+    const int sh = 128 - 2 * k;
+    K128 r;
+    if (sh >= 64) { r.lo = sh == 64 ? hi : hi >> (sh - 64); r.hi = 0; }
+    else { r.lo = (lo >> sh) | (hi << (64 - sh)); r.hi = hi >> sh; }
+    return r;
+}
+
+// one probe of slot idx.  true = done (inserted / counted)
 template <int W>
 DBG_D bool probe_once(Slot<W> *table, u32 idx, typename KeyOf<W>::type key, u64 tag, u32 meta) {
     typedef typename KeyOf<W>::type K;
@@ -326,24 +359,26 @@ DBG_D bool probe_once(Slot<W> *table, u32 idx, typename KeyOf<W>::type key, u64 
 }
 
 template <int W>
-__global__ void __launch_bounds__(DBG_BLOCK) k_insert(const u64 *__restrict__ packed, const u64 *__restrict__ off,
+__global__ void __launch_bounds__(DBG_BLOCK) k_insert(const u64 *__restrict__ packed, u64 n_words_padded,
+                                                      const u64 *__restrict__ off,
                                                       const u32 *__restrict__ chunk_read, const u8 *__restrict__ h8,
-                                                      u64 n_bases, u64 n_tiles, u64 tiles_per_block, int k,
+                                                      u64 n_bases, u64 n_units, u64 units_per_block, int k,
                                                       Slot<W> *table, u32 n_slots, u64 read_idx_base,
                                                       u32 lo8, u32 span8, DevCounters *ctr) {
     typedef typename KeyOf<W>::type K;
-    __shared__ InsertQueues<W> q;
+    __shared__ InsertShared<W> sh;
     const u32 lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const u32 lt = (1u << lane) - 1;
     u32 head1 = 0, n1 = 0, head2 = 0, n2 = 0;                            // warp-uniform ring state
     bool overflow = false;
+    u64 ub = 0;                                                          // first stream position of the unit
 
     // requeue lane's entry in Q2 (all lanes call; `again` says which need it)
     auto requeue = [&](bool again, K key, u64 tag, u32 idx, u32 meta) {
         const u32 m = __ballot_sync(0xFFFFFFFFu, again);
         if (again) {
             const u32 e = (head2 + n2 + __popc(m & lt)) & (DBG_Q2CAP - 1);
-            q.key[w][e] = key; q.tag[w][e] = tag; q.idx[w][e] = idx; q.meta[w][e] = (u16)meta;
+            sh.key[w][e] = key; sh.tag[w][e] = tag; sh.idx[w][e] = idx; sh.meta[w][e] = (u16)meta;
         }
         n2 += __popc(m);
     };
@@ -352,7 +387,7 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_insert(const u64 *__restrict__ pa
         const u32 take = n2 < 32u ? n2 : 32u;
         const bool act = lane < take;
         const u32 e = (head2 + lane) & (DBG_Q2CAP - 1);
-        K key = q.key[w][e]; u64 tag = q.tag[w][e]; u32 idx = q.idx[w][e]; u32 meta = q.meta[w][e];
+        K key = sh.key[w][e]; u64 tag = sh.tag[w][e]; u32 idx = sh.idx[w][e]; u32 meta = sh.meta[w][e];
         __syncwarp();
         head2 = (head2 + take) & (DBG_Q2CAP - 1);
         n2 -= take;
@@ -367,26 +402,31 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_insert(const u64 *__restrict__ pa
         }
         requeue(again, key, tag, idx, meta);
     };
-    const u64 tile_begin = (u64)blockIdx.x * tiles_per_block;
     auto drain1 = [&]() {                                                // up to 32 fresh positions
         __syncwarp();
         const u32 take = n1 < 32u ? n1 : 32u;
         const bool act = lane < take;
-        const u32 e = q.pos[w][(head1 + lane) & (DBG_Q1CAP - 1)];
+        const u32 rel = sh.pos[w][(head1 + lane) & (DBG_Q1CAP - 1)];
         __syncwarp();
         head1 = (head1 + take) & (DBG_Q1CAP - 1);
         n1 -= take;
         bool again = false;
         K key = zero_key<W>(); u64 tag = 0; u32 idx = 0, meta = 0;
         if (act) {
-            const u64 p = (tile_begin + (e >> 12)) * DBG_TILE + (e & 0xFFFu);
-            u32 r = __ldg(chunk_read + p / DBG_WPT);
-            u64 rs = __ldg(off + r), re = __ldg(off + r + 1);
-            while (p >= re) { r++; rs = re; re = __ldg(off + r + 1); }  // a read ends inside the chunk
-            const u32 pos = (u32)(p - rs);
-            const bool has_next = (u64)pos + (u64)k < re - rs;
-            key = extract_key<W>(packed, p, k);
-            meta = (has_next ? 4u : 0u) | base_at(packed, p + k);
+            const u32 c = rel / DBG_WPT, j = rel % DBG_WPT;
+            u32 r = sh.c_read[w][c], pos = sh.c_pos[w][c] + j;
+            const u32 end = sh.c_end[w][c];
+            bool has_next = j + (u32)k < end;
+            if (j >= end) {                                              // rare: a read ends inside the chunk
+                const u64 p = ub + rel;
+                u64 rs, re = __ldg(off + r + 1);
+                do { r++; rs = re; re = __ldg(off + r + 1); } while (p >= re);
+                pos = (u32)(p - rs);
+                has_next = (u64)pos + (u64)k < re - rs;
+            }
+            key = staged_key<W>(sh.words[w], rel, k);
+            const u32 q = rel + (u32)k;
+            meta = (has_next ? 4u : 0u) | ((u32)(sh.words[w][q >> 5] >> (62 - 2 * (q & 31))) & 3u);
             tag = ((read_idx_base + r) << 32) | pos;
             idx = (u32)slot_home(hash32_key(key), n_slots);
             again = !probe_once<W>(table, idx, key, tag, meta);
@@ -395,53 +435,71 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_insert(const u64 *__restrict__ pa
         requeue(again, key, tag, idx, meta);
     };
 
-    u64 tile_end = tile_begin + tiles_per_block;
-    if (tile_end > n_tiles) tile_end = n_tiles;
-    for (u64 tile = tile_begin; tile < tile_end; tile++) {
-        // ---- select: which of my 16 positions does this pass own?
-        const u32 rel0 = threadIdx.x * DBG_WPT;
-        const u64 p0 = tile * DBG_TILE + rel0;
-        u32 mask = 0;
-        if (p0 < n_bases) {
+    const u64 unit_begin = (u64)blockIdx.x * units_per_block;
+    u64 unit_end = unit_begin + units_per_block;
+    if (unit_end > n_units) unit_end = n_units;
+    for (u64 u = unit_begin + w; u < unit_end; u += DBG_WARPS) {
+        ub = u * DBG_UNIT;
+        __syncwarp();
+        // ---- stage the unit
+        for (u32 i = lane; i < DBG_UNIT_WORDS; i += 32) {
+            const u64 wi = ub / 32 + i;
+            sh.words[w][i] = wi < n_words_padded ? __ldg(packed + wi) : 0;
+        }
+        u32 mask[DBG_UNIT_CHUNKS / 32];
 #pragma unroll
-            for (int i = 0; i < DBG_WPT / 16; i++) {
-                const uint4 v = __ldg(reinterpret_cast<const uint4 *>(h8 + p0) + i);
+        for (int t = 0; t < DBG_UNIT_CHUNKS / 32; t++) {
+            const u32 c = (u32)t * 32 + lane;
+            const u64 p0 = ub + (u64)c * DBG_WPT;
+            u32 m = 0, r = 0, pos0 = 0, end = 0;
+            if (p0 < n_bases) {
+                r = __ldg(chunk_read + p0 / DBG_WPT);
+                const u64 rs = __ldg(off + r), re = __ldg(off + r + 1);
+                pos0 = (u32)(p0 - rs);
+                end = (u32)(re - p0 < (u64)(1u << 30) ? re - p0 : (u64)(1u << 30));
+                const uint4 v = __ldg(reinterpret_cast<const uint4 *>(h8 + p0));
                 const u32 wv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-                for (int c = 0; c < 4; c++)
+                for (int cc = 0; cc < 4; cc++)
 #pragma unroll
                     for (int bb = 0; bb < 4; bb++)
-                        if ((((wv[c] >> (8 * bb)) & 0xFFu) - lo8) <= span8) mask |= 1u << (16 * i + 4 * c + bb);
+                        if ((((wv[cc] >> (8 * bb)) & 0xFFu) - lo8) <= span8) m |= 1u << (4 * cc + bb);
+            }
+            sh.c_read[w][c] = r; sh.c_pos[w][c] = pos0; sh.c_end[w][c] = end;
+            mask[t] = m;
+        }
+        __syncwarp();
+        // ---- select (8 positions per lane at a time, so Q1 takes at most 256 entries) + drain
+#pragma unroll
+        for (int t = 0; t < DBG_UNIT_CHUNKS / 32; t++) {
+#pragma unroll
+            for (int half = 0; half < 2; half++) {
+                u32 m8 = (mask[t] >> (8 * half)) & 0xFFu;
+                u32 cnt = __popc(m8), incl = cnt;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const u32 x = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                    if (lane >= (u32)d) incl += x;
+                }
+                const u32 total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+                u32 o = head1 + n1 + incl - cnt;
+                const u32 rel0 = ((u32)t * 32 + lane) * DBG_WPT + 8 * half;
+                while (m8) {
+                    const u32 j = (u32)__ffs((int)m8) - 1;
+                    m8 &= m8 - 1;
+                    sh.pos[w][o & (DBG_Q1CAP - 1)] = (u16)(rel0 + j);
+                    o++;
+                }
+                n1 += total;
+                while (n1 >= 32) {
+                    drain1();
+                    while (n2 >= 32) drain2();
+                }
             }
         }
-        const u32 tbits = (u32)(tile - tile_begin) << 12;
-        // two halves of 8 positions, so that Q1 never has to take more than 256 entries at once
-#pragma unroll
-        for (int half = 0; half < 2; half++) {
-            u32 m8 = (mask >> (8 * half)) & 0xFFu;
-            u32 cnt = __popc(m8), incl = cnt;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const u32 t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-                if (lane >= (u32)d) incl += t;
-            }
-            const u32 total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-            u32 o = head1 + n1 + incl - cnt;
-            while (m8) {
-                const u32 j = (u32)__ffs((int)m8) - 1;
-                m8 &= m8 - 1;
-                q.pos[w][o & (DBG_Q1CAP - 1)] = tbits | (rel0 + 8 * half + j);
-                o++;
-            }
-            n1 += total;
-            // ---- expand + probe, 32 at a time
-            while (n1 >= 32) {
-                drain1();
-                while (n2 >= 32) drain2();
-            }
-        }
+        if (n1) drain1();                                                // Q1 entries die with the staged unit
+        while (n2 >= 32) drain2();
     }
-    if (n1) drain1();
     while (n2) drain2();
     if (overflow) ctr->overflow = 1;
 }
