@@ -364,7 +364,8 @@ static int build_impl(dbg_t *h, const u8 *d_bases, const u64 *d_off) {
                 const uint32_t lo8 = part * 255u / n_parts;
                 const uint32_t hi8 = (part + 1) * 255u / n_parts - 1;
                 LAUNCH_SMEM(k_insert<W>, grid, DBG_BLOCK, smem_pad, h->stream, ptr<const u64>(h->b_packed), h->n_words + 4,
-                       d_off, ptr<const u32>(h->b_chunk), ptr<const u8>(h->b_h8), h->n_bases, n_units, units_per_block, k,
+                       d_off, h->n_reads, ptr<const u32>(h->b_chunk), ptr<const u8>(h->b_h8), h->n_bases, n_units,
+                       units_per_block, k,
                        ptr<S>(h->b_table), (u32)n_slots, h->read_idx_base, lo8, hi8 - lo8, d_ctr);
                 CKK();
             }

@@ -302,18 +302,21 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_table_init(Slot<W> *table, u64 n_
 #define DBG_UNIT 1024                     // positions per warp work unit
 #define DBG_UNIT_CHUNKS (DBG_UNIT / DBG_WPT)
 #define DBG_UNIT_WORDS (DBG_UNIT / 32 + 4) // staged 2-bit words: the unit + 63 + 16 bases of overhang
-#define DBG_Q1CAP 512
-#define DBG_Q2CAP 64
+#define DBG_ILP 2                         // entries per lane per drain: two slot loads in flight
+#define DBG_DRAIN (32 * DBG_ILP)
+#define DBG_Q1CAP 512                     // >= DBG_DRAIN - 1 + 256
+#define DBG_Q2CAP 128                     // >= 2 * DBG_DRAIN
 #define DBG_MAX_PROBES 4096u
 template <int W> struct InsertShared {
     u64 words[DBG_WARPS][DBG_UNIT_WORDS];
     u32 c_read[DBG_WARPS][DBG_UNIT_CHUNKS];   // read index at the chunk's first position
     u32 c_pos[DBG_WARPS][DBG_UNIT_CHUNKS];    // position in that read
-    u32 c_end[DBG_WARPS][DBG_UNIT_CHUNKS];    // distance to the read's end (clamped)
+    u16 c_end[DBG_WARPS][DBG_UNIT_CHUNKS];    // distance to that read's end (clamped)
+    u16 c_end2[DBG_WARPS][DBG_UNIT_CHUNKS];   // distance to the end of the next non-empty read (clamped)
+    u8 c_skip[DBG_WARPS][DBG_UNIT_CHUNKS];    // index of that read minus c_read (0 = unknown: use off[])
     u16 pos[DBG_WARPS][DBG_Q1CAP];            // Q1: position inside the unit
     typename KeyOf<W>::type key[DBG_WARPS][DBG_Q2CAP];
     u64 tag[DBG_WARPS][DBG_Q2CAP];
-    u32 idx[DBG_WARPS][DBG_Q2CAP];
     u16 meta[DBG_WARPS][DBG_Q2CAP];           // probes so far << 3 | has_next << 2 | next base
 };
 
@@ -339,13 +342,11 @@ template <> DBG_D K128 staged_key<2>(const u64 *words, u32 rel, int k) {
     return r;
 }
 
-// one probe of slot idx.  true = done (inserted / counted)
+// second half of a probe: the slot's key and tag have been loaded.  true = done
 template <int W>
-DBG_D bool probe_once(Slot<W> *table, u32 idx, typename KeyOf<W>::type key, u64 tag, u32 meta) {
+DBG_D bool probe_finish(Slot<W> *s, typename KeyOf<W>::type cur, u64 seen, typename KeyOf<W>::type key, u64 tag,
+                        u32 meta) {
     typedef typename KeyOf<W>::type K;
-    Slot<W> *s = &table[idx];
-    u64 seen;
-    K cur = load_key_tag(s, &seen);
     if (cur != key) {
         if (cur != empty_key<W>()) return false;
         K old = cas_key(&s->key, empty_key<W>(), key);
@@ -360,7 +361,7 @@ DBG_D bool probe_once(Slot<W> *table, u32 idx, typename KeyOf<W>::type key, u64 
 
 template <int W>
 __global__ void __launch_bounds__(DBG_BLOCK) k_insert(const u64 *__restrict__ packed, u64 n_words_padded,
-                                                      const u64 *__restrict__ off,
+                                                      const u64 *__restrict__ off, u64 n_reads,
                                                       const u32 *__restrict__ chunk_read, const u8 *__restrict__ h8,
                                                       u64 n_bases, u64 n_units, u64 units_per_block, int k,
                                                       Slot<W> *table, u32 n_slots, u64 read_idx_base,
@@ -373,66 +374,89 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_insert(const u64 *__restrict__ pa
     bool overflow = false;
     u64 ub = 0;                                                          // first stream position of the unit
 
-    // requeue lane's entry in Q2 (all lanes call; `again` says which need it)
-    auto requeue = [&](bool again, K key, u64 tag, u32 idx, u32 meta) {
+    // requeue a lane's entry in Q2 (all lanes call; `again` says which need it).  The slot to
+    // probe next is not stored: it is home(key) + probes so far.
+    auto requeue = [&](bool again, K key, u64 tag, u32 meta) {
         const u32 m = __ballot_sync(0xFFFFFFFFu, again);
         if (again) {
             const u32 e = (head2 + n2 + __popc(m & lt)) & (DBG_Q2CAP - 1);
-            sh.key[w][e] = key; sh.tag[w][e] = tag; sh.idx[w][e] = idx; sh.meta[w][e] = (u16)meta;
+            sh.key[w][e] = key; sh.tag[w][e] = tag; sh.meta[w][e] = (u16)meta;
         }
         n2 += __popc(m);
     };
-    auto drain2 = [&]() {                                                // up to 32 retries, one probe each
+    // probe DBG_ILP entries per lane: all slot loads are issued before the first is looked at
+    auto probe_all = [&](const bool (&act)[DBG_ILP], K (&key)[DBG_ILP], u64 (&tag)[DBG_ILP], u32 (&meta)[DBG_ILP]) {
+        Slot<W> *s[DBG_ILP];
+        K cur[DBG_ILP];
+        u64 seen[DBG_ILP];
+#pragma unroll
+        for (int i = 0; i < DBG_ILP; i++) {
+            u64 idx = slot_home(hash32_key(key[i]), n_slots) + (meta[i] >> 3);
+            if (idx >= n_slots) idx -= n_slots;
+            s[i] = &table[act[i] ? idx : 0];
+            cur[i] = load_key_tag(s[i], &seen[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < DBG_ILP; i++) {
+            bool again = false;
+            if (act[i]) {
+                again = !probe_finish<W>(s[i], cur[i], seen[i], key[i], tag[i], meta[i]);
+                if (again) {
+                    meta[i] += 8u;
+                    if ((meta[i] >> 3) >= DBG_MAX_PROBES) { overflow = true; again = false; }
+                }
+            }
+            requeue(again, key[i], tag[i], meta[i]);
+        }
+    };
+    auto drain2 = [&]() {                                                // up to DBG_DRAIN retries
         __syncwarp();
-        const u32 take = n2 < 32u ? n2 : 32u;
-        const bool act = lane < take;
-        const u32 e = (head2 + lane) & (DBG_Q2CAP - 1);
-        K key = sh.key[w][e]; u64 tag = sh.tag[w][e]; u32 idx = sh.idx[w][e]; u32 meta = sh.meta[w][e];
+        const u32 take = n2 < (u32)DBG_DRAIN ? n2 : (u32)DBG_DRAIN;
+        bool act[DBG_ILP]; K key[DBG_ILP]; u64 tag[DBG_ILP]; u32 meta[DBG_ILP];
+#pragma unroll
+        for (int i = 0; i < DBG_ILP; i++) {
+            const u32 e = (head2 + 32 * i + lane) & (DBG_Q2CAP - 1);
+            act[i] = 32 * i + lane < take;
+            key[i] = sh.key[w][e]; tag[i] = sh.tag[w][e]; meta[i] = sh.meta[w][e];
+        }
         __syncwarp();
         head2 = (head2 + take) & (DBG_Q2CAP - 1);
         n2 -= take;
-        bool again = false;
-        if (act) {
-            again = !probe_once<W>(table, idx, key, tag, meta);
-            if (again) {
-                idx = idx + 1 == n_slots ? 0 : idx + 1;
-                meta += 8u;
-                if ((meta >> 3) >= DBG_MAX_PROBES) { overflow = true; again = false; }
-            }
-        }
-        requeue(again, key, tag, idx, meta);
+        probe_all(act, key, tag, meta);
     };
-    auto drain1 = [&]() {                                                // up to 32 fresh positions
+    auto drain1 = [&]() {                                                // up to DBG_DRAIN fresh positions
         __syncwarp();
-        const u32 take = n1 < 32u ? n1 : 32u;
-        const bool act = lane < take;
-        const u32 rel = sh.pos[w][(head1 + lane) & (DBG_Q1CAP - 1)];
-        __syncwarp();
-        head1 = (head1 + take) & (DBG_Q1CAP - 1);
-        n1 -= take;
-        bool again = false;
-        K key = zero_key<W>(); u64 tag = 0; u32 idx = 0, meta = 0;
-        if (act) {
+        const u32 take = n1 < (u32)DBG_DRAIN ? n1 : (u32)DBG_DRAIN;
+        bool act[DBG_ILP]; K key[DBG_ILP]; u64 tag[DBG_ILP]; u32 meta[DBG_ILP];
+#pragma unroll
+        for (int i = 0; i < DBG_ILP; i++) {
+            act[i] = 32 * i + lane < take;
+            const u32 rel = act[i] ? sh.pos[w][(head1 + 32 * i + lane) & (DBG_Q1CAP - 1)] : 0;
             const u32 c = rel / DBG_WPT, j = rel % DBG_WPT;
             u32 r = sh.c_read[w][c], pos = sh.c_pos[w][c] + j;
             const u32 end = sh.c_end[w][c];
             bool has_next = j + (u32)k < end;
-            if (j >= end) {                                              // rare: a read ends inside the chunk
-                const u64 p = ub + rel;
-                u64 rs, re = __ldg(off + r + 1);
-                do { r++; rs = re; re = __ldg(off + r + 1); } while (p >= re);
-                pos = (u32)(p - rs);
-                has_next = (u64)pos + (u64)k < re - rs;
+            if (j >= end && act[i]) {                                    // a read ends inside the chunk
+                const u32 end2 = sh.c_end2[w][c], skip = sh.c_skip[w][c];
+                if (skip && j < end2) {                                  // ... and the window is in the next one
+                    r += skip; pos = j - end; has_next = j + (u32)k < end2;
+                } else {                                                 // reads shorter than a chunk: ask off[]
+                    const u64 p = ub + rel;
+                    u64 rs, re = __ldg(off + r + 1);
+                    do { r++; rs = re; re = __ldg(off + r + 1); } while (p >= re);
+                    pos = (u32)(p - rs);
+                    has_next = (u64)pos + (u64)k < re - rs;
+                }
             }
-            key = staged_key<W>(sh.words[w], rel, k);
+            key[i] = staged_key<W>(sh.words[w], rel, k);
             const u32 q = rel + (u32)k;
-            meta = (has_next ? 4u : 0u) | ((u32)(sh.words[w][q >> 5] >> (62 - 2 * (q & 31))) & 3u);
-            tag = ((read_idx_base + r) << 32) | pos;
-            idx = (u32)slot_home(hash32_key(key), n_slots);
-            again = !probe_once<W>(table, idx, key, tag, meta);
-            if (again) { idx = idx + 1 == n_slots ? 0 : idx + 1; meta += 8u; }
+            meta[i] = (has_next ? 4u : 0u) | ((u32)(sh.words[w][q >> 5] >> (62 - 2 * (q & 31))) & 3u);
+            tag[i] = ((read_idx_base + r) << 32) | pos;
         }
-        requeue(again, key, tag, idx, meta);
+        __syncwarp();
+        head1 = (head1 + take) & (DBG_Q1CAP - 1);
+        n1 -= take;
+        probe_all(act, key, tag, meta);
     };
 
     const u64 unit_begin = (u64)blockIdx.x * units_per_block;
@@ -451,12 +475,23 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_insert(const u64 *__restrict__ pa
         for (int t = 0; t < DBG_UNIT_CHUNKS / 32; t++) {
             const u32 c = (u32)t * 32 + lane;
             const u64 p0 = ub + (u64)c * DBG_WPT;
-            u32 m = 0, r = 0, pos0 = 0, end = 0;
+            u32 m = 0, r = 0, pos0 = 0, end = 0, end2 = 0, skip = 0;
             if (p0 < n_bases) {
                 r = __ldg(chunk_read + p0 / DBG_WPT);
                 const u64 rs = __ldg(off + r), re = __ldg(off + r + 1);
                 pos0 = (u32)(p0 - rs);
-                end = (u32)(re - p0 < (u64)(1u << 30) ? re - p0 : (u64)(1u << 30));
+                end = (u32)(re - p0 < (u64)0xFFFF ? re - p0 : (u64)0xFFFF);
+                if (end < (u32)DBG_WPT) {                                // the chunk runs into the next read(s)
+                    u64 r2 = r + 1, re2 = re;
+                    while (r2 < n_reads && skip < 200u) {
+                        re2 = __ldg(off + r2 + 1);
+                        skip++;
+                        if (re2 > re) break;                             // first non-empty read after r
+                        r2++;
+                    }
+                    if (re2 > re && skip < 200u) end2 = (u32)(re2 - p0 < (u64)0xFFFF ? re2 - p0 : (u64)0xFFFF);
+                    else skip = 0;
+                }
                 const uint4 v = __ldg(reinterpret_cast<const uint4 *>(h8 + p0));
                 const u32 wv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
@@ -465,7 +500,8 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_insert(const u64 *__restrict__ pa
                     for (int bb = 0; bb < 4; bb++)
                         if ((((wv[cc] >> (8 * bb)) & 0xFFu) - lo8) <= span8) m |= 1u << (4 * cc + bb);
             }
-            sh.c_read[w][c] = r; sh.c_pos[w][c] = pos0; sh.c_end[w][c] = end;
+            sh.c_read[w][c] = r; sh.c_pos[w][c] = pos0; sh.c_end[w][c] = (u16)end;
+            sh.c_end2[w][c] = (u16)end2; sh.c_skip[w][c] = (u8)skip;
             mask[t] = m;
         }
         __syncwarp();
@@ -491,14 +527,14 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_insert(const u64 *__restrict__ pa
                     o++;
                 }
                 n1 += total;
-                while (n1 >= 32) {
+                while (n1 >= (u32)DBG_DRAIN) {
                     drain1();
-                    while (n2 >= 32) drain2();
+                    while (n2 >= (u32)DBG_DRAIN) drain2();
                 }
             }
         }
-        if (n1) drain1();                                                // Q1 entries die with the staged unit
-        while (n2 >= 32) drain2();
+        while (n1) drain1();                                             // Q1 entries die with the staged unit
+        while (n2 >= (u32)DBG_DRAIN) drain2();
     }
     while (n2) drain2();
     if (overflow) ctr->overflow = 1;
