@@ -302,10 +302,10 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_table_init(Slot<W> *table, u64 n_
 #define DBG_UNIT 1024                     // positions per warp work unit
 #define DBG_UNIT_CHUNKS (DBG_UNIT / DBG_WPT)
 #define DBG_UNIT_WORDS (DBG_UNIT / 32 + 4) // staged 2-bit words: the unit + 63 + 16 bases of overhang
-#define DBG_ILP 2                         // entries per lane per drain: two slot loads in flight
+#define DBG_ILP 1                         // entries per lane per drain: two slot loads in flight
 #define DBG_DRAIN (32 * DBG_ILP)
 #define DBG_Q1CAP 512                     // >= DBG_DRAIN - 1 + 256
-#define DBG_Q2CAP 128                     // >= 2 * DBG_DRAIN
+#define DBG_Q2CAP 64                      // >= 2 * DBG_DRAIN
 #define DBG_MAX_PROBES 4096u
 template <int W> struct InsertShared {
     u64 words[DBG_WARPS][DBG_UNIT_WORDS];
@@ -359,8 +359,11 @@ DBG_D bool probe_finish(Slot<W> *s, typename KeyOf<W>::type cur, u64 seen, typen
     return true;
 }
 
+#ifndef DBG_INSERT_MIN_BLOCKS
+#define DBG_INSERT_MIN_BLOCKS 6
+#endif
 template <int W>
-__global__ void __launch_bounds__(DBG_BLOCK) k_insert(const u64 *__restrict__ packed, u64 n_words_padded,
+__global__ void __launch_bounds__(DBG_BLOCK, DBG_INSERT_MIN_BLOCKS) k_insert(const u64 *__restrict__ packed, u64 n_words_padded,
                                                       const u64 *__restrict__ off, u64 n_reads,
                                                       const u32 *__restrict__ chunk_read, const u8 *__restrict__ h8,
                                                       u64 n_bases, u64 n_units, u64 units_per_block, int k,
