@@ -49,8 +49,13 @@ def main(rep, note=''):
             continue
         d = dict(zip(h, r))
         key = (cur, int(r[0]))
-        agg[key] += int(d.get('Instructions Executed') or 0)
-        samp[key] += int(d.get('# Samples') or 0)
+        def num(x):
+            try:
+                return int(x)
+            except (TypeError, ValueError):
+                return 0
+        agg[key] += num(d.get('Instructions Executed'))
+        samp[key] += num(d.get('# Samples'))
         text[key] = r[1][:100]
     ti, ts = sum(agg.values()) or 1, sum(samp.values()) or 1
     print('--- source hot spots over all captured launches (share of warp instructions / of stall samples)')
