@@ -69,7 +69,7 @@ struct dbg_handle {
     const uint64_t *d_off = nullptr;          // offsets in use (caller's for build_device, ours for build)
     DevBuf b_bases, b_off, b_packed, b_tile, b_table, b_flags, b_kept, b_succ, b_link, b_ctr, b_hll,
            b_order, b_tag, b_tag2, b_slot, b_slot2, b_sorttmp, b_branch, b_starts, b_pulled, b_readflags,
-           b_recs, b_cnt32, b_off64, b_contig, b_junction, b_split, b_h8, b_chunk, b_scratch[6];
+           b_recs, b_cnt32, b_off64, b_contig, b_junction, b_split, b_h8, b_chunk, b_bitmap, b_scratch[6];
     DevCounters ctr;
     dbg_stats_t st;
     std::vector<uint32_t> branch, pulled;     // reference order
@@ -198,6 +198,24 @@ static int collect_sorted(dbg_t *h, u32 want, uint64_t expect, DevBuf &out, u64 
            ptr<const u8>(h->b_flags), want, ptr<u64>(h->b_tag), ptr<u32>(h->b_slot), cursor);
     CKK();
     return sort_by_tag(h, expect, ptr<u32>(out));
+}
+
+// side set (dbg_kernels.cuh) of the slots whose flags hit `want`: entries in b_order, bitmap in b_bitmap
+template <int W>
+static int side_set(dbg_t *h, u32 want, uint64_t n_members, uint64_t *cap_out, int *bits_out) {
+    const uint64_t cap = n_members * 2 + 32;
+    int bits = 10;                                              // bitmap of >= 32 bits per member, <= 2^28 bits
+    while (bits < 28 && (1ull << bits) < n_members * 32) bits++;
+    TRY(reserve(h, h->b_order, cap * sizeof(SideEntry<W>)));
+    TRY(reserve(h, h->b_bitmap, (1ull << bits) / 8));
+    CK(cudaMemsetAsync(h->b_order.p, 0xFF, cap * sizeof(SideEntry<W>), h->stream));
+    CK(cudaMemsetAsync(h->b_bitmap.p, 0, (1ull << bits) / 8, h->stream));
+    LAUNCH(k_side_fill<W>, blocks_for(h->n_slots), DBG_BLOCK, h->stream, ptr<const Slot<W>>(h->b_table),
+           ptr<const u8>(h->b_flags), h->n_slots, want, ptr<SideEntry<W>>(h->b_order), cap, ptr<u32>(h->b_bitmap), bits);
+    CKK();
+    *cap_out = cap;
+    *bits_out = bits;
+    return DBG_OK;
 }
 
 template <int W>
@@ -404,18 +422,14 @@ static int build_impl(dbg_t *h, const u8 *d_bases, const u64 *d_off) {
 
     // ---- Counter.most_common tie order (debruijn.py:159-164) ----
     if ((h->build_flags & DBG_EXACT_ORDER) && st.n_multi) {
-        const uint64_t cap = st.n_multi * 2 + 32;
-        TRY(reserve(h, h->b_order, cap * sizeof(OrderEntry)));
-        CK(cudaMemsetAsync(h->b_order.p, 0xFF, cap * sizeof(OrderEntry), h->stream));
-        LAUNCH(k_order_fill, blocks_for(n_slots), DBG_BLOCK, h->stream, ptr<const u8>(h->b_flags), n_slots,
-               ptr<OrderEntry>(h->b_order), cap);
-        CKK();
+        uint64_t cap; int bits;
+        TRY(side_set<W>(h, F_MULTI, st.n_multi, &cap, &bits));
         LAUNCH(k_order_scan<W>, h->n_tiles, DBG_BLOCK, h->stream, ptr<const u64>(h->b_packed), d_off,
-               ptr<const u32>(h->b_tile), h->n_bases, k, ptr<const S>(h->b_table), n_slots,
-               ptr<const u8>(h->b_flags), h->read_idx_base, ptr<OrderEntry>(h->b_order), cap, d_ctr);
+               ptr<const u32>(h->b_tile), h->n_bases, k, h->read_idx_base, ptr<SideEntry<W>>(h->b_order), cap,
+               ptr<const u32>(h->b_bitmap), bits);
         CKK();
         LAUNCH(k_order_apply<W>, blocks_for(cap), DBG_BLOCK, h->stream, ptr<const S>(h->b_table), n_slots, k,
-               h->threshold, ptr<const OrderEntry>(h->b_order), cap, ptr<u16>(h->b_kept), ptr<u32>(h->b_succ), d_ctr);
+               h->threshold, ptr<const SideEntry<W>>(h->b_order), cap, ptr<u16>(h->b_kept), ptr<u32>(h->b_succ), d_ctr);
         CKK();
         TRY(check_fault(h, "k_order_*"));
     }
@@ -445,9 +459,11 @@ static int build_impl(dbg_t *h, const u8 *d_bases, const u64 *d_off) {
         if (st.n_branch && h->n_reads) {
             TRY(reserve(h, h->b_readflags, h->n_reads));
             CK(cudaMemsetAsync(h->b_readflags.p, 0, h->n_reads, h->stream));
+            uint64_t cap; int bits;
+            TRY(side_set<W>(h, F_BRANCH, st.n_branch, &cap, &bits));
             LAUNCH(k_pull_reads<W>, h->n_tiles, DBG_BLOCK, h->stream, ptr<const u64>(h->b_packed), d_off,
-                   ptr<const u32>(h->b_tile), h->n_bases, k, ptr<const S>(h->b_table), n_slots,
-                   ptr<const u8>(h->b_flags), ptr<u8>(h->b_readflags));
+                   ptr<const u32>(h->b_tile), h->n_bases, k, ptr<SideEntry<W>>(h->b_order), cap,
+                   ptr<const u32>(h->b_bitmap), bits, ptr<u8>(h->b_readflags));
             CKK();
             CK(cudaMemcpyAsync(h->read_flags.data(), h->b_readflags.p, h->n_reads, cudaMemcpyDeviceToHost, h->stream));
             CK(cudaStreamSynchronize(h->stream));
@@ -705,7 +721,7 @@ DBG_API void dbg_destroy(dbg_t *h) {
     DevBuf *all[] = {&h->b_bases, &h->b_off, &h->b_packed, &h->b_tile, &h->b_table, &h->b_flags, &h->b_kept,
                      &h->b_succ, &h->b_link, &h->b_ctr, &h->b_hll, &h->b_order, &h->b_tag, &h->b_tag2, &h->b_slot,
                      &h->b_slot2, &h->b_sorttmp, &h->b_branch, &h->b_starts, &h->b_pulled, &h->b_readflags,
-                     &h->b_recs, &h->b_cnt32, &h->b_off64, &h->b_contig, &h->b_junction, &h->b_split, &h->b_h8, &h->b_chunk, &h->b_scratch[0],
+                     &h->b_recs, &h->b_cnt32, &h->b_off64, &h->b_contig, &h->b_junction, &h->b_split, &h->b_h8, &h->b_chunk, &h->b_bitmap, &h->b_scratch[0],
                      &h->b_scratch[1], &h->b_scratch[2], &h->b_scratch[3], &h->b_scratch[4], &h->b_scratch[5]};
     for (DevBuf *b : all) if (b->p) cudaFree(b->p);
     for (int i = 0; i < EV_MAX; i++) cudaEventDestroy(h->ev[i]);

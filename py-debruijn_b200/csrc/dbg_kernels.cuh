@@ -47,7 +47,6 @@ struct DevCounters {
 #define FAULT_TIP_MISSING 2u      // k_tip_paths: ditto
 #define FAULT_JUMP_RANGE 3u       // k_jump / k_emit: link points outside the table
 #define FAULT_JUNCTION_MISSING 4u // k_junctions
-#define FAULT_ORDER_MISSING 5u    // k_order_scan: multi-successor node without an order entry
 DBG_D void raise_fault(DevCounters *ctr, u32 code, u32 info) {
     if (atomicCAS(&ctr->fault, 0u, code) == 0u) ctr->fault_info = info;
 }
@@ -593,65 +592,80 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_finalize(const Slot<W> *__restric
 }
 
 // ---------------------------------------------------------------------------------------------
-// Exact successor order (DBG_EXACT_ORDER): a side table keyed by slot index holds, for every
-// multi-successor node, the first-appearance tag of each successor base.
+// Side sets.  Two later stages re-scan every window but only care about a small subset of the
+// nodes: the exact successor order (multi-successor nodes, debruijn.py:159-164) and pull_out_read
+// (branch nodes, debruijn.py:274-278).  Probing the big node table per window would be a random
+// DRAM access each; instead the subset goes into a small open-addressing set keyed by the node
+// key, fronted by a bitmap over the top bits of the slot hash, and both stay in L2 / L1.
 // ---------------------------------------------------------------------------------------------
-struct OrderEntry {
-    u64 slot;          // ~0 = empty
-    u64 first[4];      // ~0 = never
+template <int W> struct SideEntry {
+    typename KeyOf<W>::type key;   // all ones = empty
+    u64 slot;                      // slot in the node table
+    u64 first[4];                  // first-appearance tag per successor base (~0 = never)
 };
 
-DBG_D u64 order_locate(OrderEntry *ot, u64 cap, u64 slot, bool insert) {
-    u64 idx = mulhi64(fmix64(slot + 0x632be59bd9b4e019ULL), cap);
+template <int W>
+DBG_D u64 side_locate(SideEntry<W> *st, u64 cap, typename KeyOf<W>::type key, bool insert) {
+    typedef typename KeyOf<W>::type K;
+    const K EMPTY = empty_key<W>();
+    u64 idx = ((u64)(hash32_key(key) * 0x9E3779B1u) * cap) >> 32;        // re-mixed: independent of the bitmap bits
     for (u64 probes = 0; probes < cap; ++probes) {
-        u64 cur = __ldcg(&ot[idx].slot);
-        if (cur == slot) return idx;
-        if (cur == ~0ULL) {
+        K cur = load_key(reinterpret_cast<const Slot<W> *>(&st[idx]));   // key is the first member of both
+        if (cur == key) return idx;
+        if (cur == EMPTY) {
             if (!insert) return NONE64;
-            u64 old = atomicCAS(&ot[idx].slot, ~0ULL, slot);
-            if (old == ~0ULL || old == slot) return idx;
+            K old = cas_key(&st[idx].key, EMPTY, key);
+            if (old == EMPTY || old == key) return idx;
         }
         if (++idx == cap) idx = 0;
     }
     return NONE64;
 }
+DBG_D bool bitmap_test(const u32 *__restrict__ bm, int bits, u32 h) {
+    const u32 b = h >> (32 - bits);
+    return (__ldg(bm + (b >> 5)) >> (b & 31)) & 1u;
+}
 
-__global__ void __launch_bounds__(DBG_BLOCK) k_order_fill(const u8 *__restrict__ flags, u64 n_slots,
-                                                          OrderEntry *ot, u64 cap) {
+// every slot whose flags hit `want` goes into the side set
+template <int W>
+__global__ void __launch_bounds__(DBG_BLOCK) k_side_fill(const Slot<W> *__restrict__ table, const u8 *__restrict__ flags,
+                                                         u64 n_slots, u32 want, SideEntry<W> *st, u64 cap, u32 *bm,
+                                                         int bits) {
     u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_slots) return;
-    if (flags[i] & F_MULTI) order_locate(ot, cap, i, true);
+    if (i >= n_slots || !(flags[i] & want)) return;
+    typename KeyOf<W>::type key = table[i].key;
+    u64 e = side_locate<W>(st, cap, key, true);
+    if (e != NONE64) st[e].slot = i;
+    const u32 b = hash32_key(key) >> (32 - bits);
+    atomicOr(&bm[b >> 5], 1u << (b & 31));
 }
 
 template <int W>
 __global__ void __launch_bounds__(DBG_BLOCK) k_order_scan(const u64 *__restrict__ packed, const u64 *__restrict__ off,
                                                           const u32 *__restrict__ tile_first, u64 n_bases, int k,
-                                                          const Slot<W> *__restrict__ table, u64 n_slots,
-                                                          const u8 *__restrict__ flags, u64 read_idx_base,
-                                                          OrderEntry *ot, u64 cap, DevCounters *ctr) {
+                                                          u64 read_idx_base, SideEntry<W> *st, u64 cap,
+                                                          const u32 *__restrict__ bm, int bits) {
     typedef typename KeyOf<W>::type K;
     for_windows<W, true>(packed, off, tile_first, n_bases, k,
         [&](K key, u32 r, u32 pos, bool has_next, u32 nb) {
-            if (!has_next) return;
-            u64 idx = table_find<W>(table, n_slots, key);
-            if (idx == NONE64 || !(flags[idx] & F_MULTI)) return;
-            u64 e = order_locate(ot, cap, idx, false);
-            if (e == NONE64) { raise_fault(ctr, FAULT_ORDER_MISSING, (u32)idx); return; }
+            if (!has_next || !bitmap_test(bm, bits, hash32_key(key))) return;
+            u64 e = side_locate<W>(st, cap, key, false);
+            if (e == NONE64) return;                                     // not a multi-successor node
             u64 tag = ((read_idx_base + r) << 32) | pos;
-            if (tag < __ldcg(&ot[e].first[nb])) atomicMin(&ot[e].first[nb], tag);
+            if (tag < __ldcg(&st[e].first[nb])) atomicMin(&st[e].first[nb], tag);
         });
 }
 
 template <int W>
 __global__ void __launch_bounds__(DBG_BLOCK) k_order_apply(const Slot<W> *__restrict__ table, u64 n_slots, int k,
-                                                           double threshold, const OrderEntry *__restrict__ ot,
+                                                           double threshold, const SideEntry<W> *__restrict__ ot,
                                                            u64 cap, u16 *__restrict__ kept, u32 *__restrict__ succ,
                                                            DevCounters *ctr) {
     typedef typename KeyOf<W>::type K;
     u64 e = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= cap) return;
+    if (ot[e].key == empty_key<W>()) return;
     u64 i = ot[e].slot;
-    if (i == ~0ULL) return;
     u32 cnt[4] = { table[i].cnt[0], table[i].cnt[1], table[i].cnt[2], table[i].cnt[3] };
     u64 first[4] = { ot[e].first[0], ot[e].first[1], ot[e].first[2], ot[e].first[3] };
     u32 word = prune_successors(cnt, first, threshold);
@@ -750,13 +764,13 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_mark_pulled(const u32 *__restrict
 template <int W>
 __global__ void __launch_bounds__(DBG_BLOCK) k_pull_reads(const u64 *__restrict__ packed, const u64 *__restrict__ off,
                                                           const u32 *__restrict__ tile_first, u64 n_bases, int k,
-                                                          const Slot<W> *__restrict__ table, u64 n_slots,
-                                                          const u8 *__restrict__ flags, u8 *read_flags) {
+                                                          SideEntry<W> *st, u64 cap, const u32 *__restrict__ bm, int bits,
+                                                          u8 *read_flags) {
     typedef typename KeyOf<W>::type K;
     for_windows<W, false>(packed, off, tile_first, n_bases, k,
         [&](K key, u32 r, u32, bool, u32) {
-            u64 idx = table_find<W>(table, n_slots, key);
-            if (idx != NONE64 && (flags[idx] & F_BRANCH)) read_flags[r] = 1;
+            if (!bitmap_test(bm, bits, hash32_key(key))) return;
+            if (side_locate<W>(st, cap, key, false) != NONE64) read_flags[r] = 1;     // key is a branch node
         });
 }
 
