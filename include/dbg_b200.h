@@ -48,6 +48,8 @@ typedef enum {
                                 (Counter.most_common tie order, debruijn.py:159-164); costs a
                                 second pass over the reads only when multi-successor nodes exist */
 #define DBG_NO_PULL_READS 4u /* skip pull_out_read (debruijn.py:274-278)                      */
+#define DBG_TABLE_ONLY   8u  /* stop after the node table (window loop, debruijn.py:123-144): the
+                                multi-GPU build exchanges node records before the graph stages   */
 
 /* node flag bits (dbg_export_nodes) */
 #define DBG_NODE_START   0x02u  /* reference indegree == 0 (debruijn.py:137-143 quirk)       */
@@ -122,6 +124,25 @@ int dbg_build_device(dbg_t *h, const uint8_t *d_bases, const uint64_t *d_read_of
                      uint64_t n_reads, uint64_t n_bases, uint64_t read_idx_base,
                      double threshold, uint32_t flags);
 int dbg_stats(dbg_t *h, dbg_stats_t *out);
+
+/* ---- multi-GPU building blocks: the window loop is data parallel over reads,
+ * its result per rank is a set of NODE RECORDS { key | first-occurrence tag | 4 successor counts }
+ * (dbg_record_words() u64 words each) whose merge is associative (min tag, summed counts).  A
+ * rank builds its table with DBG_TABLE_ONLY, exports its records grouped by owner
+ * ((slot hash * n_parts) >> 32), the caller exchanges them (NCCL all-to-all), merges what it
+ * owns, all-gathers the merged shards and merges those into a fresh table, then runs the graph
+ * stages: 0 = degrees/prune/branch flags, 1 = tie-order scan of the LOCAL reads (order records
+ * are then exchanged with dbg_order_export / dbg_order_merge), 2 = order apply, lists, tips,
+ * pull-out flags of the LOCAL reads.  All record pointers are DEVICE pointers.               */
+int dbg_graph_stage(dbg_t *h, int stage, double threshold, uint32_t flags);
+int dbg_record_words(const dbg_t *h);
+int dbg_order_words(const dbg_t *h);
+int dbg_export_counts(dbg_t *h, uint32_t n_parts, uint64_t *counts /* host, n_parts */);
+int dbg_export_records(dbg_t *h, uint32_t n_parts, const uint64_t *counts, uint64_t *d_out);
+int dbg_table_reset(dbg_t *h, uint64_t expected_nodes);
+int dbg_merge_records(dbg_t *h, const uint64_t *d_records, uint64_t n);
+int dbg_order_export(dbg_t *h, uint64_t *d_out, uint64_t capacity, uint64_t *n_out);
+int dbg_order_merge(dbg_t *h, const uint64_t *d_records, uint64_t n);
 
 /* nodes, unordered (sort by first_tag for the reference's dict order).  Any pointer may be
  * NULL.  succ_cnt: 4 per node = edge_count_table[node + "ACGT"[c]]; kept: low 8 bits = kept

@@ -66,6 +66,9 @@ struct dbg_handle {
     double threshold = 3.0;
     uint64_t n_reads = 0, n_bases = 0, n_words = 0, n_tiles = 0, n_slots = 0, read_idx_base = 0;
     float pending_h2d = 0;
+    bool table_ready = false, order_active = false;
+    uint64_t order_cap = 0;
+    int order_bits = 0;
     const uint64_t *d_off = nullptr;          // offsets in use (caller's for build_device, ours for build)
     DevBuf b_bases, b_off, b_packed, b_tile, b_table, b_flags, b_kept, b_succ, b_link, b_ctr, b_hll,
            b_order, b_tag, b_tag2, b_slot, b_slot2, b_sorttmp, b_branch, b_starts, b_pulled, b_readflags,
@@ -398,13 +401,30 @@ static int build_impl(dbg_t *h, const u8 *d_bases, const u64 *d_off) {
         CK(cudaMemsetAsync(&d_ctr->overflow, 0, 4, h->stream));
         h->n_ev -= 3;
     }
-    const int e3 = ev_mark(h);
+    st.ms_pack = ev_ms(h, e0, e1);
+    st.ms_estimate = ev_ms(h, e1, e2);
+    st.ms_table_init = ms_init;
+    st.ms_insert = ms_insert;
+    st.table_slots = n_slots;
+    st.table_bytes = n_slots * sizeof(S);
+    st.ms_build_total = ev_ms(h, e0, ev_mark(h));
+    h->table_ready = true;
+    return DBG_OK;
+}
 
-    // ---- degrees, pruningEdges, branch flags, successor links (kernel 4) ----
+// ---- graph stage A: degrees, pruningEdges, branch flags, successor links (kernel 4) ----
+template <int W>
+static int graph_finalize(dbg_t *h) {
+    typedef Slot<W> S;
+    dbg_stats_t &st = h->st;
+    const uint64_t n_slots = h->n_slots;
+    DevCounters *d_ctr = ptr<DevCounters>(h->b_ctr);
+    const int e3 = ev_mark(h);
+    CK(cudaMemsetAsync(&d_ctr->n_nodes, 0, 5 * 8, h->stream));          // n_nodes .. n_starts
     TRY(reserve(h, h->b_flags, n_slots));
     TRY(reserve(h, h->b_kept, n_slots * 2));
     TRY(reserve(h, h->b_succ, n_slots * 4));
-    LAUNCH(k_finalize<W>, blocks_for(n_slots), DBG_BLOCK, h->stream, ptr<const S>(h->b_table), n_slots, k,
+    LAUNCH(k_finalize<W>, blocks_for(n_slots), DBG_BLOCK, h->stream, ptr<const S>(h->b_table), n_slots, h->k,
            h->threshold, ptr<u8>(h->b_flags), ptr<u16>(h->b_kept), ptr<u32>(h->b_succ), d_ctr);
     CKK();
     TRY(fetch_counters(h));
@@ -419,19 +439,51 @@ static int build_impl(dbg_t *h, const u8 *d_bases, const u64 *d_off) {
     if (st.n_multi && h->threshold == 0.0)
         return fail(h, DBG_ERR_ZERODIV, "threshold == 0 with a multi-successor node (debruijn.py:163)");
     const int e4 = ev_mark(h);
+    CK(cudaStreamSynchronize(h->stream));
+    st.ms_finalize = ev_ms(h, e3, e4);
+    st.ms_build_total += st.ms_finalize;
+    h->order_active = false;
+    return DBG_OK;
+}
 
-    // ---- Counter.most_common tie order (debruijn.py:159-164) ----
+// ---- graph stage B: Counter.most_common tie order (debruijn.py:159-164), scan of the LOCAL reads ----
+template <int W>
+static int graph_order_scan(dbg_t *h) {
+    dbg_stats_t &st = h->st;
+    const int e4 = ev_mark(h);
     if ((h->build_flags & DBG_EXACT_ORDER) && st.n_multi) {
-        uint64_t cap; int bits;
-        TRY(side_set<W>(h, F_MULTI, st.n_multi, &cap, &bits));
-        LAUNCH(k_order_scan<W>, h->n_tiles, DBG_BLOCK, h->stream, ptr<const u64>(h->b_packed), d_off,
-               ptr<const u32>(h->b_tile), h->n_bases, k, h->read_idx_base, ptr<SideEntry<W>>(h->b_order), cap,
-               ptr<const u32>(h->b_bitmap), bits);
-        CKK();
-        LAUNCH(k_order_apply<W>, blocks_for(cap), DBG_BLOCK, h->stream, ptr<const S>(h->b_table), n_slots, k,
-               h->threshold, ptr<const SideEntry<W>>(h->b_order), cap, ptr<u16>(h->b_kept), ptr<u32>(h->b_succ), d_ctr);
+        TRY(side_set<W>(h, F_MULTI, st.n_multi, &h->order_cap, &h->order_bits));
+        h->order_active = true;
+        if (h->n_bases) {
+            LAUNCH(k_order_scan<W>, h->n_tiles, DBG_BLOCK, h->stream, ptr<const u64>(h->b_packed), (const u64 *)h->d_off,
+                   ptr<const u32>(h->b_tile), h->n_bases, h->k, h->read_idx_base, ptr<SideEntry<W>>(h->b_order),
+                   h->order_cap, ptr<const u32>(h->b_bitmap), h->order_bits);
+            CKK();
+        }
+    }
+    const int e5 = ev_mark(h);
+    CK(cudaStreamSynchronize(h->stream));
+    st.ms_order = ev_ms(h, e4, e5);
+    st.ms_build_total += st.ms_order;
+    return DBG_OK;
+}
+
+// ---- graph stage C: apply the order, branch / start lists, tip pruning, pull-out reads ----
+template <int W>
+static int graph_complete(dbg_t *h) {
+    typedef Slot<W> S;
+    dbg_stats_t &st = h->st;
+    const uint64_t n_slots = h->n_slots;
+    const int k = h->k;
+    DevCounters *d_ctr = ptr<DevCounters>(h->b_ctr);
+    const int e4 = ev_mark(h);
+    if (h->order_active) {
+        LAUNCH(k_order_apply<W>, blocks_for(h->order_cap), DBG_BLOCK, h->stream, ptr<const S>(h->b_table), n_slots, k,
+               h->threshold, ptr<const SideEntry<W>>(h->b_order), h->order_cap, ptr<u16>(h->b_kept),
+               ptr<u32>(h->b_succ), d_ctr);
         CKK();
         TRY(check_fault(h, "k_order_*"));
+        h->order_active = false;
     }
     const int e5 = ev_mark(h);
 
@@ -450,18 +502,18 @@ static int build_impl(dbg_t *h, const u8 *d_bases, const u64 *d_off) {
     st.n_pulled = h->pulled.size();
     const int e7 = ev_mark(h);
 
-    // ---- pull_out_read (debruijn.py:274-283) ----
+    // ---- pull_out_read (debruijn.py:274-283), over the LOCAL reads ----
     h->read_flags_valid = false;
     st.n_pull_reads = 0;
     const bool want_reads = !(h->build_flags & (DBG_FINAL | DBG_NO_PULL_READS));
     if (want_reads) {
         h->read_flags.assign(h->n_reads, 0);
-        if (st.n_branch && h->n_reads) {
+        if (st.n_branch && h->n_reads && h->n_bases) {
             TRY(reserve(h, h->b_readflags, h->n_reads));
             CK(cudaMemsetAsync(h->b_readflags.p, 0, h->n_reads, h->stream));
             uint64_t cap; int bits;
             TRY(side_set<W>(h, F_BRANCH, st.n_branch, &cap, &bits));
-            LAUNCH(k_pull_reads<W>, h->n_tiles, DBG_BLOCK, h->stream, ptr<const u64>(h->b_packed), d_off,
+            LAUNCH(k_pull_reads<W>, h->n_tiles, DBG_BLOCK, h->stream, ptr<const u64>(h->b_packed), (const u64 *)h->d_off,
                    ptr<const u32>(h->b_tile), h->n_bases, k, ptr<SideEntry<W>>(h->b_order), cap,
                    ptr<const u32>(h->b_bitmap), bits, ptr<u8>(h->b_readflags));
             CKK();
@@ -475,19 +527,93 @@ static int build_impl(dbg_t *h, const u8 *d_bases, const u64 *d_off) {
     }
     const int e8 = ev_mark(h);
     CK(cudaStreamSynchronize(h->stream));
-
-    st.ms_pack = ev_ms(h, e0, e1);
-    st.ms_estimate = ev_ms(h, e1, e2);
-    st.ms_table_init = ms_init;
-    st.ms_insert = ms_insert;
-    st.ms_finalize = ev_ms(h, e3, e4);
-    st.ms_order = ev_ms(h, e4, e5);
+    st.ms_order += ev_ms(h, e4, e5);
     st.ms_lists = ev_ms(h, e5, e6);
     st.ms_tips = ev_ms(h, e6, e7);
     st.ms_pull_reads = ev_ms(h, e7, e8);
-    st.ms_build_total = ev_ms(h, e0, e8);
-    st.table_slots = n_slots;
-    st.table_bytes = n_slots * sizeof(S);
+    st.ms_build_total += ev_ms(h, e4, e8);
+    h->built = true;
+    return DBG_OK;
+}
+
+// ---- node records: the unit of the multi-GPU exchange (one per occupied slot) ----
+template <int W>
+static int export_counts_impl(dbg_t *h, uint32_t n_parts, uint64_t *counts) {
+    TRY(reserve(h, h->b_off64, (uint64_t)n_parts * 8 * 2));
+    CK(cudaMemsetAsync(h->b_off64.p, 0, (uint64_t)n_parts * 8 * 2, h->stream));
+    LAUNCH(k_rec_count<W>, blocks_for(h->n_slots), DBG_BLOCK, h->stream, ptr<const Slot<W>>(h->b_table), h->n_slots,
+           n_parts, ptr<u64>(h->b_off64));
+    CKK();
+    CK(cudaMemcpyAsync(counts, h->b_off64.p, (uint64_t)n_parts * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return DBG_OK;
+}
+
+template <int W>
+static int export_records_impl(dbg_t *h, uint32_t n_parts, const uint64_t *counts, uint64_t *d_out) {
+    std::vector<u64> cursors(n_parts);
+    u64 acc = 0;
+    for (uint32_t p = 0; p < n_parts; p++) { cursors[p] = acc; acc += counts[p]; }
+    u64 *d_cur = ptr<u64>(h->b_off64) + n_parts;
+    CK(cudaMemcpyAsync(d_cur, cursors.data(), (uint64_t)n_parts * 8, cudaMemcpyHostToDevice, h->stream));
+    LAUNCH(k_rec_scatter<W>, blocks_for(h->n_slots), DBG_BLOCK, h->stream, ptr<const Slot<W>>(h->b_table), h->n_slots,
+           n_parts, d_cur, (u64 *)d_out);
+    CKK();
+    CK(cudaStreamSynchronize(h->stream));
+    return DBG_OK;
+}
+
+template <int W>
+static int table_reset_impl(dbg_t *h, uint64_t expected_nodes) {
+    typedef Slot<W> S;
+    const uint64_t n_slots = expected_nodes * 2 + 1024;
+    if (n_slots >= 0xFFFFFFF0ull) return fail(h, DBG_ERR_OVERFLOW, "node table would exceed 2^32 slots");
+    h->n_slots = n_slots;
+    TRY(reserve(h, h->b_table, n_slots * sizeof(S)));
+    LAUNCH(k_table_init<W>, blocks_for(n_slots), DBG_BLOCK, h->stream, ptr<S>(h->b_table), n_slots);
+    CKK();
+    DevCounters *d_ctr = ptr<DevCounters>(h->b_ctr);
+    CK(cudaMemsetAsync(&d_ctr->overflow, 0, 4, h->stream));
+    h->st.table_slots = n_slots;
+    h->st.table_bytes = n_slots * sizeof(S);
+    h->table_ready = true;
+    h->built = h->walked = false;
+    return DBG_OK;
+}
+
+template <int W>
+static int merge_records_impl(dbg_t *h, const uint64_t *d_records, uint64_t n) {
+    if (n == 0) return DBG_OK;
+    LAUNCH(k_rec_merge<W>, blocks_for(n), DBG_BLOCK, h->stream, ptr<Slot<W>>(h->b_table), h->n_slots,
+           (const u64 *)d_records, n, ptr<DevCounters>(h->b_ctr));
+    CKK();
+    TRY(fetch_counters(h));
+    if (h->ctr.overflow) return fail(h, DBG_ERR_NOMEM, "node table overflowed while merging records");
+    return DBG_OK;
+}
+
+template <int W>
+static int order_export_impl(dbg_t *h, uint64_t *d_out, uint64_t capacity, uint64_t *n_out) {
+    *n_out = 0;
+    if (!h->order_active) return DBG_OK;
+    DevCounters *d_ctr = ptr<DevCounters>(h->b_ctr);
+    CK(cudaMemsetAsync(&d_ctr->n_list_a, 0, 8, h->stream));
+    LAUNCH(k_side_export<W>, blocks_for(h->order_cap), DBG_BLOCK, h->stream, ptr<const SideEntry<W>>(h->b_order),
+           h->order_cap, (u64 *)d_out, capacity, &d_ctr->n_list_a);
+    CKK();
+    TRY(fetch_counters(h));
+    *n_out = h->ctr.n_list_a;
+    if (h->ctr.n_list_a > capacity) return fail(h, DBG_ERR_ARG, "order export buffer too small");
+    return DBG_OK;
+}
+
+template <int W>
+static int order_merge_impl(dbg_t *h, const uint64_t *d_records, uint64_t n) {
+    if (n == 0 || !h->order_active) return DBG_OK;
+    LAUNCH(k_side_merge<W>, blocks_for(n), DBG_BLOCK, h->stream, ptr<SideEntry<W>>(h->b_order), h->order_cap,
+           (const u64 *)d_records, n);
+    CKK();
+    CK(cudaStreamSynchronize(h->stream));
     return DBG_OK;
 }
 
@@ -760,8 +886,12 @@ DBG_API int dbg_build_device(dbg_t *h, const uint8_t *d_bases, const uint64_t *d
     h->contigs.clear();
     h->segments.clear();
     CK(cudaMemsetAsync(h->b_ctr.p, 0, sizeof(DevCounters), h->stream));
+    h->table_ready = false;
     TRY(DISPATCH(build_impl, h, (const u8 *)d_bases, (const u64 *)d_read_off));
-    h->built = true;
+    if (flags & DBG_TABLE_ONLY) return DBG_OK;
+    TRY(DISPATCH(graph_finalize, h));
+    TRY(DISPATCH(graph_order_scan, h));
+    TRY(DISPATCH(graph_complete, h));
     return DBG_OK;
 }
 
@@ -783,6 +913,67 @@ DBG_API int dbg_build(dbg_t *h, const uint8_t *bases, const uint64_t *read_off, 
     h->pending_h2d = ev_ms(h, a, b);
     return dbg_build_device(h, ptr<const uint8_t>(h->b_bases), ptr<const uint64_t>(h->b_off), n_reads, n_bases,
                             read_idx_base, threshold, flags);
+}
+
+#define NEED_TABLE() do { if (!h) return DBG_ERR_ARG; if (!h->table_ready) return fail(h, DBG_ERR_STATE, "%s needs a node table (dbg_build* or dbg_table_reset first)", __func__); } while (0)
+
+DBG_API int dbg_graph_stage(dbg_t *h, int stage, double threshold, uint32_t flags) {
+    NEED_TABLE();
+    CK(cudaSetDevice(h->device));
+    h->n_ev = 0;
+    if (stage == 0) {
+        if (threshold != threshold) return fail(h, DBG_ERR_ARG, "threshold is NaN");
+        h->threshold = threshold;
+        h->build_flags = flags;
+        h->built = h->walked = false;
+        return DISPATCH(graph_finalize, h);
+    }
+    if (stage == 1) return DISPATCH(graph_order_scan, h);
+    if (stage == 2) return DISPATCH(graph_complete, h);
+    return fail(h, DBG_ERR_ARG, "dbg_graph_stage: stage %d out of range (0..2)", stage);
+}
+
+DBG_API int dbg_record_words(const dbg_t *h) { return h ? h->W + 3 : 0; }
+DBG_API int dbg_order_words(const dbg_t *h) { return h ? h->W + 4 : 0; }
+
+DBG_API int dbg_export_counts(dbg_t *h, uint32_t n_parts, uint64_t *counts) {
+    NEED_TABLE();
+    if (n_parts == 0 || n_parts > 4096 || !counts) return fail(h, DBG_ERR_ARG, "dbg_export_counts: bad argument");
+    CK(cudaSetDevice(h->device));
+    return DISPATCH(export_counts_impl, h, n_parts, counts);
+}
+
+DBG_API int dbg_export_records(dbg_t *h, uint32_t n_parts, const uint64_t *counts, uint64_t *d_out) {
+    NEED_TABLE();
+    if (n_parts == 0 || n_parts > 4096 || !counts) return fail(h, DBG_ERR_ARG, "dbg_export_records: bad argument");
+    CK(cudaSetDevice(h->device));
+    return DISPATCH(export_records_impl, h, n_parts, counts, d_out);
+}
+
+DBG_API int dbg_table_reset(dbg_t *h, uint64_t expected_nodes) {
+    if (!h) return DBG_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    return DISPATCH(table_reset_impl, h, expected_nodes);
+}
+
+DBG_API int dbg_merge_records(dbg_t *h, const uint64_t *d_records, uint64_t n) {
+    NEED_TABLE();
+    if (n && !d_records) return fail(h, DBG_ERR_ARG, "NULL records");
+    CK(cudaSetDevice(h->device));
+    return DISPATCH(merge_records_impl, h, d_records, n);
+}
+
+DBG_API int dbg_order_export(dbg_t *h, uint64_t *d_out, uint64_t capacity, uint64_t *n_out) {
+    NEED_TABLE();
+    if (!n_out) return fail(h, DBG_ERR_ARG, "NULL n_out");
+    CK(cudaSetDevice(h->device));
+    return DISPATCH(order_export_impl, h, d_out, capacity, n_out);
+}
+
+DBG_API int dbg_order_merge(dbg_t *h, const uint64_t *d_records, uint64_t n) {
+    NEED_TABLE();
+    CK(cudaSetDevice(h->device));
+    return DISPATCH(order_merge_impl, h, d_records, n);
 }
 
 DBG_API int dbg_stats(dbg_t *h, dbg_stats_t *out) {

@@ -1078,3 +1078,84 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_export(const Slot<W> *__restrict_
     o_flags[o] = flags[i];
     o_kept[o] = kept[i];
 }
+
+// ---------------------------------------------------------------------------------------------
+// Node records: one per occupied slot, W + 3 u64 words { key (W) | tag | cnt0,cnt1 | cnt2,cnt3 }.
+// They are what ranks exchange in the multi-GPU build: the owner of a key is
+// (hash32(key) * n_parts) >> 32, and merging records is associative (min tag, summed counters).
+// ---------------------------------------------------------------------------------------------
+template <int W> DBG_D u32 record_owner(typename KeyOf<W>::type key, u32 n_parts) {
+    return (u32)(((u64)hash32_key(key) * n_parts) >> 32);
+}
+DBG_D void key_to_words(u64 key, u64 *o) { o[0] = key; }
+DBG_D void key_to_words(K128 key, u64 *o) { o[0] = key.lo; o[1] = key.hi; }
+template <int W> DBG_D typename KeyOf<W>::type key_from_words(const u64 *w);
+template <> DBG_D u64 key_from_words<1>(const u64 *w) { return w[0]; }
+template <> DBG_D K128 key_from_words<2>(const u64 *w) { K128 r; r.lo = w[0]; r.hi = w[1]; return r; }
+
+template <int W>
+__global__ void __launch_bounds__(DBG_BLOCK) k_rec_count(const Slot<W> *__restrict__ table, u64 n_slots, u32 n_parts,
+                                                         u64 *counts) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_slots) return;
+    typename KeyOf<W>::type key = table[i].key;
+    if (key == empty_key<W>()) return;
+    atomicAdd(&counts[record_owner<W>(key, n_parts)], 1ULL);
+}
+
+template <int W>
+__global__ void __launch_bounds__(DBG_BLOCK) k_rec_scatter(const Slot<W> *__restrict__ table, u64 n_slots, u32 n_parts,
+                                                           u64 *cursors, u64 *__restrict__ out) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_slots) return;
+    typename KeyOf<W>::type key = table[i].key;
+    if (key == empty_key<W>()) return;
+    const u64 o = atomicAdd(&cursors[record_owner<W>(key, n_parts)], 1ULL) * (W + 3);
+    key_to_words(key, out + o);
+    out[o + W] = table[i].tag;
+    out[o + W + 1] = (u64)table[i].cnt[0] | ((u64)table[i].cnt[1] << 32);
+    out[o + W + 2] = (u64)table[i].cnt[2] | ((u64)table[i].cnt[3] << 32);
+}
+
+template <int W>
+__global__ void __launch_bounds__(DBG_BLOCK) k_rec_merge(Slot<W> *table, u64 n_slots, const u64 *__restrict__ recs, u64 n,
+                                                         DevCounters *ctr) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const u64 *r = recs + i * (W + 3);
+    u64 idx = table_upsert<W>(table, n_slots, key_from_words<W>(r));
+    if (idx == NONE64) { ctr->overflow = 1; return; }
+    Slot<W> *s = &table[idx];
+    const u64 tag = r[W];
+    if (tag < __ldcg(&s->tag)) atomicMin(&s->tag, tag);
+    const u32 c[4] = {(u32)r[W + 1], (u32)(r[W + 1] >> 32), (u32)r[W + 2], (u32)(r[W + 2] >> 32)};
+#pragma unroll
+    for (int b = 0; b < 4; b++) if (c[b]) atomicAdd(&s->cnt[b], c[b]);
+}
+
+// order records: W + 4 words { key (W) | first[4] }
+template <int W>
+__global__ void __launch_bounds__(DBG_BLOCK) k_side_export(const SideEntry<W> *__restrict__ st, u64 cap, u64 *__restrict__ out,
+                                                           u64 capacity, u64 *cursor) {
+    u64 e = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= cap) return;
+    typename KeyOf<W>::type key = st[e].key;
+    if (key == empty_key<W>()) return;
+    const u64 o = atomicAdd(cursor, 1ULL);
+    if (o >= capacity) return;
+    u64 *w = out + o * (W + 4);
+    key_to_words(key, w);
+#pragma unroll
+    for (int b = 0; b < 4; b++) w[W + b] = st[e].first[b];
+}
+
+template <int W>
+__global__ void __launch_bounds__(DBG_BLOCK) k_side_merge(SideEntry<W> *st, u64 cap, const u64 *__restrict__ recs, u64 n) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const u64 *r = recs + i * (W + 4);
+    u64 e = side_locate<W>(st, cap, key_from_words<W>(r), false);
+    if (e == NONE64) return;                    // not a multi-successor node of the merged graph
+#pragma unroll
+    for (int b = 0; b < 4; b++) if (r[W + b] < __ldcg(&st[e].first[b])) atomicMin(&st[e].first[b], r[W + b]);
+}

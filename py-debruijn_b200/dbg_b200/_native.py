@@ -28,7 +28,7 @@ DBG_OK = 0
 DBG_ERR_CUDA, DBG_ERR_ARG, DBG_ERR_ALPHABET, DBG_ERR_NOMEM = -1, -2, -3, -4
 DBG_ERR_STATE, DBG_ERR_ZERODIV, DBG_ERR_OVERFLOW = -5, -6, -7
 # build flags
-DBG_FINAL, DBG_EXACT_ORDER, DBG_NO_PULL_READS = 1, 2, 4
+DBG_FINAL, DBG_EXACT_ORDER, DBG_NO_PULL_READS, DBG_TABLE_ONLY = 1, 2, 4, 8
 # node flags
 NODE_START, NODE_BRANCH, NODE_DEADEND, NODE_PULLED, NODE_MULTI = 0x02, 0x04, 0x08, 0x10, 0x20
 # terminal kinds
@@ -70,6 +70,15 @@ SYMBOLS = {
     'dbg_build': (C.c_int, [_P, _P, _P, C.c_uint64, C.c_uint64, C.c_double, C.c_uint32]),
     'dbg_build_device': (C.c_int, [_P, _P, _P, C.c_uint64, C.c_uint64, C.c_uint64, C.c_double, C.c_uint32]),
     'dbg_stats': (C.c_int, [_P, C.POINTER(Stats)]),
+    'dbg_graph_stage': (C.c_int, [_P, C.c_int, C.c_double, C.c_uint32]),
+    'dbg_record_words': (C.c_int, [_P]),
+    'dbg_order_words': (C.c_int, [_P]),
+    'dbg_export_counts': (C.c_int, [_P, C.c_uint32, _P]),
+    'dbg_export_records': (C.c_int, [_P, C.c_uint32, _P, _P]),
+    'dbg_table_reset': (C.c_int, [_P, C.c_uint64]),
+    'dbg_merge_records': (C.c_int, [_P, _P, C.c_uint64]),
+    'dbg_order_export': (C.c_int, [_P, _P, C.c_uint64, C.POINTER(C.c_uint64)]),
+    'dbg_order_merge': (C.c_int, [_P, _P, C.c_uint64]),
     'dbg_export_nodes': (C.c_int, [_P] + [_P] * 7),
     'dbg_branch_nodes': (C.c_int, [_P, _P]),
     'dbg_pulled_nodes': (C.c_int, [_P, _P]),

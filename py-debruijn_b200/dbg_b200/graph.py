@@ -135,6 +135,68 @@ class Graph:
         self.lib.check(self.h, rc)
         return self
 
+    # ---- multi-GPU building blocks (include/dbg_b200.h) ------------------------------------
+    def _flags(self, final, exact_order, pull_reads):
+        return (N.DBG_FINAL if final else 0) | (N.DBG_EXACT_ORDER if exact_order else 0) | \
+               (0 if pull_reads else N.DBG_NO_PULL_READS)
+
+    def build_table(self, reads=None, packed=None, read_idx_base=0):
+        """Window loop only (host buffers): leaves the node table, no graph stages."""
+        bases, off = packed if packed is not None else pack_reads(reads)
+        self.reads = reads
+        self._reset_cache()
+        self._keep = (bases, off)
+        self.n_reads = len(off) - 1
+        rc = self.lib.dbg_build(self.h, bases.ctypes.data if len(bases) else None, off.ctypes.data,
+                                self.n_reads, int(read_idx_base), 3.0, N.DBG_TABLE_ONLY)
+        self.lib.check(self.h, rc)
+        return self
+
+    def build_table_device(self, d_bases_ptr, d_off_ptr, n_reads, n_bases, read_idx_base=0):
+        self.reads = None
+        self._reset_cache()
+        self.n_reads = int(n_reads)
+        rc = self.lib.dbg_build_device(self.h, d_bases_ptr, d_off_ptr, int(n_reads), int(n_bases),
+                                       int(read_idx_base), 3.0, N.DBG_TABLE_ONLY)
+        self.lib.check(self.h, rc)
+        return self
+
+    def record_words(self):
+        return self.lib.dbg_record_words(self.h)
+
+    def order_words(self):
+        return self.lib.dbg_order_words(self.h)
+
+    def export_counts(self, n_parts):
+        counts = np.zeros(n_parts, np.uint64)
+        self.lib.check(self.h, self.lib.dbg_export_counts(self.h, n_parts, counts.ctypes.data))
+        return counts
+
+    def export_records(self, n_parts, counts, d_out_ptr):
+        counts = np.ascontiguousarray(counts, dtype=np.uint64)
+        self.lib.check(self.h, self.lib.dbg_export_records(self.h, n_parts, counts.ctypes.data, d_out_ptr))
+
+    def table_reset(self, expected_nodes):
+        self._reset_cache()
+        self.lib.check(self.h, self.lib.dbg_table_reset(self.h, int(expected_nodes)))
+
+    def merge_records(self, d_ptr, n):
+        self.lib.check(self.h, self.lib.dbg_merge_records(self.h, d_ptr, int(n)))
+
+    def graph_stage(self, stage, threshold=3, final=False, exact_order=True, pull_reads=True):
+        self.final = bool(final)
+        self._reset_cache()
+        self.lib.check(self.h, self.lib.dbg_graph_stage(self.h, int(stage), float(threshold),
+                                                        self._flags(final, exact_order, pull_reads)))
+
+    def order_export(self, d_out_ptr, capacity):
+        n = C.c_uint64()
+        self.lib.check(self.h, self.lib.dbg_order_export(self.h, d_out_ptr, int(capacity), C.byref(n)))
+        return int(n.value)
+
+    def order_merge(self, d_ptr, n):
+        self.lib.check(self.h, self.lib.dbg_order_merge(self.h, d_ptr, int(n)))
+
     def set_stream(self, cuda_stream_ptr):
         self.lib.check(self.h, self.lib.dbg_set_stream(self.h, cuda_stream_ptr))
 
