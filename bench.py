@@ -63,6 +63,31 @@ def make_reads(cfg, seed_offset=0, G=None):
     return bases, off
 
 
+def make_reads_shard(cfg, rank, world):
+    """The distributed workload: ONE read set over a genome `world` times the config's size (weak
+    scaling: per-GPU work fixed), deduped by start position, rank r holding the contiguous slice
+    shard_bounds()[r] of the global read list.  Every rank derives the same global list."""
+    G = cfg['G'] * world
+    L, cov = cfg['L'], cfg['cov']
+    rng = np.random.default_rng(cfg['seed'] + 77 * world)
+    genome = rng.integers(0, 4, G, dtype=np.uint8)
+    n = G * cov // L
+    starts = rng.integers(0, G - L + 1, n)
+    _, first = np.unique(starts, return_index=True)               # equal start <=> equal read (random genome)
+    starts = starts[np.sort(first)]
+    n_total = len(starts)
+    lo, hi = n_total * rank // world, n_total * (rank + 1) // world
+    mine = starts[lo:hi]
+    mat = genome[mine[:, None] + np.arange(L)[None, :]]
+    if cfg['err']:
+        r2 = np.random.default_rng(cfg['seed'] + 1000 + rank)
+        flip = r2.random(mat.shape) < cfg['err']
+        mat = np.where(flip, (mat + r2.integers(1, 4, mat.shape, dtype=np.uint8)) & 3, mat).astype(np.uint8)
+    bases = np.ascontiguousarray(ASCII[mat]).reshape(-1)
+    off = (np.arange(mat.shape[0] + 1, dtype=np.uint64) * np.uint64(L))
+    return bases, off, lo, n_total
+
+
 def n_windows_of(off, k):
     lens = np.diff(off.astype(np.int64))
     return int(np.maximum(lens - k, 0).sum())
@@ -196,10 +221,15 @@ def run_reference(args, cfg, rank):
 
 
 def workload_config(args, cfg, off, nwin, world):
-    return {'workload': cfg['name'], 'config_key': args.config, 'k': cfg['k'], 'threshold': cfg['thr'],
-            'genome_bp': cfg['G'], 'read_len': cfg['L'], 'coverage': cfg['cov'], 'error_rate': cfg['err'],
+    wl = cfg['name'] if world == 1 else \
+        ('%s; genome scaled x%d (%d bp) so per-GPU work is fixed, ONE graph built by %d ranks' %
+         (cfg['name'], world, cfg['G'] * world, world))
+    return {'workload': wl, 'config_key': args.config, 'k': cfg['k'], 'threshold': cfg['thr'],
+            'genome_bp': cfg['G'] * world, 'read_len': cfg['L'], 'coverage': cfg['cov'], 'error_rate': cfg['err'],
             'reads_per_gpu': int(len(off) - 1), 'windows_per_gpu': int(nwin), 'final': False,
-            'parallelism': 'single GPU' if world == 1 else 'replicas x%d (independent read sets, no exchange)' % world,
+            'parallelism': 'single GPU' if world == 1 else
+            ('reads sharded x%d; node records hash-partitioned by owner, NCCL all-to-all + all-gather; graph stages '
+             'and contig walk replicated on every rank' % world),
             'l2_policy': 'inputs (ASCII reads + node table) larger than the 126 MB L2; no explicit flush'}
 
 
@@ -220,7 +250,11 @@ def run_dbg(args, cfg, rank, local_rank, world):
         dist.init_process_group('nccl', device_id=dev)
 
     k, thr = cfg['k'], cfg['thr']
-    bases, off = make_reads(cfg, seed_offset=rank * 7919)
+    read_base = 0
+    if world > 1:
+        bases, off, read_base, _ = make_reads_shard(cfg, rank, world)
+    else:
+        bases, off = make_reads(cfg)
     n_reads, n_bases = len(off) - 1, len(bases)
     nwin = n_windows_of(off, k)
     d_bases = torch.from_numpy(bases).to(dev)
@@ -238,12 +272,23 @@ def run_dbg(args, cfg, rank, local_rank, world):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    dist_ms = {}
+
     def step_device():
-        g.build_device(d_bases.data_ptr(), d_off.data_ptr(), n_reads, n_bases, threshold=thr, final=False)
+        if world > 1:
+            from dbg_b200 import dist as ddist
+            ddist.build_distributed(g, None, read_base, threshold=thr, final=False, timings=dist_ms,
+                                    local_device=(d_bases.data_ptr(), d_off.data_ptr(), n_reads, n_bases))
+        else:
+            g.build_device(d_bases.data_ptr(), d_off.data_ptr(), n_reads, n_bases, threshold=thr, final=False)
         g.walk(stop_at_branch=True)
 
     def step_host():
-        g.build(None, threshold=thr, final=False, packed=(hb_np, ho_np))
+        if world > 1:
+            from dbg_b200 import dist as ddist
+            ddist.build_distributed(g, (hb_np, ho_np), read_base, threshold=thr, final=False)
+        else:
+            g.build(None, threshold=thr, final=False, packed=(hb_np, ho_np))
         return g.walk(stop_at_branch=True)
 
     def timed(fn, steps, collect=None):
@@ -275,7 +320,9 @@ def run_dbg(args, cfg, rank, local_rank, world):
                   'ms_tips', 'ms_pull_reads', 'ms_build_total', 'ms_walk_rank', 'ms_walk_emit', 'ms_walk_total'):
             stage[f] = stage.get(f, 0.0) + getattr(st, f) / args.steps
 
+    dist_ms.clear()
     ms_total = timed(step_device, args.steps, collect)
+    dist_stage = {kk: round(v / args.steps, 4) for kk, v in dist_ms.items()}
     st = g.stats()
     launches = int(st.n_launches)
     for _ in range(2):
@@ -285,8 +332,14 @@ def run_dbg(args, cfg, rank, local_rank, world):
     clocks = sampler.stop() if rank == 0 else None
 
     ms_step = ms_total / args.steps
-    value = world * nwin / (ms_step * 1e-3)
-    e2e_value = world * nwin / (ms_e2e / args.steps * 1e-3)
+    if world > 1:
+        tw = torch.tensor([nwin], device=dev, dtype=torch.float64)
+        dist.all_reduce(tw)
+        total_windows = float(tw.item())
+    else:
+        total_windows = float(nwin)
+    value = total_windows / (ms_step * 1e-3)
+    e2e_value = total_windows / (ms_e2e / args.steps * 1e-3)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -302,8 +355,9 @@ def run_dbg(args, cfg, rank, local_rank, world):
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'u64' if k <= 31 else 'u128', 'data': 'synthetic',
         'config': workload_config(args, cfg, off, nwin, world),
-        'build_kmers_per_sec': world * nwin / (stage['ms_build_total'] * 1e-3),
-        'contigs_per_sec': world * int(st.n_contigs) / (stage['ms_walk_total'] * 1e-3),
+        'build_kmers_per_sec': total_windows / ((ms_step - stage['ms_walk_total']) * 1e-3),
+        'contigs_per_sec': int(st.n_contigs) / (stage['ms_walk_total'] * 1e-3),
+        'dist_stage_ms': dist_stage if world > 1 else None,
         'graph': {'nodes': int(st.n_nodes), 'edges': int(st.n_edges), 'branch': int(st.n_branch),
                   'starts': int(st.n_starts), 'contigs': int(st.n_contigs), 'table_slots': int(st.table_slots),
                   'table_bytes': int(st.table_bytes), 'jump_rounds': int(st.jump_rounds)},

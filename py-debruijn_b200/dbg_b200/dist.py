@@ -57,10 +57,12 @@ def shard_bounds(n_reads, world):
 
 
 def build_distributed(graph: Graph, local_packed, read_idx_base, threshold=3, final=False, exact_order=True,
-                      pull_reads=True, group=None, timings=None):
+                      pull_reads=True, group=None, timings=None, local_device=None):
     """Run the distributed construct_graph on `graph` (one per rank).  `local_packed` =
-    (uint8 bases, uint64 offsets) of this rank's reads, `read_idx_base` the global index of its
-    first read.  Returns the LOCAL pull-out flags (uint8 per local read)."""
+    (uint8 bases, uint64 offsets) of this rank's reads in HOST memory, or pass
+    `local_device` = (d_bases_ptr, d_off_ptr, n_reads, n_bases) for reads already in HBM;
+    `read_idx_base` is the global index of the rank's first read.  Returns the LOCAL pull-out
+    flags (uint8 per local read)."""
     world = dist.get_world_size(group)
     dev = _device_of(graph, group)
     cuda = dev.type == 'cuda'
@@ -77,7 +79,10 @@ def build_distributed(graph: Graph, local_packed, read_idx_base, threshold=3, fi
     import time
     t0 = time.perf_counter()
     # 1. local window loop
-    graph.build_table(packed=local_packed, read_idx_base=read_idx_base)
+    if local_device is not None:
+        graph.build_table_device(*local_device, read_idx_base=read_idx_base)
+    else:
+        graph.build_table(packed=local_packed, read_idx_base=read_idx_base)
     t0 = tick('local_table_ms', t0)
     rw = graph.record_words()
     # 2. records grouped by owner, 3. all-to-all
