@@ -76,6 +76,12 @@ def build_distributed(graph: Graph, local_packed, read_idx_base, threshold=3, fi
             return time.perf_counter()
         return t0
 
+    def fence():
+        """The library runs on its own stream: make the host wait for torch's collectives before
+        the library reads what they wrote (the library itself returns only after its stream is idle)."""
+        if cuda:
+            torch.cuda.current_stream(dev).synchronize()
+
     import time
     t0 = time.perf_counter()
     # 1. local window loop
@@ -96,6 +102,7 @@ def build_distributed(graph: Graph, local_packed, read_idx_base, threshold=3, fi
     recv = torch.empty((sum(rc), rw), dtype=torch.int64, device=dev)
     dist.all_to_all_single(recv, send, output_split_sizes=rc, input_split_sizes=[int(c) for c in counts],
                            group=group)
+    fence()
     t0 = tick('exchange_ms', t0)
     # 4. merge what this rank owns
     graph.table_reset(max(1, recv.shape[0]))
@@ -106,6 +113,7 @@ def build_distributed(graph: Graph, local_packed, read_idx_base, threshold=3, fi
     t0 = tick('shard_merge_ms', t0)
     # 5. every shard everywhere -> the full table
     full, _ = _all_gather_var(shard, group)
+    fence()
     t0 = tick('gather_ms', t0)
     graph.table_reset(max(1, full.shape[0]))
     graph.merge_records(full.data_ptr(), full.shape[0])
@@ -121,6 +129,7 @@ def build_distributed(graph: Graph, local_packed, read_idx_base, threshold=3, fi
         mine = torch.empty((cap, ow), dtype=torch.int64, device=dev)
         n = graph.order_export(mine.data_ptr(), cap)
         allrec, _ = _all_gather_var(mine[:n].contiguous(), group)
+        fence()
         graph.order_merge(allrec.data_ptr(), allrec.shape[0])
     graph.graph_stage(2, threshold, final, exact_order, pull_reads)
     t0 = tick('graph_ms', t0)

@@ -198,7 +198,13 @@ class Graph:
         self.lib.check(self.h, self.lib.dbg_order_merge(self.h, d_ptr, int(n)))
 
     def set_stream(self, cuda_stream_ptr):
-        self.lib.check(self.h, self.lib.dbg_set_stream(self.h, cuda_stream_ptr))
+        """Run on the caller's stream.  0 / None is CUDA's legacy default stream (what
+        torch.cuda.current_stream().cuda_stream returns by default), passed as cudaStreamLegacy;
+        use own_stream() to go back to the handle's private stream."""
+        self.lib.check(self.h, self.lib.dbg_set_stream(self.h, cuda_stream_ptr or 1))
+
+    def own_stream(self):
+        self.lib.check(self.h, self.lib.dbg_set_stream(self.h, None))
 
     def stats(self):
         s = N.Stats()
