@@ -401,8 +401,8 @@ def run_dbg(args, cfg, rank, local_rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=10)
-    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--steps', type=int, default=100)
+    ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--config', default='c2', choices=sorted(CONFIGS))
     ap.add_argument('--impl', default='dbg', choices=['dbg', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')

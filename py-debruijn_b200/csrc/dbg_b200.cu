@@ -138,7 +138,7 @@ static float ev_ms(dbg_t *h, int a, int b) {
 // -------------------------------------------------------------------------------------------------
 // sort (tag, slot) pairs by tag: the reference's dict order is first-occurrence order
 // -------------------------------------------------------------------------------------------------
-static int sort_by_tag(dbg_t *h, uint64_t n, u32 *d_sorted_slots_out) {
+static int sort_by_tag(dbg_t *h, uint64_t n, u32 *d_sorted_slots_out, int begin_bit) {
     // input pairs are in b_tag / b_slot; sorted slots land in d_sorted_slots_out
     if (n == 0) return DBG_OK;
 #ifdef DBG_EMU
@@ -152,11 +152,11 @@ static int sort_by_tag(dbg_t *h, uint64_t n, u32 *d_sorted_slots_out) {
     TRY(reserve(h, h->b_tag2, n * 8));
     size_t tmp = 0;
     CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, ptr<u64>(h->b_tag), ptr<u64>(h->b_tag2), ptr<u32>(h->b_slot),
-                                       d_sorted_slots_out, (int64_t)n, 0, 64, h->stream));
+                                       d_sorted_slots_out, (int64_t)n, begin_bit, 64, h->stream));
     TRY(reserve(h, h->b_sorttmp, tmp));
     h->st.n_launches++;                                   // cub launches several kernels; counted as one
     CK(cub::DeviceRadixSort::SortPairs(h->b_sorttmp.p, tmp, ptr<u64>(h->b_tag), ptr<u64>(h->b_tag2),
-                                       ptr<u32>(h->b_slot), d_sorted_slots_out, (int64_t)n, 0, 64, h->stream));
+                                       ptr<u32>(h->b_slot), d_sorted_slots_out, (int64_t)n, begin_bit, 64, h->stream));
 #endif
     return DBG_OK;
 }
@@ -200,7 +200,8 @@ static int collect_sorted(dbg_t *h, u32 want, uint64_t expect, DevBuf &out, u64 
     LAUNCH(k_collect<W>, blocks_for(h->n_slots), DBG_BLOCK, h->stream, ptr<const Slot<W>>(h->b_table), h->n_slots,
            ptr<const u8>(h->b_flags), want, ptr<u64>(h->b_tag), ptr<u32>(h->b_slot), cursor);
     CKK();
-    return sort_by_tag(h, expect, ptr<u32>(out));
+    // a start's first occurrence is at position 0 of its read: only the read-index half of the tag orders starts
+    return sort_by_tag(h, expect, ptr<u32>(out), want == F_START ? 32 : 0);
 }
 
 // side set (dbg_kernels.cuh) of the slots whose flags hit `want`: entries in b_order, bitmap in b_bitmap
@@ -938,14 +939,14 @@ DBG_API int dbg_order_words(const dbg_t *h) { return h ? h->W + 4 : 0; }
 
 DBG_API int dbg_export_counts(dbg_t *h, uint32_t n_parts, uint64_t *counts) {
     NEED_TABLE();
-    if (n_parts == 0 || n_parts > 4096 || !counts) return fail(h, DBG_ERR_ARG, "dbg_export_counts: bad argument");
+    if (n_parts == 0 || n_parts > DBG_MAX_PARTS || !counts) return fail(h, DBG_ERR_ARG, "dbg_export_counts: bad argument");
     CK(cudaSetDevice(h->device));
     return DISPATCH(export_counts_impl, h, n_parts, counts);
 }
 
 DBG_API int dbg_export_records(dbg_t *h, uint32_t n_parts, const uint64_t *counts, uint64_t *d_out) {
     NEED_TABLE();
-    if (n_parts == 0 || n_parts > 4096 || !counts) return fail(h, DBG_ERR_ARG, "dbg_export_records: bad argument");
+    if (n_parts == 0 || n_parts > DBG_MAX_PARTS || !counts) return fail(h, DBG_ERR_ARG, "dbg_export_records: bad argument");
     CK(cudaSetDevice(h->device));
     return DISPATCH(export_records_impl, h, n_parts, counts, d_out);
 }

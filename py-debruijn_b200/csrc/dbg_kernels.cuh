@@ -1093,28 +1093,52 @@ template <int W> DBG_D typename KeyOf<W>::type key_from_words(const u64 *w);
 template <> DBG_D u64 key_from_words<1>(const u64 *w) { return w[0]; }
 template <> DBG_D K128 key_from_words<2>(const u64 *w) { K128 r; r.lo = w[0]; r.hi = w[1]; return r; }
 
+// Both kernels aggregate per block in shared memory first: one global atomic per (block, owner)
+// instead of one per record (millions of atomics on a handful of addresses serialise in L2).
+#define DBG_MAX_PARTS 1024
 template <int W>
 __global__ void __launch_bounds__(DBG_BLOCK) k_rec_count(const Slot<W> *__restrict__ table, u64 n_slots, u32 n_parts,
                                                          u64 *counts) {
+    __shared__ u32 s_cnt[DBG_MAX_PARTS];
+    for (u32 p = threadIdx.x; p < n_parts; p += blockDim.x) s_cnt[p] = 0;
+    __syncthreads();
     u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_slots) return;
-    typename KeyOf<W>::type key = table[i].key;
-    if (key == empty_key<W>()) return;
-    atomicAdd(&counts[record_owner<W>(key, n_parts)], 1ULL);
+    if (i < n_slots) {
+        typename KeyOf<W>::type key = table[i].key;
+        if (key != empty_key<W>()) atomicAdd(&s_cnt[record_owner<W>(key, n_parts)], 1u);
+    }
+    __syncthreads();
+    for (u32 p = threadIdx.x; p < n_parts; p += blockDim.x)
+        if (s_cnt[p]) atomicAdd(&counts[p], (u64)s_cnt[p]);
 }
 
 template <int W>
 __global__ void __launch_bounds__(DBG_BLOCK) k_rec_scatter(const Slot<W> *__restrict__ table, u64 n_slots, u32 n_parts,
                                                            u64 *cursors, u64 *__restrict__ out) {
+    __shared__ u32 s_cnt[DBG_MAX_PARTS];
+    __shared__ u64 s_base[DBG_MAX_PARTS];
+    for (u32 p = threadIdx.x; p < n_parts; p += blockDim.x) s_cnt[p] = 0;
+    __syncthreads();
     u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_slots) return;
-    typename KeyOf<W>::type key = table[i].key;
-    if (key == empty_key<W>()) return;
-    const u64 o = atomicAdd(&cursors[record_owner<W>(key, n_parts)], 1ULL) * (W + 3);
-    key_to_words(key, out + o);
-    out[o + W] = table[i].tag;
-    out[o + W + 1] = (u64)table[i].cnt[0] | ((u64)table[i].cnt[1] << 32);
-    out[o + W + 2] = (u64)table[i].cnt[2] | ((u64)table[i].cnt[3] << 32);
+    typename KeyOf<W>::type key = empty_key<W>();
+    u32 owner = 0, local = 0;
+    if (i < n_slots) key = table[i].key;
+    const bool have = key != empty_key<W>();
+    if (have) {
+        owner = record_owner<W>(key, n_parts);
+        local = atomicAdd(&s_cnt[owner], 1u);
+    }
+    __syncthreads();
+    for (u32 p = threadIdx.x; p < n_parts; p += blockDim.x)
+        if (s_cnt[p]) s_base[p] = atomicAdd(&cursors[p], (u64)s_cnt[p]);
+    __syncthreads();
+    if (have) {
+        const u64 o = (s_base[owner] + local) * (W + 3);
+        key_to_words(key, out + o);
+        out[o + W] = table[i].tag;
+        out[o + W + 1] = (u64)table[i].cnt[0] | ((u64)table[i].cnt[1] << 32);
+        out[o + W + 2] = (u64)table[i].cnt[2] | ((u64)table[i].cnt[3] << 32);
+    }
 }
 
 template <int W>
@@ -1138,15 +1162,22 @@ template <int W>
 __global__ void __launch_bounds__(DBG_BLOCK) k_side_export(const SideEntry<W> *__restrict__ st, u64 cap, u64 *__restrict__ out,
                                                            u64 capacity, u64 *cursor) {
     u64 e = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= cap) return;
-    typename KeyOf<W>::type key = st[e].key;
-    if (key == empty_key<W>()) return;
-    const u64 o = atomicAdd(cursor, 1ULL);
+    typename KeyOf<W>::type key = empty_key<W>();
+    if (e < cap) key = st[e].key;
+    const bool have = key != empty_key<W>();
+    const u32 b = __ballot_sync(0xFFFFFFFFu, have);
+    if (!b) return;
+    const u32 lane = threadIdx.x & 31;
+    u64 base = 0;
+    if (lane == 0) base = atomicAdd(cursor, (u64)__popc(b));
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    if (!have) return;
+    const u64 o = base + __popc(b & ((1u << lane) - 1));
     if (o >= capacity) return;
     u64 *w = out + o * (W + 4);
     key_to_words(key, w);
 #pragma unroll
-    for (int b = 0; b < 4; b++) w[W + b] = st[e].first[b];
+    for (int c = 0; c < 4; c++) w[W + c] = st[e].first[c];
 }
 
 template <int W>

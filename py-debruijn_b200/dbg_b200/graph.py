@@ -273,17 +273,16 @@ class Graph:
         return out
 
     # ---- output_contigs ------------------------------------------------------------------
+    CONTIG_DTYPE = np.dtype([('start', np.uint32), ('n_nodes', np.uint32), ('terminal', np.uint32),
+                             ('kind', np.uint32), ('seg_begin', np.uint64), ('seg_end', np.uint64)])
+
     def walk(self, stop_at_branch=True):
         n = C.c_uint64()
         self.lib.check(self.h, self.lib.dbg_walk(self.h, 1 if stop_at_branch else 0, C.byref(n)))
-        arr = (N.Contig * n.value)()
-        self.lib.check(self.h, self.lib.dbg_contigs(self.h, arr))
-        self._contigs = np.frombuffer(arr, dtype=np.dtype([
-            ('start', np.uint32), ('n_nodes', np.uint32), ('terminal', np.uint32), ('kind', np.uint32),
-            ('seg_begin', np.uint64), ('seg_end', np.uint64)]), count=n.value).copy() if n.value else \
-            np.zeros(0, dtype=[('start', np.uint32), ('n_nodes', np.uint32), ('terminal', np.uint32),
-                               ('kind', np.uint32), ('seg_begin', np.uint64), ('seg_end', np.uint64)])
-        return self._contigs
+        out = np.empty(n.value, dtype=self.CONTIG_DTYPE)           # same layout as dbg_contig_t (32 bytes)
+        self.lib.check(self.h, self.lib.dbg_contigs(self.h, out.ctypes.data if n.value else None))
+        self._contigs = out
+        return out
 
     def contig_descriptors(self):
         return self._contigs
