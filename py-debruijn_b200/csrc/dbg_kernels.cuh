@@ -551,13 +551,14 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_finalize(const Slot<W> *__restric
                                                         u16 *__restrict__ kept, u32 *__restrict__ succ,
                                                         DevCounters *ctr) {
     typedef typename KeyOf<W>::type K;
-    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    bool occ = false;
-    u32 f = 0, word = 0, sx = NONE32;
-    if (i < n_slots) {
+    // grid-stride; the five counters are summed in registers and leave the block as ONE atomic each
+    // (one atomic per warp on the same five words used to serialise in L2)
+    u32 c_nodes = 0, c_edges = 0, c_starts = 0, c_branch = 0, c_multi = 0;
+    const K mask = key_mask<W>(k);
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += (u64)gridDim.x * blockDim.x) {
+        u32 f = 0, word = 0, sx = NONE32;
         K key = table[i].key;
-        occ = key != empty_key<W>();
-        if (occ) {
+        if (key != empty_key<W>()) {
             u32 cnt[4] = { table[i].cnt[0], table[i].cnt[1], table[i].cnt[2], table[i].cnt[3] };
             u64 tag = table[i].tag;
             word = prune_successors(cnt, (const u64 *)0, threshold);
@@ -565,29 +566,35 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_finalize(const Slot<W> *__restric
             f = F_OCC | ((u32)tag == 0 ? F_START : 0) | (nk > 1 ? F_BRANCH : 0) |
                 (m == 0 ? F_DEADEND : 0) | (m > 1 ? F_MULTI : 0);
             if (nk == 1) {
-                K sk = key_roll(key, (u32)kept_base(word, 0), key_mask<W>(k));
+                K sk = key_roll(key, (u32)kept_base(word, 0), mask);
                 u64 fi = table_find<W>(table, n_slots, sk);
                 if (fi == NONE64) raise_fault(ctr, FAULT_SUCC_MISSING, (u32)i);
                 sx = (u32)fi;
             }
+            c_nodes++; c_edges += (u32)m;
+            c_starts += (f & F_START) ? 1u : 0u; c_branch += nk > 1 ? 1u : 0u; c_multi += m > 1 ? 1u : 0u;
         }
         flags[i] = (u8)f;
         kept[i] = (u16)word;
         succ[i] = sx;
     }
-    u32 lane = threadIdx.x & 31;
-    u32 b_occ = __ballot_sync(0xFFFFFFFFu, occ);
-    u32 b_start = __ballot_sync(0xFFFFFFFFu, f & F_START);
-    u32 b_branch = __ballot_sync(0xFFFFFFFFu, f & F_BRANCH);
-    u32 b_multi = __ballot_sync(0xFFFFFFFFu, f & F_MULTI);
-    u32 e = (u32)distinct_count(word);
-    for (int d = 16; d > 0; d >>= 1) e += __shfl_down_sync(0xFFFFFFFFu, e, d);
-    if (lane == 0 && b_occ) {
-        atomicAdd(&ctr->n_nodes, (u64)__popc(b_occ));
-        if (e) atomicAdd(&ctr->n_edges, (u64)e);
-        if (b_start) atomicAdd(&ctr->n_starts, (u64)__popc(b_start));
-        if (b_branch) atomicAdd(&ctr->n_branch, (u64)__popc(b_branch));
-        if (b_multi) atomicAdd(&ctr->n_multi, (u64)__popc(b_multi));
+    __shared__ u32 s_sum[5];
+    if (threadIdx.x < 5) s_sum[threadIdx.x] = 0;
+    __syncthreads();
+    u32 v[5] = {c_nodes, c_edges, c_starts, c_branch, c_multi};
+#pragma unroll
+    for (int q = 0; q < 5; q++) {
+        u32 x = v[q];
+        for (int d = 16; d > 0; d >>= 1) x += __shfl_down_sync(0xFFFFFFFFu, x, d);
+        if ((threadIdx.x & 31) == 0 && x) atomicAdd(&s_sum[q], x);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (s_sum[0]) atomicAdd(&ctr->n_nodes, (u64)s_sum[0]);
+        if (s_sum[1]) atomicAdd(&ctr->n_edges, (u64)s_sum[1]);
+        if (s_sum[2]) atomicAdd(&ctr->n_starts, (u64)s_sum[2]);
+        if (s_sum[3]) atomicAdd(&ctr->n_branch, (u64)s_sum[3]);
+        if (s_sum[4]) atomicAdd(&ctr->n_multi, (u64)s_sum[4]);
     }
 }
 
