@@ -80,6 +80,9 @@ typedef struct {
     uint64_t table_bytes;
     uint64_t hll_estimate;   /* distinct-node estimate used to size the table                 */
     uint64_t n_launches;     /* kernels this library launched in the last dbg_build* + dbg_walk */
+    uint64_t n_chunk_instances; /* super-k-mer (chunk) instances the window loop was grouped into  */
+    uint64_t n_chunk_list;   /* first / last chunks of reads (kept in a list, not deduplicated)    */
+    uint64_t chunk_slots;    /* slots of the chunk table                                           */
     uint32_t key_words;      /* 1 (k <= 31) or 2                                              */
     uint32_t jump_rounds;    /* pointer-jumping rounds run by dbg_walk                        */
     uint32_t n_insert_passes;/* L2-resident partition passes of the table build               */
@@ -87,7 +90,9 @@ typedef struct {
     /* device time per stage, CUDA events on the handle's stream, milliseconds */
     float ms_h2d, ms_pack, ms_estimate, ms_table_init, ms_insert, ms_finalize, ms_order,
           ms_lists, ms_tips, ms_pull_reads, ms_build_total, ms_walk_rank, ms_walk_emit,
-          ms_walk_total;
+          ms_walk_total,
+          /* parts of ms_insert when the chunk build runs (dbg_chunks.cuh): */
+          ms_chunk_insert, ms_expand_sketch, ms_expand, reserved1;
 } dbg_stats_t;
 
 typedef struct {

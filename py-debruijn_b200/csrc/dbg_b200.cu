@@ -14,6 +14,7 @@
 // never loaded by the product.
 #include <math.h>
 #include <stdarg.h>
+#include <stddef.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -39,6 +40,7 @@
 
 #include "../../include/dbg_b200.h"
 #include "dbg_kernels.cuh"
+#include "dbg_chunks.cuh"
 
 #define DBG_ABI_VERSION 1
 #define MAX_ENUM_CONTIGS (1ull << 26)
@@ -53,7 +55,7 @@ struct DevBuf {                 // grow-only device buffer: repeated builds on o
     size_t cap = 0;
 };
 
-enum { EV_MAX = 24 };
+enum { EV_MAX = 64 };
 
 struct dbg_handle {
     int device = 0;
@@ -72,7 +74,8 @@ struct dbg_handle {
     const uint64_t *d_off = nullptr;          // offsets in use (caller's for build_device, ours for build)
     DevBuf b_bases, b_off, b_packed, b_tile, b_table, b_flags, b_kept, b_succ, b_link, b_ctr, b_hll,
            b_order, b_tag, b_tag2, b_slot, b_slot2, b_sorttmp, b_branch, b_starts, b_pulled, b_readflags,
-           b_recs, b_cnt32, b_off64, b_contig, b_junction, b_split, b_h8, b_chunk, b_bitmap, b_scratch[6];
+           b_recs, b_cnt32, b_off64, b_contig, b_junction, b_split, b_h8, b_chunk, b_bitmap, b_stmask, b_vmask,
+           b_spanread, b_cc, b_ctable, b_clist, b_super, b_scratch[6];
     DevCounters ctr;
     dbg_stats_t st;
     std::vector<uint32_t> branch, pulled;     // reference order
@@ -284,36 +287,13 @@ static int tip_prune(dbg_t *h) {
     return DBG_OK;
 }
 
+// ---- per-window table build (k_estimate + k_insert passes); kept as the A/B baseline of the chunk build ----
 template <int W>
-static int build_impl(dbg_t *h, const u8 *d_bases, const u64 *d_off) {
+static int build_windows(dbg_t *h, const u64 *d_off, int e0, int e1) {
     typedef Slot<W> S;
     const int k = h->k;
     dbg_stats_t &st = h->st;
     DevCounters *d_ctr = ptr<DevCounters>(h->b_ctr);
-    const int e0 = ev_mark(h);
-
-    // ---- read packing (kernel 1) ----
-    h->n_words = cdiv(h->n_bases, 32);
-    TRY(reserve(h, h->b_packed, (h->n_words + 4) * 8));
-    CK(cudaMemsetAsync(ptr<u64>(h->b_packed) + h->n_words, 0, 4 * 8, h->stream));
-    h->n_tiles = cdiv(h->n_bases, DBG_TILE);
-    TRY(reserve(h, h->b_tile, (h->n_tiles + 2) * 4));
-    if (h->n_bases) {
-        LAUNCH(k_pack, blocks_for(h->n_words), DBG_BLOCK, h->stream, d_bases, h->n_bases, ptr<u64>(h->b_packed),
-               h->n_words, (int)(((uintptr_t)d_bases & 15) == 0), d_ctr);
-        CKK();
-    }
-    if (h->n_reads) {
-        LAUNCH(k_read_stats, blocks_for(h->n_reads), DBG_BLOCK, h->stream, d_off, h->n_reads, k, d_ctr);
-        CKK();
-    }
-    if (h->n_bases) {
-        LAUNCH(k_tile_first, blocks_for(h->n_tiles + 1), DBG_BLOCK, h->stream, d_off, h->n_reads, h->n_bases,
-               h->n_tiles, ptr<u32>(h->b_tile));
-        CKK();
-    }
-    const int e1 = ev_mark(h);
-
     // ---- table sizing: HyperLogLog estimate of the distinct node count ----
     uint64_t est = 0;
     if (h->n_bases) {
@@ -419,6 +399,258 @@ static int build_impl(dbg_t *h, const u8 *d_bases, const u64 *d_off) {
     }
     h->table_ready = true;
     return DBG_OK;
+}
+
+
+// ---- chunk table build (dbg_chunks.cuh): masks -> chunk table + boundary list -> node table ----
+struct ChunkGeom { int w, logw, m; };
+static ChunkGeom chunk_geom(int k) {
+    int t = k - 4;                                  // leave the minimizer at least ~5 bases where k allows it
+    if (t < 1) t = 1;
+    if (t > CH_WMAX) t = CH_WMAX;
+    ChunkGeom g;
+    g.logw = 0;
+    while ((2 << g.logw) <= t) g.logw++;
+    g.w = 1 << g.logw;                              // nodes per chunk at most (power of two <= 16, <= k)
+    g.m = k - g.w + 1;                              // every candidate m-mer lies inside the k-mer
+    if (g.m > CH_MMAX) g.m = CH_MMAX;
+    return g;
+}
+
+static uint32_t pass_count(dbg_t *h, uint64_t table_bytes) {
+    // Partition passes: each pass owns a hash range, so the table region it touches is bounded.  A pass
+    // re-reads every distinct chunk (32 + 16 bytes), so few large regions beat many L2-sized ones:
+    // measured on B200, 312 MB table: 1 / 2 / 3 / 5 passes = 0.61 / 0.50 / 0.53 / 0.61 ms;
+    // 2.1 GB table: 6 passes 2.9 ms, 15 passes 3.4 ms.
+    uint64_t region = 160ull << 20;
+    if (table_bytes / 6 > region) region = table_bytes / 6;
+    if (region > 512ull << 20) region = 512ull << 20;
+    if (const char *e = getenv("DBG_B200_L2_REGION_BYTES")) {         // tuning / tests: force more passes
+        const unsigned long long v = strtoull(e, nullptr, 10);
+        if (v >= 64) region = v;
+    }
+    uint64_t n = cdiv(table_bytes, region);
+    if (n < 1) n = 1;
+    if (n > 255) n = 255;
+    (void)h;
+    return (uint32_t)n;
+}
+
+template <int W>
+static int build_chunks(dbg_t *h, const u64 *d_off, int e0, int e1) {
+    typedef Slot<W> S;
+    typedef ChunkSlot<W> CS;
+    const int k = h->k;
+    dbg_stats_t &st = h->st;
+    DevCounters *d_ctr = ptr<DevCounters>(h->b_ctr);
+    const ChunkGeom geom = chunk_geom(k);
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+
+    // ---- phase 0: span masks + sketch of the chunk starts ----
+    // the sketch looks at 1 chunk start in 4, chosen by two bits of the minimizer's hash (distinct sampling:
+    // a function of the chunk's content); with short minimizers the hash has too few values for that
+    const u32 sample_mask = geom.m >= 8 ? (3u << 6) : 0u;
+    const uint64_t n_spans = h->n_words;
+    TRY(reserve(h, h->b_stmask, (n_spans + 2) * 4));
+    TRY(reserve(h, h->b_vmask, (n_spans + 2) * 4));
+    TRY(reserve(h, h->b_spanread, (n_spans + 2) * 4));
+    TRY(reserve(h, h->b_hll, HLL_M * 4));
+    TRY(reserve(h, h->b_cc, sizeof(ChunkCounters)));
+    ChunkCounters *d_cc = ptr<ChunkCounters>(h->b_cc);
+    CK(cudaMemsetAsync(h->b_hll.p, 0, HLL_M * 4, h->stream));
+    CK(cudaMemsetAsync(d_cc, 0, sizeof(ChunkCounters), h->stream));
+    ChunkCounters cc;
+    memset(&cc, 0, sizeof cc);
+    uint64_t est_chunks = 0;
+    if (h->n_bases) {
+        LAUNCH(k_masks, blocks_for(n_spans), DBG_BLOCK, h->stream, ptr<const u64>(h->b_packed), d_off, h->n_reads,
+               ptr<const u32>(h->b_tile), h->n_bases, n_spans, k, geom.logw, geom.m, sample_mask, ptr<u32>(h->b_stmask),
+               ptr<u32>(h->b_vmask), ptr<u32>(h->b_spanread), ptr<u32>(h->b_hll));
+        CKK();
+        std::vector<u32> regs(HLL_M);
+        CK(cudaMemcpyAsync(regs.data(), h->b_hll.p, HLL_M * 4, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(&cc, d_cc, sizeof cc, cudaMemcpyDeviceToHost, h->stream));
+        TRY(fetch_counters(h));
+        est_chunks = (uint64_t)hll_estimate(regs) * ((sample_mask >> 6) + 1);
+    } else {
+        TRY(fetch_counters(h));
+    }
+    if (h->ctr.bad_alphabet) return fail(h, DBG_ERR_ALPHABET, "a read holds a byte other than A/C/G/T");
+    if (h->ctr.too_long) return fail(h, DBG_ERR_OVERFLOW, "a read is longer than 2^32-1 bases");
+    st.n_windows = h->ctr.n_windows;
+    const int e2 = ev_mark(h);
+
+    // ---- phase 1: chunk instances -> chunk table (interior) / list (first and last chunk of a read) ----
+    // list of boundary chunks: slot 2 r = first chunk of read r, 2 r + 1 = its last chunk (EMPTY where a
+    // read has none: reads of length <= k, or one chunk that is both)
+    const uint64_t list_cap = 2 * h->n_reads + 2;
+    TRY(reserve(h, h->b_clist, list_cap * sizeof(CS)));
+    CK(cudaMemsetAsync(h->b_clist.p, 0xFF, list_cap * sizeof(CS), h->stream));
+    // the sketch hashes the 32 bases at every chunk start that is not a read start; the last chunk of a
+    // read starts at a content-defined cut like the interior chunk other reads have there, so the
+    // sketch counts (about) the distinct INTERIOR chunks; it misses variants that differ only past
+    // base 32, which the slack and the overflow retry absorb
+    const uint64_t est_interior = est_chunks;
+    uint64_t n_cslots = (uint64_t)((double)est_interior * 1.7) + 4096;
+    if (const char *e = getenv("DBG_B200_CHUNK_SLOTS")) {             // tests: force the overflow / retry path
+        const unsigned long long v = strtoull(e, nullptr, 10);
+        if (v >= 1) n_cslots = v;
+    }
+    float ms_init = 0, ms_insert = 0;
+    uint64_t n_list = 0;
+    for (int attempt = 0;; attempt++) {
+        if (n_cslots >= 0xFFFFFFF0ull) return fail(h, DBG_ERR_OVERFLOW, "chunk table would exceed 2^32 slots");
+        TRY(reserve(h, h->b_ctable, n_cslots * sizeof(CS)));
+        const int a = ev_mark(h);
+        LAUNCH(k_chunk_table_init<W>, blocks_for(n_cslots), DBG_BLOCK, h->stream, ptr<CS>(h->b_ctable), n_cslots);
+        CKK();
+        const int b = ev_mark(h);
+        if (st.n_windows) {
+            const uint64_t n_units = cdiv(h->n_bases, DBG_UNIT);
+            uint64_t grid = (uint64_t)sms * 16;
+            if (const char *e = getenv("DBG_B200_INSERT_GRID")) {        // tuning / tests
+                const unsigned long long v = strtoull(e, nullptr, 10);
+                if (v >= 1) grid = v;
+            }
+            if (grid > cdiv(n_units, DBG_WARPS)) grid = cdiv(n_units, DBG_WARPS);
+            const uint64_t units_per_block = cdiv(n_units, grid);
+            grid = cdiv(n_units, units_per_block);
+            LAUNCH(k_chunk_insert<W>, grid, DBG_BLOCK, h->stream, ptr<const u64>(h->b_packed), h->n_words + 4, d_off,
+                   h->n_reads, ptr<const u32>(h->b_stmask), ptr<const u32>(h->b_vmask), ptr<const u32>(h->b_spanread),
+                   n_spans, n_units, units_per_block, k, ptr<CS>(h->b_ctable), (u32)n_cslots, ptr<CS>(h->b_clist),
+                   list_cap, h->read_idx_base, d_cc);
+            CKK();
+        }
+        const int c = ev_mark(h);
+        CK(cudaMemcpyAsync(&cc, d_cc, sizeof cc, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        ms_init += ev_ms(h, a, b);
+        ms_insert += ev_ms(h, b, c);
+        if (cc.bad_chunk) return fail(h, DBG_ERR_STATE, "internal consistency fault: a chunk without an end");
+        if (cc.list_overflow) return fail(h, DBG_ERR_STATE, "internal consistency fault: boundary list overflow");
+        n_list = list_cap;
+        if (!cc.chunk_overflow) break;
+        if (attempt >= 8) return fail(h, DBG_ERR_NOMEM, "chunk table overflowed repeatedly");
+        n_cslots = n_cslots * 2 + 4096;                                // sketch was low: rebuild larger
+        CK(cudaMemsetAsync(&d_cc->n_instances, 0, sizeof(ChunkCounters) - offsetof(ChunkCounters, n_instances),
+                           h->stream));
+        h->n_ev -= 3;
+    }
+    const int e3 = ev_mark(h);
+    st.ms_chunk_insert = ms_insert;
+
+    // ---- phase 2a: sketch of the node keys of the distinct chunks -> node table size ----
+    uint64_t est = 0;
+    std::vector<u32> sketch(HLL_M, 0);
+    uint64_t ex_grid = cdiv(cdiv(n_cslots + n_list, 32), DBG_WARPS);
+    if (ex_grid > (uint64_t)sms * 8) ex_grid = (uint64_t)sms * 8;
+    if (ex_grid < 1) ex_grid = 1;
+    if (st.n_windows) {
+        CK(cudaMemsetAsync(h->b_hll.p, 0, HLL_M * 4, h->stream));
+        TRY(reserve(h, h->b_h8, (n_cslots + n_list + 32) * 16));      // one hash byte per (record, node)
+        LAUNCH((k_expand<W, 0>), ex_grid, DBG_BLOCK, h->stream, ptr<const CS>(h->b_ctable), n_cslots,
+               ptr<const CS>(h->b_clist), n_list, k, ptr<uint4>(h->b_h8), (S *)nullptr, 0u, 0u, 0u,
+               ptr<u32>(h->b_hll), d_ctr);
+        CKK();
+        CK(cudaMemcpyAsync(sketch.data(), h->b_hll.p, HLL_M * 4, cudaMemcpyDeviceToHost, h->stream));
+    }
+    const int e4 = ev_mark(h);
+    CK(cudaStreamSynchronize(h->stream));
+    if (st.n_windows) est = (uint64_t)hll_estimate(sketch);
+    st.hll_estimate = est;
+    ms_insert += ev_ms(h, e3, e4);
+    st.ms_expand_sketch = ev_ms(h, e3, e4);
+
+    // ---- phase 2b: node table (kernel 3): every node of every distinct chunk, x multiplicity ----
+    const uint64_t max_nodes = st.n_windows + h->n_reads;             // every window + last k-mer per read
+    uint64_t want = (uint64_t)((double)est * 1.06) + 64;              // HLL std error at 2^12 registers: 1.6 %
+    if (want > max_nodes) want = max_nodes;
+    uint64_t n_slots = want * 2 + 1024;                               // load factor <= 0.5
+    for (int attempt = 0;; attempt++) {
+        if (n_slots >= 0xFFFFFFF0ull) return fail(h, DBG_ERR_OVERFLOW, "node table would exceed 2^32 slots");
+        h->n_slots = n_slots;
+        TRY(reserve(h, h->b_table, n_slots * sizeof(S)));
+        const int a = ev_mark(h);
+        LAUNCH(k_table_init<W>, blocks_for(n_slots), DBG_BLOCK, h->stream, ptr<S>(h->b_table), n_slots);
+        CKK();
+        const int b = ev_mark(h);
+        if (st.n_windows) {
+            uint32_t n_parts = pass_count(h, n_slots * sizeof(S));
+            if (n_parts > 255) n_parts = 255;
+            st.n_insert_passes = n_parts;
+            for (uint32_t part = 0; part < n_parts; part++) {
+                // hash bytes 0..254 (255 = no node) split evenly over the passes
+                const uint32_t lo8 = part * 255u / n_parts;
+                const uint32_t hi8 = (part + 1) * 255u / n_parts - 1;
+                LAUNCH((k_expand<W, 1>), ex_grid, DBG_BLOCK, h->stream, ptr<const CS>(h->b_ctable), n_cslots,
+                       ptr<const CS>(h->b_clist), n_list, k, ptr<uint4>(h->b_h8), ptr<S>(h->b_table), (u32)n_slots,
+                       lo8, hi8 - lo8, (u32 *)nullptr, d_ctr);
+                CKK();
+            }
+        }
+        const int c = ev_mark(h);
+        TRY(fetch_counters(h));
+        ms_init += ev_ms(h, a, b);
+        ms_insert += ev_ms(h, b, c);
+        if (!h->ctr.overflow) break;
+        if (attempt >= 6) return fail(h, DBG_ERR_NOMEM, "node table overflowed repeatedly");
+        n_slots *= 2;                                                  // estimate was low: rebuild larger
+        CK(cudaMemsetAsync(&d_ctr->overflow, 0, 4, h->stream));
+        h->n_ev -= 3;
+    }
+    st.ms_pack = ev_ms(h, e0, e1);
+    st.ms_estimate = ev_ms(h, e1, e2);
+    st.ms_table_init = ms_init;
+    st.ms_insert = ms_insert;
+    st.ms_expand = ms_insert - st.ms_chunk_insert - st.ms_expand_sketch;
+    st.table_slots = n_slots;
+    st.table_bytes = n_slots * sizeof(S);
+    st.n_chunk_instances = cc.n_instances;
+    st.n_chunk_list = n_list;
+    st.chunk_slots = n_cslots;
+    {
+        const int e_end = ev_mark(h);
+        CK(cudaStreamSynchronize(h->stream));
+        st.ms_build_total = ev_ms(h, e0, e_end);
+    }
+    h->table_ready = true;
+    return DBG_OK;
+}
+
+template <int W>
+static int build_impl(dbg_t *h, const u8 *d_bases, const u64 *d_off) {
+    typedef Slot<W> S;
+    const int k = h->k;
+    dbg_stats_t &st = h->st;
+    DevCounters *d_ctr = ptr<DevCounters>(h->b_ctr);
+    const int e0 = ev_mark(h);
+
+    // ---- read packing (kernel 1) ----
+    h->n_words = cdiv(h->n_bases, 32);
+    TRY(reserve(h, h->b_packed, (h->n_words + 4) * 8));
+    CK(cudaMemsetAsync(ptr<u64>(h->b_packed) + h->n_words, 0, 4 * 8, h->stream));
+    h->n_tiles = cdiv(h->n_bases, DBG_TILE);
+    TRY(reserve(h, h->b_tile, (h->n_tiles + 2) * 4));
+    if (h->n_bases) {
+        LAUNCH(k_pack, blocks_for(h->n_words), DBG_BLOCK, h->stream, d_bases, h->n_bases, ptr<u64>(h->b_packed),
+               h->n_words, (int)(((uintptr_t)d_bases & 15) == 0), d_ctr);
+        CKK();
+    }
+    if (h->n_reads) {
+        LAUNCH(k_read_stats, blocks_for(h->n_reads), DBG_BLOCK, h->stream, d_off, h->n_reads, k, d_ctr);
+        CKK();
+    }
+    if (h->n_bases) {
+        LAUNCH(k_tile_first, blocks_for(h->n_tiles + 1), DBG_BLOCK, h->stream, d_off, h->n_reads, h->n_bases,
+               h->n_tiles, ptr<u32>(h->b_tile));
+        CKK();
+    }
+    const int e1 = ev_mark(h);
+
+    const char *mode = getenv("DBG_B200_BUILD");                      // "windows" = the per-window table build
+    if (mode && !strcmp(mode, "windows")) return build_windows<W>(h, d_off, e0, e1);
+    return build_chunks<W>(h, d_off, e0, e1);
 }
 
 // ---- graph stage A: degrees, pruningEdges, branch flags, successor links (kernel 4) ----
@@ -649,38 +881,55 @@ static int walk_impl(dbg_t *h, int stop_at_branch) {
     st.jump_rounds = 0;
     const int e0 = ev_mark(h);
 
-    // ---- list ranking over the pruned successor array, cut at splitters ----
+    // ---- list ranking over the pruned successor array: chain nodes -> splitters -> super-splitters ----
     TRY(reserve(h, h->b_link, n_slots * 8));
     const uint64_t split_cap = (n_slots >> WALK_SPLIT_LOG2) * 3 / 2 + st.n_starts + 4096;
+    const uint64_t super_cap = (split_cap >> WALK_SUPER_LOG2) * 3 / 2 + 4096;
     TRY(reserve(h, h->b_split, split_cap * 4));
-    CK(cudaMemsetAsync(&d_ctr->n_list_a, 0, 8, h->stream));
+    TRY(reserve(h, h->b_super, super_cap * 4));
+    CK(cudaMemsetAsync(&d_ctr->n_list_a, 0, 16, h->stream));             // n_list_a (splitters), n_list_b (supers)
     LAUNCH(k_link_init, blocks_for(n_slots), DBG_BLOCK, h->stream, ptr<const u8>(h->b_flags),
            ptr<const u16>(h->b_kept), ptr<const u32>(h->b_succ), n_slots, ptr<u64>(h->b_link), ptr<u32>(h->b_split),
-           split_cap, &d_ctr->n_list_a);
+           split_cap, &d_ctr->n_list_a, ptr<u32>(h->b_super), super_cap, &d_ctr->n_list_b);
     CKK();
-    TRY(fetch_counters(h));
-    const uint64_t n_split = h->ctr.n_list_a;
-    if (n_split > split_cap) return fail(h, DBG_ERR_STATE, "splitter list overflow (%llu > %llu)",
-                                         (unsigned long long)n_split, (unsigned long long)split_cap);
-    if (n_split) {
-        LAUNCH(k_sublist, blocks_for(n_split), DBG_BLOCK, h->stream, ptr<u64>(h->b_link), ptr<const u32>(h->b_split),
-               n_split);
-        CKK();
+    // the list lengths stay on the device: the kernels below read them there (no host round trip)
+    LAUNCH(k_sublist, blocks_for(split_cap), DBG_BLOCK, h->stream, ptr<u64>(h->b_link), ptr<const u32>(h->b_split),
+           (const u64 *)&d_ctr->n_list_a, split_cap);
+    CKK();
+    LAUNCH(k_suplist, blocks_for(super_cap), DBG_BLOCK, h->stream, ptr<u64>(h->b_link), ptr<const u32>(h->b_super),
+           (const u64 *)&d_ctr->n_list_b, super_cap);
+    CKK();
+    {
         int max_rounds = 2;
-        for (uint64_t n = n_split; n > 1; n >>= 1) max_rounds++;
-        CK(cudaMemsetAsync(&d_ctr->changed, 0, 4, h->stream));
-        for (int r = 0; r < max_rounds; r++) {              // no host round trip per round: the list is small
-            LAUNCH(k_jump, blocks_for(n_split), DBG_BLOCK, h->stream, ptr<u64>(h->b_link),
-                   ptr<const u32>(h->b_split), n_split, n_slots, d_ctr);
+        for (uint64_t n = super_cap; n > 1; n >>= 1) max_rounds++;
+        if (super_cap <= WALK_BLOCK_JUMP_CAP) {                      // one block jumps the whole list in one launch
+            LAUNCH(k_jump_block, 1, 1024, h->stream, ptr<u64>(h->b_link), ptr<const u32>(h->b_super),
+                   (const u64 *)&d_ctr->n_list_b, super_cap, n_slots, max_rounds, d_ctr);
             CKK();
-            st.jump_rounds++;
-            if ((r & 7) == 7 || r == max_rounds - 1) {      // look every 8 rounds whether it has converged
-                TRY(check_fault(h, "k_jump"));
-                if (!h->ctr.changed) break;
-                CK(cudaMemsetAsync(&d_ctr->changed, 0, 4, h->stream));
+            TRY(check_fault(h, "k_jump_block"));
+            st.jump_rounds = h->ctr.changed;
+        } else {
+            TRY(fetch_counters(h));
+            const uint64_t n_super = h->ctr.n_list_b < super_cap ? h->ctr.n_list_b : super_cap;
+            CK(cudaMemsetAsync(&d_ctr->changed, 0, 4, h->stream));
+            for (int r = 0; r < max_rounds && n_super; r++) {        // the list is small: look every 8 rounds
+                LAUNCH(k_jump, blocks_for(n_super), DBG_BLOCK, h->stream, ptr<u64>(h->b_link),
+                       ptr<const u32>(h->b_super), n_super, n_slots, d_ctr);
+                CKK();
+                st.jump_rounds++;
+                if ((r & 7) == 7 || r == max_rounds - 1) {
+                    TRY(check_fault(h, "k_jump"));
+                    if (!h->ctr.changed) break;
+                    CK(cudaMemsetAsync(&d_ctr->changed, 0, 4, h->stream));
+                }
             }
+            TRY(check_fault(h, "k_jump"));
         }
     }
+    if (h->ctr.n_list_a > split_cap || h->ctr.n_list_b > super_cap)
+        return fail(h, DBG_ERR_STATE, "splitter list overflow (%llu > %llu or %llu > %llu)",
+                    (unsigned long long)h->ctr.n_list_a, (unsigned long long)split_cap,
+                    (unsigned long long)h->ctr.n_list_b, (unsigned long long)super_cap);
     const int e1 = ev_mark(h);
 
     // ---- one record per start (debruijn.py:331-345) ----
@@ -858,7 +1107,8 @@ DBG_API void dbg_destroy(dbg_t *h) {
     DevBuf *all[] = {&h->b_bases, &h->b_off, &h->b_packed, &h->b_tile, &h->b_table, &h->b_flags, &h->b_kept,
                      &h->b_succ, &h->b_link, &h->b_ctr, &h->b_hll, &h->b_order, &h->b_tag, &h->b_tag2, &h->b_slot,
                      &h->b_slot2, &h->b_sorttmp, &h->b_branch, &h->b_starts, &h->b_pulled, &h->b_readflags,
-                     &h->b_recs, &h->b_cnt32, &h->b_off64, &h->b_contig, &h->b_junction, &h->b_split, &h->b_h8, &h->b_chunk, &h->b_bitmap, &h->b_scratch[0],
+                     &h->b_recs, &h->b_cnt32, &h->b_off64, &h->b_contig, &h->b_junction, &h->b_split, &h->b_h8, &h->b_chunk, &h->b_bitmap,
+                     &h->b_stmask, &h->b_vmask, &h->b_spanread, &h->b_cc, &h->b_ctable, &h->b_clist, &h->b_super, &h->b_scratch[0],
                      &h->b_scratch[1], &h->b_scratch[2], &h->b_scratch[3], &h->b_scratch[4], &h->b_scratch[5]};
     for (DevBuf *b : all) if (b->p) cudaFree(b->p);
     for (int i = 0; i < EV_MAX; i++) cudaEventDestroy(h->ev[i]);

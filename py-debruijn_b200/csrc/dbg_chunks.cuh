@@ -1,0 +1,670 @@
+// dbg_chunks.cuh -- the window loop (debruijn.py:123-144) restated over SUPER-K-MERS ("chunks").
+//
+// Why.  A scattered table touch costs about one L1TEX/LSU cycle per lane on every SM whatever it
+// hits, so a build that probes the node table once per window (k_insert, dbg_kernels.cuh) is bound
+// by ~2.5 scattered accesses x 10^8 windows.  Reads that cover the same stretch of the genome
+// repeat the same k-mers in the same order, so the windows are first grouped into content-defined
+// runs and the RUNS are deduplicated:
+//
+//   chunk    a maximal run of consecutive node occurrences (debruijn.py:127) of one read that
+//            share the position of their minimizer (leftmost smallest hashed m-mer among the
+//            first w m-mers of the k-mer; w = 2^logw <= 16 nodes).  Boundaries depend on content
+//            only, so two reads that cover the same stretch cut it at the same places and yield
+//            byte-identical chunk strings: n nodes + their successor bases = n + k bases
+//            (n + k - 1 for the last chunk of a read, whose last node has no successor).
+//   phase 0  k_masks        per 32 stream positions: V (is a node occurrence), St (starts a chunk),
+//                           the read index, and a HyperLogLog sketch of the chunk starts
+//   phase 1  k_chunk_insert every chunk instance -> chunk table keyed by the WHOLE string
+//                           (exact, no fingerprints): count += 1, tag = min (read, pos).  The
+//                           first and last chunk of a read are cut by the read, not by content,
+//                           and are unique: they go to an append-only list, not to the table.
+//   phase 2  k_expand       every DISTINCT chunk (table + list) -> its n nodes -> node table:
+//                           count[next base] += multiplicity, tag = min(chunk tag + offset).
+//                           Node-table passes own a hash range each so their slots stay in L2.
+//
+// The result is the same node table the per-window build produces (sums and minima are
+// associative), whatever the cut rule: correctness does not depend on where chunks are cut, only
+// the amount of deduplication does.  configs[1] (150 bp x 30): 99.2 M windows -> 13.5 M chunk
+// instances -> 0.6 M distinct interior chunks + 1.7 M boundary chunks -> 15.7 M node upserts.
+#pragma once
+#include "dbg_common.cuh"
+
+#define CH_WMAX 16                         // nodes per chunk at most
+#define CH_MMAX 16                         // minimizer length at most (an m-mer fits 32 bits)
+#define CH_HALF 60                         // bases per 128-bit key half (120 bits + 8 bits of meta)
+
+// ---------------------------------------------------------------------------------------------
+// Chunk keys.  A chunk string of B <= 60 W bases is stored left-aligned in W halves of 128 bits:
+//   half.hi = bases 0..31 of the half, half.lo = bases 32..59 in bits 63..8 | meta in bits 7..0
+//   meta    = n << 1 | term    (n = nodes in the chunk, term = the last node has no successor)
+// Bases beyond B are zero, so equal (string, n, term) <=> equal key.  meta is never 0xFF, so the
+// all-ones half is free: EMPTY for half 0, NOT_READY for half 1 (k > 31: the 256-bit key cannot be
+// written by one CAS; the winner of the CAS on half 0 publishes half 1 with a plain store and
+// probes that see NOT_READY come back later).
+// ---------------------------------------------------------------------------------------------
+template <int W> struct ChunkKey { K128 h[W]; };
+
+template <int W> struct ChunkSlot;
+template <> struct __align__(32) ChunkSlot<1> {
+    K128 h[1];
+    u64 tag;
+    u32 cnt;
+    u32 pad;
+    DBG_HD void zero_pad() { pad = 0; }
+};
+template <> struct __align__(64) ChunkSlot<2> {
+    K128 h[2];
+    u64 tag;
+    u32 cnt;
+    u32 pad;
+    u64 pad2[2];
+    DBG_HD void zero_pad() { pad = 0; pad2[0] = 0; pad2[1] = 0; }
+};
+
+DBG_HD K128 k128_ones() { K128 r; r.lo = ~0ULL; r.hi = ~0ULL; return r; }
+DBG_HD u64 keep_top_bases(u64 word, int nb) {          // keep the first nb (0..32) bases of a word
+    return nb >= 32 ? word : (nb <= 0 ? 0ULL : word & ~(~0ULL >> (2 * nb)));
+}
+DBG_HD u32 chunk_meta(u32 n, u32 term) { return (n << 1) | term; }
+DBG_HD u32 meta_nodes(u32 meta) { return (meta >> 1) & 31u; }
+DBG_HD u32 meta_term(u32 meta) { return meta & 1u; }
+
+template <int W> DBG_HD u32 chunk_hash(const ChunkKey<W> &key) {
+    u64 x = key.h[0].lo * 0x9E3779B97F4A7C15ULL + key.h[0].hi * 0xC2B2AE3D27D4EB4FULL;
+    if (W == 2) x += key.h[1].lo * 0xD6E8FEB86659FD93ULL + key.h[1].hi * 0xA0761D6478BD642FULL;
+    x ^= x >> 29;
+    return (u32)((x * 0x9E3779B97F4A7C15ULL) >> 32);
+}
+
+// 64 bits of a staged 2-bit word array starting at base `rel`
+DBG_D u64 staged_word(const u64 *words, u32 rel) {
+    const u32 w = rel >> 5;
+    const int s = 2 * (int)(rel & 31);
+    const u64 w0 = words[w], w1 = words[w + 1];
+    return s ? ((w0 << s) | (w1 >> (64 - s))) : w0;
+}
+
+// key of the chunk whose string is the B bases at `rel` of a staged word array
+template <int W> DBG_D ChunkKey<W> chunk_key_from_stream(const u64 *words, u32 rel, int B, u32 meta) {
+    ChunkKey<W> key;
+#pragma unroll
+    for (int h = 0; h < W; h++) {
+        const int nb = B - CH_HALF * h;                                  // bases of this half (may be <= 0)
+        u64 hi = 0, lo = 0;
+        if (nb > 0) {
+            hi = keep_top_bases(staged_word(words, rel + CH_HALF * h), nb);
+            if (nb > 32) lo = keep_top_bases(staged_word(words, rel + CH_HALF * h + 32), nb - 32 > 28 ? 28 : nb - 32);
+        }
+        key.h[h].hi = hi;
+        key.h[h].lo = (lo & ~0xFFULL) | meta;
+    }
+    return key;
+}
+
+// the chunk string as contiguous 2-bit words (same layout as the packed read stream), 2 W words
+template <int W> DBG_HD void chunk_words(const K128 *h, u64 *out);
+template <> DBG_HD void chunk_words<1>(const K128 *h, u64 *out) {
+    out[0] = h[0].hi;
+    out[1] = h[0].lo & ~0xFFULL;
+}
+template <> DBG_HD void chunk_words<2>(const K128 *h, u64 *out) {
+    const u64 l0 = h[0].lo & ~0xFFULL, l1 = h[1].lo & ~0xFFULL;
+    out[0] = h[0].hi;
+    out[1] = l0 | (h[1].hi >> 56);
+    out[2] = (h[1].hi << 8) | (l1 >> 56);
+    out[3] = l1 << 8;
+}
+
+struct ChunkCounters {
+    u64 n_first;        // unused
+    u64 n_instances;    // chunk instances seen by k_chunk_insert
+    u64 n_list;         // unused (the list is indexed by read: 2 r = first chunk, 2 r + 1 = last chunk)
+    u32 chunk_overflow; // chunk table full
+    u32 list_overflow;  // list capacity exceeded (cannot happen: capacity is 2 x n_first)
+    u32 bad_chunk;      // a chunk longer than CH_WMAX (internal consistency)
+    u32 pad;
+};
+
+DBG_D u32 bit_range(u32 lo, u32 hi) { return (~0u >> (31 - hi)) & (~0u << lo); }   // bits lo..hi, 0 <= lo <= hi <= 31
+
+// ---------------------------------------------------------------------------------------------
+// k_masks (phase 0).  One thread per span of 32 stream positions.
+//   V  bit j: position p0 + j is a node occurrence (its read is longer than k, pos <= len - k)
+//   St bit j: a chunk starts there: V and (first position of its read, or its minimizer is not at
+//             the same place as the previous position's)
+// Minimizer of the node at p: among the m-mers at p .. p + w - 1 (all inside the k-mer because
+// m <= k - w + 1) the one with the smallest 18-bit multiplicative hash, leftmost on ties.  The 48
+// hashed m-mers a span needs (positions p0 - 1 .. p0 + 46) come from the 64 bases at p0 - 1, held
+// in two registers; the sliding minimum over w = 2^logw is logw rounds of a[i] = min(a[i],
+// a[i + 2^r]) on a register array with compile-time indices.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(DBG_BLOCK) k_masks(const u64 *__restrict__ packed, const u64 *__restrict__ off,
+                                                     u64 n_reads, const u32 *__restrict__ tile_first, u64 n_bases,
+                                                     u64 n_spans, int k, int logw, int m, u32 sample_mask,
+                                                     u32 *__restrict__ st_mask,
+                                                     u32 *__restrict__ v_mask, u32 *__restrict__ span_read, u32 *regs) {
+    const u64 s = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_spans) return;
+    const u64 p0 = s * 32;
+    u32 V = 0, S = 0, r0 = 0;
+    if (p0 < n_bases) {
+        const u64 tile = p0 / DBG_TILE;
+        u32 rlo = __ldg(tile_first + tile), rhi = __ldg(tile_first + tile + 1);
+        while (rlo < rhi) {
+            const u32 mid = rlo + ((rhi - rlo + 1) >> 1);
+            if (__ldg(off + mid) <= p0) rlo = mid; else rhi = mid - 1;
+        }
+        u64 r = rlo;
+        r0 = rlo;
+        u64 rs = __ldg(off + r), re = __ldg(off + r + 1);
+        const u64 pend = p0 + 32;
+        for (;;) {
+            if (re - rs > (u64)k) {                                      // node occurrences: rs .. re - k
+                const u64 lo = rs > p0 ? rs : p0;
+                u64 hi = re - (u64)k;
+                if (hi >= pend) hi = pend - 1;
+                if (lo <= hi) V |= bit_range((u32)(lo - p0), (u32)(hi - p0));
+                if (rs >= p0 && rs < pend) S |= 1u << (u32)(rs - p0);
+            }
+            if (re >= pend || r + 1 >= n_reads) break;
+            r++; rs = re; re = __ldg(off + r + 1);
+        }
+    }
+    u32 St = 0;
+    if (V) {
+        const u64 wm = s ? __ldg(packed + s - 1) : 0ULL, w0 = __ldg(packed + s), w1 = __ldg(packed + s + 1);
+        const u64 A = (wm << 62) | (w0 >> 2);                            // bases p0 - 1 .. p0 + 30
+        const u64 B = (w0 << 62) | (w1 >> 2);                            // bases p0 + 31 .. p0 + 62
+        // the 128 bits as four 32-bit words; m-mer i = the 32 bits at bit 2 i, shifted down to 2 m bits
+        const u32 X[5] = {(u32)(A >> 32), (u32)A, (u32)(B >> 32), (u32)B, 0u};
+        const int down = 32 - 2 * m;
+        u32 a[48];
+#pragma unroll
+        for (int i = 0; i < 48; i++) {
+            const int o = 2 * i;
+            const u32 t = (o & 31) ? __funnelshift_l(X[o / 32 + 1], X[o / 32], o & 31) : X[o / 32];
+            const u32 x = t >> down;
+            a[i] = (((x * 0x9E3779B1u) >> 8) & 0xFFFFFFC0u) | (u32)i;      // 18-bit hash << 6 | i
+        }
+        if (logw > 0) {
+#pragma unroll
+            for (int i = 0; i < 47; i++) a[i] = a[i] < a[i + 1] ? a[i] : a[i + 1];
+        }
+        if (logw > 1) {
+#pragma unroll
+            for (int i = 0; i < 45; i++) a[i] = a[i] < a[i + 2] ? a[i] : a[i + 2];
+        }
+        if (logw > 2) {
+#pragma unroll
+            for (int i = 0; i < 41; i++) a[i] = a[i] < a[i + 4] ? a[i] : a[i + 4];
+        }
+        if (logw > 3) {
+#pragma unroll
+            for (int i = 0; i < 33; i++) a[i] = a[i] < a[i + 8] ? a[i] : a[i + 8];
+        }
+        u32 N = 0, Smp = 0;
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+            N |= (a[j + 1] != a[j] ? 1u : 0u) << j;
+            Smp |= ((a[j + 1] & sample_mask) == 0u ? 1u : 0u) << j;       // distinct sampling by minimizer hash
+        }
+        St = V & (S | N);
+        // sketch of the (sampled) chunk starts that are not read starts: the first min(32, k + 1) bases
+        u32 todo = St & ~S & Smp;
+        const int nbp = k + 1 < 32 ? k + 1 : 32;
+        while (todo) {
+            const int j = __ffs((int)todo) - 1;
+            todo &= todo - 1;
+            const int sh = 2 * (j + 1);
+            const u64 t0 = keep_top_bases(sh == 64 ? B : ((A << sh) | (B >> (64 - sh))), nbp);
+            const u32 hsh = (u32)(fmix64(t0) >> 32);
+            const u32 idx = hsh >> (32 - HLL_P);
+            const u32 rank = (u32)__clz((int)((hsh << HLL_P) | (1u << (HLL_P - 1)))) + 1;
+            if (regs[idx] < rank) atomicMax(&regs[idx], rank);
+        }
+    }
+    st_mask[s] = St;
+    v_mask[s] = V;
+    span_read[s] = r0;
+}
+
+template <int W>
+__global__ void __launch_bounds__(DBG_BLOCK) k_chunk_table_init(ChunkSlot<W> *table, u64 n_slots) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_slots) return;
+    ChunkSlot<W> s;
+#pragma unroll
+    for (int h = 0; h < W; h++) s.h[h] = k128_ones();
+    s.tag = ~0ULL;
+    s.cnt = 0;
+    s.zero_pad();
+    table[i] = s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_chunk_insert (phase 1).  Each warp works through units of 32 spans (1024 stream positions):
+//   stage   the unit's 2-bit words (+ overhang for the longest chunk string) in shared memory
+//   select  every lane turns the St bits of its span into queue entries (position, n, term); the
+//           end of a chunk is the next bit of St | ~V, in its own span or the next one
+//   drain   32 chunks at a time, one per lane: read index and position (span_read + off[]), the
+//           key from the staged words, then ONE probe of the chunk table; a probe that finds
+//           another key does not loop, it re-queues (key, tag, probes) in a retry ring
+// First / last chunks of a read go to the list at slot 2 r / 2 r + 1 (r = read index): no atomics, and the
+// list is in read order (a shared append cursor was measured at 1 ms: 4 x 10^5 same-address atomics).
+// ---------------------------------------------------------------------------------------------
+#define CH_UNIT_WORDS (DBG_UNIT / 32 + 6)
+#define CH_QCAP 512
+#define CH_RCAP 64
+#define CH_MAX_PROBES 1024u
+template <int W> struct ChunkInsertShared {
+    u64 words[DBG_WARPS][CH_UNIT_WORDS];
+    u16 q[DBG_WARPS][CH_QCAP];                  // rel (10 bits) | (n - 1) << 10 | term << 14
+    u32 c_read[DBG_WARPS][32];                  // per span: read holding its first position,
+    u32 c_pos[DBG_WARPS][32];                   //   position of the span start in that read,
+    u16 c_end[DBG_WARPS][32];                   //   distance to that read's end (clamped),
+    u16 c_end2[DBG_WARPS][32];                  //   distance to the end of the next non-empty read (clamped)
+    u8 c_skip[DBG_WARPS][32];                   //   and that read's index minus c_read (0 = unknown: ask off[])
+    ChunkKey<W> rkey[DBG_WARPS][CH_RCAP];
+    u64 rtag[DBG_WARPS][CH_RCAP];
+    u16 rprobes[DBG_WARPS][CH_RCAP];
+};
+
+DBG_D K128 load_k128(const K128 *p) {
+    const ulonglong2 v = __ldcg(reinterpret_cast<const ulonglong2 *>(p));
+    K128 r; r.lo = v.x; r.hi = v.y;
+    return r;
+}
+DBG_D void store_k128(K128 *p, K128 v) {
+    __stcg(reinterpret_cast<ulonglong2 *>(p), make_ulonglong2(v.lo, v.hi));
+}
+
+// one probe of one slot: 0 = counted, 1 = another key lives here (go on to the next slot),
+// 2 = the slot's second half is not published yet (come back to the same slot)
+template <int W>
+DBG_D int chunk_probe(ChunkSlot<W> *s, const ChunkKey<W> &key, u64 tag) {
+    const K128 c0 = load_k128(&s->h[0]);
+    u64 seen = __ldcg(&s->tag);
+    if (c0 != key.h[0]) {
+        if (c0 != k128_ones()) return 1;
+        const K128 old = cas_key(&s->h[0], k128_ones(), key.h[0]);
+        if (old == k128_ones()) {                                        // this probe created the entry
+            if (W == 2) store_k128(&s->h[W - 1], key.h[W - 1]);
+            atomicMin(&s->tag, tag);
+            atomicAdd(&s->cnt, 1u);
+            return 0;
+        }
+        if (old != key.h[0]) return 1;
+        seen = __ldcg(&s->tag);
+    }
+    if (W == 2) {
+        const K128 c1 = load_k128(&s->h[W - 1]);
+        if (c1 == k128_ones()) return 2;
+        if (c1 != key.h[W - 1]) return 1;
+    }
+    if (tag < seen) atomicMin(&s->tag, tag);
+    atomicAdd(&s->cnt, 1u);
+    return 0;
+}
+
+#ifndef DBG_CHUNK_MIN_BLOCKS
+#define DBG_CHUNK_MIN_BLOCKS 4
+#endif
+template <int W>
+__global__ void __launch_bounds__(DBG_BLOCK, DBG_CHUNK_MIN_BLOCKS)
+k_chunk_insert(const u64 *__restrict__ packed, u64 n_words_padded, const u64 *__restrict__ off, u64 n_reads,
+               const u32 *__restrict__ st_mask, const u32 *__restrict__ v_mask, const u32 *__restrict__ span_read,
+               u64 n_spans, u64 n_units, u64 units_per_block, int k, ChunkSlot<W> *table, u32 n_slots,
+               ChunkSlot<W> *list, u64 list_cap, u64 read_idx_base, ChunkCounters *cc) {
+    __shared__ ChunkInsertShared<W> sh;
+    const u32 lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const u32 lt = (1u << lane) - 1;
+    u32 head1 = 0, n1 = 0, head2 = 0, n2 = 0;                            // warp-uniform ring state
+    u32 flags = 0;                                                       // 1 table overflow, 2 list overflow, 4 bad chunk
+    u64 ub = 0, n_inst = 0;
+
+    auto probe = [&](bool act, const ChunkKey<W> &key, u64 tag, u32 probes) {
+        int res = 0;
+        if (act) {
+            u64 idx = slot_home(chunk_hash<W>(key), n_slots) + probes;
+            if (idx >= n_slots) idx -= n_slots;
+            res = chunk_probe<W>(&table[idx], key, tag);
+            if (res == 1) {
+                probes++;
+                if (probes >= CH_MAX_PROBES || probes >= n_slots) { flags |= 1u; res = 0; cc->chunk_overflow = 1; }
+            }
+        }
+        const bool again = res != 0;
+        const u32 mk = __ballot_sync(0xFFFFFFFFu, again);
+        if (again) {
+            const u32 e = (head2 + n2 + __popc(mk & lt)) & (CH_RCAP - 1);
+            sh.rkey[w][e] = key; sh.rtag[w][e] = tag; sh.rprobes[w][e] = (u16)probes;
+        }
+        n2 += __popc(mk);
+    };
+    auto drain2 = [&]() {                                                // up to 32 retries
+        __syncwarp();
+        const u32 take = n2 < 32u ? n2 : 32u;
+        const u32 e = (head2 + lane) & (CH_RCAP - 1);
+        const bool act = lane < take;
+        const ChunkKey<W> key = sh.rkey[w][e];
+        const u64 tag = sh.rtag[w][e];
+        const u32 probes = sh.rprobes[w][e];
+        __syncwarp();
+        head2 = (head2 + take) & (CH_RCAP - 1);
+        n2 -= take;
+        probe(act, key, tag, probes);
+    };
+    auto drain1 = [&]() {                                                // up to 32 fresh chunks
+        __syncwarp();
+        const u32 take = n1 < 32u ? n1 : 32u;
+        const bool act = lane < take;
+        const u32 ent = act ? sh.q[w][(head1 + lane) & (CH_QCAP - 1)] : 0;
+        __syncwarp();
+        head1 = (head1 + take) & (CH_QCAP - 1);
+        n1 -= take;
+        const u32 rel = ent & 1023u, n = ((ent >> 10) & 15u) + 1, term = (ent >> 14) & 1u;
+        ChunkKey<W> key;
+        u64 tag = 0;
+        bool boundary = false;
+        if (act) {
+            const u32 sp = rel >> 5, j = rel & 31;
+            u64 r = sh.c_read[w][sp];
+            u32 pos = sh.c_pos[w][sp] + j;
+            const u32 end = sh.c_end[w][sp];
+            if (j >= end) {                                              // a read ends inside the span
+                const u32 end2 = sh.c_end2[w][sp], skip = sh.c_skip[w][sp];
+                if (skip && j < end2) { r += skip; pos = j - end; }      // ... and the chunk is in the next one
+                else {                                                   // reads shorter than a span: ask off[]
+                    const u64 c = ub + rel;
+                    u64 re = __ldg(off + r + 1);
+                    while (re <= c) { r++; re = __ldg(off + r + 1); }    // also skips empty reads
+                    pos = (u32)(c - __ldg(off + r));
+                }
+            }
+            tag = ((read_idx_base + r) << 32) | pos;
+            boundary = pos == 0 || term;
+            key = chunk_key_from_stream<W>(sh.words[w], rel, (int)n + k - (int)term, chunk_meta(n, term));
+        }
+        if (boundary) {                                                  // first / last chunk of a read: its own list slot
+            const u64 o = 2 * (tag >> 32) - 2 * read_idx_base + ((u32)tag == 0 ? 0u : 1u);   // 2 x local read index (+ 1: last chunk)
+            if (o < list_cap) {
+                ChunkSlot<W> rec;
+#pragma unroll
+                for (int hh = 0; hh < W; hh++) rec.h[hh] = key.h[hh];
+                rec.tag = tag; rec.cnt = 1;
+                rec.zero_pad();
+                list[o] = rec;
+            } else flags |= 2u;
+        }
+        probe(act && !boundary, key, tag, 0);
+    };
+
+    const u64 unit_begin = (u64)blockIdx.x * units_per_block;
+    u64 unit_end = unit_begin + units_per_block;
+    if (unit_end > n_units) unit_end = n_units;
+    for (u64 u = unit_begin + w; u < unit_end; u += DBG_WARPS) {
+        ub = u * DBG_UNIT;
+        if ((u & 15) == 0 && __any_sync(0xFFFFFFFFu, __ldcg(&cc->chunk_overflow) != 0u)) break;   // table full: the host rebuilds it larger
+        __syncwarp();
+        for (u32 i = lane; i < CH_UNIT_WORDS; i += 32) {
+            const u64 wi = ub / 32 + i;
+            sh.words[w][i] = wi < n_words_padded ? __ldg(packed + wi) : 0;
+        }
+        const u64 s = u * 32 + lane;
+        u32 st = 0, E = ~0u, En = ~0u, v = 0, vn = 0;
+        if (s < n_spans) { st = __ldg(st_mask + s); v = __ldg(v_mask + s); E = st | ~v; }
+        if (s + 1 < n_spans) { vn = __ldg(v_mask + s + 1); En = __ldg(st_mask + s + 1) | ~vn; }
+        n_inst += __popc(st);
+        {                                                                // read bookkeeping of this lane's span
+            u32 r0 = 0, pos0 = 0, end = 0, end2 = 0, skip = 0;
+            if (st) {
+                const u64 p0 = s * 32;
+                r0 = __ldg(span_read + s);
+                const u64 rs = __ldg(off + r0), re = __ldg(off + r0 + 1);
+                pos0 = (u32)(p0 - rs);
+                end = (u32)(re - p0 < (u64)0xFFFF ? re - p0 : (u64)0xFFFF);
+                if (end < 32u) {                                         // the span runs into the next read(s)
+                    u64 r2 = (u64)r0 + 1, re2 = re;
+                    while (r2 < n_reads && skip < 200u) {
+                        re2 = __ldg(off + r2 + 1);
+                        skip++;
+                        if (re2 > re) break;                             // first non-empty read after r0
+                        r2++;
+                    }
+                    if (re2 > re && skip < 200u) end2 = (u32)(re2 - p0 < (u64)0xFFFF ? re2 - p0 : (u64)0xFFFF);
+                    else skip = 0;
+                }
+            }
+            sh.c_read[w][lane] = r0; sh.c_pos[w][lane] = pos0; sh.c_end[w][lane] = (u16)end;
+            sh.c_end2[w][lane] = (u16)end2; sh.c_skip[w][lane] = (u8)skip;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int quarter = 0; quarter < 4; quarter++) {
+            u32 m8 = (st >> (8 * quarter)) & 0xFFu;
+            const u32 cnt = __popc(m8);
+            u32 incl = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const u32 x = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                if (lane >= (u32)d) incl += x;
+            }
+            const u32 total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+            u32 o = head1 + n1 + incl - cnt;
+            while (m8) {
+                const u32 b = (u32)__ffs((int)m8) - 1 + 8 * quarter;
+                m8 &= m8 - 1;
+                const u32 rest = E & ~((2u << b) - 1u);                  // bits above b
+                u32 e = 64, term = 1;                                    // e = 64: no end found (flagged below)
+                if (rest) { e = (u32)__ffs((int)rest) - 1; term = ((v >> e) & 1u) ^ 1u; }
+                else if (En) { const u32 en = (u32)__ffs((int)En) - 1; e = 32 + en; term = ((vn >> en) & 1u) ^ 1u; }
+                u32 n = e - b;
+                if (n > CH_WMAX || n == 0) { flags |= 4u; n = 1; term = 1; }
+                sh.q[w][o & (CH_QCAP - 1)] = (u16)((lane * 32 + b) | ((n - 1) << 10) | (term << 14));
+                o++;
+            }
+            n1 += total;
+            while (n1 >= 32u) {
+                drain1();
+                while (n2 >= 32u) drain2();
+            }
+        }
+        while (n1) drain1();                                             // queue entries die with the staged unit
+        while (n2 >= 32u) drain2();
+    }
+    while (n2) drain2();
+    for (int d = 16; d > 0; d >>= 1) n_inst += __shfl_down_sync(0xFFFFFFFFu, n_inst, d);
+    if (lane == 0 && n_inst) atomicAdd(&cc->n_instances, n_inst);
+    if (flags & 1u) cc->chunk_overflow = 1;
+    if (flags & 2u) cc->list_overflow = 1;
+    if (flags & 4u) cc->bad_chunk = 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_expand (phase 2).  Records = the chunk table's slots followed by the boundary list.  Each lane
+// takes one record and keeps its string in registers.
+//   MODE 0  rolls the node key along the string (one shift per node, as the reference's window loop
+//           slides, debruijn.py:127-128), feeds a HyperLogLog sketch of the node keys (sizes the node
+//           table) and leaves ONE BYTE per (record, node) = top 8 bits of the node's slot hash
+//           (255 = no node), 16 bytes per record
+//   MODE 1  node-table pass: owns the hash bytes [lo8, lo8 + span8], whose home slots form a table
+//           region small enough to stay L2-resident.  A lane compares its record's 16 bytes at once
+//           (SIMD byte compares) and only rebuilds the keys of the nodes in range; those are queued in
+//           a ring and probed 32 at a time -- one probe each, a miss re-queues (as k_insert does) --
+//           so the table traffic runs with full warps although few nodes of a record are in range.
+// ---------------------------------------------------------------------------------------------
+#define EX_RCAP 128
+template <int W> struct ExpandShared {
+    typename KeyOf<W>::type rkey[DBG_WARPS][EX_RCAP];
+    u64 rtag[DBG_WARPS][EX_RCAP];
+    u32 rcnt[DBG_WARPS][EX_RCAP];
+    u16 rmeta[DBG_WARPS][EX_RCAP];            // probes so far << 3 | has_next << 2 | next base
+};
+
+// k bases at base j (< 32) of a chunk string held in registers (2 W words), right-aligned
+template <int W> DBG_D typename KeyOf<W>::type reg_key(const u64 *cw, u32 j, int k);
+template <> DBG_D u64 reg_key<1>(const u64 *cw, u32 j, int k) {
+    const int s = 2 * (int)j;
+    const u64 top = s ? ((cw[0] << s) | (cw[1] >> (64 - s))) : cw[0];
+    return top >> (64 - 2 * k);
+}
+template <> DBG_D K128 reg_key<2>(const u64 *cw, u32 j, int k) {
+    const int s = 2 * (int)j;
+    const u64 hi = s ? ((cw[0] << s) | (cw[1] >> (64 - s))) : cw[0];
+    const u64 lo = s ? ((cw[1] << s) | (cw[2] >> (64 - s))) : cw[1];
+    const int sh = 128 - 2 * k;                                          // 2 <= sh <= 126
+    K128 r;
+    if (sh >= 64) { r.lo = sh == 64 ? hi : hi >> (sh - 64); r.hi = 0; }
+    else { r.lo = (lo >> sh) | (hi << (64 - sh)); r.hi = hi >> sh; }
+    return r;
+}
+// base q of a chunk string held in registers
+template <int W> DBG_D u32 string_base(const u64 *cw, u32 q) {
+    u64 word = cw[0];
+    if (q >= 32) word = cw[1];
+    if (W == 2 && q >= 64) word = cw[2];
+    return (u32)(word >> (62 - 2 * (q & 31))) & 3u;
+}
+// bit b = byte b of x lies in [lo, hi] (lo4 / hi4 = the bound in every byte)
+DBG_D u32 bytes_in_range(u32 x, u32 lo4, u32 hi4) {
+    const u32 t = __vcmpgeu4(x, lo4) & __vcmpleu4(x, hi4) & 0x01010101u;
+    return (t * 0x10204080u) >> 28;
+}
+
+template <int W, int MODE>
+__global__ void __launch_bounds__(DBG_BLOCK, 4)
+k_expand(const ChunkSlot<W> *__restrict__ recs_a, u64 n_a, const ChunkSlot<W> *__restrict__ recs_b, u64 n_b, int k,
+         uint4 *__restrict__ hbytes, Slot<W> *table, u32 n_slots, u32 lo8, u32 span8, u32 *regs, DevCounters *ctr) {
+    typedef typename KeyOf<W>::type K;
+    __shared__ ExpandShared<W> sh;
+    const u32 lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const u32 lt = (1u << lane) - 1;
+    const K mask = key_mask<W>(k);
+    const u32 lo4 = lo8 * 0x01010101u, hi4 = (lo8 + span8) * 0x01010101u;
+    u32 head = 0, nq = 0;
+    bool overflow = false;
+
+    auto drain = [&]() {
+        __syncwarp();
+        const u32 take = nq < 32u ? nq : 32u;
+        const u32 e = (head + lane) & (EX_RCAP - 1);
+        const bool act = lane < take;
+        const K key = sh.rkey[w][e];
+        const u64 tag = sh.rtag[w][e];
+        const u32 cnt = sh.rcnt[w][e];
+        u32 meta = sh.rmeta[w][e];
+        __syncwarp();
+        head = (head + take) & (EX_RCAP - 1);
+        nq -= take;
+        bool again = false;
+        if (act) {
+            u64 idx = slot_home(hash32_key(key), n_slots) + (meta >> 3);
+            if (idx >= n_slots) idx -= n_slots;
+            Slot<W> *s = &table[idx];
+            u64 seen;
+            K cur = load_key_tag(s, &seen);
+            bool hit = true;
+            if (cur != key) {
+                hit = false;
+                if (cur == empty_key<W>()) {
+                    const K old = cas_key(&s->key, empty_key<W>(), key);
+                    if (old == empty_key<W>()) { seen = ~0ULL; hit = true; }
+                    else if (old == key) { seen = __ldcg(&s->tag); hit = true; }
+                }
+            }
+            if (hit) {
+                if (tag < seen) atomicMin(&s->tag, tag);                 // first occurrence
+                if (meta & 4u) atomicAdd(&s->cnt[meta & 3u], cnt);       // debruijn.py:132/136, x multiplicity
+            } else {
+                meta += 8u;
+                if ((meta >> 3) >= DBG_MAX_PROBES) overflow = true; else again = true;
+            }
+        }
+        const u32 mk = __ballot_sync(0xFFFFFFFFu, again);
+        if (again) {
+            const u32 o = (head + nq + __popc(mk & lt)) & (EX_RCAP - 1);
+            sh.rkey[w][o] = key; sh.rtag[w][o] = tag; sh.rcnt[w][o] = cnt; sh.rmeta[w][o] = (u16)meta;
+        }
+        nq += __popc(mk);
+    };
+
+    const u64 n_total = n_a + n_b;
+    const u64 n_batches = (n_total + 31) / 32;
+    const u64 warps_total = (u64)gridDim.x * DBG_WARPS;
+    for (u64 b = (u64)blockIdx.x * DBG_WARPS + w; b < n_batches; b += warps_total) {
+        const u64 idx = b * 32 + lane;
+        u32 n = 0, B = 0, cnt = 0, m16 = 0;
+        u64 tag = 0;
+        u64 cw[2 * W];
+#pragma unroll
+        for (int i = 0; i < 2 * W; i++) cw[i] = 0;
+        if (idx < n_total) {
+            const ChunkSlot<W> *rec = idx < n_a ? recs_a + idx : recs_b + (idx - n_a);
+            K128 h[W];
+#pragma unroll
+            for (int hh = 0; hh < W; hh++) h[hh] = load_k128(&rec->h[hh]);
+            if (h[0] != k128_ones()) {
+                const u32 meta = (u32)(h[0].lo & 0xFFu);
+                n = meta_nodes(meta);
+                B = n + (u32)k - meta_term(meta);
+                chunk_words<W>(h, cw);
+                if (MODE == 1) {
+                    const uint4 hb = __ldg(hbytes + idx);
+                    m16 = bytes_in_range(hb.x, lo4, hi4) | (bytes_in_range(hb.y, lo4, hi4) << 4) |
+                          (bytes_in_range(hb.z, lo4, hi4) << 8) | (bytes_in_range(hb.w, lo4, hi4) << 12);
+                    if (m16) {
+                        const ulonglong2 tc = __ldcg(reinterpret_cast<const ulonglong2 *>(&rec->tag));   // tag | cnt, pad
+                        tag = tc.x;
+                        cnt = (u32)tc.y;
+                    }
+                }
+            }
+        }
+        if (MODE == 0) {
+            K key = reg_key<W>(cw, 0, k);
+            u32 nmax = n;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+                const u32 x = __shfl_xor_sync(0xFFFFFFFFu, nmax, d);
+                nmax = x > nmax ? x : nmax;
+            }
+            u32 hb[4] = {~0u, ~0u, ~0u, ~0u};
+#pragma unroll
+            for (int j = 0; j < CH_WMAX; j++) {
+                if ((u32)j >= nmax) break;
+                const u32 nb = string_base<W>(cw, (u32)(j + k));          // garbage past the string: unused then
+                const u32 hsh = hash32_key(key);
+                if ((u32)j < n) {
+                    const u32 ri = hsh >> (32 - HLL_P);
+                    const u32 rank = (u32)__clz((int)((hsh << HLL_P) | (1u << (HLL_P - 1)))) + 1;
+                    if (regs[ri] < rank) atomicMax(&regs[ri], rank);
+                    const u32 byte = (hsh >> 24) > 254u ? 254u : (hsh >> 24);
+                    hb[j >> 2] = (hb[j >> 2] & ~(0xFFu << (8 * (j & 3)))) | (byte << (8 * (j & 3)));
+                }
+                key = key_roll(key, nb, mask);
+            }
+            if (idx < n_total) hbytes[idx] = make_uint4(hb[0], hb[1], hb[2], hb[3]);
+        } else {
+            while (__any_sync(0xFFFFFFFFu, m16 != 0u)) {
+                const bool want = m16 != 0u;
+                const u32 j = want ? (u32)__ffs((int)m16) - 1 : 0u;
+                m16 &= m16 - 1;
+                const u32 mk = __ballot_sync(0xFFFFFFFFu, want);
+                if (want) {
+                    const u32 q = j + (u32)k;
+                    const bool has_next = q < B;
+                    const u32 nb = string_base<W>(cw, q);
+                    const u32 o = (head + nq + __popc(mk & lt)) & (EX_RCAP - 1);
+                    sh.rkey[w][o] = reg_key<W>(cw, j, k); sh.rtag[w][o] = tag + j; sh.rcnt[w][o] = cnt;
+                    sh.rmeta[w][o] = (u16)((has_next ? 4u : 0u) | (has_next ? nb : 0u));
+                }
+                nq += __popc(mk);
+                while (nq >= 32u) drain();
+            }
+        }
+    }
+    if (MODE == 1) {
+        while (nq) drain();
+        if (overflow) ctr->overflow = 1;
+    }
+}

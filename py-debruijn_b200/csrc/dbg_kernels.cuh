@@ -802,6 +802,8 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_pull_reads(const u64 *__restrict_
 // splitters are what is left not pointing at a root after ceil(log2(m)) + 2 rounds.
 // ---------------------------------------------------------------------------------------------
 #define WALK_SPLIT_LOG2 5
+#define WALK_SUPER_LOG2 5
+#define WALK_BLOCK_JUMP_CAP 32768          // super-splitters one block pointer-jumps by itself
 #define LINK_SPLIT 0x8000000000000000ULL
 #define LINK_DIST_MAX 0x7FFFFFFFu
 DBG_HD u64 link_pack(u32 next, u32 dist) { return ((u64)dist << 32) | next; }
@@ -811,9 +813,13 @@ DBG_HD bool link_is_root(u64 l, u32 v) { return l == (u64)v; }
 DBG_HD u32 link_dist_add(u32 a, u32 b) { u64 s = (u64)a + b; return s > LINK_DIST_MAX ? LINK_DIST_MAX : (u32)s; }
 DBG_HD u32 hash32(u32 x) { x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16; return x; }
 
+// second sampling level: a splitter whose hash bits 5..9 are zero is a SUPER-splitter (1 in 32)
+DBG_HD bool super_hash(u32 v) { return ((hash32(v) >> WALK_SPLIT_LOG2) & ((1u << WALK_SUPER_LOG2) - 1)) == 0; }
+
 __global__ void __launch_bounds__(DBG_BLOCK) k_link_init(const u8 *__restrict__ flags, const u16 *__restrict__ kept,
                                                          const u32 *__restrict__ succ, u64 n_slots, u64 *link,
-                                                         u32 *__restrict__ split_list, u64 split_cap, u64 *cursor) {
+                                                         u32 *__restrict__ split_list, u64 split_cap, u64 *cursor,
+                                                         u32 *__restrict__ super_list, u64 super_cap, u64 *super_cursor) {
     u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     bool split = false;
     if (i < n_slots) {
@@ -832,6 +838,16 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_link_init(const u8 *__restrict__ 
         u64 o = base + __popc(b & ((1u << lane) - 1));
         if (o < split_cap) split_list[o] = (u32)i;
     }
+    const bool sup = split && super_hash((u32)i);
+    u32 bs = __ballot_sync(0xFFFFFFFFu, sup);
+    if (!bs) return;
+    u64 sbase = 0;
+    if (lane == 0) sbase = atomicAdd(super_cursor, (u64)__popc(bs));
+    sbase = __shfl_sync(0xFFFFFFFFu, sbase, 0);
+    if (sup) {
+        u64 o = sbase + __popc(bs & ((1u << lane) - 1));
+        if (o < super_cap) super_list[o] = (u32)i;
+    }
 }
 
 // walk from chain node `from` (exclusive) to the first splitter or root; returns that node and
@@ -849,14 +865,50 @@ DBG_D u32 walk_to_splitter(const u64 *link, u32 from_next, u32 *hops) {
     }
 }
 
-__global__ void __launch_bounds__(DBG_BLOCK) k_sublist(u64 *link, const u32 *__restrict__ split_list, u64 n_split) {
+__global__ void __launch_bounds__(DBG_BLOCK) k_sublist(u64 *link, const u32 *__restrict__ split_list,
+                                                       const u64 *__restrict__ n_split_dev, u64 split_cap) {
     u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    u64 n_split = __ldg(n_split_dev);
+    if (n_split > split_cap) n_split = split_cap;                           // the host reports the overflow
     if (j >= n_split) return;
     u32 v = split_list[j];
     u32 first = link_next(__ldcg(&link[v]));
     u32 hops = 0;
     u32 t = first == v ? NONE32 : walk_to_splitter(link, first, &hops);     // first == v: self loop
     // only this thread writes link[v]; walkers that pass by only look at its SPLIT bit
+    __stcg(&link[v], t == NONE32 ? (LINK_SPLIT | link_pack(v, LINK_DIST_MAX)) : (LINK_SPLIT | link_pack(t, hops)));
+}
+
+// walk over splitter-level links from splitter-or-root `cur` (inclusive) to the first super-splitter
+// or root, adding the hop counts to *hops; NONE32 when caught in a cycle of plain splitters
+DBG_D u32 walk_to_super(const u64 *link, u32 cur, u32 *hops) {
+    u32 d = *hops;
+    u32 check = cur, power = 1, lam = 0;              // Brent: checkpoint every power of two
+    for (;;) {
+        const u64 l = __ldcg(&link[cur]);
+        if (link_is_root(l, cur) || super_hash(cur)) { *hops = d; return cur; }
+        const u32 nx = link_next(l);
+        if (nx == cur) return NONE32;                 // marked splitter-free cycle
+        d = link_dist_add(d, link_dist(l));
+        cur = nx;
+        if (cur == check) return NONE32;
+        if (++lam == power) { check = cur; power <<= 1; lam = 0; }
+    }
+}
+
+// level 2: every super-splitter walks the splitter list to the next super-splitter or root
+__global__ void __launch_bounds__(DBG_BLOCK) k_suplist(u64 *link, const u32 *__restrict__ super_list,
+                                                       const u64 *__restrict__ n_super_dev, u64 super_cap) {
+    u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    u64 n_super = __ldg(n_super_dev);
+    if (n_super > super_cap) n_super = super_cap;
+    if (j >= n_super) return;
+    const u32 v = super_list[j];
+    const u64 l = __ldcg(&link[v]);
+    const u32 first = link_next(l);
+    u32 hops = link_dist(l);
+    const u32 t = first == v ? NONE32 : walk_to_super(link, first, &hops);
+    // only this thread writes link[v]; walkers stop AT a super-splitter (hash test) without reading through it
     __stcg(&link[v], t == NONE32 ? (LINK_SPLIT | link_pack(v, LINK_DIST_MAX)) : (LINK_SPLIT | link_pack(t, hops)));
 }
 
@@ -884,7 +936,43 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_jump(u64 *link, const u32 *__rest
     if (__any_sync(0xFFFFFFFFu, changed) && (threadIdx.x & 31) == 0) ctr->changed = 1;
 }
 
-// (terminal, hops) of an arbitrary node after k_jump has converged
+// level 3 in ONE launch: a single block pointer-jumps the super-splitter list (<= WALK_BLOCK_JUMP_CAP
+// elements) to convergence, __syncthreads between rounds; leaves the round count in ctr->changed
+__global__ void __launch_bounds__(1024) k_jump_block(u64 *link, const u32 *__restrict__ super_list,
+                                                     const u64 *__restrict__ n_super_dev, u64 super_cap,
+                                                     u64 n_slots, int max_rounds, DevCounters *ctr) {
+    __shared__ u32 s_changed;
+    u64 n = __ldg(n_super_dev);
+    if (n > super_cap) n = super_cap;
+    int rounds = 0;
+    for (int r = 0; r < max_rounds; r++) {
+        if (threadIdx.x == 0) s_changed = 0;
+        __syncthreads();
+        bool changed = false;
+        for (u64 j = threadIdx.x; j < n; j += blockDim.x) {
+            const u32 v = super_list[j];
+            const u64 l = __ldcg(&link[v]);
+            const u32 nx = link_next(l);
+            if (nx == v) continue;                      // marked cycle
+            if (nx >= n_slots) { raise_fault(ctr, FAULT_JUMP_RANGE, v); continue; }
+            const u64 ln = __ldcg(&link[nx]);
+            const u32 nn = link_next(ln);
+            if ((ln & LINK_SPLIT) && nn != nx) {        // else nx is a root (final) or a marked cycle
+                __stcg(&link[v], LINK_SPLIT | link_pack(nn, link_dist_add(link_dist(l), link_dist(ln))));
+                changed = true;
+            }
+        }
+        if (changed) s_changed = 1;
+        __syncthreads();
+        rounds = r + 1;
+        if (!s_changed) break;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) ctr->changed = (u32)rounds;
+}
+
+// (terminal, hops) of an arbitrary node after the super-splitter list has converged:
+// chain nodes -> splitter -> super-splitter -> root
 DBG_D bool resolve_chain(const u64 *link, u32 v, u32 *terminal, u32 *hops) {
     u64 l = __ldcg(&link[v]);
     u32 d = 0, w = v;
@@ -895,6 +983,10 @@ DBG_D bool resolve_chain(const u64 *link, u32 v, u32 *terminal, u32 *hops) {
         if (w == NONE32) return false;
         l = __ldcg(&link[w]);
     }
+    if (link_is_root(l, w)) { *terminal = w; *hops = d; return true; }
+    w = walk_to_super(link, w, &d);                          // w is a splitter
+    if (w == NONE32) return false;
+    l = __ldcg(&link[w]);
     if (link_is_root(l, w)) { *terminal = w; *hops = d; return true; }
     u32 t = link_next(l);
     if (!link_is_root(__ldcg(&link[t]), t)) return false;    // cycle

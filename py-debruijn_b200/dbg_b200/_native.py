@@ -18,7 +18,7 @@ CSRC = os.path.join(PKG_DIR, 'csrc')
 LIB_DIR = os.path.join(PKG_DIR, 'lib')
 LIB_PATH = os.path.join(LIB_DIR, 'libdbg_b200.so')
 SOURCES = ('dbg_b200.cu',)
-HEADERS = ('dbg_common.cuh', 'dbg_kernels.cuh')
+HEADERS = ('dbg_common.cuh', 'dbg_kernels.cuh', 'dbg_chunks.cuh')
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-shared', '-Xcompiler', '-fPIC']
@@ -39,12 +39,12 @@ class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         'n_reads', 'n_bases', 'n_windows', 'n_nodes', 'n_edges', 'n_multi', 'n_branch', 'n_starts',
         'n_pulled', 'n_pull_reads', 'n_contigs', 'n_cycle_starts', 'table_slots', 'table_bytes',
-        'hll_estimate', 'n_launches')] + [('key_words', C.c_uint32), ('jump_rounds', C.c_uint32), ('n_insert_passes', C.c_uint32),
+        'hll_estimate', 'n_launches', 'n_chunk_instances', 'n_chunk_list', 'chunk_slots')] + [('key_words', C.c_uint32), ('jump_rounds', C.c_uint32), ('n_insert_passes', C.c_uint32),
                                            ('reserved0', C.c_uint32)] + [
         (n, C.c_float) for n in (
             'ms_h2d', 'ms_pack', 'ms_estimate', 'ms_table_init', 'ms_insert', 'ms_finalize',
             'ms_order', 'ms_lists', 'ms_tips', 'ms_pull_reads', 'ms_build_total', 'ms_walk_rank',
-            'ms_walk_emit', 'ms_walk_total')]
+            'ms_walk_emit', 'ms_walk_total', 'ms_chunk_insert', 'ms_expand_sketch', 'ms_expand', 'reserved1')]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -18,9 +18,11 @@ def build(force=False):
     if not force and os.path.exists(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(d) for d in deps):
         return OUT
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
+    tmp = '%s.%d.tmp' % (OUT, os.getpid())             # concurrent builders (test workers) never see a partial file
     cmd = ['g++', '-x', 'c++', '-std=c++17', '-O2', '-g', '-w', '-DDBG_EMU', '-include',
-           os.path.join(HERE, 'cuda_emu.h'), '-shared', '-fPIC', '-o', OUT, os.path.join(CSRC, 'dbg_b200.cu')]
+           os.path.join(HERE, 'cuda_emu.h'), '-shared', '-fPIC', '-o', tmp, os.path.join(CSRC, 'dbg_b200.cu')]
     subprocess.check_call(cmd)
+    os.replace(tmp, OUT)
     return OUT
 
 

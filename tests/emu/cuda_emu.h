@@ -234,6 +234,12 @@ static inline unsigned __byte_perm(unsigned a, unsigned b, unsigned s) {
         if (sel & 8) byte = (byte & 0x80) ? 0xFF : 0; r |= byte << (8 * i); }
     return r;
 }
+static inline unsigned __vcmpgeu4(unsigned a, unsigned b) {
+    unsigned r = 0; for (int i = 0; i < 4; i++) if (((a >> (8 * i)) & 0xFF) >= ((b >> (8 * i)) & 0xFF)) r |= 0xFFu << (8 * i); return r;
+}
+static inline unsigned __vcmpleu4(unsigned a, unsigned b) {
+    unsigned r = 0; for (int i = 0; i < 4; i++) if (((a >> (8 * i)) & 0xFF) <= ((b >> (8 * i)) & 0xFF)) r |= 0xFFu << (8 * i); return r;
+}
 static inline unsigned __funnelshift_l(unsigned lo, unsigned hi, unsigned s) {
     s &= 31; return s ? (hi << s) | (lo >> (32 - s)) : hi;
 }

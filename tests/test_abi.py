@@ -33,7 +33,7 @@ def test_cuda_library_exports_every_symbol():
 def test_struct_layouts_match_header():
     assert ctypes.sizeof(_native.Contig) == 32
     assert ctypes.sizeof(_native.Segment) == 8
-    assert ctypes.sizeof(_native.Stats) == 16 * 8 + 4 * 4 + 14 * 4
+    assert ctypes.sizeof(_native.Stats) == 19 * 8 + 4 * 4 + 18 * 4      # dbg_stats_t: 19 u64, 4 u32, 18 float
 
 
 def test_product_refuses_to_run_without_a_gpu():

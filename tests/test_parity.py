@@ -195,7 +195,7 @@ def test_partition_passes(backend, monkeypatch, grid):
     """The table build replays the windows once per L2-sized table region; force many passes,
     and few blocks so that every warp carries its queues across many tiles."""
     from dbg_b200 import Graph
-    monkeypatch.setenv('DBG_B200_L2_REGION_BYTES', '4096')
+    monkeypatch.setenv('DBG_B200_L2_REGION_BYTES', '65536')
     if grid:
         monkeypatch.setenv('DBG_B200_INSERT_GRID', grid)
     _, reads = util.synth_reads(21, 12000, 70, 12, err=0.01)
