@@ -81,7 +81,11 @@ struct dbg_handle {
     std::vector<uint32_t> branch, pulled;     // reference order
     std::vector<uint8_t> read_flags;
     bool read_flags_valid = false;
-    std::vector<dbg_contig_t> contigs;
+    std::vector<dbg_contig_t> contigs;        // slow path (dropped starts, final=True enumeration)
+    const dbg_contig_t *cview = nullptr;      // what dbg_contigs / materialize / scores read: `contigs`, or the
+    uint64_t n_cview = 0;                     //   pinned buffer the device's records landed in (fast path)
+    void *pin = nullptr;                      // pinned host staging, grow-only
+    size_t pin_cap = 0;
     std::vector<dbg_segment_t> segments;
     cudaEvent_t ev[EV_MAX];
     int n_ev = 0;
@@ -123,6 +127,23 @@ static int reserve(dbg_t *h, DevBuf &b, size_t bytes) {
     return DBG_OK;
 }
 template <typename T> static T *ptr(DevBuf &b) { return (T *)b.p; }
+
+static int reserve_pinned(dbg_t *h, size_t bytes) {
+    if (h->pin_cap >= bytes) return DBG_OK;
+#ifdef DBG_EMU
+    if (h->pin) free(h->pin);
+    h->pin = malloc(bytes + bytes / 8 + 4096);
+    if (!h->pin) return fail(h, DBG_ERR_NOMEM, "host allocation failed");
+#else
+    if (h->pin) { cudaFreeHost(h->pin); h->pin = nullptr; h->pin_cap = 0; }
+    if (cudaMallocHost(&h->pin, bytes + bytes / 8 + 4096) != cudaSuccess) {
+        h->pin = nullptr;
+        return fail(h, DBG_ERR_NOMEM, "pinned host allocation of %zu bytes failed", bytes);
+    }
+#endif
+    h->pin_cap = bytes + bytes / 8 + 4096;
+    return DBG_OK;
+}
 
 static inline uint64_t cdiv(uint64_t a, uint64_t b) { return (a + b - 1) / b; }
 static inline uint64_t blocks_for(uint64_t n) { return n ? cdiv(n, DBG_BLOCK) : 1; }
@@ -876,6 +897,7 @@ static int walk_impl(dbg_t *h, int stop_at_branch) {
     DevCounters *d_ctr = ptr<DevCounters>(h->b_ctr);
     h->contigs.clear();
     h->segments.clear();
+    h->cview = nullptr; h->n_cview = 0;
     st.n_contigs = 0;
     st.n_cycle_starts = 0;
     st.jump_rounds = 0;
@@ -932,18 +954,22 @@ static int walk_impl(dbg_t *h, int stop_at_branch) {
                     (unsigned long long)h->ctr.n_list_b, (unsigned long long)super_cap);
     const int e1 = ev_mark(h);
 
-    // ---- one record per start (debruijn.py:331-345) ----
+    // ---- one record per start (debruijn.py:331-345), already in dbg_contig_t layout ----
     const uint64_t ns = st.n_starts;
-    std::vector<ContigRec> recs(ns);
+    const dbg_contig_t *recs = nullptr;
+    uint64_t n_dropped = 0;
     if (ns) {
-        TRY(reserve(h, h->b_contig, ns * sizeof(ContigRec)));
+        TRY(reserve(h, h->b_contig, ns * sizeof(dbg_contig_t)));
+        TRY(reserve_pinned(h, ns * sizeof(dbg_contig_t)));
+        CK(cudaMemsetAsync(&d_ctr->n_list_a, 0, 8, h->stream));
         LAUNCH(k_emit, blocks_for(ns), DBG_BLOCK, h->stream, ptr<const u32>(h->b_starts), ns,
-               ptr<const u64>(h->b_link), ptr<const u8>(h->b_flags), ptr<ContigRec>(h->b_contig));
+               ptr<const u64>(h->b_link), ptr<const u8>(h->b_flags), ptr<ContigRec>(h->b_contig), &d_ctr->n_list_a);
         CKK();
-        CK(cudaMemcpyAsync(recs.data(), h->b_contig.p, ns * sizeof(ContigRec), cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaStreamSynchronize(h->stream));
+        CK(cudaMemcpyAsync(h->pin, h->b_contig.p, ns * sizeof(dbg_contig_t), cudaMemcpyDeviceToHost, h->stream));
+        TRY(fetch_counters(h));
+        recs = (const dbg_contig_t *)h->pin;
+        n_dropped = h->ctr.n_list_a;                                   // starts on cycles or pulled themselves
     }
-
     const uint64_t nb = h->branch.size();
     const bool enumerate = !stop_at_branch && nb > 0;
     std::vector<JunctionSucc> junc;
@@ -969,8 +995,9 @@ static int walk_impl(dbg_t *h, int stop_at_branch) {
     };
 
     uint64_t enum_steps = 0;
-    for (uint64_t i = 0; i < ns; i++) {
-        const ContigRec &c = recs[i];
+    const bool fast = !enumerate && n_dropped == 0;                    // every start emits exactly its record
+    for (uint64_t i = 0; i < ns && !fast; i++) {
+        const dbg_contig_t &c = recs[i];
         if (c.kind == T_CYCLE) { st.n_cycle_starts++; continue; }      // debruijn.py:289
         if (!(enumerate && c.kind == T_BRANCH)) {
             if (c.n_nodes == 0) continue;                              // the start itself is pulled (:293-295)
@@ -1048,7 +1075,9 @@ static int walk_impl(dbg_t *h, int stop_at_branch) {
                             (unsigned long long)MAX_ENUM_CONTIGS);
         }
     }
-    st.n_contigs = h->contigs.size();
+    if (fast) { h->cview = recs; h->n_cview = ns; }
+    else { h->cview = h->contigs.data(); h->n_cview = h->contigs.size(); }
+    st.n_contigs = h->n_cview;
     const int e2 = ev_mark(h);
     CK(cudaStreamSynchronize(h->stream));
     st.ms_walk_rank = ev_ms(h, e0, e1);
@@ -1112,6 +1141,11 @@ DBG_API void dbg_destroy(dbg_t *h) {
                      &h->b_scratch[1], &h->b_scratch[2], &h->b_scratch[3], &h->b_scratch[4], &h->b_scratch[5]};
     for (DevBuf *b : all) if (b->p) cudaFree(b->p);
     for (int i = 0; i < EV_MAX; i++) cudaEventDestroy(h->ev[i]);
+#ifdef DBG_EMU
+    if (h->pin) free(h->pin);
+#else
+    if (h->pin) cudaFreeHost(h->pin);
+#endif
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
 }
@@ -1364,7 +1398,7 @@ DBG_API int dbg_walk(dbg_t *h, int stop_at_branch, uint64_t *n_contigs) {
     h->n_ev = 0;
     TRY(DISPATCH(walk_impl, h, stop_at_branch));
     h->walked = true;
-    if (n_contigs) *n_contigs = h->contigs.size();
+    if (n_contigs) *n_contigs = h->n_cview;
     return DBG_OK;
 }
 
@@ -1372,8 +1406,8 @@ DBG_API int dbg_walk(dbg_t *h, int stop_at_branch, uint64_t *n_contigs) {
 
 DBG_API int dbg_contigs(dbg_t *h, dbg_contig_t *out) {
     NEED_WALKED();
-    if (h->contigs.size() && !out) return fail(h, DBG_ERR_ARG, "NULL output");
-    if (h->contigs.size()) memcpy(out, h->contigs.data(), h->contigs.size() * sizeof(dbg_contig_t));
+    if (h->n_cview && !out) return fail(h, DBG_ERR_ARG, "NULL output");
+    if (h->n_cview) memcpy(out, h->cview, h->n_cview * sizeof(dbg_contig_t));
     return DBG_OK;
 }
 
@@ -1398,7 +1432,7 @@ static int materialize_impl(dbg_t *h, const uint64_t *idx, uint64_t n, char *buf
     std::vector<dbg_segment_t> segs;
     uint64_t total = 0;
     for (uint64_t i = 0; i < n; i++) {
-        const dbg_contig_t &c = h->contigs[idx[i]];
+        const dbg_contig_t &c = h->cview[idx[i]];
         segs.clear();
         contig_segments(h, c, segs);
         uint64_t o = off[i];
@@ -1435,7 +1469,7 @@ DBG_API int dbg_materialize(dbg_t *h, const uint64_t *idx, uint64_t n, char *buf
     if (n == 0) return DBG_OK;
     if (!idx || !buf || !off) return fail(h, DBG_ERR_ARG, "NULL argument");
     for (uint64_t i = 0; i < n; i++)
-        if (idx[i] >= h->contigs.size()) return fail(h, DBG_ERR_ARG, "contig index out of range");
+        if (idx[i] >= h->n_cview) return fail(h, DBG_ERR_ARG, "contig index out of range");
     CK(cudaSetDevice(h->device));
     return DISPATCH(materialize_impl, h, idx, n, buf, off);
 }
@@ -1447,7 +1481,7 @@ static int scores_impl(dbg_t *h, const uint64_t *idx, uint64_t n, uint64_t *scor
     std::vector<dbg_segment_t> segs;
     for (uint64_t i = 0; i < n; i++) {
         segs.clear();
-        contig_segments(h, h->contigs[idx[i]], segs);
+        contig_segments(h, h->cview[idx[i]], segs);
         jobs[i].seg_begin = entry.size();
         for (const dbg_segment_t &s : segs) { entry.push_back(s.entry); nodes.push_back(s.n_nodes); }
         jobs[i].seg_end = entry.size();
@@ -1473,7 +1507,7 @@ DBG_API int dbg_contig_scores(dbg_t *h, const uint64_t *idx, uint64_t n, uint64_
     if (n == 0) return DBG_OK;
     if (!idx || !scores) return fail(h, DBG_ERR_ARG, "NULL argument");
     for (uint64_t i = 0; i < n; i++)
-        if (idx[i] >= h->contigs.size()) return fail(h, DBG_ERR_ARG, "contig index out of range");
+        if (idx[i] >= h->n_cview) return fail(h, DBG_ERR_ARG, "contig index out of range");
     CK(cudaSetDevice(h->device));
     return DISPATCH(scores_impl, h, idx, n, scores);
 }

@@ -828,24 +828,32 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_link_init(const u8 *__restrict__ 
         split = chain && ((f & F_START) || (hash32((u32)i) & ((1u << WALK_SPLIT_LOG2) - 1)) == 0);
         link[i] = chain ? (link_pack(succ[i], 1) | (split ? LINK_SPLIT : 0)) : link_pack((u32)i, 0);
     }
-    u32 b = __ballot_sync(0xFFFFFFFFu, split);
-    if (!b) return;
-    u32 lane = threadIdx.x & 31;
-    u64 base = 0;
-    if (lane == 0) base = atomicAdd(cursor, (u64)__popc(b));
-    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    // list append, aggregated per block: one global atomic per block and list (one per warp on the same
+    // word serialised in L2: 3 x 10^5 of them cost more than the kernel's memory traffic)
+    __shared__ u32 s_cnt[2];
+    __shared__ u64 s_base[2];
+    if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const bool sup = split && super_hash((u32)i);
+    const u32 lane = threadIdx.x & 31;
+    const u32 b = __ballot_sync(0xFFFFFFFFu, split), bs = __ballot_sync(0xFFFFFFFFu, sup);
+    u32 w_off = 0, ws_off = 0;
+    if (lane == 0) {
+        if (b) w_off = atomicAdd(&s_cnt[0], (u32)__popc(b));
+        if (bs) ws_off = atomicAdd(&s_cnt[1], (u32)__popc(bs));
+    }
+    w_off = __shfl_sync(0xFFFFFFFFu, w_off, 0);
+    ws_off = __shfl_sync(0xFFFFFFFFu, ws_off, 0);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_cnt[0]) s_base[0] = atomicAdd(cursor, (u64)s_cnt[0]);
+    if (threadIdx.x == 1 && s_cnt[1]) s_base[1] = atomicAdd(super_cursor, (u64)s_cnt[1]);
+    __syncthreads();
     if (split) {
-        u64 o = base + __popc(b & ((1u << lane) - 1));
+        const u64 o = s_base[0] + w_off + __popc(b & ((1u << lane) - 1));
         if (o < split_cap) split_list[o] = (u32)i;
     }
-    const bool sup = split && super_hash((u32)i);
-    u32 bs = __ballot_sync(0xFFFFFFFFu, sup);
-    if (!bs) return;
-    u64 sbase = 0;
-    if (lane == 0) sbase = atomicAdd(super_cursor, (u64)__popc(bs));
-    sbase = __shfl_sync(0xFFFFFFFFu, sbase, 0);
     if (sup) {
-        u64 o = sbase + __popc(bs & ((1u << lane) - 1));
+        const u64 o = s_base[1] + ws_off + __popc(bs & ((1u << lane) - 1));
         if (o < super_cap) super_list[o] = (u32)i;
     }
 }
@@ -994,27 +1002,34 @@ DBG_D bool resolve_chain(const u64 *link, u32 v, u32 *terminal, u32 *hops) {
     return true;
 }
 
-struct ContigRec {          // one per start, in start order; kind T_CYCLE / n_nodes 0 = nothing emitted
-    u32 start, n_nodes, terminal, kind;
+struct ContigRec {          // one per start, in start order; kind T_CYCLE / n_nodes 0 = nothing emitted.
+    u32 start, n_nodes, terminal, kind;     // Same layout as dbg_contig_t (include/dbg_b200.h): the host hands
+    u64 seg_begin, seg_end;                 // the device's array straight to the caller when nothing is dropped
 };
 
 __global__ void __launch_bounds__(DBG_BLOCK) k_emit(const u32 *__restrict__ starts, u64 n_starts,
                                                     const u64 *__restrict__ link, const u8 *__restrict__ flags,
-                                                    ContigRec *__restrict__ out) {
+                                                    ContigRec *__restrict__ out, u64 *n_dropped) {
     u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_starts) return;
-    u32 s = starts[i];
-    u32 t = s, d = 0;
-    ContigRec c;
-    c.start = s;
-    if (!resolve_chain(link, s, &t, &d)) { c.terminal = t; c.kind = T_CYCLE; c.n_nodes = 0; }
-    else {
-        c.terminal = t;
-        u32 f = flags[t];
-        if (f & F_PULLED) { c.kind = T_PULLED; c.n_nodes = d; }          // path stops in front of t
-        else { c.kind = (f & F_DEADEND) ? T_DEADEND : T_BRANCH; c.n_nodes = d + 1; }
+    bool dropped = false;
+    if (i < n_starts) {
+        u32 s = starts[i];
+        u32 t = s, d = 0;
+        ContigRec c;
+        c.start = s;
+        c.seg_begin = 0; c.seg_end = 0;
+        if (!resolve_chain(link, s, &t, &d)) { c.terminal = t; c.kind = T_CYCLE; c.n_nodes = 0; }
+        else {
+            c.terminal = t;
+            u32 f = flags[t];
+            if (f & F_PULLED) { c.kind = T_PULLED; c.n_nodes = d; }          // path stops in front of t
+            else { c.kind = (f & F_DEADEND) ? T_DEADEND : T_BRANCH; c.n_nodes = d + 1; }
+        }
+        dropped = c.n_nodes == 0;
+        out[i] = c;
     }
-    out[i] = c;
+    const u32 b = __ballot_sync(0xFFFFFFFFu, dropped);
+    if (b && (threadIdx.x & 31) == 0) atomicAdd(n_dropped, (u64)__popc(b));
 }
 
 // junction table for the final=True enumeration: for every branch node and each kept successor,
