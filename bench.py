@@ -36,6 +36,9 @@ CONFIGS = {
                name='configs[1]: synthetic 4.6 Mb genome, 150 bp reads 30x, k=31'),
     'c3': dict(G=4_600_000, L=150, cov=30, err=0.01, k=31, thr=2, seed=1002,
                name='configs[2]: 4.6 Mb genome, 1% substitution errors, k=31 (reference semantics, threshold 2)'),
+    'c4': dict(T=10_000, Gmin=1000, Gmax=5000, L=100, cov=20, err=0.0, k=25, thr=2, seed=1004, G=30_000_000,
+               name='configs[3]: 10k templates of 1-5 kb, 100 bp reads 20x, k=25, every template its own graph '
+                    '(one batched pass)'),
     'c5s': dict(G=20_000_000, L=150, cov=30, err=0.0, k=63, thr=2, seed=1005,
                 name='configs[4] shape at 20 Mb: 150 bp reads 30x, k=63 (128-bit k-mers)'),
 }
@@ -61,6 +64,33 @@ def make_reads(cfg, seed_offset=0, G=None):
     bases = np.ascontiguousarray(ASCII[mat]).reshape(-1)
     off = (np.arange(mat.shape[0] + 1, dtype=np.uint64) * np.uint64(L))
     return bases, off
+
+
+def make_reads_batched(cfg, T=None, seed_offset=0):
+    """configs[3]: T templates with lengths uniform in [Gmin, Gmax], each its own read set (deduped
+    per template as II_assembleFromReads.py:52 would for that template).  Returns the concatenated
+    reads, offsets, the batch id of every read and the read range of every batch."""
+    T = T or cfg['T']
+    L, cov = cfg['L'], cfg['cov']
+    rng = np.random.default_rng(cfg['seed'] + seed_offset)
+    lens = rng.integers(cfg['Gmin'], cfg['Gmax'] + 1, T)
+    g_off = np.zeros(T + 1, np.int64)
+    np.cumsum(lens, out=g_off[1:])
+    genome = rng.integers(0, 4, int(g_off[-1]), dtype=np.uint8)
+    n_per = lens * cov // L
+    batch = np.repeat(np.arange(T, dtype=np.int64), n_per)
+    starts = (rng.random(len(batch)) * (lens[batch] - L + 1)).astype(np.int64)
+    key = batch * (cfg['Gmax'] + 1) + starts                       # equal start in one template <=> equal read
+    _, first = np.unique(key, return_index=True)
+    keep = np.sort(first)                                          # first-seen order; batch-major because key is
+    batch, starts = batch[keep], starts[keep]
+    order = np.argsort(batch, kind='stable')
+    batch, starts = batch[order], starts[order]
+    mat = genome[(g_off[batch] + starts)[:, None] + np.arange(L)[None, :]]
+    bases = np.ascontiguousarray(ASCII[mat]).reshape(-1)
+    off = (np.arange(mat.shape[0] + 1, dtype=np.uint64) * np.uint64(L))
+    batch_off = np.searchsorted(batch, np.arange(T + 1))
+    return bases, off, batch.astype(np.uint32), batch_off
 
 
 def make_reads_shard(cfg, rank, world):
@@ -228,6 +258,7 @@ def workload_config(args, cfg, off, nwin, world):
             'genome_bp': cfg['G'] * world, 'read_len': cfg['L'], 'coverage': cfg['cov'], 'error_rate': cfg['err'],
             'reads_per_gpu': int(len(off) - 1), 'windows_per_gpu': int(nwin), 'final': False,
             'parallelism': 'single GPU' if world == 1 else
+            ('templates sharded x%d by batch id, no collective (independent graphs)' % world) if 'T' in cfg else
             ('reads sharded x%d; node records hash-partitioned by owner, NCCL all-to-all + all-gather; graph stages '
              'and contig walk replicated on every rank' % world),
             'l2_policy': 'inputs (ASCII reads + node table) larger than the 126 MB L2; no explicit flush'}
@@ -251,7 +282,12 @@ def run_dbg(args, cfg, rank, local_rank, world):
 
     k, thr = cfg['k'], cfg['thr']
     read_base = 0
-    if world > 1:
+    batched = 'T' in cfg
+    read_batch = None
+    if batched:
+        # independent templates: shard by batch id, no collective; rank r builds its own T templates
+        bases, off, read_batch, _ = make_reads_batched(cfg, seed_offset=rank)
+    elif world > 1:
         bases, off, read_base, _ = make_reads_shard(cfg, rank, world)
     else:
         bases, off = make_reads(cfg)
@@ -263,7 +299,12 @@ def run_dbg(args, cfg, rank, local_rank, world):
     h_off = torch.from_numpy(off.view(np.int64)).pin_memory()
     hb_np, ho_np = h_bases.numpy(), h_off.numpy().view(np.uint64)
 
-    g = Graph(k, device=local_rank)
+    if batched:
+        n_batches = cfg['T']
+        d_batch = torch.from_numpy(read_batch.view(np.int32)).to(dev)
+        h_batch = torch.from_numpy(read_batch.view(np.int32)).pin_memory()
+        hbatch_np = h_batch.numpy().view(np.uint32)
+    g = Graph(k, device=local_rank, key_words=2 if batched and 2 * k + cfg['T'].bit_length() > 64 else 0)
     stream = torch.cuda.current_stream(dev)
     g.set_stream(stream.cuda_stream)
 
@@ -275,7 +316,10 @@ def run_dbg(args, cfg, rank, local_rank, world):
     dist_ms = {}
 
     def step_device():
-        if world > 1:
+        if batched:
+            g.build_batched_packed(None, None, None, n_batches, threshold=thr, final=False,
+                                   device_ptrs=(d_bases.data_ptr(), d_off.data_ptr(), d_batch.data_ptr(), n_reads, n_bases))
+        elif world > 1:
             from dbg_b200 import dist as ddist
             ddist.build_distributed(g, None, read_base, threshold=thr, final=False, timings=dist_ms,
                                     local_device=(d_bases.data_ptr(), d_off.data_ptr(), n_reads, n_bases))
@@ -284,7 +328,9 @@ def run_dbg(args, cfg, rank, local_rank, world):
         g.walk(stop_at_branch=True)
 
     def step_host():
-        if world > 1:
+        if batched:
+            g.build_batched_packed(hb_np, ho_np, hbatch_np, n_batches, threshold=thr, final=False)
+        elif world > 1:
             from dbg_b200 import dist as ddist
             ddist.build_distributed(g, (hb_np, ho_np), read_base, threshold=thr, final=False)
         else:
@@ -384,7 +430,7 @@ def run_dbg(args, cfg, rank, local_rank, world):
     if os.path.exists(traffic_file):
         with open(traffic_file) as f:
             line['roofline']['traffic'] = json.load(f).get('table_build_dram_bytes_per_step')
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and not batched:
         py = cpu_python_port(cfg, args.cpu_sample_bp)
         cp = cpu_c_port(cfg, bases, off)
         line['cpu_baseline'] = {

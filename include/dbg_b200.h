@@ -111,6 +111,9 @@ typedef struct {
 
 /* ---- lifetime ---- */
 int  dbg_create(dbg_t **out, int device, int k);
+/* key_words: 0 = by k (1 for k <= 31, else 2); 2 forces 128-bit keys for a small k, which leaves
+ * room for many batch ids above the k-mer (dbg_build_batched)                               */
+int  dbg_create_ex(dbg_t **out, int device, int k, int key_words);
 void dbg_destroy(dbg_t *h);
 const char *dbg_last_error(const dbg_t *h);          /* h may be NULL: error of a failed create */
 int  dbg_set_stream(dbg_t *h, void *cuda_stream);    /* cudaStream_t; NULL = handle's own stream */
@@ -128,6 +131,20 @@ int dbg_build(dbg_t *h, const uint8_t *bases, const uint64_t *read_off, uint64_t
 int dbg_build_device(dbg_t *h, const uint8_t *d_bases, const uint64_t *d_read_off,
                      uint64_t n_reads, uint64_t n_bases, uint64_t read_idx_base,
                      double threshold, uint32_t flags);
+/* Batched construct_graph: MANY independent read sets ("batches": e.g. one per template,
+ * V_FindTemplateGroups.py:152-190) assembled in ONE pass.  read_batch[r] = batch of read r,
+ * non-decreasing, < n_batches.  The batch id rides in the key bits above the k-mer, so equal
+ * k-mers of different batches are different nodes and no edge joins two batches: the result is
+ * exactly the union of the graphs construct_graph would build per batch, with the tags (global
+ * read index) keeping every per-batch list in the reference's order.  Needs
+ * 2k + ceil(log2(n_batches + 1)) <= 64 (k <= 31) or <= 128 key bits.  In dbg_export_nodes /
+ * dbg_node_keys the batch id is key >> 2k.                                                    */
+int dbg_build_batched(dbg_t *h, const uint8_t *bases, const uint64_t *read_off, uint64_t n_reads,
+                      const uint32_t *read_batch, uint32_t n_batches, double threshold, uint32_t flags);
+/* DEVICE pointers (reads and batch ids already in HBM); the caller vouches for read_batch's order */
+int dbg_build_batched_device(dbg_t *h, const uint8_t *d_bases, const uint64_t *d_read_off, uint64_t n_reads,
+                             uint64_t n_bases, const uint32_t *d_read_batch, uint32_t n_batches,
+                             double threshold, uint32_t flags);
 int dbg_stats(dbg_t *h, dbg_stats_t *out);
 
 /* ---- multi-GPU building blocks: the window loop is data parallel over reads,
@@ -163,6 +180,9 @@ int dbg_node_keys(dbg_t *h, const uint32_t *node_id, uint64_t n, uint64_t *key_l
 /* edge_count_table[(k+1)-mer] for n ASCII (k+1)-mers laid back to back; 0 = absent
  * (II_assembleFromReads.py:17 indexes it per contig window)                                 */
 int dbg_lookup_edges(dbg_t *h, const uint8_t *kplus1mers, uint64_t n, uint32_t *counts);
+/* the same in batch batch[i] of a graph built by dbg_build_batched */
+int dbg_lookup_edges_batched(dbg_t *h, const uint8_t *kplus1mers, const uint32_t *batch, uint64_t n,
+                             uint32_t *counts);
 
 /* ---- output_contigs (debruijn.py:326-347) ----
  * stop_at_branch = 1 when branch_kmer is the list construct_graph returned with final=False,

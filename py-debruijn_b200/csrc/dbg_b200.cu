@@ -72,10 +72,13 @@ struct dbg_handle {
     uint64_t order_cap = 0;
     int order_bits = 0;
     const uint64_t *d_off = nullptr;          // offsets in use (caller's for build_device, ours for build)
+    const uint32_t *d_read_batch = nullptr;   // batched build: batch id per read (device), else NULL
+    int batch_bits = 0;                       // bits the batch id takes above the 2k key bits
+    uint32_t n_batches = 0;
     DevBuf b_bases, b_off, b_packed, b_tile, b_table, b_flags, b_kept, b_succ, b_link, b_ctr, b_hll,
            b_order, b_tag, b_tag2, b_slot, b_slot2, b_sorttmp, b_branch, b_starts, b_pulled, b_readflags,
            b_recs, b_cnt32, b_off64, b_contig, b_junction, b_split, b_h8, b_chunk, b_bitmap, b_stmask, b_vmask,
-           b_spanread, b_cc, b_ctable, b_clist, b_super, b_scratch[6];
+           b_spanread, b_cc, b_ctable, b_clist, b_super, b_readbatch, b_scratch[6];
     DevCounters ctr;
     dbg_stats_t st;
     std::vector<uint32_t> branch, pulled;     // reference order
@@ -540,7 +543,7 @@ static int build_chunks(dbg_t *h, const u64 *d_off, int e0, int e1) {
             LAUNCH(k_chunk_insert<W>, grid, DBG_BLOCK, h->stream, ptr<const u64>(h->b_packed), h->n_words + 4, d_off,
                    h->n_reads, ptr<const u32>(h->b_stmask), ptr<const u32>(h->b_vmask), ptr<const u32>(h->b_spanread),
                    n_spans, n_units, units_per_block, k, ptr<CS>(h->b_ctable), (u32)n_cslots, ptr<CS>(h->b_clist),
-                   list_cap, h->read_idx_base, d_cc);
+                   list_cap, h->read_idx_base, (const u32 *)h->d_read_batch, d_cc);
             CKK();
         }
         const int c = ev_mark(h);
@@ -572,7 +575,7 @@ static int build_chunks(dbg_t *h, const u64 *d_off, int e0, int e1) {
         TRY(reserve(h, h->b_h8, (n_cslots + n_list + 32) * 16));      // one hash byte per (record, node)
         LAUNCH((k_expand<W, 0>), ex_grid, DBG_BLOCK, h->stream, ptr<const CS>(h->b_ctable), n_cslots,
                ptr<const CS>(h->b_clist), n_list, k, ptr<uint4>(h->b_h8), (S *)nullptr, 0u, 0u, 0u,
-               ptr<u32>(h->b_hll), d_ctr);
+               ptr<u32>(h->b_hll), h->batch_bits, d_ctr);
         CKK();
         CK(cudaMemcpyAsync(sketch.data(), h->b_hll.p, HLL_M * 4, cudaMemcpyDeviceToHost, h->stream));
     }
@@ -606,7 +609,7 @@ static int build_chunks(dbg_t *h, const u64 *d_off, int e0, int e1) {
                 const uint32_t hi8 = (part + 1) * 255u / n_parts - 1;
                 LAUNCH((k_expand<W, 1>), ex_grid, DBG_BLOCK, h->stream, ptr<const CS>(h->b_ctable), n_cslots,
                        ptr<const CS>(h->b_clist), n_list, k, ptr<uint4>(h->b_h8), ptr<S>(h->b_table), (u32)n_slots,
-                       lo8, hi8 - lo8, (u32 *)nullptr, d_ctr);
+                       lo8, hi8 - lo8, (u32 *)nullptr, h->batch_bits, d_ctr);
                 CKK();
             }
         }
@@ -670,7 +673,10 @@ static int build_impl(dbg_t *h, const u8 *d_bases, const u64 *d_off) {
     const int e1 = ev_mark(h);
 
     const char *mode = getenv("DBG_B200_BUILD");                      // "windows" = the per-window table build
-    if (mode && !strcmp(mode, "windows")) return build_windows<W>(h, d_off, e0, e1);
+    if (mode && !strcmp(mode, "windows")) {
+        if (h->d_read_batch) return fail(h, DBG_ERR_ARG, "the per-window build (DBG_B200_BUILD=windows) has no batched mode");
+        return build_windows<W>(h, d_off, e0, e1);
+    }
     return build_chunks<W>(h, d_off, e0, e1);
 }
 
@@ -721,7 +727,7 @@ static int graph_order_scan(dbg_t *h) {
         if (h->n_bases) {
             LAUNCH(k_order_scan<W>, h->n_tiles, DBG_BLOCK, h->stream, ptr<const u64>(h->b_packed), (const u64 *)h->d_off,
                    ptr<const u32>(h->b_tile), h->n_bases, h->k, h->read_idx_base, ptr<SideEntry<W>>(h->b_order),
-                   h->order_cap, ptr<const u32>(h->b_bitmap), h->order_bits);
+                   h->order_cap, ptr<const u32>(h->b_bitmap), h->order_bits, (const u32 *)h->d_read_batch);
             CKK();
         }
     }
@@ -779,7 +785,7 @@ static int graph_complete(dbg_t *h) {
             TRY(side_set<W>(h, F_BRANCH, st.n_branch, &cap, &bits));
             LAUNCH(k_pull_reads<W>, h->n_tiles, DBG_BLOCK, h->stream, ptr<const u64>(h->b_packed), (const u64 *)h->d_off,
                    ptr<const u32>(h->b_tile), h->n_bases, k, ptr<SideEntry<W>>(h->b_order), cap,
-                   ptr<const u32>(h->b_bitmap), bits, ptr<u8>(h->b_readflags));
+                   ptr<const u32>(h->b_bitmap), bits, ptr<u8>(h->b_readflags), (const u32 *)h->d_read_batch);
             CKK();
             CK(cudaMemcpyAsync(h->read_flags.data(), h->b_readflags.p, h->n_reads, cudaMemcpyDeviceToHost, h->stream));
             CK(cudaStreamSynchronize(h->stream));
@@ -1097,11 +1103,15 @@ DBG_API int dbg_version(void) { return DBG_ABI_VERSION; }
 
 DBG_API const char *dbg_last_error(const dbg_t *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
-DBG_API int dbg_create(dbg_t **out, int device, int k) {
+DBG_API int dbg_create(dbg_t **out, int device, int k) { return dbg_create_ex(out, device, k, 0); }
+
+DBG_API int dbg_create_ex(dbg_t **out, int device, int k, int key_words) {
     dbg_t *h = nullptr;
     if (!out) return fail(nullptr, DBG_ERR_ARG, "dbg_create: out is NULL");
     *out = nullptr;
     if (k < 1 || k > 63) return fail(nullptr, DBG_ERR_ARG, "k = %d out of range (1..63)", k);
+    if (key_words < 0 || key_words > 2 || (key_words == 1 && k > 31))
+        return fail(nullptr, DBG_ERR_ARG, "key_words = %d is not possible for k = %d", key_words, k);
     int n_dev = 0;
     cudaError_t e = cudaGetDeviceCount(&n_dev);
     if (e != cudaSuccess || n_dev == 0)
@@ -1113,7 +1123,7 @@ DBG_API int dbg_create(dbg_t **out, int device, int k) {
     h = new dbg_handle();
     h->device = device;
     h->k = k;
-    h->W = k <= 31 ? 1 : 2;
+    h->W = key_words ? key_words : (k <= 31 ? 1 : 2);
     memset(&h->st, 0, sizeof h->st);
     memset(&h->ctr, 0, sizeof h->ctr);
     h->st.key_words = (uint32_t)h->W;
@@ -1137,7 +1147,7 @@ DBG_API void dbg_destroy(dbg_t *h) {
                      &h->b_succ, &h->b_link, &h->b_ctr, &h->b_hll, &h->b_order, &h->b_tag, &h->b_tag2, &h->b_slot,
                      &h->b_slot2, &h->b_sorttmp, &h->b_branch, &h->b_starts, &h->b_pulled, &h->b_readflags,
                      &h->b_recs, &h->b_cnt32, &h->b_off64, &h->b_contig, &h->b_junction, &h->b_split, &h->b_h8, &h->b_chunk, &h->b_bitmap,
-                     &h->b_stmask, &h->b_vmask, &h->b_spanread, &h->b_cc, &h->b_ctable, &h->b_clist, &h->b_super, &h->b_scratch[0],
+                     &h->b_stmask, &h->b_vmask, &h->b_spanread, &h->b_cc, &h->b_ctable, &h->b_clist, &h->b_super, &h->b_readbatch, &h->b_scratch[0],
                      &h->b_scratch[1], &h->b_scratch[2], &h->b_scratch[3], &h->b_scratch[4], &h->b_scratch[5]};
     for (DevBuf *b : all) if (b->p) cudaFree(b->p);
     for (int i = 0; i < EV_MAX; i++) cudaEventDestroy(h->ev[i]);
@@ -1156,10 +1166,26 @@ DBG_API int dbg_set_stream(dbg_t *h, void *cuda_stream) {
     return DBG_OK;
 }
 
-DBG_API int dbg_build_device(dbg_t *h, const uint8_t *d_bases, const uint64_t *d_read_off, uint64_t n_reads,
-                     uint64_t n_bases, uint64_t read_idx_base, double threshold, uint32_t flags) {
+static int build_device_common(dbg_t *h, const uint8_t *d_bases, const uint64_t *d_read_off, uint64_t n_reads,
+                               uint64_t n_bases, uint64_t read_idx_base, double threshold, uint32_t flags,
+                               const uint32_t *d_read_batch, uint32_t n_batches) {
     if (!h) return DBG_ERR_ARG;
     if ((n_bases && !d_bases) || !d_read_off) return fail(h, DBG_ERR_ARG, "dbg_build_device: NULL input");
+    h->d_read_batch = nullptr;
+    h->batch_bits = 0;
+    h->n_batches = 0;
+    if (d_read_batch) {
+        // batch ids live in the key bits above the k-mer; the all-ones key stays free for EMPTY
+        int bb = 0;
+        while (bb < 32 && ((1ull << bb) - 1) < (uint64_t)n_batches) bb++;
+        if (((1ull << bb) - 1) < (uint64_t)n_batches || 2 * h->k + bb > 64 * h->W)
+            return fail(h, DBG_ERR_ARG, "%u batches need %d key bits above the %d bits of a %d-mer: more than the %d-bit key has",
+                        n_batches, bb, 2 * h->k, h->k, 64 * h->W);
+        if (flags & DBG_TABLE_ONLY) return fail(h, DBG_ERR_ARG, "a batched build cannot be DBG_TABLE_ONLY");
+        h->d_read_batch = d_read_batch;
+        h->batch_bits = bb;
+        h->n_batches = n_batches;
+    }
     if (n_reads + read_idx_base >= 0xFFFFFFFFull)
         return fail(h, DBG_ERR_OVERFLOW, "read index exceeds 32 bits");
     if (threshold != threshold) return fail(h, DBG_ERR_ARG, "threshold is NaN");
@@ -1190,14 +1216,12 @@ DBG_API int dbg_build_device(dbg_t *h, const uint8_t *d_bases, const uint64_t *d
     return DBG_OK;
 }
 
-DBG_API int dbg_build(dbg_t *h, const uint8_t *bases, const uint64_t *read_off, uint64_t n_reads,
-              uint64_t read_idx_base, double threshold, uint32_t flags) {
-    if (!h) return DBG_ERR_ARG;
-    if (!read_off) return fail(h, DBG_ERR_ARG, "dbg_build: read_off is NULL");
-    const uint64_t n_bases = read_off[n_reads];
-    if (n_bases && !bases) return fail(h, DBG_ERR_ARG, "dbg_build: bases is NULL");
-    CK(cudaSetDevice(h->device));
-    h->n_ev = 0;
+DBG_API int dbg_build_device(dbg_t *h, const uint8_t *d_bases, const uint64_t *d_read_off, uint64_t n_reads,
+                     uint64_t n_bases, uint64_t read_idx_base, double threshold, uint32_t flags) {
+    return build_device_common(h, d_bases, d_read_off, n_reads, n_bases, read_idx_base, threshold, flags, nullptr, 0);
+}
+
+static int upload_reads(dbg_t *h, const uint8_t *bases, const uint64_t *read_off, uint64_t n_reads, uint64_t n_bases) {
     TRY(reserve(h, h->b_bases, n_bases + 32));
     TRY(reserve(h, h->b_off, (n_reads + 1) * 8));
     const int a = ev_mark(h);
@@ -1206,6 +1230,48 @@ DBG_API int dbg_build(dbg_t *h, const uint8_t *bases, const uint64_t *read_off, 
     const int b = ev_mark(h);
     CK(cudaStreamSynchronize(h->stream));
     h->pending_h2d = ev_ms(h, a, b);
+    return DBG_OK;
+}
+
+DBG_API int dbg_build_batched(dbg_t *h, const uint8_t *bases, const uint64_t *read_off, uint64_t n_reads,
+                              const uint32_t *read_batch, uint32_t n_batches, double threshold, uint32_t flags) {
+    if (!h) return DBG_ERR_ARG;
+    if (!read_off || (n_reads && !read_batch)) return fail(h, DBG_ERR_ARG, "dbg_build_batched: NULL input");
+    if (n_batches == 0) return fail(h, DBG_ERR_ARG, "dbg_build_batched: n_batches is 0");
+    const uint64_t n_bases = read_off[n_reads];
+    if (n_bases && !bases) return fail(h, DBG_ERR_ARG, "dbg_build_batched: bases is NULL");
+    for (uint64_t r = 0; r < n_reads; r++)
+        if (read_batch[r] >= n_batches || (r && read_batch[r] < read_batch[r - 1]))
+            return fail(h, DBG_ERR_ARG, "dbg_build_batched: read_batch must be non-decreasing and < n_batches (read %llu)",
+                        (unsigned long long)r);
+    CK(cudaSetDevice(h->device));
+    h->n_ev = 0;
+    TRY(upload_reads(h, bases, read_off, n_reads, n_bases));
+    TRY(reserve(h, h->b_readbatch, (n_reads + 1) * 4));
+    if (n_reads) CK(cudaMemcpyAsync(h->b_readbatch.p, read_batch, n_reads * 4, cudaMemcpyHostToDevice, h->stream));
+    return build_device_common(h, ptr<const uint8_t>(h->b_bases), ptr<const uint64_t>(h->b_off), n_reads, n_bases, 0,
+                               threshold, flags, ptr<const uint32_t>(h->b_readbatch), n_batches);
+}
+
+DBG_API int dbg_build_batched_device(dbg_t *h, const uint8_t *d_bases, const uint64_t *d_read_off, uint64_t n_reads,
+                                     uint64_t n_bases, const uint32_t *d_read_batch, uint32_t n_batches,
+                                     double threshold, uint32_t flags) {
+    if (!h) return DBG_ERR_ARG;
+    if (n_batches == 0 || (n_reads && !d_read_batch))
+        return fail(h, DBG_ERR_ARG, "dbg_build_batched_device: bad argument");
+    CK(cudaSetDevice(h->device));
+    return build_device_common(h, d_bases, d_read_off, n_reads, n_bases, 0, threshold, flags, d_read_batch, n_batches);
+}
+
+DBG_API int dbg_build(dbg_t *h, const uint8_t *bases, const uint64_t *read_off, uint64_t n_reads,
+              uint64_t read_idx_base, double threshold, uint32_t flags) {
+    if (!h) return DBG_ERR_ARG;
+    if (!read_off) return fail(h, DBG_ERR_ARG, "dbg_build: read_off is NULL");
+    const uint64_t n_bases = read_off[n_reads];
+    if (n_bases && !bases) return fail(h, DBG_ERR_ARG, "dbg_build: bases is NULL");
+    CK(cudaSetDevice(h->device));
+    h->n_ev = 0;
+    TRY(upload_reads(h, bases, read_off, n_reads, n_bases));
     return dbg_build_device(h, ptr<const uint8_t>(h->b_bases), ptr<const uint64_t>(h->b_off), n_reads, n_bases,
                             read_idx_base, threshold, flags);
 }
@@ -1369,14 +1435,16 @@ DBG_API int dbg_node_keys(dbg_t *h, const uint32_t *node_id, uint64_t n, uint64_
 }
 
 template <int W>
-static int lookup_impl(dbg_t *h, const uint8_t *q, uint64_t n, uint32_t *counts) {
+static int lookup_impl(dbg_t *h, const uint8_t *q, const uint32_t *batch, uint64_t n, uint32_t *counts) {
     DevBuf *s = h->b_scratch;
     const uint64_t bytes = n * (uint64_t)(h->k + 1);
     TRY(reserve(h, s[0], bytes));
     TRY(reserve(h, s[1], n * 4));
+    TRY(reserve(h, s[2], n * 4));
     CK(cudaMemcpyAsync(s[0].p, q, bytes, cudaMemcpyHostToDevice, h->stream));
+    if (batch) CK(cudaMemcpyAsync(s[2].p, batch, n * 4, cudaMemcpyHostToDevice, h->stream));
     LAUNCH(k_lookup_edges<W>, blocks_for(n), DBG_BLOCK, h->stream, ptr<const Slot<W>>(h->b_table), h->n_slots, h->k,
-           ptr<const u8>(s[0]), n, ptr<u32>(s[1]));
+           ptr<const u8>(s[0]), batch ? ptr<const u32>(s[2]) : (const u32 *)nullptr, n, ptr<u32>(s[1]));
     CKK();
     CK(cudaMemcpyAsync(counts, s[1].p, n * 4, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -1388,7 +1456,19 @@ DBG_API int dbg_lookup_edges(dbg_t *h, const uint8_t *kplus1mers, uint64_t n, ui
     if (n == 0) return DBG_OK;
     if (!kplus1mers || !counts) return fail(h, DBG_ERR_ARG, "NULL argument");
     CK(cudaSetDevice(h->device));
-    return DISPATCH(lookup_impl, h, kplus1mers, n, counts);
+    return DISPATCH(lookup_impl, h, kplus1mers, (const uint32_t *)nullptr, n, counts);
+}
+
+DBG_API int dbg_lookup_edges_batched(dbg_t *h, const uint8_t *kplus1mers, const uint32_t *batch, uint64_t n,
+                                     uint32_t *counts) {
+    NEED_BUILT();
+    if (n == 0) return DBG_OK;
+    if (!kplus1mers || !counts || !batch) return fail(h, DBG_ERR_ARG, "NULL argument");
+    if (!h->batch_bits && h->n_batches == 0) return fail(h, DBG_ERR_STATE, "the graph was not built by dbg_build_batched");
+    for (uint64_t i = 0; i < n; i++)
+        if (batch[i] >= h->n_batches) return fail(h, DBG_ERR_ARG, "batch id %u out of range", batch[i]);
+    CK(cudaSetDevice(h->device));
+    return DISPATCH(lookup_impl, h, kplus1mers, batch, n, counts);
 }
 
 DBG_API int dbg_walk(dbg_t *h, int stop_at_branch, uint64_t *n_contigs) {

@@ -314,7 +314,8 @@ __global__ void __launch_bounds__(DBG_BLOCK, DBG_CHUNK_MIN_BLOCKS)
 k_chunk_insert(const u64 *__restrict__ packed, u64 n_words_padded, const u64 *__restrict__ off, u64 n_reads,
                const u32 *__restrict__ st_mask, const u32 *__restrict__ v_mask, const u32 *__restrict__ span_read,
                u64 n_spans, u64 n_units, u64 units_per_block, int k, ChunkSlot<W> *table, u32 n_slots,
-               ChunkSlot<W> *list, u64 list_cap, u64 read_idx_base, ChunkCounters *cc) {
+               ChunkSlot<W> *list, u64 list_cap, u64 read_idx_base, const u32 *__restrict__ read_batch,
+               ChunkCounters *cc) {
     __shared__ ChunkInsertShared<W> sh;
     const u32 lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const u32 lt = (1u << lane) - 1;
@@ -384,6 +385,7 @@ k_chunk_insert(const u64 *__restrict__ packed, u64 n_words_padded, const u64 *__
             tag = ((read_idx_base + r) << 32) | pos;
             boundary = pos == 0 || term;
             key = chunk_key_from_stream<W>(sh.words[w], rel, (int)n + k - (int)term, chunk_meta(n, term));
+            if (read_batch) key.h[W - 1].lo |= (u64)__ldg(read_batch + r) << 8;     // batch id: spare bits past the string
         }
         if (boundary) {                                                  // first / last chunk of a read: its own list slot
             const u64 o = 2 * (tag >> 32) - 2 * read_idx_base + ((u32)tag == 0 ? 0u : 1u);   // 2 x local read index (+ 1: last chunk)
@@ -534,7 +536,8 @@ DBG_D u32 bytes_in_range(u32 x, u32 lo4, u32 hi4) {
 template <int W, int MODE>
 __global__ void __launch_bounds__(DBG_BLOCK, 4)
 k_expand(const ChunkSlot<W> *__restrict__ recs_a, u64 n_a, const ChunkSlot<W> *__restrict__ recs_b, u64 n_b, int k,
-         uint4 *__restrict__ hbytes, Slot<W> *table, u32 n_slots, u32 lo8, u32 span8, u32 *regs, DevCounters *ctr) {
+         uint4 *__restrict__ hbytes, Slot<W> *table, u32 n_slots, u32 lo8, u32 span8, u32 *regs, int batch_bits,
+         DevCounters *ctr) {
     typedef typename KeyOf<W>::type K;
     __shared__ ExpandShared<W> sh;
     const u32 lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -593,7 +596,7 @@ k_expand(const ChunkSlot<W> *__restrict__ recs_a, u64 n_a, const ChunkSlot<W> *_
     const u64 warps_total = (u64)gridDim.x * DBG_WARPS;
     for (u64 b = (u64)blockIdx.x * DBG_WARPS + w; b < n_batches; b += warps_total) {
         const u64 idx = b * 32 + lane;
-        u32 n = 0, B = 0, cnt = 0, m16 = 0;
+        u32 n = 0, B = 0, cnt = 0, m16 = 0, batch = 0;
         u64 tag = 0;
         u64 cw[2 * W];
 #pragma unroll
@@ -608,6 +611,7 @@ k_expand(const ChunkSlot<W> *__restrict__ recs_a, u64 n_a, const ChunkSlot<W> *_
                 n = meta_nodes(meta);
                 B = n + (u32)k - meta_term(meta);
                 chunk_words<W>(h, cw);
+                if (batch_bits) batch = (u32)(h[W - 1].lo >> 8) & (u32)((1ull << batch_bits) - 1);
                 if (MODE == 1) {
                     const uint4 hb = __ldg(hbytes + idx);
                     m16 = bytes_in_range(hb.x, lo4, hi4) | (bytes_in_range(hb.y, lo4, hi4) << 4) |
@@ -621,7 +625,7 @@ k_expand(const ChunkSlot<W> *__restrict__ recs_a, u64 n_a, const ChunkSlot<W> *_
             }
         }
         if (MODE == 0) {
-            K key = reg_key<W>(cw, 0, k);
+            K key = key_add_batch(reg_key<W>(cw, 0, k), batch, k);
             u32 nmax = n;
 #pragma unroll
             for (int d = 16; d > 0; d >>= 1) {
@@ -655,7 +659,8 @@ k_expand(const ChunkSlot<W> *__restrict__ recs_a, u64 n_a, const ChunkSlot<W> *_
                     const bool has_next = q < B;
                     const u32 nb = string_base<W>(cw, q);
                     const u32 o = (head + nq + __popc(mk & lt)) & (EX_RCAP - 1);
-                    sh.rkey[w][o] = reg_key<W>(cw, j, k); sh.rtag[w][o] = tag + j; sh.rcnt[w][o] = cnt;
+                    sh.rkey[w][o] = key_add_batch(reg_key<W>(cw, j, k), batch, k); sh.rtag[w][o] = tag + j;
+                    sh.rcnt[w][o] = cnt;
                     sh.rmeta[w][o] = (u16)((has_next ? 4u : 0u) | (has_next ? nb : 0u));
                 }
                 nq += __popc(mk);

@@ -73,13 +73,23 @@ template <> DBG_HD K128 key_mask<2>(int k) {
     return r;
 }
 
-// successor key: drop the first base, append `nb` (debruijn.py:128: read[i+1:i+k+1])
-DBG_HD u64 key_roll(u64 key, u32 nb, u64 mask) { return ((key << 2) | (u64)nb) & mask; }
+// successor key: drop the first base, append `nb` (debruijn.py:128: read[i+1:i+k+1]).  Bits above
+// the 2k key bits are kept as they are: a batched build (many independent read sets in one table)
+// stores the batch id there, so a node and its successor stay in the same batch.
+DBG_HD u64 key_roll(u64 key, u32 nb, u64 mask) { return (((key << 2) | (u64)nb) & mask) | (key & ~mask); }
 DBG_HD K128 key_roll(K128 key, u32 nb, K128 mask) {
     K128 r;
-    r.hi = ((key.hi << 2) | (key.lo >> 62)) & mask.hi;
-    r.lo = ((key.lo << 2) | (u64)nb) & mask.lo;
+    r.hi = (((key.hi << 2) | (key.lo >> 62)) & mask.hi) | (key.hi & ~mask.hi);
+    r.lo = (((key.lo << 2) | (u64)nb) & mask.lo) | (key.lo & ~mask.lo);
     return r;
+}
+// batch id in the bits above the k-mer (0 = not batched: a no-op)
+DBG_HD u64 key_add_batch(u64 key, u32 batch, int k) { return key | ((u64)batch << (2 * k)); }
+DBG_HD K128 key_add_batch(K128 key, u32 batch, int k) {
+    const int sh = 2 * k;                                    // 2 .. 126
+    if (sh >= 64) key.hi |= (u64)batch << (sh - 64);
+    else { key.lo |= (u64)batch << sh; if (sh > 32) key.hi |= (u64)batch >> (64 - sh); }
+    return key;
 }
 // append without masking (building a key base by base)
 DBG_HD u64 key_push(u64 key, u32 nb) { return (key << 2) | (u64)nb; }

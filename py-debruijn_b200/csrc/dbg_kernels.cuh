@@ -651,10 +651,12 @@ template <int W>
 __global__ void __launch_bounds__(DBG_BLOCK) k_order_scan(const u64 *__restrict__ packed, const u64 *__restrict__ off,
                                                           const u32 *__restrict__ tile_first, u64 n_bases, int k,
                                                           u64 read_idx_base, SideEntry<W> *st, u64 cap,
-                                                          const u32 *__restrict__ bm, int bits) {
+                                                          const u32 *__restrict__ bm, int bits,
+                                                          const u32 *__restrict__ read_batch) {
     typedef typename KeyOf<W>::type K;
     for_windows<W, true>(packed, off, tile_first, n_bases, k,
         [&](K key, u32 r, u32 pos, bool has_next, u32 nb) {
+            if (read_batch) key = key_add_batch(key, __ldg(read_batch + r), k);
             if (!has_next || !bitmap_test(bm, bits, hash32_key(key))) return;
             u64 e = side_locate<W>(st, cap, key, false);
             if (e == NONE64) return;                                     // not a multi-successor node
@@ -772,10 +774,11 @@ template <int W>
 __global__ void __launch_bounds__(DBG_BLOCK) k_pull_reads(const u64 *__restrict__ packed, const u64 *__restrict__ off,
                                                           const u32 *__restrict__ tile_first, u64 n_bases, int k,
                                                           SideEntry<W> *st, u64 cap, const u32 *__restrict__ bm, int bits,
-                                                          u8 *read_flags) {
+                                                          u8 *read_flags, const u32 *__restrict__ read_batch) {
     typedef typename KeyOf<W>::type K;
     for_windows<W, false>(packed, off, tile_first, n_bases, k,
         [&](K key, u32 r, u32, bool, u32) {
+            if (read_batch) key = key_add_batch(key, __ldg(read_batch + r), k);
             if (!bitmap_test(bm, bits, hash32_key(key))) return;
             if (side_locate<W>(st, cap, key, false) != NONE64) read_flags[r] = 1;     // key is a branch node
         });
@@ -1132,7 +1135,8 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_scores(const Slot<W> *__restrict_
 
 template <int W>
 __global__ void __launch_bounds__(DBG_BLOCK) k_lookup_edges(const Slot<W> *__restrict__ table, u64 n_slots, int k,
-                                                            const u8 *__restrict__ q, u64 n, u32 *__restrict__ out) {
+                                                            const u8 *__restrict__ q, const u32 *__restrict__ q_batch,
+                                                            u64 n, u32 *__restrict__ out) {
     typedef typename KeyOf<W>::type K;
     u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -1148,6 +1152,7 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_lookup_edges(const Slot<W> *__res
     }
     u32 res = 0;
     if (!bad) {
+        if (q_batch) key = key_add_batch(key, q_batch[i], k);
         u64 idx = table_find<W>(table, n_slots, key);
         if (idx != NONE64) res = table[idx].cnt[code];
     }

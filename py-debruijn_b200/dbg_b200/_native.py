@@ -63,12 +63,15 @@ class Segment(C.Structure):
 _P = C.c_void_p
 SYMBOLS = {
     'dbg_create': (C.c_int, [C.POINTER(_P), C.c_int, C.c_int]),
+    'dbg_create_ex': (C.c_int, [C.POINTER(_P), C.c_int, C.c_int, C.c_int]),
     'dbg_destroy': (None, [_P]),
     'dbg_last_error': (C.c_char_p, [_P]),
     'dbg_set_stream': (C.c_int, [_P, _P]),
     'dbg_version': (C.c_int, []),
     'dbg_build': (C.c_int, [_P, _P, _P, C.c_uint64, C.c_uint64, C.c_double, C.c_uint32]),
     'dbg_build_device': (C.c_int, [_P, _P, _P, C.c_uint64, C.c_uint64, C.c_uint64, C.c_double, C.c_uint32]),
+    'dbg_build_batched': (C.c_int, [_P, _P, _P, C.c_uint64, _P, C.c_uint32, C.c_double, C.c_uint32]),
+    'dbg_build_batched_device': (C.c_int, [_P, _P, _P, C.c_uint64, C.c_uint64, _P, C.c_uint32, C.c_double, C.c_uint32]),
     'dbg_stats': (C.c_int, [_P, C.POINTER(Stats)]),
     'dbg_graph_stage': (C.c_int, [_P, C.c_int, C.c_double, C.c_uint32]),
     'dbg_record_words': (C.c_int, [_P]),
@@ -85,6 +88,7 @@ SYMBOLS = {
     'dbg_pull_reads': (C.c_int, [_P, _P]),
     'dbg_node_keys': (C.c_int, [_P, _P, C.c_uint64, _P, _P]),
     'dbg_lookup_edges': (C.c_int, [_P, _P, C.c_uint64, _P]),
+    'dbg_lookup_edges_batched': (C.c_int, [_P, _P, _P, C.c_uint64, _P]),
     'dbg_walk': (C.c_int, [_P, C.c_int, C.POINTER(C.c_uint64)]),
     'dbg_contigs': (C.c_int, [_P, _P]),
     'dbg_segments': (C.c_int, [_P, _P, C.POINTER(C.c_uint64)]),

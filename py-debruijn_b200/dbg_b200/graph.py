@@ -73,12 +73,12 @@ class Graph:
     """One de Bruijn graph resident on one GPU (one ``dbg_t``).  Re-usable: ``build`` may be
     called again with new reads and keeps its HBM."""
 
-    def __init__(self, k, device=None, lib=None):
+    def __init__(self, k, device=None, lib=None, key_words=0):
         self.lib = lib or N.get()
         self.k = int(k)
         self.device = _default_device() if device is None else int(device)
         h = C.c_void_p()
-        rc = self.lib.dbg_create(C.byref(h), self.device, self.k)
+        rc = self.lib.dbg_create_ex(C.byref(h), self.device, self.k, int(key_words))
         if rc != N.DBG_OK:
             msg = self.lib.dbg_last_error(None)
             N._raise(rc, msg.decode() if msg else '')
@@ -88,6 +88,7 @@ class Graph:
         self._reset_cache()
 
     def _reset_cache(self):
+        self._batch_cache = None
         self._nodes = None
         self._labels = None
         self._contigs = None
@@ -118,6 +119,50 @@ class Graph:
         self.n_reads = len(off) - 1
         rc = self.lib.dbg_build(self.h, bases.ctypes.data if len(bases) else None, off.ctypes.data,
                                 self.n_reads, int(read_idx_base), float(threshold), flags)
+        self.lib.check(self.h, rc)
+        return self
+
+    def build_batched(self, batches, threshold=3, final=False, exact_order=True, pull_reads=True):
+        """MANY independent read sets in one pass (include/dbg_b200.h, dbg_build_batched):
+        `batches` is a list of list[str]; batch b's reads are reads[batch_off[b]:batch_off[b+1]]."""
+        reads = [r for b in batches for r in b]
+        bases, off = pack_reads(reads)
+        sizes = np.fromiter((len(b) for b in batches), dtype=np.int64, count=len(batches))
+        self.batch_off = np.zeros(len(batches) + 1, np.int64)
+        np.cumsum(sizes, out=self.batch_off[1:])
+        read_batch = np.repeat(np.arange(len(batches), dtype=np.uint32), sizes)
+        self.reads = reads
+        self.final = bool(final)
+        self.n_batches = len(batches)
+        self._reset_cache()
+        self._keep = (bases, off, read_batch)
+        self.n_reads = len(off) - 1
+        rc = self.lib.dbg_build_batched(self.h, bases.ctypes.data if len(bases) else None, off.ctypes.data,
+                                        self.n_reads, read_batch.ctypes.data if len(read_batch) else None,
+                                        self.n_batches, float(threshold), self._flags(final, exact_order, pull_reads))
+        self.lib.check(self.h, rc)
+        return self
+
+    def build_batched_packed(self, bases, off, read_batch, n_batches, threshold=3, final=False, exact_order=True,
+                             pull_reads=True, device_ptrs=None):
+        """build_batched on packed arrays (uint8 bases, uint64 offsets, uint32 batch per read), or on
+        device pointers: device_ptrs = (d_bases, d_off, d_read_batch, n_reads, n_bases)."""
+        self.reads = None
+        self.final = bool(final)
+        self.n_batches = int(n_batches)
+        self._reset_cache()
+        flags = self._flags(final, exact_order, pull_reads)
+        if device_ptrs is not None:
+            d_bases, d_off, d_batch, n_reads, n_bases = device_ptrs
+            self.n_reads = int(n_reads)
+            rc = self.lib.dbg_build_batched_device(self.h, d_bases, d_off, self.n_reads, int(n_bases), d_batch,
+                                                   self.n_batches, float(threshold), flags)
+        else:
+            self._keep = (bases, off, read_batch)
+            self.n_reads = len(off) - 1
+            rc = self.lib.dbg_build_batched(self.h, bases.ctypes.data if len(bases) else None, off.ctypes.data,
+                                            self.n_reads, read_batch.ctypes.data if len(read_batch) else None,
+                                            self.n_batches, float(threshold), flags)
         self.lib.check(self.h, rc)
         return self
 
@@ -226,7 +271,19 @@ class Graph:
             self.lib.check(self.h, rc)
             order = np.argsort(a['tag'], kind='stable')
             self._nodes = {f: v[order] for f, v in a.items()}
+            self._nodes['batch'] = self.batch_of_keys(self._nodes['key_lo'], self._nodes['key_hi'])
         return self._nodes
+
+    def batch_of_keys(self, key_lo, key_hi):
+        """Batch id of node keys (the bits above the 2k key bits; 0 for a graph built without batches)."""
+        sh = 2 * self.k
+        lo = np.asarray(key_lo, dtype=np.uint64)
+        hi = np.asarray(key_hi, dtype=np.uint64)
+        if sh >= 64:
+            b = hi >> np.uint64(sh - 64)
+        else:
+            b = (lo >> np.uint64(sh)) | (hi << np.uint64(64 - sh))
+        return (b & np.uint64(0xFFFFFFFF)).astype(np.uint32)
 
     def labels(self):
         if self._labels is None:
@@ -260,8 +317,9 @@ class Graph:
         self.lib.check(self.h, self.lib.dbg_pull_reads(self.h, out.ctypes.data if self.n_reads else None))
         return out
 
-    def lookup_edges(self, kplus1mers):
-        """edge_count_table values for a list of (k+1)-mer strings; 0 = absent."""
+    def lookup_edges(self, kplus1mers, batch=None):
+        """edge_count_table values for a list of (k+1)-mer strings; 0 = absent.  `batch` = one
+        batch id per query for a graph built by build_batched."""
         n = len(kplus1mers)
         out = np.zeros(n, np.uint32)
         if n == 0:
@@ -269,7 +327,11 @@ class Graph:
         buf = ''.join(kplus1mers).encode('ascii', 'replace')
         if len(buf) != n * (self.k + 1):
             raise ValueError('every query must have length k+1')
-        self.lib.check(self.h, self.lib.dbg_lookup_edges(self.h, buf, n, out.ctypes.data))
+        if batch is None:
+            self.lib.check(self.h, self.lib.dbg_lookup_edges(self.h, buf, n, out.ctypes.data))
+        else:
+            b = np.ascontiguousarray(np.broadcast_to(np.asarray(batch, dtype=np.uint32), (n,)))
+            self.lib.check(self.h, self.lib.dbg_lookup_edges_batched(self.h, buf, b.ctypes.data, n, out.ctypes.data))
         return out
 
     # ---- output_contigs ------------------------------------------------------------------
@@ -320,6 +382,90 @@ class Graph:
         if len(idx):
             self.lib.check(self.h, self.lib.dbg_contig_scores(self.h, idx.ctypes.data, len(idx), out.ctypes.data))
         return out
+
+
+class _BatchStats:
+    __slots__ = ('n_nodes', 'n_edges', 'n_branch', 'n_starts', 'n_pulled', 'n_pull_reads')
+
+
+class BatchGraph:
+    """One batch of a graph built by Graph.build_batched, with the part of Graph's interface the
+    views and debruijn.output_contigs use.  Tags carry the global read index and reads are
+    batch-major, so every per-batch list is a contiguous slice of the whole graph's list, already in
+    the reference's order."""
+
+    def __init__(self, parent, b):
+        self.parent, self.b = parent, int(b)
+        self.k, self.device = parent.k, parent.device
+        nd = parent.nodes()
+        lo, hi = np.searchsorted(nd['batch'], [self.b, self.b + 1])      # nodes are sorted by tag = batch-major
+        self._lo, self._hi = int(lo), int(hi)
+        self._nodes = None
+        self._labels = None
+
+    def nodes(self):
+        if self._nodes is None:
+            nd = self.parent.nodes()
+            self._nodes = {f: v[self._lo:self._hi] for f, v in nd.items()}
+        return self._nodes
+
+    def labels(self):
+        if self._labels is None:
+            nd = self.nodes()
+            self._labels = decode_keys(nd['key_lo'], nd['key_hi'], self.k)
+        return self._labels
+
+    def stats(self):
+        nd = self.nodes()
+        s = _BatchStats()
+        s.n_nodes = self._hi - self._lo
+        s.n_edges = int(np.count_nonzero(nd['cnt']))
+        s.n_branch = int(np.count_nonzero(nd['flags'] & N.NODE_BRANCH))
+        s.n_starts = int(np.count_nonzero(nd['flags'] & N.NODE_START))
+        s.n_pulled = int(np.count_nonzero(nd['flags'] & N.NODE_PULLED))
+        return s
+
+    def lookup_edges(self, kplus1mers):
+        return self.parent.lookup_edges(kplus1mers, batch=self.b)
+
+    def _split(self, name, ids_fn):
+        """Slice of a whole-graph id list (reference order = batch-major) that belongs to this batch;
+        the batch of every id is looked up once per graph and cached on the parent."""
+        p = self.parent
+        if p._batch_cache is None:
+            p._batch_cache = {}
+        if name not in p._batch_cache:
+            ids = np.ascontiguousarray(ids_fn(), np.uint32)
+            lo_k, hi_k = np.zeros(len(ids), np.uint64), np.zeros(len(ids), np.uint64)
+            if len(ids):
+                p.lib.check(p.h, p.lib.dbg_node_keys(p.h, ids.ctypes.data, len(ids), lo_k.ctypes.data, hi_k.ctypes.data))
+            p._batch_cache[name] = (ids, p.batch_of_keys(lo_k, hi_k))
+        ids, batch = p._batch_cache[name]
+        a, z = np.searchsorted(batch, [self.b, self.b + 1])
+        return ids, int(a), int(z)
+
+    def branch_ids(self):
+        ids, a, z = self._split('branch', self.parent.branch_ids)
+        return ids[a:z]
+
+    def pulled_ids(self):
+        ids, a, z = self._split('pulled', self.parent.pulled_ids)
+        return ids[a:z]
+
+    def label_of_ids(self, ids):
+        return self.parent.label_of_ids(ids)
+
+    def walk(self, stop_at_branch=True):
+        """The whole graph is walked once; `stop_at_branch` is what construct_graph's `final` implies
+        (a batch without branch nodes walks the same either way, debruijn.py:304)."""
+        p = self.parent
+        _, a, z = self._split('contigs', lambda: p.walk(stop_at_branch=not p.final)['start'])
+        self._contig_range = (a, z)                                    # contigs come in start order = batch-major
+        return p.contig_descriptors()[a:z]
+
+    def contig_strings(self):
+        a, z = self._contig_range
+        return self.parent.contig_strings(np.arange(a, z, dtype=np.uint64))
 
 
 # ---------------------------------------------------------------------------------------------

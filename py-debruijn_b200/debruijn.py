@@ -18,9 +18,9 @@ alphabet (ACGT) only, 1 <= k <= 63.
 """
 from __future__ import annotations
 
-from dbg_b200.graph import EdgeCountTable, Edges, Graph, KmerList, Node, Vertices  # noqa: F401
+from dbg_b200.graph import BatchGraph, EdgeCountTable, Edges, Graph, KmerList, Node, Vertices  # noqa: F401
 
-__all__ = ['Node', 'read_reads', 'construct_graph', 'output_contigs', 'get_score']
+__all__ = ['Node', 'read_reads', 'construct_graph', 'construct_graph_batch', 'output_contigs', 'get_score']
 
 
 def read_reads(fname):
@@ -50,11 +50,38 @@ def construct_graph(reads, k, threshold=3, final=False):
     return (Vertices(g), Edges(g)), pull_out_read, branch_kmer, already_pull_out, EdgeCountTable(g)
 
 
+def construct_graph_batch(batches, k, threshold=3, final=False):
+    """construct_graph for MANY independent read lists at once (BASELINE.json configs[3]: one small
+    assembly per template, V_FindTemplateGroups.py:152-190): `batches` is a list of read lists and
+    the result is a list with, per batch, exactly the tuple construct_graph(batch, k, threshold, final)
+    returns -- one pass over all reads on the GPU (dbg_build_batched: the batch id rides above the
+    k-mer in every node key).  Prints the reference's two lines per batch, in batch order."""
+    batch_bits = len(batches).bit_length()                              # ids 0 .. n-1 and the all-ones pattern stays free
+    g = Graph(k, key_words=2 if 2 * k + batch_bits > 64 else 0)          # 128-bit keys when 64 bits cannot hold both
+    g.build_batched(batches, threshold=threshold, final=final)
+    flags = g.pull_read_flags().tolist() if (not final and g.stats().n_pull_reads) else None
+    out = []
+    for b, reads in enumerate(batches):
+        bg = BatchGraph(g, b)
+        st = bg.stats()
+        print('number of {}mer: '.format(k), st.n_nodes)                  # debruijn.py:224
+        print('branch number: ', st.n_branch)                             # debruijn.py:236
+        if final:
+            pull_out_read, branch_kmer = [], KmerList((), bg)
+        else:
+            r0 = int(g.batch_off[b])
+            pull_out_read = [r for i, r in enumerate(reads) if flags[r0 + i]] if flags is not None else []
+            branch_kmer = KmerList(bg.label_of_ids(bg.branch_ids()), bg)
+        already_pull_out = KmerList(bg.label_of_ids(bg.pulled_ids()), bg)
+        out.append(((Vertices(bg), Edges(bg)), pull_out_read, branch_kmer, already_pull_out, EdgeCountTable(bg)))
+    return out
+
+
 def output_contigs(g, branch_kmer, already_pull_out):
     """debruijn.py:326-347 on the GPU.  `g` must be the pair construct_graph returned; the walk
     stops at branch nodes iff `branch_kmer` is non-empty (it is emptied by final=True)."""
     graph = getattr(g[0], '_graph', None)
-    if not isinstance(graph, Graph):
+    if not isinstance(graph, (Graph, BatchGraph)):
         raise TypeError('output_contigs needs the graph returned by this module\'s construct_graph')
     st = graph.stats()
     print('Number of kmers have no income edges: ', st.n_starts)           # debruijn.py:336

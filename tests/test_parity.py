@@ -207,3 +207,54 @@ def test_partition_passes(backend, monkeypatch, grid):
         g.build(reads, threshold=2)
         assert g.stats().n_insert_passes > 8
         g.close()
+
+
+def test_batched_equals_per_batch_oracle(backend):
+    """BASELINE.json configs[3] shape: many independent small read sets assembled in ONE pass
+    (dbg_build_batched) must give, per batch, exactly what construct_graph gives on that batch alone
+    -- including batches that share k-mers, empty batches and batches without any window."""
+    import contextlib
+    import io
+    import debruijn as db
+    r = random.Random(77)
+    for k, final in ((9, False), (25, False), (25, True), (31, False), (40, False)):
+        batches = []
+        shared = ''.join(r.choice('ACGT') for _ in range(120))          # the same stretch in several batches
+        for b in range(12):
+            G = r.choice([60, 150, 300])
+            genome = ''.join(r.choice('ACGT') for _ in range(G))
+            if b % 3 == 0:
+                genome = genome[:G // 2] + shared + genome[G // 2:]
+            L = r.choice([k + 3, 50, 70])
+            reads = []
+            for _ in range(r.choice([0, 3, 20, 40])):
+                p = r.randrange(0, max(1, len(genome) - L))
+                s = list(genome[p:p + L])
+                for j in range(len(s)):
+                    if r.random() < 0.03:
+                        s[j] = r.choice('ACGT')
+                reads.append(''.join(s))
+            if b == 5:
+                reads = ['ACG', '']                                    # nothing longer than k
+            batches.append(reads)
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf):
+            res = db.construct_graph_batch(batches, k, threshold=2, final=final)
+            got = []
+            for (g, pull, branch, pulled, ect) in res:
+                contigs = db.output_contigs(g, branch, pulled)
+                V, E = g
+                got.append({'nodes': [[v, n.indegree, n.outdegree] for v, n in V.items()],
+                            'edges': [[v, list(s)] for v, s in E.items()], 'pull_out_read': list(pull),
+                            'branch': list(branch), 'pulled': list(pulled), 'ect': [[e, c] for e, c in ect.items()],
+                            'contigs': list(contigs)})
+        for b, reads in enumerate(batches):
+            exp = dbg_oracle.snapshot(reads, k, 2, final, max_paths=2000)
+            util.assert_same(got[b], exp, 'batched k=%d final=%s batch %d' % (k, final, b))
+        # get_score through the batched device lookup (II_assembleFromReads.py:14-18)
+        g, pull, branch, pulled, ect = res[0]
+        for c in got[0]['contigs'][:5]:
+            assert db.get_score(ect, c, k) == sum(dict(map(tuple, got[0]['ect']))[c[i:i + k + 1]] for i in range(len(c) - k))
+    from dbg_b200 import Graph
+    with pytest.raises(ValueError):                                      # 5 batches need 3 bits, a 64-bit key leaves 2
+        Graph(31).build_batched([['ACGT' * 20]] * 5)
