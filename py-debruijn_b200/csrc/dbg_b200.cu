@@ -55,13 +55,19 @@ struct DevBuf {                 // grow-only device buffer: repeated builds on o
     size_t cap = 0;
 };
 
-enum { EV_MAX = 64 };
+enum { EV_MAX = 64, MAX_SLICES = 32 };
+#define SLICE_BYTES (16ull << 20)         // host reads are uploaded in slices of this size
 
 struct dbg_handle {
     int device = 0;
     int k = 0;
     int W = 1;
-    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
+    const uint8_t *host_bases = nullptr;      // dbg_build*: the reads still sit in host memory and are copied in
+                                              //   slices on copy_stream while k_pack / k_masks work on earlier ones
+    cudaEvent_t slice_ev[MAX_SLICES + 1];
+    int geom_logw = 0, geom_m = 1;
+    uint32_t sample_mask = 0;
     std::string err;
     bool built = false, walked = false;
     uint32_t build_flags = 0;
@@ -471,27 +477,14 @@ static int build_chunks(dbg_t *h, const u64 *d_off, int e0, int e1) {
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
 
-    // ---- phase 0: span masks + sketch of the chunk starts ----
-    // the sketch looks at 1 chunk start in 4, chosen by two bits of the minimizer's hash (distinct sampling:
-    // a function of the chunk's content); with short minimizers the hash has too few values for that
-    const u32 sample_mask = geom.m >= 8 ? (3u << 6) : 0u;
+    // ---- phase 0 (span masks + sketch of the chunk starts) ran with the packing, slice by slice ----
     const uint64_t n_spans = h->n_words;
-    TRY(reserve(h, h->b_stmask, (n_spans + 2) * 4));
-    TRY(reserve(h, h->b_vmask, (n_spans + 2) * 4));
-    TRY(reserve(h, h->b_spanread, (n_spans + 2) * 4));
-    TRY(reserve(h, h->b_hll, HLL_M * 4));
-    TRY(reserve(h, h->b_cc, sizeof(ChunkCounters)));
+    const u32 sample_mask = h->sample_mask;
     ChunkCounters *d_cc = ptr<ChunkCounters>(h->b_cc);
-    CK(cudaMemsetAsync(h->b_hll.p, 0, HLL_M * 4, h->stream));
-    CK(cudaMemsetAsync(d_cc, 0, sizeof(ChunkCounters), h->stream));
     ChunkCounters cc;
     memset(&cc, 0, sizeof cc);
     uint64_t est_chunks = 0;
     if (h->n_bases) {
-        LAUNCH(k_masks, blocks_for(n_spans), DBG_BLOCK, h->stream, ptr<const u64>(h->b_packed), d_off, h->n_reads,
-               ptr<const u32>(h->b_tile), h->n_bases, n_spans, k, geom.logw, geom.m, sample_mask, ptr<u32>(h->b_stmask),
-               ptr<u32>(h->b_vmask), ptr<u32>(h->b_spanread), ptr<u32>(h->b_hll));
-        CKK();
         std::vector<u32> regs(HLL_M);
         CK(cudaMemcpyAsync(regs.data(), h->b_hll.p, HLL_M * 4, cudaMemcpyDeviceToHost, h->stream));
         CK(cudaMemcpyAsync(&cc, d_cc, sizeof cc, cudaMemcpyDeviceToHost, h->stream));
@@ -650,16 +643,30 @@ static int build_impl(dbg_t *h, const u8 *d_bases, const u64 *d_off) {
     DevCounters *d_ctr = ptr<DevCounters>(h->b_ctr);
     const int e0 = ev_mark(h);
 
-    // ---- read packing (kernel 1) ----
+    const char *mode = getenv("DBG_B200_BUILD");                      // "windows" = the per-window table build
+    const bool chunks = !(mode && !strcmp(mode, "windows"));
+
+    // ---- read packing (kernel 1) + span masks (phase 0 of the chunk build), slice by slice ----
     h->n_words = cdiv(h->n_bases, 32);
     TRY(reserve(h, h->b_packed, (h->n_words + 4) * 8));
     CK(cudaMemsetAsync(ptr<u64>(h->b_packed) + h->n_words, 0, 4 * 8, h->stream));
     h->n_tiles = cdiv(h->n_bases, DBG_TILE);
     TRY(reserve(h, h->b_tile, (h->n_tiles + 2) * 4));
-    if (h->n_bases) {
-        LAUNCH(k_pack, blocks_for(h->n_words), DBG_BLOCK, h->stream, d_bases, h->n_bases, ptr<u64>(h->b_packed),
-               h->n_words, (int)(((uintptr_t)d_bases & 15) == 0), d_ctr);
-        CKK();
+    const uint64_t n_spans = h->n_words;
+    if (chunks) {
+        const ChunkGeom geom = chunk_geom(k);
+        h->geom_logw = geom.logw;
+        h->geom_m = geom.m;
+        // the sketch looks at 1 chunk start in 4, chosen by two bits of the minimizer's hash (distinct sampling:
+        // a function of the chunk's content); with short minimizers the hash has too few values for that
+        h->sample_mask = geom.m >= 8 ? (3u << 6) : 0u;
+        TRY(reserve(h, h->b_stmask, (n_spans + 2) * 4));
+        TRY(reserve(h, h->b_vmask, (n_spans + 2) * 4));
+        TRY(reserve(h, h->b_spanread, (n_spans + 2) * 4));
+        TRY(reserve(h, h->b_hll, HLL_M * 4));
+        TRY(reserve(h, h->b_cc, sizeof(ChunkCounters)));
+        CK(cudaMemsetAsync(h->b_hll.p, 0, HLL_M * 4, h->stream));
+        CK(cudaMemsetAsync(h->b_cc.p, 0, sizeof(ChunkCounters), h->stream));
     }
     if (h->n_reads) {
         LAUNCH(k_read_stats, blocks_for(h->n_reads), DBG_BLOCK, h->stream, d_off, h->n_reads, k, d_ctr);
@@ -669,11 +676,59 @@ static int build_impl(dbg_t *h, const u8 *d_bases, const u64 *d_off) {
         LAUNCH(k_tile_first, blocks_for(h->n_tiles + 1), DBG_BLOCK, h->stream, d_off, h->n_reads, h->n_bases,
                h->n_tiles, ptr<u32>(h->b_tile));
         CKK();
+        // Reads that still sit in host memory (dbg_build*) come over in slices on the copy stream; slice i
+        // is packed, and the spans whose 2-word lookahead it completes are masked, while slice i + 1 is
+        // on the wire.  Reads already in HBM are one slice.
+        uint64_t slice_bytes = SLICE_BYTES;
+        if (const char *e = getenv("DBG_B200_SLICE_BYTES")) {             // tests: many small slices
+            const unsigned long long v = strtoull(e, nullptr, 10);
+            if (v >= 1) slice_bytes = v;
+        }
+        uint64_t n_slices = h->host_bases ? cdiv(h->n_bases, slice_bytes) : 1;
+        if (n_slices > MAX_SLICES) n_slices = MAX_SLICES;
+        const uint64_t slice = cdiv(cdiv(h->n_bases, n_slices), DBG_TILE) * DBG_TILE;    // whole tiles
+        if (h->host_bases) {
+            CK(cudaEventRecord(h->slice_ev[MAX_SLICES], h->stream));                 // the buffers are ours from here on
+            CK(cudaStreamWaitEvent(h->copy_stream, h->slice_ev[MAX_SLICES], 0));
+            for (uint64_t i = 0; i < n_slices; i++) {
+                const uint64_t b0 = i * slice, b1 = b0 + slice < h->n_bases ? b0 + slice : h->n_bases;
+                if (b0 >= b1) { n_slices = i; break; }
+                CK(cudaMemcpyAsync((u8 *)d_bases + b0, h->host_bases + b0, b1 - b0, cudaMemcpyHostToDevice, h->copy_stream));
+                CK(cudaEventRecord(h->slice_ev[i], h->copy_stream));
+            }
+        }
+        uint64_t s_done = 0;
+        for (uint64_t i = 0; i < n_slices; i++) {
+            const uint64_t b0 = i * slice, b1 = b0 + slice < h->n_bases ? b0 + slice : h->n_bases;
+            if (b0 >= b1) break;
+            const bool last = b1 == h->n_bases;
+            if (h->host_bases) CK(cudaStreamWaitEvent(h->stream, h->slice_ev[i], 0));
+            const uint64_t w0 = b0 / 32, w1 = last ? h->n_words : b1 / 32;
+            LAUNCH(k_pack, blocks_for(w1 - w0), DBG_BLOCK, h->stream, d_bases, h->n_bases, ptr<u64>(h->b_packed),
+                   w0, w1, (int)(((uintptr_t)d_bases & 15) == 0), d_ctr);
+            CKK();
+            if (chunks) {
+                const uint64_t s1 = last ? n_spans : (w1 > 2 ? w1 - 2 : 0);           // k_masks reads words s - 1 .. s + 1
+                if (s1 > s_done) {
+                    LAUNCH(k_masks, blocks_for(s1 - s_done), DBG_BLOCK, h->stream, ptr<const u64>(h->b_packed), d_off,
+                           h->n_reads, ptr<const u32>(h->b_tile), h->n_bases, s_done, s1, k, h->geom_logw, h->geom_m,
+                           h->sample_mask, ptr<u32>(h->b_stmask), ptr<u32>(h->b_vmask), ptr<u32>(h->b_spanread),
+                           ptr<u32>(h->b_hll));
+                    CKK();
+                    s_done = s1;
+                }
+            }
+        }
+        if (h->host_bases) {                                                          // H2D time: first to last slice
+            CK(cudaStreamSynchronize(h->copy_stream));
+            float ms = 0;
+            cudaEventElapsedTime(&ms, h->slice_ev[MAX_SLICES], h->slice_ev[n_slices ? n_slices - 1 : 0]);
+            st.ms_h2d = ms;
+        }
     }
     const int e1 = ev_mark(h);
 
-    const char *mode = getenv("DBG_B200_BUILD");                      // "windows" = the per-window table build
-    if (mode && !strcmp(mode, "windows")) {
+    if (!chunks) {
         if (h->d_read_batch) return fail(h, DBG_ERR_ARG, "the per-window build (DBG_B200_BUILD=windows) has no batched mode");
         return build_windows<W>(h, d_off, e0, e1);
     }
@@ -1131,6 +1186,8 @@ DBG_API int dbg_create_ex(dbg_t **out, int device, int k, int key_words) {
     if (e != cudaSuccess) { delete h; return fail(nullptr, DBG_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
     h->stream = h->own_stream;
     for (int i = 0; i < EV_MAX; i++) cudaEventCreate(&h->ev[i]);
+    for (int i = 0; i <= MAX_SLICES; i++) cudaEventCreate(&h->slice_ev[i]);
+    cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
     if (reserve(h, h->b_ctr, sizeof(DevCounters)) != DBG_OK) {
         g_create_error = h->err;
         dbg_destroy(h);
@@ -1151,6 +1208,8 @@ DBG_API void dbg_destroy(dbg_t *h) {
                      &h->b_scratch[1], &h->b_scratch[2], &h->b_scratch[3], &h->b_scratch[4], &h->b_scratch[5]};
     for (DevBuf *b : all) if (b->p) cudaFree(b->p);
     for (int i = 0; i < EV_MAX; i++) cudaEventDestroy(h->ev[i]);
+    for (int i = 0; i <= MAX_SLICES; i++) cudaEventDestroy(h->slice_ev[i]);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
 #ifdef DBG_EMU
     if (h->pin) free(h->pin);
 #else
@@ -1221,15 +1280,13 @@ DBG_API int dbg_build_device(dbg_t *h, const uint8_t *d_bases, const uint64_t *d
     return build_device_common(h, d_bases, d_read_off, n_reads, n_bases, read_idx_base, threshold, flags, nullptr, 0);
 }
 
-static int upload_reads(dbg_t *h, const uint8_t *bases, const uint64_t *read_off, uint64_t n_reads, uint64_t n_bases) {
+// host entry points: the offsets go over first (everything that needs only them starts at once); the
+// bases follow in slices inside build_impl, overlapped with k_pack / k_masks
+static int stage_host_reads(dbg_t *h, const uint8_t *bases, const uint64_t *read_off, uint64_t n_reads, uint64_t n_bases) {
     TRY(reserve(h, h->b_bases, n_bases + 32));
     TRY(reserve(h, h->b_off, (n_reads + 1) * 8));
-    const int a = ev_mark(h);
-    if (n_bases) CK(cudaMemcpyAsync(h->b_bases.p, bases, n_bases, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->b_off.p, read_off, (n_reads + 1) * 8, cudaMemcpyHostToDevice, h->stream));
-    const int b = ev_mark(h);
-    CK(cudaStreamSynchronize(h->stream));
-    h->pending_h2d = ev_ms(h, a, b);
+    h->host_bases = n_bases ? bases : nullptr;
     return DBG_OK;
 }
 
@@ -1246,11 +1303,13 @@ DBG_API int dbg_build_batched(dbg_t *h, const uint8_t *bases, const uint64_t *re
                         (unsigned long long)r);
     CK(cudaSetDevice(h->device));
     h->n_ev = 0;
-    TRY(upload_reads(h, bases, read_off, n_reads, n_bases));
+    TRY(stage_host_reads(h, bases, read_off, n_reads, n_bases));
     TRY(reserve(h, h->b_readbatch, (n_reads + 1) * 4));
     if (n_reads) CK(cudaMemcpyAsync(h->b_readbatch.p, read_batch, n_reads * 4, cudaMemcpyHostToDevice, h->stream));
-    return build_device_common(h, ptr<const uint8_t>(h->b_bases), ptr<const uint64_t>(h->b_off), n_reads, n_bases, 0,
-                               threshold, flags, ptr<const uint32_t>(h->b_readbatch), n_batches);
+    const int rc = build_device_common(h, ptr<const uint8_t>(h->b_bases), ptr<const uint64_t>(h->b_off), n_reads, n_bases,
+                                       0, threshold, flags, ptr<const uint32_t>(h->b_readbatch), n_batches);
+    h->host_bases = nullptr;
+    return rc;
 }
 
 DBG_API int dbg_build_batched_device(dbg_t *h, const uint8_t *d_bases, const uint64_t *d_read_off, uint64_t n_reads,
@@ -1271,9 +1330,11 @@ DBG_API int dbg_build(dbg_t *h, const uint8_t *bases, const uint64_t *read_off, 
     if (n_bases && !bases) return fail(h, DBG_ERR_ARG, "dbg_build: bases is NULL");
     CK(cudaSetDevice(h->device));
     h->n_ev = 0;
-    TRY(upload_reads(h, bases, read_off, n_reads, n_bases));
-    return dbg_build_device(h, ptr<const uint8_t>(h->b_bases), ptr<const uint64_t>(h->b_off), n_reads, n_bases,
-                            read_idx_base, threshold, flags);
+    TRY(stage_host_reads(h, bases, read_off, n_reads, n_bases));
+    const int rc = build_device_common(h, ptr<const uint8_t>(h->b_bases), ptr<const uint64_t>(h->b_off), n_reads, n_bases,
+                                       read_idx_base, threshold, flags, nullptr, 0);
+    h->host_bases = nullptr;
+    return rc;
 }
 
 #define NEED_TABLE() do { if (!h) return DBG_ERR_ARG; if (!h->table_ready) return fail(h, DBG_ERR_STATE, "%s needs a node table (dbg_build* or dbg_table_reset first)", __func__); } while (0)

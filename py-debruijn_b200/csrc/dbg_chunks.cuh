@@ -140,10 +140,10 @@ DBG_D u32 bit_range(u32 lo, u32 hi) { return (~0u >> (31 - hi)) & (~0u << lo); }
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(DBG_BLOCK) k_masks(const u64 *__restrict__ packed, const u64 *__restrict__ off,
                                                      u64 n_reads, const u32 *__restrict__ tile_first, u64 n_bases,
-                                                     u64 n_spans, int k, int logw, int m, u32 sample_mask,
+                                                     u64 s_begin, u64 n_spans, int k, int logw, int m, u32 sample_mask,
                                                      u32 *__restrict__ st_mask,
                                                      u32 *__restrict__ v_mask, u32 *__restrict__ span_read, u32 *regs) {
-    const u64 s = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const u64 s = s_begin + (u64)blockIdx.x * blockDim.x + threadIdx.x;   // spans [s_begin, n_spans)
     if (s >= n_spans) return;
     const u64 p0 = s * 32;
     u32 V = 0, S = 0, r0 = 0;

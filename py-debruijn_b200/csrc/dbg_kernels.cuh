@@ -66,10 +66,10 @@ DBG_D u32 pack16(uint4 v, bool &bad) {
 }
 
 __global__ void __launch_bounds__(DBG_BLOCK) k_pack(const u8 *__restrict__ bases, u64 n_bases,
-                                                    u64 *__restrict__ packed, u64 n_words,
+                                                    u64 *__restrict__ packed, u64 w_begin, u64 w_end,
                                                     int aligned16, DevCounters *ctr) {
-    u64 w = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= n_words) return;
+    u64 w = w_begin + (u64)blockIdx.x * blockDim.x + threadIdx.x;   // words [w_begin, w_end): one slice of the stream
+    if (w >= w_end) return;
     u64 b0 = w * 32;
     u64 word = 0;
     bool bad = false;

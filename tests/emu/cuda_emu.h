@@ -281,6 +281,8 @@ static inline cudaError_t cudaStreamCreate(cudaStream_t *s) { *s = 0; return cud
 static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) { *s = 0; return cudaSuccess; }
 static inline cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+struct emu_event;
+static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, emu_event *, unsigned = 0) { return cudaSuccess; }
 #define cudaStreamNonBlocking 1
 static inline double emu_now() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
 static inline cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = new emu_event{0}; return cudaSuccess; }

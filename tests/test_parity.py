@@ -196,6 +196,7 @@ def test_partition_passes(backend, monkeypatch, grid):
     and few blocks so that every warp carries its queues across many tiles."""
     from dbg_b200 import Graph
     monkeypatch.setenv('DBG_B200_L2_REGION_BYTES', '65536')
+    monkeypatch.setenv('DBG_B200_SLICE_BYTES', '8192')        # the host reads arrive in many slices
     if grid:
         monkeypatch.setenv('DBG_B200_INSERT_GRID', grid)
     _, reads = util.synth_reads(21, 12000, 70, 12, err=0.01)
