@@ -525,7 +525,7 @@ static int build_chunks(dbg_t *h, const u64 *d_off, int e0, int e1) {
         const int b = ev_mark(h);
         if (st.n_windows) {
             const uint64_t n_units = cdiv(h->n_bases, DBG_UNIT);
-            uint64_t grid = (uint64_t)sms * 16;
+            uint64_t grid = (uint64_t)sms * DBG_CHUNK_MIN_BLOCKS;   // persistent: measured 0.39 ms vs 0.43 (x16) / 0.47 (x32)
             if (const char *e = getenv("DBG_B200_INSERT_GRID")) {        // tuning / tests
                 const unsigned long long v = strtoull(e, nullptr, 10);
                 if (v >= 1) grid = v;
@@ -561,7 +561,12 @@ static int build_chunks(dbg_t *h, const u64 *d_off, int e0, int e1) {
     uint64_t est = 0;
     std::vector<u32> sketch(HLL_M, 0);
     uint64_t ex_grid = cdiv(cdiv(n_cslots + n_list, 32), DBG_WARPS);
-    if (ex_grid > (uint64_t)sms * 8) ex_grid = (uint64_t)sms * 8;
+    uint64_t ex_per_sm = DBG_EXPAND_MIN_BLOCKS;                       // persistent: one resident wave (0.48 vs 0.51 ms at x8)
+    if (const char *e = getenv("DBG_B200_EXPAND_GRID")) {             // tuning: blocks per SM
+        const unsigned long long v = strtoull(e, nullptr, 10);
+        if (v >= 1) ex_per_sm = v;
+    }
+    if (ex_grid > (uint64_t)sms * ex_per_sm) ex_grid = (uint64_t)sms * ex_per_sm;
     if (ex_grid < 1) ex_grid = 1;
     if (st.n_windows) {
         CK(cudaMemsetAsync(h->b_hll.p, 0, HLL_M * 4, h->stream));
@@ -583,7 +588,12 @@ static int build_chunks(dbg_t *h, const u64 *d_off, int e0, int e1) {
     const uint64_t max_nodes = st.n_windows + h->n_reads;             // every window + last k-mer per read
     uint64_t want = (uint64_t)((double)est * 1.06) + 64;              // HLL std error at 2^12 registers: 1.6 %
     if (want > max_nodes) want = max_nodes;
-    uint64_t n_slots = want * 2 + 1024;                               // load factor <= 0.5
+    double load = 0.5;                                                // load factor: measured 0.5 / 0.6 / 0.7 = 0.51 / 0.53 / 0.60 ms of passes
+    if (const char *e = getenv("DBG_B200_TABLE_LOAD")) {              // tuning: percent
+        const double v = atof(e) / 100.0;
+        if (v >= 0.05 && v <= 0.95) load = v;
+    }
+    uint64_t n_slots = (uint64_t)((double)want / load) + 1024;
     for (int attempt = 0;; attempt++) {
         if (n_slots >= 0xFFFFFFF0ull) return fail(h, DBG_ERR_OVERFLOW, "node table would exceed 2^32 slots");
         h->n_slots = n_slots;

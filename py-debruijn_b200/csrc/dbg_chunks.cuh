@@ -533,8 +533,11 @@ DBG_D u32 bytes_in_range(u32 x, u32 lo4, u32 hi4) {
     return (t * 0x10204080u) >> 28;
 }
 
+#ifndef DBG_EXPAND_MIN_BLOCKS
+#define DBG_EXPAND_MIN_BLOCKS 4
+#endif
 template <int W, int MODE>
-__global__ void __launch_bounds__(DBG_BLOCK, 4)
+__global__ void __launch_bounds__(DBG_BLOCK, DBG_EXPAND_MIN_BLOCKS)
 k_expand(const ChunkSlot<W> *__restrict__ recs_a, u64 n_a, const ChunkSlot<W> *__restrict__ recs_b, u64 n_b, int k,
          uint4 *__restrict__ hbytes, Slot<W> *table, u32 n_slots, u32 lo8, u32 span8, u32 *regs, int batch_bits,
          DevCounters *ctr) {
