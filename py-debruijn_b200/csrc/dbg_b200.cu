@@ -55,7 +55,7 @@ struct DevBuf {                 // grow-only device buffer: repeated builds on o
     size_t cap = 0;
 };
 
-enum { EV_MAX = 64, MAX_SLICES = 32 };
+enum { EV_MAX = 64, EV_WALK = 48, MAX_SLICES = 32 };
 #define SLICE_BYTES (16ull << 20)         // host reads are uploaded in slices of this size
 
 struct dbg_handle {
@@ -97,7 +97,12 @@ struct dbg_handle {
     size_t pin_cap = 0;
     std::vector<dbg_segment_t> segments;
     cudaEvent_t ev[EV_MAX];
-    int n_ev = 0;
+    int n_ev = 0;                             // build stages use events [0, EV_WALK), dbg_walk [EV_WALK, EV_MAX)
+    int n_ev_walk = EV_WALK;
+    struct TimeRec { float *dst; int a, b; bool add; };
+    std::vector<TimeRec> tm;                  // stage times still to be read from their events (after a sync)
+    bool expand_pending = false;              // the node table was built without looking at its overflow flag yet
+    uint64_t n_cslots = 0, n_clist = 0, ex_grid = 1;
 };
 
 static std::string g_create_error;
@@ -166,6 +171,22 @@ static float ev_ms(dbg_t *h, int a, int b) {
     float ms = 0;
     cudaEventElapsedTime(&ms, h->ev[a], h->ev[b]);
     return ms;
+}
+static int ev_mark_walk(dbg_t *h) {
+    int i = h->n_ev_walk++;
+    cudaEventRecord(h->ev[i], h->stream);
+    return i;
+}
+// Stage times are read from their events later, when the stream is idle anyway (dbg_stats, or the next
+// sync the data path needs): a stage never waits for the GPU just to time itself.
+static void tm_set(dbg_t *h, float *dst, int a, int b) { h->tm.push_back(dbg_handle::TimeRec{dst, a, b, false}); }
+static void tm_add(dbg_t *h, float *dst, int a, int b) { h->tm.push_back(dbg_handle::TimeRec{dst, a, b, true}); }
+static void tm_flush(dbg_t *h) {                      // the stream must be idle
+    for (const dbg_handle::TimeRec &r : h->tm) {
+        const float ms = ev_ms(h, r.a, r.b);
+        if (r.add) *r.dst += ms; else *r.dst = ms;
+    }
+    h->tm.clear();
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -466,6 +487,63 @@ static uint32_t pass_count(dbg_t *h, uint64_t table_bytes) {
     return (uint32_t)n;
 }
 
+// node table from the distinct chunks (phase 2b): init + the k_expand passes at h->n_slots; no host sync.
+template <int W>
+static int expand_node_table(dbg_t *h) {
+    typedef Slot<W> S;
+    typedef ChunkSlot<W> CS;
+    dbg_stats_t &st = h->st;
+    DevCounters *d_ctr = ptr<DevCounters>(h->b_ctr);
+    const uint64_t n_slots = h->n_slots;
+    if (n_slots >= 0xFFFFFFF0ull) return fail(h, DBG_ERR_OVERFLOW, "node table would exceed 2^32 slots");
+    TRY(reserve(h, h->b_table, n_slots * sizeof(S)));
+    const int a = ev_mark(h);
+    LAUNCH(k_table_init<W>, blocks_for(n_slots), DBG_BLOCK, h->stream, ptr<S>(h->b_table), n_slots);
+    CKK();
+    const int b = ev_mark(h);
+    if (st.n_windows) {
+        uint32_t n_parts = pass_count(h, n_slots * sizeof(S));
+        if (n_parts > 255) n_parts = 255;
+        st.n_insert_passes = n_parts;
+        for (uint32_t part = 0; part < n_parts; part++) {
+            // hash bytes 0..254 (255 = no node) split evenly over the passes
+            const uint32_t lo8 = part * 255u / n_parts;
+            const uint32_t hi8 = (part + 1) * 255u / n_parts - 1;
+            LAUNCH((k_expand<W, 1>), h->ex_grid, DBG_BLOCK, h->stream, ptr<const CS>(h->b_ctable), h->n_cslots,
+                   ptr<const CS>(h->b_clist), h->n_clist, h->k, ptr<uint4>(h->b_h8), ptr<S>(h->b_table), (u32)n_slots,
+                   lo8, hi8 - lo8, (u32 *)nullptr, h->batch_bits, d_ctr);
+            CKK();
+        }
+    }
+    const int c = ev_mark(h);
+    tm_add(h, &st.ms_table_init, a, b);
+    tm_add(h, &st.ms_insert, b, c);
+    tm_add(h, &st.ms_expand, b, c);
+    st.table_slots = n_slots;
+    st.table_bytes = n_slots * sizeof(S);
+    return DBG_OK;
+}
+
+// look at the overflow flag of the last expand_node_table (counters fetched = stream idle); rebuild larger
+// until it fits.  `fetched` = h->ctr is already current.
+template <int W>
+static int settle_node_table(dbg_t *h, bool fetched) {
+    DevCounters *d_ctr = ptr<DevCounters>(h->b_ctr);
+    for (int attempt = 0;; attempt++) {
+        if (!fetched) TRY(fetch_counters(h));
+        fetched = false;
+        tm_flush(h);
+        if (!h->ctr.overflow) break;
+        if (attempt >= 6) return fail(h, DBG_ERR_NOMEM, "node table overflowed repeatedly");
+        h->n_slots *= 2;                                               // estimate was low: rebuild larger
+        CK(cudaMemsetAsync(&d_ctr->overflow, 0, 4, h->stream));
+        h->n_ev -= 3;
+        TRY(expand_node_table<W>(h));
+    }
+    h->expand_pending = false;
+    return DBG_OK;
+}
+
 template <int W>
 static int build_chunks(dbg_t *h, const u64 *d_off, int e0, int e1) {
     typedef Slot<W> S;
@@ -515,10 +593,14 @@ static int build_chunks(dbg_t *h, const u64 *d_off, int e0, int e1) {
         if (v >= 1) n_cslots = v;
     }
     float ms_init = 0, ms_insert = 0;
-    uint64_t n_list = 0;
+    const uint64_t n_list = list_cap;
+    uint64_t est = 0;
+    std::vector<u32> sketch(HLL_M, 0);
+    uint64_t ex_grid = 1;
     for (int attempt = 0;; attempt++) {
         if (n_cslots >= 0xFFFFFFF0ull) return fail(h, DBG_ERR_OVERFLOW, "chunk table would exceed 2^32 slots");
         TRY(reserve(h, h->b_ctable, n_cslots * sizeof(CS)));
+        TRY(reserve(h, h->b_h8, (n_cslots + n_list + 32) * 16));      // one hash byte per (record, node)
         const int a = ev_mark(h);
         LAUNCH(k_chunk_table_init<W>, blocks_for(n_cslots), DBG_BLOCK, h->stream, ptr<CS>(h->b_ctable), n_cslots);
         CKK();
@@ -541,48 +623,47 @@ static int build_chunks(dbg_t *h, const u64 *d_off, int e0, int e1) {
         }
         const int c = ev_mark(h);
         CK(cudaMemcpyAsync(&cc, d_cc, sizeof cc, cudaMemcpyDeviceToHost, h->stream));
+        // ---- phase 2a right behind it (no host round trip in between): sketch of the node keys of the
+        // distinct chunks -> node table size; wasted only when the chunk table turns out to have overflowed
+        ex_grid = cdiv(cdiv(n_cslots + n_list, 32), DBG_WARPS);
+        uint64_t ex_per_sm = DBG_EXPAND_MIN_BLOCKS;                   // persistent: one resident wave (0.48 vs 0.51 ms at x8)
+        if (const char *e = getenv("DBG_B200_EXPAND_GRID")) {         // tuning: blocks per SM
+            const unsigned long long v = strtoull(e, nullptr, 10);
+            if (v >= 1) ex_per_sm = v;
+        }
+        if (ex_grid > (uint64_t)sms * ex_per_sm) ex_grid = (uint64_t)sms * ex_per_sm;
+        if (ex_grid < 1) ex_grid = 1;
+        if (st.n_windows) {
+            CK(cudaMemsetAsync(h->b_hll.p, 0, HLL_M * 4, h->stream));
+            LAUNCH((k_expand<W, 0>), ex_grid, DBG_BLOCK, h->stream, ptr<const CS>(h->b_ctable), n_cslots,
+                   ptr<const CS>(h->b_clist), n_list, k, ptr<uint4>(h->b_h8), (S *)nullptr, 0u, 0u, 0u,
+                   ptr<u32>(h->b_hll), h->batch_bits, d_ctr);
+            CKK();
+            CK(cudaMemcpyAsync(sketch.data(), h->b_hll.p, HLL_M * 4, cudaMemcpyDeviceToHost, h->stream));
+        }
+        const int d = ev_mark(h);
         CK(cudaStreamSynchronize(h->stream));
         ms_init += ev_ms(h, a, b);
-        ms_insert += ev_ms(h, b, c);
+        ms_insert += ev_ms(h, b, d);
+        st.ms_chunk_insert += ev_ms(h, b, c);
+        st.ms_expand_sketch += ev_ms(h, c, d);
         if (cc.bad_chunk) return fail(h, DBG_ERR_STATE, "internal consistency fault: a chunk without an end");
         if (cc.list_overflow) return fail(h, DBG_ERR_STATE, "internal consistency fault: boundary list overflow");
-        n_list = list_cap;
         if (!cc.chunk_overflow) break;
         if (attempt >= 8) return fail(h, DBG_ERR_NOMEM, "chunk table overflowed repeatedly");
         n_cslots = n_cslots * 2 + 4096;                                // sketch was low: rebuild larger
         CK(cudaMemsetAsync(&d_cc->n_instances, 0, sizeof(ChunkCounters) - offsetof(ChunkCounters, n_instances),
                            h->stream));
-        h->n_ev -= 3;
+        h->n_ev -= 4;
     }
-    const int e3 = ev_mark(h);
-    st.ms_chunk_insert = ms_insert;
-
-    // ---- phase 2a: sketch of the node keys of the distinct chunks -> node table size ----
-    uint64_t est = 0;
-    std::vector<u32> sketch(HLL_M, 0);
-    uint64_t ex_grid = cdiv(cdiv(n_cslots + n_list, 32), DBG_WARPS);
-    uint64_t ex_per_sm = DBG_EXPAND_MIN_BLOCKS;                       // persistent: one resident wave (0.48 vs 0.51 ms at x8)
-    if (const char *e = getenv("DBG_B200_EXPAND_GRID")) {             // tuning: blocks per SM
-        const unsigned long long v = strtoull(e, nullptr, 10);
-        if (v >= 1) ex_per_sm = v;
-    }
-    if (ex_grid > (uint64_t)sms * ex_per_sm) ex_grid = (uint64_t)sms * ex_per_sm;
-    if (ex_grid < 1) ex_grid = 1;
-    if (st.n_windows) {
-        CK(cudaMemsetAsync(h->b_hll.p, 0, HLL_M * 4, h->stream));
-        TRY(reserve(h, h->b_h8, (n_cslots + n_list + 32) * 16));      // one hash byte per (record, node)
-        LAUNCH((k_expand<W, 0>), ex_grid, DBG_BLOCK, h->stream, ptr<const CS>(h->b_ctable), n_cslots,
-               ptr<const CS>(h->b_clist), n_list, k, ptr<uint4>(h->b_h8), (S *)nullptr, 0u, 0u, 0u,
-               ptr<u32>(h->b_hll), h->batch_bits, d_ctr);
-        CKK();
-        CK(cudaMemcpyAsync(sketch.data(), h->b_hll.p, HLL_M * 4, cudaMemcpyDeviceToHost, h->stream));
-    }
-    const int e4 = ev_mark(h);
-    CK(cudaStreamSynchronize(h->stream));
     if (st.n_windows) est = (uint64_t)hll_estimate(sketch);
     st.hll_estimate = est;
-    ms_insert += ev_ms(h, e3, e4);
-    st.ms_expand_sketch = ev_ms(h, e3, e4);
+    h->n_cslots = n_cslots;
+    h->n_clist = n_list;
+    h->ex_grid = ex_grid;
+    st.n_chunk_instances = cc.n_instances;
+    st.n_chunk_list = n_list;
+    st.chunk_slots = n_cslots;
 
     // ---- phase 2b: node table (kernel 3): every node of every distinct chunk, x multiplicity ----
     const uint64_t max_nodes = st.n_windows + h->n_reads;             // every window + last k-mer per read
@@ -593,54 +674,20 @@ static int build_chunks(dbg_t *h, const u64 *d_off, int e0, int e1) {
         const double v = atof(e) / 100.0;
         if (v >= 0.05 && v <= 0.95) load = v;
     }
-    uint64_t n_slots = (uint64_t)((double)want / load) + 1024;
-    for (int attempt = 0;; attempt++) {
-        if (n_slots >= 0xFFFFFFF0ull) return fail(h, DBG_ERR_OVERFLOW, "node table would exceed 2^32 slots");
-        h->n_slots = n_slots;
-        TRY(reserve(h, h->b_table, n_slots * sizeof(S)));
-        const int a = ev_mark(h);
-        LAUNCH(k_table_init<W>, blocks_for(n_slots), DBG_BLOCK, h->stream, ptr<S>(h->b_table), n_slots);
-        CKK();
-        const int b = ev_mark(h);
-        if (st.n_windows) {
-            uint32_t n_parts = pass_count(h, n_slots * sizeof(S));
-            if (n_parts > 255) n_parts = 255;
-            st.n_insert_passes = n_parts;
-            for (uint32_t part = 0; part < n_parts; part++) {
-                // hash bytes 0..254 (255 = no node) split evenly over the passes
-                const uint32_t lo8 = part * 255u / n_parts;
-                const uint32_t hi8 = (part + 1) * 255u / n_parts - 1;
-                LAUNCH((k_expand<W, 1>), ex_grid, DBG_BLOCK, h->stream, ptr<const CS>(h->b_ctable), n_cslots,
-                       ptr<const CS>(h->b_clist), n_list, k, ptr<uint4>(h->b_h8), ptr<S>(h->b_table), (u32)n_slots,
-                       lo8, hi8 - lo8, (u32 *)nullptr, h->batch_bits, d_ctr);
-                CKK();
-            }
-        }
-        const int c = ev_mark(h);
-        TRY(fetch_counters(h));
-        ms_init += ev_ms(h, a, b);
-        ms_insert += ev_ms(h, b, c);
-        if (!h->ctr.overflow) break;
-        if (attempt >= 6) return fail(h, DBG_ERR_NOMEM, "node table overflowed repeatedly");
-        n_slots *= 2;                                                  // estimate was low: rebuild larger
-        CK(cudaMemsetAsync(&d_ctr->overflow, 0, 4, h->stream));
-        h->n_ev -= 3;
+    h->n_slots = (uint64_t)((double)want / load) + 1024;
+    if (const char *e = getenv("DBG_B200_NODE_SLOTS")) {              // tests: force the overflow / rebuild path
+        const unsigned long long v = strtoull(e, nullptr, 10);
+        if (v >= 1) h->n_slots = v;
     }
-    st.ms_pack = ev_ms(h, e0, e1);
-    st.ms_estimate = ev_ms(h, e1, e2);
     st.ms_table_init = ms_init;
     st.ms_insert = ms_insert;
-    st.ms_expand = ms_insert - st.ms_chunk_insert - st.ms_expand_sketch;
-    st.table_slots = n_slots;
-    st.table_bytes = n_slots * sizeof(S);
-    st.n_chunk_instances = cc.n_instances;
-    st.n_chunk_list = n_list;
-    st.chunk_slots = n_cslots;
-    {
-        const int e_end = ev_mark(h);
-        CK(cudaStreamSynchronize(h->stream));
-        st.ms_build_total = ev_ms(h, e0, e_end);
-    }
+    tm_set(h, &st.ms_pack, e0, e1);
+    tm_set(h, &st.ms_estimate, e1, e2);
+    TRY(expand_node_table<W>(h));
+    if (h->build_flags & DBG_TABLE_ONLY) TRY(settle_node_table<W>(h, false));   // nobody downstream looks at the flag
+    else h->expand_pending = true;                                   // graph_finalize looks at it with its own counters
+    const int e_end = ev_mark(h);
+    tm_set(h, &st.ms_build_total, e0, e_end);
     h->table_ready = true;
     return DBG_OK;
 }
@@ -750,19 +797,28 @@ template <int W>
 static int graph_finalize(dbg_t *h) {
     typedef Slot<W> S;
     dbg_stats_t &st = h->st;
-    const uint64_t n_slots = h->n_slots;
     DevCounters *d_ctr = ptr<DevCounters>(h->b_ctr);
     const int e3 = ev_mark(h);
-    CK(cudaMemsetAsync(&d_ctr->n_nodes, 0, 5 * 8, h->stream));          // n_nodes .. n_starts
-    TRY(reserve(h, h->b_flags, n_slots));
-    TRY(reserve(h, h->b_kept, n_slots * 2));
-    TRY(reserve(h, h->b_succ, n_slots * 4));
-    uint64_t fin_grid = blocks_for(n_slots);
-    if (fin_grid > 148 * 16) fin_grid = 148 * 16;
-    LAUNCH(k_finalize<W>, fin_grid, DBG_BLOCK, h->stream, ptr<const S>(h->b_table), n_slots, h->k,
-           h->threshold, ptr<u8>(h->b_flags), ptr<u16>(h->b_kept), ptr<u32>(h->b_succ), d_ctr);
-    CKK();
-    TRY(fetch_counters(h));
+    for (;;) {
+        const uint64_t n_slots = h->n_slots;
+        CK(cudaMemsetAsync(&d_ctr->n_nodes, 0, 5 * 8, h->stream));      // n_nodes .. n_starts
+        TRY(reserve(h, h->b_flags, n_slots));
+        TRY(reserve(h, h->b_kept, n_slots * 2));
+        TRY(reserve(h, h->b_succ, n_slots * 4));
+        uint64_t fin_grid = blocks_for(n_slots);
+        if (fin_grid > 148 * 16) fin_grid = 148 * 16;
+        LAUNCH(k_finalize<W>, fin_grid, DBG_BLOCK, h->stream, ptr<const S>(h->b_table), n_slots, h->k,
+               h->threshold, ptr<u8>(h->b_flags), ptr<u16>(h->b_kept), ptr<u32>(h->b_succ), d_ctr);
+        CKK();
+        TRY(fetch_counters(h));
+        tm_flush(h);
+        if (!(h->expand_pending && h->ctr.overflow)) break;
+        // the node table the chunk build left had overflowed (its flag is looked at here, with this
+        // stage's own counters, to save a host round trip on the common path): rebuild it larger
+        CK(cudaMemsetAsync(&d_ctr->fault, 0, 8, h->stream));            // whatever k_finalize met in the torn table
+        TRY(settle_node_table<W>(h, true));
+    }
+    h->expand_pending = false;
     st.n_nodes = h->ctr.n_nodes;
     st.n_edges = h->ctr.n_edges;
     st.n_multi = h->ctr.n_multi;
@@ -774,9 +830,8 @@ static int graph_finalize(dbg_t *h) {
     if (st.n_multi && h->threshold == 0.0)
         return fail(h, DBG_ERR_ZERODIV, "threshold == 0 with a multi-successor node (debruijn.py:163)");
     const int e4 = ev_mark(h);
-    CK(cudaStreamSynchronize(h->stream));
-    st.ms_finalize = ev_ms(h, e3, e4);
-    st.ms_build_total += st.ms_finalize;
+    tm_set(h, &st.ms_finalize, e3, e4);
+    tm_add(h, &st.ms_build_total, e3, e4);
     h->order_active = false;
     return DBG_OK;
 }
@@ -797,9 +852,8 @@ static int graph_order_scan(dbg_t *h) {
         }
     }
     const int e5 = ev_mark(h);
-    CK(cudaStreamSynchronize(h->stream));
-    st.ms_order = ev_ms(h, e4, e5);
-    st.ms_build_total += st.ms_order;
+    tm_set(h, &st.ms_order, e4, e5);
+    tm_add(h, &st.ms_build_total, e4, e5);
     return DBG_OK;
 }
 
@@ -861,12 +915,11 @@ static int graph_complete(dbg_t *h) {
         h->read_flags_valid = true;
     }
     const int e8 = ev_mark(h);
-    CK(cudaStreamSynchronize(h->stream));
-    st.ms_order += ev_ms(h, e4, e5);
-    st.ms_lists = ev_ms(h, e5, e6);
-    st.ms_tips = ev_ms(h, e6, e7);
-    st.ms_pull_reads = ev_ms(h, e7, e8);
-    st.ms_build_total += ev_ms(h, e4, e8);
+    tm_add(h, &st.ms_order, e4, e5);
+    tm_set(h, &st.ms_lists, e5, e6);
+    tm_set(h, &st.ms_tips, e6, e7);
+    tm_set(h, &st.ms_pull_reads, e7, e8);
+    tm_add(h, &st.ms_build_total, e4, e8);
     h->built = true;
     return DBG_OK;
 }
@@ -972,7 +1025,8 @@ static int walk_impl(dbg_t *h, int stop_at_branch) {
     st.n_contigs = 0;
     st.n_cycle_starts = 0;
     st.jump_rounds = 0;
-    const int e0 = ev_mark(h);
+    h->n_ev_walk = EV_WALK;
+    const int e0 = ev_mark_walk(h);
 
     // ---- list ranking over the pruned successor array: chain nodes -> splitters -> super-splitters ----
     TRY(reserve(h, h->b_link, n_slots * 8));
@@ -992,15 +1046,20 @@ static int walk_impl(dbg_t *h, int stop_at_branch) {
     LAUNCH(k_suplist, blocks_for(super_cap), DBG_BLOCK, h->stream, ptr<u64>(h->b_link), ptr<const u32>(h->b_super),
            (const u64 *)&d_ctr->n_list_b, super_cap);
     CKK();
+    bool deferred_check = false;
     {
         int max_rounds = 2;
         for (uint64_t n = super_cap; n > 1; n >>= 1) max_rounds++;
-        if (super_cap <= WALK_BLOCK_JUMP_CAP) {                      // one block jumps the whole list in one launch
+        if (super_cap <= WALK_BLOCK_JUMP_CAP) {                      // the whole list in one launch
+#ifdef DBG_EMU
             LAUNCH(k_jump_block, 1, 1024, h->stream, ptr<u64>(h->b_link), ptr<const u32>(h->b_super),
                    (const u64 *)&d_ctr->n_list_b, super_cap, n_slots, max_rounds, d_ctr);
+#else
+            LAUNCH(k_jump_cluster, WALK_CLUSTER, 1024, h->stream, ptr<u64>(h->b_link), ptr<const u32>(h->b_super),
+                   (const u64 *)&d_ctr->n_list_b, super_cap, n_slots, d_ctr);
+#endif
             CKK();
-            TRY(check_fault(h, "k_jump_block"));
-            st.jump_rounds = h->ctr.changed;
+            deferred_check = true;                                   // looked at with k_emit's counters below
         } else {
             TRY(fetch_counters(h));
             const uint64_t n_super = h->ctr.n_list_b < super_cap ? h->ctr.n_list_b : super_cap;
@@ -1019,11 +1078,7 @@ static int walk_impl(dbg_t *h, int stop_at_branch) {
             TRY(check_fault(h, "k_jump"));
         }
     }
-    if (h->ctr.n_list_a > split_cap || h->ctr.n_list_b > super_cap)
-        return fail(h, DBG_ERR_STATE, "splitter list overflow (%llu > %llu or %llu > %llu)",
-                    (unsigned long long)h->ctr.n_list_a, (unsigned long long)split_cap,
-                    (unsigned long long)h->ctr.n_list_b, (unsigned long long)super_cap);
-    const int e1 = ev_mark(h);
+    const int e1 = ev_mark_walk(h);
 
     // ---- one record per start (debruijn.py:331-345), already in dbg_contig_t layout ----
     const uint64_t ns = st.n_starts;
@@ -1032,15 +1087,20 @@ static int walk_impl(dbg_t *h, int stop_at_branch) {
     if (ns) {
         TRY(reserve(h, h->b_contig, ns * sizeof(dbg_contig_t)));
         TRY(reserve_pinned(h, ns * sizeof(dbg_contig_t)));
-        CK(cudaMemsetAsync(&d_ctr->n_list_a, 0, 8, h->stream));
+        CK(cudaMemsetAsync(&d_ctr->n_dropped, 0, 8, h->stream));
         LAUNCH(k_emit, blocks_for(ns), DBG_BLOCK, h->stream, ptr<const u32>(h->b_starts), ns,
-               ptr<const u64>(h->b_link), ptr<const u8>(h->b_flags), ptr<ContigRec>(h->b_contig), &d_ctr->n_list_a);
+               ptr<const u64>(h->b_link), ptr<const u8>(h->b_flags), ptr<ContigRec>(h->b_contig), &d_ctr->n_dropped);
         CKK();
         CK(cudaMemcpyAsync(h->pin, h->b_contig.p, ns * sizeof(dbg_contig_t), cudaMemcpyDeviceToHost, h->stream));
-        TRY(fetch_counters(h));
         recs = (const dbg_contig_t *)h->pin;
-        n_dropped = h->ctr.n_list_a;                                   // starts on cycles or pulled themselves
     }
+    TRY(check_fault(h, "the list ranking kernels"));                    // ONE host round trip for the whole walk
+    if (deferred_check) st.jump_rounds = h->ctr.changed;
+    if (h->ctr.n_list_a > split_cap || h->ctr.n_list_b > super_cap)
+        return fail(h, DBG_ERR_STATE, "splitter list overflow (%llu > %llu or %llu > %llu)",
+                    (unsigned long long)h->ctr.n_list_a, (unsigned long long)split_cap,
+                    (unsigned long long)h->ctr.n_list_b, (unsigned long long)super_cap);
+    if (ns) n_dropped = h->ctr.n_dropped;                              // starts on cycles or pulled themselves
     const uint64_t nb = h->branch.size();
     const bool enumerate = !stop_at_branch && nb > 0;
     std::vector<JunctionSucc> junc;
@@ -1149,11 +1209,10 @@ static int walk_impl(dbg_t *h, int stop_at_branch) {
     if (fast) { h->cview = recs; h->n_cview = ns; }
     else { h->cview = h->contigs.data(); h->n_cview = h->contigs.size(); }
     st.n_contigs = h->n_cview;
-    const int e2 = ev_mark(h);
-    CK(cudaStreamSynchronize(h->stream));
-    st.ms_walk_rank = ev_ms(h, e0, e1);
-    st.ms_walk_emit = ev_ms(h, e1, e2);
-    st.ms_walk_total = ev_ms(h, e0, e2);
+    const int e2 = ev_mark_walk(h);
+    tm_set(h, &st.ms_walk_rank, e0, e1);
+    tm_set(h, &st.ms_walk_emit, e1, e2);
+    tm_set(h, &st.ms_walk_total, e0, e2);
     return DBG_OK;
 }
 
@@ -1259,6 +1318,8 @@ static int build_device_common(dbg_t *h, const uint8_t *d_bases, const uint64_t 
         return fail(h, DBG_ERR_OVERFLOW, "read index exceeds 32 bits");
     if (threshold != threshold) return fail(h, DBG_ERR_ARG, "threshold is NaN");
     CK(cudaSetDevice(h->device));
+    if (!h->tm.empty()) { CK(cudaStreamSynchronize(h->stream)); tm_flush(h); }   // a previous build's stage times
+    h->expand_pending = false;
     h->built = h->walked = false;
     h->n_ev = 0;
     h->n_reads = n_reads;
@@ -1312,7 +1373,6 @@ DBG_API int dbg_build_batched(dbg_t *h, const uint8_t *bases, const uint64_t *re
             return fail(h, DBG_ERR_ARG, "dbg_build_batched: read_batch must be non-decreasing and < n_batches (read %llu)",
                         (unsigned long long)r);
     CK(cudaSetDevice(h->device));
-    h->n_ev = 0;
     TRY(stage_host_reads(h, bases, read_off, n_reads, n_bases));
     TRY(reserve(h, h->b_readbatch, (n_reads + 1) * 4));
     if (n_reads) CK(cudaMemcpyAsync(h->b_readbatch.p, read_batch, n_reads * 4, cudaMemcpyHostToDevice, h->stream));
@@ -1339,7 +1399,6 @@ DBG_API int dbg_build(dbg_t *h, const uint8_t *bases, const uint64_t *read_off, 
     const uint64_t n_bases = read_off[n_reads];
     if (n_bases && !bases) return fail(h, DBG_ERR_ARG, "dbg_build: bases is NULL");
     CK(cudaSetDevice(h->device));
-    h->n_ev = 0;
     TRY(stage_host_reads(h, bases, read_off, n_reads, n_bases));
     const int rc = build_device_common(h, ptr<const uint8_t>(h->b_bases), ptr<const uint64_t>(h->b_off), n_reads, n_bases,
                                        read_idx_base, threshold, flags, nullptr, 0);
@@ -1352,6 +1411,7 @@ DBG_API int dbg_build(dbg_t *h, const uint8_t *bases, const uint64_t *read_off, 
 DBG_API int dbg_graph_stage(dbg_t *h, int stage, double threshold, uint32_t flags) {
     NEED_TABLE();
     CK(cudaSetDevice(h->device));
+    if (!h->tm.empty()) { CK(cudaStreamSynchronize(h->stream)); tm_flush(h); }   // the previous stage's times
     h->n_ev = 0;
     if (stage == 0) {
         if (threshold != threshold) return fail(h, DBG_ERR_ARG, "threshold is NaN");
@@ -1410,6 +1470,11 @@ DBG_API int dbg_order_merge(dbg_t *h, const uint64_t *d_records, uint64_t n) {
 
 DBG_API int dbg_stats(dbg_t *h, dbg_stats_t *out) {
     if (!h || !out) return DBG_ERR_ARG;
+    if (!h->tm.empty()) {                               // stage times still sitting in their events
+        CK(cudaSetDevice(h->device));
+        CK(cudaStreamSynchronize(h->stream));
+        tm_flush(h);
+    }
     *out = h->st;
     return DBG_OK;
 }
@@ -1546,7 +1611,6 @@ DBG_API int dbg_walk(dbg_t *h, int stop_at_branch, uint64_t *n_contigs) {
     NEED_BUILT();
     CK(cudaSetDevice(h->device));
     h->walked = false;
-    h->n_ev = 0;
     TRY(DISPATCH(walk_impl, h, stop_at_branch));
     h->walked = true;
     if (n_contigs) *n_contigs = h->n_cview;

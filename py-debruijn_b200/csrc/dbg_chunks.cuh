@@ -496,6 +496,9 @@ k_chunk_insert(const u64 *__restrict__ packed, u64 n_words_padded, const u64 *__
 //           so the table traffic runs with full warps although few nodes of a record are in range.
 // ---------------------------------------------------------------------------------------------
 #define EX_RCAP 128
+#ifndef EX_ILP
+#define EX_ILP 2                           // entries per lane per drain
+#endif
 template <int W> struct ExpandShared {
     typename KeyOf<W>::type rkey[DBG_WARPS][EX_RCAP];
     u64 rtag[DBG_WARPS][EX_RCAP];
@@ -550,54 +553,66 @@ k_expand(const ChunkSlot<W> *__restrict__ recs_a, u64 n_a, const ChunkSlot<W> *_
     u32 head = 0, nq = 0;
     bool overflow = false;
 
+    // up to 32 * EX_ILP entries per drain: every lane issues the slot loads of all its entries before it
+    // looks at the first one, so EX_ILP random accesses per lane are in flight
     auto drain = [&]() {
         __syncwarp();
-        const u32 take = nq < 32u ? nq : 32u;
-        const u32 e = (head + lane) & (EX_RCAP - 1);
-        const bool act = lane < take;
-        const K key = sh.rkey[w][e];
-        const u64 tag = sh.rtag[w][e];
-        const u32 cnt = sh.rcnt[w][e];
-        u32 meta = sh.rmeta[w][e];
+        const u32 cap = 32u * EX_ILP;
+        const u32 take = nq < cap ? nq : cap;
+        bool act[EX_ILP]; K key[EX_ILP]; u64 tag[EX_ILP]; u32 cnt[EX_ILP]; u32 meta[EX_ILP];
+#pragma unroll
+        for (int i = 0; i < EX_ILP; i++) {
+            const u32 e = (head + 32 * i + lane) & (EX_RCAP - 1);
+            act[i] = 32 * i + lane < take;
+            key[i] = sh.rkey[w][e]; tag[i] = sh.rtag[w][e]; cnt[i] = sh.rcnt[w][e]; meta[i] = sh.rmeta[w][e];
+        }
         __syncwarp();
         head = (head + take) & (EX_RCAP - 1);
         nq -= take;
-        bool again = false;
-        if (act) {
-            u64 idx = slot_home(hash32_key(key), n_slots) + (meta >> 3);
+        Slot<W> *s[EX_ILP]; K cur[EX_ILP]; u64 seen[EX_ILP];
+#pragma unroll
+        for (int i = 0; i < EX_ILP; i++) {
+            u64 idx = slot_home(hash32_key(key[i]), n_slots) + (meta[i] >> 3);
             if (idx >= n_slots) idx -= n_slots;
-            Slot<W> *s = &table[idx];
-            u64 seen;
-            K cur = load_key_tag(s, &seen);
-            bool hit = true;
-            if (cur != key) {
-                hit = false;
-                if (cur == empty_key<W>()) {
-                    const K old = cas_key(&s->key, empty_key<W>(), key);
-                    if (old == empty_key<W>()) { seen = ~0ULL; hit = true; }
-                    else if (old == key) { seen = __ldcg(&s->tag); hit = true; }
+            s[i] = &table[act[i] ? idx : 0];
+            cur[i] = load_key_tag(s[i], &seen[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < EX_ILP; i++) {
+            bool again = false;
+            if (act[i]) {
+                bool hit = true;
+                if (cur[i] != key[i]) {
+                    hit = false;
+                    if (cur[i] == empty_key<W>()) {
+                        const K old = cas_key(&s[i]->key, empty_key<W>(), key[i]);
+                        if (old == empty_key<W>()) { seen[i] = ~0ULL; hit = true; }
+                        else if (old == key[i]) { seen[i] = __ldcg(&s[i]->tag); hit = true; }
+                    }
+                }
+                if (hit) {
+                    if (tag[i] < seen[i]) atomicMin(&s[i]->tag, tag[i]);             // first occurrence
+                    if (meta[i] & 4u) atomicAdd(&s[i]->cnt[meta[i] & 3u], cnt[i]);   // debruijn.py:132/136, x multiplicity
+                } else {
+                    meta[i] += 8u;
+                    if ((meta[i] >> 3) >= CH_MAX_PROBES) { overflow = true; ctr->overflow = 1; } else again = true;
                 }
             }
-            if (hit) {
-                if (tag < seen) atomicMin(&s->tag, tag);                 // first occurrence
-                if (meta & 4u) atomicAdd(&s->cnt[meta & 3u], cnt);       // debruijn.py:132/136, x multiplicity
-            } else {
-                meta += 8u;
-                if ((meta >> 3) >= DBG_MAX_PROBES) overflow = true; else again = true;
+            const u32 mk = __ballot_sync(0xFFFFFFFFu, again);
+            if (again) {
+                const u32 o = (head + nq + __popc(mk & lt)) & (EX_RCAP - 1);
+                sh.rkey[w][o] = key[i]; sh.rtag[w][o] = tag[i]; sh.rcnt[w][o] = cnt[i]; sh.rmeta[w][o] = (u16)meta[i];
             }
+            nq += __popc(mk);
         }
-        const u32 mk = __ballot_sync(0xFFFFFFFFu, again);
-        if (again) {
-            const u32 o = (head + nq + __popc(mk & lt)) & (EX_RCAP - 1);
-            sh.rkey[w][o] = key; sh.rtag[w][o] = tag; sh.rcnt[w][o] = cnt; sh.rmeta[w][o] = (u16)meta;
-        }
-        nq += __popc(mk);
     };
 
     const u64 n_total = n_a + n_b;
     const u64 n_batches = (n_total + 31) / 32;
     const u64 warps_total = (u64)gridDim.x * DBG_WARPS;
     for (u64 b = (u64)blockIdx.x * DBG_WARPS + w; b < n_batches; b += warps_total) {
+        // the table is full: the host rebuilds it larger (looked at now and then; the flag is set at once)
+        if (MODE == 1 && ((b / warps_total) & 7) == 0 && __any_sync(0xFFFFFFFFu, __ldcg(&ctr->overflow) != 0u)) break;
         const u64 idx = b * 32 + lane;
         u32 n = 0, B = 0, cnt = 0, m16 = 0, batch = 0;
         u64 tag = 0;
@@ -667,7 +682,7 @@ k_expand(const ChunkSlot<W> *__restrict__ recs_a, u64 n_a, const ChunkSlot<W> *_
                     sh.rmeta[w][o] = (u16)((has_next ? 4u : 0u) | (has_next ? nb : 0u));
                 }
                 nq += __popc(mk);
-                while (nq >= 32u) drain();
+                while (nq >= 32u * EX_ILP) drain();
             }
         }
     }

@@ -259,3 +259,25 @@ def test_batched_equals_per_batch_oracle(backend):
     from dbg_b200 import Graph
     with pytest.raises(ValueError):                                      # 5 batches need 3 bits, a 64-bit key leaves 2
         Graph(31).build_batched([['ACGT' * 20]] * 5)
+
+
+@pytest.mark.parametrize('table_only', [False, True])
+def test_undersized_tables_are_rebuilt(backend, monkeypatch, table_only):
+    """Chunk table and node table both start far too small: the build notices (the node table's flag
+    is only looked at by the next stage's counters) and rebuilds them larger, results unchanged."""
+    from dbg_b200 import Graph
+    monkeypatch.setenv('DBG_B200_CHUNK_SLOTS', '512')
+    monkeypatch.setenv('DBG_B200_NODE_SLOTS', '4096')
+    _, reads = util.synth_reads(23, 4000, 70, 8, err=0.01)
+    for k in (21, 40):
+        if table_only:
+            g = Graph(k)
+            g.build_table(reads)
+            n = int(g.export_counts(1)[0])
+            exp = dbg_oracle.snapshot(reads, k, 2, False)
+            assert n == len(exp['nodes'])
+            g.close()
+        else:
+            exp = dbg_oracle.snapshot(reads, k, 2, False)
+            got = util.product_snapshot(reads, k, 2, False)
+            util.assert_same(got, exp, 'undersized tables k=%d' % k)
