@@ -84,7 +84,7 @@ struct dbg_handle {
     DevBuf b_bases, b_off, b_packed, b_tile, b_table, b_flags, b_kept, b_succ, b_link, b_ctr, b_hll,
            b_order, b_tag, b_tag2, b_slot, b_slot2, b_sorttmp, b_branch, b_starts, b_pulled, b_readflags,
            b_recs, b_cnt32, b_off64, b_contig, b_junction, b_split, b_h8, b_chunk, b_bitmap, b_stmask, b_vmask,
-           b_spanread, b_cc, b_ctable, b_clist, b_super, b_readbatch, b_scratch[6];
+           b_spanread, b_cc, b_ctable, b_clist, b_super, b_readbatch, b_ctable2, b_scratch[6];
     DevCounters ctr;
     dbg_stats_t st;
     std::vector<uint32_t> branch, pulled;     // reference order
@@ -102,6 +102,7 @@ struct dbg_handle {
     struct TimeRec { float *dst; int a, b; bool add; };
     std::vector<TimeRec> tm;                  // stage times still to be read from their events (after a sync)
     bool expand_pending = false;              // the node table was built without looking at its overflow flag yet
+    bool chunks_streamed = false;             // phase 1 already ran, slice by slice, while the reads were arriving
     uint64_t n_cslots = 0, n_clist = 0, ex_grid = 1;
 };
 
@@ -487,6 +488,61 @@ static uint32_t pass_count(dbg_t *h, uint64_t table_bytes) {
     return (uint32_t)n;
 }
 
+// phase 1 over the units [u0, u1) of the read stream
+template <int W>
+static int launch_chunk_insert(dbg_t *h, const u64 *d_off, uint64_t u0, uint64_t u1) {
+    typedef ChunkSlot<W> CS;
+    if (u1 <= u0) return DBG_OK;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+    const uint64_t n = u1 - u0;
+    uint64_t grid = (uint64_t)sms * DBG_CHUNK_MIN_BLOCKS;       // persistent: measured 0.39 ms vs 0.43 (x16) / 0.47 (x32)
+    if (const char *e = getenv("DBG_B200_INSERT_GRID")) {            // tuning / tests
+        const unsigned long long v = strtoull(e, nullptr, 10);
+        if (v >= 1) grid = v;
+    }
+    if (grid > cdiv(n, DBG_WARPS)) grid = cdiv(n, DBG_WARPS);
+    const uint64_t units_per_block = cdiv(n, grid);
+    grid = cdiv(n, units_per_block);
+    LAUNCH(k_chunk_insert<W>, grid, DBG_BLOCK, h->stream, ptr<const u64>(h->b_packed), h->n_words + 4, d_off,
+           h->n_reads, ptr<const u32>(h->b_stmask), ptr<const u32>(h->b_vmask), ptr<const u32>(h->b_spanread),
+           h->n_words, u0, u1, units_per_block, h->k, ptr<CS>(h->b_ctable), (u32)h->n_cslots, ptr<CS>(h->b_clist),
+           2 * h->n_reads + 2, h->read_idx_base, (const u32 *)h->d_read_batch, ptr<ChunkCounters>(h->b_cc));
+    CKK();
+    return DBG_OK;
+}
+
+// streamed host build: make sure the chunk table can take what the sketch has seen so far
+template <int W>
+static int chunk_table_fit(dbg_t *h, uint64_t est_chunks_so_far) {
+    typedef ChunkSlot<W> CS;
+    const uint64_t need = (uint64_t)((double)est_chunks_so_far * 1.7) + 4096;
+    if (h->n_cslots == 0) {                                          // first slice: leave room for what later slices add
+        uint64_t n = need + need / 3;
+        if (const char *e = getenv("DBG_B200_CHUNK_SLOTS")) {        // tests: force the growth / overflow paths
+            const unsigned long long v = strtoull(e, nullptr, 10);
+            if (v >= 1) n = v;
+        }
+        if (n >= 0xFFFFFFF0ull) return fail(h, DBG_ERR_OVERFLOW, "chunk table would exceed 2^32 slots");
+        TRY(reserve(h, h->b_ctable, n * sizeof(CS)));
+        LAUNCH(k_chunk_table_init<W>, blocks_for(n), DBG_BLOCK, h->stream, ptr<CS>(h->b_ctable), n);
+        CKK();
+        h->n_cslots = n;
+    } else if (need > h->n_cslots) {                                 // grow: move every entry into a larger table
+        const uint64_t n = need + need / 2;
+        if (n >= 0xFFFFFFF0ull) return fail(h, DBG_ERR_OVERFLOW, "chunk table would exceed 2^32 slots");
+        TRY(reserve(h, h->b_ctable2, n * sizeof(CS)));
+        LAUNCH(k_chunk_table_init<W>, blocks_for(n), DBG_BLOCK, h->stream, ptr<CS>(h->b_ctable2), n);
+        CKK();
+        LAUNCH(k_chunk_rehash<W>, blocks_for(h->n_cslots), DBG_BLOCK, h->stream, ptr<const CS>(h->b_ctable), h->n_cslots,
+               ptr<CS>(h->b_ctable2), (u32)n, ptr<ChunkCounters>(h->b_cc));
+        CKK();
+        std::swap(h->b_ctable, h->b_ctable2);
+        h->n_cslots = n;
+    }
+    return DBG_OK;
+}
+
 // node table from the distinct chunks (phase 2b): init + the k_expand passes at h->n_slots; no host sync.
 template <int W>
 static int expand_node_table(dbg_t *h) {
@@ -579,9 +635,7 @@ static int build_chunks(dbg_t *h, const u64 *d_off, int e0, int e1) {
     // ---- phase 1: chunk instances -> chunk table (interior) / list (first and last chunk of a read) ----
     // list of boundary chunks: slot 2 r = first chunk of read r, 2 r + 1 = its last chunk (EMPTY where a
     // read has none: reads of length <= k, or one chunk that is both)
-    const uint64_t list_cap = 2 * h->n_reads + 2;
-    TRY(reserve(h, h->b_clist, list_cap * sizeof(CS)));
-    CK(cudaMemsetAsync(h->b_clist.p, 0xFF, list_cap * sizeof(CS), h->stream));
+    const uint64_t list_cap = 2 * h->n_reads + 2;                     // reserved and cleared by build_impl
     // the sketch hashes the 32 bases at every chunk start that is not a read start; the last chunk of a
     // read starts at a content-defined cut like the interior chunk other reads have there, so the
     // sketch counts (about) the distinct INTERIOR chunks; it misses variants that differ only past
@@ -592,6 +646,7 @@ static int build_chunks(dbg_t *h, const u64 *d_off, int e0, int e1) {
         const unsigned long long v = strtoull(e, nullptr, 10);
         if (v >= 1) n_cslots = v;
     }
+    if (h->chunks_streamed) n_cslots = h->n_cslots;                   // phase 1 ran while the reads were arriving
     float ms_init = 0, ms_insert = 0;
     const uint64_t n_list = list_cap;
     uint64_t est = 0;
@@ -602,25 +657,16 @@ static int build_chunks(dbg_t *h, const u64 *d_off, int e0, int e1) {
         TRY(reserve(h, h->b_ctable, n_cslots * sizeof(CS)));
         TRY(reserve(h, h->b_h8, (n_cslots + n_list + 32) * 16));      // one hash byte per (record, node)
         const int a = ev_mark(h);
-        LAUNCH(k_chunk_table_init<W>, blocks_for(n_cslots), DBG_BLOCK, h->stream, ptr<CS>(h->b_ctable), n_cslots);
-        CKK();
-        const int b = ev_mark(h);
-        if (st.n_windows) {
-            const uint64_t n_units = cdiv(h->n_bases, DBG_UNIT);
-            uint64_t grid = (uint64_t)sms * DBG_CHUNK_MIN_BLOCKS;   // persistent: measured 0.39 ms vs 0.43 (x16) / 0.47 (x32)
-            if (const char *e = getenv("DBG_B200_INSERT_GRID")) {        // tuning / tests
-                const unsigned long long v = strtoull(e, nullptr, 10);
-                if (v >= 1) grid = v;
-            }
-            if (grid > cdiv(n_units, DBG_WARPS)) grid = cdiv(n_units, DBG_WARPS);
-            const uint64_t units_per_block = cdiv(n_units, grid);
-            grid = cdiv(n_units, units_per_block);
-            LAUNCH(k_chunk_insert<W>, grid, DBG_BLOCK, h->stream, ptr<const u64>(h->b_packed), h->n_words + 4, d_off,
-                   h->n_reads, ptr<const u32>(h->b_stmask), ptr<const u32>(h->b_vmask), ptr<const u32>(h->b_spanread),
-                   n_spans, n_units, units_per_block, k, ptr<CS>(h->b_ctable), (u32)n_cslots, ptr<CS>(h->b_clist),
-                   list_cap, h->read_idx_base, (const u32 *)h->d_read_batch, d_cc);
+        if (!h->chunks_streamed) {
+            LAUNCH(k_chunk_table_init<W>, blocks_for(n_cslots), DBG_BLOCK, h->stream, ptr<CS>(h->b_ctable), n_cslots);
             CKK();
         }
+        const int b = ev_mark(h);
+        if (st.n_windows && !h->chunks_streamed) {
+            h->n_cslots = n_cslots;
+            TRY(launch_chunk_insert<W>(h, d_off, 0, cdiv(h->n_bases, DBG_UNIT)));
+        }
+        h->chunks_streamed = false;                                  // a retry redoes phase 1 in one go
         const int c = ev_mark(h);
         CK(cudaMemcpyAsync(&cc, d_cc, sizeof cc, cudaMemcpyDeviceToHost, h->stream));
         // ---- phase 2a right behind it (no host round trip in between): sketch of the node keys of the
@@ -724,6 +770,13 @@ static int build_impl(dbg_t *h, const u8 *d_bases, const u64 *d_off) {
         TRY(reserve(h, h->b_cc, sizeof(ChunkCounters)));
         CK(cudaMemsetAsync(h->b_hll.p, 0, HLL_M * 4, h->stream));
         CK(cudaMemsetAsync(h->b_cc.p, 0, sizeof(ChunkCounters), h->stream));
+        // list of boundary chunks: slot 2 r = first chunk of read r, 2 r + 1 = its last chunk (EMPTY where a
+        // read has none: reads of length <= k, or one chunk that is both)
+        const uint64_t list_cap = 2 * h->n_reads + 2;
+        TRY(reserve(h, h->b_clist, list_cap * sizeof(ChunkSlot<W>)));
+        CK(cudaMemsetAsync(h->b_clist.p, 0xFF, list_cap * sizeof(ChunkSlot<W>), h->stream));
+        h->n_cslots = 0;
+        h->chunks_streamed = false;
     }
     if (h->n_reads) {
         LAUNCH(k_read_stats, blocks_for(h->n_reads), DBG_BLOCK, h->stream, d_off, h->n_reads, k, d_ctr);
@@ -754,7 +807,12 @@ static int build_impl(dbg_t *h, const u8 *d_bases, const u64 *d_off) {
                 CK(cudaEventRecord(h->slice_ev[i], h->copy_stream));
             }
         }
-        uint64_t s_done = 0;
+        // with the reads arriving in several slices, phase 1 of the chunk build (k_chunk_insert) also runs slice
+        // by slice, hidden behind the copies; the chunk table is sized from the running sketch and grows
+        // (k_chunk_rehash) when later slices bring more distinct chunks than the first ones promised
+        const bool stream_insert = chunks && h->host_bases && n_slices > 1;
+        std::vector<u32> regs(stream_insert ? HLL_M : 0);
+        uint64_t s_done = 0, u_done = 0;
         for (uint64_t i = 0; i < n_slices; i++) {
             const uint64_t b0 = i * slice, b1 = b0 + slice < h->n_bases ? b0 + slice : h->n_bases;
             if (b0 >= b1) break;
@@ -773,6 +831,19 @@ static int build_impl(dbg_t *h, const u8 *d_bases, const u64 *d_off) {
                            ptr<u32>(h->b_hll));
                     CKK();
                     s_done = s1;
+                }
+                if (stream_insert) {
+                    // units whose masks (32 spans + 1) and string overhang (3 words) are complete
+                    const uint64_t u1 = last ? cdiv(h->n_bases, DBG_UNIT) : (s_done >= 36 ? (s_done - 4) / 32 : 0);
+                    if (u1 > u_done) {
+                        CK(cudaMemcpyAsync(regs.data(), h->b_hll.p, HLL_M * 4, cudaMemcpyDeviceToHost, h->stream));
+                        CK(cudaStreamSynchronize(h->stream));              // the next slices are already on the wire
+                        const uint64_t est = (uint64_t)hll_estimate(regs) * ((h->sample_mask >> 6) + 1);
+                        TRY(chunk_table_fit<W>(h, est));
+                        TRY(launch_chunk_insert<W>(h, d_off, u_done, u1));
+                        u_done = u1;
+                        h->chunks_streamed = true;
+                    }
                 }
             }
         }
@@ -1273,7 +1344,7 @@ DBG_API void dbg_destroy(dbg_t *h) {
                      &h->b_succ, &h->b_link, &h->b_ctr, &h->b_hll, &h->b_order, &h->b_tag, &h->b_tag2, &h->b_slot,
                      &h->b_slot2, &h->b_sorttmp, &h->b_branch, &h->b_starts, &h->b_pulled, &h->b_readflags,
                      &h->b_recs, &h->b_cnt32, &h->b_off64, &h->b_contig, &h->b_junction, &h->b_split, &h->b_h8, &h->b_chunk, &h->b_bitmap,
-                     &h->b_stmask, &h->b_vmask, &h->b_spanread, &h->b_cc, &h->b_ctable, &h->b_clist, &h->b_super, &h->b_readbatch, &h->b_scratch[0],
+                     &h->b_stmask, &h->b_vmask, &h->b_spanread, &h->b_cc, &h->b_ctable, &h->b_clist, &h->b_super, &h->b_readbatch, &h->b_ctable2, &h->b_scratch[0],
                      &h->b_scratch[1], &h->b_scratch[2], &h->b_scratch[3], &h->b_scratch[4], &h->b_scratch[5]};
     for (DevBuf *b : all) if (b->p) cudaFree(b->p);
     for (int i = 0; i < EV_MAX; i++) cudaEventDestroy(h->ev[i]);

@@ -306,6 +306,31 @@ DBG_D int chunk_probe(ChunkSlot<W> *s, const ChunkKey<W> &key, u64 tag) {
     return 0;
 }
 
+// the chunk table grows while reads are still arriving (streamed host build): every entry of the old
+// table is moved into the new one.  Keys are unique, so a probe only looks for an EMPTY slot.
+template <int W>
+__global__ void __launch_bounds__(DBG_BLOCK) k_chunk_rehash(const ChunkSlot<W> *__restrict__ old_table, u64 n_old,
+                                                            ChunkSlot<W> *table, u32 n_slots, ChunkCounters *cc) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_old) return;
+    ChunkKey<W> key;
+#pragma unroll
+    for (int hh = 0; hh < W; hh++) key.h[hh] = old_table[i].h[hh];
+    if (key.h[0] == k128_ones()) return;
+    u64 idx = slot_home(chunk_hash<W>(key), n_slots);
+    for (u32 probes = 0; probes < n_slots; probes++) {
+        if (load_k128(&table[idx].h[0]) == k128_ones() &&
+            cas_key(&table[idx].h[0], k128_ones(), key.h[0]) == k128_ones()) {
+            if (W == 2) table[idx].h[W - 1] = key.h[W - 1];
+            table[idx].tag = old_table[i].tag;
+            table[idx].cnt = old_table[i].cnt;
+            return;
+        }
+        if (++idx == n_slots) idx = 0;
+    }
+    cc->chunk_overflow = 1;
+}
+
 #ifndef DBG_CHUNK_MIN_BLOCKS
 #define DBG_CHUNK_MIN_BLOCKS 4
 #endif
@@ -313,7 +338,7 @@ template <int W>
 __global__ void __launch_bounds__(DBG_BLOCK, DBG_CHUNK_MIN_BLOCKS)
 k_chunk_insert(const u64 *__restrict__ packed, u64 n_words_padded, const u64 *__restrict__ off, u64 n_reads,
                const u32 *__restrict__ st_mask, const u32 *__restrict__ v_mask, const u32 *__restrict__ span_read,
-               u64 n_spans, u64 n_units, u64 units_per_block, int k, ChunkSlot<W> *table, u32 n_slots,
+               u64 n_spans, u64 unit_base, u64 n_units, u64 units_per_block, int k, ChunkSlot<W> *table, u32 n_slots,
                ChunkSlot<W> *list, u64 list_cap, u64 read_idx_base, const u32 *__restrict__ read_batch,
                ChunkCounters *cc) {
     __shared__ ChunkInsertShared<W> sh;
@@ -401,7 +426,7 @@ k_chunk_insert(const u64 *__restrict__ packed, u64 n_words_padded, const u64 *__
         probe(act && !boundary, key, tag, 0);
     };
 
-    const u64 unit_begin = (u64)blockIdx.x * units_per_block;
+    const u64 unit_begin = unit_base + (u64)blockIdx.x * units_per_block;       // units [unit_base, n_units)
     u64 unit_end = unit_begin + units_per_block;
     if (unit_end > n_units) unit_end = n_units;
     for (u64 u = unit_begin + w; u < unit_end; u += DBG_WARPS) {
