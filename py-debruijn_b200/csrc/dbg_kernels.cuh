@@ -809,9 +809,11 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_pull_reads(const u64 *__restrict_
 #define WALK_SPLIT_LOG2 5
 #endif
 #ifndef WALK_SUPER_LOG2
-#define WALK_SUPER_LOG2 5
+#define WALK_SUPER_LOG2 3             // measured (split, super) = (5,5) 0.466 / (5,3) 0.436 / (4,3) 0.445 / (5,2) 0.447 ms of walk at C2
 #endif
-#define WALK_BLOCK_JUMP_CAP 32768          // super-splitters one block pointer-jumps by itself
+#ifndef WALK_BLOCK_JUMP_CAP
+#define WALK_BLOCK_JUMP_CAP 131072         // super-splitter list capacity up to which ONE cluster launch jumps it
+#endif
 #define LINK_SPLIT 0x8000000000000000ULL
 #define LINK_DIST_MAX 0x7FFFFFFFu
 DBG_HD u64 link_pack(u32 next, u32 dist) { return ((u64)dist << 32) | next; }
