@@ -102,6 +102,7 @@ struct dbg_handle {
     struct TimeRec { float *dst; int a, b; bool add; };
     std::vector<TimeRec> tm;                  // stage times still to be read from their events (after a sync)
     bool expand_pending = false;              // the node table was built without looking at its overflow flag yet
+    bool tags_local = false;                  // every tag in the table comes from this handle's own reads
     bool chunks_streamed = false;             // phase 1 already ran, slice by slice, while the reads were arriving
     uint64_t n_cslots = 0, n_clist = 0, ex_grid = 1;
 };
@@ -194,6 +195,12 @@ static void tm_flush(dbg_t *h) {                      // the stream must be idle
 // sort (tag, slot) pairs by tag: the reference's dict order is first-occurrence order
 // -------------------------------------------------------------------------------------------------
 static int sort_by_tag(dbg_t *h, uint64_t n, u32 *d_sorted_slots_out, int begin_bit) {
+    // tags are (global read index << 32 | pos): the read index needs only so many bits
+    int end_bit = 64;
+    if (h->tags_local) {                                // not for a table merged from other ranks' records
+        end_bit = 33;
+        while (end_bit < 64 && ((h->read_idx_base + h->n_reads) >> (end_bit - 32)) != 0) end_bit++;
+    }
     // input pairs are in b_tag / b_slot; sorted slots land in d_sorted_slots_out
     if (n == 0) return DBG_OK;
 #ifdef DBG_EMU
@@ -207,11 +214,11 @@ static int sort_by_tag(dbg_t *h, uint64_t n, u32 *d_sorted_slots_out, int begin_
     TRY(reserve(h, h->b_tag2, n * 8));
     size_t tmp = 0;
     CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, ptr<u64>(h->b_tag), ptr<u64>(h->b_tag2), ptr<u32>(h->b_slot),
-                                       d_sorted_slots_out, (int64_t)n, begin_bit, 64, h->stream));
+                                       d_sorted_slots_out, (int64_t)n, begin_bit, end_bit, h->stream));
     TRY(reserve(h, h->b_sorttmp, tmp));
     h->st.n_launches++;                                   // cub launches several kernels; counted as one
     CK(cub::DeviceRadixSort::SortPairs(h->b_sorttmp.p, tmp, ptr<u64>(h->b_tag), ptr<u64>(h->b_tag2),
-                                       ptr<u32>(h->b_slot), d_sorted_slots_out, (int64_t)n, begin_bit, 64, h->stream));
+                                       ptr<u32>(h->b_slot), d_sorted_slots_out, (int64_t)n, begin_bit, end_bit, h->stream));
 #endif
     return DBG_OK;
 }
@@ -779,7 +786,9 @@ static int build_impl(dbg_t *h, const u8 *d_bases, const u64 *d_off) {
         h->chunks_streamed = false;
     }
     if (h->n_reads) {
-        LAUNCH(k_read_stats, blocks_for(h->n_reads), DBG_BLOCK, h->stream, d_off, h->n_reads, k, d_ctr);
+        uint64_t rs_grid = blocks_for(h->n_reads);
+        if (rs_grid > 148 * 4) rs_grid = 148 * 4;
+        LAUNCH(k_read_stats, rs_grid, DBG_BLOCK, h->stream, d_off, h->n_reads, k, d_ctr);
         CKK();
     }
     if (h->n_bases) {
@@ -1036,6 +1045,8 @@ static int table_reset_impl(dbg_t *h, uint64_t expected_nodes) {
     h->st.table_slots = n_slots;
     h->st.table_bytes = n_slots * sizeof(S);
     h->table_ready = true;
+    h->tags_local = false;                              // records of other ranks' reads are merged in
+    h->expand_pending = false;
     h->built = h->walked = false;
     return DBG_OK;
 }
@@ -1391,6 +1402,7 @@ static int build_device_common(dbg_t *h, const uint8_t *d_bases, const uint64_t 
     CK(cudaSetDevice(h->device));
     if (!h->tm.empty()) { CK(cudaStreamSynchronize(h->stream)); tm_flush(h); }   // a previous build's stage times
     h->expand_pending = false;
+    h->tags_local = true;
     h->built = h->walked = false;
     h->n_ev = 0;
     h->n_reads = n_reads;

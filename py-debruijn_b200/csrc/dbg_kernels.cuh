@@ -99,16 +99,21 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_pack(const u8 *__restrict__ bases
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(DBG_BLOCK) k_read_stats(const u64 *__restrict__ off, u64 n_reads, int k,
                                                           DevCounters *ctr) {
-    u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    // grid-stride, one atomic per block (one per warp on the same word serialises in L2)
     u64 win = 0;
     bool too_long = false;
-    if (r < n_reads) {
+    for (u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x; r < n_reads; r += (u64)gridDim.x * blockDim.x) {
         u64 len = __ldg(off + r + 1) - __ldg(off + r);
-        if (len > (u64)k) win = len - k;
-        too_long = len > 0xFFFFFFFFULL;
+        if (len > (u64)k) win += len - k;
+        too_long |= len > 0xFFFFFFFFULL;
     }
     for (int d = 16; d > 0; d >>= 1) win += __shfl_down_sync(0xFFFFFFFFu, win, d);
-    if ((threadIdx.x & 31) == 0 && win) atomicAdd(&ctr->n_windows, win);
+    __shared__ u64 s_win;
+    if (threadIdx.x == 0) s_win = 0;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0 && win) atomicAdd(&s_win, win);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_win) atomicAdd(&ctr->n_windows, s_win);
     if (too_long) ctr->too_long = 1;
 }
 
