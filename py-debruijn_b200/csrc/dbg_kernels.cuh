@@ -701,24 +701,16 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_collect(const Slot<W> *__restrict
                                                        const u8 *__restrict__ flags, u32 want,
                                                        u64 *__restrict__ out_tag, u32 *__restrict__ out_slot,
                                                        u64 *cursor) {
-    // append aggregated per block: one global atomic per block (3 x 10^5 starts meant as many atomics on
-    // ONE word when every warp took its own range: 0.3 ms of a 0.55 ms stage at C3)
-    __shared__ u32 s_cnt;
-    __shared__ u64 s_base;
-    if (threadIdx.x == 0) s_cnt = 0;
-    __syncthreads();
     u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool hit = i < n_slots && (flags[i] & want);
-    const u32 b = __ballot_sync(0xFFFFFFFFu, hit);
-    const u32 lane = threadIdx.x & 31;
-    u32 w_off = 0;
-    if (lane == 0 && b) w_off = atomicAdd(&s_cnt, (u32)__popc(b));
-    w_off = __shfl_sync(0xFFFFFFFFu, w_off, 0);
-    __syncthreads();
-    if (threadIdx.x == 0 && s_cnt) s_base = atomicAdd(cursor, (u64)s_cnt);
-    __syncthreads();
+    bool hit = i < n_slots && (flags[i] & want);
+    u32 b = __ballot_sync(0xFFFFFFFFu, hit);
+    if (!b) return;
+    u32 lane = threadIdx.x & 31;
+    u64 base = 0;
+    if (lane == 0) base = atomicAdd(cursor, (u64)__popc(b));
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
     if (hit) {
-        const u64 o = s_base + w_off + __popc(b & ((1u << lane) - 1));
+        u64 o = base + __popc(b & ((1u << lane) - 1));
         out_tag[o] = table[i].tag;
         out_slot[o] = (u32)i;
     }
