@@ -51,6 +51,9 @@ typedef enum {
 #define DBG_TABLE_ONLY   8u  /* stop after the node table (window loop, debruijn.py:123-144): the
                                 multi-GPU build exchanges node records before the graph stages   */
 
+#define DBG_CHUNKS_ONLY 16u  /* stop after phase 1 of the chunk build (the distinct super-k-mers of the
+                                reads): the multi-GPU build exchanges CHUNK records, before any node table */
+
 /* node flag bits (dbg_export_nodes) */
 #define DBG_NODE_START   0x02u  /* reference indegree == 0 (debruijn.py:137-143 quirk)       */
 #define DBG_NODE_BRANCH  0x04u  /* > 1 successor survives pruningEdges (debruijn.py:230-236) */
@@ -165,6 +168,20 @@ int dbg_table_reset(dbg_t *h, uint64_t expected_nodes);
 int dbg_merge_records(dbg_t *h, const uint64_t *d_records, uint64_t n);
 int dbg_order_export(dbg_t *h, uint64_t *d_out, uint64_t capacity, uint64_t *n_out);
 int dbg_order_merge(dbg_t *h, const uint64_t *d_records, uint64_t n);
+
+/* The same exchange one level earlier (less volume, and only the owner expands): what the window loop
+ * of a rank's reads leaves BEFORE any node table is the set of its distinct chunks { string | min tag |
+ * multiplicity } (dbg_chunk_record_words() u64 words each), whose merge is associative too.  A chunk's
+ * owner is a function of its minimizer, which all its nodes share and every occurrence of those nodes
+ * has, so everything about one node meets on one rank.  dbg_build* with DBG_CHUNKS_ONLY, export grouped
+ * by owner, all-to-all, dbg_chunk_table_reset + dbg_chunk_merge_records, then dbg_chunk_expand leaves
+ * the rank's shard of the node table, ready for dbg_export_records(1 part) and the steps above.    */
+int dbg_chunk_record_words(const dbg_t *h);
+int dbg_chunk_export_counts(dbg_t *h, uint32_t n_parts, uint64_t *counts /* host, n_parts */);
+int dbg_chunk_export_records(dbg_t *h, uint32_t n_parts, const uint64_t *counts, uint64_t *d_out);
+int dbg_chunk_table_reset(dbg_t *h, uint64_t expected_chunks);
+int dbg_chunk_merge_records(dbg_t *h, const uint64_t *d_records, uint64_t n);
+int dbg_chunk_expand(dbg_t *h);
 
 /* nodes, unordered (sort by first_tag for the reference's dict order).  Any pointer may be
  * NULL.  succ_cnt: 4 per node = edge_count_table[node + "ACGT"[c]]; kept: low 8 bits = kept

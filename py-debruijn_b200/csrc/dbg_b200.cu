@@ -102,6 +102,7 @@ struct dbg_handle {
     struct TimeRec { float *dst; int a, b; bool add; };
     std::vector<TimeRec> tm;                  // stage times still to be read from their events (after a sync)
     bool expand_pending = false;              // the node table was built without looking at its overflow flag yet
+    bool chunks_merged = false;               // the chunk table holds records merged from other ranks (dbg_chunk_merge_records)
     bool chunks_valid = false;                // the chunk table + list of the last build still describe the local reads
     bool tags_local = false;                  // every tag in the table comes from this handle's own reads
     bool chunks_streamed = false;             // phase 1 already ran, slice by slice, while the reads were arriving
@@ -608,6 +609,8 @@ static int settle_node_table(dbg_t *h, bool fetched) {
     return DBG_OK;
 }
 
+template <int W> static int node_table_from_chunks(dbg_t *h, uint64_t est);
+
 template <int W>
 static int build_chunks(dbg_t *h, const u64 *d_off, int e0, int e1) {
     typedef Slot<W> S;
@@ -718,11 +721,31 @@ static int build_chunks(dbg_t *h, const u64 *d_off, int e0, int e1) {
     st.n_chunk_instances = cc.n_instances;
     st.n_chunk_list = n_list;
     st.chunk_slots = n_cslots;
+    st.ms_table_init = ms_init;
+    st.ms_insert = ms_insert;
+    tm_set(h, &st.ms_pack, e0, e1);
+    tm_set(h, &st.ms_estimate, e1, e2);
+    if (h->build_flags & DBG_CHUNKS_ONLY) {                          // multi-GPU: the chunks are exchanged before any node table
+        const int e_end = ev_mark(h);
+        tm_set(h, &st.ms_build_total, e0, e_end);
+        h->chunks_valid = true;
+        return DBG_OK;
+    }
+    TRY(node_table_from_chunks<W>(h, est));
+    const int e_end = ev_mark(h);
+    tm_set(h, &st.ms_build_total, e0, e_end);
+    h->table_ready = true;
+    h->chunks_valid = true;
+    return DBG_OK;
+}
 
-    // ---- phase 2b: node table (kernel 3): every node of every distinct chunk, x multiplicity ----
+// ---- phase 2b: node table (kernel 3): every node of every distinct chunk, x multiplicity ----
+template <int W>
+static int node_table_from_chunks(dbg_t *h, uint64_t est) {
+    dbg_stats_t &st = h->st;
     const uint64_t max_nodes = st.n_windows + h->n_reads;             // every window + last k-mer per read
     uint64_t want = (uint64_t)((double)est * 1.06) + 64;              // HLL std error at 2^12 registers: 1.6 %
-    if (want > max_nodes) want = max_nodes;
+    if (want > max_nodes && !h->chunks_merged) want = max_nodes;
     double load = 0.5;                                                // load factor: measured 0.5 / 0.6 / 0.7 = 0.51 / 0.53 / 0.60 ms of passes
     if (const char *e = getenv("DBG_B200_TABLE_LOAD")) {              // tuning: percent
         const double v = atof(e) / 100.0;
@@ -733,17 +756,9 @@ static int build_chunks(dbg_t *h, const u64 *d_off, int e0, int e1) {
         const unsigned long long v = strtoull(e, nullptr, 10);
         if (v >= 1) h->n_slots = v;
     }
-    st.ms_table_init = ms_init;
-    st.ms_insert = ms_insert;
-    tm_set(h, &st.ms_pack, e0, e1);
-    tm_set(h, &st.ms_estimate, e1, e2);
     TRY(expand_node_table<W>(h));
-    if (h->build_flags & DBG_TABLE_ONLY) TRY(settle_node_table<W>(h, false));   // nobody downstream looks at the flag
+    if ((h->build_flags & DBG_TABLE_ONLY) || h->chunks_merged) TRY(settle_node_table<W>(h, false));   // nobody downstream looks at the flag
     else h->expand_pending = true;                                   // graph_finalize looks at it with its own counters
-    const int e_end = ev_mark(h);
-    tm_set(h, &st.ms_build_total, e0, e_end);
-    h->table_ready = true;
-    h->chunks_valid = true;
     return DBG_OK;
 }
 
@@ -1039,6 +1054,106 @@ static int export_records_impl(dbg_t *h, uint32_t n_parts, const uint64_t *count
            n_parts, d_cur, (u64 *)d_out);
     CKK();
     CK(cudaStreamSynchronize(h->stream));
+    return DBG_OK;
+}
+
+// ---- chunk records: the unit of the multi-GPU exchange when it happens before any node table ----
+template <int W>
+static int chunk_export_counts_impl(dbg_t *h, uint32_t n_parts, uint64_t *counts) {
+    typedef ChunkSlot<W> CS;
+    const ChunkGeom geom = chunk_geom(h->k);
+    TRY(reserve(h, h->b_off64, (uint64_t)n_parts * 8 * 2));
+    CK(cudaMemsetAsync(h->b_off64.p, 0, (uint64_t)n_parts * 8 * 2, h->stream));
+    LAUNCH(k_chunk_rec_count<W>, blocks_for(h->n_cslots + h->n_clist), DBG_BLOCK, h->stream, ptr<const CS>(h->b_ctable),
+           h->n_cslots, ptr<const CS>(h->b_clist), h->n_clist, geom.w, geom.m, h->batch_bits, n_parts, ptr<u64>(h->b_off64));
+    CKK();
+    CK(cudaMemcpyAsync(counts, h->b_off64.p, (uint64_t)n_parts * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return DBG_OK;
+}
+
+template <int W>
+static int chunk_export_records_impl(dbg_t *h, uint32_t n_parts, const uint64_t *counts, uint64_t *d_out) {
+    typedef ChunkSlot<W> CS;
+    const ChunkGeom geom = chunk_geom(h->k);
+    std::vector<u64> cursors(n_parts);
+    u64 acc = 0;
+    for (uint32_t p = 0; p < n_parts; p++) { cursors[p] = acc; acc += counts[p]; }
+    u64 *d_cur = ptr<u64>(h->b_off64) + n_parts;
+    CK(cudaMemcpyAsync(d_cur, cursors.data(), (uint64_t)n_parts * 8, cudaMemcpyHostToDevice, h->stream));
+    LAUNCH(k_chunk_rec_scatter<W>, blocks_for(h->n_cslots + h->n_clist), DBG_BLOCK, h->stream, ptr<const CS>(h->b_ctable),
+           h->n_cslots, ptr<const CS>(h->b_clist), h->n_clist, geom.w, geom.m, h->batch_bits, n_parts, d_cur, (CS *)d_out);
+    CKK();
+    CK(cudaStreamSynchronize(h->stream));
+    return DBG_OK;
+}
+
+template <int W>
+static int chunk_table_reset_impl(dbg_t *h, uint64_t expected_chunks) {
+    typedef ChunkSlot<W> CS;
+    const uint64_t n = (uint64_t)((double)expected_chunks * 1.7) + 4096;      // received records are an upper bound
+    if (n >= 0xFFFFFFF0ull) return fail(h, DBG_ERR_OVERFLOW, "chunk table would exceed 2^32 slots");
+    TRY(reserve(h, h->b_ctable, n * sizeof(CS)));
+    TRY(reserve(h, h->b_cc, sizeof(ChunkCounters)));
+    LAUNCH(k_chunk_table_init<W>, blocks_for(n), DBG_BLOCK, h->stream, ptr<CS>(h->b_ctable), n);
+    CKK();
+    CK(cudaMemsetAsync(h->b_cc.p, 0, sizeof(ChunkCounters), h->stream));
+    h->n_cslots = n;
+    h->n_clist = 0;                                                   // boundary chunks arrive as records like the others
+    h->chunks_merged = true;
+    h->chunks_valid = true;
+    h->tags_local = false;
+    h->expand_pending = false;
+    h->table_ready = false;
+    h->built = h->walked = false;
+    return DBG_OK;
+}
+
+template <int W>
+static int chunk_merge_records_impl(dbg_t *h, const uint64_t *d_records, uint64_t n) {
+    typedef ChunkSlot<W> CS;
+    if (n == 0) return DBG_OK;
+    LAUNCH(k_chunk_rec_merge<W>, blocks_for(n), DBG_BLOCK, h->stream, ptr<CS>(h->b_ctable), (u32)h->n_cslots,
+           (const CS *)d_records, n, ptr<ChunkCounters>(h->b_cc));
+    CKK();
+    ChunkCounters cc;
+    CK(cudaMemcpyAsync(&cc, h->b_cc.p, sizeof cc, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (cc.chunk_overflow) return fail(h, DBG_ERR_NOMEM, "chunk table overflowed while merging records");
+    return DBG_OK;
+}
+
+// phase 2 on the merged chunk table: this rank's shard of the node table
+template <int W>
+static int chunk_expand_impl(dbg_t *h) {
+    typedef Slot<W> S;
+    typedef ChunkSlot<W> CS;
+    DevCounters *d_ctr = ptr<DevCounters>(h->b_ctr);
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+    if (!h->tm.empty()) { CK(cudaStreamSynchronize(h->stream)); tm_flush(h); }
+    h->n_ev = 0;
+    uint64_t ex_grid = cdiv(cdiv(h->n_cslots + h->n_clist, 32), DBG_WARPS);
+    if (ex_grid > (uint64_t)sms * DBG_EXPAND_MIN_BLOCKS) ex_grid = (uint64_t)sms * DBG_EXPAND_MIN_BLOCKS;
+    if (ex_grid < 1) ex_grid = 1;
+    h->ex_grid = ex_grid;
+    std::vector<u32> sketch(HLL_M, 0);
+    TRY(reserve(h, h->b_hll, HLL_M * 4));
+    TRY(reserve(h, h->b_h8, (h->n_cslots + h->n_clist + 32) * 16));
+    CK(cudaMemsetAsync(h->b_hll.p, 0, HLL_M * 4, h->stream));
+    CK(cudaMemsetAsync(&d_ctr->overflow, 0, 4, h->stream));
+    LAUNCH((k_expand<W, 0>), ex_grid, DBG_BLOCK, h->stream, ptr<const CS>(h->b_ctable), h->n_cslots,
+           ptr<const CS>(h->b_clist), h->n_clist, h->k, ptr<uint4>(h->b_h8), (S *)nullptr, 0u, 0u, 0u,
+           ptr<u32>(h->b_hll), h->batch_bits, d_ctr);
+    CKK();
+    CK(cudaMemcpyAsync(sketch.data(), h->b_hll.p, HLL_M * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    const uint64_t local_windows = h->st.n_windows;
+    h->st.n_windows = 1;                                              // expand_node_table skips its passes for an empty read set,
+    const int rc = node_table_from_chunks<W>(h, (uint64_t)hll_estimate(sketch));   // but the chunks here may all be other ranks'
+    h->st.n_windows = local_windows;
+    TRY(rc);
+    h->table_ready = true;
     return DBG_OK;
 }
 
@@ -1402,7 +1517,7 @@ static int build_device_common(dbg_t *h, const uint8_t *d_bases, const uint64_t 
         if (((1ull << bb) - 1) < (uint64_t)n_batches || 2 * h->k + bb > 64 * h->W)
             return fail(h, DBG_ERR_ARG, "%u batches need %d key bits above the %d bits of a %d-mer: more than the %d-bit key has",
                         n_batches, bb, 2 * h->k, h->k, 64 * h->W);
-        if (flags & DBG_TABLE_ONLY) return fail(h, DBG_ERR_ARG, "a batched build cannot be DBG_TABLE_ONLY");
+        if (flags & (DBG_TABLE_ONLY | DBG_CHUNKS_ONLY)) return fail(h, DBG_ERR_ARG, "a batched build cannot be DBG_TABLE_ONLY / DBG_CHUNKS_ONLY");
         h->d_read_batch = d_read_batch;
         h->batch_bits = bb;
         h->n_batches = n_batches;
@@ -1415,6 +1530,7 @@ static int build_device_common(dbg_t *h, const uint8_t *d_bases, const uint64_t 
     h->expand_pending = false;
     h->tags_local = true;
     h->chunks_valid = false;
+    h->chunks_merged = false;
     h->built = h->walked = false;
     h->n_ev = 0;
     h->n_reads = n_reads;
@@ -1434,7 +1550,7 @@ static int build_device_common(dbg_t *h, const uint8_t *d_bases, const uint64_t 
     CK(cudaMemsetAsync(h->b_ctr.p, 0, sizeof(DevCounters), h->stream));
     h->table_ready = false;
     TRY(DISPATCH(build_impl, h, (const u8 *)d_bases, (const u64 *)d_read_off));
-    if (flags & DBG_TABLE_ONLY) return DBG_OK;
+    if (flags & (DBG_TABLE_ONLY | DBG_CHUNKS_ONLY)) return DBG_OK;
     TRY(DISPATCH(graph_finalize, h));
     TRY(DISPATCH(graph_order_scan, h));
     TRY(DISPATCH(graph_complete, h));
@@ -1561,6 +1677,43 @@ DBG_API int dbg_order_merge(dbg_t *h, const uint64_t *d_records, uint64_t n) {
     NEED_TABLE();
     CK(cudaSetDevice(h->device));
     return DISPATCH(order_merge_impl, h, d_records, n);
+}
+
+#define NEED_CHUNKS() do { if (!h) return DBG_ERR_ARG; if (!h->chunks_valid) return fail(h, DBG_ERR_STATE, "%s needs a chunk table (dbg_build* with DBG_CHUNKS_ONLY, or dbg_chunk_table_reset, first)", __func__); } while (0)
+
+DBG_API int dbg_chunk_record_words(const dbg_t *h) { return h ? (h->W == 1 ? 4 : 8) : 0; }
+
+DBG_API int dbg_chunk_export_counts(dbg_t *h, uint32_t n_parts, uint64_t *counts) {
+    NEED_CHUNKS();
+    if (n_parts == 0 || n_parts > DBG_MAX_PARTS || !counts) return fail(h, DBG_ERR_ARG, "dbg_chunk_export_counts: bad argument");
+    CK(cudaSetDevice(h->device));
+    return DISPATCH(chunk_export_counts_impl, h, n_parts, counts);
+}
+
+DBG_API int dbg_chunk_export_records(dbg_t *h, uint32_t n_parts, const uint64_t *counts, uint64_t *d_out) {
+    NEED_CHUNKS();
+    if (n_parts == 0 || n_parts > DBG_MAX_PARTS || !counts) return fail(h, DBG_ERR_ARG, "dbg_chunk_export_records: bad argument");
+    CK(cudaSetDevice(h->device));
+    return DISPATCH(chunk_export_records_impl, h, n_parts, counts, d_out);
+}
+
+DBG_API int dbg_chunk_table_reset(dbg_t *h, uint64_t expected_chunks) {
+    if (!h) return DBG_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    return DISPATCH(chunk_table_reset_impl, h, expected_chunks);
+}
+
+DBG_API int dbg_chunk_merge_records(dbg_t *h, const uint64_t *d_records, uint64_t n) {
+    NEED_CHUNKS();
+    if (n && !d_records) return fail(h, DBG_ERR_ARG, "NULL records");
+    CK(cudaSetDevice(h->device));
+    return DISPATCH(chunk_merge_records_impl, h, d_records, n);
+}
+
+DBG_API int dbg_chunk_expand(dbg_t *h) {
+    NEED_CHUNKS();
+    CK(cudaSetDevice(h->device));
+    return DISPATCH(chunk_expand_impl, h);
 }
 
 DBG_API int dbg_stats(dbg_t *h, dbg_stats_t *out) {

@@ -761,3 +761,128 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_order_chunks(const ChunkSlot<W> *
         }
     }
 }
+
+// ---------------------------------------------------------------------------------------------
+// Chunk records: the unit of the multi-GPU exchange when it happens BEFORE any node table exists.
+// A rank's window loop leaves its distinct chunks {string | min tag | multiplicity} (chunk table + the
+// boundary list); merging them is associative (min tag, summed multiplicity).  The owner of a chunk is a
+// function of its MINIMIZER -- the m-mer all its nodes share, and which every occurrence of any of its
+// nodes has wherever it turns up -- so all contributions to one node meet on one rank, which expands
+// only what it owns.  The owner function must pick exactly the minimizer k_masks picked: same hash,
+// leftmost on ties.
+// ---------------------------------------------------------------------------------------------
+template <int W>
+DBG_D u32 chunk_owner(const u64 *cw, int w, int m, u32 batch, u32 n_parts) {
+    u32 best = 0xFFFFFFFFu, best_x = 0;
+    for (int i = 0; i < w; i++) {                              // the first node's w candidate m-mers
+        const int s = 2 * i;                                   // i < 16: inside the first two words
+        const u64 t = s ? ((cw[0] << s) | (cw[1] >> (64 - s))) : cw[0];
+        const u32 x = (u32)(t >> 32) >> (32 - 2 * m);
+        const u32 g = (((x * 0x9E3779B1u) >> 8) & 0xFFFFFFC0u) | (u32)i;
+        if (g < best) { best = g; best_x = x; }
+    }
+    const u32 hsh = hash32_key((u64)best_x | ((u64)batch << 32));
+    return (u32)(((u64)hsh * n_parts) >> 32);
+}
+
+template <int W>
+DBG_D bool chunk_record_load(const ChunkSlot<W> *recs_a, u64 n_a, const ChunkSlot<W> *recs_b, u64 idx, K128 *h) {
+    const ChunkSlot<W> *rec = idx < n_a ? recs_a + idx : recs_b + (idx - n_a);
+#pragma unroll
+    for (int hh = 0; hh < W; hh++) h[hh] = load_k128(&rec->h[hh]);
+    return h[0] != k128_ones();
+}
+
+template <int W>
+__global__ void __launch_bounds__(DBG_BLOCK) k_chunk_rec_count(const ChunkSlot<W> *__restrict__ recs_a, u64 n_a,
+                                                               const ChunkSlot<W> *__restrict__ recs_b, u64 n_b,
+                                                               int w, int m, int batch_bits, u32 n_parts, u64 *counts) {
+    __shared__ u32 s_cnt[DBG_MAX_PARTS];
+    for (u32 p = threadIdx.x; p < n_parts; p += blockDim.x) s_cnt[p] = 0;
+    __syncthreads();
+    const u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    K128 h[W];
+    if (idx < n_a + n_b && chunk_record_load<W>(recs_a, n_a, recs_b, idx, h)) {
+        u64 cw[2 * W];
+        chunk_words<W>(h, cw);
+        const u32 batch = batch_bits ? (u32)(h[W - 1].lo >> 8) & (u32)((1ull << batch_bits) - 1) : 0u;
+        atomicAdd(&s_cnt[chunk_owner<W>(cw, w, m, batch, n_parts)], 1u);
+    }
+    __syncthreads();
+    for (u32 p = threadIdx.x; p < n_parts; p += blockDim.x)
+        if (s_cnt[p]) atomicAdd(&counts[p], (u64)s_cnt[p]);
+}
+
+template <int W>
+__global__ void __launch_bounds__(DBG_BLOCK) k_chunk_rec_scatter(const ChunkSlot<W> *__restrict__ recs_a, u64 n_a,
+                                                                 const ChunkSlot<W> *__restrict__ recs_b, u64 n_b,
+                                                                 int w, int m, int batch_bits, u32 n_parts,
+                                                                 u64 *cursors, ChunkSlot<W> *__restrict__ out) {
+    __shared__ u32 s_cnt[DBG_MAX_PARTS];
+    __shared__ u64 s_base[DBG_MAX_PARTS];
+    for (u32 p = threadIdx.x; p < n_parts; p += blockDim.x) s_cnt[p] = 0;
+    __syncthreads();
+    const u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    K128 h[W];
+    u32 owner = 0, local = 0;
+    const bool have = idx < n_a + n_b && chunk_record_load<W>(recs_a, n_a, recs_b, idx, h);
+    if (have) {
+        u64 cw[2 * W];
+        chunk_words<W>(h, cw);
+        const u32 batch = batch_bits ? (u32)(h[W - 1].lo >> 8) & (u32)((1ull << batch_bits) - 1) : 0u;
+        owner = chunk_owner<W>(cw, w, m, batch, n_parts);
+        local = atomicAdd(&s_cnt[owner], 1u);
+    }
+    __syncthreads();
+    for (u32 p = threadIdx.x; p < n_parts; p += blockDim.x)
+        if (s_cnt[p]) s_base[p] = atomicAdd(&cursors[p], (u64)s_cnt[p]);
+    __syncthreads();
+    if (have) {
+        const ChunkSlot<W> *rec = idx < n_a ? recs_a + idx : recs_b + (idx - n_a);
+        ChunkSlot<W> o;
+#pragma unroll
+        for (int hh = 0; hh < W; hh++) o.h[hh] = h[hh];
+        o.tag = __ldcg(&rec->tag);
+        o.cnt = __ldcg(&rec->cnt);
+        o.zero_pad();
+        out[s_base[owner] + local] = o;
+    }
+}
+
+// merge received chunk records into this rank's chunk table: multiplicities add, tags take the minimum
+template <int W>
+__global__ void __launch_bounds__(DBG_BLOCK) k_chunk_rec_merge(ChunkSlot<W> *table, u32 n_slots,
+                                                               const ChunkSlot<W> *__restrict__ recs, u64 n,
+                                                               ChunkCounters *cc) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    ChunkKey<W> key;
+#pragma unroll
+    for (int hh = 0; hh < W; hh++) key.h[hh] = load_k128(&recs[i].h[hh]);
+    const u64 tag = __ldcg(&recs[i].tag);
+    const u32 cnt = __ldcg(&recs[i].cnt);
+    u64 idx = slot_home(chunk_hash<W>(key), n_slots);
+    for (u32 probes = 0; probes < CH_MAX_PROBES && probes < n_slots;) {
+        ChunkSlot<W> *s = &table[idx];
+        const K128 c0 = load_k128(&s->h[0]);
+        bool mine = c0 == key.h[0];
+        if (!mine && c0 == k128_ones()) {
+            const K128 old = cas_key(&s->h[0], k128_ones(), key.h[0]);
+            if (old == k128_ones()) { if (W == 2) store_k128(&s->h[W - 1], key.h[W - 1]); mine = true; }
+            else mine = old == key.h[0];
+        }
+        if (mine && W == 2) {
+            const K128 c1 = load_k128(&s->h[W - 1]);
+            if (c1 == k128_ones()) continue;                              // being published: look again
+            mine = c1 == key.h[W - 1];
+        }
+        if (mine) {
+            atomicMin(&s->tag, tag);
+            atomicAdd(&s->cnt, cnt);
+            return;
+        }
+        probes++;
+        if (++idx == n_slots) idx = 0;
+    }
+    cc->chunk_overflow = 1;
+}

@@ -28,7 +28,7 @@ DBG_OK = 0
 DBG_ERR_CUDA, DBG_ERR_ARG, DBG_ERR_ALPHABET, DBG_ERR_NOMEM = -1, -2, -3, -4
 DBG_ERR_STATE, DBG_ERR_ZERODIV, DBG_ERR_OVERFLOW = -5, -6, -7
 # build flags
-DBG_FINAL, DBG_EXACT_ORDER, DBG_NO_PULL_READS, DBG_TABLE_ONLY = 1, 2, 4, 8
+DBG_FINAL, DBG_EXACT_ORDER, DBG_NO_PULL_READS, DBG_TABLE_ONLY, DBG_CHUNKS_ONLY = 1, 2, 4, 8, 16
 # node flags
 NODE_START, NODE_BRANCH, NODE_DEADEND, NODE_PULLED, NODE_MULTI = 0x02, 0x04, 0x08, 0x10, 0x20
 # terminal kinds
@@ -80,6 +80,12 @@ SYMBOLS = {
     'dbg_export_records': (C.c_int, [_P, C.c_uint32, _P, _P]),
     'dbg_table_reset': (C.c_int, [_P, C.c_uint64]),
     'dbg_merge_records': (C.c_int, [_P, _P, C.c_uint64]),
+    'dbg_chunk_record_words': (C.c_int, [_P]),
+    'dbg_chunk_export_counts': (C.c_int, [_P, C.c_uint32, _P]),
+    'dbg_chunk_export_records': (C.c_int, [_P, C.c_uint32, _P, _P]),
+    'dbg_chunk_table_reset': (C.c_int, [_P, C.c_uint64]),
+    'dbg_chunk_merge_records': (C.c_int, [_P, _P, C.c_uint64]),
+    'dbg_chunk_expand': (C.c_int, [_P]),
     'dbg_order_export': (C.c_int, [_P, _P, C.c_uint64, C.POINTER(C.c_uint64)]),
     'dbg_order_merge': (C.c_int, [_P, _P, C.c_uint64]),
     'dbg_export_nodes': (C.c_int, [_P] + [_P] * 7),

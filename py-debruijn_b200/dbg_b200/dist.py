@@ -6,9 +6,10 @@ reads leaves behind is a set of node records {key | first-occurrence tag | 4 suc
 whose merge is associative (min tag, summed counts) -- tags carry the GLOBAL read index, so the
 reference's dict order and its indegree flag are partition invariant.
 
-    rank r:  reads[lo_r:hi_r] --dbg_build(TABLE_ONLY)--> local table
-             --dbg_export_records(P)--> records grouped by owner = (slot hash * P) >> 32
-             ==all-to-all==> records of the keys this rank owns --merge--> shard
+    rank r:  reads[lo_r:hi_r] --dbg_build(CHUNKS_ONLY)--> the distinct super-k-mers (chunks) of the local reads
+             --dbg_chunk_export_records(P)--> chunk records grouped by owner = f(minimizer)
+             ==all-to-all==> chunks of the minimizers this rank owns --merge, dbg_chunk_expand--> node shard
+             (DBG_B200_DIST=records: the older exchange of NODE records from a full local node table)
              ==all-gather==> every shard --merge--> the full node table, on every rank
              graph stage 0 (degrees / prune / branch flags)
              graph stage 1 (tie-order scan of the LOCAL reads) ==all-gather order records==> merge
@@ -82,31 +83,59 @@ def build_distributed(graph: Graph, local_packed, read_idx_base, threshold=3, fi
         if cuda:
             torch.cuda.current_stream(dev).synchronize()
 
+    import os
     import time
     t0 = time.perf_counter()
-    # 1. local window loop
-    if local_device is not None:
-        graph.build_table_device(*local_device, read_idx_base=read_idx_base)
+    if os.environ.get('DBG_B200_DIST', 'chunks') == 'chunks':
+        # 1. phase 1 of the chunk build on the local reads: their distinct super-k-mers, no node table
+        if local_device is not None:
+            graph.build_chunks(device_ptrs=local_device, read_idx_base=read_idx_base)
+        else:
+            graph.build_chunks(packed=local_packed, read_idx_base=read_idx_base)
+        t0 = tick('local_table_ms', t0)
+        cw = graph.chunk_record_words()
+        # 2. chunk records grouped by owner = f(minimizer), 3. all-to-all
+        counts = graph.chunk_export_counts(world)
+        send = torch.empty((int(counts.sum()), cw), dtype=torch.int64, device=dev)
+        graph.chunk_export_records(world, counts, send.data_ptr())
+        send_counts = torch.tensor(counts.astype(np.int64), dtype=torch.int64, device=dev)
+        recv_counts = torch.empty_like(send_counts)
+        dist.all_to_all_single(recv_counts, send_counts, group=group)
+        rc = [int(x) for x in recv_counts.tolist()]
+        recv = torch.empty((sum(rc), cw), dtype=torch.int64, device=dev)
+        dist.all_to_all_single(recv, send, output_split_sizes=rc, input_split_sizes=[int(c) for c in counts],
+                               group=group)
+        fence()
+        t0 = tick('exchange_ms', t0)
+        # 4. merge the chunks this rank owns and expand them: its shard of the node table
+        graph.chunk_table_reset(max(1, recv.shape[0]))
+        graph.chunk_merge_records(recv.data_ptr(), recv.shape[0])
+        graph.chunk_expand()
     else:
-        graph.build_table(packed=local_packed, read_idx_base=read_idx_base)
-    t0 = tick('local_table_ms', t0)
+        # 1. local window loop -> local node table
+        if local_device is not None:
+            graph.build_table_device(*local_device, read_idx_base=read_idx_base)
+        else:
+            graph.build_table(packed=local_packed, read_idx_base=read_idx_base)
+        t0 = tick('local_table_ms', t0)
+        rw = graph.record_words()
+        # 2. node records grouped by owner, 3. all-to-all
+        counts = graph.export_counts(world)
+        send = torch.empty((int(counts.sum()), rw), dtype=torch.int64, device=dev)
+        graph.export_records(world, counts, send.data_ptr())
+        send_counts = torch.tensor(counts.astype(np.int64), dtype=torch.int64, device=dev)
+        recv_counts = torch.empty_like(send_counts)
+        dist.all_to_all_single(recv_counts, send_counts, group=group)
+        rc = [int(x) for x in recv_counts.tolist()]
+        recv = torch.empty((sum(rc), rw), dtype=torch.int64, device=dev)
+        dist.all_to_all_single(recv, send, output_split_sizes=rc, input_split_sizes=[int(c) for c in counts],
+                               group=group)
+        fence()
+        t0 = tick('exchange_ms', t0)
+        # 4. merge what this rank owns
+        graph.table_reset(max(1, recv.shape[0]))
+        graph.merge_records(recv.data_ptr(), recv.shape[0])
     rw = graph.record_words()
-    # 2. records grouped by owner, 3. all-to-all
-    counts = graph.export_counts(world)
-    send = torch.empty((int(counts.sum()), rw), dtype=torch.int64, device=dev)
-    graph.export_records(world, counts, send.data_ptr())
-    send_counts = torch.tensor(counts.astype(np.int64), dtype=torch.int64, device=dev)
-    recv_counts = torch.empty_like(send_counts)
-    dist.all_to_all_single(recv_counts, send_counts, group=group)
-    rc = [int(x) for x in recv_counts.tolist()]
-    recv = torch.empty((sum(rc), rw), dtype=torch.int64, device=dev)
-    dist.all_to_all_single(recv, send, output_split_sizes=rc, input_split_sizes=[int(c) for c in counts],
-                           group=group)
-    fence()
-    t0 = tick('exchange_ms', t0)
-    # 4. merge what this rank owns
-    graph.table_reset(max(1, recv.shape[0]))
-    graph.merge_records(recv.data_ptr(), recv.shape[0])
     c1 = graph.export_counts(1)
     shard = torch.empty((int(c1[0]), rw), dtype=torch.int64, device=dev)
     graph.export_records(1, c1, shard.data_ptr())

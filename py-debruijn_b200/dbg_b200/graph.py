@@ -206,6 +206,48 @@ class Graph:
         self.lib.check(self.h, rc)
         return self
 
+    def build_chunks(self, reads=None, packed=None, read_idx_base=0, device_ptrs=None):
+        """Phase 1 of the chunk build only (DBG_CHUNKS_ONLY): the distinct super-k-mers of the reads.
+        Host buffers, or device_ptrs = (d_bases, d_off, n_reads, n_bases)."""
+        self._reset_cache()
+        if device_ptrs is not None:
+            d_bases, d_off, n_reads, n_bases = device_ptrs
+            self.reads = None
+            self.n_reads = int(n_reads)
+            rc = self.lib.dbg_build_device(self.h, d_bases, d_off, self.n_reads, int(n_bases), int(read_idx_base), 3.0,
+                                           N.DBG_CHUNKS_ONLY)
+        else:
+            bases, off = packed if packed is not None else pack_reads(reads)
+            self.reads = reads
+            self._keep = (bases, off)
+            self.n_reads = len(off) - 1
+            rc = self.lib.dbg_build(self.h, bases.ctypes.data if len(bases) else None, off.ctypes.data, self.n_reads,
+                                    int(read_idx_base), 3.0, N.DBG_CHUNKS_ONLY)
+        self.lib.check(self.h, rc)
+        return self
+
+    def chunk_record_words(self):
+        return self.lib.dbg_chunk_record_words(self.h)
+
+    def chunk_export_counts(self, n_parts):
+        counts = np.zeros(n_parts, np.uint64)
+        self.lib.check(self.h, self.lib.dbg_chunk_export_counts(self.h, n_parts, counts.ctypes.data))
+        return counts
+
+    def chunk_export_records(self, n_parts, counts, d_out_ptr):
+        counts = np.ascontiguousarray(counts, dtype=np.uint64)
+        self.lib.check(self.h, self.lib.dbg_chunk_export_records(self.h, n_parts, counts.ctypes.data, d_out_ptr))
+
+    def chunk_table_reset(self, expected_chunks):
+        self._reset_cache()
+        self.lib.check(self.h, self.lib.dbg_chunk_table_reset(self.h, int(expected_chunks)))
+
+    def chunk_merge_records(self, d_ptr, n):
+        self.lib.check(self.h, self.lib.dbg_chunk_merge_records(self.h, d_ptr, int(n)))
+
+    def chunk_expand(self):
+        self.lib.check(self.h, self.lib.dbg_chunk_expand(self.h))
+
     def record_words(self):
         return self.lib.dbg_record_words(self.h)
 

@@ -12,7 +12,7 @@ import util
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-def _worker(rank, world, port, cases, out_q):
+def _worker(rank, world, port, cases, out_q, mode='chunks'):
     import contextlib
     import io
     import torch.distributed as dist
@@ -24,6 +24,7 @@ def _worker(rank, world, port, cases, out_q):
     from dbg_b200 import _native, dist as ddist
     import debruijn as db
     _native._lib = _native.Library(build_emu.build())
+    os.environ['DBG_B200_DIST'] = mode
     os.environ['MASTER_ADDR'] = '127.0.0.1'
     os.environ['MASTER_PORT'] = str(port)
     dist.init_process_group('gloo', rank=rank, world_size=world)
@@ -45,8 +46,10 @@ def _worker(rank, world, port, cases, out_q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('world', [2, 3])
-def test_distributed_equals_oracle(world):
+@pytest.mark.parametrize('world,mode', [(2, 'chunks'), (3, 'chunks'), (2, 'records')])
+def test_distributed_equals_oracle(world, mode):
+    """mode = what the ranks exchange: distinct CHUNKS of their reads (default; owner = f(minimizer), only
+    the owner expands them into nodes) or NODE records of a full local node table (the older path)."""
     import random
     from oracle import dbg_oracle
     r = random.Random(500 + world)
@@ -65,8 +68,8 @@ def test_distributed_equals_oracle(world):
         cases.append((rd, k, thr, final))
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
-    port = 29500 + (os.getpid() % 1000) + world
-    procs = [ctx.Process(target=_worker, args=(rk, world, port, cases, q)) for rk in range(world)]
+    port = 29500 + (os.getpid() % 1000) + world + (7 if mode == 'records' else 0)
+    procs = [ctx.Process(target=_worker, args=(rk, world, port, cases, q, mode)) for rk in range(world)]
     for p in procs:
         p.start()
     got = {}
