@@ -140,13 +140,26 @@ def build_distributed(graph: Graph, local_packed, read_idx_base, threshold=3, fi
     shard = torch.empty((int(c1[0]), rw), dtype=torch.int64, device=dev)
     graph.export_records(1, c1, shard.data_ptr())
     t0 = tick('shard_merge_ms', t0)
-    # 5. every shard everywhere -> the full table
-    full, _ = _all_gather_var(shard, group)
+    # 5. every shard everywhere -> the full table (one all-gather into one buffer, merged slice by slice)
+    n_mine = torch.tensor([shard.shape[0]], dtype=torch.int64, device=dev)
+    ns_t = [torch.zeros_like(n_mine) for _ in range(world)]
+    dist.all_gather(ns_t, n_mine, group=group)
+    ns = [int(x.item()) for x in ns_t]
+    m = max(max(ns), 1)
+    if shard.shape[0] < m:
+        pad = torch.empty((m, rw), dtype=torch.int64, device=dev)
+        pad[:shard.shape[0]] = shard
+    else:
+        pad = shard
+    everything = torch.empty((world * m, rw), dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(everything, pad, group=group)
     fence()
     t0 = tick('gather_ms', t0)
-    graph.table_reset(max(1, full.shape[0]))
-    graph.merge_records(full.data_ptr(), full.shape[0])
-    del send, recv, shard, full
+    graph.table_reset(max(1, sum(ns)))
+    for r in range(world):
+        if ns[r]:
+            graph.merge_records(everything[r * m:r * m + ns[r]].data_ptr(), ns[r])
+    del send, recv, shard, pad, everything
     t0 = tick('full_merge_ms', t0)
     # 6. graph stages; the tie-order scan runs over the local reads and is merged by key
     graph.graph_stage(0, threshold, final, exact_order, pull_reads)
