@@ -459,7 +459,7 @@ def main():
     ap.add_argument('--config', default='c2', choices=sorted(CONFIGS))
     ap.add_argument('--impl', default='dbg', choices=['dbg', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--cpu-sample-bp', type=int, default=30_000)
+    ap.add_argument('--cpu-sample-bp', type=int, default=42_000)     # ~10 s of pure-Python work (the walk is super-linear)
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
