@@ -56,6 +56,10 @@ struct DevBuf {                 // grow-only device buffer: repeated builds on o
 };
 
 enum { EV_MAX = 64, EV_WALK = 48, MAX_SLICES = 32 };
+#define CTL_BYTES 65536
+#define CTL_SKETCH 0                       // HLL_M x u32
+#define CTL_CC (HLL_M * 4)                 // ChunkCounters
+#define CTL_CTR (HLL_M * 4 + 1024)         // DevCounters
 #define SLICE_BYTES (16ull << 20)         // host reads are uploaded in slices of this size
 
 struct dbg_handle {
@@ -93,6 +97,8 @@ struct dbg_handle {
     std::vector<dbg_contig_t> contigs;        // slow path (dropped starts, final=True enumeration)
     const dbg_contig_t *cview = nullptr;      // what dbg_contigs / materialize / scores read: `contigs`, or the
     uint64_t n_cview = 0;                     //   pinned buffer the device's records landed in (fast path)
+    unsigned char *ctl = nullptr;             // pinned 64 KB for the small control read-backs (sketch registers,
+                                              //   counters): a pageable destination would make every such copy a host sync
     void *pin = nullptr;                      // pinned host staging, grow-only
     size_t pin_cap = 0;
     std::vector<dbg_segment_t> segments;
@@ -240,8 +246,10 @@ static double hll_estimate(const std::vector<u32> &regs) {
 }
 
 static int fetch_counters(dbg_t *h) {
-    CK(cudaMemcpyAsync(&h->ctr, h->b_ctr.p, sizeof(DevCounters), cudaMemcpyDeviceToHost, h->stream));
+    void *dst = h->ctl ? (void *)(h->ctl + CTL_CTR) : (void *)&h->ctr;
+    CK(cudaMemcpyAsync(dst, h->b_ctr.p, sizeof(DevCounters), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    if (h->ctl) memcpy(&h->ctr, dst, sizeof(DevCounters));
     return DBG_OK;
 }
 
@@ -631,9 +639,12 @@ static int build_chunks(dbg_t *h, const u64 *d_off, int e0, int e1) {
     uint64_t est_chunks = 0;
     if (h->n_bases) {
         std::vector<u32> regs(HLL_M);
-        CK(cudaMemcpyAsync(regs.data(), h->b_hll.p, HLL_M * 4, cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaMemcpyAsync(&cc, d_cc, sizeof cc, cudaMemcpyDeviceToHost, h->stream));
+        void *r_dst = h->ctl ? (void *)(h->ctl + CTL_SKETCH) : (void *)regs.data();
+        void *c_dst = h->ctl ? (void *)(h->ctl + CTL_CC) : (void *)&cc;
+        CK(cudaMemcpyAsync(r_dst, h->b_hll.p, HLL_M * 4, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(c_dst, d_cc, sizeof cc, cudaMemcpyDeviceToHost, h->stream));
         TRY(fetch_counters(h));
+        if (h->ctl) { memcpy(regs.data(), r_dst, HLL_M * 4); memcpy(&cc, c_dst, sizeof cc); }
         est_chunks = (uint64_t)hll_estimate(regs) * ((sample_mask >> 6) + 1);
     } else {
         TRY(fetch_counters(h));
@@ -679,7 +690,9 @@ static int build_chunks(dbg_t *h, const u64 *d_off, int e0, int e1) {
         }
         h->chunks_streamed = false;                                  // a retry redoes phase 1 in one go
         const int c = ev_mark(h);
-        CK(cudaMemcpyAsync(&cc, d_cc, sizeof cc, cudaMemcpyDeviceToHost, h->stream));
+        void *c_dst = h->ctl ? (void *)(h->ctl + CTL_CC) : (void *)&cc;
+        void *s_dst = h->ctl ? (void *)(h->ctl + CTL_SKETCH) : (void *)sketch.data();
+        CK(cudaMemcpyAsync(c_dst, d_cc, sizeof cc, cudaMemcpyDeviceToHost, h->stream));
         // ---- phase 2a right behind it (no host round trip in between): sketch of the node keys of the
         // distinct chunks -> node table size; wasted only when the chunk table turns out to have overflowed
         ex_grid = cdiv(cdiv(n_cslots + n_list, 32), DBG_WARPS);
@@ -696,10 +709,11 @@ static int build_chunks(dbg_t *h, const u64 *d_off, int e0, int e1) {
                    ptr<const CS>(h->b_clist), n_list, k, ptr<uint4>(h->b_h8), (S *)nullptr, 0u, 0u, 0u,
                    ptr<u32>(h->b_hll), h->batch_bits, d_ctr);
             CKK();
-            CK(cudaMemcpyAsync(sketch.data(), h->b_hll.p, HLL_M * 4, cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaMemcpyAsync(s_dst, h->b_hll.p, HLL_M * 4, cudaMemcpyDeviceToHost, h->stream));
         }
         const int d = ev_mark(h);
         CK(cudaStreamSynchronize(h->stream));
+        if (h->ctl) { memcpy(&cc, c_dst, sizeof cc); memcpy(sketch.data(), s_dst, HLL_M * 4); }
         ms_init += ev_ms(h, a, b);
         ms_insert += ev_ms(h, b, d);
         st.ms_chunk_insert += ev_ms(h, b, c);
@@ -862,8 +876,10 @@ static int build_impl(dbg_t *h, const u8 *d_bases, const u64 *d_off) {
                     // units whose masks (32 spans + 1) and string overhang (3 words) are complete
                     const uint64_t u1 = last ? cdiv(h->n_bases, DBG_UNIT) : (s_done >= 36 ? (s_done - 4) / 32 : 0);
                     if (u1 > u_done) {
-                        CK(cudaMemcpyAsync(regs.data(), h->b_hll.p, HLL_M * 4, cudaMemcpyDeviceToHost, h->stream));
+                        void *r_dst = h->ctl ? (void *)(h->ctl + CTL_SKETCH) : (void *)regs.data();
+                        CK(cudaMemcpyAsync(r_dst, h->b_hll.p, HLL_M * 4, cudaMemcpyDeviceToHost, h->stream));
                         CK(cudaStreamSynchronize(h->stream));              // the next slices are already on the wire
+                        if (h->ctl) memcpy(regs.data(), r_dst, HLL_M * 4);
                         const uint64_t est = (uint64_t)hll_estimate(regs) * ((h->sample_mask >> 6) + 1);
                         TRY(chunk_table_fit<W>(h, est));
                         TRY(launch_chunk_insert<W>(h, d_off, u_done, u1));
@@ -1465,6 +1481,7 @@ DBG_API int dbg_create_ex(dbg_t **out, int device, int k, int key_words) {
     for (int i = 0; i < EV_MAX; i++) cudaEventCreate(&h->ev[i]);
     for (int i = 0; i <= MAX_SLICES; i++) cudaEventCreate(&h->slice_ev[i]);
     cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
+    if (cudaMallocHost(&h->ctl, CTL_BYTES) != cudaSuccess) h->ctl = nullptr;
     if (reserve(h, h->b_ctr, sizeof(DevCounters)) != DBG_OK) {
         g_create_error = h->err;
         dbg_destroy(h);
@@ -1492,6 +1509,7 @@ DBG_API void dbg_destroy(dbg_t *h) {
 #else
     if (h->pin) cudaFreeHost(h->pin);
 #endif
+    if (h->ctl) cudaFreeHost(h->ctl);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
 }
