@@ -490,9 +490,9 @@ static uint32_t pass_count(dbg_t *h, uint64_t table_bytes) {
     // Partition passes: each pass owns a hash range, so the table region it touches is bounded.  A pass
     // re-reads every distinct chunk (32 + 16 bytes), so few large regions beat many L2-sized ones:
     // measured on B200, 312 MB table: 1 / 2 / 3 / 5 passes = 0.61 / 0.50 / 0.53 / 0.61 ms;
-    // 2.1 GB table: 6 passes 2.9 ms, 15 passes 3.4 ms.
+    // 2.1 GB table: 5 / 6 / 9 / 10 passes = 3.41 / 3.05 / 2.70 / 2.81 ms.
     uint64_t region = 160ull << 20;
-    if (table_bytes / 6 > region) region = table_bytes / 6;
+    if (table_bytes / 9 > region) region = table_bytes / 9;
     if (region > 512ull << 20) region = 512ull << 20;
     if (const char *e = getenv("DBG_B200_L2_REGION_BYTES")) {         // tuning / tests: force more passes
         const unsigned long long v = strtoull(e, nullptr, 10);
