@@ -151,18 +151,26 @@ def build(force=False, verbose=False):
     if not os.path.exists(nvcc):
         raise RuntimeError('nvcc not found; cannot build %s' % LIB_PATH)
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-o', LIB_PATH] + srcs
+    tmp = '%s.%d.tmp' % (LIB_PATH, os.getpid())        # several ranks may build at once: never expose a partial file
+    cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-o', tmp] + srcs
     subprocess.check_call(cmd)
+    os.replace(tmp, LIB_PATH)
     return LIB_PATH
 
 
 _lib = None
+_DEFAULT_LIB_PATH = LIB_PATH
 
 
 def get():
-    """The product library.  Raises if it has not been built; never substitutes anything."""
+    """The product library.  Raises if it has not been built; never substitutes anything.  (A missing
+    in-tree library is compiled on the spot when nvcc is there -- that is building the product, not
+    falling back.)"""
     global _lib
     if _lib is None:
+        if not os.path.exists(LIB_PATH) and LIB_PATH == _DEFAULT_LIB_PATH and \
+                (shutil.which('nvcc') or os.path.exists('/usr/local/cuda/bin/nvcc')):
+            build()
         if not os.path.exists(LIB_PATH):
             raise RuntimeError(
                 'dbg_b200: %s is missing. Build it with `python -c "import __graft_entry__ as g; '
