@@ -419,7 +419,7 @@ def run_dbg(args, cfg, rank, local_rank, world):
                      'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
                      'bytes_per_window': b_build, 'kernel_ms': ms_table},
         'e2e': {'value': e2e_value, 'unit': 'k-mers/s', 'h2d_bytes_per_step': int(n_bases + 8 * (n_reads + 1)),
-                'd2h_bytes_per_step': int(32 * st.n_starts + 2 * 4096 * 4 + 4 * 128)   # contig records + 2 sketches + counters, 'ms_per_step': ms_e2e / args.steps,
+                'd2h_bytes_per_step': int(32 * st.n_starts + 2 * 4096 * 4 + 4 * 128), 'ms_per_step': ms_e2e / args.steps,
                 'ms_h2d': h2d_stage, 'api': 'dbg_build (host pointers, pinned) + dbg_walk + dbg_contigs'},
         'gpu_launches': launches * args.steps,
         'gpu_launches_per_step': launches,
