@@ -41,6 +41,8 @@ CONFIGS = {
                     '(one batched pass)'),
     'c5s': dict(G=20_000_000, L=150, cov=30, err=0.0, k=63, thr=2, seed=1005,
                 name='configs[4] shape at 20 Mb: 150 bp reads 30x, k=63 (128-bit k-mers)'),
+    'c5': dict(G=100_000_000, L=150, cov=30, err=0.0, k=63, thr=2, seed=1005,
+               name='configs[4] shape on ONE GPU: 100 Mb genome, 150 bp reads 30x, k=63 (128-bit k-mers)'),
 }
 ASCII = np.frombuffer(b'ACGT', dtype=np.uint8)
 
