@@ -45,7 +45,6 @@
 #define DBG_ABI_VERSION 1
 #define MAX_ENUM_CONTIGS (1ull << 26)
 #define MAX_ENUM_STEPS (1ull << 32)
-#define L2_REGION_BYTES (72ull << 20)        // table bytes one insert pass may touch (B200 L2: 126 MB)
 
 // -------------------------------------------------------------------------------------------------
 // handle
@@ -87,7 +86,7 @@ struct dbg_handle {
     uint32_t n_batches = 0;
     DevBuf b_bases, b_off, b_packed, b_tile, b_table, b_flags, b_kept, b_succ, b_link, b_ctr, b_hll,
            b_order, b_tag, b_tag2, b_slot, b_slot2, b_sorttmp, b_branch, b_starts, b_pulled, b_readflags,
-           b_recs, b_cnt32, b_off64, b_contig, b_junction, b_split, b_h8, b_chunk, b_bitmap, b_stmask, b_vmask,
+           b_recs, b_cnt32, b_off64, b_contig, b_junction, b_split, b_h8, b_bitmap, b_stmask, b_vmask,
            b_spanread, b_cc, b_ctable, b_clist, b_super, b_readbatch, b_ctable2, b_scratch[6];
     DevCounters ctr;
     dbg_stats_t st;
@@ -355,121 +354,6 @@ static int tip_prune(dbg_t *h) {
     }
     return DBG_OK;
 }
-
-// ---- per-window table build (k_estimate + k_insert passes); kept as the A/B baseline of the chunk build ----
-template <int W>
-static int build_windows(dbg_t *h, const u64 *d_off, int e0, int e1) {
-    typedef Slot<W> S;
-    const int k = h->k;
-    dbg_stats_t &st = h->st;
-    DevCounters *d_ctr = ptr<DevCounters>(h->b_ctr);
-    // ---- table sizing: HyperLogLog estimate of the distinct node count ----
-    uint64_t est = 0;
-    if (h->n_bases) {
-        TRY(reserve(h, h->b_hll, HLL_M * 4));
-        CK(cudaMemsetAsync(h->b_hll.p, 0, HLL_M * 4, h->stream));
-        TRY(reserve(h, h->b_h8, h->n_tiles * DBG_TILE));
-        TRY(reserve(h, h->b_chunk, h->n_tiles * (DBG_TILE / DBG_WPT) * 4));
-        LAUNCH(k_estimate<W>, h->n_tiles, DBG_BLOCK, h->stream, ptr<const u64>(h->b_packed), d_off,
-               ptr<const u32>(h->b_tile), h->n_bases, k, ptr<u32>(h->b_hll), ptr<u8>(h->b_h8), ptr<u32>(h->b_chunk));
-        CKK();
-        std::vector<u32> regs(HLL_M);
-        CK(cudaMemcpyAsync(regs.data(), h->b_hll.p, HLL_M * 4, cudaMemcpyDeviceToHost, h->stream));
-        TRY(fetch_counters(h));
-        est = (uint64_t)hll_estimate(regs);
-    } else {
-        TRY(fetch_counters(h));
-    }
-    if (h->ctr.bad_alphabet) return fail(h, DBG_ERR_ALPHABET, "a read holds a byte other than A/C/G/T");
-    if (h->ctr.too_long) return fail(h, DBG_ERR_OVERFLOW, "a read is longer than 2^32-1 bases");
-    st.n_windows = h->ctr.n_windows;
-    st.hll_estimate = est;
-    const int e2 = ev_mark(h);
-
-    // ---- node table (kernel 3): upsert every node occurrence ----
-    const uint64_t max_nodes = st.n_windows + h->n_reads;             // every window + last k-mer per read
-    uint64_t want = (uint64_t)((double)est * 1.06) + 64;              // HLL std error at 2^12 registers: 1.6 %
-    if (want > max_nodes) want = max_nodes;
-    uint64_t n_slots = want * 2 + 1024;                               // load factor <= 0.5
-    float ms_init = 0, ms_insert = 0;
-    for (int attempt = 0;; attempt++) {
-        if (n_slots >= 0xFFFFFFF0ull) return fail(h, DBG_ERR_OVERFLOW, "node table would exceed 2^32 slots");
-        h->n_slots = n_slots;
-        TRY(reserve(h, h->b_table, n_slots * sizeof(S)));
-        const int a = ev_mark(h);
-        LAUNCH(k_table_init<W>, blocks_for(n_slots), DBG_BLOCK, h->stream, ptr<S>(h->b_table), n_slots);
-        CKK();
-        const int b = ev_mark(h);
-        if (st.n_windows) {
-            // partition passes: each pass owns a hash range whose table region stays L2-resident
-            // measured: 72 MB regions are best for a 0.3 GB table, 144 MB for a 2 GB one (each pass also
-            // re-reads one hash byte per window, so very many passes cost more than some L2 misses)
-            uint64_t region = (uint64_t)L2_REGION_BYTES;
-            if (n_slots * sizeof(S) / 14 > region) region = n_slots * sizeof(S) / 14;
-            if (region > 192ull << 20) region = 192ull << 20;
-            if (const char *e = getenv("DBG_B200_L2_REGION_BYTES")) {     // tuning / tests: force more passes
-                const unsigned long long v = strtoull(e, nullptr, 10);
-                if (v >= 64) region = v;
-            }
-            uint32_t n_parts = (uint32_t)cdiv(n_slots * sizeof(S), region);
-            if (n_parts < 1) n_parts = 1;
-            st.n_insert_passes = n_parts;
-            if (n_parts > 255) n_parts = 255;
-            // persistent-style grid: each block owns a contiguous run of tiles
-            int sms = 148;
-            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
-            // persistent-style grid: each block owns a contiguous run of warp units
-            const uint64_t n_units = cdiv(h->n_bases, DBG_UNIT);
-            uint64_t grid = (uint64_t)sms * 16;
-            size_t smem_pad = 0;                                         // tuning: extra smem = fewer blocks, more L1
-            if (const char *e = getenv("DBG_B200_INSERT_SMEM_PAD")) smem_pad = (size_t)strtoull(e, nullptr, 10);
-#ifndef DBG_EMU
-            if (const char *e = getenv("DBG_B200_INSERT_CARVEOUT"))       // tuning: % of the unified L1 given to smem
-                cudaFuncSetAttribute(k_insert<W>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e));
-#endif
-            if (const char *e = getenv("DBG_B200_INSERT_GRID")) {        // tuning / tests
-                const unsigned long long v = strtoull(e, nullptr, 10);
-                if (v >= 1) grid = v;
-            }
-            if (grid > cdiv(n_units, DBG_WARPS)) grid = cdiv(n_units, DBG_WARPS);
-            const uint64_t units_per_block = cdiv(n_units, grid);
-            grid = cdiv(n_units, units_per_block);
-            for (uint32_t part = 0; part < n_parts; part++) {
-                // hash bytes 0..254 (255 = not a window) split evenly over the passes
-                const uint32_t lo8 = part * 255u / n_parts;
-                const uint32_t hi8 = (part + 1) * 255u / n_parts - 1;
-                LAUNCH_SMEM(k_insert<W>, grid, DBG_BLOCK, smem_pad, h->stream, ptr<const u64>(h->b_packed), h->n_words + 4,
-                       d_off, h->n_reads, ptr<const u32>(h->b_chunk), ptr<const u8>(h->b_h8), h->n_bases, n_units,
-                       units_per_block, k,
-                       ptr<S>(h->b_table), (u32)n_slots, h->read_idx_base, lo8, hi8 - lo8, d_ctr);
-                CKK();
-            }
-        }
-        const int c = ev_mark(h);
-        TRY(fetch_counters(h));
-        ms_init += ev_ms(h, a, b);
-        ms_insert += ev_ms(h, b, c);
-        if (!h->ctr.overflow) break;
-        if (attempt >= 6) return fail(h, DBG_ERR_NOMEM, "node table overflowed repeatedly");
-        n_slots *= 2;                                                  // estimate was low: rebuild larger
-        CK(cudaMemsetAsync(&d_ctr->overflow, 0, 4, h->stream));
-        h->n_ev -= 3;
-    }
-    st.ms_pack = ev_ms(h, e0, e1);
-    st.ms_estimate = ev_ms(h, e1, e2);
-    st.ms_table_init = ms_init;
-    st.ms_insert = ms_insert;
-    st.table_slots = n_slots;
-    st.table_bytes = n_slots * sizeof(S);
-    {
-        const int e_end = ev_mark(h);
-        CK(cudaStreamSynchronize(h->stream));
-        st.ms_build_total = ev_ms(h, e0, e_end);
-    }
-    h->table_ready = true;
-    return DBG_OK;
-}
-
 
 // ---- chunk table build (dbg_chunks.cuh): masks -> chunk table + boundary list -> node table ----
 struct ChunkGeom { int w, logw, m; };
@@ -784,9 +668,6 @@ static int build_impl(dbg_t *h, const u8 *d_bases, const u64 *d_off) {
     DevCounters *d_ctr = ptr<DevCounters>(h->b_ctr);
     const int e0 = ev_mark(h);
 
-    const char *mode = getenv("DBG_B200_BUILD");                      // "windows" = the per-window table build
-    const bool chunks = !(mode && !strcmp(mode, "windows"));
-
     // ---- read packing (kernel 1) + span masks (phase 0 of the chunk build), slice by slice ----
     h->n_words = cdiv(h->n_bases, 32);
     TRY(reserve(h, h->b_packed, (h->n_words + 4) * 8));
@@ -794,7 +675,7 @@ static int build_impl(dbg_t *h, const u8 *d_bases, const u64 *d_off) {
     h->n_tiles = cdiv(h->n_bases, DBG_TILE);
     TRY(reserve(h, h->b_tile, (h->n_tiles + 2) * 4));
     const uint64_t n_spans = h->n_words;
-    if (chunks) {
+    {
         const ChunkGeom geom = chunk_geom(k);
         h->geom_logw = geom.logw;
         h->geom_m = geom.m;
@@ -850,7 +731,7 @@ static int build_impl(dbg_t *h, const u8 *d_bases, const u64 *d_off) {
         // with the reads arriving in several slices, phase 1 of the chunk build (k_chunk_insert) also runs slice
         // by slice, hidden behind the copies; the chunk table is sized from the running sketch and grows
         // (k_chunk_rehash) when later slices bring more distinct chunks than the first ones promised
-        const bool stream_insert = chunks && h->host_bases && n_slices > 1;
+        const bool stream_insert = h->host_bases && n_slices > 1;
         std::vector<u32> regs(stream_insert ? HLL_M : 0);
         uint64_t s_done = 0, u_done = 0;
         for (uint64_t i = 0; i < n_slices; i++) {
@@ -862,7 +743,7 @@ static int build_impl(dbg_t *h, const u8 *d_bases, const u64 *d_off) {
             LAUNCH(k_pack, blocks_for(w1 - w0), DBG_BLOCK, h->stream, d_bases, h->n_bases, ptr<u64>(h->b_packed),
                    w0, w1, (int)(((uintptr_t)d_bases & 15) == 0), d_ctr);
             CKK();
-            if (chunks) {
+            {
                 const uint64_t s1 = last ? n_spans : (w1 > 2 ? w1 - 2 : 0);           // k_masks reads words s - 1 .. s + 1
                 if (s1 > s_done) {
                     LAUNCH(k_masks, blocks_for(s1 - s_done), DBG_BLOCK, h->stream, ptr<const u64>(h->b_packed), d_off,
@@ -898,10 +779,6 @@ static int build_impl(dbg_t *h, const u8 *d_bases, const u64 *d_off) {
     }
     const int e1 = ev_mark(h);
 
-    if (!chunks) {
-        if (h->d_read_batch) return fail(h, DBG_ERR_ARG, "the per-window build (DBG_B200_BUILD=windows) has no batched mode");
-        return build_windows<W>(h, d_off, e0, e1);
-    }
     return build_chunks<W>(h, d_off, e0, e1);
 }
 
@@ -957,7 +834,7 @@ static int graph_order_scan(dbg_t *h) {
     if ((h->build_flags & DBG_EXACT_ORDER) && st.n_multi) {
         TRY(side_set<W>(h, F_MULTI, st.n_multi, &h->order_cap, &h->order_bits));
         h->order_active = true;
-        if (h->n_bases && h->chunks_valid && !getenv("DBG_B200_ORDER_WINDOWS")) {
+        if (h->n_bases && h->chunks_valid) {
             // from the distinct chunks of the local reads (2 - 20 x fewer than windows)
             typedef ChunkSlot<W> CS;
             uint64_t g = blocks_for(h->n_cslots + h->n_clist);
@@ -965,11 +842,6 @@ static int graph_order_scan(dbg_t *h) {
             LAUNCH(k_order_chunks<W>, g, DBG_BLOCK, h->stream, ptr<const CS>(h->b_ctable), h->n_cslots,
                    ptr<const CS>(h->b_clist), h->n_clist, h->k, h->batch_bits, ptr<SideEntry<W>>(h->b_order),
                    h->order_cap, ptr<const u32>(h->b_bitmap), h->order_bits);
-            CKK();
-        } else if (h->n_bases) {
-            LAUNCH(k_order_scan<W>, h->n_tiles, DBG_BLOCK, h->stream, ptr<const u64>(h->b_packed), (const u64 *)h->d_off,
-                   ptr<const u32>(h->b_tile), h->n_bases, h->k, h->read_idx_base, ptr<SideEntry<W>>(h->b_order),
-                   h->order_cap, ptr<const u32>(h->b_bitmap), h->order_bits, (const u32 *)h->d_read_batch);
             CKK();
         }
     }
@@ -1497,7 +1369,7 @@ DBG_API void dbg_destroy(dbg_t *h) {
     DevBuf *all[] = {&h->b_bases, &h->b_off, &h->b_packed, &h->b_tile, &h->b_table, &h->b_flags, &h->b_kept,
                      &h->b_succ, &h->b_link, &h->b_ctr, &h->b_hll, &h->b_order, &h->b_tag, &h->b_tag2, &h->b_slot,
                      &h->b_slot2, &h->b_sorttmp, &h->b_branch, &h->b_starts, &h->b_pulled, &h->b_readflags,
-                     &h->b_recs, &h->b_cnt32, &h->b_off64, &h->b_contig, &h->b_junction, &h->b_split, &h->b_h8, &h->b_chunk, &h->b_bitmap,
+                     &h->b_recs, &h->b_cnt32, &h->b_off64, &h->b_contig, &h->b_junction, &h->b_split, &h->b_h8, &h->b_bitmap,
                      &h->b_stmask, &h->b_vmask, &h->b_spanread, &h->b_cc, &h->b_ctable, &h->b_clist, &h->b_super, &h->b_readbatch, &h->b_ctable2, &h->b_scratch[0],
                      &h->b_scratch[1], &h->b_scratch[2], &h->b_scratch[3], &h->b_scratch[4], &h->b_scratch[5]};
     for (DevBuf *b : all) if (b->p) cudaFree(b->p);

@@ -388,7 +388,8 @@ k_chunk_insert(const u64 *__restrict__ packed, u64 n_words_padded, const u64 *__
         __syncwarp();
         head1 = (head1 + take) & (CH_QCAP - 1);
         n1 -= take;
-        const u32 rel = ent & 1023u, n = ((ent >> 10) & 15u) + 1, term = (ent >> 14) & 1u;
+        const u32 rel = ent & 1023u, n = ((ent >> 10) & 15u) + 1;
+        u32 term = (ent >> 14) & 1u;
         ChunkKey<W> key;
         u64 tag = 0;
         bool boundary = false;
@@ -397,16 +398,22 @@ k_chunk_insert(const u64 *__restrict__ packed, u64 n_words_padded, const u64 *__
             u64 r = sh.c_read[w][sp];
             u32 pos = sh.c_pos[w][sp] + j;
             const u32 end = sh.c_end[w][sp];
+            u32 left = end - j;                                          // bases from the chunk start to its read's end (clamped)
             if (j >= end) {                                              // a read ends inside the span
                 const u32 end2 = sh.c_end2[w][sp], skip = sh.c_skip[w][sp];
-                if (skip && j < end2) { r += skip; pos = j - end; }      // ... and the chunk is in the next one
+                if (skip && j < end2) { r += skip; pos = j - end; left = end2 - j; }   // ... and the chunk is in the next one
                 else {                                                   // reads shorter than a span: ask off[]
                     const u64 c = ub + rel;
                     u64 re = __ldg(off + r + 1);
                     while (re <= c) { r++; re = __ldg(off + r + 1); }    // also skips empty reads
                     pos = (u32)(c - __ldg(off + r));
+                    left = (u32)(re - c < (u64)0xFFFF ? re - c : (u64)0xFFFF);
                 }
             }
+            // the last node has a successor only if its read goes on for one more base (debruijn.py:126).  The
+            // masks say so too whenever a non-node position separates two reads' nodes, i.e. for k >= 2; with
+            // k = 1 every base is a node and the next read's first base must not be taken for a successor.
+            if (left < n + (u32)k) term = 1u;
             tag = ((read_idx_base + r) << 32) | pos;
             boundary = pos == 0 || term;
             key = chunk_key_from_stream<W>(sh.words[w], rel, (int)n + k - (int)term, chunk_meta(n, term));

@@ -2,9 +2,9 @@
 //
 // Stage map (reference file:line -> kernel):
 //   read packing                       (new: 2-bit stream)          k_pack
-//   window loop   debruijn.py:123-144  (nodes, successor counts)    k_insert  (+ k_estimate sizing)
+//   window loop   debruijn.py:123-144  (nodes, successor counts)    dbg_chunks.cuh: k_masks, k_chunk_insert, k_expand
 //   degrees/prune debruijn.py:129-143, 150-166, 230-236             k_finalize
-//   tie order     debruijn.py:159-164  (Counter.most_common)        k_order_fill/scan/apply
+//   tie order     debruijn.py:159-164  (Counter.most_common)        k_side_fill, k_order_chunks, k_order_apply
 //   tip pruning   debruijn.py:169-186  (candidate paths)            k_tip_paths
 //   pull-out      debruijn.py:274-278                                k_pull_reads
 //   contig walk   debruijn.py:288-316, 326-347                      k_link_init, k_sublist, k_jump, k_emit
@@ -183,94 +183,8 @@ DBG_D void for_windows(const u64 *__restrict__ packed, const u64 *__restrict__ o
     }
 }
 
-// Warp-uniform variant for the hot kernels: every lane calls f for all DBG_WPT steps, with
-// `valid` false where the position is not a node occurrence, so f may use warp collectives.
-// The read-boundary bookkeeping is 32-bit and relative to the thread's first position.
-template <int W, typename F>
-DBG_D void for_windows_uniform(const u64 *__restrict__ packed, const u64 *__restrict__ off,
-                               const u32 *__restrict__ tile_first, u64 n_bases, int k, F f) {
-    typedef typename KeyOf<W>::type K;
-    const u64 tile = blockIdx.x;
-    u64 p0 = tile * DBG_TILE + (u64)threadIdx.x * DBG_WPT;
-    int n_here = 0;                                               // positions of this thread inside the stream
-    if (p0 < n_bases) n_here = (int)(n_bases - p0 < (u64)DBG_WPT ? n_bases - p0 : (u64)DBG_WPT);
-    else p0 = 0;                                                  // idle lane: harmless loads, never valid
-    u32 rlo = __ldg(tile_first + tile), rhi = __ldg(tile_first + tile + 1);
-    if (n_here == 0) rlo = rhi = 0;
-    while (rlo < rhi) {
-        u32 mid = rlo + ((rhi - rlo + 1) >> 1);
-        if (__ldg(off + mid) <= p0) rlo = mid; else rhi = mid - 1;
-    }
-    u32 r = rlo;
-    const u64 rs = __ldg(off + r);
-    u64 re = __ldg(off + r + 1);
-    const K mask = key_mask<W>(k);
-    K key = extract_key<W>(packed, p0, k);
-    const u32 nbw = extract_bases(packed, p0 + k, DBG_WPT);
-    const u64 CLAMP = 1u << 30;
-    int end = (int)(re - p0 < CLAMP ? re - p0 : CLAMP);           // read end, relative to p0
-    u32 pos0 = (u32)(p0 - rs);
-    bool long_enough = re - rs > (u64)k;
-    int lim = long_enough ? end - k : -1;                         // node occurrence iff j <= lim; edge iff j < lim
-#pragma unroll
-    for (int j = 0; j < DBG_WPT; j++) {
-        if (j == end && j < n_here) {                             // rare: a read ends inside this thread's span
-            do {
-                r++;
-                const u64 ne = __ldg(off + r + 1);
-                long_enough = ne - re > (u64)k;
-                pos0 = (u32)0 - (u32)end;
-                end = (int)(ne - p0 < CLAMP ? ne - p0 : CLAMP);
-                re = ne;
-            } while (j >= end);                                   // skips empty reads
-            lim = long_enough ? end - k : -1;
-        }
-        const u32 nb = (nbw >> (2 * (DBG_WPT - 1 - j))) & 3u;
-        f(j, j <= lim && j < n_here, key, r, pos0 + (u32)j, j < lim, nb);
-        key = key_roll(key, nb, mask);
-    }
-}
-
 // ---------------------------------------------------------------------------------------------
-// k_estimate: HyperLogLog over node keys (2^12 registers) -> distinct-node estimate that sizes
-// the table.  Registers saturate after a few thousand keys, so almost every window is a plain
-// load and no atomic.
-// ---------------------------------------------------------------------------------------------
-// Pass 0 of the table build.  Besides the HLL registers it leaves, for every stream position, one
-// byte = top 8 bits of the node key's slot hash (255 = "not a node occurrence", 254 = hash bytes
-// 254 and 255), and for every 16-position chunk the index of the read holding its first position.
-// The insert passes select their windows from those bytes instead of re-rolling every key.
-template <int W>
-__global__ void __launch_bounds__(DBG_BLOCK) k_estimate(const u64 *__restrict__ packed, const u64 *__restrict__ off,
-                                                        const u32 *__restrict__ tile_first, u64 n_bases, int k,
-                                                        u32 *regs, u8 *__restrict__ h8, u32 *__restrict__ chunk_read) {
-    typedef typename KeyOf<W>::type K;
-    u32 acc[DBG_WPT / 4];
-#pragma unroll
-    for (int i = 0; i < DBG_WPT / 4; i++) acc[i] = 0;
-    u32 r0 = 0;
-    for_windows_uniform<W>(packed, off, tile_first, n_bases, k,
-        [&](int j, bool valid, K key, u32 r, u32, bool, u32) {
-            if (j == 0) r0 = r;
-            u32 h = hash32_key(key);
-            u32 idx = h >> (32 - HLL_P);
-            u32 rank = (u32)__clz((int)((h << HLL_P) | (1u << (HLL_P - 1)))) + 1;
-            if (valid && regs[idx] < rank) atomicMax(&regs[idx], rank);
-            u32 b = h >> 24;
-            b = valid ? (b > 254u ? 254u : b) : 255u;
-            acc[j >> 2] |= b << (8 * (j & 3));
-        });
-    const u64 p0 = (u64)blockIdx.x * DBG_TILE + (u64)threadIdx.x * DBG_WPT;
-    if (p0 < n_bases) {
-        uint4 *dst = reinterpret_cast<uint4 *>(h8 + p0);                 // h8 is padded to whole tiles
-#pragma unroll
-        for (int i = 0; i < DBG_WPT / 16; i++) dst[i] = make_uint4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
-        chunk_read[p0 / DBG_WPT] = r0;
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// table init + insert
+// table init
 // ---------------------------------------------------------------------------------------------
 template <int W>
 __global__ void __launch_bounds__(DBG_BLOCK) k_table_init(Slot<W> *table, u64 n_slots) {
@@ -283,270 +197,8 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_table_init(Slot<W> *table, u64 n_
     table[i] = s;
 }
 
-// Partition passes: the table (32 B x 2 slots per node) is larger than the 126 MB L2 for any
-// genome above ~2 Mb, and a random 32-byte slot touch that misses L2 costs a 64-byte DRAM burst in
-// and, later, a dirty sector out (measured: 9.7 GB of DRAM traffic for 99 M windows, 2.2 TB/s).
-// So the windows are replayed n_parts times; pass `part` only touches keys whose home slot lies in
-// [part, part + 1) * n_slots / n_parts, a region sized to stay L2-resident, and the rolling key +
-// multiply-shift hash of the other windows (about 25 instructions) is all those cost.
-// Insert pass.  A pass owns the keys whose hash byte lies in [lo8, lo8 + span8]; their home slots
-// form a contiguous table region small enough to stay L2-resident while every read is replayed.
-// Each warp works through units of DBG_UNIT = 1024 stream positions on its own (no block barrier):
-//   stage   the unit's 2-bit words (+ k bases of overhang) and, per 16-position chunk, the read
-//           index / position-in-read / distance to the read's end go to shared memory with
-//           coalesced loads, so nothing below touches L2 except the table itself
-//   select  each lane loads the 16 hash bytes of its chunks (128-bit loads) and the positions of
-//           the bytes in range are compacted into ring Q1 (warp prefix sum for the offsets)
-//   expand  32 positions at a time, one per lane: key, next base and tag are rebuilt from the
-//           staged words, the home slot is hashed, and ONE probe is made
-//   probe   a lane whose slot holds another key does not loop: it re-queues (key, tag, slot + 1)
-//           in ring Q2, which is drained 32 at a time the same way
-// so table traffic always runs with (close to) 32 busy lanes, without divergent probe loops, and
-// costs two L2 sector accesses per window (slot load, counter RED) plus the retries.
 #define DBG_WARPS (DBG_BLOCK / 32)
-#define DBG_UNIT 1024                     // positions per warp work unit
-#define DBG_UNIT_CHUNKS (DBG_UNIT / DBG_WPT)
-#define DBG_UNIT_WORDS (DBG_UNIT / 32 + 4) // staged 2-bit words: the unit + 63 + 16 bases of overhang
-#define DBG_ILP 1                         // entries per lane per drain: two slot loads in flight
-#define DBG_DRAIN (32 * DBG_ILP)
-#define DBG_Q1CAP 512                     // >= DBG_DRAIN - 1 + 256
-#define DBG_Q2CAP 64                      // >= 2 * DBG_DRAIN
-#define DBG_MAX_PROBES 4096u
-template <int W> struct InsertShared {
-    u64 words[DBG_WARPS][DBG_UNIT_WORDS];
-    u32 c_read[DBG_WARPS][DBG_UNIT_CHUNKS];   // read index at the chunk's first position
-    u32 c_pos[DBG_WARPS][DBG_UNIT_CHUNKS];    // position in that read
-    u16 c_end[DBG_WARPS][DBG_UNIT_CHUNKS];    // distance to that read's end (clamped)
-    u16 c_end2[DBG_WARPS][DBG_UNIT_CHUNKS];   // distance to the end of the next non-empty read (clamped)
-    u8 c_skip[DBG_WARPS][DBG_UNIT_CHUNKS];    // index of that read minus c_read (0 = unknown: use off[])
-    u16 pos[DBG_WARPS][DBG_Q1CAP];            // Q1: position inside the unit
-    typename KeyOf<W>::type key[DBG_WARPS][DBG_Q2CAP];
-    u64 tag[DBG_WARPS][DBG_Q2CAP];
-    u16 meta[DBG_WARPS][DBG_Q2CAP];           // probes so far << 3 | has_next << 2 | next base
-};
-
-// k bases starting at base `rel` of a staged word array (same layout as extract_key)
-template <int W> DBG_D typename KeyOf<W>::type staged_key(const u64 *words, u32 rel, int k);
-template <> DBG_D u64 staged_key<1>(const u64 *words, u32 rel, int k) {
-    const u32 w = rel >> 5;
-    const int s = 2 * (int)(rel & 31);
-    const u64 w0 = words[w], w1 = words[w + 1];
-    const u64 top = s ? ((w0 << s) | (w1 >> (64 - s))) : w0;
-    return top >> (64 - 2 * k);
-}
-template <> DBG_D K128 staged_key<2>(const u64 *words, u32 rel, int k) {
-    const u32 w = rel >> 5;
-    const int s = 2 * (int)(rel & 31);
-    const u64 w0 = words[w], w1 = words[w + 1], w2 = words[w + 2];
-    const u64 hi = s ? ((w0 << s) | (w1 >> (64 - s))) : w0;
-    const u64 lo = s ? ((w1 << s) | (w2 >> (64 - s))) : w1;
-    const int sh = 128 - 2 * k;
-    K128 r;
-    if (sh >= 64) { r.lo = sh == 64 ? hi : hi >> (sh - 64); r.hi = 0; }
-    else { r.lo = (lo >> sh) | (hi << (64 - sh)); r.hi = hi >> sh; }
-    return r;
-}
-
-// second half of a probe: the slot's key and tag have been loaded.  true = done
-template <int W>
-DBG_D bool probe_finish(Slot<W> *s, typename KeyOf<W>::type cur, u64 seen, typename KeyOf<W>::type key, u64 tag,
-                        u32 meta) {
-    typedef typename KeyOf<W>::type K;
-    if (cur != key) {
-        if (cur != empty_key<W>()) return false;
-        K old = cas_key(&s->key, empty_key<W>(), key);
-        if (old == empty_key<W>()) seen = ~0ULL;
-        else if (old == key) seen = __ldcg(&s->tag);
-        else return false;
-    }
-    if (tag < seen) atomicMin(&s->tag, tag);                             // first occurrence
-    if (meta & 4u) atomicAdd(&s->cnt[meta & 3u], 1u);                    // debruijn.py:132/136
-    return true;
-}
-
-#ifndef DBG_INSERT_MIN_BLOCKS
-#define DBG_INSERT_MIN_BLOCKS 6
-#endif
-template <int W>
-__global__ void __launch_bounds__(DBG_BLOCK, DBG_INSERT_MIN_BLOCKS) k_insert(const u64 *__restrict__ packed, u64 n_words_padded,
-                                                      const u64 *__restrict__ off, u64 n_reads,
-                                                      const u32 *__restrict__ chunk_read, const u8 *__restrict__ h8,
-                                                      u64 n_bases, u64 n_units, u64 units_per_block, int k,
-                                                      Slot<W> *table, u32 n_slots, u64 read_idx_base,
-                                                      u32 lo8, u32 span8, DevCounters *ctr) {
-    typedef typename KeyOf<W>::type K;
-    __shared__ InsertShared<W> sh;
-    const u32 lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const u32 lt = (1u << lane) - 1;
-    u32 head1 = 0, n1 = 0, head2 = 0, n2 = 0;                            // warp-uniform ring state
-    bool overflow = false;
-    u64 ub = 0;                                                          // first stream position of the unit
-
-    // requeue a lane's entry in Q2 (all lanes call; `again` says which need it).  The slot to
-    // probe next is not stored: it is home(key) + probes so far.
-    auto requeue = [&](bool again, K key, u64 tag, u32 meta) {
-        const u32 m = __ballot_sync(0xFFFFFFFFu, again);
-        if (again) {
-            const u32 e = (head2 + n2 + __popc(m & lt)) & (DBG_Q2CAP - 1);
-            sh.key[w][e] = key; sh.tag[w][e] = tag; sh.meta[w][e] = (u16)meta;
-        }
-        n2 += __popc(m);
-    };
-    // probe DBG_ILP entries per lane: all slot loads are issued before the first is looked at
-    auto probe_all = [&](const bool (&act)[DBG_ILP], K (&key)[DBG_ILP], u64 (&tag)[DBG_ILP], u32 (&meta)[DBG_ILP]) {
-        Slot<W> *s[DBG_ILP];
-        K cur[DBG_ILP];
-        u64 seen[DBG_ILP];
-#pragma unroll
-        for (int i = 0; i < DBG_ILP; i++) {
-            u64 idx = slot_home(hash32_key(key[i]), n_slots) + (meta[i] >> 3);
-            if (idx >= n_slots) idx -= n_slots;
-            s[i] = &table[act[i] ? idx : 0];
-            cur[i] = load_key_tag(s[i], &seen[i]);
-        }
-#pragma unroll
-        for (int i = 0; i < DBG_ILP; i++) {
-            bool again = false;
-            if (act[i]) {
-                again = !probe_finish<W>(s[i], cur[i], seen[i], key[i], tag[i], meta[i]);
-                if (again) {
-                    meta[i] += 8u;
-                    if ((meta[i] >> 3) >= DBG_MAX_PROBES) { overflow = true; again = false; }
-                }
-            }
-            requeue(again, key[i], tag[i], meta[i]);
-        }
-    };
-    auto drain2 = [&]() {                                                // up to DBG_DRAIN retries
-        __syncwarp();
-        const u32 take = n2 < (u32)DBG_DRAIN ? n2 : (u32)DBG_DRAIN;
-        bool act[DBG_ILP]; K key[DBG_ILP]; u64 tag[DBG_ILP]; u32 meta[DBG_ILP];
-#pragma unroll
-        for (int i = 0; i < DBG_ILP; i++) {
-            const u32 e = (head2 + 32 * i + lane) & (DBG_Q2CAP - 1);
-            act[i] = 32 * i + lane < take;
-            key[i] = sh.key[w][e]; tag[i] = sh.tag[w][e]; meta[i] = sh.meta[w][e];
-        }
-        __syncwarp();
-        head2 = (head2 + take) & (DBG_Q2CAP - 1);
-        n2 -= take;
-        probe_all(act, key, tag, meta);
-    };
-    auto drain1 = [&]() {                                                // up to DBG_DRAIN fresh positions
-        __syncwarp();
-        const u32 take = n1 < (u32)DBG_DRAIN ? n1 : (u32)DBG_DRAIN;
-        bool act[DBG_ILP]; K key[DBG_ILP]; u64 tag[DBG_ILP]; u32 meta[DBG_ILP];
-#pragma unroll
-        for (int i = 0; i < DBG_ILP; i++) {
-            act[i] = 32 * i + lane < take;
-            const u32 rel = act[i] ? sh.pos[w][(head1 + 32 * i + lane) & (DBG_Q1CAP - 1)] : 0;
-            const u32 c = rel / DBG_WPT, j = rel % DBG_WPT;
-            u32 r = sh.c_read[w][c], pos = sh.c_pos[w][c] + j;
-            const u32 end = sh.c_end[w][c];
-            bool has_next = j + (u32)k < end;
-            if (j >= end && act[i]) {                                    // a read ends inside the chunk
-                const u32 end2 = sh.c_end2[w][c], skip = sh.c_skip[w][c];
-                if (skip && j < end2) {                                  // ... and the window is in the next one
-                    r += skip; pos = j - end; has_next = j + (u32)k < end2;
-                } else {                                                 // reads shorter than a chunk: ask off[]
-                    const u64 p = ub + rel;
-                    u64 rs, re = __ldg(off + r + 1);
-                    do { r++; rs = re; re = __ldg(off + r + 1); } while (p >= re);
-                    pos = (u32)(p - rs);
-                    has_next = (u64)pos + (u64)k < re - rs;
-                }
-            }
-            key[i] = staged_key<W>(sh.words[w], rel, k);
-            const u32 q = rel + (u32)k;
-            meta[i] = (has_next ? 4u : 0u) | ((u32)(sh.words[w][q >> 5] >> (62 - 2 * (q & 31))) & 3u);
-            tag[i] = ((read_idx_base + r) << 32) | pos;
-        }
-        __syncwarp();
-        head1 = (head1 + take) & (DBG_Q1CAP - 1);
-        n1 -= take;
-        probe_all(act, key, tag, meta);
-    };
-
-    const u64 unit_begin = (u64)blockIdx.x * units_per_block;
-    u64 unit_end = unit_begin + units_per_block;
-    if (unit_end > n_units) unit_end = n_units;
-    for (u64 u = unit_begin + w; u < unit_end; u += DBG_WARPS) {
-        ub = u * DBG_UNIT;
-        __syncwarp();
-        // ---- stage the unit
-        for (u32 i = lane; i < DBG_UNIT_WORDS; i += 32) {
-            const u64 wi = ub / 32 + i;
-            sh.words[w][i] = wi < n_words_padded ? __ldg(packed + wi) : 0;
-        }
-        u32 mask[DBG_UNIT_CHUNKS / 32];
-#pragma unroll
-        for (int t = 0; t < DBG_UNIT_CHUNKS / 32; t++) {
-            const u32 c = (u32)t * 32 + lane;
-            const u64 p0 = ub + (u64)c * DBG_WPT;
-            u32 m = 0, r = 0, pos0 = 0, end = 0, end2 = 0, skip = 0;
-            if (p0 < n_bases) {
-                r = __ldg(chunk_read + p0 / DBG_WPT);
-                const u64 rs = __ldg(off + r), re = __ldg(off + r + 1);
-                pos0 = (u32)(p0 - rs);
-                end = (u32)(re - p0 < (u64)0xFFFF ? re - p0 : (u64)0xFFFF);
-                if (end < (u32)DBG_WPT) {                                // the chunk runs into the next read(s)
-                    u64 r2 = r + 1, re2 = re;
-                    while (r2 < n_reads && skip < 200u) {
-                        re2 = __ldg(off + r2 + 1);
-                        skip++;
-                        if (re2 > re) break;                             // first non-empty read after r
-                        r2++;
-                    }
-                    if (re2 > re && skip < 200u) end2 = (u32)(re2 - p0 < (u64)0xFFFF ? re2 - p0 : (u64)0xFFFF);
-                    else skip = 0;
-                }
-                const uint4 v = __ldg(reinterpret_cast<const uint4 *>(h8 + p0));
-                const u32 wv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                for (int cc = 0; cc < 4; cc++)
-#pragma unroll
-                    for (int bb = 0; bb < 4; bb++)
-                        if ((((wv[cc] >> (8 * bb)) & 0xFFu) - lo8) <= span8) m |= 1u << (4 * cc + bb);
-            }
-            sh.c_read[w][c] = r; sh.c_pos[w][c] = pos0; sh.c_end[w][c] = (u16)end;
-            sh.c_end2[w][c] = (u16)end2; sh.c_skip[w][c] = (u8)skip;
-            mask[t] = m;
-        }
-        __syncwarp();
-        // ---- select (8 positions per lane at a time, so Q1 takes at most 256 entries) + drain
-#pragma unroll
-        for (int t = 0; t < DBG_UNIT_CHUNKS / 32; t++) {
-#pragma unroll
-            for (int half = 0; half < 2; half++) {
-                u32 m8 = (mask[t] >> (8 * half)) & 0xFFu;
-                u32 cnt = __popc(m8), incl = cnt;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const u32 x = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-                    if (lane >= (u32)d) incl += x;
-                }
-                const u32 total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-                u32 o = head1 + n1 + incl - cnt;
-                const u32 rel0 = ((u32)t * 32 + lane) * DBG_WPT + 8 * half;
-                while (m8) {
-                    const u32 j = (u32)__ffs((int)m8) - 1;
-                    m8 &= m8 - 1;
-                    sh.pos[w][o & (DBG_Q1CAP - 1)] = (u16)(rel0 + j);
-                    o++;
-                }
-                n1 += total;
-                while (n1 >= (u32)DBG_DRAIN) {
-                    drain1();
-                    while (n2 >= (u32)DBG_DRAIN) drain2();
-                }
-            }
-        }
-        while (n1) drain1();                                             // Q1 entries die with the staged unit
-        while (n2 >= (u32)DBG_DRAIN) drain2();
-    }
-    while (n2) drain2();
-    if (overflow) ctr->overflow = 1;
-}
+#define DBG_UNIT 1024                     // stream positions per warp work unit (k_chunk_insert)
 
 // ---------------------------------------------------------------------------------------------
 // k_finalize: per slot, degrees + pruningEdges + branch flag + the single surviving successor.
@@ -651,24 +303,6 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_side_fill(const Slot<W> *__restri
     if (e != NONE64) st[e].slot = i;
     const u32 b = hash32_key(key) >> (32 - bits);
     atomicOr(&bm[b >> 5], 1u << (b & 31));
-}
-
-template <int W>
-__global__ void __launch_bounds__(DBG_BLOCK) k_order_scan(const u64 *__restrict__ packed, const u64 *__restrict__ off,
-                                                          const u32 *__restrict__ tile_first, u64 n_bases, int k,
-                                                          u64 read_idx_base, SideEntry<W> *st, u64 cap,
-                                                          const u32 *__restrict__ bm, int bits,
-                                                          const u32 *__restrict__ read_batch) {
-    typedef typename KeyOf<W>::type K;
-    for_windows<W, true>(packed, off, tile_first, n_bases, k,
-        [&](K key, u32 r, u32 pos, bool has_next, u32 nb) {
-            if (read_batch) key = key_add_batch(key, __ldg(read_batch + r), k);
-            if (!has_next || !bitmap_test(bm, bits, hash32_key(key))) return;
-            u64 e = side_locate<W>(st, cap, key, false);
-            if (e == NONE64) return;                                     // not a multi-successor node
-            u64 tag = ((read_idx_base + r) << 32) | pos;
-            if (tag < __ldcg(&st[e].first[nb])) atomicMin(&st[e].first[nb], tag);
-        });
 }
 
 template <int W>

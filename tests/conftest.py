@@ -40,3 +40,12 @@ def backend(request, monkeypatch):
         monkeypatch.setattr(_native, '_lib', None)
         _native.get()                       # fails loudly if the CUDA library is not built
     return request.param
+
+
+@pytest.fixture
+def backend_gpu(monkeypatch):
+    """The product library on a real GPU, nothing else (tests marked ``gpu``)."""
+    from dbg_b200 import _native
+    monkeypatch.setattr(_native, '_lib', None)
+    _native.get()                           # fails loudly if the CUDA library is not built
+    return 'gpu'

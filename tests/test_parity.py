@@ -71,11 +71,30 @@ def test_random_vs_oracle(backend, seed, big):
         n += 1
 
 
+def test_k1_every_base_is_a_node(backend):
+    """k = 1: no non-node position separates the nodes of two reads, so the end of a read's last chunk
+    must come from the read structure (the masks alone gave a phantom edge 'CG' for
+    ['AC', 'GT'])."""
+    r = random.Random(4242)
+    for _ in range(60):
+        alphabet = r.choice(['ACGT', 'AC', 'ACG'])
+        reads = [''.join(r.choice(alphabet) for _ in range(r.choice([0, 1, 2, 3, 5, 9, 33, 40]))) for _ in range(r.choice([1, 2, 5, 20, 70]))]
+        thr, final = r.choice([1, 2, 3, 0.5]), r.random() < 0.3
+        try:
+            exp = dbg_oracle.snapshot(reads, 1, thr, final, max_paths=200)
+        except RuntimeError:
+            continue
+        got = util.product_snapshot(reads, 1, thr, final)
+        util.assert_same(got, exp, 'k=1 %r' % ((reads, thr, final),))
+
+
 def test_edge_cases(backend):
     import debruijn as db
     cases = [
         ([], 5, 2, False),                                  # no reads at all
         ([''], 5, 2, False),                                # one empty read
+        (['AC', 'GT'], 1, 2, False),                        # k = 1: every base is a node; no edge joins two reads
+        (['A', 'C', 'ACGT', 'T', 'TTTT', 'GA'], 1, 2, True),
         (['ACG', 'AC', ''], 3, 2, False),                   # every read has len <= k (debruijn.py:126)
         (['ACGT'], 3, 2, False),                            # exactly one window
         (['AAAAAAAAAA'], 3, 2, False),                      # self loop: the only start is on a cycle (:289)

@@ -56,7 +56,7 @@ def assert_same(got, exp, where=''):
 def random_dna_case(r: random.Random, big=False):
     """Small random problems with branches, tips, cycles, duplicates, short and empty reads."""
     alphabet = r.choice(['ACGT', 'ACGT', 'ACG', 'AC'])
-    k = r.choice([2, 3, 4, 5, 6, 7, 9, 12] if not big else [15, 21, 31, 32, 33, 47, 63])
+    k = r.choice([1, 2, 3, 4, 5, 6, 7, 9, 12] if not big else [15, 21, 31, 32, 33, 47, 63])
     G = r.choice([12, 20, 30, 50, 80, 120, 300]) if not big else r.choice([200, 400, 800])
     genome = ''.join(r.choice(alphabet) for _ in range(G))
     if r.random() < 0.4:
