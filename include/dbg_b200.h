@@ -183,6 +183,43 @@ int dbg_chunk_table_reset(dbg_t *h, uint64_t expected_chunks);
 int dbg_chunk_merge_records(dbg_t *h, const uint64_t *d_records, uint64_t n);
 int dbg_chunk_expand(dbg_t *h);
 
+/* ---- owner-computes graph stages and contig walk on a SHARDED node table ----
+ * After dbg_chunk_expand a rank holds the shard of the node table whose minimizers it owns.  With
+ * dbg_shard_config(rank, n_ranks) set, dbg_graph_stage 0 / 1 / 2 run on the shard alone (degrees,
+ * pruningEdges, tie order, branch flags and start list are per-node work, debruijn.py:129-166, 230-236; a kept
+ * successor owned by another rank makes its node an EXIT instead of an internal-consistency fault).  Stage 2
+ * refuses a shard with branch nodes: ordered tip pruning (debruijn.py:241-254) needs the neighbourhoods on one
+ * rank -- gather the shards (dbg_export_records / dbg_merge_records) for such inputs.
+ * The contig walk (debruijn.py:288-347) then runs as a two-level list ranking, the caller moving three small
+ * buffers between ranks (device pointers; in this order):
+ *   dbg_shard_exit_counts   exits grouped by the rank that owns their successor (host counts, n_ranks)
+ *   dbg_shard_exit_keys     the successors' keys in that order, key_words u64 each      -> all-to-all
+ *   dbg_shard_mark_entries  received keys: these nodes are ENTRIES of this shard
+ *   dbg_shard_rank_local    list ranking of the shard with exits as roots; *n_reduced = entries + starts
+ *   dbg_shard_entry_ordinals one u32 per received key, in order                          -> all-to-all back
+ *   dbg_shard_reduced_records  replies (exit order) + the first reduced id of every rank (host, n_ranks: prefix
+ *                           sums of all ranks' n_reduced) -> 2 u64 per reduced vertex     -> all-gather
+ *   dbg_shard_walk          every rank's records back to back, my_base = this rank's first reduced id: ranks the
+ *                           reduced list and leaves one dbg_shard_contig_t per start of THIS shard that emits a
+ *                           contig, sorted by tag; all ranks' records merged by tag are the reference's order. */
+typedef struct {
+    uint64_t tag;            /* first-occurrence tag of the start node                                */
+    uint32_t start_slot, start_rank;       /* node id = (rank, slot in that rank's shard)             */
+    uint32_t terminal_slot, terminal_rank;
+    uint32_t n_nodes;        /* contig length = k + n_nodes - 1                                       */
+    uint32_t kind;           /* DBG_TERM_*                                                            */
+} dbg_shard_contig_t;
+int dbg_shard_config(dbg_t *h, uint32_t rank, uint32_t n_ranks);     /* n_ranks <= 1: not sharded    */
+int dbg_shard_exit_counts(dbg_t *h, uint64_t *counts /* host, n_ranks */);
+int dbg_shard_exit_keys(dbg_t *h, uint64_t *d_keys_out);
+int dbg_shard_mark_entries(dbg_t *h, const uint64_t *d_keys, uint64_t n);
+int dbg_shard_rank_local(dbg_t *h, uint64_t *n_reduced);
+int dbg_shard_entry_ordinals(dbg_t *h, uint32_t *d_out);
+int dbg_shard_reduced_records(dbg_t *h, const uint32_t *d_replies, const uint64_t *rid_base /* host, n_ranks */,
+                              uint64_t *d_out);
+int dbg_shard_walk(dbg_t *h, const uint64_t *d_all_records, uint64_t n_total, uint64_t my_base, uint64_t *n_contigs);
+int dbg_shard_contigs(dbg_t *h, dbg_shard_contig_t *out);            /* n_contigs entries            */
+
 /* nodes, unordered (sort by first_tag for the reference's dict order).  Any pointer may be
  * NULL.  succ_cnt: 4 per node = edge_count_table[node + "ACGT"[c]]; kept: low 8 bits = kept
  * successor bases in E order (2 bits each, first in bits 0-1), bits 8-10 = how many are kept

@@ -4,7 +4,8 @@ node table in the reference's dict order (keys, first-occurrence tags, edge coun
 flag, outdegree, kept successors in E order), branch / pulled lists, pull-out read flags and the
 contig descriptors (start, n_nodes, terminal, kind) in the reference's order.
 
-Test infrastructure: imported by tests/test_fullsize.py and the tools/check_*.py scripts only.
+TEST INFRASTRUCTURE (like everything under oracle/): imported by tests/, tools/check_*.py and the parity
+block of bench.py (the checker, outside every timed region) -- never by the product.
 """
 import numpy as np
 

@@ -41,6 +41,7 @@
 #include "../../include/dbg_b200.h"
 #include "dbg_kernels.cuh"
 #include "dbg_chunks.cuh"
+#include "dbg_shard.cuh"
 
 #define DBG_ABI_VERSION 1
 #define MAX_ENUM_CONTIGS (1ull << 26)
@@ -87,7 +88,8 @@ struct dbg_handle {
     DevBuf b_bases, b_off, b_packed, b_tile, b_table, b_flags, b_kept, b_succ, b_link, b_ctr, b_hll,
            b_order, b_tag, b_tag2, b_slot, b_slot2, b_sorttmp, b_branch, b_starts, b_pulled, b_readflags,
            b_recs, b_cnt32, b_off64, b_contig, b_junction, b_split, b_h8, b_bitmap, b_stmask, b_vmask,
-           b_spanread, b_cc, b_ctable, b_clist, b_super, b_readbatch, b_ctable2, b_scratch[6];
+           b_spanread, b_cc, b_ctable, b_clist, b_super, b_readbatch, b_ctable2, b_scratch[6],
+           b_exitslot, b_reqslot, b_rvslot, b_rvord, b_link2, b_scontig, b_owneroff;
     DevCounters ctr;
     dbg_stats_t st;
     std::vector<uint32_t> branch, pulled;     // reference order
@@ -112,6 +114,12 @@ struct dbg_handle {
     bool tags_local = false;                  // every tag in the table comes from this handle's own reads
     bool chunks_streamed = false;             // phase 1 already ran, slice by slice, while the reads were arriving
     uint64_t n_cslots = 0, n_clist = 0, ex_grid = 1;
+    // sharded node table (dbg_shard.cuh): this handle holds shard `shard_rank` of `shard_n` (0 / 1 = not sharded)
+    uint32_t shard_rank = 0, shard_n = 0;
+    uint64_t n_exit = 0, n_req = 0, n_rv = 0;
+    std::vector<uint64_t> exit_off;           // exits grouped by the owner of their successor: n_ranks + 1 offsets
+    std::vector<dbg_shard_contig_t> scontigs;
+    int shard_stage = 0;                      // 0 none, 1 exits listed, 2 entries marked, 3 ranked locally, 4 reduced records out, 5 walked
 };
 
 static std::string g_create_error;
@@ -798,7 +806,7 @@ static int graph_finalize(dbg_t *h) {
         uint64_t fin_grid = blocks_for(n_slots);
         if (fin_grid > 148 * 16) fin_grid = 148 * 16;
         LAUNCH(k_finalize<W>, fin_grid, DBG_BLOCK, h->stream, ptr<const S>(h->b_table), n_slots, h->k,
-               h->threshold, ptr<u8>(h->b_flags), ptr<u16>(h->b_kept), ptr<u32>(h->b_succ), d_ctr);
+               h->threshold, ptr<u8>(h->b_flags), ptr<u16>(h->b_kept), ptr<u32>(h->b_succ), h->shard_n > 1 ? 1 : 0, d_ctr);
         CKK();
         TRY(fetch_counters(h));
         tm_flush(h);
@@ -834,7 +842,7 @@ static int graph_order_scan(dbg_t *h) {
     if ((h->build_flags & DBG_EXACT_ORDER) && st.n_multi) {
         TRY(side_set<W>(h, F_MULTI, st.n_multi, &h->order_cap, &h->order_bits));
         h->order_active = true;
-        if (h->n_bases && h->chunks_valid) {
+        if ((h->n_bases || h->chunks_merged) && h->chunks_valid) {
             // from the distinct chunks of the local reads (2 - 20 x fewer than windows)
             typedef ChunkSlot<W> CS;
             uint64_t g = blocks_for(h->n_cslots + h->n_clist);
@@ -863,7 +871,7 @@ static int graph_complete(dbg_t *h) {
     if (h->order_active) {
         LAUNCH(k_order_apply<W>, blocks_for(h->order_cap), DBG_BLOCK, h->stream, ptr<const S>(h->b_table), n_slots, k,
                h->threshold, ptr<const SideEntry<W>>(h->b_order), h->order_cap, ptr<u16>(h->b_kept),
-               ptr<u32>(h->b_succ), d_ctr);
+               ptr<u32>(h->b_succ), ptr<u8>(h->b_flags), h->shard_n > 1 ? 1 : 0, d_ctr);
         CKK();
         TRY(check_fault(h, "k_order_*"));
         h->order_active = false;
@@ -879,6 +887,10 @@ static int graph_complete(dbg_t *h) {
         CK(cudaStreamSynchronize(h->stream));
     }
     const int e6 = ev_mark(h);
+    if (h->shard_n > 1 && st.n_branch)
+        return fail(h, DBG_ERR_STATE, "a sharded graph with branch nodes needs the whole table on one rank for tip pruning "
+                    "(debruijn.py:241-254): gather the shards (dbg_export_records / dbg_merge_records) instead");
+    h->shard_stage = 0;
 
     // ---- tip pruning (debruijn.py:241-254) ----
     TRY(tip_prune<W>(h));
@@ -1313,6 +1325,213 @@ static int walk_impl(dbg_t *h, int stop_at_branch) {
 }
 
 // -------------------------------------------------------------------------------------------------
+// sharded node table: owner-computes contig walk (dbg_shard.cuh)
+// -------------------------------------------------------------------------------------------------
+template <int W>
+static int shard_exit_counts_impl(dbg_t *h, uint64_t *counts) {
+    const uint32_t P = h->shard_n;
+    const ChunkGeom geom = chunk_geom(h->k);
+    TRY(reserve(h, h->b_off64, (uint64_t)P * 8 * 2));
+    CK(cudaMemsetAsync(h->b_off64.p, 0, (uint64_t)P * 8 * 2, h->stream));
+    LAUNCH(k_exit_count<W>, blocks_for(h->n_slots), DBG_BLOCK, h->stream, ptr<const Slot<W>>(h->b_table), h->n_slots,
+           ptr<const u8>(h->b_flags), ptr<const u16>(h->b_kept), h->k, geom.w, geom.m, P, ptr<u64>(h->b_off64));
+    CKK();
+    CK(cudaMemcpyAsync(counts, h->b_off64.p, (uint64_t)P * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->exit_off.assign(P + 1, 0);
+    for (uint32_t p = 0; p < P; p++) h->exit_off[p + 1] = h->exit_off[p] + counts[p];
+    h->n_exit = h->exit_off[P];
+    h->shard_stage = 1;
+    return DBG_OK;
+}
+
+template <int W>
+static int shard_exit_keys_impl(dbg_t *h, uint64_t *d_keys_out) {
+    const uint32_t P = h->shard_n;
+    const ChunkGeom geom = chunk_geom(h->k);
+    TRY(reserve(h, h->b_exitslot, (h->n_exit + 1) * 4));
+    u64 *d_cur = ptr<u64>(h->b_off64) + P;
+    CK(cudaMemcpyAsync(d_cur, h->exit_off.data(), (uint64_t)P * 8, cudaMemcpyHostToDevice, h->stream));
+    if (h->n_exit) {
+        LAUNCH(k_exit_scatter<W>, blocks_for(h->n_slots), DBG_BLOCK, h->stream, ptr<const Slot<W>>(h->b_table), h->n_slots,
+               ptr<const u8>(h->b_flags), ptr<const u16>(h->b_kept), h->k, geom.w, geom.m, P, d_cur,
+               ptr<u32>(h->b_exitslot), (u64 *)d_keys_out);
+        CKK();
+    }
+    CK(cudaStreamSynchronize(h->stream));                 // exit_off (host memory of this handle) was the copy's source
+    return DBG_OK;
+}
+
+template <int W>
+static int shard_mark_entries_impl(dbg_t *h, const uint64_t *d_keys, uint64_t n) {
+    TRY(reserve(h, h->b_reqslot, (n + 1) * 4));
+    h->n_req = n;
+    if (n) {
+        LAUNCH(k_mark_entries<W>, blocks_for(n), DBG_BLOCK, h->stream, ptr<const Slot<W>>(h->b_table), h->n_slots,
+               (const u64 *)d_keys, n, ptr<u8>(h->b_flags), ptr<u32>(h->b_reqslot), ptr<DevCounters>(h->b_ctr));
+        CKK();
+    }
+    h->shard_stage = 2;
+    return DBG_OK;
+}
+
+// list ranking of chain nodes -> splitters -> super-splitters on link[] (shared by the local and the reduced ranking)
+static int rank_links(dbg_t *h, u64 *d_link, uint64_t n_ids, uint64_t split_cap, uint64_t super_cap) {
+    DevCounters *d_ctr = ptr<DevCounters>(h->b_ctr);
+    LAUNCH(k_sublist, blocks_for(split_cap), DBG_BLOCK, h->stream, d_link, ptr<const u32>(h->b_split),
+           (const u64 *)&d_ctr->n_list_a, split_cap);
+    CKK();
+    LAUNCH(k_suplist, blocks_for(super_cap), DBG_BLOCK, h->stream, d_link, ptr<const u32>(h->b_super),
+           (const u64 *)&d_ctr->n_list_b, super_cap);
+    CKK();
+    int max_rounds = 2;
+    for (uint64_t n = super_cap; n > 1; n >>= 1) max_rounds++;
+    if (super_cap <= WALK_BLOCK_JUMP_CAP) {
+#ifdef DBG_EMU
+        LAUNCH(k_jump_block, 1, 1024, h->stream, d_link, ptr<const u32>(h->b_super), (const u64 *)&d_ctr->n_list_b,
+               super_cap, n_ids, max_rounds, d_ctr);
+#else
+        LAUNCH(k_jump_cluster, WALK_CLUSTER, 1024, h->stream, d_link, ptr<const u32>(h->b_super),
+               (const u64 *)&d_ctr->n_list_b, super_cap, n_ids, d_ctr);
+#endif
+        CKK();
+    } else {
+        TRY(fetch_counters(h));
+        const uint64_t n_super = h->ctr.n_list_b < super_cap ? h->ctr.n_list_b : super_cap;
+        CK(cudaMemsetAsync(&d_ctr->changed, 0, 4, h->stream));
+        for (int r = 0; r < max_rounds && n_super; r++) {
+            LAUNCH(k_jump, blocks_for(n_super), DBG_BLOCK, h->stream, d_link, ptr<const u32>(h->b_super), n_super, n_ids, d_ctr);
+            CKK();
+            if ((r & 7) == 7 || r == max_rounds - 1) {
+                TRY(check_fault(h, "k_jump"));
+                if (!h->ctr.changed) break;
+                CK(cudaMemsetAsync(&d_ctr->changed, 0, 4, h->stream));
+            }
+        }
+    }
+    return DBG_OK;
+}
+
+template <int W>
+static int shard_rank_local_impl(dbg_t *h, uint64_t *n_reduced) {
+    dbg_stats_t &st = h->st;
+    const uint64_t n_slots = h->n_slots;
+    DevCounters *d_ctr = ptr<DevCounters>(h->b_ctr);
+    h->n_ev_walk = EV_WALK;
+    const int e0 = ev_mark_walk(h);
+    TRY(reserve(h, h->b_link, n_slots * 8));
+    // splitters: starts, entries (at most one per request received) and the hash sample
+    const uint64_t split_cap = (n_slots >> WALK_SPLIT_LOG2) * 3 / 2 + st.n_starts + h->n_req + 4096;
+    const uint64_t super_cap = (split_cap >> WALK_SUPER_LOG2) * 3 / 2 + 4096;
+    TRY(reserve(h, h->b_split, split_cap * 4));
+    TRY(reserve(h, h->b_super, super_cap * 4));
+    CK(cudaMemsetAsync(&d_ctr->n_list_a, 0, 16, h->stream));
+    LAUNCH(k_link_init, blocks_for(n_slots), DBG_BLOCK, h->stream, ptr<const u8>(h->b_flags),
+           ptr<const u16>(h->b_kept), ptr<const u32>(h->b_succ), n_slots, ptr<u64>(h->b_link), ptr<u32>(h->b_split),
+           split_cap, &d_ctr->n_list_a, ptr<u32>(h->b_super), super_cap, &d_ctr->n_list_b);
+    CKK();
+    TRY(rank_links(h, ptr<u64>(h->b_link), n_slots, split_cap, super_cap));
+    // reduced vertices of this shard: entries + starts
+    const uint64_t rv_cap = st.n_starts + h->n_req + 1;
+    TRY(reserve(h, h->b_rvslot, rv_cap * 4));
+    TRY(reserve(h, h->b_rvord, n_slots * 4));
+    CK(cudaMemsetAsync(&d_ctr->n_dropped, 0, 8, h->stream));
+    LAUNCH(k_rv_collect, blocks_for(n_slots), DBG_BLOCK, h->stream, ptr<const u8>(h->b_flags), n_slots,
+           ptr<u32>(h->b_rvslot), ptr<u32>(h->b_rvord), &d_ctr->n_dropped);
+    CKK();
+    TRY(check_fault(h, "the local list ranking of the shard"));
+    if (h->ctr.n_list_a > split_cap || h->ctr.n_list_b > super_cap)
+        return fail(h, DBG_ERR_STATE, "splitter list overflow in the sharded walk");
+    h->n_rv = h->ctr.n_dropped;
+    if (h->n_rv > rv_cap) return fail(h, DBG_ERR_STATE, "reduced vertex list overflow");
+    *n_reduced = h->n_rv;
+    const int e1 = ev_mark_walk(h);
+    tm_set(h, &st.ms_walk_rank, e0, e1);
+    h->shard_stage = 3;
+    return DBG_OK;
+}
+
+static int shard_entry_ordinals_impl(dbg_t *h, uint32_t *d_out) {
+    if (h->n_req) {
+        LAUNCH(k_entry_ordinals, blocks_for(h->n_req), DBG_BLOCK, h->stream, ptr<const u32>(h->b_reqslot), h->n_req,
+               ptr<const u32>(h->b_rvord), (u32 *)d_out);
+        CKK();
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    return DBG_OK;
+}
+
+static int shard_reduced_records_impl(dbg_t *h, const uint32_t *d_replies, const uint64_t *rid_base, uint64_t *d_out) {
+    const uint32_t P = h->shard_n;
+    TRY(reserve(h, h->b_owneroff, (uint64_t)(2 * P + 2) * 8));
+    u64 *d_off = ptr<u64>(h->b_owneroff), *d_base = d_off + P + 1;
+    CK(cudaMemcpyAsync(d_off, h->exit_off.data(), (uint64_t)(P + 1) * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(d_base, rid_base, (uint64_t)P * 8, cudaMemcpyHostToDevice, h->stream));
+    if (h->n_exit) {
+        LAUNCH(k_exit_store, blocks_for(h->n_exit), DBG_BLOCK, h->stream, ptr<const u32>(h->b_exitslot), h->n_exit,
+               (const u64 *)d_off, P, (const u64 *)d_base, (const u32 *)d_replies, ptr<u32>(h->b_succ));
+        CKK();
+    }
+    if (h->n_rv) {
+        LAUNCH(k_reduced_build, blocks_for(h->n_rv), DBG_BLOCK, h->stream, ptr<const u32>(h->b_rvslot), h->n_rv,
+               ptr<const u64>(h->b_link), ptr<const u8>(h->b_flags), ptr<const u16>(h->b_kept), ptr<const u32>(h->b_succ),
+               h->shard_rank, (u64 *)d_out);
+        CKK();
+    }
+    CK(cudaStreamSynchronize(h->stream));                 // rid_base is the caller's host memory
+    h->shard_stage = 4;
+    return DBG_OK;
+}
+
+template <int W>
+static int shard_walk_impl(dbg_t *h, const uint64_t *d_all, uint64_t n_total, uint64_t my_base, uint64_t *n_contigs) {
+    dbg_stats_t &st = h->st;
+    DevCounters *d_ctr = ptr<DevCounters>(h->b_ctr);
+    const int e0 = ev_mark_walk(h);
+    h->scontigs.clear();
+    *n_contigs = 0;
+    if (n_total >= 0xFFFFFFF0ull) return fail(h, DBG_ERR_OVERFLOW, "the reduced list exceeds 2^32 vertices");
+    TRY(reserve(h, h->b_link2, (n_total + 1) * 8));
+    const uint64_t split_cap = (n_total >> WALK_SPLIT_LOG2) * 3 / 2 + h->n_rv + 4096;
+    const uint64_t super_cap = (split_cap >> WALK_SUPER_LOG2) * 3 / 2 + 4096;
+    TRY(reserve(h, h->b_split, split_cap * 4));
+    TRY(reserve(h, h->b_super, super_cap * 4));
+    CK(cudaMemsetAsync(&d_ctr->n_list_a, 0, 16, h->stream));
+    LAUNCH(k_rlink_init, blocks_for(n_total), DBG_BLOCK, h->stream, (const u64 *)d_all, n_total, my_base, h->n_rv,
+           ptr<u64>(h->b_link2), ptr<u32>(h->b_split), split_cap, &d_ctr->n_list_a, ptr<u32>(h->b_super), super_cap,
+           &d_ctr->n_list_b, d_ctr);
+    CKK();
+    TRY(rank_links(h, ptr<u64>(h->b_link2), n_total, split_cap, super_cap));
+    const uint64_t ns = st.n_starts;
+    if (ns) {
+        TRY(reserve(h, h->b_scontig, ns * sizeof(ShardContig)));
+        CK(cudaMemsetAsync(&d_ctr->n_dropped, 0, 8, h->stream));
+        LAUNCH(k_emit_reduced<W>, blocks_for(ns), DBG_BLOCK, h->stream, ptr<const Slot<W>>(h->b_table),
+               ptr<const u32>(h->b_starts), ns, ptr<const u32>(h->b_rvord), my_base, h->shard_rank,
+               ptr<const u64>(h->b_link2), (const u64 *)d_all, ptr<ShardContig>(h->b_scontig), &d_ctr->n_dropped);
+        CKK();
+    }
+    TRY(check_fault(h, "the ranking of the reduced list"));
+    if (h->ctr.n_list_a > split_cap || h->ctr.n_list_b > super_cap)
+        return fail(h, DBG_ERR_STATE, "splitter list overflow in the reduced walk");
+    const uint64_t nc = ns ? h->ctr.n_dropped : 0;          // (the cursor counts emitted records here)
+    h->scontigs.resize(nc);
+    if (nc) {
+        CK(cudaMemcpyAsync(h->scontigs.data(), h->b_scontig.p, nc * sizeof(ShardContig), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        std::sort(h->scontigs.begin(), h->scontigs.end(),
+                  [](const dbg_shard_contig_t &a, const dbg_shard_contig_t &b) { return a.tag < b.tag; });
+    }
+    st.n_contigs = nc;
+    st.n_cycle_starts = 0;
+    *n_contigs = nc;
+    const int e1 = ev_mark_walk(h);
+    tm_set(h, &st.ms_walk_emit, e0, e1);
+    h->shard_stage = 5;
+    return DBG_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
 // C ABI
 // -------------------------------------------------------------------------------------------------
 #define DISPATCH(fn, ...) (h->W == 1 ? fn<1>(__VA_ARGS__) : fn<2>(__VA_ARGS__))
@@ -1371,7 +1590,8 @@ DBG_API void dbg_destroy(dbg_t *h) {
                      &h->b_slot2, &h->b_sorttmp, &h->b_branch, &h->b_starts, &h->b_pulled, &h->b_readflags,
                      &h->b_recs, &h->b_cnt32, &h->b_off64, &h->b_contig, &h->b_junction, &h->b_split, &h->b_h8, &h->b_bitmap,
                      &h->b_stmask, &h->b_vmask, &h->b_spanread, &h->b_cc, &h->b_ctable, &h->b_clist, &h->b_super, &h->b_readbatch, &h->b_ctable2, &h->b_scratch[0],
-                     &h->b_scratch[1], &h->b_scratch[2], &h->b_scratch[3], &h->b_scratch[4], &h->b_scratch[5]};
+                     &h->b_scratch[1], &h->b_scratch[2], &h->b_scratch[3], &h->b_scratch[4], &h->b_scratch[5],
+                     &h->b_exitslot, &h->b_reqslot, &h->b_rvslot, &h->b_rvord, &h->b_link2, &h->b_scontig, &h->b_owneroff};
     for (DevBuf *b : all) if (b->p) cudaFree(b->p);
     for (int i = 0; i < EV_MAX; i++) cudaEventDestroy(h->ev[i]);
     for (int i = 0; i <= MAX_SLICES; i++) cudaEventDestroy(h->slice_ev[i]);
@@ -1679,6 +1899,76 @@ DBG_API int dbg_pull_reads(dbg_t *h, uint8_t *read_flags) {
         return DBG_OK;
     }
     if (h->n_reads) memcpy(read_flags, h->read_flags.data(), h->n_reads);
+    return DBG_OK;
+}
+
+// ---- sharded node table (dbg_shard.cuh) ----
+#define NEED_SHARD(stage_min) do { NEED_BUILT(); if (h->shard_n < 2) return fail(h, DBG_ERR_STATE, "%s: the handle is not sharded (dbg_shard_config)", __func__); \
+    if (h->shard_stage < (stage_min)) return fail(h, DBG_ERR_STATE, "%s called out of order", __func__); } while (0)
+
+DBG_API int dbg_shard_config(dbg_t *h, uint32_t rank, uint32_t n_ranks) {
+    if (!h) return DBG_ERR_ARG;
+    if (n_ranks > DBG_MAX_PARTS || (n_ranks && rank >= n_ranks)) return fail(h, DBG_ERR_ARG, "dbg_shard_config: bad rank %u of %u", rank, n_ranks);
+    if (n_ranks > 1 && n_ranks > 0xFFFFFFu) return fail(h, DBG_ERR_ARG, "too many ranks");
+    h->shard_rank = n_ranks > 1 ? rank : 0;
+    h->shard_n = n_ranks > 1 ? n_ranks : 0;
+    h->shard_stage = 0;
+    return DBG_OK;
+}
+
+DBG_API int dbg_shard_exit_counts(dbg_t *h, uint64_t *counts) {
+    NEED_SHARD(0);
+    if (!counts) return fail(h, DBG_ERR_ARG, "NULL counts");
+    CK(cudaSetDevice(h->device));
+    return DISPATCH(shard_exit_counts_impl, h, counts);
+}
+
+DBG_API int dbg_shard_exit_keys(dbg_t *h, uint64_t *d_keys_out) {
+    NEED_SHARD(1);
+    if (h->n_exit && !d_keys_out) return fail(h, DBG_ERR_ARG, "NULL output");
+    CK(cudaSetDevice(h->device));
+    return DISPATCH(shard_exit_keys_impl, h, d_keys_out);
+}
+
+DBG_API int dbg_shard_mark_entries(dbg_t *h, const uint64_t *d_keys, uint64_t n) {
+    NEED_SHARD(1);
+    if (n && !d_keys) return fail(h, DBG_ERR_ARG, "NULL keys");
+    CK(cudaSetDevice(h->device));
+    return DISPATCH(shard_mark_entries_impl, h, d_keys, n);
+}
+
+DBG_API int dbg_shard_rank_local(dbg_t *h, uint64_t *n_reduced) {
+    NEED_SHARD(2);
+    if (!n_reduced) return fail(h, DBG_ERR_ARG, "NULL n_reduced");
+    CK(cudaSetDevice(h->device));
+    return DISPATCH(shard_rank_local_impl, h, n_reduced);
+}
+
+DBG_API int dbg_shard_entry_ordinals(dbg_t *h, uint32_t *d_out) {
+    NEED_SHARD(3);
+    if (h->n_req && !d_out) return fail(h, DBG_ERR_ARG, "NULL output");
+    CK(cudaSetDevice(h->device));
+    return shard_entry_ordinals_impl(h, d_out);
+}
+
+DBG_API int dbg_shard_reduced_records(dbg_t *h, const uint32_t *d_replies, const uint64_t *rid_base, uint64_t *d_out) {
+    NEED_SHARD(3);
+    if (!rid_base || (h->n_exit && !d_replies) || (h->n_rv && !d_out)) return fail(h, DBG_ERR_ARG, "NULL argument");
+    CK(cudaSetDevice(h->device));
+    return shard_reduced_records_impl(h, d_replies, rid_base, d_out);
+}
+
+DBG_API int dbg_shard_walk(dbg_t *h, const uint64_t *d_all_records, uint64_t n_total, uint64_t my_base, uint64_t *n_contigs) {
+    NEED_SHARD(4);
+    if (!n_contigs || (n_total && !d_all_records) || my_base + h->n_rv > n_total) return fail(h, DBG_ERR_ARG, "dbg_shard_walk: bad argument");
+    CK(cudaSetDevice(h->device));
+    return DISPATCH(shard_walk_impl, h, d_all_records, n_total, my_base, n_contigs);
+}
+
+DBG_API int dbg_shard_contigs(dbg_t *h, dbg_shard_contig_t *out) {
+    NEED_SHARD(5);
+    if (h->scontigs.size() && !out) return fail(h, DBG_ERR_ARG, "NULL output");
+    if (h->scontigs.size()) memcpy(out, h->scontigs.data(), h->scontigs.size() * sizeof(dbg_shard_contig_t));
     return DBG_OK;
 }
 

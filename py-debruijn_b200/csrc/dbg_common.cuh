@@ -26,6 +26,8 @@ typedef unsigned char u8;
 #define F_DEADEND 0x08u
 #define F_PULLED  0x10u
 #define F_MULTI   0x20u
+#define F_EXIT    0x40u   // sharded table: the single kept successor lives on another rank (dbg_shard.cuh)
+#define F_ENTRY   0x80u   // sharded table: this node is the kept successor of another rank's exit
 
 #define NONE32 0xFFFFFFFFu
 #define NONE64 0xFFFFFFFFFFFFFFFFULL

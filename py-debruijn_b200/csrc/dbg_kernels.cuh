@@ -207,7 +207,7 @@ template <int W>
 __global__ void __launch_bounds__(DBG_BLOCK) k_finalize(const Slot<W> *__restrict__ table, u64 n_slots, int k,
                                                         double threshold, u8 *__restrict__ flags,
                                                         u16 *__restrict__ kept, u32 *__restrict__ succ,
-                                                        DevCounters *ctr) {
+                                                        int sharded, DevCounters *ctr) {
     typedef typename KeyOf<W>::type K;
     // grid-stride; the five counters are summed in registers and leave the block as ONE atomic each
     // (one atomic per warp on the same five words used to serialise in L2)
@@ -226,7 +226,9 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_finalize(const Slot<W> *__restric
             if (nk == 1) {
                 K sk = key_roll(key, (u32)kept_base(word, 0), mask);
                 u64 fi = table_find<W>(table, n_slots, sk);
-                if (fi == NONE64) raise_fault(ctr, FAULT_SUCC_MISSING, (u32)i);
+                if (fi == NONE64) {                                  // sharded table: the successor is another rank's node
+                    if (sharded) f |= F_EXIT; else raise_fault(ctr, FAULT_SUCC_MISSING, (u32)i);
+                }
                 sx = (u32)fi;
             }
             c_nodes++; c_edges += (u32)m;
@@ -309,7 +311,7 @@ template <int W>
 __global__ void __launch_bounds__(DBG_BLOCK) k_order_apply(const Slot<W> *__restrict__ table, u64 n_slots, int k,
                                                            double threshold, const SideEntry<W> *__restrict__ ot,
                                                            u64 cap, u16 *__restrict__ kept, u32 *__restrict__ succ,
-                                                           DevCounters *ctr) {
+                                                           u8 *flags, int sharded, DevCounters *ctr) {
     typedef typename KeyOf<W>::type K;
     u64 e = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= cap) return;
@@ -322,8 +324,9 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_order_apply(const Slot<W> *__rest
     if (kept_count(word) == 1) {        // threshold < 1: the tie decides WHICH successor survives
         K sk = key_roll(table[i].key, (u32)kept_base(word, 0), key_mask<W>(k));
         u64 fi = table_find<W>(table, n_slots, sk);
-        if (fi == NONE64) raise_fault(ctr, FAULT_SUCC_MISSING, (u32)i);
+        if (fi == NONE64 && !sharded) raise_fault(ctr, FAULT_SUCC_MISSING, (u32)i);
         succ[i] = (u32)fi;
+        if (sharded) flags[i] = (u8)((flags[i] & ~F_EXIT) | (fi == NONE64 ? F_EXIT : 0u));   // only this thread writes slot i
     }
 }
 
@@ -473,8 +476,9 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_link_init(const u8 *__restrict__ 
     bool split = false;
     if (i < n_slots) {
         u32 f = flags[i];
-        bool chain = (f & F_OCC) && !(f & F_PULLED) && kept_count(kept[i]) == 1;
-        split = chain && ((f & F_START) || (hash32((u32)i) & ((1u << WALK_SPLIT_LOG2) - 1)) == 0);
+        // sharded table (dbg_shard.cuh): an exit is a root of the local ranking, an entry a splitter
+        bool chain = (f & F_OCC) && !(f & (F_PULLED | F_EXIT)) && kept_count(kept[i]) == 1;
+        split = chain && ((f & (F_START | F_ENTRY)) || (hash32((u32)i) & ((1u << WALK_SPLIT_LOG2) - 1)) == 0);
         link[i] = chain ? (link_pack(succ[i], 1) | (split ? LINK_SPLIT : 0)) : link_pack((u32)i, 0);
     }
     // list append, aggregated per block: one global atomic per block and list (one per warp on the same
@@ -507,16 +511,18 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_link_init(const u8 *__restrict__ 
     }
 }
 
-// walk from chain node `from` (exclusive) to the first splitter or root; returns that node and
-// the hop count, or NONE32 when the walk is caught in a splitter-free cycle
-DBG_D u32 walk_to_splitter(const u64 *link, u32 from_next, u32 *hops) {
-    u32 cur = from_next, d = 1;
+// walk from a chain node (exclusive; its own link leads to `from_next` over `first_dist` hops) to the first
+// splitter or root; returns that node and the hop count, or NONE32 when the walk is caught in a splitter-free
+// cycle.  Hops are weighted by the links' own distances: 1 on the node table, anything on the reduced
+// list of a sharded walk (dbg_shard.cuh).
+DBG_D u32 walk_to_splitter(const u64 *link, u32 from_next, u32 first_dist, u32 *hops) {
+    u32 cur = from_next, d = first_dist;
     u32 check = cur, power = 1, lam = 0;              // Brent: checkpoint every power of two
     for (;;) {
         u64 l = __ldcg(&link[cur]);
         if ((l & LINK_SPLIT) || link_is_root(l, cur)) { *hops = d; return cur; }
         cur = link_next(l);
-        d = link_dist_add(d, 1);
+        d = link_dist_add(d, link_dist(l));
         if (cur == check) return NONE32;
         if (++lam == power) { check = cur; power <<= 1; lam = 0; }
     }
@@ -529,9 +535,10 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_sublist(u64 *link, const u32 *__r
     if (n_split > split_cap) n_split = split_cap;                           // the host reports the overflow
     if (j >= n_split) return;
     u32 v = split_list[j];
-    u32 first = link_next(__ldcg(&link[v]));
+    const u64 l0 = __ldcg(&link[v]);
+    u32 first = link_next(l0);
     u32 hops = 0;
-    u32 t = first == v ? NONE32 : walk_to_splitter(link, first, &hops);     // first == v: self loop
+    u32 t = first == v ? NONE32 : walk_to_splitter(link, first, link_dist(l0), &hops);     // first == v: self loop
     // only this thread writes link[v]; walkers that pass by only look at its SPLIT bit
     __stcg(&link[v], t == NONE32 ? (LINK_SPLIT | link_pack(v, LINK_DIST_MAX)) : (LINK_SPLIT | link_pack(t, hops)));
 }
@@ -672,7 +679,7 @@ DBG_D bool resolve_chain(const u64 *link, u32 v, u32 *terminal, u32 *hops) {
     if (!link_is_root(l, v) && !(l & LINK_SPLIT)) {          // plain chain node: reach a splitter first
         u32 first = link_next(l);
         if (first == v) return false;
-        w = walk_to_splitter(link, first, &d);
+        w = walk_to_splitter(link, first, link_dist(l), &d);
         if (w == NONE32) return false;
         l = __ldcg(&link[w]);
     }

@@ -18,7 +18,7 @@ CSRC = os.path.join(PKG_DIR, 'csrc')
 LIB_DIR = os.path.join(PKG_DIR, 'lib')
 LIB_PATH = os.path.join(LIB_DIR, 'libdbg_b200.so')
 SOURCES = ('dbg_b200.cu',)
-HEADERS = ('dbg_common.cuh', 'dbg_kernels.cuh', 'dbg_chunks.cuh')
+HEADERS = ('dbg_common.cuh', 'dbg_kernels.cuh', 'dbg_chunks.cuh', 'dbg_shard.cuh')
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-shared', '-Xcompiler', '-fPIC']
@@ -55,6 +55,12 @@ class Contig(C.Structure):
                 ('kind', C.c_uint32), ('seg_begin', C.c_uint64), ('seg_end', C.c_uint64)]
 
 
+class ShardContig(C.Structure):
+    _fields_ = [('tag', C.c_uint64), ('start_slot', C.c_uint32), ('start_rank', C.c_uint32),
+                ('terminal_slot', C.c_uint32), ('terminal_rank', C.c_uint32), ('n_nodes', C.c_uint32),
+                ('kind', C.c_uint32)]
+
+
 class Segment(C.Structure):
     _fields_ = [('entry', C.c_uint32), ('n_nodes', C.c_uint32)]
 
@@ -88,6 +94,15 @@ SYMBOLS = {
     'dbg_chunk_expand': (C.c_int, [_P]),
     'dbg_order_export': (C.c_int, [_P, _P, C.c_uint64, C.POINTER(C.c_uint64)]),
     'dbg_order_merge': (C.c_int, [_P, _P, C.c_uint64]),
+    'dbg_shard_config': (C.c_int, [_P, C.c_uint32, C.c_uint32]),
+    'dbg_shard_exit_counts': (C.c_int, [_P, _P]),
+    'dbg_shard_exit_keys': (C.c_int, [_P, _P]),
+    'dbg_shard_mark_entries': (C.c_int, [_P, _P, C.c_uint64]),
+    'dbg_shard_rank_local': (C.c_int, [_P, C.POINTER(C.c_uint64)]),
+    'dbg_shard_entry_ordinals': (C.c_int, [_P, _P]),
+    'dbg_shard_reduced_records': (C.c_int, [_P, _P, _P, _P]),
+    'dbg_shard_walk': (C.c_int, [_P, _P, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64)]),
+    'dbg_shard_contigs': (C.c_int, [_P, _P]),
     'dbg_export_nodes': (C.c_int, [_P] + [_P] * 7),
     'dbg_branch_nodes': (C.c_int, [_P, _P]),
     'dbg_pulled_nodes': (C.c_int, [_P, _P]),

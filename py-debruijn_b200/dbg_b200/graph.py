@@ -284,6 +284,44 @@ class Graph:
     def order_merge(self, d_ptr, n):
         self.lib.check(self.h, self.lib.dbg_order_merge(self.h, d_ptr, int(n)))
 
+    # ---- sharded node table: owner-computes walk (include/dbg_b200.h, dbg_shard_*) ----------
+    SHARD_CONTIG_DTYPE = np.dtype([('tag', np.uint64), ('start_slot', np.uint32), ('start_rank', np.uint32),
+                                   ('terminal_slot', np.uint32), ('terminal_rank', np.uint32),
+                                   ('n_nodes', np.uint32), ('kind', np.uint32)])
+
+    def shard_config(self, rank, n_ranks):
+        self.lib.check(self.h, self.lib.dbg_shard_config(self.h, int(rank), int(n_ranks)))
+
+    def shard_exit_counts(self, n_ranks):
+        counts = np.zeros(n_ranks, np.uint64)
+        self.lib.check(self.h, self.lib.dbg_shard_exit_counts(self.h, counts.ctypes.data))
+        return counts
+
+    def shard_exit_keys(self, d_out_ptr):
+        self.lib.check(self.h, self.lib.dbg_shard_exit_keys(self.h, d_out_ptr))
+
+    def shard_mark_entries(self, d_keys_ptr, n):
+        self.lib.check(self.h, self.lib.dbg_shard_mark_entries(self.h, d_keys_ptr, int(n)))
+
+    def shard_rank_local(self):
+        n = C.c_uint64()
+        self.lib.check(self.h, self.lib.dbg_shard_rank_local(self.h, C.byref(n)))
+        return int(n.value)
+
+    def shard_entry_ordinals(self, d_out_ptr):
+        self.lib.check(self.h, self.lib.dbg_shard_entry_ordinals(self.h, d_out_ptr))
+
+    def shard_reduced_records(self, d_replies_ptr, rid_base, d_out_ptr):
+        rid_base = np.ascontiguousarray(rid_base, dtype=np.uint64)
+        self.lib.check(self.h, self.lib.dbg_shard_reduced_records(self.h, d_replies_ptr, rid_base.ctypes.data, d_out_ptr))
+
+    def shard_walk(self, d_all_ptr, n_total, my_base):
+        n = C.c_uint64()
+        self.lib.check(self.h, self.lib.dbg_shard_walk(self.h, d_all_ptr, int(n_total), int(my_base), C.byref(n)))
+        out = np.empty(n.value, dtype=self.SHARD_CONTIG_DTYPE)
+        self.lib.check(self.h, self.lib.dbg_shard_contigs(self.h, out.ctypes.data if n.value else None))
+        return out
+
     def set_stream(self, cuda_stream_ptr):
         """Run on the caller's stream.  0 / None is CUDA's legacy default stream (what
         torch.cuda.current_stream().cuda_stream returns by default), passed as cudaStreamLegacy;

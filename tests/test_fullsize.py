@@ -1,7 +1,7 @@
 """Full-size parity of every BASELINE.json config on the GPU (``-m gpu``): the product through the
 C ABI against the C oracle (oracle/dbg_oracle.c, pinned to the literal reference by
 tests/test_oracle_golden.py) on the WHOLE workload, compared row by row at descriptor level
-(tests/fullsize.py) -- strings cannot be materialised at these sizes (configs[1]
+(oracle/compare.py) -- strings cannot be materialised at these sizes (configs[1]
 would be 9e10 characters).  Plus the size-independent properties the domain offers: every
 window is counted exactly once (sum of edge counts == n_windows), node count == distinct
 k-mers of a brute-force numpy count on a sample, idempotence of a rebuild on the same handle.
@@ -17,7 +17,7 @@ import numpy as np
 import pytest
 
 import bench
-import fullsize
+from oracle import compare as fullsize
 from oracle import c_oracle
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -149,7 +149,7 @@ def test_nccl_two_ranks_equal_one_gpu(backend_gpu):
     if torch.cuda.device_count() < 2:
         pytest.skip('needs 2 GPUs on the box')
     port = 29700 + os.getpid() % 200
-    for name, G in (('c3', 400_000), ('c5s', 300_000)):
+    for name, G in (('c3', 400_000), ('c2', 600_000), ('c5s', 300_000)):
         cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
                '--master-addr', '127.0.0.1', '--master-port', str(port), os.path.join(ROOT, 'tools', 'check_dist.py'),
                name, str(G)]

@@ -16,7 +16,7 @@ sys.path[:0] = [ROOT, os.path.join(ROOT, 'py-debruijn_b200'), os.path.join(ROOT,
 import bench                                   # noqa: E402
 from dbg_b200 import Graph                     # noqa: E402
 from oracle import c_oracle                    # noqa: E402
-import fullsize                                # noqa: E402
+from oracle import compare as fullsize        # noqa: E402
 
 
 def main():

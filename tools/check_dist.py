@@ -1,5 +1,7 @@
-"""torchrun --nproc-per-node N tools/check_dist.py [config] : the N-GPU distributed build must give
-exactly the single-GPU result (node table, branch / pulled lists, pull-out flags, contig descriptors)."""
+"""torchrun --nproc-per-node N tools/check_dist.py [config] [G]: the N-GPU build (dist.build_sharded:
+owner-computes walk on a sharded node table; replicated fallback when the graph has branch nodes) must
+give exactly the single-GPU result -- node table in dict order (keys, tags, edge counts, flags, kept
+successors) and contig descriptors by node key (dist.global_snapshot vs dist.single_snapshot)."""
 import os
 import sys
 
@@ -11,18 +13,6 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, 'py-debruijn_b200')]
 import bench                                   # noqa: E402
 from dbg_b200 import Graph, dist as ddist      # noqa: E402
-
-
-def snapshot(g):
-    nd = g.nodes()
-    slot_to_idx = np.full(int(g.stats().table_slots), -1, np.int64)
-    slot_to_idx[nd['id']] = np.arange(len(nd['id']))
-    d = g.contig_descriptors()
-    return {
-        'key_lo': nd['key_lo'], 'key_hi': nd['key_hi'], 'tag': nd['tag'], 'cnt': nd['cnt'], 'flags': nd['flags'],
-        'kept': nd['kept'], 'branch': slot_to_idx[g.branch_ids()], 'pulled': slot_to_idx[g.pulled_ids()],
-        'c_start': slot_to_idx[d['start']], 'c_n': d['n_nodes'], 'c_term': slot_to_idx[d['terminal']], 'c_kind': d['kind'],
-    }
 
 
 def main():
@@ -40,28 +30,34 @@ def main():
     lo, hi = b[rank], b[rank + 1]
     local = (bases[lo * L:hi * L].copy(), (off[lo:hi + 1] - off[lo]).copy())
     g = Graph(cfg['k'], device=lr)
-    flags = ddist.build_distributed(g, local, lo, threshold=cfg['thr'], final=False)
-    g.walk(stop_at_branch=True)
-    mine = snapshot(g)
-    f = torch.from_numpy(flags.astype(np.int64)).cuda().reshape(-1, 1)
-    allf, _ = ddist._all_gather_var(f, None)
+    res = ddist.build_sharded(g, local, lo, threshold=cfg['thr'], final=False)
+    snap = ddist.global_snapshot(res)
     ok = True
     if rank == 0:
         ref = Graph(cfg['k'], device=lr)
         ref.build(None, threshold=cfg['thr'], final=False, packed=(bases, off))
         ref.walk(stop_at_branch=True)
-        exp = snapshot(ref)
+        exp = ddist.single_snapshot(ref)
         st = ref.stats()
-        print('single GPU: nodes %d multi %d branch %d pulled %d starts %d contigs %d pull_reads %d' %
-              (st.n_nodes, st.n_multi, st.n_branch, st.n_pulled, st.n_starts, st.n_contigs, st.n_pull_reads))
+        print('single GPU: nodes %d multi %d branch %d pulled %d starts %d contigs %d; %d ranks ran mode %s' %
+              (st.n_nodes, st.n_multi, st.n_branch, st.n_pulled, st.n_starts, st.n_contigs, world, res.mode))
         for f_ in exp:
-            same = np.array_equal(mine[f_], exp[f_])
+            same = np.array_equal(np.asarray(snap[f_]), np.asarray(exp[f_]))
             ok &= same
-            print('  %-8s %s' % (f_, 'OK' if same else 'MISMATCH'))
+            print('  %-10s %s' % (f_, 'OK' if same else 'MISMATCH'))
+        if res.mode == 'replicated':
+            f = torch.from_numpy(res.pull_flags.astype(np.int64)).cuda().reshape(-1, 1)
+        else:
+            f = torch.zeros((hi - lo, 1), dtype=torch.int64, device='cuda')
+    else:
+        f = torch.from_numpy(res.pull_flags.astype(np.int64)).cuda().reshape(-1, 1) if res.mode == 'replicated' \
+            else torch.zeros((hi - lo, 1), dtype=torch.int64, device='cuda')
+    allf, _ = ddist._all_gather_var(f, None)
+    if rank == 0:
         same = np.array_equal(allf.reshape(-1).cpu().numpy().astype(np.uint8), ref.pull_read_flags())
         ok &= same
-        print('  %-8s %s' % ('pullflag', 'OK' if same else 'MISMATCH'))
-        print('DIST PARITY (%d ranks, %s, G=%d): %s' % (world, name, G, 'OK' if ok else 'FAILED'))
+        print('  %-10s %s' % ('pullflag', 'OK' if same else 'MISMATCH'))
+        print('DIST PARITY (%d ranks, %s, G=%d, %s): %s' % (world, name, G, res.mode, 'OK' if ok else 'FAILED'))
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
