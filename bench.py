@@ -590,8 +590,9 @@ def run_dbg(args, cfg, rank, local_rank, world):
     if sharded:
         for _ in range(3):
             dist_ms.clear()
-            ddist.build_sharded(g, None, read_base, threshold=thr, final=False, timings=dist_ms,
-                                local_device=(d_bases.data_ptr(), d_off.data_ptr(), n_reads, n_bases))
+            # (the handle now holds THIS build: node ids of an earlier step's contigs would not match its table)
+            last['res'] = ddist.build_sharded(g, None, read_base, threshold=thr, final=False, timings=dist_ms,
+                                              local_device=(d_bases.data_ptr(), d_off.data_ptr(), n_reads, n_bases))
 
     ms_step = ms_total / args.steps
     total_windows = R.total(nwin)

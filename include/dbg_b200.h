@@ -12,9 +12,11 @@
  *   - the caller owns every buffer it passes; the handle owns all device memory
  *   - one handle per host thread / stream; the library starts no host threads
  *   - node ids are table-slot indices, valid until the next dbg_build* on the handle
- *   - alphabet: DNA, exactly the bytes 'A','C','G','T' (2-bit codes 0..3 in that order)
- *   - k-mers ("nodes", debruijn.py:127) are 2k-bit integers, first base most significant:
- *     k <= 31 uses 64-bit keys, k <= 63 uses 128-bit keys (key_hi is 0 for k <= 31)
+ *   - alphabet: dbg_create / dbg_create_ex handles take DNA, exactly the bytes 'A','C','G','T' (2-bit codes
+ *     0..3 in that order): k-mers ("nodes", debruijn.py:127) are 2k-bit integers, first base most
+ *     significant; k <= 31 uses 64-bit keys, k <= 63 uses 128-bit keys (key_hi is 0 for k <= 31).
+ *     dbg_create_alpha handles take ANY alphabet of up to 32 byte values (the reference's real inputs are
+ *     peptides, II_assembleFromReads.py:43-47): 5-bit codes = position in the symbol list, k <= 24, 128-bit keys
  *   - a tag is (global read index << 32 | position in read) of a node's FIRST occurrence
  *     in the reference's iteration order (debruijn.py:123-126); sorting by tag reproduces
  *     the reference's dict order
@@ -117,6 +119,10 @@ int  dbg_create(dbg_t **out, int device, int k);
 /* key_words: 0 = by k (1 for k <= 31, else 2); 2 forces 128-bit keys for a small k, which leaves
  * room for many batch ids above the k-mer (dbg_build_batched)                               */
 int  dbg_create_ex(dbg_t **out, int device, int k, int key_words);
+/* generic-alphabet engine: `symbols` = the n_symbols <= 32 distinct byte values the reads may hold; a node key is
+ * k x 5 bits (symbol codes, first symbol most significant).  Same calls as a DNA handle except the batched and
+ * multi-GPU ones; successors are reported by dbg_export_edges instead of 4 counters per node.                */
+int  dbg_create_alpha(dbg_t **out, int device, int k, const uint8_t *symbols, int n_symbols);
 void dbg_destroy(dbg_t *h);
 const char *dbg_last_error(const dbg_t *h);          /* h may be NULL: error of a failed create */
 int  dbg_set_stream(dbg_t *h, void *cuda_stream);    /* cudaStream_t; NULL = handle's own stream */
@@ -226,6 +232,11 @@ int dbg_shard_contigs(dbg_t *h, dbg_shard_contig_t *out);            /* n_contig
  * (pruningEdges result, debruijn.py:150-166).                                               */
 int dbg_export_nodes(dbg_t *h, uint32_t *node_id, uint64_t *key_lo, uint64_t *key_hi,
                      uint64_t *first_tag, uint32_t *succ_cnt, uint8_t *flags, uint16_t *kept);
+/* generic-alphabet handles: the n_edges distinct (k+1)-mers, grouped by source node and, inside a node, in
+ * the reference's E order (count descending, ties by first appearance, debruijn.py:159-164): src / dst node
+ * ids, the (k+1)-mer's last symbol (byte), its multiplicity = edge_count_table value, kept = 1 if it survives
+ * pruningEdges (a prefix of every node's run).  Any pointer may be NULL.                                    */
+int dbg_export_edges(dbg_t *h, uint32_t *src_id, uint32_t *dst_id, uint8_t *symbol, uint32_t *count, uint8_t *kept);
 int dbg_branch_nodes(dbg_t *h, uint32_t *node_id);   /* n_branch ids, reference order        */
 int dbg_pulled_nodes(dbg_t *h, uint32_t *node_id);   /* n_pulled ids, reference order        */
 int dbg_pull_reads(dbg_t *h, uint8_t *read_flags);   /* n_reads bytes, 1 = in pull_out_read  */

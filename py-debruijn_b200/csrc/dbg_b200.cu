@@ -42,6 +42,7 @@
 #include "dbg_kernels.cuh"
 #include "dbg_chunks.cuh"
 #include "dbg_shard.cuh"
+#include "dbg_generic.cuh"
 
 #define DBG_ABI_VERSION 1
 #define MAX_ENUM_CONTIGS (1ull << 26)
@@ -114,11 +115,20 @@ struct dbg_handle {
     bool tags_local = false;                  // every tag in the table comes from this handle's own reads
     bool chunks_streamed = false;             // phase 1 already ran, slice by slice, while the reads were arriving
     uint64_t n_cslots = 0, n_clist = 0, ex_grid = 1;
+    // generic-alphabet engine (dbg_generic.cuh): sym_bits == 5; 2 = the DNA engine
+    int sym_bits = 2, n_symbols = 4;
+    uint8_t sym_of_code[GEN_MAX_SYMBOLS] = {'A', 'C', 'G', 'T'}, code_of_byte[256];
+    uint64_t n_eslots = 0, n_earr = 0;
+    DevBuf b_up;                              // lifted successor arrays (strings / scores), built on demand
+    bool up_ready = false;
+    DevBuf b_codes, b_etable, b_earr, b_earr2, b_estart, b_edeg, b_enk, b_lut;
     // sharded node table (dbg_shard.cuh): this handle holds shard `shard_rank` of `shard_n` (0 / 1 = not sharded)
     uint32_t shard_rank = 0, shard_n = 0;
     uint64_t n_exit = 0, n_req = 0, n_rv = 0;
     std::vector<uint64_t> exit_off;           // exits grouped by the owner of their successor: n_ranks + 1 offsets
     std::vector<dbg_shard_contig_t> scontigs;
+    const dbg_shard_contig_t *sview = nullptr;  // what dbg_shard_contigs reads: the pinned records, or `scontigs` when some were dropped
+    uint64_t n_sview = 0;
     int shard_stage = 0;                      // 0 none, 1 exits listed, 2 entries marked, 3 ranked locally, 4 reduced records out, 5 walked
 };
 
@@ -311,9 +321,14 @@ static int tip_prune(dbg_t *h) {
     if (nb == 0) return DBG_OK;
     TRY(reserve(h, h->b_cnt32, nb * 4));
     TRY(reserve(h, h->b_off64, (nb + 1) * 8));
-    LAUNCH(k_tip_paths<W>, blocks_for(nb), DBG_BLOCK, h->stream, ptr<const Slot<W>>(h->b_table), h->n_slots, h->k,
-           ptr<const u8>(h->b_flags), ptr<const u16>(h->b_kept), ptr<const u32>(h->b_branch), nb, 0,
-           ptr<u32>(h->b_cnt32), (const u64 *)nullptr, (u32 *)nullptr, ptr<DevCounters>(h->b_ctr));
+    if (h->sym_bits == GEN_BITS)
+        LAUNCH(k_g_tip_paths, blocks_for(nb), DBG_BLOCK, h->stream, ptr<const u8>(h->b_flags), ptr<const u32>(h->b_enk),
+               ptr<const u32>(h->b_estart), ptr<const GEdge>(h->b_earr), ptr<const u32>(h->b_branch), nb, 0,
+               ptr<u32>(h->b_cnt32), (const u64 *)nullptr, (u32 *)nullptr);
+    else
+        LAUNCH(k_tip_paths<W>, blocks_for(nb), DBG_BLOCK, h->stream, ptr<const Slot<W>>(h->b_table), h->n_slots, h->k,
+               ptr<const u8>(h->b_flags), ptr<const u16>(h->b_kept), ptr<const u32>(h->b_branch), nb, 0,
+               ptr<u32>(h->b_cnt32), (const u64 *)nullptr, (u32 *)nullptr, ptr<DevCounters>(h->b_ctr));
     CKK();
     std::vector<u32> counts(nb);
     CK(cudaMemcpyAsync(counts.data(), h->b_cnt32.p, nb * 4, cudaMemcpyDeviceToHost, h->stream));
@@ -325,9 +340,14 @@ static int tip_prune(dbg_t *h) {
     if (total == 0) return DBG_OK;
     TRY(reserve(h, h->b_recs, total * 6 * 4));
     CK(cudaMemcpyAsync(h->b_off64.p, offs.data(), (nb + 1) * 8, cudaMemcpyHostToDevice, h->stream));
-    LAUNCH(k_tip_paths<W>, blocks_for(nb), DBG_BLOCK, h->stream, ptr<const Slot<W>>(h->b_table), h->n_slots, h->k,
-           ptr<const u8>(h->b_flags), ptr<const u16>(h->b_kept), ptr<const u32>(h->b_branch), nb, 1,
-           ptr<u32>(h->b_cnt32), ptr<const u64>(h->b_off64), ptr<u32>(h->b_recs), ptr<DevCounters>(h->b_ctr));
+    if (h->sym_bits == GEN_BITS)
+        LAUNCH(k_g_tip_paths, blocks_for(nb), DBG_BLOCK, h->stream, ptr<const u8>(h->b_flags), ptr<const u32>(h->b_enk),
+               ptr<const u32>(h->b_estart), ptr<const GEdge>(h->b_earr), ptr<const u32>(h->b_branch), nb, 1,
+               ptr<u32>(h->b_cnt32), ptr<const u64>(h->b_off64), ptr<u32>(h->b_recs));
+    else
+        LAUNCH(k_tip_paths<W>, blocks_for(nb), DBG_BLOCK, h->stream, ptr<const Slot<W>>(h->b_table), h->n_slots, h->k,
+               ptr<const u8>(h->b_flags), ptr<const u16>(h->b_kept), ptr<const u32>(h->b_branch), nb, 1,
+               ptr<u32>(h->b_cnt32), ptr<const u64>(h->b_off64), ptr<u32>(h->b_recs), ptr<DevCounters>(h->b_ctr));
     CKK();
     std::vector<u32> recs(total * 6);
     CK(cudaMemcpyAsync(recs.data(), h->b_recs.p, total * 6 * 4, cudaMemcpyDeviceToHost, h->stream));
@@ -1114,6 +1134,181 @@ static int order_merge_impl(dbg_t *h, const uint64_t *d_records, uint64_t n) {
 }
 
 // -------------------------------------------------------------------------------------------------
+// generic-alphabet engine (dbg_generic.cuh): construct_graph for reads over up to 32 symbols
+// -------------------------------------------------------------------------------------------------
+static int gen_sort_edges(dbg_t *h, uint64_t n) {
+    // edge array -> sorted by (source slot, count descending, first appearance): b_earr holds the result
+    if (n == 0) return DBG_OK;
+#ifdef DBG_EMU
+    GEdge *e = ptr<GEdge>(h->b_earr);
+    std::stable_sort(e, e + n, [](const GEdge &a, const GEdge &b) {
+        if (a.src != b.src) return a.src < b.src;
+        if (a.cnt != b.cnt) return a.cnt > b.cnt;
+        return a.first < b.first;
+    });
+#else
+    TRY(reserve(h, h->b_tag, n * 8));
+    TRY(reserve(h, h->b_tag2, n * 8));
+    TRY(reserve(h, h->b_slot, n * 4));
+    TRY(reserve(h, h->b_slot2, n * 4));
+    TRY(reserve(h, h->b_earr2, n * sizeof(GEdge)));
+    size_t tmp = 0;
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, ptr<u64>(h->b_tag), ptr<u64>(h->b_tag2), ptr<u32>(h->b_slot),
+                                       ptr<u32>(h->b_slot2), (int64_t)n, 0, 64, h->stream));
+    TRY(reserve(h, h->b_sorttmp, tmp));
+    // LSD: stable sort by the minor key (first appearance), then by the major one (source, ~count)
+    LAUNCH(k_g_sortkeys1, blocks_for(n), DBG_BLOCK, h->stream, ptr<const GEdge>(h->b_earr), n, ptr<u64>(h->b_tag), ptr<u32>(h->b_slot));
+    CKK();
+    h->st.n_launches++;
+    CK(cub::DeviceRadixSort::SortPairs(h->b_sorttmp.p, tmp, ptr<u64>(h->b_tag), ptr<u64>(h->b_tag2), ptr<u32>(h->b_slot),
+                                       ptr<u32>(h->b_slot2), (int64_t)n, 0, 64, h->stream));
+    LAUNCH(k_g_sortkeys2, blocks_for(n), DBG_BLOCK, h->stream, ptr<const GEdge>(h->b_earr), ptr<const u32>(h->b_slot2), n,
+           ptr<u64>(h->b_tag));
+    CKK();
+    h->st.n_launches++;
+    CK(cub::DeviceRadixSort::SortPairs(h->b_sorttmp.p, tmp, ptr<u64>(h->b_tag), ptr<u64>(h->b_tag2), ptr<u32>(h->b_slot2),
+                                       ptr<u32>(h->b_slot), (int64_t)n, 0, 64, h->stream));
+    LAUNCH(k_g_gather, blocks_for(n), DBG_BLOCK, h->stream, ptr<const GEdge>(h->b_earr), ptr<const u32>(h->b_slot), n,
+           ptr<GEdge>(h->b_earr2));
+    CKK();
+    std::swap(h->b_earr, h->b_earr2);
+#endif
+    return DBG_OK;
+}
+
+static int gen_build(dbg_t *h, const u8 *d_bases, const u64 *d_off) {
+    typedef Slot<2> S;
+    const int k = h->k;
+    dbg_stats_t &st = h->st;
+    DevCounters *d_ctr = ptr<DevCounters>(h->b_ctr);
+    const int e0 = ev_mark(h);
+    if (h->host_bases && h->n_bases)
+        CK(cudaMemcpyAsync((u8 *)d_bases, h->host_bases, h->n_bases, cudaMemcpyHostToDevice, h->stream));
+    // ---- symbols -> 5-bit codes; window count ----
+    TRY(reserve(h, h->b_lut, 256 + GEN_MAX_SYMBOLS));
+    CK(cudaMemcpyAsync(h->b_lut.p, h->code_of_byte, 256, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(ptr<u8>(h->b_lut) + 256, h->sym_of_code, GEN_MAX_SYMBOLS, cudaMemcpyHostToDevice, h->stream));
+    TRY(reserve(h, h->b_codes, h->n_bases + 64));
+    if (h->n_bases) {
+        LAUNCH(k_g_encode, blocks_for(h->n_bases), DBG_BLOCK, h->stream, d_bases, h->n_bases, ptr<const u8>(h->b_lut),
+               ptr<u8>(h->b_codes), d_ctr);
+        CKK();
+    }
+    if (h->n_reads) {
+        uint64_t rs_grid = blocks_for(h->n_reads);
+        if (rs_grid > 148 * 4) rs_grid = 148 * 4;
+        LAUNCH(k_read_stats, rs_grid, DBG_BLOCK, h->stream, d_off, h->n_reads, k, d_ctr);
+        CKK();
+    }
+    TRY(fetch_counters(h));
+    if (h->ctr.bad_alphabet) return fail(h, DBG_ERR_ALPHABET, "a read holds a byte that is not a symbol of this handle's alphabet");
+    if (h->ctr.too_long) return fail(h, DBG_ERR_OVERFLOW, "a read is longer than 2^32-1 symbols");
+    st.n_windows = h->ctr.n_windows;
+    const int e1 = ev_mark(h);
+    // ---- node table + edge table (debruijn.py:123-144, 213-222) ----
+    const uint64_t n_nslots = 2 * (st.n_windows + h->n_reads) + 64, n_eslots = 2 * st.n_windows + 64;
+    if (n_nslots >= 0xFFFFFFF0ull) return fail(h, DBG_ERR_OVERFLOW, "node table would exceed 2^32 slots");
+    h->n_slots = n_nslots;
+    h->n_eslots = n_eslots;
+    TRY(reserve(h, h->b_table, n_nslots * sizeof(S)));
+    TRY(reserve(h, h->b_etable, n_eslots * sizeof(S)));
+    LAUNCH(k_table_init<2>, blocks_for(n_nslots), DBG_BLOCK, h->stream, ptr<S>(h->b_table), n_nslots);
+    CKK();
+    LAUNCH(k_table_init<2>, blocks_for(n_eslots), DBG_BLOCK, h->stream, ptr<S>(h->b_etable), n_eslots);
+    CKK();
+    if (st.n_windows) {
+        LAUNCH(k_g_insert, blocks_for(h->n_bases), DBG_BLOCK, h->stream, ptr<const u8>(h->b_codes), d_off, h->n_reads,
+               h->n_bases, k, ptr<S>(h->b_table), n_nslots, ptr<S>(h->b_etable), n_eslots, h->read_idx_base, d_ctr);
+        CKK();
+    }
+    // ---- edge array in E order, CSR ----
+    TRY(reserve(h, h->b_earr, (st.n_windows + 1) * sizeof(GEdge)));
+    CK(cudaMemsetAsync(&d_ctr->n_list_a, 0, 8, h->stream));
+    LAUNCH(k_g_edges, blocks_for(n_eslots), DBG_BLOCK, h->stream, ptr<const S>(h->b_etable), n_eslots, ptr<const S>(h->b_table),
+           n_nslots, k, ptr<GEdge>(h->b_earr), &d_ctr->n_list_a, d_ctr);
+    CKK();
+    TRY(check_fault(h, "the generic table build"));
+    if (h->ctr.overflow) return fail(h, DBG_ERR_STATE, "internal consistency fault: a table sized by its upper bound overflowed");
+    const uint64_t n_e = h->ctr.n_list_a;
+    h->n_earr = n_e;
+    const int e2 = ev_mark(h);
+    TRY(gen_sort_edges(h, n_e));
+    TRY(reserve(h, h->b_estart, n_nslots * 4));
+    TRY(reserve(h, h->b_edeg, n_nslots * 4));
+    TRY(reserve(h, h->b_enk, n_nslots * 4));
+    CK(cudaMemsetAsync(h->b_edeg.p, 0, n_nslots * 4, h->stream));
+    CK(cudaMemsetAsync(h->b_estart.p, 0, n_nslots * 4, h->stream));
+    if (n_e) {
+        LAUNCH(k_g_csr, blocks_for(n_e), DBG_BLOCK, h->stream, ptr<const GEdge>(h->b_earr), n_e, ptr<u32>(h->b_estart),
+               ptr<u32>(h->b_edeg));
+        CKK();
+    }
+    // ---- degrees / pruningEdges / branch flags ----
+    CK(cudaMemsetAsync(&d_ctr->n_nodes, 0, 5 * 8, h->stream));
+    TRY(reserve(h, h->b_flags, n_nslots));
+    TRY(reserve(h, h->b_kept, n_nslots * 2));
+    TRY(reserve(h, h->b_succ, n_nslots * 4));
+    LAUNCH(k_g_finalize, blocks_for(n_nslots), DBG_BLOCK, h->stream, ptr<const S>(h->b_table), n_nslots,
+           ptr<const GEdge>(h->b_earr), ptr<const u32>(h->b_estart), ptr<const u32>(h->b_edeg), h->threshold,
+           ptr<u8>(h->b_flags), ptr<u16>(h->b_kept), ptr<u32>(h->b_succ), ptr<u32>(h->b_enk), d_ctr);
+    CKK();
+    TRY(fetch_counters(h));
+    st.n_nodes = h->ctr.n_nodes;
+    st.n_edges = h->ctr.n_edges;
+    st.n_multi = h->ctr.n_multi;
+    st.n_branch = h->ctr.n_branch;
+    st.n_starts = h->ctr.n_starts;
+    st.table_slots = n_nslots;
+    st.table_bytes = (n_nslots + n_eslots) * sizeof(S);
+    st.hll_estimate = 0;
+    if (st.n_multi && h->threshold == 0.0)
+        return fail(h, DBG_ERR_ZERODIV, "threshold == 0 with a multi-successor node (debruijn.py:163)");
+    const int e3 = ev_mark(h);
+    tm_set(h, &st.ms_pack, e0, e1);
+    tm_set(h, &st.ms_insert, e1, e2);
+    tm_set(h, &st.ms_finalize, e2, e3);
+    h->table_ready = true;
+    h->tags_local = true;
+    // ---- lists, tip pruning, pull-out reads ----
+    TRY(collect_sorted<2>(h, F_BRANCH, st.n_branch, h->b_branch, &d_ctr->n_list_a));
+    TRY(collect_sorted<2>(h, F_START, st.n_starts, h->b_starts, &d_ctr->n_list_b));
+    h->branch.resize(st.n_branch);
+    if (st.n_branch) {
+        CK(cudaMemcpyAsync(h->branch.data(), h->b_branch.p, st.n_branch * 4, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    const int e4 = ev_mark(h);
+    TRY(tip_prune<2>(h));
+    st.n_pulled = h->pulled.size();
+    const int e5 = ev_mark(h);
+    h->read_flags_valid = false;
+    st.n_pull_reads = 0;
+    if (!(h->build_flags & (DBG_FINAL | DBG_NO_PULL_READS))) {
+        h->read_flags.assign(h->n_reads, 0);
+        if (st.n_branch && h->n_reads && h->n_bases) {
+            TRY(reserve(h, h->b_readflags, h->n_reads));
+            CK(cudaMemsetAsync(h->b_readflags.p, 0, h->n_reads, h->stream));
+            LAUNCH(k_g_pull_reads, blocks_for(h->n_bases), DBG_BLOCK, h->stream, ptr<const u8>(h->b_codes), d_off, h->n_reads,
+                   h->n_bases, k, ptr<const S>(h->b_table), n_nslots, ptr<const u8>(h->b_flags), ptr<u8>(h->b_readflags));
+            CKK();
+            CK(cudaMemcpyAsync(h->read_flags.data(), h->b_readflags.p, h->n_reads, cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+            uint64_t n = 0;
+            for (uint8_t f : h->read_flags) n += f;
+            st.n_pull_reads = n;
+        }
+        h->read_flags_valid = true;
+    }
+    const int e6 = ev_mark(h);
+    tm_set(h, &st.ms_lists, e3, e4);
+    tm_set(h, &st.ms_tips, e4, e5);
+    tm_set(h, &st.ms_pull_reads, e5, e6);
+    tm_set(h, &st.ms_build_total, e0, e6);
+    h->built = true;
+    return DBG_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
 // walk
 // -------------------------------------------------------------------------------------------------
 struct EnumFrame {
@@ -1212,17 +1407,38 @@ static int walk_impl(dbg_t *h, int stop_at_branch) {
     const uint64_t nb = h->branch.size();
     const bool enumerate = !stop_at_branch && nb > 0;
     std::vector<JunctionSucc> junc;
+    std::vector<u64> joff;                            // kept successors of branch i: junc[joff[i] .. joff[i + 1])
     std::vector<std::pair<u32, u32>> jindex;           // (slot, index in branch list), sorted by slot
     if (enumerate) {
-        TRY(reserve(h, h->b_junction, nb * 4 * sizeof(JunctionSucc)));
-        LAUNCH(k_junctions<W>, blocks_for(nb), DBG_BLOCK, h->stream, ptr<const S>(h->b_table), n_slots, h->k,
-               ptr<const u8>(h->b_flags), ptr<const u16>(h->b_kept), ptr<const u64>(h->b_link),
-               ptr<const u32>(h->b_branch), nb, ptr<JunctionSucc>(h->b_junction), d_ctr);
-        CKK();
+        joff.assign(nb + 1, 0);
+        if (h->sym_bits == GEN_BITS) {                 // any number of kept successors: their counts first
+            std::vector<u32> nk(nb);
+            TRY(reserve(h, h->b_cnt32, nb * 4));
+            LAUNCH(k_g_gather_u32, blocks_for(nb), DBG_BLOCK, h->stream, ptr<const u32>(h->b_enk), ptr<const u32>(h->b_branch),
+                   nb, ptr<u32>(h->b_cnt32));
+            CKK();
+            CK(cudaMemcpyAsync(nk.data(), h->b_cnt32.p, nb * 4, cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+            for (uint64_t i = 0; i < nb; i++) joff[i + 1] = joff[i] + nk[i];
+            TRY(reserve(h, h->b_off64, (nb + 1) * 8));
+            CK(cudaMemcpyAsync(h->b_off64.p, joff.data(), (nb + 1) * 8, cudaMemcpyHostToDevice, h->stream));
+            TRY(reserve(h, h->b_junction, (joff[nb] + 1) * sizeof(JunctionSucc)));
+            LAUNCH(k_g_junctions, blocks_for(nb), DBG_BLOCK, h->stream, ptr<const u8>(h->b_flags), ptr<const u32>(h->b_enk),
+                   ptr<const u32>(h->b_estart), ptr<const GEdge>(h->b_earr), ptr<const u64>(h->b_link),
+                   ptr<const u32>(h->b_branch), nb, ptr<const u64>(h->b_off64), ptr<JunctionSucc>(h->b_junction));
+            CKK();
+        } else {
+            for (uint64_t i = 0; i < nb; i++) joff[i + 1] = joff[i] + 4;          // 4 slots a node, unused ones say NONE32
+            TRY(reserve(h, h->b_junction, nb * 4 * sizeof(JunctionSucc)));
+            LAUNCH(k_junctions<W>, blocks_for(nb), DBG_BLOCK, h->stream, ptr<const S>(h->b_table), n_slots, h->k,
+                   ptr<const u8>(h->b_flags), ptr<const u16>(h->b_kept), ptr<const u64>(h->b_link),
+                   ptr<const u32>(h->b_branch), nb, ptr<JunctionSucc>(h->b_junction), d_ctr);
+            CKK();
+        }
         TRY(check_fault(h, "k_junctions"));
-        junc.resize(nb * 4);
-        CK(cudaMemcpyAsync(junc.data(), h->b_junction.p, nb * 4 * sizeof(JunctionSucc), cudaMemcpyDeviceToHost,
-                           h->stream));
+        junc.resize(joff[nb]);
+        if (joff[nb]) CK(cudaMemcpyAsync(junc.data(), h->b_junction.p, joff[nb] * sizeof(JunctionSucc), cudaMemcpyDeviceToHost,
+                                         h->stream));
         CK(cudaStreamSynchronize(h->stream));
         jindex.resize(nb);
         for (uint64_t i = 0; i < nb; i++) jindex[i] = std::make_pair(h->branch[i], (u32)i);
@@ -1264,14 +1480,14 @@ static int walk_impl(dbg_t *h, int stop_at_branch) {
                             "exponential in the reference too, debruijn.py:314)", (unsigned long long)MAX_ENUM_STEPS);
             EnumFrame &fr = stack.back();
             const u32 jv = fr.junction_index;
-            if (fr.next_child >= 4 || junc[(uint64_t)jv * 4 + fr.next_child].entry == NONE32) {
+            if ((u64)fr.next_child >= joff[jv + 1] - joff[jv] || junc[joff[jv] + fr.next_child].entry == NONE32) {
                 stack.pop_back();
                 on_path.pop_back();
                 if (!node_stack.empty()) { total_nodes = node_stack.back(); node_stack.pop_back(); }
                 segs.pop_back();
                 continue;
             }
-            const JunctionSucc js = junc[(uint64_t)jv * 4 + fr.next_child];
+            const JunctionSucc js = junc[joff[jv] + fr.next_child];
             fr.next_child++;
             if (js.kind == T_CYCLE) continue;
             if (js.kind == T_BRANCH) {
@@ -1489,6 +1705,7 @@ static int shard_walk_impl(dbg_t *h, const uint64_t *d_all, uint64_t n_total, ui
     DevCounters *d_ctr = ptr<DevCounters>(h->b_ctr);
     const int e0 = ev_mark_walk(h);
     h->scontigs.clear();
+    h->sview = nullptr; h->n_sview = 0;
     *n_contigs = 0;
     if (n_total >= 0xFFFFFFF0ull) return fail(h, DBG_ERR_OVERFLOW, "the reduced list exceeds 2^32 vertices");
     TRY(reserve(h, h->b_link2, (n_total + 1) * 8));
@@ -1511,17 +1728,22 @@ static int shard_walk_impl(dbg_t *h, const uint64_t *d_all, uint64_t n_total, ui
                ptr<const u64>(h->b_link2), (const u64 *)d_all, ptr<ShardContig>(h->b_scontig), &d_ctr->n_dropped);
         CKK();
     }
-    TRY(check_fault(h, "the ranking of the reduced list"));
+    if (ns) {
+        TRY(reserve_pinned(h, ns * sizeof(ShardContig)));
+        CK(cudaMemcpyAsync(h->pin, h->b_scontig.p, ns * sizeof(ShardContig), cudaMemcpyDeviceToHost, h->stream));
+    }
+    TRY(check_fault(h, "the ranking of the reduced list"));            // one host round trip: counters + records
     if (h->ctr.n_list_a > split_cap || h->ctr.n_list_b > super_cap)
         return fail(h, DBG_ERR_STATE, "splitter list overflow in the reduced walk");
-    const uint64_t nc = ns ? h->ctr.n_dropped : 0;          // (the cursor counts emitted records here)
-    h->scontigs.resize(nc);
-    if (nc) {
-        CK(cudaMemcpyAsync(h->scontigs.data(), h->b_scontig.p, nc * sizeof(ShardContig), cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaStreamSynchronize(h->stream));
-        std::sort(h->scontigs.begin(), h->scontigs.end(),
-                  [](const dbg_shard_contig_t &a, const dbg_shard_contig_t &b) { return a.tag < b.tag; });
+    const uint64_t n_drop = ns ? h->ctr.n_dropped : 0;
+    const dbg_shard_contig_t *recs = (const dbg_shard_contig_t *)h->pin;
+    if (n_drop == 0) { h->sview = recs; h->n_sview = ns; }
+    else {                                                              // starts on cycles / pulled starts emit nothing
+        h->scontigs.reserve(ns - n_drop);
+        for (uint64_t i = 0; i < ns; i++) if (recs[i].n_nodes) h->scontigs.push_back(recs[i]);
+        h->sview = h->scontigs.data(); h->n_sview = h->scontigs.size();
     }
+    const uint64_t nc = h->n_sview;
     st.n_contigs = nc;
     st.n_cycle_starts = 0;
     *n_contigs = nc;
@@ -1582,6 +1804,31 @@ DBG_API int dbg_create_ex(dbg_t **out, int device, int k, int key_words) {
     return DBG_OK;
 }
 
+DBG_API int dbg_create_alpha(dbg_t **out, int device, int k, const uint8_t *symbols, int n_symbols) {
+    if (!out) return fail(nullptr, DBG_ERR_ARG, "dbg_create_alpha: out is NULL");
+    *out = nullptr;
+    if (!symbols || n_symbols < 1 || n_symbols > GEN_MAX_SYMBOLS)
+        return fail(nullptr, DBG_ERR_ARG, "an alphabet has 1 .. %d symbols (got %d)", GEN_MAX_SYMBOLS, n_symbols);
+    if (k < 1 || k > GEN_MAX_K)
+        return fail(nullptr, DBG_ERR_ARG, "k = %d out of range for 5-bit symbols (1..%d)", k, GEN_MAX_K);
+    uint8_t code_of[256];
+    memset(code_of, 0xFF, sizeof code_of);
+    for (int i = 0; i < n_symbols; i++) {
+        if (code_of[symbols[i]] != 0xFF) return fail(nullptr, DBG_ERR_ARG, "symbol %d appears twice in the alphabet", (int)symbols[i]);
+        code_of[symbols[i]] = (uint8_t)i;
+    }
+    const int rc = dbg_create_ex(out, device, 1, 2);                   // 128-bit keys; k is set below (5 bits a symbol)
+    if (rc != DBG_OK) return rc;
+    dbg_t *h = *out;
+    h->k = k;
+    h->sym_bits = GEN_BITS;
+    h->n_symbols = n_symbols;
+    memset(h->sym_of_code, '?', sizeof h->sym_of_code);
+    memcpy(h->sym_of_code, symbols, (size_t)n_symbols);
+    memcpy(h->code_of_byte, code_of, sizeof code_of);
+    return DBG_OK;
+}
+
 DBG_API void dbg_destroy(dbg_t *h) {
     if (!h) return;
     cudaSetDevice(h->device);
@@ -1591,6 +1838,7 @@ DBG_API void dbg_destroy(dbg_t *h) {
                      &h->b_recs, &h->b_cnt32, &h->b_off64, &h->b_contig, &h->b_junction, &h->b_split, &h->b_h8, &h->b_bitmap,
                      &h->b_stmask, &h->b_vmask, &h->b_spanread, &h->b_cc, &h->b_ctable, &h->b_clist, &h->b_super, &h->b_readbatch, &h->b_ctable2, &h->b_scratch[0],
                      &h->b_scratch[1], &h->b_scratch[2], &h->b_scratch[3], &h->b_scratch[4], &h->b_scratch[5],
+                     &h->b_up, &h->b_codes, &h->b_etable, &h->b_earr, &h->b_earr2, &h->b_estart, &h->b_edeg, &h->b_enk, &h->b_lut,
                      &h->b_exitslot, &h->b_reqslot, &h->b_rvslot, &h->b_rvord, &h->b_link2, &h->b_scontig, &h->b_owneroff};
     for (DevBuf *b : all) if (b->p) cudaFree(b->p);
     for (int i = 0; i < EV_MAX; i++) cudaEventDestroy(h->ev[i]);
@@ -1642,6 +1890,7 @@ static int build_device_common(dbg_t *h, const uint8_t *d_bases, const uint64_t 
     h->chunks_valid = false;
     h->chunks_merged = false;
     h->built = h->walked = false;
+    h->up_ready = false;
     h->n_ev = 0;
     h->n_reads = n_reads;
     h->n_bases = n_bases;
@@ -1659,6 +1908,11 @@ static int build_device_common(dbg_t *h, const uint8_t *d_bases, const uint64_t 
     h->segments.clear();
     CK(cudaMemsetAsync(h->b_ctr.p, 0, sizeof(DevCounters), h->stream));
     h->table_ready = false;
+    if (h->sym_bits == GEN_BITS) {
+        if (d_read_batch || (flags & (DBG_TABLE_ONLY | DBG_CHUNKS_ONLY)))
+            return fail(h, DBG_ERR_ARG, "batched and multi-GPU builds exist for the DNA engine only");
+        return gen_build(h, (const u8 *)d_bases, (const u64 *)d_read_off);
+    }
     TRY(DISPATCH(build_impl, h, (const u8 *)d_bases, (const u64 *)d_read_off));
     if (flags & (DBG_TABLE_ONLY | DBG_CHUNKS_ONLY)) return DBG_OK;
     TRY(DISPATCH(graph_finalize, h));
@@ -1682,6 +1936,16 @@ static int stage_host_reads(dbg_t *h, const uint8_t *bases, const uint64_t *read
     return DBG_OK;
 }
 
+// The caller's buffers are its own again when dbg_build* returns -- also when it returns an error from the middle
+// of the slice loop, with copies of later slices still queued on the copy stream.
+static void release_host_reads(dbg_t *h, int rc) {
+    if (rc != DBG_OK) {
+        cudaStreamSynchronize(h->copy_stream);
+        cudaStreamSynchronize(h->stream);
+    }
+    h->host_bases = nullptr;
+}
+
 DBG_API int dbg_build_batched(dbg_t *h, const uint8_t *bases, const uint64_t *read_off, uint64_t n_reads,
                               const uint32_t *read_batch, uint32_t n_batches, double threshold, uint32_t flags) {
     if (!h) return DBG_ERR_ARG;
@@ -1699,7 +1963,7 @@ DBG_API int dbg_build_batched(dbg_t *h, const uint8_t *bases, const uint64_t *re
     if (n_reads) CK(cudaMemcpyAsync(h->b_readbatch.p, read_batch, n_reads * 4, cudaMemcpyHostToDevice, h->stream));
     const int rc = build_device_common(h, ptr<const uint8_t>(h->b_bases), ptr<const uint64_t>(h->b_off), n_reads, n_bases,
                                        0, threshold, flags, ptr<const uint32_t>(h->b_readbatch), n_batches);
-    h->host_bases = nullptr;
+    release_host_reads(h, rc);
     return rc;
 }
 
@@ -1723,11 +1987,11 @@ DBG_API int dbg_build(dbg_t *h, const uint8_t *bases, const uint64_t *read_off, 
     TRY(stage_host_reads(h, bases, read_off, n_reads, n_bases));
     const int rc = build_device_common(h, ptr<const uint8_t>(h->b_bases), ptr<const uint64_t>(h->b_off), n_reads, n_bases,
                                        read_idx_base, threshold, flags, nullptr, 0);
-    h->host_bases = nullptr;
+    release_host_reads(h, rc);
     return rc;
 }
 
-#define NEED_TABLE() do { if (!h) return DBG_ERR_ARG; if (!h->table_ready) return fail(h, DBG_ERR_STATE, "%s needs a node table (dbg_build* or dbg_table_reset first)", __func__); } while (0)
+#define NEED_TABLE() do { if (!h) return DBG_ERR_ARG; if (h->sym_bits != 2) return fail(h, DBG_ERR_STATE, "%s exists for the DNA engine only", __func__); if (!h->table_ready) return fail(h, DBG_ERR_STATE, "%s needs a node table (dbg_build* or dbg_table_reset first)", __func__); } while (0)
 
 DBG_API int dbg_graph_stage(dbg_t *h, int stage, double threshold, uint32_t flags) {
     NEED_TABLE();
@@ -1739,6 +2003,7 @@ DBG_API int dbg_graph_stage(dbg_t *h, int stage, double threshold, uint32_t flag
         h->threshold = threshold;
         h->build_flags = flags;
         h->built = h->walked = false;
+        h->up_ready = false;
         return DISPATCH(graph_finalize, h);
     }
     if (stage == 1) return DISPATCH(graph_order_scan, h);
@@ -1765,6 +2030,7 @@ DBG_API int dbg_export_records(dbg_t *h, uint32_t n_parts, const uint64_t *count
 
 DBG_API int dbg_table_reset(dbg_t *h, uint64_t expected_nodes) {
     if (!h) return DBG_ERR_ARG;
+    if (h->sym_bits != 2) return fail(h, DBG_ERR_STATE, "dbg_table_reset exists for the DNA engine only");
     CK(cudaSetDevice(h->device));
     return DISPATCH(table_reset_impl, h, expected_nodes);
 }
@@ -1789,7 +2055,7 @@ DBG_API int dbg_order_merge(dbg_t *h, const uint64_t *d_records, uint64_t n) {
     return DISPATCH(order_merge_impl, h, d_records, n);
 }
 
-#define NEED_CHUNKS() do { if (!h) return DBG_ERR_ARG; if (!h->chunks_valid) return fail(h, DBG_ERR_STATE, "%s needs a chunk table (dbg_build* with DBG_CHUNKS_ONLY, or dbg_chunk_table_reset, first)", __func__); } while (0)
+#define NEED_CHUNKS() do { if (!h) return DBG_ERR_ARG; if (h->sym_bits != 2) return fail(h, DBG_ERR_STATE, "%s exists for the DNA engine only", __func__); if (!h->chunks_valid) return fail(h, DBG_ERR_STATE, "%s needs a chunk table (dbg_build* with DBG_CHUNKS_ONLY, or dbg_chunk_table_reset, first)", __func__); } while (0)
 
 DBG_API int dbg_chunk_record_words(const dbg_t *h) { return h ? (h->W == 1 ? 4 : 8) : 0; }
 
@@ -1809,6 +2075,7 @@ DBG_API int dbg_chunk_export_records(dbg_t *h, uint32_t n_parts, const uint64_t 
 
 DBG_API int dbg_chunk_table_reset(dbg_t *h, uint64_t expected_chunks) {
     if (!h) return DBG_ERR_ARG;
+    if (h->sym_bits != 2) return fail(h, DBG_ERR_STATE, "dbg_chunk_table_reset exists for the DNA engine only");
     CK(cudaSetDevice(h->device));
     return DISPATCH(chunk_table_reset_impl, h, expected_chunks);
 }
@@ -1875,6 +2142,32 @@ DBG_API int dbg_export_nodes(dbg_t *h, uint32_t *node_id, uint64_t *key_lo, uint
     NEED_BUILT();
     CK(cudaSetDevice(h->device));
     return DISPATCH(export_impl, h, node_id, key_lo, key_hi, first_tag, succ_cnt, flags, kept);
+}
+
+DBG_API int dbg_export_edges(dbg_t *h, uint32_t *src_id, uint32_t *dst_id, uint8_t *symbol, uint32_t *count, uint8_t *kept) {
+    NEED_BUILT();
+    if (h->sym_bits != GEN_BITS) return fail(h, DBG_ERR_STATE, "dbg_export_edges is the generic-alphabet engine's export; the DNA engine "
+                                             "reports successor counts per node (dbg_export_nodes)");
+    const uint64_t n = h->n_earr;
+    if (n == 0) return DBG_OK;
+    CK(cudaSetDevice(h->device));
+    DevBuf *s = h->b_scratch;
+    TRY(reserve(h, s[0], n * 4));
+    TRY(reserve(h, s[1], n * 4));
+    TRY(reserve(h, s[2], n * 4));
+    TRY(reserve(h, s[3], n));
+    TRY(reserve(h, s[4], n));
+    LAUNCH(k_g_export_edges, blocks_for(n), DBG_BLOCK, h->stream, ptr<const GEdge>(h->b_earr), n, ptr<const u32>(h->b_estart),
+           ptr<const u32>(h->b_enk), ptr<const u8>(h->b_lut) + 256, ptr<u32>(s[0]), ptr<u32>(s[1]), ptr<u8>(s[3]), ptr<u32>(s[2]),
+           ptr<u8>(s[4]));
+    CKK();
+    if (src_id) CK(cudaMemcpyAsync(src_id, s[0].p, n * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (dst_id) CK(cudaMemcpyAsync(dst_id, s[1].p, n * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (count) CK(cudaMemcpyAsync(count, s[2].p, n * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (symbol) CK(cudaMemcpyAsync(symbol, s[3].p, n, cudaMemcpyDeviceToHost, h->stream));
+    if (kept) CK(cudaMemcpyAsync(kept, s[4].p, n, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return DBG_OK;
 }
 
 DBG_API int dbg_branch_nodes(dbg_t *h, uint32_t *node_id) {
@@ -1967,8 +2260,8 @@ DBG_API int dbg_shard_walk(dbg_t *h, const uint64_t *d_all_records, uint64_t n_t
 
 DBG_API int dbg_shard_contigs(dbg_t *h, dbg_shard_contig_t *out) {
     NEED_SHARD(5);
-    if (h->scontigs.size() && !out) return fail(h, DBG_ERR_ARG, "NULL output");
-    if (h->scontigs.size()) memcpy(out, h->scontigs.data(), h->scontigs.size() * sizeof(dbg_shard_contig_t));
+    if (h->n_sview && !out) return fail(h, DBG_ERR_ARG, "NULL output");
+    if (h->n_sview) memcpy(out, h->sview, h->n_sview * sizeof(dbg_shard_contig_t));
     return DBG_OK;
 }
 
@@ -2007,6 +2300,10 @@ static int lookup_impl(dbg_t *h, const uint8_t *q, const uint32_t *batch, uint64
     TRY(reserve(h, s[2], n * 4));
     CK(cudaMemcpyAsync(s[0].p, q, bytes, cudaMemcpyHostToDevice, h->stream));
     if (batch) CK(cudaMemcpyAsync(s[2].p, batch, n * 4, cudaMemcpyHostToDevice, h->stream));
+    if (h->sym_bits == GEN_BITS)
+        LAUNCH(k_g_lookup_edges, blocks_for(n), DBG_BLOCK, h->stream, ptr<const Slot<2>>(h->b_etable), h->n_eslots, h->k,
+               ptr<const u8>(h->b_lut), ptr<const u8>(s[0]), n, ptr<u32>(s[1]));
+    else
     LAUNCH(k_lookup_edges<W>, blocks_for(n), DBG_BLOCK, h->stream, ptr<const Slot<W>>(h->b_table), h->n_slots, h->k,
            ptr<const u8>(s[0]), batch ? ptr<const u32>(s[2]) : (const u32 *)nullptr, n, ptr<u32>(s[1]));
     CKK();
@@ -2028,7 +2325,7 @@ DBG_API int dbg_lookup_edges_batched(dbg_t *h, const uint8_t *kplus1mers, const 
     NEED_BUILT();
     if (n == 0) return DBG_OK;
     if (!kplus1mers || !counts || !batch) return fail(h, DBG_ERR_ARG, "NULL argument");
-    if (!h->batch_bits && h->n_batches == 0) return fail(h, DBG_ERR_STATE, "the graph was not built by dbg_build_batched");
+    if (h->sym_bits != 2 || (!h->batch_bits && h->n_batches == 0)) return fail(h, DBG_ERR_STATE, "the graph was not built by dbg_build_batched");
     for (uint64_t i = 0; i < n; i++)
         if (batch[i] >= h->n_batches) return fail(h, DBG_ERR_ARG, "batch id %u out of range", batch[i]);
     CK(cudaSetDevice(h->device));
@@ -2069,6 +2366,22 @@ static void contig_segments(const dbg_t *h, const dbg_contig_t &c, std::vector<d
         out.push_back(dbg_segment_t{c.start, c.n_nodes});
 }
 
+// up[j][v] = succ^(2^(j+1))(v) for the strings / scores kernels; once per build, on first use
+static int ensure_lift(dbg_t *h) {
+    if (h->up_ready) return DBG_OK;
+    const uint64_t n = h->n_slots;
+    TRY(reserve(h, h->b_up, (uint64_t)LIFT_LEVELS * n * 4));
+    const u32 *prev = ptr<const u32>(h->b_succ);
+    for (int j = 0; j < LIFT_LEVELS; j++) {
+        u32 *next = ptr<u32>(h->b_up) + (uint64_t)j * n;
+        LAUNCH(k_lift, blocks_for(n), DBG_BLOCK, h->stream, prev, next, n);
+        CKK();
+        prev = next;
+    }
+    h->up_ready = true;
+    return DBG_OK;
+}
+
 template <int W>
 static int materialize_impl(dbg_t *h, const uint64_t *idx, uint64_t n, char *buf, const uint64_t *off) {
     std::vector<SegJob> jobs;
@@ -2095,8 +2408,10 @@ static int materialize_impl(dbg_t *h, const uint64_t *idx, uint64_t n, char *buf
     TRY(reserve(h, s[0], jobs.size() * sizeof(SegJob)));
     TRY(reserve(h, s[1], total));
     CK(cudaMemcpyAsync(s[0].p, jobs.data(), jobs.size() * sizeof(SegJob), cudaMemcpyHostToDevice, h->stream));
-    LAUNCH(k_materialize<W>, blocks_for(jobs.size()), DBG_BLOCK, h->stream, ptr<const Slot<W>>(h->b_table), h->k,
-           ptr<const u32>(h->b_succ), ptr<const SegJob>(s[0]), (u64)jobs.size(), ptr<char>(s[1]));
+    TRY(ensure_lift(h));
+    LAUNCH((k_materialize<W>), jobs.size(), LIFT_BLOCK, h->stream, ptr<const Slot<W>>(h->b_table), h->n_slots, h->k,
+           ptr<const u32>(h->b_succ), ptr<const u32>(h->b_up),
+           h->sym_bits == GEN_BITS ? ptr<const u8>(h->b_lut) + 256 : (const u8 *)nullptr, ptr<const SegJob>(s[0]), ptr<char>(s[1]));
     CKK();
     // strings may be requested with gaps between them: copy each back to where the caller wants it
     uint64_t lo = off[0], hi = 0;
@@ -2137,8 +2452,12 @@ static int scores_impl(dbg_t *h, const uint64_t *idx, uint64_t n, uint64_t *scor
     CK(cudaMemcpyAsync(s[0].p, entry.data(), entry.size() * 4, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(s[1].p, nodes.data(), nodes.size() * 4, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(s[2].p, jobs.data(), n * sizeof(ScoreJob), cudaMemcpyHostToDevice, h->stream));
-    LAUNCH(k_scores<W>, blocks_for(n), DBG_BLOCK, h->stream, ptr<const Slot<W>>(h->b_table), ptr<const u32>(h->b_succ),
-           ptr<const u32>(s[0]), ptr<const u32>(s[1]), ptr<const ScoreJob>(s[2]), n, ptr<u64>(s[3]));
+    TRY(ensure_lift(h));
+    const bool gen = h->sym_bits == GEN_BITS;
+    LAUNCH((k_scores<W>), n, LIFT_BLOCK, h->stream, ptr<const Slot<W>>(h->b_table), h->n_slots, ptr<const u16>(h->b_kept),
+           ptr<const u32>(h->b_succ), ptr<const u32>(h->b_up), gen ? ptr<const GEdge>(h->b_earr) : (const GEdge *)nullptr,
+           gen ? ptr<const u32>(h->b_estart) : (const u32 *)nullptr, gen ? ptr<const u32>(h->b_edeg) : (const u32 *)nullptr,
+           ptr<const u32>(s[0]), ptr<const u32>(s[1]), ptr<const ScoreJob>(s[2]), ptr<u64>(s[3]));
     CKK();
     CK(cudaMemcpyAsync(scores, s[3].p, n * 8, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));

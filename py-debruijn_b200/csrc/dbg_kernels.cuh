@@ -761,65 +761,144 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_junctions(const Slot<W> *__restri
 }
 
 // ---------------------------------------------------------------------------------------------
-// strings and scores: one thread per segment walks succ[] (debruijn.py:298-300: first node's
-// label, then the last base of every later node).
+// strings and scores (debruijn.py:298-300; II_assembleFromReads.py:14-18).  A contig is a chain of up
+// to 10^5..10^8 nodes, and "first node's label, then the last base of every later node" walked node by
+// node is that many DEPENDENT loads on one thread.  Instead the successor array is lifted once per
+// build: up[j][v] = succ^(2^(j+1))(v), j = 0..LIFT_LEVELS-1 (pointer doubling), and a block of 2^LIFT_LEVELS threads takes
+// one chain segment: thread t reaches node t with <= LIFT_LEVELS hops, then strides 2^LIFT_LEVELS nodes a hop, so
+// consecutive threads write consecutive characters (coalesced) and the dependent chain is n / 256 long.
 // ---------------------------------------------------------------------------------------------
+#define LIFT_LEVELS 8
+#define LIFT_BLOCK (1 << LIFT_LEVELS)
 struct SegJob {
     u32 entry, n_nodes;
     u64 out;            // offset into the char buffer
     u32 first;          // 1 = first segment of its contig: write the whole entry label
     u32 pad;
 };
-
-template <int W>
-__global__ void __launch_bounds__(DBG_BLOCK) k_materialize(const Slot<W> *__restrict__ table, int k,
-                                                           const u32 *__restrict__ succ,
-                                                           const SegJob *__restrict__ jobs, u64 n_jobs,
-                                                           char *__restrict__ buf) {
-    typedef typename KeyOf<W>::type K;
-    u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n_jobs) return;
-    SegJob job = jobs[j];
-    if (job.n_nodes == 0) return;
-    const u32 ALPHA = 0x54474341u;
-    u32 v = job.entry;
-    char *o = buf + job.out;
-    K key = table[v].key;
-    if (job.first) {
-        for (int i = 0; i < k; i++) *o++ = (char)((ALPHA >> (8 * key_base(key, k, i))) & 0xFF);
-    } else {
-        *o++ = (char)((ALPHA >> (8 * key_last_base(key))) & 0xFF);
-    }
-    for (u32 i = 1; i < job.n_nodes; i++) {
-        v = succ[v];
-        *o++ = (char)((ALPHA >> (8 * key_last_base(table[v].key))) & 0xFF);
-    }
-}
-
 struct ScoreJob {
     u64 seg_begin, seg_end;     // into the uploaded segment array
 };
+
+__global__ void __launch_bounds__(DBG_BLOCK) k_lift(const u32 *__restrict__ prev, u32 *__restrict__ next, u64 n_slots) {
+    const u64 v = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n_slots) return;
+    const u32 a = prev[v];
+    next[v] = (a == NONE32 || a >= n_slots) ? NONE32 : prev[a];     // a >= n_slots: a sharded table keeps remote ids there
+}
+
+// node t hops after `entry` (t < 2^LIFT_LEVELS); level 0 = succ, level j = up + (j-1) * n_slots
+DBG_D u32 lift_to(const u32 *__restrict__ succ, const u32 *__restrict__ up, u64 n_slots, u32 entry, u32 t) {
+    u32 v = entry;
+    if (t & 1u) v = succ[v];
+#pragma unroll
+    for (int j = 1; j < LIFT_LEVELS; j++)
+        if (((t >> j) & 1u) && v != NONE32) v = up[(u64)(j - 1) * n_slots + v];
+    return v;
+}
+
+// last symbol / symbol i of a node label as a character: 2-bit DNA keys or 5-bit generic keys (lut = code -> byte)
+template <int W> DBG_D char label_last_char(typename KeyOf<W>::type key, const u8 *__restrict__ lut) {
+    if (lut) return (char)lut[(u32)key_lo64(key) & 31u];
+    return (char)((0x54474341u >> (8 * key_last_base(key))) & 0xFFu);
+}
+DBG_D u32 key_symbol5(u64, int, int) { return 0; }                   // 64-bit keys are DNA only
+DBG_D u32 key_symbol5(K128 key, int n, int j) {
+    const int sh = 5 * (n - 1 - j);
+    if (sh >= 64) return (u32)(key.hi >> (sh - 64)) & 31u;
+    u64 x = key.lo >> sh;
+    if (sh + 5 > 64) x |= key.hi << (64 - sh);
+    return (u32)x & 31u;
+}
+template <int W> DBG_D char label_char(typename KeyOf<W>::type key, int k, int i, const u8 *__restrict__ lut) {
+    if (lut) return (char)lut[key_symbol5(key, k, i)];
+    return (char)((0x54474341u >> (8 * key_base(key, k, i))) & 0xFFu);
+}
+
 template <int W>
-__global__ void __launch_bounds__(DBG_BLOCK) k_scores(const Slot<W> *__restrict__ table,
-                                                      const u32 *__restrict__ succ,
-                                                      const u32 *__restrict__ seg_entry,
-                                                      const u32 *__restrict__ seg_nodes,
-                                                      const ScoreJob *__restrict__ jobs, u64 n_jobs,
-                                                      u64 *__restrict__ scores) {
-    u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n_jobs) return;
-    ScoreJob job = jobs[j];
-    u64 total = 0;
-    u32 prev = NONE32;
-    for (u64 s = job.seg_begin; s < job.seg_end; s++) {
-        u32 v = seg_entry[s];
-        for (u32 i = 0; i < seg_nodes[s]; i++) {
-            if (i) v = succ[v];
-            if (prev != NONE32) total += table[prev].cnt[key_last_base(table[v].key)];
-            prev = v;
-        }
+__global__ void __launch_bounds__(LIFT_BLOCK) k_materialize(const Slot<W> *__restrict__ table, u64 n_slots, int k,
+                                                            const u32 *__restrict__ succ, const u32 *__restrict__ up,
+                                                            const u8 *__restrict__ lut, const SegJob *__restrict__ jobs,
+                                                            char *__restrict__ buf) {
+    const SegJob job = jobs[blockIdx.x];
+    const u32 n = job.n_nodes, t = threadIdx.x;
+    if (n == 0) return;
+    char *o = buf + job.out;
+    u64 shift = 0;                                                   // node i writes its last character at o[shift + i]
+    if (job.first) {
+        const typename KeyOf<W>::type key = table[job.entry].key;
+        for (int i = (int)t; i < k; i += LIFT_BLOCK) o[i] = label_char<W>(key, k, i, lut);
+        shift = (u64)k - 1;                                          // node 0's last character is o[k - 1], written above
     }
-    scores[j] = total;
+    if (t >= n) return;
+    u32 v = lift_to(succ, up, n_slots, job.entry, t);
+    const u32 *top = up + (u64)(LIFT_LEVELS - 1) * n_slots;          // succ^(2^LIFT_LEVELS)
+    for (u32 i = t; i < n && v != NONE32; i += LIFT_BLOCK) {
+        if (i || !job.first) o[shift + i] = label_last_char<W>(table[v].key, lut);
+        v = top[v];
+    }
+}
+
+// edge of the generic-alphabet engine (dbg_generic.cuh): one distinct (k+1)-mer
+struct GEdge {
+    u32 src, dst;                          // node-table slots
+    u32 cnt;                               // multiplicity of the (k+1)-mer
+    u32 sym;                               // code of its last symbol
+    u64 first;                             // tag of its first appearance
+};
+
+// getScore: sum of the counts of the edges along a contig.  Inside a segment every edge is the single kept
+// successor of its source (DNA: cnt[kept base]; generic: the first edge of the node's run); between two segments
+// (final=True: the path runs through a multi-successor node) it is looked up by the pair (last node, next entry).
+template <int W>
+DBG_D u32 edge_count_between(const Slot<W> *__restrict__ table, const GEdge *__restrict__ ge, const u32 *__restrict__ estart,
+                             const u32 *__restrict__ edeg, u32 a, u32 b) {
+    if (ge) {
+        const u32 s = estart[a], m = edeg[a];
+        for (u32 q = 0; q < m; q++) if (ge[s + q].dst == b) return ge[s + q].cnt;
+        return 0;
+    }
+    return table[a].cnt[key_last_base(table[b].key)];
+}
+
+template <int W>
+__global__ void __launch_bounds__(LIFT_BLOCK) k_scores(const Slot<W> *__restrict__ table, u64 n_slots,
+                                                       const u16 *__restrict__ kept, const u32 *__restrict__ succ,
+                                                       const u32 *__restrict__ up, const GEdge *__restrict__ ge,
+                                                       const u32 *__restrict__ estart, const u32 *__restrict__ edeg,
+                                                       const u32 *__restrict__ seg_entry, const u32 *__restrict__ seg_nodes,
+                                                       const ScoreJob *__restrict__ jobs, u64 *__restrict__ scores) {
+    __shared__ u64 s_sum[LIFT_BLOCK / 32];
+    __shared__ u32 s_last;
+    const ScoreJob job = jobs[blockIdx.x];
+    const u32 t = threadIdx.x;
+    const u32 *top = up + (u64)(LIFT_LEVELS - 1) * n_slots;
+    u64 total = 0;
+    u32 prev_last = NONE32;
+    for (u64 s = job.seg_begin; s < job.seg_end; s++) {
+        const u32 entry = seg_entry[s], n = seg_nodes[s];
+        if (n == 0) continue;
+        if (t == 0 && prev_last != NONE32) total += edge_count_between<W>(table, ge, estart, edeg, prev_last, entry);
+        if (t < n) {
+            u32 v = lift_to(succ, up, n_slots, entry, t);
+            for (u32 i = t; i < n && v != NONE32; i += LIFT_BLOCK) {
+                if (i + 1 < n) total += ge ? ge[estart[v]].cnt : table[v].cnt[kept_base(kept[v], 0)];
+                else s_last = v;
+                v = top[v];
+            }
+        }
+        __syncthreads();
+        prev_last = s_last;
+        __syncthreads();
+    }
+    for (int d = 16; d > 0; d >>= 1) total += __shfl_down_sync(0xFFFFFFFFu, total, d);
+    if ((t & 31) == 0) s_sum[t >> 5] = total;
+    __syncthreads();
+    if (t == 0) {
+        u64 x = 0;
+        for (int q = 0; q < LIFT_BLOCK / 32; q++) x += s_sum[q];
+        scores[blockIdx.x] = x;
+    }
 }
 
 template <int W>

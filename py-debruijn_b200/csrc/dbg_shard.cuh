@@ -243,34 +243,31 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_emit_reduced(const Slot<W> *__res
                                                             const u32 *__restrict__ starts, u64 n_starts,
                                                             const u32 *__restrict__ rv_ord, u64 my_base, u32 my_rank,
                                                             const u64 *__restrict__ link, const u64 *__restrict__ recs,
-                                                            ShardContig *__restrict__ out, u64 *cursor) {
+                                                            ShardContig *__restrict__ out, u64 *n_dropped) {
+    // one record per start, in start order (the start list is sorted by tag); n_nodes == 0 = nothing emitted
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    bool emit = false;
-    ShardContig c;
+    bool dropped = false;
     if (i < n_starts) {
         const u32 s = starts[i];
         const u32 r0 = (u32)(my_base + rv_ord[s]);
         u32 R = r0, h = 0;
+        ShardContig c;
+        c.tag = table[s].tag;
+        c.start_slot = s; c.start_rank = my_rank;
+        c.terminal_slot = NONE32; c.terminal_rank = 0; c.n_nodes = 0; c.kind = T_CYCLE;
         if (resolve_chain(link, r0, &R, &h)) {
             const u64 w0 = recs[2 * (u64)R], w1 = recs[2 * (u64)R + 1];
             const u32 info = (u32)(w1 >> 32), kind = info & 0xFFu;
             if (kind != T_CYCLE) {
                 const u32 total = link_dist_add(h, (u32)(w0 >> 32));
-                c.tag = table[s].tag;
-                c.start_slot = s; c.start_rank = my_rank;
                 c.terminal_slot = (u32)w1; c.terminal_rank = info >> 8;
                 c.kind = kind;
                 c.n_nodes = kind == T_PULLED ? total : total + 1;
-                emit = c.n_nodes != 0;
             }
         }
+        dropped = c.n_nodes == 0;
+        out[i] = c;
     }
-    // compaction keeps the start order inside a warp; the host sorts by tag anyway
-    const u32 b = __ballot_sync(0xFFFFFFFFu, emit);
-    if (!b) return;
-    const u32 lane = threadIdx.x & 31;
-    u64 base = 0;
-    if (lane == 0) base = atomicAdd(cursor, (u64)__popc(b));
-    base = __shfl_sync(0xFFFFFFFFu, base, 0);
-    if (emit) out[base + __popc(b & ((1u << lane) - 1))] = c;
+    const u32 b = __ballot_sync(0xFFFFFFFFu, dropped);
+    if (b && (threadIdx.x & 31) == 0) atomicAdd(n_dropped, (u64)__popc(b));
 }

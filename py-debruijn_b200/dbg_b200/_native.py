@@ -18,7 +18,7 @@ CSRC = os.path.join(PKG_DIR, 'csrc')
 LIB_DIR = os.path.join(PKG_DIR, 'lib')
 LIB_PATH = os.path.join(LIB_DIR, 'libdbg_b200.so')
 SOURCES = ('dbg_b200.cu',)
-HEADERS = ('dbg_common.cuh', 'dbg_kernels.cuh', 'dbg_chunks.cuh', 'dbg_shard.cuh')
+HEADERS = ('dbg_common.cuh', 'dbg_kernels.cuh', 'dbg_chunks.cuh', 'dbg_shard.cuh', 'dbg_generic.cuh')
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-shared', '-Xcompiler', '-fPIC']
@@ -70,6 +70,7 @@ _P = C.c_void_p
 SYMBOLS = {
     'dbg_create': (C.c_int, [C.POINTER(_P), C.c_int, C.c_int]),
     'dbg_create_ex': (C.c_int, [C.POINTER(_P), C.c_int, C.c_int, C.c_int]),
+    'dbg_create_alpha': (C.c_int, [C.POINTER(_P), C.c_int, C.c_int, _P, C.c_int]),
     'dbg_destroy': (None, [_P]),
     'dbg_last_error': (C.c_char_p, [_P]),
     'dbg_set_stream': (C.c_int, [_P, _P]),
@@ -104,6 +105,7 @@ SYMBOLS = {
     'dbg_shard_walk': (C.c_int, [_P, _P, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64)]),
     'dbg_shard_contigs': (C.c_int, [_P, _P]),
     'dbg_export_nodes': (C.c_int, [_P] + [_P] * 7),
+    'dbg_export_edges': (C.c_int, [_P] + [_P] * 5),
     'dbg_branch_nodes': (C.c_int, [_P, _P]),
     'dbg_pulled_nodes': (C.c_int, [_P, _P]),
     'dbg_pull_reads': (C.c_int, [_P, _P]),
@@ -118,6 +120,10 @@ SYMBOLS = {
 }
 
 
+class AlphabetError(ValueError):
+    """A read holds a byte outside the handle's alphabet (DBG_ERR_ALPHABET)."""
+
+
 class DbgError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__('dbg_b200 error %d: %s' % (code, msg))
@@ -127,7 +133,7 @@ class DbgError(RuntimeError):
 def _raise(code, msg):
     """Map the C status codes onto the exceptions the reference would raise."""
     if code == DBG_ERR_ALPHABET:
-        raise ValueError('dbg_b200: only the DNA alphabet ACGT is supported on the B200 path (%s)' % msg)
+        raise AlphabetError('dbg_b200: %s' % msg)
     if code == DBG_ERR_ZERODIV:
         raise ZeroDivisionError('division by zero')            # debruijn.py:163 with threshold == 0
     if code == DBG_ERR_NOMEM:

@@ -83,10 +83,11 @@ class _Clock:
         self.t0 = now
 
 
-def _fence(dev):
-    """The library runs on its own stream: make the host wait for torch's collectives before the
-    library reads what they wrote (the library itself returns only after its stream is idle)."""
-    if dev.type == 'cuda':
+def _fence(dev, graph=None):
+    """A handle that runs on its own stream must not read what a torch collective wrote before the
+    collective is done: make the host wait for it.  A handle set to torch's current stream
+    (Graph.set_stream) is ordered behind the collective by the stream itself -- no host wait."""
+    if dev.type == 'cuda' and not (graph is not None and graph.shares_stream(torch.cuda.current_stream(dev).cuda_stream)):
         torch.cuda.current_stream(dev).synchronize()
 
 
@@ -117,7 +118,7 @@ def build_shard(graph: Graph, local_packed, read_idx_base, group=None, clock=Non
     rc = _exchange_counts(counts, dev, group)
     recv = torch.empty((sum(rc), cw), dtype=torch.int64, device=dev)
     dist.all_to_all_single(recv, send, output_split_sizes=rc, input_split_sizes=[int(c) for c in counts], group=group)
-    _fence(dev)
+    _fence(dev, graph)
     if stats is not None:
         stats['exchange_bytes_out'] = int(counts.sum() - counts[rank]) * cw * 8
     if clock:
@@ -140,7 +141,7 @@ def _replicate(graph: Graph, threshold, final, exact_order, pull_reads, group, c
     shard = torch.empty((int(c1[0]), rw), dtype=torch.int64, device=dev)
     graph.export_records(1, c1, shard.data_ptr())
     everything, ns = _all_gather_var(shard, group)
-    _fence(dev)
+    _fence(dev, graph)
     if clock:
         clock.tick('gather_ms')
     graph.table_reset(max(1, sum(ns)))
@@ -158,7 +159,7 @@ def _replicate(graph: Graph, threshold, final, exact_order, pull_reads, group, c
         mine = torch.empty((cap, ow), dtype=torch.int64, device=dev)
         n = graph.order_export(mine.data_ptr(), cap)
         allrec, _ = _all_gather_var(mine[:n].contiguous(), group)
-        _fence(dev)
+        _fence(dev, graph)
         graph.order_merge(allrec.data_ptr(), allrec.shape[0])
     graph.graph_stage(2, threshold, final, exact_order, pull_reads)
     if clock:
@@ -234,7 +235,7 @@ def build_sharded(graph: Graph, local_packed, read_idx_base, threshold=3, final=
     sc = [int(c) for c in counts]
     req = torch.empty((sum(rc), W), dtype=torch.int64, device=dev)
     dist.all_to_all_single(req, exit_keys, output_split_sizes=rc, input_split_sizes=sc, group=group)
-    _fence(dev)
+    _fence(dev, graph)
     graph.shard_mark_entries(req.data_ptr(), req.shape[0])
     n_rv = graph.shard_rank_local()
     nrv = torch.tensor([n_rv], dtype=torch.int64, device=dev)
@@ -247,11 +248,11 @@ def build_sharded(graph: Graph, local_packed, read_idx_base, threshold=3, final=
     graph.shard_entry_ordinals(ords.data_ptr())
     replies = torch.empty((n_exit,), dtype=torch.int32, device=dev)
     dist.all_to_all_single(replies, ords, output_split_sizes=sc, input_split_sizes=rc, group=group)
-    _fence(dev)
+    _fence(dev, graph)
     mine = torch.empty((n_rv, 2), dtype=torch.int64, device=dev)
     graph.shard_reduced_records(replies.data_ptr(), rid_base, mine.data_ptr())
     everything, _ = _all_gather_var(mine, group)
-    _fence(dev)
+    _fence(dev, graph)
     if stats is not None:
         stats['walk_bytes_out'] = (n_exit - sc[rank]) * W * 8 + (sum(rc) - rc[rank]) * 4 + n_rv * 16 * (world - 1)
     contigs = graph.shard_walk(everything.data_ptr(), everything.shape[0], int(rid_base[rank]))

@@ -37,27 +37,32 @@ def pack_reads(reads):
     off = np.zeros(n + 1, dtype=np.uint64)
     np.cumsum(lens, out=off[1:])
     try:
-        data = ''.join(reads).encode('ascii')
+        data = ''.join(reads).encode('latin-1')
     except UnicodeEncodeError as e:
-        raise ValueError('dbg_b200: only the DNA alphabet ACGT is supported on the B200 path') from e
+        raise ValueError('dbg_b200: reads must be strings of single-byte characters') from e
     bases = np.frombuffer(data, dtype=np.uint8)
     return bases, off
 
 
-def decode_keys(key_lo, key_hi, k):
-    """2-bit keys (first base most significant) -> list[str]."""
+def decode_keys(key_lo, key_hi, k, bits=2, symbols=_ALPHA):
+    """Packed keys (`bits` per symbol, first symbol most significant) -> list[str]."""
     n = len(key_lo)
     if n == 0:
         return []
-    shifts = 2 * (k - 1 - np.arange(k, dtype=np.int64))
+    shifts = bits * (k - 1 - np.arange(k, dtype=np.int64))
     lo = np.asarray(key_lo, dtype=np.uint64)[:, None]
+    hi = np.asarray(key_hi, dtype=np.uint64)[:, None]
+    mask = np.uint64((1 << bits) - 1)
     codes = np.empty((n, k), dtype=np.uint8)
-    low = shifts < 64
-    codes[:, low] = ((lo >> shifts[low].astype(np.uint64)) & np.uint64(3)).astype(np.uint8)
-    if not low.all():
-        hi = np.asarray(key_hi, dtype=np.uint64)[:, None]
-        codes[:, ~low] = ((hi >> (shifts[~low] - 64).astype(np.uint64)) & np.uint64(3)).astype(np.uint8)
-    chars = _ALPHA[codes]
+    low = shifts + bits <= 64                       # the symbol lies in the low word
+    high = shifts >= 64                             # ... in the high word
+    codes[:, low] = ((lo >> shifts[low].astype(np.uint64)) & mask).astype(np.uint8)
+    if high.any():
+        codes[:, high] = ((hi >> (shifts[high] - 64).astype(np.uint64)) & mask).astype(np.uint8)
+    for j in np.nonzero(~low & ~high)[0]:           # straddles the two words (5-bit symbols only)
+        sh = int(shifts[j])
+        codes[:, j] = (((lo[:, 0] >> np.uint64(sh)) | (hi[:, 0] << np.uint64(64 - sh))) & mask).astype(np.uint8)
+    chars = np.asarray(symbols, dtype=np.uint8)[codes]
     return chars.view('S%d' % k).ravel().astype('U%d' % k).tolist()
 
 
@@ -73,12 +78,18 @@ class Graph:
     """One de Bruijn graph resident on one GPU (one ``dbg_t``).  Re-usable: ``build`` may be
     called again with new reads and keeps its HBM."""
 
-    def __init__(self, k, device=None, lib=None, key_words=0):
+    def __init__(self, k, device=None, lib=None, key_words=0, alphabet=None):
+        """`alphabet` = bytes of up to 32 distinct symbols: the generic-alphabet engine (peptides; k <= 24).
+        None = the DNA engine (ACGT, k <= 63)."""
         self.lib = lib or N.get()
         self.k = int(k)
         self.device = _default_device() if device is None else int(device)
+        self.alphabet = bytes(alphabet) if alphabet is not None else None
         h = C.c_void_p()
-        rc = self.lib.dbg_create_ex(C.byref(h), self.device, self.k, int(key_words))
+        if self.alphabet is not None:
+            rc = self.lib.dbg_create_alpha(C.byref(h), self.device, self.k, self.alphabet, len(self.alphabet))
+        else:
+            rc = self.lib.dbg_create_ex(C.byref(h), self.device, self.k, int(key_words))
         if rc != N.DBG_OK:
             msg = self.lib.dbg_last_error(None)
             N._raise(rc, msg.decode() if msg else '')
@@ -89,6 +100,7 @@ class Graph:
 
     def _reset_cache(self):
         self._batch_cache = None
+        self._edges = None
         self._nodes = None
         self._labels = None
         self._contigs = None
@@ -327,9 +339,15 @@ class Graph:
         torch.cuda.current_stream().cuda_stream returns by default), passed as cudaStreamLegacy;
         use own_stream() to go back to the handle's private stream."""
         self.lib.check(self.h, self.lib.dbg_set_stream(self.h, cuda_stream_ptr or 1))
+        self._stream = int(cuda_stream_ptr or 0)
 
     def own_stream(self):
         self.lib.check(self.h, self.lib.dbg_set_stream(self.h, None))
+        self._stream = None
+
+    def shares_stream(self, cuda_stream_ptr):
+        """True if the handle was put on exactly this stream with set_stream."""
+        return getattr(self, '_stream', None) is not None and self._stream == int(cuda_stream_ptr or 0)
 
     def stats(self):
         s = N.Stats()
@@ -365,11 +383,33 @@ class Graph:
             b = (lo >> np.uint64(sh)) | (hi << np.uint64(64 - sh))
         return (b & np.uint64(0xFFFFFFFF)).astype(np.uint32)
 
+    def _decode(self, lo, hi):
+        if self.alphabet is not None:
+            return decode_keys(lo, hi, self.k, 5, np.frombuffer(self.alphabet.ljust(32, b'?'), dtype=np.uint8))
+        return decode_keys(lo, hi, self.k)
+
     def labels(self):
         if self._labels is None:
             nd = self.nodes()
-            self._labels = decode_keys(nd['key_lo'], nd['key_hi'], self.k)
+            self._labels = self._decode(nd['key_lo'], nd['key_hi'])
         return self._labels
+
+    def edges(self):
+        """Generic-alphabet engine: the distinct (k+1)-mers grouped by source node in the reference's E order
+        (dbg_export_edges); src / dst are positions in nodes() order."""
+        if self._edges is None:
+            nd = self.nodes()
+            n = int(self.stats().n_edges)
+            a = {'src': np.zeros(n, np.uint32), 'dst': np.zeros(n, np.uint32), 'symbol': np.zeros(n, np.uint8),
+                 'count': np.zeros(n, np.uint32), 'kept': np.zeros(n, np.uint8)}
+            self.lib.check(self.h, self.lib.dbg_export_edges(self.h, *(a[f].ctypes.data if n else None for f in
+                                                                    ('src', 'dst', 'symbol', 'count', 'kept'))))
+            slot_to_idx = np.full(int(self.stats().table_slots), -1, np.int64)
+            slot_to_idx[nd['id']] = np.arange(len(nd['id']))
+            a['src'] = slot_to_idx[a['src']]
+            a['dst'] = slot_to_idx[a['dst']]
+            self._edges = a
+        return self._edges
 
     def label_of_ids(self, ids):
         ids = np.ascontiguousarray(ids, dtype=np.uint32)
@@ -378,7 +418,7 @@ class Graph:
         hi = np.zeros(n, np.uint64)
         if n:
             self.lib.check(self.h, self.lib.dbg_node_keys(self.h, ids.ctypes.data, n, lo.ctypes.data, hi.ctypes.data))
-        return decode_keys(lo, hi, self.k)
+        return self._decode(lo, hi)
 
     def branch_ids(self):
         n = self.stats().n_branch
@@ -404,7 +444,7 @@ class Graph:
         out = np.zeros(n, np.uint32)
         if n == 0:
             return out
-        buf = ''.join(kplus1mers).encode('ascii', 'replace')
+        buf = ''.join(kplus1mers).encode('latin-1', 'replace')
         if len(buf) != n * (self.k + 1):
             raise ValueError('every query must have length k+1')
         if batch is None:
@@ -536,14 +576,32 @@ class BatchGraph:
         return self.parent.label_of_ids(ids)
 
     def walk(self, stop_at_branch=True):
-        """The whole graph is walked once; `stop_at_branch` is what construct_graph's `final` implies
-        (a batch without branch nodes walks the same either way, debruijn.py:304)."""
+        """The whole graph is walked once, the way construct_graph's `final` implies, and every batch takes its
+        slice.  A batch without branch nodes walks the same either way (debruijn.py:304); a batch WITH branch nodes
+        whose caller asks for the other behaviour (an emptied / kept branch_kmer, debruijn.py:326) gets a walk of its
+        own with that flag, its strings materialised at once."""
         p = self.parent
-        _, a, z = self._split('contigs', lambda: p.walk(stop_at_branch=not p.final)['start'])
+        default = not p.final
+        self._strings = None
+        if bool(stop_at_branch) != default and self.stats().n_branch:
+            starts = p.walk(stop_at_branch=bool(stop_at_branch))['start']
+            ids = np.ascontiguousarray(starts, np.uint32)
+            lo_k, hi_k = np.zeros(len(ids), np.uint64), np.zeros(len(ids), np.uint64)
+            if len(ids):
+                p.lib.check(p.h, p.lib.dbg_node_keys(p.h, ids.ctypes.data, len(ids), lo_k.ctypes.data, hi_k.ctypes.data))
+            a, z = np.searchsorted(p.batch_of_keys(lo_k, hi_k), [self.b, self.b + 1])
+            self._contig_range = (int(a), int(z))
+            self._strings = p.contig_strings(np.arange(a, z, dtype=np.uint64))
+            if p._batch_cache:
+                p._batch_cache.pop('contigs', None)                      # the handle no longer holds the default walk
+            return p.contig_descriptors()[a:z]
+        _, a, z = self._split('contigs', lambda: p.walk(stop_at_branch=default)['start'])
         self._contig_range = (a, z)                                    # contigs come in start order = batch-major
         return p.contig_descriptors()[a:z]
 
     def contig_strings(self):
+        if getattr(self, '_strings', None) is not None:
+            return self._strings
         a, z = self._contig_range
         return self.parent.contig_strings(np.arange(a, z, dtype=np.uint64))
 
@@ -555,6 +613,7 @@ class _View(Mapping):
     def __init__(self, graph):
         self._graph = graph
         self._d = None
+        self._n = None
 
     def _dict(self):
         if self._d is None:
@@ -568,7 +627,9 @@ class _View(Mapping):
         return iter(self._dict())
 
     def __len__(self):
-        return int(self._graph.stats().n_nodes)
+        if self._n is None:                              # one ctypes round trip, not one per call
+            self._n = int(self._graph.stats().n_nodes)
+        return self._n
 
     def __repr__(self):
         return '<%s of %d entries on cuda:%d>' % (type(self).__name__, len(self), self._graph.device)
@@ -582,7 +643,10 @@ class Vertices(_View):
         nd = g.nodes()
         labels = g.labels()
         indeg = ((nd['flags'] & N.NODE_START) == 0).astype(np.int64).tolist()
-        outdeg = ((nd['kept'] >> 12) & 7).tolist()
+        if getattr(g, 'alphabet', None) is not None:                     # any number of distinct successors
+            outdeg = np.bincount(g.edges()['src'], minlength=len(labels)).tolist()
+        else:
+            outdeg = ((nd['kept'] >> 12) & 7).tolist()
         d = {}
         for lab, i, o in zip(labels, indeg, outdeg):
             node = Node(lab)
@@ -602,6 +666,15 @@ class Edges(_View):
         kept = nd['kept'].tolist()
         pulled = (nd['flags'] & N.NODE_PULLED).tolist()
         d = {}
+        if getattr(g, 'alphabet', None) is not None:
+            for lab, p in zip(labels, pulled):
+                if not p:
+                    d[lab] = []
+            e = g.edges()
+            for s_, t_, kp in zip(e['src'].tolist(), e['dst'].tolist(), e['kept'].tolist()):   # E order inside a node
+                if kp and not pulled[s_]:
+                    d[labels[s_]].append(labels[t_])
+            return d
         for lab, w, p in zip(labels, kept, pulled):
             if p:
                 continue
@@ -610,8 +683,10 @@ class Edges(_View):
         return d
 
     def __len__(self):
-        s = self._graph.stats()
-        return int(s.n_nodes - s.n_pulled)
+        if self._n is None:
+            s = self._graph.stats()
+            self._n = int(s.n_nodes - s.n_pulled)
+        return self._n
 
 
 class EdgeCountTable(Mapping):
@@ -631,6 +706,12 @@ class EdgeCountTable(Mapping):
             labels = g.labels()
             cnt = nd['cnt']
             d = {}
+            if getattr(g, 'alphabet', None) is not None:
+                e = g.edges()
+                for s_, sym, c in zip(e['src'].tolist(), e['symbol'].tobytes().decode('latin-1'), e['count'].tolist()):
+                    d[labels[s_] + sym] = c
+                self._d = d
+                return d
             rows, cols = np.nonzero(cnt)
             vals = cnt[rows, cols].tolist()
             for r, c, v in zip(rows.tolist(), cols.tolist(), vals):
@@ -644,7 +725,10 @@ class EdgeCountTable(Mapping):
             return self._dict()[key]
         if not isinstance(key, str) or len(key) != g.k + 1:
             raise KeyError(key)
-        v = int(g.lookup_edges([key])[0])
+        try:
+            v = int(g.lookup_edges([key])[0])
+        except ValueError:                               # a character outside the alphabet: not a key of the dict
+            raise KeyError(key) from None
         if v == 0:
             raise KeyError(key)
         return v

@@ -13,12 +13,16 @@ All graph work runs in the CUDA library behind ``include/dbg_b200.h`` (sm_100a);
 only packs the read list, calls the library and wraps the results.  ``vertices``, ``edges`` and
 ``edge_count_table`` are lazy mappings backed by the graph in HBM (II never inspects the first
 two and only indexes the third); they compare equal to the reference's dicts when materialised.
-There is no CPU path: without the built library or a CUDA device these calls raise.  DNA
-alphabet (ACGT) only, 1 <= k <= 63.
+There is no CPU path: without the built library or a CUDA device these calls raise.  DNA reads
+(ACGT) run on the 2-bit engine, 1 <= k <= 63; reads over any other alphabet of up to 32 characters
+(peptides) on the 5-bit generic engine, 1 <= k <= 24.
 """
 from __future__ import annotations
 
-from dbg_b200.graph import BatchGraph, EdgeCountTable, Edges, Graph, KmerList, Node, Vertices  # noqa: F401
+import numpy as np
+
+from dbg_b200._native import AlphabetError
+from dbg_b200.graph import BatchGraph, EdgeCountTable, Edges, Graph, KmerList, Node, Vertices, pack_reads  # noqa: F401
 
 __all__ = ['Node', 'read_reads', 'construct_graph', 'construct_graph_batch', 'output_contigs', 'get_score']
 
@@ -33,10 +37,26 @@ def read_reads(fname):
     return reads
 
 
+def _graph_for(reads, k, threshold, final):
+    """Build on the DNA engine; reads over another alphabet (the reference's real inputs are peptides,
+    II_assembleFromReads.py:43-47) go to the generic-alphabet engine with the symbols they use."""
+    packed = pack_reads(reads)
+    g = Graph(k)
+    try:
+        return g.build(reads, threshold=threshold, final=final, packed=packed)
+    except AlphabetError:
+        g.close()
+    symbols = np.flatnonzero(np.bincount(packed[0], minlength=256)).astype(np.uint8)
+    if len(symbols) > 32:
+        raise ValueError('dbg_b200: the reads use %d distinct characters; the GPU path handles alphabets of up to 32'
+                         % len(symbols))
+    g = Graph(k, alphabet=symbols.tobytes())
+    return g.build(reads, threshold=threshold, final=final, packed=packed)
+
+
 def construct_graph(reads, k, threshold=3, final=False):
     """debruijn.py:206-285 on the GPU."""
-    g = Graph(k)
-    g.build(reads, threshold=threshold, final=final)
+    g = _graph_for(reads, k, threshold, final)
     st = g.stats()
     print('number of {}mer: '.format(k), st.n_nodes)                      # debruijn.py:224
     print('branch number: ', st.n_branch)                                 # debruijn.py:236
@@ -58,7 +78,11 @@ def construct_graph_batch(batches, k, threshold=3, final=False):
     k-mer in every node key).  Prints the reference's two lines per batch, in batch order."""
     batch_bits = len(batches).bit_length()                              # ids 0 .. n-1 and the all-ones pattern stays free
     g = Graph(k, key_words=2 if 2 * k + batch_bits > 64 else 0)          # 128-bit keys when 64 bits cannot hold both
-    g.build_batched(batches, threshold=threshold, final=final)
+    try:
+        g.build_batched(batches, threshold=threshold, final=final)
+    except AlphabetError:                                                # not DNA: one generic-alphabet build per batch
+        g.close()
+        return [construct_graph(b, k, threshold, final) for b in batches]
     flags = g.pull_read_flags().tolist() if (not final and g.stats().n_pull_reads) else None
     out = []
     for b, reads in enumerate(batches):

@@ -20,27 +20,99 @@ def digest(obj):
 
 
 def test_golden_fuzz_corpus(backend):
-    """Outputs of /root/reference/debruijn.py itself (DNA-alphabet cases of the corpus)."""
+    """Outputs of /root/reference/debruijn.py itself: the DNA cases run on the 2-bit engine, the others
+    (peptides, 2- and 3-letter alphabets count as DNA subsets) on the generic-alphabet engine."""
     cases = util.load_golden('fuzz.json.gz')
-    n = 0
+    n_dna = n_other = 0
     for i, case in enumerate(cases):
-        if not util.is_dna(case['reads']):
-            continue
         got = util.product_snapshot(case['reads'], case['k'], case['threshold'], case['final'])
         util.assert_same(got, case['expect'], 'golden fuzz %d' % i)
-        n += 1
-    assert n > 400
+        if util.is_dna(case['reads']):
+            n_dna += 1
+        else:
+            n_other += 1
+    assert n_dna > 400 and n_other >= 75
 
 
-def test_non_dna_input_raises(backend):
-    """No CPU fallback: the peptide example at II_assembleFromReads.py:55 must raise."""
+def test_kat1_peptides_of_the_reference(backend):
+    """KAT-1: the only example input in the reference, II_assembleFromReads.py:55
+    (['EVQLVE','QLVAPG','LVESGGAL','LVESGGGL']), outputs recorded from the literal debruijn.py."""
+    cases = util.load_golden('kat.json.gz')
+    assert cases
+    for case in cases:
+        got = util.product_snapshot(case['reads'], case['k'], case['threshold'], case['final'])
+        util.assert_same(got, case['expect'], 'KAT-1 k=%d final=%s' % (case['k'], case['final']))
+
+
+def test_generic_alphabet_vs_oracle(backend):
+    """Random peptide-like problems (20 letters, k 2..12, errors, duplicates, branches, cycles, final=True):
+    the generic-alphabet engine against the pure-Python restatement; plus DNA with N's, lower case, and the
+    same DNA problem forced through the generic engine must equal the 2-bit engine."""
     import debruijn as db
+    from dbg_b200 import Graph
+    r = random.Random(20241019)
+    aa = 'ACDEFGHIKLMNPQRSTVWY'
+    n = 0
+    while n < 120:
+        alphabet = r.choice([aa, aa, aa[:6], 'ACGTN', 'acgtACGT', 'XY'])
+        k = r.choice([2, 3, 4, 5, 6, 8, 10, 12])
+        G = r.choice([15, 30, 60, 150, 400])
+        genome = ''.join(r.choice(alphabet) for _ in range(G))
+        if r.random() < 0.4 and G > 2 * k + 10:
+            a = r.randrange(0, G // 2)
+            ln = r.randrange(k, k + 6)
+            b = r.randrange(G // 2, max(G // 2 + 1, G - ln))
+            genome = (genome[:b] + genome[a:a + ln] + genome[b + ln:])[:G]
+        L = max(1, min(G, r.choice([k, k + 1, k + 3, 12, 20, 35])))
+        reads = []
+        for _ in range(r.choice([1, 3, 8, 20, 60, 150])):
+            ln = max(0, min(G, L + r.choice([0, 0, -1, 2, -3])))
+            p = r.randrange(0, G - ln + 1)
+            s_ = list(genome[p:p + ln])
+            for j in range(len(s_)):
+                if r.random() < r.choice([0.0, 0.03, 0.08]):
+                    s_[j] = r.choice(alphabet)
+            reads.append(''.join(s_))
+        if r.random() < 0.5:
+            reads = list(dict.fromkeys(reads))
+        thr, final = r.choice([1, 2, 2, 3, 5, 1.5, 0.5]), r.random() < 0.4
+        try:
+            exp = dbg_oracle.snapshot(reads, k, thr, final, max_paths=300)
+        except RuntimeError:
+            continue
+        got = util.product_snapshot(reads, k, thr, final)
+        util.assert_same(got, exp, 'generic case %d: %r' % (n, (reads, k, thr, final)))
+        n += 1
+    # a DNA problem through both engines
+    _, reads = util.synth_reads(9, 1500, 50, 12, err=0.02)
+    a = util.product_snapshot(reads, 15, 2, False)
+    g = Graph(15, alphabet=b'ACGT')
+    g.build(reads, threshold=2, final=False)
+    g.walk(stop_at_branch=True)
+    assert g.contig_strings() == a['contigs']
+    assert g.contig_scores().tolist() == [db.get_score(dict(map(tuple, a['ect'])), c, 15) for c in a['contigs']]
+    g.close()
+    # getScore through the device lookup (II_assembleFromReads.py:14-18) on a peptide graph
+    pep = ['EVQLVESGGALVQPGG', 'VQLVESGGGLVQ', 'LVESGGALVQPGGSLR', 'ESGGGLVQPGGSLRLS']
+    gr, pull, branch, pulled, ect = db.construct_graph(pep, 5, threshold=2, final=True)
+    for c in db.output_contigs(gr, branch, pulled):
+        assert db.get_score(ect, c, 5) == sum(dict(ect)[c[i:i + 6]] for i in range(len(c) - 5))
+    with pytest.raises(KeyError):
+        ect['WWWWWW']
+
+
+def test_invalid_input_raises(backend):
+    """No CPU fallback and no silent truncation: more than 32 distinct characters, or k beyond what the
+    engine's keys hold, raise."""
+    import debruijn as db
+    import string
+    many = string.ascii_letters + string.digits                      # 62 distinct characters
     with pytest.raises(ValueError):
-        db.construct_graph(['EVQLVE', 'QLVAPG', 'LVESGGAL', 'LVESGGGL'], 3, 2)
+        db.construct_graph([many, many[::-1]], 3, 2)
     with pytest.raises(ValueError):
-        db.construct_graph(['ACGTN', 'ACGTA'], 3, 2)
+        db.construct_graph(['EVQLVESGGALVQPGGSLRLSCAASGFTFS' * 2], 25, 2)     # 5-bit symbols: k <= 24
     with pytest.raises(ValueError):
-        db.construct_graph(['acgta', 'ACGTA'], 3, 2)
+        db.construct_graph(['ACGT' * 40], 64, 2)
 
 
 def test_kat2_config1_shape(backend):
