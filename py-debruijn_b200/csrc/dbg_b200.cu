@@ -45,6 +45,7 @@
 #include "dbg_generic.cuh"
 
 #define DBG_ABI_VERSION 1
+#define DBG_RETRY_COLD 1                      // internal: a build sized from the handle's hint did not fit; redo it cold
 #define MAX_ENUM_CONTIGS (1ull << 26)
 #define MAX_ENUM_STEPS (1ull << 32)
 
@@ -68,6 +69,8 @@ struct dbg_handle {
     int k = 0;
     int W = 1;
     cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
+    bool ext_stream = false;                  // the caller put the handle on ITS stream (dbg_set_stream): device buffers a call
+                                              //   leaves for the caller are ordered by that stream, no host wait at the end of the call
     const uint8_t *host_bases = nullptr;      // dbg_build*: the reads still sit in host memory and are copied in
                                               //   slices on copy_stream while k_pack / k_masks work on earlier ones
     cudaEvent_t slice_ev[MAX_SLICES + 1];
@@ -119,6 +122,18 @@ struct dbg_handle {
     int sym_bits = 2, n_symbols = 4;
     uint8_t sym_of_code[GEN_MAX_SYMBOLS] = {'A', 'C', 'G', 'T'}, code_of_byte[256];
     uint64_t n_eslots = 0, n_earr = 0;
+    // Table sizes remembered from the last successful build on this handle (like the grow-only buffers): a build of
+    // a similar read set sizes its chunk and node table from them at once -- no sketch round trips, no sketch pass,
+    // tables initialised on a side stream under the packing -- and CHECKS afterwards (overflow flags, read with the
+    // counters graph_finalize fetches anyway); a build they do not fit is redone the cold way.
+    struct { bool valid = false; uint64_t n_bases = 0, chunks = 0, nodes = 0; uint32_t n_batches = 0; } hint;
+    bool hinted = false, preinit = false;
+    bool have_hbytes = false;                 // a sketch pass (k_expand MODE 0) left hash bytes for the chunks now in the tables
+    uint64_t last_est_chunks = 0;
+    uint64_t shard_hint_nodes = 0;            // nodes of the last shard this handle expanded (dbg_chunk_expand)
+    bool merge_check_pending = false;         // dbg_chunk_merge_records' overflow flag is looked at by graph_finalize
+    cudaStream_t init_stream = nullptr;
+    cudaEvent_t ev_init[2];
     DevBuf b_up;                              // lifted successor arrays (strings / scores), built on demand
     bool up_ready = false;
     DevBuf b_codes, b_etable, b_earr, b_earr2, b_estart, b_edeg, b_enk, b_lut;
@@ -185,6 +200,9 @@ static int reserve_pinned(dbg_t *h, size_t bytes) {
     h->pin_cap = bytes + bytes / 8 + 4096;
     return DBG_OK;
 }
+
+// end of a call whose only result is a DEVICE buffer the caller will use (or feed to a collective)
+#define SYNC_FOR_CALLER() do { if (!h->ext_stream) CK(cudaStreamSynchronize(h->stream)); } while (0)
 
 static inline uint64_t cdiv(uint64_t a, uint64_t b) { return (a + b - 1) / b; }
 static inline uint64_t blocks_for(uint64_t n) { return n ? cdiv(n, DBG_BLOCK) : 1; }
@@ -483,8 +501,12 @@ static int expand_node_table(dbg_t *h) {
     if (n_slots >= 0xFFFFFFF0ull) return fail(h, DBG_ERR_OVERFLOW, "node table would exceed 2^32 slots");
     TRY(reserve(h, h->b_table, n_slots * sizeof(S)));
     const int a = ev_mark(h);
-    LAUNCH(k_table_init<W>, blocks_for(n_slots), DBG_BLOCK, h->stream, ptr<S>(h->b_table), n_slots);
-    CKK();
+    if (!h->preinit) {
+        LAUNCH(k_table_init<W>, blocks_for(n_slots), DBG_BLOCK, h->stream, ptr<S>(h->b_table), n_slots);
+        CKK();
+    }
+    const bool self_hash = !h->have_hbytes;                          // no sketch pass ran: no hash bytes
+    h->preinit = false;                                              // a rebuild (overflow) initialises its own table
     const int b = ev_mark(h);
     if (st.n_windows) {
         uint32_t n_parts = pass_count(h, n_slots * sizeof(S));
@@ -494,9 +516,14 @@ static int expand_node_table(dbg_t *h) {
             // hash bytes 0..254 (255 = no node) split evenly over the passes
             const uint32_t lo8 = part * 255u / n_parts;
             const uint32_t hi8 = (part + 1) * 255u / n_parts - 1;
-            LAUNCH((k_expand<W, 1>), h->ex_grid, DBG_BLOCK, h->stream, ptr<const CS>(h->b_ctable), h->n_cslots,
-                   ptr<const CS>(h->b_clist), h->n_clist, h->k, ptr<uint4>(h->b_h8), ptr<S>(h->b_table), (u32)n_slots,
-                   lo8, hi8 - lo8, (u32 *)nullptr, h->batch_bits, d_ctr);
+            if (self_hash)
+                LAUNCH((k_expand<W, 2>), h->ex_grid, DBG_BLOCK, h->stream, ptr<const CS>(h->b_ctable), h->n_cslots,
+                       ptr<const CS>(h->b_clist), h->n_clist, h->k, (uint4 *)nullptr, ptr<S>(h->b_table), (u32)n_slots,
+                       lo8, n_parts == 1 ? 254u : hi8 - lo8, (u32 *)nullptr, h->batch_bits, d_ctr);
+            else
+                LAUNCH((k_expand<W, 1>), h->ex_grid, DBG_BLOCK, h->stream, ptr<const CS>(h->b_ctable), h->n_cslots,
+                       ptr<const CS>(h->b_clist), h->n_clist, h->k, ptr<uint4>(h->b_h8), ptr<S>(h->b_table), (u32)n_slots,
+                       lo8, hi8 - lo8, (u32 *)nullptr, h->batch_bits, d_ctr);
             CKK();
         }
     }
@@ -522,7 +549,7 @@ static int settle_node_table(dbg_t *h, bool fetched) {
         if (attempt >= 6) return fail(h, DBG_ERR_NOMEM, "node table overflowed repeatedly");
         h->n_slots *= 2;                                               // estimate was low: rebuild larger
         CK(cudaMemsetAsync(&d_ctr->overflow, 0, 4, h->stream));
-        h->n_ev -= 3;
+        if (h->n_ev >= 3) h->n_ev -= 3;                                // (the table may have been expanded by an earlier call)
         TRY(expand_node_table<W>(h));
     }
     h->expand_pending = false;
@@ -549,6 +576,70 @@ static int build_chunks(dbg_t *h, const u64 *d_off, int e0, int e1) {
     ChunkCounters cc;
     memset(&cc, 0, sizeof cc);
     uint64_t est_chunks = 0;
+    if (h->hinted) {
+        // Tables were sized from the previous build on this handle and initialised on the side stream: no host
+        // round trip here.  Sketch registers and chunk counters land in pinned memory and are looked at, with
+        // the graph counters, by graph_finalize -- which redoes the build the cold way if they say "did not fit".
+        const int e2h = ev_mark(h);
+        if (!h->chunks_streamed) {
+            CK(cudaStreamWaitEvent(h->stream, h->ev_init[1], 0));
+            TRY(launch_chunk_insert<W>(h, d_off, 0, cdiv(h->n_bases, DBG_UNIT)));
+        }
+        h->chunks_streamed = false;
+        const int ch = ev_mark(h);
+        CK(cudaMemcpyAsync(h->ctl + CTL_CC, d_cc, sizeof cc, cudaMemcpyDeviceToHost, h->stream));
+        h->n_clist = 2 * h->n_reads + 2;
+        uint64_t g = cdiv(cdiv(h->n_cslots + h->n_clist, 32), DBG_WARPS);
+        uint64_t per_sm = DBG_EXPAND_MIN_BLOCKS;
+        if (const char *e = getenv("DBG_B200_EXPAND_GRID")) {
+            const unsigned long long v = strtoull(e, nullptr, 10);
+            if (v >= 1) per_sm = v;
+        }
+        if (g > (uint64_t)sms * per_sm) g = (uint64_t)sms * per_sm;
+        h->ex_grid = g < 1 ? 1 : g;
+        st.n_windows = 1;                                            // the real count arrives with graph_finalize's counters
+        st.n_chunk_list = h->n_clist;
+        st.chunk_slots = h->n_cslots;
+        tm_set(h, &st.ms_pack, e0, e1);
+        tm_set(h, &st.ms_estimate, e1, e2h);
+        tm_set(h, &st.ms_chunk_insert, e2h, ch);
+        tm_set(h, &st.ms_insert, e2h, ch);
+        if (h->build_flags & DBG_CHUNKS_ONLY) {                      // multi-GPU: the chunks leave for their owners
+            TRY(fetch_counters(h));                                   // ONE round trip: counters of packing + phase 1
+            tm_flush(h);
+            memcpy(&cc, h->ctl + CTL_CC, sizeof cc);
+            if (h->ctr.bad_alphabet) return fail(h, DBG_ERR_ALPHABET, "a read holds a byte other than A/C/G/T");
+            if (h->ctr.too_long) return fail(h, DBG_ERR_OVERFLOW, "a read is longer than 2^32-1 bases");
+            if (cc.chunk_overflow || cc.bad_chunk || cc.list_overflow) return DBG_RETRY_COLD;
+            st.n_windows = h->ctr.n_windows;
+            st.n_chunk_instances = cc.n_instances;
+            h->hint.chunks = cc.n_first;
+            h->hint.n_bases = h->n_bases;
+            h->hinted = false;
+            h->chunks_valid = true;
+            const int e_endc = ev_mark(h);
+            tm_set(h, &st.ms_build_total, e0, e_endc);
+            return DBG_OK;
+        }
+        if (pass_count(h, h->n_slots * sizeof(S)) > 2) {
+            // many node-table passes: one sweep that leaves a hash byte per (record, node) is cheaper than hashing every
+            // node again in every pass (measured at C3, 10 passes: 2.8 ms with the bytes, 4.3 ms without)
+            TRY(reserve(h, h->b_h8, (h->n_cslots + h->n_clist + 32) * 16));
+            CK(cudaMemsetAsync(h->b_hll.p, 0, HLL_M * 4, h->stream));
+            LAUNCH((k_expand<W, 0>), h->ex_grid, DBG_BLOCK, h->stream, ptr<const CS>(h->b_ctable), h->n_cslots,
+                   ptr<const CS>(h->b_clist), h->n_clist, k, ptr<uint4>(h->b_h8), (S *)nullptr, 0u, 0u, 0u,
+                   ptr<u32>(h->b_hll), h->batch_bits, d_ctr);
+            CKK();
+            h->have_hbytes = true;
+        }
+        TRY(expand_node_table<W>(h));
+        h->expand_pending = true;
+        const int e_end = ev_mark(h);
+        tm_set(h, &st.ms_build_total, e0, e_end);
+        h->table_ready = true;
+        h->chunks_valid = true;
+        return DBG_OK;
+    }
     if (h->n_bases) {
         std::vector<u32> regs(HLL_M);
         void *r_dst = h->ctl ? (void *)(h->ctl + CTL_SKETCH) : (void *)regs.data();
@@ -615,12 +706,13 @@ static int build_chunks(dbg_t *h, const u64 *d_off, int e0, int e1) {
         }
         if (ex_grid > (uint64_t)sms * ex_per_sm) ex_grid = (uint64_t)sms * ex_per_sm;
         if (ex_grid < 1) ex_grid = 1;
-        if (st.n_windows) {
+        if (st.n_windows && !(h->build_flags & DBG_CHUNKS_ONLY)) {      // (chunks that get exchanged are expanded by their owners)
             CK(cudaMemsetAsync(h->b_hll.p, 0, HLL_M * 4, h->stream));
             LAUNCH((k_expand<W, 0>), ex_grid, DBG_BLOCK, h->stream, ptr<const CS>(h->b_ctable), n_cslots,
                    ptr<const CS>(h->b_clist), n_list, k, ptr<uint4>(h->b_h8), (S *)nullptr, 0u, 0u, 0u,
                    ptr<u32>(h->b_hll), h->batch_bits, d_ctr);
             CKK();
+            h->have_hbytes = true;
             CK(cudaMemcpyAsync(s_dst, h->b_hll.p, HLL_M * 4, cudaMemcpyDeviceToHost, h->stream));
         }
         const int d = ev_mark(h);
@@ -641,6 +733,7 @@ static int build_chunks(dbg_t *h, const u64 *d_off, int e0, int e1) {
     }
     if (st.n_windows) est = (uint64_t)hll_estimate(sketch);
     st.hll_estimate = est;
+    h->last_est_chunks = est_interior;
     h->n_cslots = n_cslots;
     h->n_clist = n_list;
     h->ex_grid = ex_grid;
@@ -652,6 +745,10 @@ static int build_chunks(dbg_t *h, const u64 *d_off, int e0, int e1) {
     tm_set(h, &st.ms_pack, e0, e1);
     tm_set(h, &st.ms_estimate, e1, e2);
     if (h->build_flags & DBG_CHUNKS_ONLY) {                          // multi-GPU: the chunks are exchanged before any node table
+        h->hint.valid = true;                                        // sizes for the next build of this kind on the handle
+        h->hint.n_bases = h->n_bases;
+        h->hint.chunks = est_interior;
+        h->hint.n_batches = 0;
         const int e_end = ev_mark(h);
         tm_set(h, &st.ms_build_total, e0, e_end);
         h->chunks_valid = true;
@@ -724,6 +821,38 @@ static int build_impl(dbg_t *h, const u8 *d_bases, const u64 *d_off) {
         CK(cudaMemsetAsync(h->b_clist.p, 0xFF, list_cap * sizeof(ChunkSlot<W>), h->stream));
         h->n_cslots = 0;
         h->chunks_streamed = false;
+        if (h->hinted) {
+            typedef ChunkSlot<W> CS;
+            const uint64_t n_cs = (uint64_t)((double)h->hint.chunks * 1.7 * 1.15) + 4096;
+            double load = 0.5;
+            if (const char *e = getenv("DBG_B200_TABLE_LOAD")) {
+                const double v = atof(e) / 100.0;
+                if (v >= 0.05 && v <= 0.95) load = v;
+            }
+            const bool chunks_only = (h->build_flags & DBG_CHUNKS_ONLY) != 0;
+            const uint64_t n_ns = chunks_only ? 16 : (uint64_t)((double)h->hint.nodes * 1.06 * 1.03 / load) + 1024;
+            if (n_cs >= 0xFFFFFFF0ull || n_ns >= 0xFFFFFFF0ull) h->hinted = false;
+            else {
+                TRY(reserve(h, h->b_ctable, n_cs * sizeof(CS)));
+                if (!chunks_only) TRY(reserve(h, h->b_table, n_ns * sizeof(S)));
+                h->n_cslots = n_cs;
+                if (!chunks_only) h->n_slots = n_ns;
+                // both tables are cleared on the side stream while the reads are packed and masked
+                CK(cudaEventRecord(h->ev_init[0], h->stream));
+                CK(cudaStreamWaitEvent(h->init_stream, h->ev_init[0], 0));
+                int sms_ = 148;
+                cudaDeviceGetAttribute(&sms_, cudaDevAttrMultiProcessorCount, h->device);
+                const uint64_t bg = (uint64_t)sms_ * 2;                   // background grid: two blocks an SM
+                LAUNCH(k_chunk_table_init<W>, std::min<uint64_t>(bg, blocks_for(n_cs)), DBG_BLOCK, h->init_stream, ptr<CS>(h->b_ctable), n_cs);
+                CKK();
+                if (!chunks_only) {
+                    LAUNCH(k_table_init<W>, std::min<uint64_t>(bg, blocks_for(n_ns)), DBG_BLOCK, h->init_stream, ptr<S>(h->b_table), n_ns);
+                    CKK();
+                }
+                CK(cudaEventRecord(h->ev_init[1], h->init_stream));
+                h->preinit = !chunks_only;
+            }
+        }
     }
     if (h->n_reads) {
         uint64_t rs_grid = blocks_for(h->n_reads);
@@ -777,14 +906,19 @@ static int build_impl(dbg_t *h, const u8 *d_bases, const u64 *d_off) {
                     LAUNCH(k_masks, blocks_for(s1 - s_done), DBG_BLOCK, h->stream, ptr<const u64>(h->b_packed), d_off,
                            h->n_reads, ptr<const u32>(h->b_tile), h->n_bases, s_done, s1, k, h->geom_logw, h->geom_m,
                            h->sample_mask, ptr<u32>(h->b_stmask), ptr<u32>(h->b_vmask), ptr<u32>(h->b_spanread),
-                           ptr<u32>(h->b_hll));
+                           h->hinted ? (u32 *)nullptr : ptr<u32>(h->b_hll));
                     CKK();
                     s_done = s1;
                 }
                 if (stream_insert) {
                     // units whose masks (32 spans + 1) and string overhang (3 words) are complete
                     const uint64_t u1 = last ? cdiv(h->n_bases, DBG_UNIT) : (s_done >= 36 ? (s_done - 4) / 32 : 0);
-                    if (u1 > u_done) {
+                    if (u1 > u_done && h->hinted) {
+                        if (!h->chunks_streamed) CK(cudaStreamWaitEvent(h->stream, h->ev_init[1], 0));
+                        TRY(launch_chunk_insert<W>(h, d_off, u_done, u1));
+                        u_done = u1;
+                        h->chunks_streamed = true;
+                    } else if (u1 > u_done) {
                         void *r_dst = h->ctl ? (void *)(h->ctl + CTL_SKETCH) : (void *)regs.data();
                         CK(cudaMemcpyAsync(r_dst, h->b_hll.p, HLL_M * 4, cudaMemcpyDeviceToHost, h->stream));
                         CK(cudaStreamSynchronize(h->stream));              // the next slices are already on the wire
@@ -830,6 +964,23 @@ static int graph_finalize(dbg_t *h) {
         CKK();
         TRY(fetch_counters(h));
         tm_flush(h);
+        if (h->hinted) {                                               // what the cold path checks between its phases
+            ChunkCounters cc;
+            memcpy(&cc, h->ctl + CTL_CC, sizeof cc);
+            if (h->ctr.bad_alphabet) return fail(h, DBG_ERR_ALPHABET, "a read holds a byte other than A/C/G/T");
+            if (h->ctr.too_long) return fail(h, DBG_ERR_OVERFLOW, "a read is longer than 2^32-1 bases");
+            if (cc.chunk_overflow || cc.bad_chunk || cc.list_overflow) return DBG_RETRY_COLD;   // the hint did not fit
+            h->last_est_chunks = cc.n_first;                          // exact: entries the chunk table's CAS winners created
+            st.n_windows = h->ctr.n_windows;
+            st.n_chunk_instances = cc.n_instances;
+            h->hinted = false;                                         // validated; a node-table rebuild below runs cold
+        }
+        if (h->merge_check_pending) {
+            h->merge_check_pending = false;
+            ChunkCounters cc;
+            memcpy(&cc, h->ctl + CTL_CC, sizeof cc);
+            if (cc.chunk_overflow) return fail(h, DBG_ERR_NOMEM, "chunk table overflowed while merging records");
+        }
         if (!(h->expand_pending && h->ctr.overflow)) break;
         // the node table the chunk build left had overflowed (its flag is looked at here, with this
         // stage's own counters, to save a host round trip on the common path): rebuild it larger
@@ -851,6 +1002,14 @@ static int graph_finalize(dbg_t *h) {
     tm_set(h, &st.ms_finalize, e3, e4);
     tm_add(h, &st.ms_build_total, e3, e4);
     h->order_active = false;
+    if (h->chunks_merged) h->shard_hint_nodes = st.n_nodes;          // size of the next shard this handle expands
+    if (h->chunks_valid && !h->chunks_merged && h->shard_n < 2) {      // sizes for the next build on this handle
+        h->hint.valid = true;
+        h->hint.n_bases = h->n_bases;
+        h->hint.chunks = h->last_est_chunks;
+        h->hint.nodes = st.n_nodes;
+        h->hint.n_batches = h->n_batches;
+    }
     return DBG_OK;
 }
 
@@ -973,7 +1132,7 @@ static int export_records_impl(dbg_t *h, uint32_t n_parts, const uint64_t *count
     LAUNCH(k_rec_scatter<W>, blocks_for(h->n_slots), DBG_BLOCK, h->stream, ptr<const Slot<W>>(h->b_table), h->n_slots,
            n_parts, d_cur, (u64 *)d_out);
     CKK();
-    CK(cudaStreamSynchronize(h->stream));
+    SYNC_FOR_CALLER();                                    // (pageable H2D sources are staged before cudaMemcpyAsync returns)
     return DBG_OK;
 }
 
@@ -1004,7 +1163,7 @@ static int chunk_export_records_impl(dbg_t *h, uint32_t n_parts, const uint64_t 
     LAUNCH(k_chunk_rec_scatter<W>, blocks_for(h->n_cslots + h->n_clist), DBG_BLOCK, h->stream, ptr<const CS>(h->b_ctable),
            h->n_cslots, ptr<const CS>(h->b_clist), h->n_clist, geom.w, geom.m, h->batch_bits, n_parts, d_cur, (CS *)d_out);
     CKK();
-    CK(cudaStreamSynchronize(h->stream));
+    SYNC_FOR_CALLER();
     return DBG_OK;
 }
 
@@ -1021,6 +1180,7 @@ static int chunk_table_reset_impl(dbg_t *h, uint64_t expected_chunks) {
     h->n_cslots = n;
     h->n_clist = 0;                                                   // boundary chunks arrive as records like the others
     h->chunks_merged = true;
+    h->have_hbytes = false;
     h->chunks_valid = true;
     h->tags_local = false;
     h->expand_pending = false;
@@ -1036,11 +1196,7 @@ static int chunk_merge_records_impl(dbg_t *h, const uint64_t *d_records, uint64_
     LAUNCH(k_chunk_rec_merge<W>, blocks_for(n), DBG_BLOCK, h->stream, ptr<CS>(h->b_ctable), (u32)h->n_cslots,
            (const CS *)d_records, n, ptr<ChunkCounters>(h->b_cc));
     CKK();
-    ChunkCounters cc;
-    CK(cudaMemcpyAsync(&cc, h->b_cc.p, sizeof cc, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    if (cc.chunk_overflow) return fail(h, DBG_ERR_NOMEM, "chunk table overflowed while merging records");
-    return DBG_OK;
+    return DBG_OK;                                        // the overflow flag is looked at by dbg_chunk_expand
 }
 
 // phase 2 on the merged chunk table: this rank's shard of the node table
@@ -1059,15 +1215,49 @@ static int chunk_expand_impl(dbg_t *h) {
     h->ex_grid = ex_grid;
     std::vector<u32> sketch(HLL_M, 0);
     TRY(reserve(h, h->b_hll, HLL_M * 4));
+    CK(cudaMemsetAsync(&d_ctr->overflow, 0, 4, h->stream));
+    if (h->shard_hint_nodes && h->ctl && !getenv("DBG_B200_NO_HINT") && !getenv("DBG_B200_NODE_SLOTS")) {
+        // the shard this handle expanded last time tells the size of this one: no sketch pass, no host round trip
+        // here; the overflow flags (chunk merge, node table) are looked at by graph_finalize with its own counters
+        double load = 0.5;
+        if (const char *e = getenv("DBG_B200_TABLE_LOAD")) {
+            const double v = atof(e) / 100.0;
+            if (v >= 0.05 && v <= 0.95) load = v;
+        }
+        h->n_slots = (uint64_t)((double)h->shard_hint_nodes * 1.06 * 1.03 / load) + 1024;
+        h->have_hbytes = false;
+        if (pass_count(h, h->n_slots * sizeof(S)) > 2) {
+            TRY(reserve(h, h->b_h8, (h->n_cslots + h->n_clist + 32) * 16));
+            CK(cudaMemsetAsync(h->b_hll.p, 0, HLL_M * 4, h->stream));
+            LAUNCH((k_expand<W, 0>), ex_grid, DBG_BLOCK, h->stream, ptr<const CS>(h->b_ctable), h->n_cslots,
+                   ptr<const CS>(h->b_clist), h->n_clist, h->k, ptr<uint4>(h->b_h8), (S *)nullptr, 0u, 0u, 0u,
+                   ptr<u32>(h->b_hll), h->batch_bits, d_ctr);
+            CKK();
+            h->have_hbytes = true;
+        }
+        CK(cudaMemcpyAsync(h->ctl + CTL_CC, h->b_cc.p, sizeof(ChunkCounters), cudaMemcpyDeviceToHost, h->stream));
+        h->merge_check_pending = true;
+        const uint64_t lw = h->st.n_windows;
+        h->st.n_windows = 1;
+        const int rc2 = expand_node_table<W>(h);
+        h->st.n_windows = lw;
+        TRY(rc2);
+        h->expand_pending = true;
+        h->table_ready = true;
+        return DBG_OK;
+    }
     TRY(reserve(h, h->b_h8, (h->n_cslots + h->n_clist + 32) * 16));
     CK(cudaMemsetAsync(h->b_hll.p, 0, HLL_M * 4, h->stream));
-    CK(cudaMemsetAsync(&d_ctr->overflow, 0, 4, h->stream));
     LAUNCH((k_expand<W, 0>), ex_grid, DBG_BLOCK, h->stream, ptr<const CS>(h->b_ctable), h->n_cslots,
            ptr<const CS>(h->b_clist), h->n_clist, h->k, ptr<uint4>(h->b_h8), (S *)nullptr, 0u, 0u, 0u,
            ptr<u32>(h->b_hll), h->batch_bits, d_ctr);
     CKK();
+    h->have_hbytes = true;
     CK(cudaMemcpyAsync(sketch.data(), h->b_hll.p, HLL_M * 4, cudaMemcpyDeviceToHost, h->stream));
+    ChunkCounters cc;
+    CK(cudaMemcpyAsync(&cc, h->b_cc.p, sizeof cc, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    if (cc.chunk_overflow) return fail(h, DBG_ERR_NOMEM, "chunk table overflowed while merging records");
     const uint64_t local_windows = h->st.n_windows;
     h->st.n_windows = 1;                                              // expand_node_table skips its passes for an empty read set,
     const int rc = node_table_from_chunks<W>(h, (uint64_t)hll_estimate(sketch));   // but the chunks here may all be other ranks'
@@ -1574,7 +1764,7 @@ static int shard_exit_keys_impl(dbg_t *h, uint64_t *d_keys_out) {
                ptr<u32>(h->b_exitslot), (u64 *)d_keys_out);
         CKK();
     }
-    CK(cudaStreamSynchronize(h->stream));                 // exit_off (host memory of this handle) was the copy's source
+    SYNC_FOR_CALLER();
     return DBG_OK;
 }
 
@@ -1673,7 +1863,7 @@ static int shard_entry_ordinals_impl(dbg_t *h, uint32_t *d_out) {
                ptr<const u32>(h->b_rvord), (u32 *)d_out);
         CKK();
     }
-    CK(cudaStreamSynchronize(h->stream));
+    SYNC_FOR_CALLER();
     return DBG_OK;
 }
 
@@ -1694,7 +1884,7 @@ static int shard_reduced_records_impl(dbg_t *h, const uint32_t *d_replies, const
                h->shard_rank, (u64 *)d_out);
         CKK();
     }
-    CK(cudaStreamSynchronize(h->stream));                 // rid_base is the caller's host memory
+    SYNC_FOR_CALLER();                                    // (rid_base: pageable H2D sources are staged before the call returns)
     h->shard_stage = 4;
     return DBG_OK;
 }
@@ -1794,6 +1984,8 @@ DBG_API int dbg_create_ex(dbg_t **out, int device, int k, int key_words) {
     for (int i = 0; i < EV_MAX; i++) cudaEventCreate(&h->ev[i]);
     for (int i = 0; i <= MAX_SLICES; i++) cudaEventCreate(&h->slice_ev[i]);
     cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&h->init_stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 2; i++) cudaEventCreate(&h->ev_init[i]);
     if (cudaMallocHost(&h->ctl, CTL_BYTES) != cudaSuccess) h->ctl = nullptr;
     if (reserve(h, h->b_ctr, sizeof(DevCounters)) != DBG_OK) {
         g_create_error = h->err;
@@ -1844,6 +2036,8 @@ DBG_API void dbg_destroy(dbg_t *h) {
     for (int i = 0; i < EV_MAX; i++) cudaEventDestroy(h->ev[i]);
     for (int i = 0; i <= MAX_SLICES; i++) cudaEventDestroy(h->slice_ev[i]);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->init_stream) cudaStreamDestroy(h->init_stream);
+    for (int i = 0; i < 2; i++) cudaEventDestroy(h->ev_init[i]);
 #ifdef DBG_EMU
     if (h->pin) free(h->pin);
 #else
@@ -1857,6 +2051,7 @@ DBG_API void dbg_destroy(dbg_t *h) {
 DBG_API int dbg_set_stream(dbg_t *h, void *cuda_stream) {
     if (!h) return DBG_ERR_ARG;
     h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+    h->ext_stream = cuda_stream != nullptr;
     return DBG_OK;
 }
 
@@ -1913,9 +2108,40 @@ static int build_device_common(dbg_t *h, const uint8_t *d_bases, const uint64_t 
             return fail(h, DBG_ERR_ARG, "batched and multi-GPU builds exist for the DNA engine only");
         return gen_build(h, (const u8 *)d_bases, (const u64 *)d_read_off);
     }
-    TRY(DISPATCH(build_impl, h, (const u8 *)d_bases, (const u64 *)d_read_off));
-    if (flags & (DBG_TABLE_ONLY | DBG_CHUNKS_ONLY)) return DBG_OK;
-    TRY(DISPATCH(graph_finalize, h));
+    // sizes remembered from the last build fit a read set of about the same size (checked afterwards, see dbg_handle::hint)
+    h->hinted = h->hint.valid && h->ctl && n_bases > 0 && !(flags & DBG_TABLE_ONLY) && h->hint.chunks > 0 &&
+                ((flags & DBG_CHUNKS_ONLY) || h->hint.nodes > 0) &&
+                h->hint.n_batches == h->n_batches && n_bases >= h->hint.n_bases / 2 && n_bases <= h->hint.n_bases + h->hint.n_bases / 2 &&
+                !getenv("DBG_B200_NO_HINT") && !getenv("DBG_B200_CHUNK_SLOTS") && !getenv("DBG_B200_NODE_SLOTS");
+    h->preinit = false;
+    h->have_hbytes = false;
+    int rc = DISPATCH(build_impl, h, (const u8 *)d_bases, (const u64 *)d_read_off);
+    if (rc != DBG_OK && rc != DBG_RETRY_COLD) return rc;
+    const bool stop_early = (flags & (DBG_TABLE_ONLY | DBG_CHUNKS_ONLY)) != 0;
+    if (rc == DBG_OK && stop_early) return DBG_OK;
+    if (rc == DBG_OK) rc = DISPATCH(graph_finalize, h);
+    if (rc == DBG_RETRY_COLD) {                                       // the remembered sizes did not fit this read set
+        h->hint.valid = false;
+        h->hinted = false;
+        h->n_ev = 0;
+        h->tm.clear();
+        memset(&h->st, 0, sizeof h->st);
+        h->st.key_words = (uint32_t)h->W;
+        h->st.n_reads = n_reads;
+        h->st.n_bases = n_bases;
+        CK(cudaMemsetAsync(h->b_ctr.p, 0, sizeof(DevCounters), h->stream));
+        h->table_ready = false;
+        h->expand_pending = false;
+        h->have_hbytes = false;
+        if (h->host_bases) CK(cudaStreamSynchronize(h->copy_stream));   // the reads are all in HBM by now: one slice
+        const uint8_t *hb = h->host_bases;
+        h->host_bases = nullptr;
+        rc = DISPATCH(build_impl, h, (const u8 *)d_bases, (const u64 *)d_read_off);
+        h->host_bases = hb;
+        if (rc == DBG_OK && stop_early) return DBG_OK;
+        if (rc == DBG_OK) rc = DISPATCH(graph_finalize, h);
+    }
+    TRY(rc);
     TRY(DISPATCH(graph_order_scan, h));
     TRY(DISPATCH(graph_complete, h));
     return DBG_OK;

@@ -116,7 +116,7 @@ template <> DBG_HD void chunk_words<2>(const K128 *h, u64 *out) {
 }
 
 struct ChunkCounters {
-    u64 n_first;        // unused
+    u64 n_first;        // entries created in the chunk table = distinct interior chunks
     u64 n_instances;    // chunk instances seen by k_chunk_insert
     u64 n_list;         // unused (the list is indexed by read: 2 r = first chunk, 2 r + 1 = last chunk)
     u32 chunk_overflow; // chunk table full
@@ -124,6 +124,17 @@ struct ChunkCounters {
     u32 bad_chunk;      // a chunk longer than CH_WMAX (internal consistency)
     u32 pad;
 };
+
+// position of the r-th (0-based) set bit of m; m must have more than r bits set
+DBG_D u32 nth_set_bit(u32 m, u32 r) {
+    u32 pos = 0, c;
+    c = __popc(m & 0xFFFFu); if (r >= c) { r -= c; pos += 16; m >>= 16; }
+    c = __popc(m & 0xFFu);   if (r >= c) { r -= c; pos += 8;  m >>= 8; }
+    c = __popc(m & 0xFu);    if (r >= c) { r -= c; pos += 4;  m >>= 4; }
+    c = __popc(m & 0x3u);    if (r >= c) { r -= c; pos += 2;  m >>= 2; }
+    if (r >= (m & 1u)) pos += 1;
+    return pos;
+}
 
 DBG_D u32 bit_range(u32 lo, u32 hi) { return (~0u >> (31 - hi)) & (~0u << lo); }   // bits lo..hi, 0 <= lo <= hi <= 31
 
@@ -175,7 +186,8 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_masks(const u64 *__restrict__ pac
         const u64 wm = s ? __ldg(packed + s - 1) : 0ULL, w0 = __ldg(packed + s), w1 = __ldg(packed + s + 1);
         const u64 A = (wm << 62) | (w0 >> 2);                            // bases p0 - 1 .. p0 + 30
         const u64 B = (w0 << 62) | (w1 >> 2);                            // bases p0 + 31 .. p0 + 62
-        // the 128 bits as four 32-bit words; m-mer i = the 32 bits at bit 2 i, shifted down to 2 m bits
+        // the 128 bits as four 32-bit words; m-mer i = the 32 bits at bit 2 i, shifted down to 2 m bits.
+        // Order of the candidates: 26-bit multiplicative hash, ties to the leftmost (the index rides in the low 6 bits)
         const u32 X[5] = {(u32)(A >> 32), (u32)A, (u32)(B >> 32), (u32)B, 0u};
         const int down = 32 - 2 * m;
         u32 a[48];
@@ -184,7 +196,7 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_masks(const u64 *__restrict__ pac
             const int o = 2 * i;
             const u32 t = (o & 31) ? __funnelshift_l(X[o / 32 + 1], X[o / 32], o & 31) : X[o / 32];
             const u32 x = t >> down;
-            a[i] = (((x * 0x9E3779B1u) >> 8) & 0xFFFFFFC0u) | (u32)i;      // 18-bit hash << 6 | i
+            a[i] = ((x * 0x9E3779B1u) | 63u) - (u32)(63 - i);              // 26-bit hash << 6 | i  (3 instructions)
         }
         if (logw > 0) {
 #pragma unroll
@@ -204,9 +216,10 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_masks(const u64 *__restrict__ pac
         }
         u32 N = 0, Smp = 0;
 #pragma unroll
-        for (int j = 0; j < 32; j++) {
-            N |= (a[j + 1] != a[j] ? 1u : 0u) << j;
-            Smp |= ((a[j + 1] & sample_mask) == 0u ? 1u : 0u) << j;       // distinct sampling by minimizer hash
+        for (int j = 0; j < 32; j++) N |= (a[j + 1] != a[j] ? 1u : 0u) << j;
+        if (regs) {                                                      // no sketch when the table is sized from the handle's hint
+#pragma unroll
+            for (int j = 0; j < 32; j++) Smp |= ((a[j + 1] & sample_mask) == 0u ? 1u : 0u) << j;   // distinct sampling by minimizer hash
         }
         St = V & (S | N);
         // sketch of the (sampled) chunk starts that are not read starts: the first min(32, k + 1) bases
@@ -230,35 +243,32 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_masks(const u64 *__restrict__ pac
 
 template <int W>
 __global__ void __launch_bounds__(DBG_BLOCK) k_chunk_table_init(ChunkSlot<W> *table, u64 n_slots) {
-    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_slots) return;
     ChunkSlot<W> s;
 #pragma unroll
     for (int h = 0; h < W; h++) s.h[h] = k128_ones();
     s.tag = ~0ULL;
     s.cnt = 0;
     s.zero_pad();
-    table[i] = s;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += (u64)gridDim.x * blockDim.x) table[i] = s;   // grid-stride
 }
 
 // ---------------------------------------------------------------------------------------------
 // k_chunk_insert (phase 1).  Each warp works through units of 32 spans (1024 stream positions):
 //   stage   the unit's 2-bit words (+ overhang for the longest chunk string) in shared memory
-//   select  every lane turns the St bits of its span into queue entries (position, n, term); the
-//           end of a chunk is the next bit of St | ~V, in its own span or the next one
-//   drain   32 chunks at a time, one per lane: read index and position (span_read + off[]), the
-//           key from the staged words, then ONE probe of the chunk table; a probe that finds
-//           another key does not loop, it re-queues (key, tag, probes) in a retry ring
+//   select  the unit's chunk instances are dealt to the lanes 32 at a time through prefix sums of
+//           popc(St) (no per-lane queueing loop); the end of a chunk is the next bit of St | ~V, in
+//           its own span or the next one
+//   probe   one chunk per lane: read index and position (span_read + off[]), the key from the
+//           staged words, then ONE probe of the chunk table; a probe that finds another key does
+//           not loop, it re-queues (key, tag, probes) in a retry ring
 // First / last chunks of a read go to the list at slot 2 r / 2 r + 1 (r = read index): no atomics, and the
 // list is in read order (a shared append cursor was measured at 1 ms: 4 x 10^5 same-address atomics).
 // ---------------------------------------------------------------------------------------------
 #define CH_UNIT_WORDS (DBG_UNIT / 32 + 6)
-#define CH_QCAP 512
 #define CH_RCAP 64
 #define CH_MAX_PROBES 1024u
 template <int W> struct ChunkInsertShared {
     u64 words[DBG_WARPS][CH_UNIT_WORDS];
-    u16 q[DBG_WARPS][CH_QCAP];                  // rel (10 bits) | (n - 1) << 10 | term << 14
     u32 c_read[DBG_WARPS][32];                  // per span: read holding its first position,
     u32 c_pos[DBG_WARPS][32];                   //   position of the span start in that read,
     u16 c_end[DBG_WARPS][32];                   //   distance to that read's end (clamped),
@@ -278,8 +288,8 @@ DBG_D void store_k128(K128 *p, K128 v) {
     __stcg(reinterpret_cast<ulonglong2 *>(p), make_ulonglong2(v.lo, v.hi));
 }
 
-// one probe of one slot: 0 = counted, 1 = another key lives here (go on to the next slot),
-// 2 = the slot's second half is not published yet (come back to the same slot)
+// one probe of one slot: 0 = counted, 3 = counted and this probe created the entry, 1 = another key lives
+// here (go on to the next slot), 2 = the slot's second half is not published yet (come back to the same slot)
 template <int W>
 DBG_D int chunk_probe(ChunkSlot<W> *s, const ChunkKey<W> &key, u64 tag) {
     const K128 c0 = load_k128(&s->h[0]);
@@ -291,7 +301,7 @@ DBG_D int chunk_probe(ChunkSlot<W> *s, const ChunkKey<W> &key, u64 tag) {
             if (W == 2) store_k128(&s->h[W - 1], key.h[W - 1]);
             atomicMin(&s->tag, tag);
             atomicAdd(&s->cnt, 1u);
-            return 0;
+            return 3;
         }
         if (old != key.h[0]) return 1;
         seen = __ldcg(&s->tag);
@@ -344,9 +354,10 @@ k_chunk_insert(const u64 *__restrict__ packed, u64 n_words_padded, const u64 *__
     __shared__ ChunkInsertShared<W> sh;
     const u32 lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const u32 lt = (1u << lane) - 1;
-    u32 head1 = 0, n1 = 0, head2 = 0, n2 = 0;                            // warp-uniform ring state
+    u32 head2 = 0, n2 = 0;                                               // warp-uniform state of the retry ring
     u32 flags = 0;                                                       // 1 table overflow, 2 list overflow, 4 bad chunk
     u64 ub = 0, n_inst = 0;
+    u32 n_new = 0;                                                       // entries this lane created = distinct interior chunks
 
     auto probe = [&](bool act, const ChunkKey<W> &key, u64 tag, u32 probes) {
         int res = 0;
@@ -354,6 +365,7 @@ k_chunk_insert(const u64 *__restrict__ packed, u64 n_words_padded, const u64 *__
             u64 idx = slot_home(chunk_hash<W>(key), n_slots) + probes;
             if (idx >= n_slots) idx -= n_slots;
             res = chunk_probe<W>(&table[idx], key, tag);
+            if (res == 3) { n_new++; res = 0; }
             if (res == 1) {
                 probes++;
                 if (probes >= CH_MAX_PROBES || probes >= n_slots) { flags |= 1u; res = 0; cc->chunk_overflow = 1; }
@@ -380,16 +392,7 @@ k_chunk_insert(const u64 *__restrict__ packed, u64 n_words_padded, const u64 *__
         n2 -= take;
         probe(act, key, tag, probes);
     };
-    auto drain1 = [&]() {                                                // up to 32 fresh chunks
-        __syncwarp();
-        const u32 take = n1 < 32u ? n1 : 32u;
-        const bool act = lane < take;
-        const u32 ent = act ? sh.q[w][(head1 + lane) & (CH_QCAP - 1)] : 0;
-        __syncwarp();
-        head1 = (head1 + take) & (CH_QCAP - 1);
-        n1 -= take;
-        const u32 rel = ent & 1023u, n = ((ent >> 10) & 15u) + 1;
-        u32 term = (ent >> 14) & 1u;
+    auto fresh = [&](bool act, u32 rel, u32 n, u32 term) {               // up to 32 fresh chunks, one per lane
         ChunkKey<W> key;
         u64 tag = 0;
         bool boundary = false;
@@ -473,42 +476,55 @@ k_chunk_insert(const u64 *__restrict__ packed, u64 n_words_padded, const u64 *__
             sh.c_end2[w][lane] = (u16)end2; sh.c_skip[w][lane] = (u8)skip;
         }
         __syncwarp();
-#pragma unroll
-        for (int quarter = 0; quarter < 4; quarter++) {
-            u32 m8 = (st >> (8 * quarter)) & 0xFFu;
-            const u32 cnt = __popc(m8);
-            u32 incl = cnt;
+        // ---- hand the unit's chunk instances to the lanes, 32 at a time.  Instance g belongs to the span (lane) s with
+        // excl[s] <= g < incl[s] (prefix sums of popc(St), found by a 5-step search over shuffles) and starts at the
+        // (g - excl[s])-th set bit of that span's St; its end is the next bit of St | ~V, in that span or the next.
+        // (Each lane used to walk its own span's bits and queue them: a loop at 1/4 lane occupancy that was a quarter
+        // of this kernel's instructions.)
+        {
+            const u32 c = __popc(st);
+            u32 incl = c;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
                 const u32 x = __shfl_up_sync(0xFFFFFFFFu, incl, d);
                 if (lane >= (u32)d) incl += x;
             }
             const u32 total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-            u32 o = head1 + n1 + incl - cnt;
-            while (m8) {
-                const u32 b = (u32)__ffs((int)m8) - 1 + 8 * quarter;
-                m8 &= m8 - 1;
-                const u32 rest = E & ~((2u << b) - 1u);                  // bits above b
-                u32 e = 64, term = 1;                                    // e = 64: no end found (flagged below)
-                if (rest) { e = (u32)__ffs((int)rest) - 1; term = ((v >> e) & 1u) ^ 1u; }
-                else if (En) { const u32 en = (u32)__ffs((int)En) - 1; e = 32 + en; term = ((vn >> en) & 1u) ^ 1u; }
-                u32 n = e - b;
-                if (n > CH_WMAX || n == 0) { flags |= 4u; n = 1; term = 1; }
-                sh.q[w][o & (CH_QCAP - 1)] = (u16)((lane * 32 + b) | ((n - 1) << 10) | (term << 14));
-                o++;
-            }
-            n1 += total;
-            while (n1 >= 32u) {
-                drain1();
+            const u32 excl = incl - c;
+            for (u32 base = 0; base < total; base += 32u) {
+                const u32 g = base + lane;
+                const bool act = g < total;
+                u32 lo = 0;                                              // first lane whose inclusive sum exceeds g
+#pragma unroll
+                for (int step = 16; step > 0; step >>= 1) {
+                    const u32 x = __shfl_sync(0xFFFFFFFFu, incl, (int)((lo + step - 1) & 31u));
+                    if (x <= g) lo += (u32)step;
+                }
+                const int src = (int)(lo & 31u);
+                const u32 ex_s = __shfl_sync(0xFFFFFFFFu, excl, src);
+                const u32 st_s = __shfl_sync(0xFFFFFFFFu, st, src);
+                const u32 E_s = __shfl_sync(0xFFFFFFFFu, E, src), En_s = __shfl_sync(0xFFFFFFFFu, En, src);
+                const u32 v_s = __shfl_sync(0xFFFFFFFFu, v, src), vn_s = __shfl_sync(0xFFFFFFFFu, vn, src);
+                u32 b = 0, n = 1, term = 1;
+                if (act) {
+                    b = nth_set_bit(st_s, g - ex_s);
+                    const u32 rest = E_s & ~((2u << b) - 1u);            // bits above b
+                    u32 e = 64;                                          // e = 64: no end found (flagged below)
+                    if (rest) { e = (u32)__ffs((int)rest) - 1; term = ((v_s >> e) & 1u) ^ 1u; }
+                    else if (En_s) { const u32 en = (u32)__ffs((int)En_s) - 1; e = 32 + en; term = ((vn_s >> en) & 1u) ^ 1u; }
+                    n = e - b;
+                    if (n > CH_WMAX || n == 0) { flags |= 4u; n = 1; term = 1; }
+                }
+                fresh(act, (u32)src * 32u + b, n, term);
                 while (n2 >= 32u) drain2();
             }
         }
-        while (n1) drain1();                                             // queue entries die with the staged unit
-        while (n2 >= 32u) drain2();
     }
     while (n2) drain2();
     for (int d = 16; d > 0; d >>= 1) n_inst += __shfl_down_sync(0xFFFFFFFFu, n_inst, d);
     if (lane == 0 && n_inst) atomicAdd(&cc->n_instances, n_inst);
+    for (int d = 16; d > 0; d >>= 1) n_new += __shfl_down_sync(0xFFFFFFFFu, n_new, d);
+    if (lane == 0 && n_new) atomicAdd(&cc->n_first, (u64)n_new);
     if (flags & 1u) cc->chunk_overflow = 1;
     if (flags & 2u) cc->list_overflow = 1;
     if (flags & 4u) cc->bad_chunk = 1;
@@ -521,6 +537,8 @@ k_chunk_insert(const u64 *__restrict__ packed, u64 n_words_padded, const u64 *__
 //           slides, debruijn.py:127-128), feeds a HyperLogLog sketch of the node keys (sizes the node
 //           table) and leaves ONE BYTE per (record, node) = top 8 bits of the node's slot hash
 //           (255 = no node), 16 bytes per record
+//   MODE 2  MODE 1 without the hash bytes of a sketch pass: the lane hashes its record's nodes itself (the
+//           build that knows its table sizes from the previous one on the handle skips MODE 0 altogether)
 //   MODE 1  node-table pass: owns the hash bytes [lo8, lo8 + span8], whose home slots form a table
 //           region small enough to stay L2-resident.  A lane compares its record's 16 bytes at once
 //           (SIMD byte compares) and only rebuilds the keys of the nodes in range; those are queued in
@@ -585,22 +603,11 @@ k_expand(const ChunkSlot<W> *__restrict__ recs_a, u64 n_a, const ChunkSlot<W> *_
     u32 head = 0, nq = 0;
     bool overflow = false;
 
-    // up to 32 * EX_ILP entries per drain: every lane issues the slot loads of all its entries before it
-    // looks at the first one, so EX_ILP random accesses per lane are in flight
-    auto drain = [&]() {
-        __syncwarp();
-        const u32 cap = 32u * EX_ILP;
-        const u32 take = nq < cap ? nq : cap;
-        bool act[EX_ILP]; K key[EX_ILP]; u64 tag[EX_ILP]; u32 cnt[EX_ILP]; u32 meta[EX_ILP];
-#pragma unroll
-        for (int i = 0; i < EX_ILP; i++) {
-            const u32 e = (head + 32 * i + lane) & (EX_RCAP - 1);
-            act[i] = 32 * i + lane < take;
-            key[i] = sh.rkey[w][e]; tag[i] = sh.rtag[w][e]; cnt[i] = sh.rcnt[w][e]; meta[i] = sh.rmeta[w][e];
-        }
-        __syncwarp();
-        head = (head + take) & (EX_RCAP - 1);
-        nq -= take;
+    // up to 32 * EX_ILP entries at a time: every lane issues the slot loads of all its entries before it
+    // looks at the first one, so EX_ILP random accesses per lane are in flight.  A probe that finds another
+    // key does not loop: the entry goes to the retry ring (shared memory) and comes back in a later drain.
+    auto probe_entries = [&](const bool (&act)[EX_ILP], K (&key)[EX_ILP], u64 (&tag)[EX_ILP], u32 (&cnt)[EX_ILP],
+                             u32 (&meta)[EX_ILP]) {
         Slot<W> *s[EX_ILP]; K cur[EX_ILP]; u64 seen[EX_ILP];
 #pragma unroll
         for (int i = 0; i < EX_ILP; i++) {
@@ -638,13 +645,29 @@ k_expand(const ChunkSlot<W> *__restrict__ recs_a, u64 n_a, const ChunkSlot<W> *_
             nq += __popc(mk);
         }
     };
+    auto drain = [&]() {                                                 // retries out of the ring
+        __syncwarp();
+        const u32 cap = 32u * EX_ILP;
+        const u32 take = nq < cap ? nq : cap;
+        bool act[EX_ILP]; K key[EX_ILP]; u64 tag[EX_ILP]; u32 cnt[EX_ILP]; u32 meta[EX_ILP];
+#pragma unroll
+        for (int i = 0; i < EX_ILP; i++) {
+            const u32 e = (head + 32 * i + lane) & (EX_RCAP - 1);
+            act[i] = 32 * i + lane < take;
+            key[i] = sh.rkey[w][e]; tag[i] = sh.rtag[w][e]; cnt[i] = sh.rcnt[w][e]; meta[i] = sh.rmeta[w][e];
+        }
+        __syncwarp();
+        head = (head + take) & (EX_RCAP - 1);
+        nq -= take;
+        probe_entries(act, key, tag, cnt, meta);
+    };
 
     const u64 n_total = n_a + n_b;
     const u64 n_batches = (n_total + 31) / 32;
     const u64 warps_total = (u64)gridDim.x * DBG_WARPS;
     for (u64 b = (u64)blockIdx.x * DBG_WARPS + w; b < n_batches; b += warps_total) {
         // the table is full: the host rebuilds it larger (looked at now and then; the flag is set at once)
-        if (MODE == 1 && ((b / warps_total) & 7) == 0 && __any_sync(0xFFFFFFFFu, __ldcg(&ctr->overflow) != 0u)) break;
+        if (MODE != 0 && ((b / warps_total) & 7) == 0 && __any_sync(0xFFFFFFFFu, __ldcg(&ctr->overflow) != 0u)) break;
         const u64 idx = b * 32 + lane;
         u32 n = 0, B = 0, cnt = 0, m16 = 0, batch = 0;
         u64 tag = 0;
@@ -666,12 +689,32 @@ k_expand(const ChunkSlot<W> *__restrict__ recs_a, u64 n_a, const ChunkSlot<W> *_
                     const uint4 hb = __ldg(hbytes + idx);
                     m16 = bytes_in_range(hb.x, lo4, hi4) | (bytes_in_range(hb.y, lo4, hi4) << 4) |
                           (bytes_in_range(hb.z, lo4, hi4) << 8) | (bytes_in_range(hb.w, lo4, hi4) << 12);
-                    if (m16) {
-                        const ulonglong2 tc = __ldcg(reinterpret_cast<const ulonglong2 *>(&rec->tag));   // tag | cnt, pad
-                        tag = tc.x;
-                        cnt = (u32)tc.y;
-                    }
                 }
+                if (MODE == 2 && span8 >= 254u) m16 = (1u << n) - 1u;   // one pass owns every node
+                if (MODE == 2 || m16) {
+                    const ulonglong2 tc = __ldcg(reinterpret_cast<const ulonglong2 *>(&rec->tag));   // tag | cnt, pad
+                    tag = tc.x;
+                    cnt = (u32)tc.y;
+                }
+            }
+        }
+        if (MODE == 2 && span8 < 254u) {
+            // no hash bytes were left by a sketch pass (the table was sized from the previous build on this handle):
+            // roll the node key along the string and pick the nodes of this pass by their hash byte
+            K key = key_add_batch(reg_key<W>(cw, 0, k), batch, k);
+            u32 nmax = n;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+                const u32 x = __shfl_xor_sync(0xFFFFFFFFu, nmax, d);
+                nmax = x > nmax ? x : nmax;
+            }
+#pragma unroll
+            for (int j = 0; j < CH_WMAX; j++) {
+                if ((u32)j >= nmax) break;
+                const u32 hsh = hash32_key(key);
+                const u32 byte = (hsh >> 24) > 254u ? 254u : (hsh >> 24);
+                if ((u32)j < n && byte - lo8 <= span8) m16 |= 1u << j;
+                key = key_roll(key, string_base<W>(cw, (u32)(j + k)), mask);
             }
         }
         if (MODE == 0) {
@@ -699,26 +742,57 @@ k_expand(const ChunkSlot<W> *__restrict__ recs_a, u64 n_a, const ChunkSlot<W> *_
             }
             if (idx < n_total) hbytes[idx] = make_uint4(hb[0], hb[1], hb[2], hb[3]);
         } else {
-            while (__any_sync(0xFFFFFFFFu, m16 != 0u)) {
-                const bool want = m16 != 0u;
-                const u32 j = want ? (u32)__ffs((int)m16) - 1 : 0u;
-                m16 &= m16 - 1;
-                const u32 mk = __ballot_sync(0xFFFFFFFFu, want);
-                if (want) {
+            // ---- hand the selected (record, node) pairs to the lanes, 32 * EX_ILP at a time.  No lane walks its own
+            // record's nodes one by one (that loop ran at 1/4 lane occupancy and was half of this kernel's
+            // instructions): pair g belongs to the lane s with excl[s] <= g < incl[s] (prefix sums of the per-record
+            // counts, found by a 5-step search over shuffles) and is the (g - excl[s])-th set bit of that lane's mask;
+            // the record's words, tag and multiplicity come over by shuffle and the node key is cut in registers.
+            const u32 c = __popc(m16);
+            u32 incl = c;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const u32 x = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                if (lane >= (u32)d) incl += x;
+            }
+            const u32 total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+            const u32 excl = incl - c;
+            const u32 packed = m16 | (B << 16);
+            for (u32 base = 0; base < total; base += 32u * EX_ILP) {
+                bool act[EX_ILP]; K key[EX_ILP]; u64 tg[EX_ILP]; u32 cn[EX_ILP]; u32 meta[EX_ILP];
+#pragma unroll
+                for (int i = 0; i < EX_ILP; i++) {
+                    const u32 g = base + 32u * i + lane;
+                    act[i] = g < total;
+                    u32 lo = 0;                                          // first lane whose inclusive sum exceeds g
+#pragma unroll
+                    for (int step = 16; step > 0; step >>= 1) {
+                        const u32 v = __shfl_sync(0xFFFFFFFFu, incl, (int)((lo + step - 1) & 31u));
+                        if (v <= g) lo += (u32)step;
+                    }
+                    const int src = (int)(lo & 31u);
+                    const u32 ex_s = __shfl_sync(0xFFFFFFFFu, excl, src);
+                    const u32 pm = __shfl_sync(0xFFFFFFFFu, packed, src);
+                    u64 cws[2 * W];
+#pragma unroll
+                    for (int q = 0; q < 2 * W; q++) cws[q] = __shfl_sync(0xFFFFFFFFu, cw[q], src);
+                    const u64 tag_s = __shfl_sync(0xFFFFFFFFu, tag, src);
+                    const u32 cnt_s = __shfl_sync(0xFFFFFFFFu, cnt, src);
+                    const u32 batch_s = batch_bits ? __shfl_sync(0xFFFFFFFFu, batch, src) : 0u;
+                    const u32 j = act[i] ? nth_set_bit(pm & 0xFFFFu, g - ex_s) : 0u;
                     const u32 q = j + (u32)k;
-                    const bool has_next = q < B;
-                    const u32 nb = string_base<W>(cw, q);
-                    const u32 o = (head + nq + __popc(mk & lt)) & (EX_RCAP - 1);
-                    sh.rkey[w][o] = key_add_batch(reg_key<W>(cw, j, k), batch, k); sh.rtag[w][o] = tag + j;
-                    sh.rcnt[w][o] = cnt;
-                    sh.rmeta[w][o] = (u16)((has_next ? 4u : 0u) | (has_next ? nb : 0u));
+                    const bool has_next = q < (pm >> 16);
+                    const u32 nb = string_base<W>(cws, q);
+                    key[i] = key_add_batch(reg_key<W>(cws, j, k), batch_s, k);
+                    tg[i] = tag_s + j;
+                    cn[i] = cnt_s;
+                    meta[i] = (has_next ? 4u : 0u) | (has_next ? nb : 0u);
                 }
-                nq += __popc(mk);
+                probe_entries(act, key, tg, cn, meta);
                 while (nq >= 32u * EX_ILP) drain();
             }
         }
     }
-    if (MODE == 1) {
+    if (MODE != 0) {
         while (nq) drain();
         if (overflow) ctr->overflow = 1;
     }
@@ -785,7 +859,7 @@ DBG_D u32 chunk_owner(const u64 *cw, int w, int m, u32 batch, u32 n_parts) {
         const int s = 2 * i;                                   // i < 16: inside the first two words
         const u64 t = s ? ((cw[0] << s) | (cw[1] >> (64 - s))) : cw[0];
         const u32 x = (u32)(t >> 32) >> (32 - 2 * m);
-        const u32 g = (((x * 0x9E3779B1u) >> 8) & 0xFFFFFFC0u) | (u32)i;
+        const u32 g = ((x * 0x9E3779B1u) | 63u) - (u32)(63 - i);          // exactly k_masks' order: hash, then leftmost
         if (g < best) { best = g; best_x = x; }
     }
     const u32 hsh = hash32_key((u64)best_x | ((u64)batch << 32));

@@ -266,7 +266,7 @@ DBG_D u64 table_find(const Slot<W> *table, u64 n_slots, typename KeyOf<W>::type 
     typedef typename KeyOf<W>::type K;
     const K EMPTY = empty_key<W>();
     u64 idx = slot_home(hash32_key(key), n_slots);
-    for (u64 probes = 0; probes < n_slots; ++probes) {
+    for (u32 probes = (u32)n_slots; probes; --probes) {          // n_slots < 2^32; a torn (overflowed) table may be full
         K cur = load_key(&table[idx]);
         if (cur == key) return idx;
         if (cur == EMPTY) return NONE64;
@@ -283,6 +283,14 @@ DBG_D u64 table_find(const Slot<W> *table, u64 n_slots, typename KeyOf<W>::type 
 // of distinct successors (the reference's outdegree).
 // ---------------------------------------------------------------------------------------------
 DBG_HD u32 prune_successors(const u32 cnt[4], const u64 *first, double threshold) {
+    // almost every node has at most one distinct successor: no sort, no indexed array (which would live in
+    // local memory: that loop was a third of k_finalize's instructions)
+    const u32 nz = (cnt[0] ? 1u : 0u) | (cnt[1] ? 2u : 0u) | (cnt[2] ? 4u : 0u) | (cnt[3] ? 8u : 0u);
+    if ((nz & (nz - 1u)) == 0u) {
+        if (nz == 0u) return 0u;
+        const u32 c = (nz >> 1) - (nz >> 3);                        // 1, 2, 4, 8 -> 0, 1, 2, 3
+        return (1u << 12) | (1u << 8) | c;
+    }
     int order[4], m = 0;
     for (int c = 0; c < 4; c++) if (cnt[c]) order[m++] = c;
     for (int a = 1; a < m; a++) {                  // insertion sort: count desc, then first asc

@@ -188,13 +188,13 @@ DBG_D void for_windows(const u64 *__restrict__ packed, const u64 *__restrict__ o
 // ---------------------------------------------------------------------------------------------
 template <int W>
 __global__ void __launch_bounds__(DBG_BLOCK) k_table_init(Slot<W> *table, u64 n_slots) {
-    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_slots) return;
+    // grid-stride: a small grid on a side stream clears the table in the background of the packing kernels
+    // (a full grid would take every block slot of every SM and serialise with them)
     Slot<W> s;
     s.key = empty_key<W>();
     s.tag = ~0ULL;
     s.cnt[0] = s.cnt[1] = s.cnt[2] = s.cnt[3] = 0;
-    table[i] = s;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += (u64)gridDim.x * blockDim.x) table[i] = s;
 }
 
 #define DBG_WARPS (DBG_BLOCK / 32)

@@ -40,13 +40,15 @@ def _device_of(graph, group):
     return torch.device('cpu')
 
 
-def _all_gather_var(t, group):
-    """All-gather of int64 tensors [n_i, words] with different n_i; returns the concatenation."""
+def _all_gather_var(t, group, ns=None):
+    """All-gather of int64 tensors [n_i, words] with different n_i; returns the concatenation.
+    `ns` = the n_i of every rank if the caller already knows them (saves a collective + a host wait)."""
     world = dist.get_world_size(group)
-    n = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
-    ns = torch.zeros(world, dtype=torch.int64, device=t.device)
-    dist.all_gather_into_tensor(ns, n, group=group)
-    ns = [int(x) for x in ns.tolist()]
+    if ns is None:
+        n = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
+        ns = torch.zeros(world, dtype=torch.int64, device=t.device)
+        dist.all_gather_into_tensor(ns, n, group=group)
+        ns = [int(x) for x in ns.tolist()]
     m = max(max(ns), 1)
     words = t.shape[1]
     if t.shape[0] < m:
@@ -251,7 +253,7 @@ def build_sharded(graph: Graph, local_packed, read_idx_base, threshold=3, final=
     _fence(dev, graph)
     mine = torch.empty((n_rv, 2), dtype=torch.int64, device=dev)
     graph.shard_reduced_records(replies.data_ptr(), rid_base, mine.data_ptr())
-    everything, _ = _all_gather_var(mine, group)
+    everything, _ = _all_gather_var(mine, group, all_nrv)
     _fence(dev, graph)
     if stats is not None:
         stats['walk_bytes_out'] = (n_exit - sc[rank]) * W * 8 + (sum(rc) - rc[rank]) * 4 + n_rv * 16 * (world - 1)

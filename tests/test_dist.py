@@ -99,9 +99,12 @@ def _sharded_worker(rank, world, port, cases, out_q):
     os.environ['MASTER_PORT'] = str(port)
     dist.init_process_group('gloo', rank=rank, world_size=world)
     results = []
+    handles = {}                                   # one handle per k, reused: later builds are sized from the remembered hints
     for reads, k, thr, final in cases:
         b = ddist.shard_bounds(len(reads), world)
-        g = Graph(k)
+        g = handles.get(k)
+        if g is None:
+            g = handles[k] = Graph(k)
         res = ddist.build_sharded(g, pack_reads(reads[b[rank]:b[rank + 1]]), b[rank], threshold=thr, final=final)
         snap = ddist.global_snapshot(res)
         if rank == 0:
@@ -112,6 +115,7 @@ def _sharded_worker(rank, world, port, cases, out_q):
             diff = [f for f in exp if not np.array_equal(np.asarray(snap[f]), np.asarray(exp[f]))]
             results.append((res.mode, diff, int(len(snap['c_n'])), ddist.snapshot_digest(snap) == ddist.snapshot_digest(exp)))
             ref.close()
+    for g in handles.values():
         g.close()
     out_q.put((rank, results))
     dist.barrier()
@@ -128,6 +132,8 @@ def test_sharded_walk_equals_single(world):
     cases = []
     _, clean = util.synth_reads(41, 4000, 70, 10, err=0.0)
     cases.append((clean, 17, 2, False))                              # error-free: no branch nodes, sharded walk
+    cases.append((clean, 17, 2, False))                              # the same again on the same handle: sized from its hints
+    cases.append((clean[:len(clean) // 2] + [x[::-1] for x in clean], 17, 2, False))   # more distinct k-mers than remembered
     cases.append((clean, 35, 2, False))                              # 128-bit keys
     cases.append((clean, 17, 2, True))
     cases.append((['ACGTACGTACGTACGT'], 4, 2, False))                # a pure cycle: the start emits nothing
