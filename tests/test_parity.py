@@ -400,7 +400,7 @@ def test_remembered_table_sizes(backend, monkeypatch):
             slots.append((int(st.chunk_slots), int(st.table_slots)))
             assert st.n_windows == sum(max(0, len(x) - k) for x in reads)
             assert [r_ for r_, f in zip(reads, g.pull_read_flags().tolist()) if f] == exp['pull_out_read']
-        assert slots[2][0] > 2 * slots[1][0] and slots[2][1] > 2 * slots[1][1]      # the remembered sizes did not fit: redone cold
+        assert slots[2][1] > 2 * slots[1][1]                          # the remembered sizes did not fit: rebuilt larger
         assert st.n_insert_passes > 1
         monkeypatch.setenv('DBG_B200_NO_HINT', '1')
         g.build(clean, threshold=2, final=False)
