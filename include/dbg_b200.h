@@ -91,13 +91,13 @@ typedef struct {
     uint32_t key_words;      /* 1 (k <= 31) or 2                                              */
     uint32_t jump_rounds;    /* pointer-jumping rounds run by dbg_walk                        */
     uint32_t n_insert_passes;/* L2-resident partition passes of the table build               */
-    uint32_t reserved0;
+    uint32_t n_regions;      /* node table laid out by minimizer: regions (1 = plain hash layout)   */
     /* device time per stage, CUDA events on the handle's stream, milliseconds */
     float ms_h2d, ms_pack, ms_estimate, ms_table_init, ms_insert, ms_finalize, ms_order,
           ms_lists, ms_tips, ms_pull_reads, ms_build_total, ms_walk_rank, ms_walk_emit,
           ms_walk_total,
           /* parts of ms_insert when the chunk build runs (dbg_chunks.cuh): */
-          ms_chunk_insert, ms_expand_sketch, ms_expand, reserved1;
+          ms_chunk_insert, ms_expand_sketch, ms_expand, ms_region_order;
 } dbg_stats_t;
 
 typedef struct {
@@ -127,6 +127,12 @@ void dbg_destroy(dbg_t *h);
 const char *dbg_last_error(const dbg_t *h);          /* h may be NULL: error of a failed create */
 int  dbg_set_stream(dbg_t *h, void *cuda_stream);    /* cudaStream_t; NULL = handle's own stream */
 int  dbg_version(void);
+/* EXTENSION without a reference line (SURVEY.md section 9 delta 5; BASELINE.json configs[2] "abundance filter
+ * min-count=2"): the following builds on this handle skip every window whose (k+1)-mer occurs fewer than
+ * min_count times over all reads, as if `if total[read[i:i+k+1]] < min_count: continue` stood at the top of the
+ * loop body of debruijn.py:126; everything downstream is the reference's semantics on what is left.  1 = off
+ * (the reference).  Pinned by oracle/dbg_oracle.py build(min_count) and oracle/dbg_oracle.c build_filtered only. */
+int  dbg_set_min_count(dbg_t *h, uint32_t min_count);
 
 /* ---- construct_graph (debruijn.py:206-285) ----
  * reads = concatenated ASCII bases + n_reads+1 offsets; read i is bases[off[i] .. off[i+1]).

@@ -35,6 +35,8 @@ def lib():
         L = C.CDLL(LIB)
         L.dbgo_run.restype = C.c_void_p
         L.dbgo_run.argtypes = [C.c_char_p, C.c_void_p, C.c_uint64, C.c_int, C.c_double, C.c_int, C.c_int]
+        L.dbgo_run_mc.restype = C.c_void_p
+        L.dbgo_run_mc.argtypes = [C.c_char_p, C.c_void_p, C.c_uint64, C.c_int, C.c_double, C.c_int, C.c_int, C.c_uint32]
         L.dbgo_free.argtypes = [C.c_void_p]
         L.dbgo_error.argtypes = [C.c_void_p]
         for name in ('n_nodes', 'n_windows', 'n_branch', 'n_branch_internal', 'n_pulled', 'n_starts',
@@ -131,12 +133,12 @@ class Result:
         return decode(self.key_lo[v], self.key_hi[v], self.k)
 
 
-def run(reads, k, threshold, final, stages=3, strings=True, packed=None):
+def run(reads, k, threshold, final, stages=3, strings=True, packed=None, min_count=1):
     """Run the C oracle.  `packed` = (bytes, offsets) skips re-packing of `reads`."""
     L = lib()
     data, off = packed if packed is not None else pack_reads(reads)
     n_reads = len(off) - 1
-    h = L.dbgo_run(data, off.ctypes.data, n_reads, k, float(threshold), int(bool(final)), stages)
+    h = L.dbgo_run_mc(data, off.ctypes.data, n_reads, k, float(threshold), int(bool(final)), stages, int(min_count))
     if not h:
         raise ValueError('k out of range for the C oracle (1..63)')
     try:
@@ -153,9 +155,9 @@ def run(reads, k, threshold, final, stages=3, strings=True, packed=None):
         L.dbgo_free(h)
 
 
-def snapshot(reads, k, threshold, final):
+def snapshot(reads, k, threshold, final, min_count=1):
     """Same structure as dbg_oracle.snapshot (DNA inputs only)."""
-    res = run(reads, k, threshold, final)
+    res = run(reads, k, threshold, final, min_count=min_count)
     lab = [res.label(v) for v in range(res.n_nodes)]
     edges = []
     for v in range(res.n_nodes):

@@ -32,6 +32,7 @@
 #else
 #include <cuda_runtime.h>
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 #define LAUNCH(kernel, grid, block, stream, ...) \
     (h->st.n_launches++, kernel<<<(unsigned)(grid), (unsigned)(block), 0, stream>>>(__VA_ARGS__))
 #define LAUNCH_SMEM(kernel, grid, block, smem, stream, ...) \
@@ -129,6 +130,15 @@ struct dbg_handle {
     struct { bool valid = false; uint64_t n_bases = 0, chunks = 0, nodes = 0; uint32_t n_batches = 0; } hint;
     bool hinted = false, preinit = false;
     bool have_hbytes = false;                 // a sketch pass (k_expand MODE 0) left hash bytes for the chunks now in the tables
+    // node table laid out by minimizer (TGeom, dbg_common.cuh): region_slots > 0.  region_mode is decided per build
+    // (minimizer long enough to spread over regions); have_vhash / have_order: the per-record region hashes +
+    // histogram / the record order of the chunks now in the tables are valid
+    bool region_mode = false, have_vhash = false, have_order = false;
+    uint32_t region_slots = 0;
+    uint32_t min_count = 1;                   // EXTENSION (dbg_set_min_count): windows whose (k+1)-mer is rarer are skipped
+    int expand_evs = 3;                       // events the last expand_node_table marked
+    int vb_bits = 0;
+    DevBuf b_recvh, b_vhist, b_voffs, b_recorder;
     uint64_t last_est_chunks = 0;
     uint64_t shard_hint_nodes = 0;            // nodes of the last shard this handle expanded (dbg_chunk_expand)
     bool merge_check_pending = false;         // dbg_chunk_merge_records' overflow flag is looked at by graph_finalize
@@ -148,6 +158,7 @@ struct dbg_handle {
 };
 
 static std::string g_create_error;
+static TGeom geom_of(const dbg_t *h);
 
 static int fail(dbg_t *h, int code, const char *fmt, ...) {
     char buf[512];
@@ -344,7 +355,7 @@ static int tip_prune(dbg_t *h) {
                ptr<const u32>(h->b_estart), ptr<const GEdge>(h->b_earr), ptr<const u32>(h->b_branch), nb, 0,
                ptr<u32>(h->b_cnt32), (const u64 *)nullptr, (u32 *)nullptr);
     else
-        LAUNCH(k_tip_paths<W>, blocks_for(nb), DBG_BLOCK, h->stream, ptr<const Slot<W>>(h->b_table), h->n_slots, h->k,
+        LAUNCH(k_tip_paths<W>, blocks_for(nb), DBG_BLOCK, h->stream, ptr<const Slot<W>>(h->b_table), geom_of(h), h->k,
                ptr<const u8>(h->b_flags), ptr<const u16>(h->b_kept), ptr<const u32>(h->b_branch), nb, 0,
                ptr<u32>(h->b_cnt32), (const u64 *)nullptr, (u32 *)nullptr, ptr<DevCounters>(h->b_ctr));
     CKK();
@@ -363,7 +374,7 @@ static int tip_prune(dbg_t *h) {
                ptr<const u32>(h->b_estart), ptr<const GEdge>(h->b_earr), ptr<const u32>(h->b_branch), nb, 1,
                ptr<u32>(h->b_cnt32), ptr<const u64>(h->b_off64), ptr<u32>(h->b_recs));
     else
-        LAUNCH(k_tip_paths<W>, blocks_for(nb), DBG_BLOCK, h->stream, ptr<const Slot<W>>(h->b_table), h->n_slots, h->k,
+        LAUNCH(k_tip_paths<W>, blocks_for(nb), DBG_BLOCK, h->stream, ptr<const Slot<W>>(h->b_table), geom_of(h), h->k,
                ptr<const u8>(h->b_flags), ptr<const u16>(h->b_kept), ptr<const u32>(h->b_branch), nb, 1,
                ptr<u32>(h->b_cnt32), ptr<const u64>(h->b_off64), ptr<u32>(h->b_recs), ptr<DevCounters>(h->b_ctr));
     CKK();
@@ -433,6 +444,128 @@ static uint32_t pass_count(dbg_t *h, uint64_t table_bytes) {
     if (n > 255) n = 255;
     (void)h;
     return (uint32_t)n;
+}
+
+// ---- node table laid out by minimizer: geometry, record order ----
+static bool want_regions(const dbg_t *h) {
+    // the region of a node is a hash of its minimizer (+ batch id): short minimizers take too few values to spread
+    const ChunkGeom g = chunk_geom(h->k);
+    bool on = 2 * g.m + h->batch_bits >= 24 && h->sym_bits == 2;
+    if (const char *e = getenv("DBG_B200_REGIONS")) on = atoi(e) != 0 && h->sym_bits == 2;    // tests / tuning: 0 = plain hash layout, 1 = force
+    return on;
+}
+#define VB_BITS_MAX 21
+static int vb_bits_for(uint64_t n_record_slots) {             // virtual buckets: >= record slots / 16, 2^10 .. 2^21
+    int b = 10;
+    while (b < VB_BITS_MAX && (1ull << b) < n_record_slots / 16) b++;
+    if (const char *e = getenv("DBG_B200_VB_BITS")) {              // tests: a few buckets, nearly every record spills
+        const int v = atoi(e);
+        if (v >= 1 && v <= VB_BITS_MAX) b = v;
+    }
+    return b;
+}
+// node-table size for `want` slots under the current layout: whole regions, at most 2^vb_bits / 4 of them
+static uint64_t fit_slots(dbg_t *h, uint64_t want) {
+    h->region_slots = 0;
+    if (!h->region_mode) return want;
+    uint64_t R = 2048;
+    if (const char *e = getenv("DBG_B200_REGION_SLOTS")) {        // tests: many small regions
+        const unsigned long long v = strtoull(e, nullptr, 10);
+        if (v >= 2) R = v;
+    }
+    const uint64_t max_regions = (1ull << (h->vb_bits && !getenv("DBG_B200_VB_BITS") ? h->vb_bits : VB_BITS_MAX)) / 4;
+    if (cdiv(want, R) > max_regions) R = cdiv(want, max_regions);
+    if (R >= 0xFFFFFFFFull) return want;
+    h->region_slots = (uint32_t)R;
+    return cdiv(want, R) * R;
+}
+static TGeom geom_of(const dbg_t *h) {
+    TGeom g = plain_geom(h->n_slots);
+    if (h->region_slots && h->n_slots >= h->region_slots && h->n_slots % h->region_slots == 0) {
+        const ChunkGeom cg = chunk_geom(h->k);
+        g.n_regions = (u32)(h->n_slots / h->region_slots);
+        g.region_slots = h->region_slots;
+        g.k = h->k; g.w = cg.w; g.m = cg.m;
+    }
+    return g;
+}
+
+// per record slot: region hash + histogram over virtual buckets (+ the node-key sketch that sizes the node table)
+template <int W>
+static int launch_rec_vhash(dbg_t *h, bool sketch) {
+    typedef ChunkSlot<W> CS;
+    const uint64_t n_rec = h->n_cslots + h->n_clist;
+    if (n_rec >= 0xFFFFFFF0ull) return fail(h, DBG_ERR_OVERFLOW, "more than 2^32 chunk record slots");
+    const ChunkGeom cg = chunk_geom(h->k);
+    h->vb_bits = vb_bits_for(n_rec);
+    TRY(reserve(h, h->b_recvh, (n_rec + 32) * 4));
+    TRY(reserve(h, h->b_vhist, ((1ull << h->vb_bits) + 2) * 4));
+    CK(cudaMemsetAsync(h->b_vhist.p, 0, ((1ull << h->vb_bits) + 2) * 4, h->stream));
+    uint64_t grid = blocks_for(n_rec);
+    if (grid > 148 * 16) grid = 148 * 16;
+    if (sketch) {
+        CK(cudaMemsetAsync(h->b_hll.p, 0, HLL_M * 4, h->stream));
+        LAUNCH((k_rec_vhash<W, true>), grid, DBG_BLOCK, h->stream, ptr<const CS>(h->b_ctable), h->n_cslots,
+               ptr<const CS>(h->b_clist), h->n_clist, h->k, cg.w, cg.m, h->batch_bits, h->vb_bits, ptr<u32>(h->b_recvh),
+               ptr<u32>(h->b_vhist), ptr<u32>(h->b_hll));
+    } else {
+        LAUNCH((k_rec_vhash<W, false>), grid, DBG_BLOCK, h->stream, ptr<const CS>(h->b_ctable), h->n_cslots,
+               ptr<const CS>(h->b_clist), h->n_clist, h->k, cg.w, cg.m, h->batch_bits, h->vb_bits, ptr<u32>(h->b_recvh),
+               ptr<u32>(h->b_vhist), (u32 *)nullptr);
+    }
+    CKK();
+    h->have_vhash = true;
+    h->have_order = false;
+    return DBG_OK;
+}
+
+// the records in region order: exclusive scan of the histogram, then one scatter
+static int launch_rec_order(dbg_t *h) {
+    const uint64_t n_rec = h->n_cslots + h->n_clist;
+    const uint64_t nv = (1ull << h->vb_bits) + 1;                  // + 1: the total lands behind the last bucket
+    TRY(reserve(h, h->b_voffs, (nv + 1) * 4));
+    TRY(reserve(h, h->b_recorder, (n_rec + 32) * 8));
+#ifdef DBG_EMU
+    {
+        const u32 *hist = ptr<const u32>(h->b_vhist);
+        u32 *offs = ptr<u32>(h->b_voffs);
+        u32 acc = 0;
+        for (uint64_t i = 0; i < nv; i++) { offs[i] = acc; acc += hist[i]; }
+    }
+#else
+    {
+        size_t tmp = 0;
+        CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp, ptr<const u32>(h->b_vhist), ptr<u32>(h->b_voffs), (int)nv, h->stream));
+        TRY(reserve(h, h->b_sorttmp, tmp));
+        h->st.n_launches++;
+        CK(cub::DeviceScan::ExclusiveSum(h->b_sorttmp.p, tmp, ptr<const u32>(h->b_vhist), ptr<u32>(h->b_voffs), (int)nv, h->stream));
+    }
+#endif
+    uint64_t grid = blocks_for(n_rec);
+    if (grid > 148 * 16) grid = 148 * 16;
+    LAUNCH(k_rec_order, grid, DBG_BLOCK, h->stream, ptr<const u32>(h->b_recvh), n_rec, h->vb_bits, ptr<u32>(h->b_vhist),
+           ptr<const u32>(h->b_voffs), ptr<u64>(h->b_recorder));
+    CKK();
+    h->have_order = true;
+    return DBG_OK;
+}
+
+// sketch of the node keys of the distinct chunks (sizes the node table); leaves what the node-table pass(es) want
+// with it: hash bytes per (record, node) for the plain layout, region hashes + histogram for the region layout
+template <int W>
+static int launch_node_sketch(dbg_t *h, uint64_t ex_grid) {
+    typedef Slot<W> S;
+    typedef ChunkSlot<W> CS;
+    if (h->region_mode) return launch_rec_vhash<W>(h, true);
+    TRY(reserve(h, h->b_h8, (h->n_cslots + h->n_clist + 32) * 16));      // one hash byte per (record, node)
+    CK(cudaMemsetAsync(h->b_hll.p, 0, HLL_M * 4, h->stream));
+    LAUNCH((k_expand<W, 0>), ex_grid, DBG_BLOCK, h->stream, ptr<const CS>(h->b_ctable), h->n_cslots,
+           ptr<const CS>(h->b_clist), h->n_clist, h->k, ptr<uint4>(h->b_h8), (S *)nullptr, 0u, 0u, 0u,
+           ptr<u32>(h->b_hll), h->batch_bits, ptr<DevCounters>(h->b_ctr), (const u64 *)nullptr, (const u32 *)nullptr,
+           plain_geom(0));
+    CKK();
+    h->have_hbytes = true;
+    return DBG_OK;
 }
 
 // phase 1 over the units [u0, u1) of the read stream
@@ -508,7 +641,19 @@ static int expand_node_table(dbg_t *h) {
     const bool self_hash = !h->have_hbytes;                          // no sketch pass ran: no hash bytes
     h->preinit = false;                                              // a rebuild (overflow) initialises its own table
     const int b = ev_mark(h);
-    if (st.n_windows) {
+    if (st.n_windows && geom_of(h).n_regions > 1) {
+        // table laid out by minimizer: ONE pass over the records in region order, the table is built front to back
+        if (!h->have_vhash) TRY(launch_rec_vhash<W>(h, false));
+        if (!h->have_order) TRY(launch_rec_order(h));
+        const int b2 = ev_mark(h);
+        tm_add(h, &st.ms_region_order, b, b2);
+        st.n_insert_passes = 1;
+        LAUNCH((k_expand<W, 3>), h->ex_grid, DBG_BLOCK, h->stream, ptr<const CS>(h->b_ctable), h->n_cslots,
+               ptr<const CS>(h->b_clist), h->n_clist, h->k, (uint4 *)nullptr, ptr<S>(h->b_table), 0u, 0u, 254u,
+               (u32 *)nullptr, h->batch_bits, d_ctr, ptr<const u64>(h->b_recorder),
+               ptr<const u32>(h->b_voffs) + (1ull << h->vb_bits), geom_of(h));
+        CKK();
+    } else if (st.n_windows) {
         uint32_t n_parts = pass_count(h, n_slots * sizeof(S));
         if (n_parts > 255) n_parts = 255;
         st.n_insert_passes = n_parts;
@@ -519,11 +664,13 @@ static int expand_node_table(dbg_t *h) {
             if (self_hash)
                 LAUNCH((k_expand<W, 2>), h->ex_grid, DBG_BLOCK, h->stream, ptr<const CS>(h->b_ctable), h->n_cslots,
                        ptr<const CS>(h->b_clist), h->n_clist, h->k, (uint4 *)nullptr, ptr<S>(h->b_table), (u32)n_slots,
-                       lo8, n_parts == 1 ? 254u : hi8 - lo8, (u32 *)nullptr, h->batch_bits, d_ctr);
+                       lo8, n_parts == 1 ? 254u : hi8 - lo8, (u32 *)nullptr, h->batch_bits, d_ctr, (const u64 *)nullptr,
+                       (const u32 *)nullptr, plain_geom(n_slots));
             else
                 LAUNCH((k_expand<W, 1>), h->ex_grid, DBG_BLOCK, h->stream, ptr<const CS>(h->b_ctable), h->n_cslots,
                        ptr<const CS>(h->b_clist), h->n_clist, h->k, ptr<uint4>(h->b_h8), ptr<S>(h->b_table), (u32)n_slots,
-                       lo8, hi8 - lo8, (u32 *)nullptr, h->batch_bits, d_ctr);
+                       lo8, hi8 - lo8, (u32 *)nullptr, h->batch_bits, d_ctr, (const u64 *)nullptr, (const u32 *)nullptr,
+                       plain_geom(n_slots));
             CKK();
         }
     }
@@ -533,6 +680,8 @@ static int expand_node_table(dbg_t *h) {
     tm_add(h, &st.ms_expand, b, c);
     st.table_slots = n_slots;
     st.table_bytes = n_slots * sizeof(S);
+    st.n_regions = geom_of(h).n_regions;
+    h->expand_evs = h->n_ev - a;
     return DBG_OK;
 }
 
@@ -549,7 +698,7 @@ static int settle_node_table(dbg_t *h, bool fetched) {
         if (attempt >= 6) return fail(h, DBG_ERR_NOMEM, "node table overflowed repeatedly");
         h->n_slots *= 2;                                               // estimate was low: rebuild larger
         CK(cudaMemsetAsync(&d_ctr->overflow, 0, 4, h->stream));
-        if (h->n_ev >= 3) h->n_ev -= 3;                                // (the table may have been expanded by an earlier call)
+        if (h->n_ev >= h->expand_evs) h->n_ev -= h->expand_evs;                                // (the table may have been expanded by an earlier call)
         TRY(expand_node_table<W>(h));
     }
     h->expand_pending = false;
@@ -621,16 +770,10 @@ static int build_chunks(dbg_t *h, const u64 *d_off, int e0, int e1) {
             tm_set(h, &st.ms_build_total, e0, e_endc);
             return DBG_OK;
         }
-        if (pass_count(h, h->n_slots * sizeof(S)) > 2) {
+        if (!h->region_mode && pass_count(h, h->n_slots * sizeof(S)) > 2) {
             // many node-table passes: one sweep that leaves a hash byte per (record, node) is cheaper than hashing every
             // node again in every pass (measured at C3, 10 passes: 2.8 ms with the bytes, 4.3 ms without)
-            TRY(reserve(h, h->b_h8, (h->n_cslots + h->n_clist + 32) * 16));
-            CK(cudaMemsetAsync(h->b_hll.p, 0, HLL_M * 4, h->stream));
-            LAUNCH((k_expand<W, 0>), h->ex_grid, DBG_BLOCK, h->stream, ptr<const CS>(h->b_ctable), h->n_cslots,
-                   ptr<const CS>(h->b_clist), h->n_clist, k, ptr<uint4>(h->b_h8), (S *)nullptr, 0u, 0u, 0u,
-                   ptr<u32>(h->b_hll), h->batch_bits, d_ctr);
-            CKK();
-            h->have_hbytes = true;
+            TRY(launch_node_sketch<W>(h, h->ex_grid));
         }
         TRY(expand_node_table<W>(h));
         h->expand_pending = true;
@@ -707,12 +850,9 @@ static int build_chunks(dbg_t *h, const u64 *d_off, int e0, int e1) {
         if (ex_grid > (uint64_t)sms * ex_per_sm) ex_grid = (uint64_t)sms * ex_per_sm;
         if (ex_grid < 1) ex_grid = 1;
         if (st.n_windows && !(h->build_flags & DBG_CHUNKS_ONLY)) {      // (chunks that get exchanged are expanded by their owners)
-            CK(cudaMemsetAsync(h->b_hll.p, 0, HLL_M * 4, h->stream));
-            LAUNCH((k_expand<W, 0>), ex_grid, DBG_BLOCK, h->stream, ptr<const CS>(h->b_ctable), n_cslots,
-                   ptr<const CS>(h->b_clist), n_list, k, ptr<uint4>(h->b_h8), (S *)nullptr, 0u, 0u, 0u,
-                   ptr<u32>(h->b_hll), h->batch_bits, d_ctr);
-            CKK();
-            h->have_hbytes = true;
+            h->n_cslots = n_cslots;
+            h->n_clist = n_list;
+            TRY(launch_node_sketch<W>(h, ex_grid));
             CK(cudaMemcpyAsync(s_dst, h->b_hll.p, HLL_M * 4, cudaMemcpyDeviceToHost, h->stream));
         }
         const int d = ev_mark(h);
@@ -779,6 +919,7 @@ static int node_table_from_chunks(dbg_t *h, uint64_t est) {
         const unsigned long long v = strtoull(e, nullptr, 10);
         if (v >= 1) h->n_slots = v;
     }
+    h->n_slots = fit_slots(h, h->n_slots);
     TRY(expand_node_table<W>(h));
     if ((h->build_flags & DBG_TABLE_ONLY) || h->chunks_merged) TRY(settle_node_table<W>(h, false));   // nobody downstream looks at the flag
     else h->expand_pending = true;                                   // graph_finalize looks at it with its own counters
@@ -830,7 +971,8 @@ static int build_impl(dbg_t *h, const u8 *d_bases, const u64 *d_off) {
                 if (v >= 0.05 && v <= 0.95) load = v;
             }
             const bool chunks_only = (h->build_flags & DBG_CHUNKS_ONLY) != 0;
-            const uint64_t n_ns = chunks_only ? 16 : (uint64_t)((double)h->hint.nodes * 1.06 * 1.03 / load) + 1024;
+            h->vb_bits = 0;                                              // (not known yet: fit_slots assumes the largest)
+            const uint64_t n_ns = chunks_only ? 16 : fit_slots(h, (uint64_t)((double)h->hint.nodes * 1.06 * 1.03 / load) + 1024);
             if (n_cs >= 0xFFFFFFF0ull || n_ns >= 0xFFFFFFF0ull) h->hinted = false;
             else {
                 TRY(reserve(h, h->b_ctable, n_cs * sizeof(CS)));
@@ -944,6 +1086,24 @@ static int build_impl(dbg_t *h, const u8 *d_bases, const u64 *d_off) {
     return build_chunks<W>(h, d_off, e0, e1);
 }
 
+// ---- min_count (extension): the graph of the windows whose (k+1)-mer occurs >= min_count times, made from the
+// unfiltered table (whose counters are those totals); kernels k_mc_* in dbg_kernels.cuh ----
+template <int W>
+static int min_count_stage(dbg_t *h) {
+    typedef Slot<W> S;
+    if (h->expand_pending) TRY(settle_node_table<W>(h, false));        // the counters must be complete
+    if (!h->n_bases || !h->st.n_windows) return DBG_OK;
+    uint64_t grid = blocks_for(h->n_slots);
+    if (grid > 148 * 16) grid = 148 * 16;
+    LAUNCH(k_mc_filter<W>, grid, DBG_BLOCK, h->stream, ptr<S>(h->b_table), h->n_slots, h->min_count);
+    CKK();
+    LAUNCH(k_mc_retag<W>, h->n_tiles, DBG_BLOCK, h->stream, ptr<const u64>(h->b_packed), (const u64 *)h->d_off,
+           ptr<const u32>(h->b_tile), h->n_bases, h->k, ptr<S>(h->b_table), geom_of(h), h->read_idx_base,
+           (const u32 *)h->d_read_batch, ptr<DevCounters>(h->b_ctr));
+    CKK();
+    return DBG_OK;
+}
+
 // ---- graph stage A: degrees, pruningEdges, branch flags, successor links (kernel 4) ----
 template <int W>
 static int graph_finalize(dbg_t *h) {
@@ -953,15 +1113,29 @@ static int graph_finalize(dbg_t *h) {
     const int e3 = ev_mark(h);
     for (;;) {
         const uint64_t n_slots = h->n_slots;
-        CK(cudaMemsetAsync(&d_ctr->n_nodes, 0, 5 * 8, h->stream));      // n_nodes .. n_starts
+        CK(cudaMemsetAsync(&d_ctr->n_nodes, 0, 6 * 8, h->stream));      // n_nodes .. n_starts, n_list_a
+        TRY(reserve(h, h->b_link, n_slots * 8));                        // (the walk's links; until then the far list of k_finalize)
         TRY(reserve(h, h->b_flags, n_slots));
         TRY(reserve(h, h->b_kept, n_slots * 2));
         TRY(reserve(h, h->b_succ, n_slots * 4));
-        uint64_t fin_grid = blocks_for(n_slots);
-        if (fin_grid > 148 * 16) fin_grid = 148 * 16;
-        LAUNCH(k_finalize<W>, fin_grid, DBG_BLOCK, h->stream, ptr<const S>(h->b_table), n_slots, h->k,
-               h->threshold, ptr<u8>(h->b_flags), ptr<u16>(h->b_kept), ptr<u32>(h->b_succ), h->shard_n > 1 ? 1 : 0, d_ctr);
+        uint64_t fin_grid = cdiv(cdiv(n_slots, FIN_SLOTS), DBG_WARPS);
+        if (fin_grid > 148 * 8) fin_grid = 148 * 8;
+        if (fin_grid < 1) fin_grid = 1;
+        LAUNCH(k_finalize<W>, fin_grid, DBG_BLOCK, h->stream, ptr<const S>(h->b_table), geom_of(h), h->k,
+               h->threshold, ptr<u8>(h->b_flags), ptr<u16>(h->b_kept), ptr<u32>(h->b_succ), h->shard_n > 1 ? 1 : 0,
+               ptr<u32>(h->b_link), d_ctr);
         CKK();
+        if (geom_of(h).n_regions > 1) {
+            LAUNCH(k_finalize_far<W>, 148 * 4, DBG_BLOCK, h->stream, ptr<const S>(h->b_table), geom_of(h), h->k,
+                   ptr<const u16>(h->b_kept), ptr<const u32>(h->b_link), ptr<u8>(h->b_flags), ptr<u32>(h->b_succ),
+                   h->shard_n > 1 ? 1 : 0, d_ctr);
+            CKK();
+        }
+        if (h->min_count > 1 && h->n_bases) {                           // nodes created as the SOURCE of a surviving window
+            LAUNCH(k_mc_starts<W>, fin_grid, DBG_BLOCK, h->stream, ptr<const u64>(h->b_packed), (const u64 *)h->d_off,
+                   ptr<const S>(h->b_table), geom_of(h), h->k, h->read_idx_base, ptr<u8>(h->b_flags), d_ctr);
+            CKK();
+        }
         TRY(fetch_counters(h));
         tm_flush(h);
         if (h->hinted) {                                               // what the cold path checks between its phases
@@ -1048,7 +1222,7 @@ static int graph_complete(dbg_t *h) {
     DevCounters *d_ctr = ptr<DevCounters>(h->b_ctr);
     const int e4 = ev_mark(h);
     if (h->order_active) {
-        LAUNCH(k_order_apply<W>, blocks_for(h->order_cap), DBG_BLOCK, h->stream, ptr<const S>(h->b_table), n_slots, k,
+        LAUNCH(k_order_apply<W>, blocks_for(h->order_cap), DBG_BLOCK, h->stream, ptr<const S>(h->b_table), geom_of(h), k,
                h->threshold, ptr<const SideEntry<W>>(h->b_order), h->order_cap, ptr<u16>(h->b_kept),
                ptr<u32>(h->b_succ), ptr<u8>(h->b_flags), h->shard_n > 1 ? 1 : 0, d_ctr);
         CKK();
@@ -1179,8 +1353,9 @@ static int chunk_table_reset_impl(dbg_t *h, uint64_t expected_chunks) {
     CK(cudaMemsetAsync(h->b_cc.p, 0, sizeof(ChunkCounters), h->stream));
     h->n_cslots = n;
     h->n_clist = 0;                                                   // boundary chunks arrive as records like the others
+    h->region_mode = want_regions(h);
     h->chunks_merged = true;
-    h->have_hbytes = false;
+    h->have_hbytes = false; h->have_vhash = false; h->have_order = false;
     h->chunks_valid = true;
     h->tags_local = false;
     h->expand_pending = false;
@@ -1224,17 +1399,10 @@ static int chunk_expand_impl(dbg_t *h) {
             const double v = atof(e) / 100.0;
             if (v >= 0.05 && v <= 0.95) load = v;
         }
-        h->n_slots = (uint64_t)((double)h->shard_hint_nodes * 1.06 * 1.03 / load) + 1024;
-        h->have_hbytes = false;
-        if (pass_count(h, h->n_slots * sizeof(S)) > 2) {
-            TRY(reserve(h, h->b_h8, (h->n_cslots + h->n_clist + 32) * 16));
-            CK(cudaMemsetAsync(h->b_hll.p, 0, HLL_M * 4, h->stream));
-            LAUNCH((k_expand<W, 0>), ex_grid, DBG_BLOCK, h->stream, ptr<const CS>(h->b_ctable), h->n_cslots,
-                   ptr<const CS>(h->b_clist), h->n_clist, h->k, ptr<uint4>(h->b_h8), (S *)nullptr, 0u, 0u, 0u,
-                   ptr<u32>(h->b_hll), h->batch_bits, d_ctr);
-            CKK();
-            h->have_hbytes = true;
-        }
+        h->vb_bits = 0;
+        h->n_slots = fit_slots(h, (uint64_t)((double)h->shard_hint_nodes * 1.06 * 1.03 / load) + 1024);
+        h->have_hbytes = false; h->have_vhash = false; h->have_order = false;
+        if (!h->region_mode && pass_count(h, h->n_slots * sizeof(S)) > 2) TRY(launch_node_sketch<W>(h, ex_grid));
         CK(cudaMemcpyAsync(h->ctl + CTL_CC, h->b_cc.p, sizeof(ChunkCounters), cudaMemcpyDeviceToHost, h->stream));
         h->merge_check_pending = true;
         const uint64_t lw = h->st.n_windows;
@@ -1246,13 +1414,7 @@ static int chunk_expand_impl(dbg_t *h) {
         h->table_ready = true;
         return DBG_OK;
     }
-    TRY(reserve(h, h->b_h8, (h->n_cslots + h->n_clist + 32) * 16));
-    CK(cudaMemsetAsync(h->b_hll.p, 0, HLL_M * 4, h->stream));
-    LAUNCH((k_expand<W, 0>), ex_grid, DBG_BLOCK, h->stream, ptr<const CS>(h->b_ctable), h->n_cslots,
-           ptr<const CS>(h->b_clist), h->n_clist, h->k, ptr<uint4>(h->b_h8), (S *)nullptr, 0u, 0u, 0u,
-           ptr<u32>(h->b_hll), h->batch_bits, d_ctr);
-    CKK();
-    h->have_hbytes = true;
+    TRY(launch_node_sketch<W>(h, ex_grid));
     CK(cudaMemcpyAsync(sketch.data(), h->b_hll.p, HLL_M * 4, cudaMemcpyDeviceToHost, h->stream));
     ChunkCounters cc;
     CK(cudaMemcpyAsync(&cc, h->b_cc.p, sizeof cc, cudaMemcpyDeviceToHost, h->stream));
@@ -1270,7 +1432,9 @@ static int chunk_expand_impl(dbg_t *h) {
 template <int W>
 static int table_reset_impl(dbg_t *h, uint64_t expected_nodes) {
     typedef Slot<W> S;
-    const uint64_t n_slots = expected_nodes * 2 + 1024;
+    h->region_mode = want_regions(h);
+    h->vb_bits = 0;
+    const uint64_t n_slots = fit_slots(h, expected_nodes * 2 + 1024);
     if (n_slots >= 0xFFFFFFF0ull) return fail(h, DBG_ERR_OVERFLOW, "node table would exceed 2^32 slots");
     h->n_slots = n_slots;
     TRY(reserve(h, h->b_table, n_slots * sizeof(S)));
@@ -1290,7 +1454,7 @@ static int table_reset_impl(dbg_t *h, uint64_t expected_nodes) {
 template <int W>
 static int merge_records_impl(dbg_t *h, const uint64_t *d_records, uint64_t n) {
     if (n == 0) return DBG_OK;
-    LAUNCH(k_rec_merge<W>, blocks_for(n), DBG_BLOCK, h->stream, ptr<Slot<W>>(h->b_table), h->n_slots,
+    LAUNCH(k_rec_merge<W>, blocks_for(n), DBG_BLOCK, h->stream, ptr<Slot<W>>(h->b_table), geom_of(h),
            (const u64 *)d_records, n, ptr<DevCounters>(h->b_ctr));
     CKK();
     TRY(fetch_counters(h));
@@ -1620,7 +1784,7 @@ static int walk_impl(dbg_t *h, int stop_at_branch) {
         } else {
             for (uint64_t i = 0; i < nb; i++) joff[i + 1] = joff[i] + 4;          // 4 slots a node, unused ones say NONE32
             TRY(reserve(h, h->b_junction, nb * 4 * sizeof(JunctionSucc)));
-            LAUNCH(k_junctions<W>, blocks_for(nb), DBG_BLOCK, h->stream, ptr<const S>(h->b_table), n_slots, h->k,
+            LAUNCH(k_junctions<W>, blocks_for(nb), DBG_BLOCK, h->stream, ptr<const S>(h->b_table), geom_of(h), h->k,
                    ptr<const u8>(h->b_flags), ptr<const u16>(h->b_kept), ptr<const u64>(h->b_link),
                    ptr<const u32>(h->b_branch), nb, ptr<JunctionSucc>(h->b_junction), d_ctr);
             CKK();
@@ -1773,7 +1937,7 @@ static int shard_mark_entries_impl(dbg_t *h, const uint64_t *d_keys, uint64_t n)
     TRY(reserve(h, h->b_reqslot, (n + 1) * 4));
     h->n_req = n;
     if (n) {
-        LAUNCH(k_mark_entries<W>, blocks_for(n), DBG_BLOCK, h->stream, ptr<const Slot<W>>(h->b_table), h->n_slots,
+        LAUNCH(k_mark_entries<W>, blocks_for(n), DBG_BLOCK, h->stream, ptr<const Slot<W>>(h->b_table), geom_of(h),
                (const u64 *)d_keys, n, ptr<u8>(h->b_flags), ptr<u32>(h->b_reqslot), ptr<DevCounters>(h->b_ctr));
         CKK();
     }
@@ -2048,6 +2212,13 @@ DBG_API void dbg_destroy(dbg_t *h) {
     delete h;
 }
 
+DBG_API int dbg_set_min_count(dbg_t *h, uint32_t min_count) {
+    if (!h) return DBG_ERR_ARG;
+    if (h->sym_bits != 2 && min_count > 1) return fail(h, DBG_ERR_ARG, "min_count exists for the DNA engine only");
+    h->min_count = min_count < 1 ? 1 : min_count;
+    return DBG_OK;
+}
+
 DBG_API int dbg_set_stream(dbg_t *h, void *cuda_stream) {
     if (!h) return DBG_ERR_ARG;
     h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
@@ -2113,12 +2284,19 @@ static int build_device_common(dbg_t *h, const uint8_t *d_bases, const uint64_t 
                 ((flags & DBG_CHUNKS_ONLY) || h->hint.nodes > 0) &&
                 h->hint.n_batches == h->n_batches && n_bases >= h->hint.n_bases / 2 && n_bases <= h->hint.n_bases + h->hint.n_bases / 2 &&
                 !getenv("DBG_B200_NO_HINT") && !getenv("DBG_B200_CHUNK_SLOTS") && !getenv("DBG_B200_NODE_SLOTS");
+    if (h->min_count > 1) {
+        if (flags & (DBG_TABLE_ONLY | DBG_CHUNKS_ONLY)) return fail(h, DBG_ERR_ARG, "min_count > 1 needs the whole graph stage on one handle");
+        h->hinted = false;                                              // (the filter stage wants a settled table first)
+    }
     h->preinit = false;
-    h->have_hbytes = false;
+    h->have_hbytes = false; h->have_vhash = false; h->have_order = false;
+    h->region_mode = want_regions(h);
+    h->region_slots = 0;
     int rc = DISPATCH(build_impl, h, (const u8 *)d_bases, (const u64 *)d_read_off);
     if (rc != DBG_OK && rc != DBG_RETRY_COLD) return rc;
     const bool stop_early = (flags & (DBG_TABLE_ONLY | DBG_CHUNKS_ONLY)) != 0;
     if (rc == DBG_OK && stop_early) return DBG_OK;
+    if (rc == DBG_OK && h->min_count > 1) rc = DISPATCH(min_count_stage, h);
     if (rc == DBG_OK) rc = DISPATCH(graph_finalize, h);
     if (rc == DBG_RETRY_COLD) {                                       // the remembered sizes did not fit this read set
         h->hint.valid = false;
@@ -2132,7 +2310,7 @@ static int build_device_common(dbg_t *h, const uint8_t *d_bases, const uint64_t 
         CK(cudaMemsetAsync(h->b_ctr.p, 0, sizeof(DevCounters), h->stream));
         h->table_ready = false;
         h->expand_pending = false;
-        h->have_hbytes = false;
+        h->have_hbytes = false; h->have_vhash = false; h->have_order = false;
         if (h->host_bases) CK(cudaStreamSynchronize(h->copy_stream));   // the reads are all in HBM by now: one slice
         const uint8_t *hb = h->host_bases;
         h->host_bases = nullptr;
@@ -2530,7 +2708,7 @@ static int lookup_impl(dbg_t *h, const uint8_t *q, const uint32_t *batch, uint64
         LAUNCH(k_g_lookup_edges, blocks_for(n), DBG_BLOCK, h->stream, ptr<const Slot<2>>(h->b_etable), h->n_eslots, h->k,
                ptr<const u8>(h->b_lut), ptr<const u8>(s[0]), n, ptr<u32>(s[1]));
     else
-    LAUNCH(k_lookup_edges<W>, blocks_for(n), DBG_BLOCK, h->stream, ptr<const Slot<W>>(h->b_table), h->n_slots, h->k,
+    LAUNCH(k_lookup_edges<W>, blocks_for(n), DBG_BLOCK, h->stream, ptr<const Slot<W>>(h->b_table), geom_of(h), h->k,
            ptr<const u8>(s[0]), batch ? ptr<const u32>(s[2]) : (const u32 *)nullptr, n, ptr<u32>(s[1]));
     CKK();
     CK(cudaMemcpyAsync(counts, s[1].p, n * 4, cudaMemcpyDeviceToHost, h->stream));

@@ -125,17 +125,6 @@ struct ChunkCounters {
     u32 pad;
 };
 
-// position of the r-th (0-based) set bit of m; m must have more than r bits set
-DBG_D u32 nth_set_bit(u32 m, u32 r) {
-    u32 pos = 0, c;
-    c = __popc(m & 0xFFFFu); if (r >= c) { r -= c; pos += 16; m >>= 16; }
-    c = __popc(m & 0xFFu);   if (r >= c) { r -= c; pos += 8;  m >>= 8; }
-    c = __popc(m & 0xFu);    if (r >= c) { r -= c; pos += 4;  m >>= 4; }
-    c = __popc(m & 0x3u);    if (r >= c) { r -= c; pos += 2;  m >>= 2; }
-    if (r >= (m & 1u)) pos += 1;
-    return pos;
-}
-
 DBG_D u32 bit_range(u32 lo, u32 hi) { return (~0u >> (31 - hi)) & (~0u << lo); }   // bits lo..hi, 0 <= lo <= hi <= 31
 
 // ---------------------------------------------------------------------------------------------
@@ -554,6 +543,7 @@ template <int W> struct ExpandShared {
     u64 rtag[DBG_WARPS][EX_RCAP];
     u32 rcnt[DBG_WARPS][EX_RCAP];
     u16 rmeta[DBG_WARPS][EX_RCAP];            // probes so far << 3 | has_next << 2 | next base
+    u32 rhome[DBG_WARPS][EX_RCAP];            // home slot
 };
 
 // k bases at base j (< 32) of a chunk string held in registers (2 W words), right-aligned
@@ -589,11 +579,15 @@ DBG_D u32 bytes_in_range(u32 x, u32 lo4, u32 hi4) {
 #ifndef DBG_EXPAND_MIN_BLOCKS
 #define DBG_EXPAND_MIN_BLOCKS 4
 #endif
+#ifndef EX_NP
+#define EX_NP 2                            // MODE 3: slots of the probe sequence read per round
+#endif
+
 template <int W, int MODE>
 __global__ void __launch_bounds__(DBG_BLOCK, DBG_EXPAND_MIN_BLOCKS)
 k_expand(const ChunkSlot<W> *__restrict__ recs_a, u64 n_a, const ChunkSlot<W> *__restrict__ recs_b, u64 n_b, int k,
-         uint4 *__restrict__ hbytes, Slot<W> *table, u32 n_slots, u32 lo8, u32 span8, u32 *regs, int batch_bits,
-         DevCounters *ctr) {
+         uint4 *__restrict__ hbytes, Slot<W> *table, u32 n_slots_, u32 lo8, u32 span8, u32 *regs, int batch_bits,
+         DevCounters *ctr, const u64 *__restrict__ order, const u32 *__restrict__ n_order, TGeom tg) {
     typedef typename KeyOf<W>::type K;
     __shared__ ExpandShared<W> sh;
     const u32 lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -602,38 +596,68 @@ k_expand(const ChunkSlot<W> *__restrict__ recs_a, u64 n_a, const ChunkSlot<W> *_
     const u32 lo4 = lo8 * 0x01010101u, hi4 = (lo8 + span8) * 0x01010101u;
     u32 head = 0, nq = 0;
     bool overflow = false;
+    const u64 n_slots = MODE == 3 ? tg.n_slots : (u64)n_slots_;
 
     // up to 32 * EX_ILP entries at a time: every lane issues the slot loads of all its entries before it
-    // looks at the first one, so EX_ILP random accesses per lane are in flight.  A probe that finds another
-    // key does not loop: the entry goes to the retry ring (shared memory) and comes back in a later drain.
+    // looks at the first one, then the CAS of every entry that met an EMPTY slot before it looks at the first
+    // result, so a round costs two memory round trips whatever EX_ILP is.  With the table laid out by region
+    // (MODE 3) the NEXT slot of the probe sequence is read in the same round trip (same or neighbouring
+    // sector).  A probe that finds other keys does not loop: the entry goes to the retry ring (shared memory)
+    // and comes back in a later drain.
+    constexpr int NP = MODE == 3 ? EX_NP : 1;                                // slots looked at per round
     auto probe_entries = [&](const bool (&act)[EX_ILP], K (&key)[EX_ILP], u64 (&tag)[EX_ILP], u32 (&cnt)[EX_ILP],
-                             u32 (&meta)[EX_ILP]) {
-        Slot<W> *s[EX_ILP]; K cur[EX_ILP]; u64 seen[EX_ILP];
+                             u32 (&meta)[EX_ILP], u32 (&home)[EX_ILP]) {
+        Slot<W> *s[EX_ILP]; K cur[EX_ILP][NP]; u64 seen[EX_ILP][NP];
+        u32 first[EX_ILP];
 #pragma unroll
         for (int i = 0; i < EX_ILP; i++) {
-            u64 idx = slot_home(hash32_key(key[i]), n_slots) + (meta[i] >> 3);
-            if (idx >= n_slots) idx -= n_slots;
-            s[i] = &table[act[i] ? idx : 0];
-            cur[i] = load_key_tag(s[i], &seen[i]);
+            u64 idx = (u64)home[i] + (meta[i] >> 3);
+            if (idx >= n_slots) idx %= n_slots;
+            if (!act[i]) idx = 0;
+            first[i] = (u32)idx;
+#pragma unroll
+            for (int q = 0; q < NP; q++) {
+                u64 iq = idx + q;
+                if (iq >= n_slots) iq -= n_slots;
+                cur[i][q] = load_key_tag(&table[iq], &seen[i][q]);
+            }
+        }
+        int which[EX_ILP];                                               // slot of the round that is, or may become, this key's
+        bool cas[EX_ILP];
+        K old[EX_ILP];
+#pragma unroll
+        for (int i = 0; i < EX_ILP; i++) {
+            which[i] = -1; cas[i] = false;
+#pragma unroll
+            for (int q = NP - 1; q >= 0; q--) {                          // the first slot that holds the key or is EMPTY,
+                bool earlier_other = true;                               // provided every slot before it holds another key
+#pragma unroll
+                for (int p = 0; p < q; p++) earlier_other = earlier_other && cur[i][p] != key[i] && cur[i][p] != empty_key<W>();
+                if (earlier_other && (cur[i][q] == key[i] || cur[i][q] == empty_key<W>())) { which[i] = q; cas[i] = cur[i][q] != key[i]; }
+            }
+            if (!act[i]) { which[i] = -1; cas[i] = false; }
+            u64 it = (u64)first[i] + (which[i] > 0 ? (u32)which[i] : 0u);
+            if (it >= n_slots) it -= n_slots;
+            s[i] = &table[it];
+            old[i] = empty_key<W>();
+            if (cas[i]) old[i] = cas_key(&s[i]->key, empty_key<W>(), key[i]);
         }
 #pragma unroll
         for (int i = 0; i < EX_ILP; i++) {
             bool again = false;
             if (act[i]) {
-                bool hit = true;
-                if (cur[i] != key[i]) {
-                    hit = false;
-                    if (cur[i] == empty_key<W>()) {
-                        const K old = cas_key(&s[i]->key, empty_key<W>(), key[i]);
-                        if (old == empty_key<W>()) { seen[i] = ~0ULL; hit = true; }
-                        else if (old == key[i]) { seen[i] = __ldcg(&s[i]->tag); hit = true; }
-                    }
+                bool hit = which[i] >= 0;
+                u64 sn = which[i] > 0 ? seen[i][NP - 1] : seen[i][0];
+                if (cas[i]) {
+                    if (old[i] == empty_key<W>()) sn = ~0ULL;                     // this probe created the node
+                    else if (old[i] == key[i]) sn = __ldcg(&s[i]->tag);
+                    else hit = false;                                            // somebody else's key got there first
                 }
                 if (hit) {
-                    if (tag[i] < seen[i]) atomicMin(&s[i]->tag, tag[i]);             // first occurrence
+                    if (tag[i] < sn) atomicMin(&s[i]->tag, tag[i]);                  // first occurrence
                     if (meta[i] & 4u) atomicAdd(&s[i]->cnt[meta[i] & 3u], cnt[i]);   // debruijn.py:132/136, x multiplicity
                 } else {
-                    meta[i] += 8u;
+                    meta[i] += 8u * (which[i] >= 0 ? (u32)which[i] + 1u : (u32)NP);  // on past the slots that hold other keys
                     if ((meta[i] >> 3) >= CH_MAX_PROBES) { overflow = true; ctr->overflow = 1; } else again = true;
                 }
             }
@@ -641,6 +665,7 @@ k_expand(const ChunkSlot<W> *__restrict__ recs_a, u64 n_a, const ChunkSlot<W> *_
             if (again) {
                 const u32 o = (head + nq + __popc(mk & lt)) & (EX_RCAP - 1);
                 sh.rkey[w][o] = key[i]; sh.rtag[w][o] = tag[i]; sh.rcnt[w][o] = cnt[i]; sh.rmeta[w][o] = (u16)meta[i];
+                sh.rhome[w][o] = home[i];
             }
             nq += __popc(mk);
         }
@@ -649,33 +674,39 @@ k_expand(const ChunkSlot<W> *__restrict__ recs_a, u64 n_a, const ChunkSlot<W> *_
         __syncwarp();
         const u32 cap = 32u * EX_ILP;
         const u32 take = nq < cap ? nq : cap;
-        bool act[EX_ILP]; K key[EX_ILP]; u64 tag[EX_ILP]; u32 cnt[EX_ILP]; u32 meta[EX_ILP];
+        bool act[EX_ILP]; K key[EX_ILP]; u64 tag[EX_ILP]; u32 cnt[EX_ILP]; u32 meta[EX_ILP]; u32 home[EX_ILP];
 #pragma unroll
         for (int i = 0; i < EX_ILP; i++) {
             const u32 e = (head + 32 * i + lane) & (EX_RCAP - 1);
             act[i] = 32 * i + lane < take;
             key[i] = sh.rkey[w][e]; tag[i] = sh.rtag[w][e]; cnt[i] = sh.rcnt[w][e]; meta[i] = sh.rmeta[w][e];
+            home[i] = sh.rhome[w][e];
         }
         __syncwarp();
         head = (head + take) & (EX_RCAP - 1);
         nq -= take;
-        probe_entries(act, key, tag, cnt, meta);
+        probe_entries(act, key, tag, cnt, meta, home);
     };
 
-    const u64 n_total = n_a + n_b;
+    // MODE 3: the records in region order
+    const u64 n_total = MODE == 3 ? (u64)__ldg(n_order) : n_a + n_b;
     const u64 n_batches = (n_total + 31) / 32;
     const u64 warps_total = (u64)gridDim.x * DBG_WARPS;
     for (u64 b = (u64)blockIdx.x * DBG_WARPS + w; b < n_batches; b += warps_total) {
         // the table is full: the host rebuilds it larger (looked at now and then; the flag is set at once)
         if (MODE != 0 && ((b / warps_total) & 7) == 0 && __any_sync(0xFFFFFFFFu, __ldcg(&ctr->overflow) != 0u)) break;
         const u64 idx = b * 32 + lane;
-        u32 n = 0, B = 0, cnt = 0, m16 = 0, batch = 0;
+        u32 n = 0, B = 0, cnt = 0, m16 = 0, batch = 0, vh = 0;
         u64 tag = 0;
         u64 cw[2 * W];
 #pragma unroll
         for (int i = 0; i < 2 * W; i++) cw[i] = 0;
         if (idx < n_total) {
-            const ChunkSlot<W> *rec = idx < n_a ? recs_a + idx : recs_b + (idx - n_a);
+            u64 oe = 0;
+            if (MODE == 3) oe = __ldg(order + idx);
+            u64 ridx = idx;
+            if (MODE == 3) { ridx = (u32)oe; vh = (u32)(oe >> 32); }
+            const ChunkSlot<W> *rec = ridx < n_a ? recs_a + ridx : recs_b + (ridx - n_a);
             K128 h[W];
 #pragma unroll
             for (int hh = 0; hh < W; hh++) h[hh] = load_k128(&rec->h[hh]);
@@ -690,8 +721,8 @@ k_expand(const ChunkSlot<W> *__restrict__ recs_a, u64 n_a, const ChunkSlot<W> *_
                     m16 = bytes_in_range(hb.x, lo4, hi4) | (bytes_in_range(hb.y, lo4, hi4) << 4) |
                           (bytes_in_range(hb.z, lo4, hi4) << 8) | (bytes_in_range(hb.w, lo4, hi4) << 12);
                 }
-                if (MODE == 2 && span8 >= 254u) m16 = (1u << n) - 1u;   // one pass owns every node
-                if (MODE == 2 || m16) {
+                if ((MODE == 2 && span8 >= 254u) || MODE == 3) m16 = (1u << n) - 1u;   // one pass owns every node
+                if (MODE == 2 || MODE == 3 || m16) {
                     const ulonglong2 tc = __ldcg(reinterpret_cast<const ulonglong2 *>(&rec->tag));   // tag | cnt, pad
                     tag = tc.x;
                     cnt = (u32)tc.y;
@@ -717,7 +748,7 @@ k_expand(const ChunkSlot<W> *__restrict__ recs_a, u64 n_a, const ChunkSlot<W> *_
                 key = key_roll(key, string_base<W>(cw, (u32)(j + k)), mask);
             }
         }
-        if (MODE == 0) {
+        if (MODE == 0) {                                                  // (plain hash layout only)
             K key = key_add_batch(reg_key<W>(cw, 0, k), batch, k);
             u32 nmax = n;
 #pragma unroll
@@ -758,7 +789,7 @@ k_expand(const ChunkSlot<W> *__restrict__ recs_a, u64 n_a, const ChunkSlot<W> *_
             const u32 excl = incl - c;
             const u32 packed = m16 | (B << 16);
             for (u32 base = 0; base < total; base += 32u * EX_ILP) {
-                bool act[EX_ILP]; K key[EX_ILP]; u64 tg[EX_ILP]; u32 cn[EX_ILP]; u32 meta[EX_ILP];
+                bool act[EX_ILP]; K key[EX_ILP]; u64 tg_[EX_ILP]; u32 cn[EX_ILP]; u32 meta[EX_ILP]; u32 home[EX_ILP];
 #pragma unroll
                 for (int i = 0; i < EX_ILP; i++) {
                     const u32 g = base + 32u * i + lane;
@@ -778,16 +809,18 @@ k_expand(const ChunkSlot<W> *__restrict__ recs_a, u64 n_a, const ChunkSlot<W> *_
                     const u64 tag_s = __shfl_sync(0xFFFFFFFFu, tag, src);
                     const u32 cnt_s = __shfl_sync(0xFFFFFFFFu, cnt, src);
                     const u32 batch_s = batch_bits ? __shfl_sync(0xFFFFFFFFu, batch, src) : 0u;
+                    const u32 vh_s = MODE == 3 ? __shfl_sync(0xFFFFFFFFu, vh, src) : 0u;
                     const u32 j = act[i] ? nth_set_bit(pm & 0xFFFFu, g - ex_s) : 0u;
                     const u32 q = j + (u32)k;
                     const bool has_next = q < (pm >> 16);
                     const u32 nb = string_base<W>(cws, q);
                     key[i] = key_add_batch(reg_key<W>(cws, j, k), batch_s, k);
-                    tg[i] = tag_s + j;
+                    tg_[i] = tag_s + j;
                     cn[i] = cnt_s;
                     meta[i] = (has_next ? 4u : 0u) | (has_next ? nb : 0u);
+                    home[i] = MODE == 3 ? (u32)region_home(tg, vh_s, hash32_key(key[i])) : (u32)slot_home(hash32_key(key[i]), n_slots);
                 }
-                probe_entries(act, key, tg, cn, meta);
+                probe_entries(act, key, tg_, cn, meta, home);
                 while (nq >= 32u * EX_ILP) drain();
             }
         }
@@ -795,6 +828,66 @@ k_expand(const ChunkSlot<W> *__restrict__ recs_a, u64 n_a, const ChunkSlot<W> *_
     if (MODE != 0) {
         while (nq) drain();
         if (overflow) ctr->overflow = 1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Region order of the distinct chunks (node table laid out by minimizer, TGeom in dbg_common.cuh).
+//   k_rec_vhash    one thread per record slot (chunk table + boundary list): vhash = node_vhash of the record's
+//                  first node = of all its nodes; histogram over virtual buckets = top vb_bits of vhash (a
+//                  bucketing that does not depend on the node table's size, which is not known yet when the
+//                  sketch runs).  SKETCH also rolls the node key along the string and feeds the HyperLogLog
+//                  sketch of the node keys that sizes the node table.
+//   (exclusive scan of the histogram -> offs[]; offs[2^vb_bits] = number of records)
+//   k_rec_order    order[offs[b] + --hist[b]] = vhash << 32 | record index: the records in bucket order, which
+//                  is region order for ANY region count (region = vhash * n_regions >> 32 is monotone in vhash).
+//                  Any order is correct; this one keeps k_expand's table traffic in L2.
+// ---------------------------------------------------------------------------------------------
+template <int W, bool SKETCH>
+__global__ void __launch_bounds__(DBG_BLOCK) k_rec_vhash(const ChunkSlot<W> *__restrict__ recs_a, u64 n_a,
+                                                         const ChunkSlot<W> *__restrict__ recs_b, u64 n_b, int k, int w,
+                                                         int m, int batch_bits, int vb_bits, u32 *__restrict__ rec_vhash,
+                                                         u32 *vhist, u32 *regs) {
+    typedef typename KeyOf<W>::type K;
+    const u64 n_total = n_a + n_b;
+    const K mask = key_mask<W>(k);
+    for (u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x; idx < n_total; idx += (u64)gridDim.x * blockDim.x) {
+        const ChunkSlot<W> *rec = idx < n_a ? recs_a + idx : recs_b + (idx - n_a);
+        K128 h[W];
+#pragma unroll
+        for (int hh = 0; hh < W; hh++) h[hh] = load_k128(&rec->h[hh]);
+        u32 vh = NONE32;
+        if (h[0] != k128_ones()) {
+            u64 cw[2 * W];
+            chunk_words<W>(h, cw);
+            const u32 batch = batch_bits ? (u32)(h[W - 1].lo >> 8) & (u32)((1ull << batch_bits) - 1) : 0u;
+            K key = key_add_batch(reg_key<W>(cw, 0, k), batch, k);
+            vh = node_vhash(key, k, w, m);
+            if (vh == NONE32) vh = NONE32 - 1;                           // NONE32 marks an empty record slot
+            atomicAdd(&vhist[vh >> (32 - vb_bits)], 1u);
+            if (SKETCH) {
+                const u32 n = meta_nodes((u32)(h[0].lo & 0xFFu));
+                for (u32 j = 0; j < n; j++) {
+                    const u32 hsh = hash32_key(key);
+                    const u32 ri = hsh >> (32 - HLL_P);
+                    const u32 rank = (u32)__clz((int)((hsh << HLL_P) | (1u << (HLL_P - 1)))) + 1;
+                    if (regs[ri] < rank) atomicMax(&regs[ri], rank);
+                    key = key_roll(key, string_base<W>(cw, j + (u32)k), mask);   // garbage past the string: unused then
+                }
+            }
+        }
+        rec_vhash[idx] = vh;
+    }
+}
+
+__global__ void __launch_bounds__(DBG_BLOCK) k_rec_order(const u32 *__restrict__ rec_vhash, u64 n_total, int vb_bits,
+                                                         u32 *vhist, const u32 *__restrict__ offs, u64 *__restrict__ order) {
+    for (u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x; idx < n_total; idx += (u64)gridDim.x * blockDim.x) {
+        const u32 vh = __ldg(rec_vhash + idx);
+        if (vh == NONE32) continue;
+        const u32 b = vh >> (32 - vb_bits);
+        const u32 o = __ldg(offs + b) + (atomicSub(&vhist[b], 1u) - 1u);  // the bucket fills from its end; its count returns to 0
+        order[o] = ((u64)vh << 32) | idx;
     }
 }
 

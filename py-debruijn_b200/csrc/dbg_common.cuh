@@ -105,6 +105,22 @@ template <int W> DBG_HD typename KeyOf<W>::type zero_key();
 template <> DBG_HD u64 zero_key<1>() { return 0; }
 template <> DBG_HD K128 zero_key<2>() { K128 r; r.lo = 0; r.hi = 0; return r; }
 
+// pieces for "shift the k-mer right by one base and put base pb in front" (predecessor key)
+DBG_HD u64 key_and_mask(u64 key, u64 mask) { return key & mask; }
+DBG_HD K128 key_and_mask(K128 key, K128 mask) { K128 r; r.lo = key.lo & mask.lo; r.hi = key.hi & mask.hi; return r; }
+DBG_HD u64 key_andnot_mask(u64 key, u64 mask) { return key & ~mask; }
+DBG_HD K128 key_andnot_mask(K128 key, K128 mask) { K128 r; r.lo = key.lo & ~mask.lo; r.hi = key.hi & ~mask.hi; return r; }
+DBG_HD u64 key_or(u64 a, u64 b) { return a | b; }
+DBG_HD K128 key_or(K128 a, K128 b) { K128 r; r.lo = a.lo | b.lo; r.hi = a.hi | b.hi; return r; }
+DBG_HD u64 key_shr2_put(u64 low, u32 pb, int k) { return (low >> 2) | ((u64)pb << (2 * (k - 1))); }
+DBG_HD K128 key_shr2_put(K128 low, u32 pb, int k) {
+    K128 r;
+    r.lo = (low.lo >> 2) | (low.hi << 62);
+    r.hi = low.hi >> 2;
+    const int sh = 2 * (k - 1);
+    if (sh >= 64) r.hi |= (u64)pb << (sh - 64); else r.lo |= (u64)pb << sh;
+    return r;
+}
 DBG_HD u32 key_last_base(u64 key) { return (u32)(key & 3); }
 DBG_HD u32 key_last_base(K128 key) { return (u32)(key.lo & 3); }
 // base j (0 = first) of a k-mer key
@@ -274,6 +290,111 @@ DBG_D u64 table_find(const Slot<W> *table, u64 n_slots, typename KeyOf<W>::type 
     }
     return NONE64;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Node table laid out by MINIMIZER ("regions").  The table is n_regions x region_slots slots; a node's
+// home slot is  region(minimizer of the node) * region_slots + hash(node) mod region_slots,  then linear
+// probing as before (over the whole table, so a crowded region spills into the next one and nothing else
+// changes).  Every occurrence of a node has the same minimizer, and all nodes of a chunk share theirs, so
+// (1) a chunk's node upserts land inside one region (k_expand walks the chunks in region order: the table
+// is built front to back through L2 instead of by random DRAM sectors), and (2) a node's successor is in
+// the same region unless the minimizer changes between them (1 node in ~8): k_finalize's probes stay local.
+// The minimizer is exactly the one k_masks cuts chunks by: smallest 26-bit multiplicative hash among the
+// node's first w m-mers, leftmost on ties.  n_regions == 1 is the plain hash layout (short minimizers do
+// not spread over regions; the generic-alphabet engine).
+// ---------------------------------------------------------------------------------------------
+struct TGeom {
+    u64 n_slots;
+    u32 n_regions;       // >= 1
+    u32 region_slots;    // n_slots == n_regions * region_slots when n_regions > 1
+    int k, w, m;         // chunk geometry: w candidate m-mers per node
+};
+DBG_HD TGeom plain_geom(u64 n_slots) {
+    TGeom g; g.n_slots = n_slots; g.n_regions = 1; g.region_slots = (u32)n_slots; g.k = 0; g.w = 0; g.m = 0;
+    return g;
+}
+DBG_HD u32 mix32(u32 x) { x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16; return x; }
+
+// the 2 m bits of the m-mer at offset i of a k-mer key (m <= 16)
+DBG_HD u32 key_mmer(u64 key, int k, int m, int i) {
+    return (u32)(key >> (2 * (k - m - i))) & (u32)((1ULL << (2 * m)) - 1);
+}
+DBG_HD u32 key_mmer(K128 key, int k, int m, int i) {
+    const int sh = 2 * (k - m - i);
+    const u64 x = sh >= 64 ? key.hi >> (sh - 64) : (sh ? (key.lo >> sh) | (key.hi << (64 - sh)) : key.lo);
+    return (u32)x & (u32)((1ULL << (2 * m)) - 1);
+}
+// batch id of a batched build: the key bits above the k-mer
+DBG_HD u32 key_batch(u64 key, int k) { return (u32)(key >> (2 * k)); }
+DBG_HD u32 key_batch(K128 key, int k) {
+    const int sh = 2 * k;
+    return (u32)(sh >= 64 ? key.hi >> (sh - 64) : (key.lo >> sh) | (key.hi << (64 - sh)));
+}
+// order of the minimizer candidates: 26-bit multiplicative hash, ties to the leftmost (k_masks, chunk_owner)
+DBG_HD u32 mmer_rank(u32 x, int i) { return ((x * 0x9E3779B1u) | 63u) - (u32)(63 - i); }
+DBG_HD u32 mmer_owner_hash(u32 x, u32 batch) { return hash32_key((u64)x | ((u64)batch << 32)); }
+
+// 32-bit "where in the table" hash of a node: a function of its minimizer (and batch) only; remixed so
+// that it is independent of the multi-GPU owner function, which uses mmer_owner_hash directly
+template <typename K> DBG_HD u32 node_vhash(K key, int k, int w, int m) {
+    u32 best = 0xFFFFFFFFu, best_x = 0;
+    for (int i = 0; i < w; i++) {
+        const u32 x = key_mmer(key, k, m, i);
+        const u32 g = mmer_rank(x, i);
+        if (g < best) { best = g; best_x = x; }
+    }
+    return mix32(mmer_owner_hash(best_x, key_batch(key, k)) ^ 0x5bd1e995u);
+}
+DBG_HD u64 region_home(const TGeom &g, u32 vhash, u32 h) {
+    return (((u64)vhash * g.n_regions) >> 32) * g.region_slots + (((u64)h * g.region_slots) >> 32);
+}
+template <typename K> DBG_HD u64 node_home(const TGeom &g, K key) {
+    const u32 h = hash32_key(key);
+    if (g.n_regions <= 1) return slot_home(h, g.n_slots);
+    return region_home(g, node_vhash(key, g.k, g.w, g.m), h);
+}
+
+template <int W>
+DBG_D u64 table_find(const Slot<W> *table, const TGeom &g, typename KeyOf<W>::type key) {
+    typedef typename KeyOf<W>::type K;
+    const K EMPTY = empty_key<W>();
+    u64 idx = node_home(g, key);
+    for (u32 probes = (u32)g.n_slots; probes; --probes) {        // n_slots < 2^32; a torn (overflowed) table may be full
+        K cur = load_key(&table[idx]);
+        if (cur == key) return idx;
+        if (cur == EMPTY) return NONE64;
+        if (++idx == g.n_slots) idx = 0;
+    }
+    return NONE64;
+}
+template <int W>
+DBG_D u64 table_upsert(Slot<W> *table, const TGeom &g, typename KeyOf<W>::type key) {
+    typedef typename KeyOf<W>::type K;
+    const K EMPTY = empty_key<W>();
+    u64 idx = node_home(g, key);
+    for (u64 probes = 0; probes < g.n_slots; ++probes) {
+        K cur = load_key(&table[idx]);
+        if (cur == key) return idx;
+        if (cur == EMPTY) {
+            K old = cas_key(&table[idx].key, EMPTY, key);
+            if (old == EMPTY || old == key) return idx;
+        }
+        if (++idx == g.n_slots) idx = 0;
+    }
+    return NONE64;
+}
+
+// position of the r-th (0-based) set bit of m; m must have more than r bits set
+DBG_D u32 nth_set_bit(u32 m, u32 r) {
+    u32 pos = 0, c;
+    c = __popc(m & 0xFFFFu); if (r >= c) { r -= c; pos += 16; m >>= 16; }
+    c = __popc(m & 0xFFu);   if (r >= c) { r -= c; pos += 8;  m >>= 8; }
+    c = __popc(m & 0xFu);    if (r >= c) { r -= c; pos += 4;  m >>= 4; }
+    c = __popc(m & 0x3u);    if (r >= c) { r -= c; pos += 2;  m >>= 2; }
+    if (r >= (m & 1u)) pos += 1;
+    return pos;
+}
+
 
 // ---------------------------------------------------------------------------------------------
 // pruningEdges (debruijn.py:150-166) for one node.  cnt[c] = multiplicity of successor base c,

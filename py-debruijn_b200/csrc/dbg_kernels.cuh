@@ -202,41 +202,107 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_table_init(Slot<W> *table, u64 n_
 
 // ---------------------------------------------------------------------------------------------
 // k_finalize: per slot, degrees + pruningEdges + branch flag + the single surviving successor.
+// A warp sweeps FIN_SLOTS slots per step and hands the OCCUPIED ones to its lanes densely (half the slots
+// are empty: one slot per lane left half the lanes idle through the whole body).  The successor is looked
+// for in the node's OWN region first -- it has the same minimizer, hence the same region, unless the
+// minimizer changes between the two (1 node in ~8) or this node was pushed over a region border; a key
+// that is found is the key wherever it is found -- and only what that misses goes to a list that
+// k_finalize_far resolves through the successor's own minimizer (16 hashed m-mers a node).
 // ---------------------------------------------------------------------------------------------
+#define FIN_SLOTS 56
+#define FIN_NEAR_PROBES 6
 template <int W>
-__global__ void __launch_bounds__(DBG_BLOCK) k_finalize(const Slot<W> *__restrict__ table, u64 n_slots, int k,
+__global__ void __launch_bounds__(DBG_BLOCK) k_finalize(const Slot<W> *__restrict__ table, TGeom tg, int k,
                                                         double threshold, u8 *__restrict__ flags,
                                                         u16 *__restrict__ kept, u32 *__restrict__ succ,
-                                                        int sharded, DevCounters *ctr) {
+                                                        int sharded, u32 *__restrict__ far_list, DevCounters *ctr) {
     typedef typename KeyOf<W>::type K;
-    // grid-stride; the five counters are summed in registers and leave the block as ONE atomic each
+    __shared__ u32 s_far[DBG_WARPS][64];                                 // far list, staged per warp: one global atomic per 32 entries
+    u32 n_far = 0;                                                       // (warp-uniform)
+    const u32 wib = threadIdx.x >> 5;
+    // the five counters are summed in registers and leave the block as ONE atomic each
     // (one atomic per warp on the same five words used to serialise in L2)
     u32 c_nodes = 0, c_edges = 0, c_starts = 0, c_branch = 0, c_multi = 0;
+    const u64 n_slots = tg.n_slots;
     const K mask = key_mask<W>(k);
-    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += (u64)gridDim.x * blockDim.x) {
-        u32 f = 0, word = 0, sx = NONE32;
-        K key = table[i].key;
-        if (key != empty_key<W>()) {
-            u32 cnt[4] = { table[i].cnt[0], table[i].cnt[1], table[i].cnt[2], table[i].cnt[3] };
-            u64 tag = table[i].tag;
-            word = prune_successors(cnt, (const u64 *)0, threshold);
-            int nk = kept_count(word), m = distinct_count(word);
-            f = F_OCC | ((u32)tag == 0 ? F_START : 0) | (nk > 1 ? F_BRANCH : 0) |
-                (m == 0 ? F_DEADEND : 0) | (m > 1 ? F_MULTI : 0);
+    const u32 lane = threadIdx.x & 31;
+    const u64 warp0 = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((u64)gridDim.x * blockDim.x) >> 5;
+    for (u64 base = warp0 * FIN_SLOTS; base < n_slots; base += n_warps * FIN_SLOTS) {
+        const u64 i0 = base + lane, i1 = base + 32 + lane;
+        const bool in0 = i0 < n_slots, in1 = lane < FIN_SLOTS - 32 && i1 < n_slots;
+        // (a key whose tag is still ~0 is no node: min_count left no window that touches it)
+        u64 tg0 = 0, tg1 = 0;
+        const bool o0 = in0 && load_key_tag(&table[i0], &tg0) != empty_key<W>() && tg0 != ~0ULL;
+        const bool o1 = in1 && load_key_tag(&table[i1], &tg1) != empty_key<W>() && tg1 != ~0ULL;
+        if (in0 && !o0) { flags[i0] = 0; kept[i0] = 0; succ[i0] = NONE32; }
+        if (in1 && !o1) { flags[i1] = 0; kept[i1] = 0; succ[i1] = NONE32; }
+        const u32 occ0 = __ballot_sync(0xFFFFFFFFu, o0), occ1 = __ballot_sync(0xFFFFFFFFu, o1);
+        const u32 n0 = (u32)__popc(occ0), total = n0 + (u32)__popc(occ1);
+        for (u32 gb = 0; gb < total; gb += 32) {
+          const u32 g = gb + lane;
+          bool far = false;
+          u64 i = 0;
+          if (g < total) {
+            i = g < n0 ? base + nth_set_bit(occ0, g) : base + 32 + nth_set_bit(occ1, g - n0);
+            u64 tag;
+            const K key = load_key_tag(&table[i], &tag);
+            const uint4 c4 = __ldcg(reinterpret_cast<const uint4 *>(&table[i].cnt[0]));
+            const u32 cnt[4] = {c4.x, c4.y, c4.z, c4.w};
+            const u32 word = prune_successors(cnt, (const u64 *)0, threshold);
+            const int nk = kept_count(word), m = distinct_count(word);
+            u32 f = F_OCC | ((u32)tag == 0 ? F_START : 0) | (nk > 1 ? F_BRANCH : 0) |
+                    (m == 0 ? F_DEADEND : 0) | (m > 1 ? F_MULTI : 0);
+            u32 sx = NONE32;
             if (nk == 1) {
-                K sk = key_roll(key, (u32)kept_base(word, 0), mask);
-                u64 fi = table_find<W>(table, n_slots, sk);
-                if (fi == NONE64) {                                  // sharded table: the successor is another rank's node
+                const K sk = key_roll(key, (u32)kept_base(word, 0), mask);
+                const u32 hs = hash32_key(sk);
+                bool found = false, settled = false;
+                u64 idx;
+                if (tg.n_regions > 1) idx = (i / tg.region_slots) * tg.region_slots + (((u64)hs * tg.region_slots) >> 32);
+                else idx = slot_home(hs, n_slots);
+                const u32 limit = tg.n_regions > 1 ? FIN_NEAR_PROBES : (u32)n_slots;
+                for (u32 p = 0; p < limit; p++) {
+                    const K cur = load_key(&table[idx]);
+                    if (cur == sk) { found = true; break; }
+                    if (cur == empty_key<W>()) { settled = tg.n_regions <= 1; break; }   // (own region: the real home may be elsewhere)
+                    if (++idx == n_slots) idx = 0;
+                }
+                if (found) sx = (u32)idx;
+                else if (tg.n_regions > 1 && !settled) far = true;       // not near: resolve through the successor's own minimizer
+                else {                                                 // plain layout: the probe sequence ended at EMPTY (or the table is full)
                     if (sharded) f |= F_EXIT; else raise_fault(ctr, FAULT_SUCC_MISSING, (u32)i);
                 }
-                sx = (u32)fi;
             }
             c_nodes++; c_edges += (u32)m;
             c_starts += (f & F_START) ? 1u : 0u; c_branch += nk > 1 ? 1u : 0u; c_multi += m > 1 ? 1u : 0u;
+            flags[i] = (u8)f;
+            kept[i] = (u16)word;
+            succ[i] = sx;
+          }
+          const u32 fm = __ballot_sync(0xFFFFFFFFu, far);
+          if (fm) {
+              if (far) s_far[wib][n_far + __popc(fm & ((1u << lane) - 1))] = (u32)i;
+              n_far += (u32)__popc(fm);
+              __syncwarp();
+              if (n_far >= 32) {
+                  u64 o = 0;
+                  if (lane == 0) o = atomicAdd(&ctr->n_list_a, 32ULL);
+                  o = __shfl_sync(0xFFFFFFFFu, o, 0);
+                  far_list[o + lane] = s_far[wib][lane];
+                  const u32 rest = s_far[wib][32 + lane];
+                  __syncwarp();
+                  s_far[wib][lane] = rest;
+                  n_far -= 32;
+                  __syncwarp();
+              }
+          }
         }
-        flags[i] = (u8)f;
-        kept[i] = (u16)word;
-        succ[i] = sx;
+    }
+    if (n_far) {
+        u64 o = 0;
+        if (lane == 0) o = atomicAdd(&ctr->n_list_a, (u64)n_far);
+        o = __shfl_sync(0xFFFFFFFFu, o, 0);
+        if (lane < n_far) far_list[o + lane] = s_far[wib][lane];
     }
     __shared__ u32 s_sum[5];
     if (threadIdx.x < 5) s_sum[threadIdx.x] = 0;
@@ -255,6 +321,99 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_finalize(const Slot<W> *__restric
         if (s_sum[2]) atomicAdd(&ctr->n_starts, (u64)s_sum[2]);
         if (s_sum[3]) atomicAdd(&ctr->n_branch, (u64)s_sum[3]);
         if (s_sum[4]) atomicAdd(&ctr->n_multi, (u64)s_sum[4]);
+    }
+}
+
+// the successors k_finalize did not find near their predecessor
+template <int W>
+__global__ void __launch_bounds__(DBG_BLOCK) k_finalize_far(const Slot<W> *__restrict__ table, TGeom tg, int k,
+                                                            const u16 *__restrict__ kept, const u32 *__restrict__ far_list,
+                                                            u8 *flags, u32 *__restrict__ succ, int sharded, DevCounters *ctr) {
+    typedef typename KeyOf<W>::type K;
+    const u64 n = __ldcg(&ctr->n_list_a);
+    const K mask = key_mask<W>(k);
+    for (u64 e = (u64)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (u64)gridDim.x * blockDim.x) {
+        const u32 i = far_list[e];
+        const K sk = key_roll(load_key(&table[i]), (u32)kept_base(kept[i], 0), mask);
+        const u64 fi = table_find<W>(table, tg, sk);
+        if (fi == NONE64) {                                              // sharded table: the successor is another rank's node
+            if (sharded) flags[i] = (u8)(flags[i] | F_EXIT); else raise_fault(ctr, FAULT_SUCC_MISSING, i);
+        }
+        succ[i] = (u32)fi;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// min_count (EXTENSION, no reference line: SURVEY.md section 9 delta 5, BASELINE configs[2]).  The window loop
+// skips every window whose (k+1)-mer occurs fewer than min_count times over all reads (oracle/dbg_oracle.py
+// build()).  The unfiltered table holds exactly those totals, so the filtered graph is made FROM it:
+//   k_mc_filter  zeroes the counters below min_count and forgets every first-occurrence tag
+//   k_mc_retag   re-scans the windows: a surviving window at (read, i) is the first occurrence candidate of
+//                its node (read, i) and of its successor (read, i + 1); nodes no surviving window touches keep
+//                tag ~0 and are no nodes (k_finalize skips them)
+//   k_mc_starts  a node first touched at position i > 0 was created as a successor (the reference's indegree
+//                1) only if window i - 1 of that read survived; otherwise it was created as the source of
+//                window i: indegree 0, a contig start
+// ---------------------------------------------------------------------------------------------
+template <int W>
+__global__ void __launch_bounds__(DBG_BLOCK) k_mc_filter(Slot<W> *table, u64 n_slots, u32 min_count) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += (u64)gridDim.x * blockDim.x) {
+        if (load_key(&table[i]) == empty_key<W>()) continue;
+#pragma unroll
+        for (int c = 0; c < 4; c++) if (table[i].cnt[c] < min_count) table[i].cnt[c] = 0;
+        table[i].tag = ~0ULL;
+    }
+}
+
+template <int W>
+__global__ void __launch_bounds__(DBG_BLOCK) k_mc_retag(const u64 *__restrict__ packed, const u64 *__restrict__ off,
+                                                        const u32 *__restrict__ tile_first, u64 n_bases, int k,
+                                                        Slot<W> *table, TGeom tg, u64 read_idx_base,
+                                                        const u32 *__restrict__ read_batch, DevCounters *ctr) {
+    typedef typename KeyOf<W>::type K;
+    const K mask = key_mask<W>(k);
+    for_windows<W, true>(packed, off, tile_first, n_bases, k,
+        [&](K key, u32 r, u32 pos, bool has_next, u32 nb) {
+            if (!has_next) return;
+            if (read_batch) key = key_add_batch(key, __ldg(read_batch + r), k);
+            const u64 s1 = table_find<W>(table, tg, key);
+            if (s1 == NONE64) { raise_fault(ctr, FAULT_SUCC_MISSING, r); return; }
+            if (__ldcg(&table[s1].cnt[nb]) == 0u) return;                  // the window does not survive
+            const u64 t1 = ((read_idx_base + r) << 32) | pos;
+            if (t1 < __ldcg(&table[s1].tag)) atomicMin(&table[s1].tag, t1);
+            const u64 s2 = table_find<W>(table, tg, key_roll(key, nb, mask));
+            if (s2 == NONE64) { raise_fault(ctr, FAULT_SUCC_MISSING, r); return; }
+            if (t1 + 1 < __ldcg(&table[s2].tag)) atomicMin(&table[s2].tag, t1 + 1);
+        });
+}
+
+template <int W>
+__global__ void __launch_bounds__(DBG_BLOCK) k_mc_starts(const u64 *__restrict__ packed, const u64 *__restrict__ off,
+                                                         const Slot<W> *__restrict__ table, TGeom tg, int k,
+                                                         u64 read_idx_base, u8 *flags, DevCounters *ctr) {
+    typedef typename KeyOf<W>::type K;
+    const K mask = key_mask<W>(k);
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < tg.n_slots; i += (u64)gridDim.x * blockDim.x) {
+        const u32 f = flags[i];
+        if (!(f & F_OCC) || (f & F_START)) continue;
+        const K key = load_key(&table[i]);
+        const u64 tag = table[i].tag;
+        const u64 r = (tag >> 32) - read_idx_base;
+        const u32 pos = (u32)tag;                                        // > 0 (pos == 0 is a start already)
+        const u32 pb = base_at(packed, __ldg(off + r) + pos - 1);
+        // predecessor in that read: previous base + the node's first k - 1 bases (batch bits stay)
+        K pk = key;
+        {
+            // shift right by one base inside the 2k key bits
+            const K low = key_and_mask(key, mask);
+            pk = key_or(key_andnot_mask(key, mask), key_shr2_put(low, pb, k));
+        }
+        const u64 sp = table_find<W>(table, tg, pk);
+        const bool came_in = sp != NONE64 && __ldcg(&table[sp].cnt[key_last_base(key)]) != 0u;
+        if (!came_in) {
+            flags[i] = (u8)(f | F_START);
+            atomicAdd(&ctr->n_starts, 1ULL);
+        }
     }
 }
 
@@ -308,7 +467,7 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_side_fill(const Slot<W> *__restri
 }
 
 template <int W>
-__global__ void __launch_bounds__(DBG_BLOCK) k_order_apply(const Slot<W> *__restrict__ table, u64 n_slots, int k,
+__global__ void __launch_bounds__(DBG_BLOCK) k_order_apply(const Slot<W> *__restrict__ table, TGeom tg, int k,
                                                            double threshold, const SideEntry<W> *__restrict__ ot,
                                                            u64 cap, u16 *__restrict__ kept, u32 *__restrict__ succ,
                                                            u8 *flags, int sharded, DevCounters *ctr) {
@@ -323,7 +482,7 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_order_apply(const Slot<W> *__rest
     kept[i] = (u16)word;
     if (kept_count(word) == 1) {        // threshold < 1: the tie decides WHICH successor survives
         K sk = key_roll(table[i].key, (u32)kept_base(word, 0), key_mask<W>(k));
-        u64 fi = table_find<W>(table, n_slots, sk);
+        u64 fi = table_find<W>(table, tg, sk);
         if (fi == NONE64 && !sharded) raise_fault(ctr, FAULT_SUCC_MISSING, (u32)i);
         succ[i] = (u32)fi;
         if (sharded) flags[i] = (u8)((flags[i] & ~F_EXIT) | (fi == NONE64 ? F_EXIT : 0u));   // only this thread writes slot i
@@ -360,7 +519,7 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_collect(const Slot<W> *__restrict
 // mode 0 counts, mode 1 fills at offs[b].
 // ---------------------------------------------------------------------------------------------
 template <int W>
-__global__ void __launch_bounds__(DBG_BLOCK) k_tip_paths(const Slot<W> *__restrict__ table, u64 n_slots, int k,
+__global__ void __launch_bounds__(DBG_BLOCK) k_tip_paths(const Slot<W> *__restrict__ table, TGeom tg, int k,
                                                          const u8 *__restrict__ flags, const u16 *__restrict__ kept,
                                                          const u32 *__restrict__ branch, u64 n_branch, int mode,
                                                          u32 *__restrict__ counts, const u64 *__restrict__ offs,
@@ -381,7 +540,7 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_tip_paths(const Slot<W> *__restri
         child[d] = ci + 1;
         if (depth == 5) continue;                                   // callee would see depth == 0
         K sk = key_roll(keyv[d], (u32)kept_base(word[d], (int)ci), mask);
-        u64 fi = table_find<W>(table, n_slots, sk);
+        u64 fi = table_find<W>(table, tg, sk);
         if (fi == NONE64) { raise_fault(ctr, FAULT_TIP_MISSING, vec[d]); continue; }
         u32 nx = (u32)fi;
         vec[depth] = nx;
@@ -463,7 +622,7 @@ DBG_HD u32 link_next(u64 l) { return (u32)l; }
 DBG_HD u32 link_dist(u64 l) { return (u32)(l >> 32) & LINK_DIST_MAX; }
 DBG_HD bool link_is_root(u64 l, u32 v) { return l == (u64)v; }
 DBG_HD u32 link_dist_add(u32 a, u32 b) { u64 s = (u64)a + b; return s > LINK_DIST_MAX ? LINK_DIST_MAX : (u32)s; }
-DBG_HD u32 hash32(u32 x) { x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16; return x; }
+DBG_HD u32 hash32(u32 x) { return mix32(x); }
 
 // second sampling level: a splitter whose hash bits 5..9 are zero is a SUPER-splitter (1 in 32)
 DBG_HD bool super_hash(u32 v) { return ((hash32(v) >> WALK_SPLIT_LOG2) & ((1u << WALK_SUPER_LOG2) - 1)) == 0; }
@@ -730,7 +889,7 @@ struct JunctionSucc {
     u32 entry, n_hops, terminal, kind;      // kind as above; n_hops = distance entry -> terminal
 };
 template <int W>
-__global__ void __launch_bounds__(DBG_BLOCK) k_junctions(const Slot<W> *__restrict__ table, u64 n_slots, int k,
+__global__ void __launch_bounds__(DBG_BLOCK) k_junctions(const Slot<W> *__restrict__ table, TGeom tg, int k,
                                                          const u8 *__restrict__ flags, const u16 *__restrict__ kept,
                                                          const u64 *__restrict__ link, const u32 *__restrict__ branch,
                                                          u64 n_branch, JunctionSucc *__restrict__ out, DevCounters *ctr) {
@@ -745,7 +904,7 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_junctions(const Slot<W> *__restri
         js.entry = NONE32; js.n_hops = 0; js.terminal = NONE32; js.kind = T_CYCLE;
         if (j < kept_count(word)) {
             K sk = key_roll(key, (u32)kept_base(word, j), key_mask<W>(k));
-            u64 fi = table_find<W>(table, n_slots, sk);
+            u64 fi = table_find<W>(table, tg, sk);
             if (fi == NONE64) { raise_fault(ctr, FAULT_JUNCTION_MISSING, v); out[b * 4 + j] = js; continue; }
             u32 s = (u32)fi, t = s, d = 0;
             js.entry = s;
@@ -902,7 +1061,7 @@ __global__ void __launch_bounds__(LIFT_BLOCK) k_scores(const Slot<W> *__restrict
 }
 
 template <int W>
-__global__ void __launch_bounds__(DBG_BLOCK) k_lookup_edges(const Slot<W> *__restrict__ table, u64 n_slots, int k,
+__global__ void __launch_bounds__(DBG_BLOCK) k_lookup_edges(const Slot<W> *__restrict__ table, TGeom tg, int k,
                                                             const u8 *__restrict__ q, const u32 *__restrict__ q_batch,
                                                             u64 n, u32 *__restrict__ out) {
     typedef typename KeyOf<W>::type K;
@@ -921,7 +1080,7 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_lookup_edges(const Slot<W> *__res
     u32 res = 0;
     if (!bad) {
         if (q_batch) key = key_add_batch(key, q_batch[i], k);
-        u64 idx = table_find<W>(table, n_slots, key);
+        u64 idx = table_find<W>(table, tg, key);
         if (idx != NONE64) res = table[idx].cnt[code];
     }
     out[i] = res;
@@ -1029,12 +1188,12 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_rec_scatter(const Slot<W> *__rest
 }
 
 template <int W>
-__global__ void __launch_bounds__(DBG_BLOCK) k_rec_merge(Slot<W> *table, u64 n_slots, const u64 *__restrict__ recs, u64 n,
+__global__ void __launch_bounds__(DBG_BLOCK) k_rec_merge(Slot<W> *table, TGeom tg, const u64 *__restrict__ recs, u64 n,
                                                          DevCounters *ctr) {
     u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const u64 *r = recs + i * (W + 3);
-    u64 idx = table_upsert<W>(table, n_slots, key_from_words<W>(r));
+    u64 idx = table_upsert<W>(table, tg, key_from_words<W>(r));
     if (idx == NONE64) { ctr->overflow = 1; return; }
     Slot<W> *s = &table[idx];
     const u64 tag = r[W];

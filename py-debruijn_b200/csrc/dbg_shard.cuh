@@ -99,12 +99,12 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_exit_scatter(const Slot<W> *__res
 
 // ---- entries: received successor keys -> slots of this shard, flagged ----------------------------
 template <int W>
-__global__ void __launch_bounds__(DBG_BLOCK) k_mark_entries(const Slot<W> *__restrict__ table, u64 n_slots,
+__global__ void __launch_bounds__(DBG_BLOCK) k_mark_entries(const Slot<W> *__restrict__ table, TGeom tg,
                                                             const u64 *__restrict__ keys, u64 n, u8 *flags,
                                                             u32 *__restrict__ req_slot, DevCounters *ctr) {
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const u64 idx = table_find<W>(table, n_slots, key_from_words<W>(keys + i * W));
+    const u64 idx = table_find<W>(table, tg, key_from_words<W>(keys + i * W));
     if (idx == NONE64) { raise_fault(ctr, FAULT_SUCC_MISSING, (u32)i); req_slot[i] = NONE32; return; }
     req_slot[i] = (u32)idx;
     // the flag bytes of four slots share a word; several exits may point at one entry

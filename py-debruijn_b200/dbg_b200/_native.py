@@ -40,11 +40,11 @@ class Stats(C.Structure):
         'n_reads', 'n_bases', 'n_windows', 'n_nodes', 'n_edges', 'n_multi', 'n_branch', 'n_starts',
         'n_pulled', 'n_pull_reads', 'n_contigs', 'n_cycle_starts', 'table_slots', 'table_bytes',
         'hll_estimate', 'n_launches', 'n_chunk_instances', 'n_chunk_list', 'chunk_slots')] + [('key_words', C.c_uint32), ('jump_rounds', C.c_uint32), ('n_insert_passes', C.c_uint32),
-                                           ('reserved0', C.c_uint32)] + [
+                                           ('n_regions', C.c_uint32)] + [
         (n, C.c_float) for n in (
             'ms_h2d', 'ms_pack', 'ms_estimate', 'ms_table_init', 'ms_insert', 'ms_finalize',
             'ms_order', 'ms_lists', 'ms_tips', 'ms_pull_reads', 'ms_build_total', 'ms_walk_rank',
-            'ms_walk_emit', 'ms_walk_total', 'ms_chunk_insert', 'ms_expand_sketch', 'ms_expand', 'reserved1')]
+            'ms_walk_emit', 'ms_walk_total', 'ms_chunk_insert', 'ms_expand_sketch', 'ms_expand', 'ms_region_order')]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -74,6 +74,7 @@ SYMBOLS = {
     'dbg_destroy': (None, [_P]),
     'dbg_last_error': (C.c_char_p, [_P]),
     'dbg_set_stream': (C.c_int, [_P, _P]),
+    'dbg_set_min_count': (C.c_int, [_P, C.c_uint32]),
     'dbg_version': (C.c_int, []),
     'dbg_build': (C.c_int, [_P, _P, _P, C.c_uint64, C.c_uint64, C.c_double, C.c_uint32]),
     'dbg_build_device': (C.c_int, [_P, _P, _P, C.c_uint64, C.c_uint64, C.c_uint64, C.c_double, C.c_uint32]),

@@ -118,9 +118,16 @@ class Graph:
             pass
 
     # ---- construct_graph -----------------------------------------------------------------
+    def set_min_count(self, min_count):
+        """EXTENSION (no reference line, include/dbg_b200.h dbg_set_min_count): the following builds skip every
+        window whose (k+1)-mer occurs fewer than `min_count` times over all reads.  1 = the reference."""
+        self.lib.check(self.h, self.lib.dbg_set_min_count(self.h, int(min_count)))
+        return self
+
     def build(self, reads, threshold=3, final=False, exact_order=True, pull_reads=True,
-              packed=None, read_idx_base=0):
+              packed=None, read_idx_base=0, min_count=1):
         """Host entry: `reads` is a list[str] (or pass packed=(uint8 bases, uint64 offsets))."""
+        self.set_min_count(min_count)
         bases, off = packed if packed is not None else pack_reads(reads)
         self.reads = reads
         self.final = bool(final)
@@ -179,8 +186,9 @@ class Graph:
         return self
 
     def build_device(self, d_bases_ptr, d_off_ptr, n_reads, n_bases, threshold=3, final=False,
-                     exact_order=True, pull_reads=True, read_idx_base=0):
+                     exact_order=True, pull_reads=True, read_idx_base=0, min_count=1):
         """Device entry: raw device pointers (e.g. torch tensors' data_ptr()) already in HBM."""
+        self.set_min_count(min_count)
         self.reads = None
         self.final = bool(final)
         self._reset_cache()

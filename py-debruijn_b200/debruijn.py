@@ -37,13 +37,13 @@ def read_reads(fname):
     return reads
 
 
-def _graph_for(reads, k, threshold, final):
+def _graph_for(reads, k, threshold, final, min_count=1):
     """Build on the DNA engine; reads over another alphabet (the reference's real inputs are peptides,
     II_assembleFromReads.py:43-47) go to the generic-alphabet engine with the symbols they use."""
     packed = pack_reads(reads)
     g = Graph(k)
     try:
-        return g.build(reads, threshold=threshold, final=final, packed=packed)
+        return g.build(reads, threshold=threshold, final=final, packed=packed, min_count=min_count)
     except AlphabetError:
         g.close()
     symbols = np.flatnonzero(np.bincount(packed[0], minlength=256)).astype(np.uint8)
@@ -51,12 +51,14 @@ def _graph_for(reads, k, threshold, final):
         raise ValueError('dbg_b200: the reads use %d distinct characters; the GPU path handles alphabets of up to 32'
                          % len(symbols))
     g = Graph(k, alphabet=symbols.tobytes())
-    return g.build(reads, threshold=threshold, final=final, packed=packed)
+    return g.build(reads, threshold=threshold, final=final, packed=packed, min_count=min_count)
 
 
-def construct_graph(reads, k, threshold=3, final=False):
-    """debruijn.py:206-285 on the GPU."""
-    g = _graph_for(reads, k, threshold, final)
+def construct_graph(reads, k, threshold=3, final=False, min_count=1):
+    """debruijn.py:206-285 on the GPU.  `min_count` > 1 is an extension the reference does not have (an absolute
+    abundance filter on the (k+1)-mers before the window loop, dbg_set_min_count in include/dbg_b200.h);
+    the default is the reference."""
+    g = _graph_for(reads, k, threshold, final, min_count)
     st = g.stats()
     print('number of {}mer: '.format(k), st.n_nodes)                      # debruijn.py:224
     print('branch number: ', st.n_branch)                                 # debruijn.py:236
@@ -70,7 +72,7 @@ def construct_graph(reads, k, threshold=3, final=False):
     return (Vertices(g), Edges(g)), pull_out_read, branch_kmer, already_pull_out, EdgeCountTable(g)
 
 
-def construct_graph_batch(batches, k, threshold=3, final=False):
+def construct_graph_batch(batches, k, threshold=3, final=False, min_count=1):
     """construct_graph for MANY independent read lists at once (BASELINE.json configs[3]: one small
     assembly per template, V_FindTemplateGroups.py:152-190): `batches` is a list of read lists and
     the result is a list with, per batch, exactly the tuple construct_graph(batch, k, threshold, final)
@@ -79,10 +81,11 @@ def construct_graph_batch(batches, k, threshold=3, final=False):
     batch_bits = len(batches).bit_length()                              # ids 0 .. n-1 and the all-ones pattern stays free
     g = Graph(k, key_words=2 if 2 * k + batch_bits > 64 else 0)          # 128-bit keys when 64 bits cannot hold both
     try:
+        g.set_min_count(min_count)
         g.build_batched(batches, threshold=threshold, final=final)
     except AlphabetError:                                                # not DNA: one generic-alphabet build per batch
         g.close()
-        return [construct_graph(b, k, threshold, final) for b in batches]
+        return [construct_graph(b, k, threshold, final, min_count) for b in batches]
     flags = g.pull_read_flags().tolist() if (not final and g.stats().n_pull_reads) else None
     out = []
     for b, reads in enumerate(batches):

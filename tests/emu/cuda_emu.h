@@ -207,6 +207,17 @@ template <typename T> static inline uint32_t __match_any_sync(uint32_t mask, T v
     uint32_t r = 0; for (int i = 0; i < 32; i++) if (((m >> i) & 1) && s[i] == raw) r |= 1u << i; return r;
 }
 
+/* reductions over the lanes named in `mask` (REDUX): lanes of different groups may call it together with their own
+   group's mask (cooperative-groups labeled partitions do); the emulator needs the WHOLE warp to make the call. */
+static inline unsigned emu_reduce(uint32_t mask, unsigned v, int op) {
+    uint32_t m; const uint64_t *s = emu::collective(emu_warp_full_mask(), v, &m);
+    unsigned r = op == 0 ? 0u : 0xFFFFFFFFu;
+    for (int i = 0; i < 32; i++) if ((mask >> i) & (m >> i) & 1) { unsigned x = (unsigned)s[i]; r = op == 0 ? r + x : (x < r ? x : r); }
+    return r;
+}
+static inline unsigned __reduce_add_sync(uint32_t mask, unsigned v) { return emu_reduce(mask, v, 0); }
+static inline unsigned __reduce_min_sync(uint32_t mask, unsigned v) { return emu_reduce(mask, v, 1); }
+
 /* ---- atomics (fibers never preempt, so plain code is atomic) ---- */
 template <typename T> static inline T atomicAdd(T *p, T v) { T o = *p; *p = o + v; return o; }
 template <typename T> static inline T atomicSub(T *p, T v) { T o = *p; *p = o - v; return o; }

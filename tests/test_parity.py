@@ -287,6 +287,7 @@ def test_partition_passes(backend, monkeypatch, grid):
     and few blocks so that every warp carries its queues across many tiles."""
     from dbg_b200 import Graph
     monkeypatch.setenv('DBG_B200_L2_REGION_BYTES', '16384')
+    monkeypatch.setenv('DBG_B200_REGIONS', '0')                 # the plain hash layout is the one that needs passes
     monkeypatch.setenv('DBG_B200_SLICE_BYTES', '8192')        # the host reads arrive in many slices
     if grid:
         monkeypatch.setenv('DBG_B200_INSERT_GRID', grid)
@@ -385,6 +386,7 @@ def test_remembered_table_sizes(backend, monkeypatch):
     noisy = [''.join(r.choice('ACGT') for _ in range(150)) for _ in range(len(clean) + 50)]   # all distinct, same size
     _, small = util.synth_reads(53, 900, 150, 42, err=0.01)
     monkeypatch.setenv('DBG_B200_L2_REGION_BYTES', '262144')         # several node-table passes: the self-hashing k_expand
+    monkeypatch.setenv('DBG_B200_REGION_SLOTS', '256')               # (k = 41 lays the table out by minimizer: many small regions)
     for k in (19, 41):
         if k == 41:
             monkeypatch.setenv('DBG_B200_SLICE_BYTES', '16384')       # host reads arrive in slices: phase 1 runs behind the copies
@@ -401,10 +403,46 @@ def test_remembered_table_sizes(backend, monkeypatch):
             assert st.n_windows == sum(max(0, len(x) - k) for x in reads)
             assert [r_ for r_, f in zip(reads, g.pull_read_flags().tolist()) if f] == exp['pull_out_read']
         assert slots[2][1] > 2 * slots[1][1]                          # the remembered sizes did not fit: rebuilt larger
-        assert st.n_insert_passes > 1
+        assert st.n_insert_passes > 1 or st.n_regions > 1
         monkeypatch.setenv('DBG_B200_NO_HINT', '1')
         g.build(clean, threshold=2, final=False)
         g.walk(stop_at_branch=True)
         assert g.contig_strings() == dbg_oracle.snapshot(clean, k, 2, False)['contigs']
         monkeypatch.delenv('DBG_B200_NO_HINT')
+        g.close()
+
+
+@pytest.mark.parametrize('region_slots', ['16', '512'])
+def test_region_layout(backend, monkeypatch, region_slots):
+    """Node table laid out by minimizer (TGeom): forced on for every k, with regions so small that crowded ones
+    spill into their neighbours; every lookup (successor links, tips, junctions, edge counts) goes through the
+    region home of its key.  Same results as the oracle, single build pass."""
+    from dbg_b200 import Graph
+    monkeypatch.setenv('DBG_B200_REGIONS', '1')
+    monkeypatch.setenv('DBG_B200_REGION_SLOTS', region_slots)
+    if region_slots == '16':
+        monkeypatch.setenv('DBG_B200_VB_BITS', '3')                  # 8 buckets of 16: the order array is nearly all spill
+    r = random.Random(4242)
+    n = 0
+    while n < 40:
+        reads, k, thr, final = util.random_dna_case(r, big=(n % 4 == 3))
+        try:
+            exp = dbg_oracle.snapshot(reads, k, thr, final, max_paths=200)
+        except RuntimeError:
+            continue
+        got = util.product_snapshot(reads, k, thr, final)
+        util.assert_same(got, exp, 'region layout case %d: %r' % (n, (reads, k, thr, final)))
+        n += 1
+    _, reads = util.synth_reads(29, 5000, 80, 12, err=0.01)
+    for k in (17, 31, 45):
+        exp = dbg_oracle.snapshot(reads, k, 2, False)
+        got = util.product_snapshot(reads, k, 2, False)
+        util.assert_same(got, exp, 'region layout k=%d' % k)
+        g = Graph(k)
+        g.build(reads, threshold=2)
+        st = g.stats()
+        assert st.n_regions > 8 and st.n_insert_passes == 1
+        ect = dict(map(tuple, exp['ect']))
+        qs = list(ect)[:50] + ['A' * (k + 1)]
+        assert g.lookup_edges(qs).tolist() == [ect.get(q, 0) for q in qs]
         g.close()

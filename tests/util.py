@@ -20,12 +20,13 @@ def is_dna(reads):
     return all(set(r) <= set('ACGT') for r in reads)
 
 
-def product_snapshot(reads, k, threshold, final):
+def product_snapshot(reads, k, threshold, final, min_count=1):
     """Run the product's drop-in module exactly as II_assembleFromReads.py:58-63 does."""
     import debruijn as db
     buf = io.StringIO()
     with contextlib.redirect_stdout(buf):
-        g, pull, branch, pulled, ect = db.construct_graph(list(reads), k, threshold=threshold, final=final)
+        kw = {'min_count': min_count} if min_count != 1 else {}
+        g, pull, branch, pulled, ect = db.construct_graph(list(reads), k, threshold=threshold, final=final, **kw)
         contigs = db.output_contigs(g, branch, pulled)
     V, E = g
     return {

@@ -1,0 +1,16 @@
+python -m pytest tests -m gpu -x -q -k "region_layout or kat2 or random_vs or c2_full or c3_full or batched_full or undersized or remembered" > gpurun_out/r2m_pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/r2m_pytest_gpu.log
+B="python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-extras"
+run() { name=$1; shift; e=(); a=(); for x in "$@"; do if [[ "$x" == *=* ]]; then e+=("$x"); else a+=("$x"); fi; done; env "${e[@]}" $B "${a[@]}" 2>gpurun_out/r2m_err_$name.log | python -c "
+import json,sys
+p=json.loads([l for l in sys.stdin if l.startswith('{')][-1]); s=p['stage_ms']
+print('$name', 'step %.3f e2e %.3f table %.3f frac %.3f | pack %.3f est %.3f cins %.3f sk %.3f exp %.3f init %.3f fin %.3f lists %.3f walk %.3f passes %d cslots %d launches %d' % (p['ms_per_step'], p['e2e']['ms_per_step'], p['roofline']['kernel_ms'], p['roofline']['frac'], s['ms_pack'], s['ms_estimate'], s['ms_chunk_insert'], s['ms_expand_sketch'], s['ms_expand'], s['ms_table_init'], s['ms_finalize'], s['ms_lists'], s['ms_walk_total'], p['graph']['insert_passes'], p['graph']['chunk_slots_rank0'], p['gpu_launches_per_step']), s.get('ms_region_order'))
+"; }
+{
+run hinted A=1
+run nohint DBG_B200_NO_HINT=1
+run plain_hinted DBG_B200_REGIONS=0
+run c3_hinted A=1 --config c3
+run c3_nohint DBG_B200_NO_HINT=1 --config c3
+run c5s_hinted A=1 --config c5s
+run c4_hinted A=1 --config c4
+} 2>&1 | tee gpurun_out/r2m_runs.log
