@@ -236,6 +236,9 @@ def static_config(args, cfg, world):
     return {'workload': wl, 'config_key': args.config, 'k': cfg['k'], 'threshold': cfg['thr'],
             'genome_bp': cfg['G'] * world, 'read_len': cfg['L'], 'coverage': cfg['cov'], 'error_rate': cfg['err'],
             'final': False,
+            'min_count': getattr(args, 'min_count', 1),
+            'min_count_note': None if getattr(args, 'min_count', 1) <= 1 else
+            'EXTENSION without a reference oracle (SURVEY.md section 9 delta 5): pinned by the two restatements only',
             'parallelism': 'single GPU' if world == 1 else
             ('templates sharded x%d by batch id, no collective (independent graphs)' % world) if batched else
             ('reads sharded x%d; distinct chunks hash-partitioned by minimizer owner, ONE NCCL all-to-all; degrees / '
@@ -549,7 +552,8 @@ def run_dbg(args, cfg, rank, local_rank, world):
             last['res'] = ddist.build_sharded(g, None, read_base, threshold=thr, final=False, stats=ex_stats,
                                               local_device=(d_bases.data_ptr(), d_off.data_ptr(), n_reads, n_bases))
         else:
-            g.build_device(d_bases.data_ptr(), d_off.data_ptr(), n_reads, n_bases, threshold=thr, final=False)
+            g.build_device(d_bases.data_ptr(), d_off.data_ptr(), n_reads, n_bases, threshold=thr, final=False,
+                           min_count=args.min_count)
             g.walk(stop_at_branch=True)
 
     def step_host():
@@ -559,7 +563,7 @@ def run_dbg(args, cfg, rank, local_rank, world):
         elif sharded:
             last['res'] = ddist.build_sharded(g, (hb_np, ho_np), read_base, threshold=thr, final=False)
         else:
-            g.build(None, threshold=thr, final=False, packed=(hb_np, ho_np))
+            g.build(None, threshold=thr, final=False, packed=(hb_np, ho_np), min_count=args.min_count)
             g.walk(stop_at_branch=True)
 
     for _ in range(max(args.warmup, 3)):
@@ -717,9 +721,9 @@ def run_dbg(args, cfg, rank, local_rank, world):
         # parity at N = 1: the product's result of the timed workload against the C oracle, row by row
         from oracle import c_oracle, compare
         g.shard_config(0, 0)
-        g.build(None, threshold=thr, final=False, packed=(bases, off))
+        g.build(None, threshold=thr, final=False, packed=(bases, off), min_count=args.min_count)
         g.walk(stop_at_branch=True)
-        res = c_oracle.run(None, k, thr, False, strings=False, packed=(bases.tobytes(), off))
+        res = c_oracle.run(None, k, thr, False, strings=False, packed=(bases.tobytes(), off), min_count=args.min_count)
         rows = []
         bad = compare.compare_with_oracle(g, res, False, report=lambda name, ok: rows.append(name))
         line['parity'] = {'against': 'C oracle (oracle/dbg_oracle.c) on the FULL workload of this run',
@@ -742,6 +746,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--cpu-sample-bp', type=int, default=42_000)     # ~10 s of pure-Python work (the walk is super-linear)
     ap.add_argument('--ref-sample-bp', type=int, default=0)          # --impl reference: 0 = the full N=1 workload per step
+    ap.add_argument('--min-count', type=int, default=1)              # EXTENSION (no reference oracle): abundance filter, configs[2] (ii)
     ap.add_argument('--no-extras', action='store_true')              # skip strong_c5 / c4_batched / e2e_api
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))

@@ -319,7 +319,8 @@ static int collect_sorted(dbg_t *h, u32 want, uint64_t expect, DevBuf &out, u64 
            ptr<const u8>(h->b_flags), want, ptr<u64>(h->b_tag), ptr<u32>(h->b_slot), cursor);
     CKK();
     // a start's first occurrence is at position 0 of its read: only the read-index half of the tag orders starts
-    return sort_by_tag(h, expect, ptr<u32>(out), want == F_START ? 32 : 0);
+    // (not under min_count: a node whose incoming window was filtered away starts a contig at any position)
+    return sort_by_tag(h, expect, ptr<u32>(out), want == F_START && h->min_count <= 1 ? 32 : 0);
 }
 
 // side set (dbg_kernels.cuh) of the slots whose flags hit `want`: entries in b_order, bitmap in b_bitmap
@@ -1097,9 +1098,12 @@ static int min_count_stage(dbg_t *h) {
     if (grid > 148 * 16) grid = 148 * 16;
     LAUNCH(k_mc_filter<W>, grid, DBG_BLOCK, h->stream, ptr<S>(h->b_table), h->n_slots, h->min_count);
     CKK();
-    LAUNCH(k_mc_retag<W>, h->n_tiles, DBG_BLOCK, h->stream, ptr<const u64>(h->b_packed), (const u64 *)h->d_off,
-           ptr<const u32>(h->b_tile), h->n_bases, h->k, ptr<S>(h->b_table), geom_of(h), h->read_idx_base,
-           (const u32 *)h->d_read_batch, ptr<DevCounters>(h->b_ctr));
+    if (!h->chunks_valid || h->chunks_merged) return fail(h, DBG_ERR_STATE, "min_count needs the chunks of this build");
+    uint64_t rgrid = blocks_for(h->n_cslots + h->n_clist);
+    if (rgrid > 148 * 16) rgrid = 148 * 16;
+    LAUNCH(k_mc_retag<W>, rgrid, DBG_BLOCK, h->stream, ptr<const ChunkSlot<W>>(h->b_ctable), h->n_cslots,
+           ptr<const ChunkSlot<W>>(h->b_clist), h->n_clist, h->k, h->batch_bits, ptr<S>(h->b_table), geom_of(h),
+           ptr<DevCounters>(h->b_ctr));
     CKK();
     return DBG_OK;
 }

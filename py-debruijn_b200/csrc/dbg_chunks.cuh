@@ -936,6 +936,50 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_order_chunks(const ChunkSlot<W> *
     }
 }
 
+// min_count (extension, see k_mc_filter in dbg_kernels.cuh): first-occurrence tags of the nodes that surviving
+// windows touch, from the distinct chunks.  The counters in the table are already filtered (0 = the window's
+// (k+1)-mer was too rare).
+template <int W>
+__global__ void __launch_bounds__(DBG_BLOCK) k_mc_retag(const ChunkSlot<W> *__restrict__ recs_a, u64 n_a,
+                                                        const ChunkSlot<W> *__restrict__ recs_b, u64 n_b, int k,
+                                                        int batch_bits, Slot<W> *table, TGeom tg, DevCounters *ctr) {
+    typedef typename KeyOf<W>::type K;
+    const u64 n_total = n_a + n_b;
+    const K mask = key_mask<W>(k);
+    for (u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x; idx < n_total; idx += (u64)gridDim.x * blockDim.x) {
+        const ChunkSlot<W> *rec = idx < n_a ? recs_a + idx : recs_b + (idx - n_a);
+        K128 h[W];
+#pragma unroll
+        for (int hh = 0; hh < W; hh++) h[hh] = load_k128(&rec->h[hh]);
+        if (h[0] == k128_ones()) continue;
+        const u32 meta = (u32)(h[0].lo & 0xFFu);
+        const u32 n = meta_nodes(meta), B = n + (u32)k - meta_term(meta);
+        u64 cw[2 * W];
+        chunk_words<W>(h, cw);
+        const u32 batch = batch_bits ? (u32)(h[W - 1].lo >> 8) & (u32)((1ull << batch_bits) - 1) : 0u;
+        const u64 tag = __ldcg(&rec->tag);
+        K key = key_add_batch(reg_key<W>(cw, 0, k), batch, k);
+        bool touched = false;                                            // the window before this node survived
+        for (u32 j = 0; j < n; j++) {
+            const u32 q = j + (u32)k;
+            const bool has_next = q < B;                                 // (the last node of a read: no window)
+            const u32 nb = has_next ? string_base<W>(cw, q) : 0u;
+            const u64 s = table_find<W>(table, tg, key);
+            if (s == NONE64) { raise_fault(ctr, FAULT_SUCC_MISSING, (u32)idx); break; }
+            const bool alive = has_next && __ldcg(&table[s].cnt[nb]) != 0u;
+            if ((alive || touched) && tag + j < __ldcg(&table[s].tag)) atomicMin(&table[s].tag, tag + j);
+            touched = alive;
+            if (!has_next) break;
+            key = key_roll(key, nb, mask);
+        }
+        if (touched) {                                                   // the successor of the chunk's last node: another chunk's node
+            const u64 s = table_find<W>(table, tg, key);
+            if (s == NONE64) raise_fault(ctr, FAULT_SUCC_MISSING, (u32)idx);
+            else if (tag + n < __ldcg(&table[s].tag)) atomicMin(&table[s].tag, tag + n);
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Chunk records: the unit of the multi-GPU exchange when it happens BEFORE any node table exists.
 // A rank's window loop leaves its distinct chunks {string | min tag | multiplicity} (chunk table + the

@@ -348,9 +348,10 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_finalize_far(const Slot<W> *__res
 // skips every window whose (k+1)-mer occurs fewer than min_count times over all reads (oracle/dbg_oracle.py
 // build()).  The unfiltered table holds exactly those totals, so the filtered graph is made FROM it:
 //   k_mc_filter  zeroes the counters below min_count and forgets every first-occurrence tag
-//   k_mc_retag   re-scans the windows: a surviving window at (read, i) is the first occurrence candidate of
-//                its node (read, i) and of its successor (read, i + 1); nodes no surviving window touches keep
-//                tag ~0 and are no nodes (k_finalize skips them)
+//   k_mc_retag   (dbg_chunks.cuh) walks the DISTINCT chunks: a surviving window at offset j of a chunk tagged
+//                (read, pos) is the first-occurrence candidate (read, pos + j) of its node and (read, pos + j + 1)
+//                of its successor -- the chunk's tag is the minimum over its instances, which all hold the same
+//                windows; nodes no surviving window touches keep tag ~0 and are no nodes (k_finalize skips them)
 //   k_mc_starts  a node first touched at position i > 0 was created as a successor (the reference's indegree
 //                1) only if window i - 1 of that read survived; otherwise it was created as the source of
 //                window i: indegree 0, a contig start
@@ -363,28 +364,6 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_mc_filter(Slot<W> *table, u64 n_s
         for (int c = 0; c < 4; c++) if (table[i].cnt[c] < min_count) table[i].cnt[c] = 0;
         table[i].tag = ~0ULL;
     }
-}
-
-template <int W>
-__global__ void __launch_bounds__(DBG_BLOCK) k_mc_retag(const u64 *__restrict__ packed, const u64 *__restrict__ off,
-                                                        const u32 *__restrict__ tile_first, u64 n_bases, int k,
-                                                        Slot<W> *table, TGeom tg, u64 read_idx_base,
-                                                        const u32 *__restrict__ read_batch, DevCounters *ctr) {
-    typedef typename KeyOf<W>::type K;
-    const K mask = key_mask<W>(k);
-    for_windows<W, true>(packed, off, tile_first, n_bases, k,
-        [&](K key, u32 r, u32 pos, bool has_next, u32 nb) {
-            if (!has_next) return;
-            if (read_batch) key = key_add_batch(key, __ldg(read_batch + r), k);
-            const u64 s1 = table_find<W>(table, tg, key);
-            if (s1 == NONE64) { raise_fault(ctr, FAULT_SUCC_MISSING, r); return; }
-            if (__ldcg(&table[s1].cnt[nb]) == 0u) return;                  // the window does not survive
-            const u64 t1 = ((read_idx_base + r) << 32) | pos;
-            if (t1 < __ldcg(&table[s1].tag)) atomicMin(&table[s1].tag, t1);
-            const u64 s2 = table_find<W>(table, tg, key_roll(key, nb, mask));
-            if (s2 == NONE64) { raise_fault(ctr, FAULT_SUCC_MISSING, r); return; }
-            if (t1 + 1 < __ldcg(&table[s2].tag)) atomicMin(&table[s2].tag, t1 + 1);
-        });
 }
 
 template <int W>
