@@ -584,6 +584,25 @@ def run_dbg(args, cfg, rank, local_rank, world):
     mode = last['res'].mode if sharded else ('batched' if batched else 'single')
     n_contigs_local = len(last['res'].contigs) if sharded and last['res'].mode == 'sharded' else int(st.n_contigs)
     totals = last['res'].totals if sharded else None
+    # the same step with the handle's remembered table sizes switched off (every build sketches its tables first,
+    # as the very first build on a handle does): reported beside the headline, never instead of it
+    cold = None
+    if not sharded and not batched:
+        os.environ['DBG_B200_NO_HINT'] = '1'
+        try:
+            step_device()
+            cstage = {}
+
+            def ccollect():
+                st_ = g.stats()
+                for f in STAGE_FIELDS:
+                    cstage[f] = cstage.get(f, 0.0) + getattr(st_, f) / min(args.steps, 10)
+            ms_cold = R.timed(step_device, min(args.steps, 10), ccollect) / min(args.steps, 10)
+            cold = {'ms_per_step': ms_cold, 'value': nwin / (ms_cold * 1e-3),
+                    'table_build_ms': cstage['ms_pack'] + cstage['ms_estimate'] + cstage['ms_insert']}
+        finally:
+            del os.environ['DBG_B200_NO_HINT']
+        step_device()
     for _ in range(2):
         step_host()
     ms_e2e = R.timed(step_host, args.steps)
@@ -686,6 +705,13 @@ def run_dbg(args, cfg, rank, local_rank, world):
                 'ms_h2d': h2d_stage,
                 'api': 'dbg_build (host pointers, pinned) + dbg_walk + dbg_contigs' if not sharded else
                        'dist.build_sharded over dbg_build(DBG_CHUNKS_ONLY, host pointers, pinned) ... dbg_shard_walk + dbg_shard_contigs'},
+        'table_sizing': {
+            'timed_steps': 'chunk and node table sized from the previous build on the same handle (grow-only buffers '
+                           'remember their fill; checked after the build, redone with sketches when it does not fit)',
+            'cold': None if cold is None else dict(
+                cold, roofline_frac=nwin * b_build / (cold['table_build_ms'] * 1e-3) / 1e9 / peak,
+                note='every build sizes its tables from HyperLogLog sketches first (DBG_B200_NO_HINT=1), as the first '
+                     'build on a handle does')},
         'gpu_launches': launches * args.steps,
         'gpu_launches_per_step': launches,
         'clocks': clocks,

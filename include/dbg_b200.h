@@ -127,6 +127,15 @@ void dbg_destroy(dbg_t *h);
 const char *dbg_last_error(const dbg_t *h);          /* h may be NULL: error of a failed create */
 int  dbg_set_stream(dbg_t *h, void *cuda_stream);    /* cudaStream_t; NULL = handle's own stream */
 int  dbg_version(void);
+/* findSupportReadScore of IV_sortOutputs.py:10-15 for MANY contigs: out_scores[c] = sum, in read order and in
+ * float64 (the reference's left-to-right `score +=`), of read_score[r] over the reads r that are substrings of
+ * contig c (a read that occurs more than once counts once, as `read in contig` does; an empty read is in every
+ * contig).  reads = the keys of the reference's score_table in dict order, concatenated bytes + n_reads + 1
+ * offsets; contigs likewise; all HOST pointers.  Any alphabet; the handle only lends its device, stream and
+ * scratch memory (its k does not matter).                                                                  */
+int  dbg_support_scores(dbg_t *h, const uint8_t *reads, const uint64_t *read_off, uint64_t n_reads,
+                        const double *read_score, const uint8_t *contigs, const uint64_t *contig_off,
+                        uint64_t n_contigs, double *out_scores);
 /* EXTENSION without a reference line (SURVEY.md section 9 delta 5; BASELINE.json configs[2] "abundance filter
  * min-count=2"): the following builds on this handle skip every window whose (k+1)-mer occurs fewer than
  * min_count times over all reads, as if `if total[read[i:i+k+1]] < min_count: continue` stood at the top of the

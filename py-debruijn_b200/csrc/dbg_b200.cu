@@ -44,6 +44,7 @@
 #include "dbg_chunks.cuh"
 #include "dbg_shard.cuh"
 #include "dbg_generic.cuh"
+#include "dbg_support.cuh"
 
 #define DBG_ABI_VERSION 1
 #define DBG_RETRY_COLD 1                      // internal: a build sized from the handle's hint did not fit; redo it cold
@@ -960,7 +961,7 @@ static int build_impl(dbg_t *h, const u8 *d_bases, const u64 *d_off) {
         // read has none: reads of length <= k, or one chunk that is both)
         const uint64_t list_cap = 2 * h->n_reads + 2;
         TRY(reserve(h, h->b_clist, list_cap * sizeof(ChunkSlot<W>)));
-        CK(cudaMemsetAsync(h->b_clist.p, 0xFF, list_cap * sizeof(ChunkSlot<W>), h->stream));
+        bool list_cleared = false;
         h->n_cslots = 0;
         h->chunks_streamed = false;
         if (h->hinted) {
@@ -983,6 +984,8 @@ static int build_impl(dbg_t *h, const u8 *d_bases, const u64 *d_off) {
                 // both tables are cleared on the side stream while the reads are packed and masked
                 CK(cudaEventRecord(h->ev_init[0], h->stream));
                 CK(cudaStreamWaitEvent(h->init_stream, h->ev_init[0], 0));
+                CK(cudaMemsetAsync(h->b_clist.p, 0xFF, list_cap * sizeof(ChunkSlot<W>), h->init_stream));   // (k_chunk_insert waits for ev_init[1])
+                list_cleared = true;
                 int sms_ = 148;
                 cudaDeviceGetAttribute(&sms_, cudaDevAttrMultiProcessorCount, h->device);
                 const uint64_t bg = (uint64_t)sms_ * 2;                   // background grid: two blocks an SM
@@ -996,6 +999,7 @@ static int build_impl(dbg_t *h, const u8 *d_bases, const u64 *d_off) {
                 h->preinit = !chunks_only;
             }
         }
+        if (!list_cleared) CK(cudaMemsetAsync(h->b_clist.p, 0xFF, list_cap * sizeof(ChunkSlot<W>), h->stream));
     }
     if (h->n_reads) {
         uint64_t rs_grid = blocks_for(h->n_reads);
@@ -2214,6 +2218,114 @@ DBG_API void dbg_destroy(dbg_t *h) {
     if (h->ctl) cudaFreeHost(h->ctl);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
+}
+
+// findSupportReadScore (IV_sortOutputs.py:10-15) for many contigs at once; kernels in dbg_support.cuh
+DBG_API int dbg_support_scores(dbg_t *h, const uint8_t *reads, const uint64_t *read_off, uint64_t n_reads,
+                               const double *read_score, const uint8_t *contigs, const uint64_t *contig_off,
+                               uint64_t n_contigs, double *out_scores) {
+    if (!h || !read_off || !contig_off || (n_contigs && !out_scores)) return h ? fail(h, DBG_ERR_ARG, "null argument") : DBG_ERR_ARG;
+    cudaSetDevice(h->device);
+    if (n_contigs == 0) return DBG_OK;
+    const uint64_t rbytes = read_off[n_reads], cbytes = contig_off[n_contigs];
+    if (n_reads >= 0xFFFFFFF0ull || n_contigs >= 0xFFFFFFF0ull) return fail(h, DBG_ERR_OVERFLOW, "more than 2^32 reads or contigs");
+    // distinct non-empty read lengths, ascending, with BASE^len
+    std::vector<u32> lens;
+    uint64_t n_empty = 0;
+    for (uint64_t r = 0; r < n_reads; r++) {
+        const uint64_t l = read_off[r + 1] - read_off[r];
+        if (l > 0xFFFFFFFFull) return fail(h, DBG_ERR_OVERFLOW, "a read is longer than 2^32-1");
+        if (l == 0) n_empty++; else lens.push_back((u32)l);
+    }
+    std::sort(lens.begin(), lens.end());
+    lens.erase(std::unique(lens.begin(), lens.end()), lens.end());
+    std::vector<u64> pows(lens.size());
+    for (size_t i = 0; i < lens.size(); i++) { u64 p = 1; for (u32 j = 0; j < lens[i]; j++) p *= SUP_BASE; pows[i] = p; }
+    double empty_sum = 0.0;                                              // '' in contig is always True (handled in read order below)
+    (void)empty_sum;
+    const uint64_t cap = 2 * n_reads + 16;
+    DevBuf &b_r = h->b_scratch[0], &b_c = h->b_scratch[1], &b_off = h->b_scratch[2], &b_tab = h->b_scratch[3],
+           &b_pre = h->b_scratch[4], &b_misc = h->b_scratch[5];
+    TRY(reserve(h, b_r, rbytes + 16));
+    TRY(reserve(h, b_c, cbytes + 16));
+    TRY(reserve(h, b_off, (n_reads + n_contigs + 2) * 8));
+    TRY(reserve(h, b_tab, cap * sizeof(SupSlot)));
+    TRY(reserve(h, b_pre, (cbytes + n_contigs + 1) * 8));
+    // misc: lens (u32, padded to 8) | pows | scores | out | cursor
+    const size_t o_lens = 0, o_pows = ((lens.size() * 4 + 7) / 8) * 8, o_sc = o_pows + pows.size() * 8,
+                 o_out = o_sc + n_reads * 8, o_cur = o_out + n_contigs * 8;
+    TRY(reserve(h, b_misc, o_cur + 16));
+    char *misc = (char *)b_misc.p;
+    u64 *d_roff = ptr<u64>(b_off), *d_coff = ptr<u64>(b_off) + n_reads + 1;
+    if (rbytes) CK(cudaMemcpyAsync(b_r.p, reads, rbytes, cudaMemcpyHostToDevice, h->stream));
+    if (cbytes) CK(cudaMemcpyAsync(b_c.p, contigs, cbytes, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(d_roff, read_off, (n_reads + 1) * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(d_coff, contig_off, (n_contigs + 1) * 8, cudaMemcpyHostToDevice, h->stream));
+    if (!lens.empty()) {
+        CK(cudaMemcpyAsync(misc + o_lens, lens.data(), lens.size() * 4, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(misc + o_pows, pows.data(), pows.size() * 8, cudaMemcpyHostToDevice, h->stream));
+    }
+    if (n_reads) CK(cudaMemcpyAsync(misc + o_sc, read_score, n_reads * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemsetAsync(b_tab.p, 0xFF, cap * sizeof(SupSlot), h->stream));
+    CK(cudaMemsetAsync(misc + o_cur, 0, 8, h->stream));
+    if (n_reads) {
+        LAUNCH(k_sup_reads, blocks_for(n_reads), DBG_BLOCK, h->stream, ptr<const u8>(b_r), (const u64 *)d_roff, n_reads,
+               ptr<SupSlot>(b_tab), cap);
+        CKK();
+    }
+    LAUNCH(k_sup_prefix, blocks_for(n_contigs), DBG_BLOCK, h->stream, ptr<const u8>(b_c), (const u64 *)d_coff, n_contigs,
+           ptr<u64>(b_pre));
+    CKK();
+    uint64_t n_hits = 0;
+    DevBuf &b_hits = h->b_tag, &b_hits2 = h->b_tag2;
+    if (cbytes && !lens.empty()) {
+        LAUNCH(k_sup_match, blocks_for(cbytes), DBG_BLOCK, h->stream, ptr<const u8>(b_c), (const u64 *)d_coff, n_contigs,
+               ptr<const u64>(b_pre), ptr<const u8>(b_r), (const u64 *)d_roff, ptr<const SupSlot>(b_tab), cap,
+               (const u32 *)(misc + o_lens), (const u64 *)(misc + o_pows), (u32)lens.size(), 0, (u64 *)(misc + o_cur),
+               (u64 *)nullptr, (u64)0);
+        CKK();
+        CK(cudaMemcpyAsync(&n_hits, misc + o_cur, 8, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    // reads of length 0 are in every contig (`'' in contig`): one hit per (contig, empty read), made on the host side
+    // of the list so that they take their place in read order
+    std::vector<u64> empty_hits;
+    if (n_empty)
+        for (uint64_t c = 0; c < n_contigs; c++)
+            for (uint64_t r = 0; r < n_reads; r++)
+                if (read_off[r + 1] == read_off[r]) empty_hits.push_back((c << 32) | r);
+    const uint64_t n_all = n_hits + empty_hits.size();
+    TRY(reserve(h, b_hits, (n_all + 1) * 8));
+    TRY(reserve(h, b_hits2, (n_all + 1) * 8));
+    if (n_hits) {
+        CK(cudaMemsetAsync(misc + o_cur, 0, 8, h->stream));
+        LAUNCH(k_sup_match, blocks_for(cbytes), DBG_BLOCK, h->stream, ptr<const u8>(b_c), (const u64 *)d_coff, n_contigs,
+               ptr<const u64>(b_pre), ptr<const u8>(b_r), (const u64 *)d_roff, ptr<const SupSlot>(b_tab), cap,
+               (const u32 *)(misc + o_lens), (const u64 *)(misc + o_pows), (u32)lens.size(), 1, (u64 *)(misc + o_cur),
+               ptr<u64>(b_hits), n_hits);
+        CKK();
+    }
+    if (!empty_hits.empty())
+        CK(cudaMemcpyAsync(ptr<u64>(b_hits) + n_hits, empty_hits.data(), empty_hits.size() * 8, cudaMemcpyHostToDevice, h->stream));
+    const u64 *d_sorted = ptr<u64>(b_hits);
+    if (n_all > 1) {
+#ifdef DBG_EMU
+        std::sort(ptr<u64>(b_hits), ptr<u64>(b_hits) + n_all);
+#else
+        size_t tmp = 0;
+        CK(cub::DeviceRadixSort::SortKeys(nullptr, tmp, ptr<u64>(b_hits), ptr<u64>(b_hits2), (int64_t)n_all, 0, 64, h->stream));
+        TRY(reserve(h, h->b_sorttmp, tmp));
+        h->st.n_launches++;
+        CK(cub::DeviceRadixSort::SortKeys(h->b_sorttmp.p, tmp, ptr<u64>(b_hits), ptr<u64>(b_hits2), (int64_t)n_all, 0, 64, h->stream));
+        d_sorted = ptr<u64>(b_hits2);
+#endif
+    }
+    LAUNCH(k_sup_sum, blocks_for(n_contigs), DBG_BLOCK, h->stream, d_sorted, n_all, (const double *)(misc + o_sc), n_contigs,
+           (double *)(misc + o_out));
+    CKK();
+    CK(cudaMemcpyAsync(out_scores, misc + o_out, n_contigs * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return DBG_OK;
 }
 
 DBG_API int dbg_set_min_count(dbg_t *h, uint32_t min_count) {

@@ -18,7 +18,7 @@ CSRC = os.path.join(PKG_DIR, 'csrc')
 LIB_DIR = os.path.join(PKG_DIR, 'lib')
 LIB_PATH = os.path.join(LIB_DIR, 'libdbg_b200.so')
 SOURCES = ('dbg_b200.cu',)
-HEADERS = ('dbg_common.cuh', 'dbg_kernels.cuh', 'dbg_chunks.cuh', 'dbg_shard.cuh', 'dbg_generic.cuh')
+HEADERS = ('dbg_common.cuh', 'dbg_kernels.cuh', 'dbg_chunks.cuh', 'dbg_shard.cuh', 'dbg_generic.cuh', 'dbg_support.cuh')
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-shared', '-Xcompiler', '-fPIC']
@@ -75,6 +75,7 @@ SYMBOLS = {
     'dbg_last_error': (C.c_char_p, [_P]),
     'dbg_set_stream': (C.c_int, [_P, _P]),
     'dbg_set_min_count': (C.c_int, [_P, C.c_uint32]),
+    'dbg_support_scores': (C.c_int, [_P, _P, _P, C.c_uint64, _P, _P, _P, C.c_uint64, _P]),
     'dbg_version': (C.c_int, []),
     'dbg_build': (C.c_int, [_P, _P, _P, C.c_uint64, C.c_uint64, C.c_double, C.c_uint32]),
     'dbg_build_device': (C.c_int, [_P, _P, _P, C.c_uint64, C.c_uint64, C.c_uint64, C.c_double, C.c_uint32]),

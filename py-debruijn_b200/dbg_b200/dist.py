@@ -75,6 +75,16 @@ class _Clock:
         self.t, self.dev = timings, dev
         self.t0 = time.perf_counter()
 
+    def sub(self, name):
+        """Finer breakdown inside a stage: recorded under `name` AND left in the enclosing stage's total."""
+        if self.t is None:
+            return
+        if self.dev.type == 'cuda':
+            torch.cuda.synchronize(self.dev)
+        now = time.perf_counter()
+        self.t[name] = self.t.get(name, 0.0) + (now - getattr(self, 'ts', self.t0)) * 1e3
+        self.ts = now
+
     def tick(self, name):
         if self.t is None:
             return
@@ -83,6 +93,7 @@ class _Clock:
         now = time.perf_counter()
         self.t[name] = self.t.get(name, 0.0) + (now - self.t0) * 1e3
         self.t0 = now
+        self.ts = now
 
 
 def _fence(dev, graph=None):
@@ -127,6 +138,8 @@ def build_shard(graph: Graph, local_packed, read_idx_base, group=None, clock=Non
         clock.tick('exchange_ms')
     graph.chunk_table_reset(max(1, recv.shape[0]))
     graph.chunk_merge_records(recv.data_ptr(), recv.shape[0])
+    if clock:
+        clock.sub('expand.merge_ms')
     graph.chunk_expand()
     if clock:
         clock.tick('owner_expand_ms')
@@ -208,6 +221,8 @@ def build_sharded(graph: Graph, local_packed, read_idx_base, threshold=3, final=
     # ---- degrees / prune / branch flags on the shard ----
     graph.shard_config(rank, world)
     graph.graph_stage(0, threshold, final, exact_order, False)
+    if clock:
+        clock.sub('graph.stage0_ms')
     st = graph.stats()
     tot = torch.tensor([st.n_nodes, st.n_edges, st.n_multi, st.n_branch, st.n_starts, st.n_windows],
                        dtype=torch.int64, device=dev)
@@ -233,13 +248,21 @@ def build_sharded(graph: Graph, local_packed, read_idx_base, threshold=3, final=
     n_exit = int(counts.sum())
     exit_keys = torch.empty((n_exit, W), dtype=torch.int64, device=dev)
     graph.shard_exit_keys(exit_keys.data_ptr())
+    if clock:
+        clock.sub('walk.exit_keys_ms')
     rc = _exchange_counts(counts, dev, group)
     sc = [int(c) for c in counts]
     req = torch.empty((sum(rc), W), dtype=torch.int64, device=dev)
     dist.all_to_all_single(req, exit_keys, output_split_sizes=rc, input_split_sizes=sc, group=group)
     _fence(dev, graph)
+    if clock:
+        clock.sub('walk.exchange_keys_ms')
     graph.shard_mark_entries(req.data_ptr(), req.shape[0])
+    if clock:
+        clock.sub('walk.mark_entries_ms')
     n_rv = graph.shard_rank_local()
+    if clock:
+        clock.sub('walk.rank_local_ms')
     nrv = torch.tensor([n_rv], dtype=torch.int64, device=dev)
     all_nrv = torch.zeros(world, dtype=torch.int64, device=dev)
     dist.all_gather_into_tensor(all_nrv, nrv, group=group)
@@ -251,10 +274,14 @@ def build_sharded(graph: Graph, local_packed, read_idx_base, threshold=3, final=
     replies = torch.empty((n_exit,), dtype=torch.int32, device=dev)
     dist.all_to_all_single(replies, ords, output_split_sizes=sc, input_split_sizes=rc, group=group)
     _fence(dev, graph)
+    if clock:
+        clock.sub('walk.replies_ms')
     mine = torch.empty((n_rv, 2), dtype=torch.int64, device=dev)
     graph.shard_reduced_records(replies.data_ptr(), rid_base, mine.data_ptr())
     everything, _ = _all_gather_var(mine, group, all_nrv)
     _fence(dev, graph)
+    if clock:
+        clock.sub('walk.gather_reduced_ms')
     if stats is not None:
         stats['walk_bytes_out'] = (n_exit - sc[rank]) * W * 8 + (sum(rc) - rc[rank]) * 4 + n_rv * 16 * (world - 1)
     contigs = graph.shard_walk(everything.data_ptr(), everything.shape[0], int(rid_base[rank]))

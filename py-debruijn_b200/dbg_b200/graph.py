@@ -757,3 +757,37 @@ class KmerList(list):
     def __init__(self, items=(), graph=None):
         super().__init__(items)
         self._graph = graph
+
+
+def _pack_any(strings):
+    """list[str] -> (uint8 bytes, uint64 offsets); any characters (latin-1), no alphabet check."""
+    off = np.zeros(len(strings) + 1, np.uint64)
+    if strings:
+        np.cumsum(np.fromiter((len(x) for x in strings), dtype=np.uint64, count=len(strings)), out=off[1:])
+    data = np.frombuffer(''.join(strings).encode('latin-1'), dtype=np.uint8) if strings else np.zeros(0, np.uint8)
+    return np.ascontiguousarray(data), off
+
+
+def support_read_scores(contigs, score_table, device=0):
+    """findSupportReadScore (IV_sortOutputs.py:10-15) for every contig of a list, on the GPU (include/dbg_b200.h,
+    dbg_support_scores): float64 sums in the score_table's own key order, bit-identical with the reference's
+    left-to-right `score +=`.  `score_table` is the reference's dict read -> score."""
+    contigs = list(contigs)
+    reads = list(score_table.keys())
+    for x in contigs + reads:
+        if any(ord(ch) > 255 for ch in x):
+            raise ValueError('dbg_b200: support scores take latin-1 strings')
+    out = np.zeros(len(contigs), np.float64)
+    if not contigs:
+        return out
+    rb, ro = _pack_any(reads)
+    cb, co = _pack_any(contigs)
+    sc = np.ascontiguousarray(np.fromiter((float(score_table[r]) for r in reads), dtype=np.float64, count=len(reads)))
+    g = Graph(1, device=device)
+    try:
+        g.lib.check(g.h, g.lib.dbg_support_scores(g.h, rb.ctypes.data if len(rb) else None, ro.ctypes.data, len(reads),
+                                                  sc.ctypes.data if len(sc) else None, cb.ctypes.data if len(cb) else None,
+                                                  co.ctypes.data, len(contigs), out.ctypes.data))
+    finally:
+        g.close()
+    return out

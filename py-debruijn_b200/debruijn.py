@@ -128,3 +128,22 @@ def get_score(edge_count_table, contig, k):
     if (counts == 0).any():
         raise KeyError(contig[int((counts == 0).argmax()):][:k + 1])
     return int(counts.sum())
+
+
+def support_read_scores(contigs, score_table):
+    """IV_sortOutputs.py:10-15 (`findSupportReadScore`) for a whole contig list in one GPU pass: list of float."""
+    from dbg_b200.graph import support_read_scores as _srs
+    return [float(x) for x in _srs(contigs, score_table)]
+
+
+def findSupportReadScore(contig, score_table):
+    """Same name and arguments as IV_sortOutputs.py:10 (one contig; use support_read_scores for many)."""
+    return support_read_scores([contig], score_table)[0]
+
+
+def sort_by_support(contigs, score_table):
+    """IV_sortOutputs.py:54: `contigs.sort(key=findSupportReadScore, reverse=True)` -- a stable sort, so contigs of
+    equal score keep their order.  Returns (sorted contigs, their scores)."""
+    scores = support_read_scores(contigs, score_table)
+    order = sorted(range(len(contigs)), key=lambda i: scores[i], reverse=True)
+    return [contigs[i] for i in order], [scores[i] for i in order]
