@@ -217,6 +217,25 @@ def cpu_python_port(cfg, G_sample):
             'sample': '%d bp sub-genome of the same shape (%d reads, %d windows)' % (G_sample, len(reads), nwin)}
 
 
+def cpu_literal(cfg, G_sample):
+    """The LITERAL reference (debruijn.py, unmodified, recursion limit raised), 1 core, bounded sample of the C1
+    shape -- only where its file is present (the build container; it does not travel to the GPU box)."""
+    from oracle import literal
+    if not literal.available():
+        return None
+    c1 = CONFIGS['c1']
+    bases, off = make_reads(c1, G=G_sample)
+    L = c1['L']
+    raw = bases.tobytes().decode('ascii')
+    reads = [raw[i * L:(i + 1) * L] for i in range(len(off) - 1)]
+    nwin = n_windows_of(off, c1['k'])
+    build_s, walk_s, n_contigs = literal.timed(reads, c1['k'], c1['thr'], False)
+    return {'value': nwin / (build_s + walk_s), 'unit': 'k-mers/s', 'cores': 1, 'kind': 'literal',
+            'sample': 'the unmodified debruijn.py on a %d bp sub-genome of the configs[0] shape (%d reads, %d windows), '
+                      'construct_graph %.3f s + output_contigs %.3f s' % (G_sample, len(reads), nwin, build_s, walk_s),
+            'contigs': n_contigs}
+
+
 def cpu_c_port(cfg, bases, off, final=False):
     """The C restatement (oracle/dbg_oracle.c), 1 core, on the given reads."""
     from oracle import c_oracle
@@ -738,6 +757,9 @@ def run_dbg(args, cfg, rank, local_rank, world):
                       'output_contigs on a ' + py['sample'],
             'build_kmers_per_sec': py['windows'] / py['build_s'], 'contigs_per_sec': py['contigs'] / py['walk_s'],
         }
+        lit = cpu_literal(cfg, 2500)
+        if lit is not None:
+            line['cpu_baseline_literal'] = lit
         line['cpu_baseline_c'] = {
             'value': cp['windows'] / cp['total_s'], 'unit': 'k-mers/s', 'cores': 1, 'kind': 'port',
             'sample': 'C restatement (oracle/dbg_oracle.c) on the FULL workload of this run',

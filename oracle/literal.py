@@ -19,7 +19,9 @@ import os
 import sys
 import threading
 
-REFERENCE_PATHS = ('/root/reference/debruijn.py',)
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# the build container's reference tree, or an unmodified copy that travelled with the repo (git-ignored baseline/_ref)
+REFERENCE_PATHS = ('/root/reference/debruijn.py', os.path.join(_ROOT, 'baseline', '_ref', 'debruijn.py'))
 
 
 def available():
@@ -85,5 +87,22 @@ def snapshot(reads, k, threshold, final, mod=None):
             'contigs': list(contigs),
             'stdout': buf.getvalue().splitlines(),
         }
+
+    return _run_big_stack(go)
+
+
+def timed(reads, k, threshold, final, mod=None):
+    """construct_graph + output_contigs of the literal reference, timed separately (seconds)."""
+    import time
+    mod = mod or load()
+
+    def go():
+        with contextlib.redirect_stdout(io.StringIO()):
+            t0 = time.perf_counter()
+            g, pull, branch, pulled, ect = mod.construct_graph(list(reads), k, threshold=threshold, final=final)
+            t1 = time.perf_counter()
+            contigs = mod.output_contigs(g, branch, pulled)
+            t2 = time.perf_counter()
+        return t1 - t0, t2 - t1, len(contigs)
 
     return _run_big_stack(go)
