@@ -144,7 +144,7 @@ struct dbg_handle {
     uint64_t shard_hint_nodes = 0;            // nodes of the last shard this handle expanded (dbg_chunk_expand)
     bool merge_check_pending = false;         // dbg_chunk_merge_records' overflow flag is looked at by graph_finalize
     cudaStream_t init_stream = nullptr;
-    cudaEvent_t ev_init[2];
+    cudaEvent_t ev_init[3];                   // [0] build start, [1] chunk table + boundary list cleared, [2] node table cleared
     DevBuf b_up;                              // lifted successor arrays (strings / scores), built on demand
     bool up_ready = false;
     DevBuf b_codes, b_etable, b_earr, b_earr2, b_estart, b_edeg, b_enk, b_lut;
@@ -639,7 +639,7 @@ static int expand_node_table(dbg_t *h) {
     if (!h->preinit) {
         LAUNCH(k_table_init<W>, blocks_for(n_slots), DBG_BLOCK, h->stream, ptr<S>(h->b_table), n_slots);
         CKK();
-    }
+    } else CK(cudaStreamWaitEvent(h->stream, h->ev_init[2], 0));        // cleared on the side stream
     const bool self_hash = !h->have_hbytes;                          // no sketch pass ran: no hash bytes
     h->preinit = false;                                              // a rebuild (overflow) initialises its own table
     const int b = ev_mark(h);
@@ -988,14 +988,22 @@ static int build_impl(dbg_t *h, const u8 *d_bases, const u64 *d_off) {
                 list_cleared = true;
                 int sms_ = 148;
                 cudaDeviceGetAttribute(&sms_, cudaDevAttrMultiProcessorCount, h->device);
-                const uint64_t bg = (uint64_t)sms_ * 2;                   // background grid: two blocks an SM
+                uint64_t bg = (uint64_t)sms_;                             // background grid: one block an SM (measured 1 / 2 / 8 / 64:
+                                                                          //   C2 step 2.070 / 2.089 / 2.122 / 2.125 ms)
+                if (const char *e = getenv("DBG_B200_BG_BLOCKS")) {       // tuning: blocks per SM of the background clears
+                    const unsigned long long v = strtoull(e, nullptr, 10);
+                    if (v >= 1) bg = (uint64_t)sms_ * v;
+                }
                 LAUNCH(k_chunk_table_init<W>, std::min<uint64_t>(bg, blocks_for(n_cs)), DBG_BLOCK, h->init_stream, ptr<CS>(h->b_ctable), n_cs);
                 CKK();
+                CK(cudaEventRecord(h->ev_init[1], h->init_stream));
                 if (!chunks_only) {
+                    // the node table is not needed before k_expand: its 0.3 GB of writes land under k_chunk_insert (which
+                    // lives in L2) instead of competing with k_pack for HBM
                     LAUNCH(k_table_init<W>, std::min<uint64_t>(bg, blocks_for(n_ns)), DBG_BLOCK, h->init_stream, ptr<S>(h->b_table), n_ns);
                     CKK();
+                    CK(cudaEventRecord(h->ev_init[2], h->init_stream));
                 }
-                CK(cudaEventRecord(h->ev_init[1], h->init_stream));
                 h->preinit = !chunks_only;
             }
         }
@@ -2156,8 +2164,17 @@ DBG_API int dbg_create_ex(dbg_t **out, int device, int k, int key_words) {
     for (int i = 0; i < EV_MAX; i++) cudaEventCreate(&h->ev[i]);
     for (int i = 0; i <= MAX_SLICES; i++) cudaEventCreate(&h->slice_ev[i]);
     cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
+#ifdef DBG_EMU
     cudaStreamCreateWithFlags(&h->init_stream, cudaStreamNonBlocking);
-    for (int i = 0; i < 2; i++) cudaEventCreate(&h->ev_init[i]);
+#else
+    {   // background work (table clears) at the LOWEST priority: blocks of the main stream's kernels go first
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if (cudaStreamCreateWithPriority(&h->init_stream, cudaStreamNonBlocking, lo) != cudaSuccess)
+            cudaStreamCreateWithFlags(&h->init_stream, cudaStreamNonBlocking);
+    }
+#endif
+    for (int i = 0; i < 3; i++) cudaEventCreate(&h->ev_init[i]);
     if (cudaMallocHost(&h->ctl, CTL_BYTES) != cudaSuccess) h->ctl = nullptr;
     if (reserve(h, h->b_ctr, sizeof(DevCounters)) != DBG_OK) {
         g_create_error = h->err;
@@ -2209,7 +2226,7 @@ DBG_API void dbg_destroy(dbg_t *h) {
     for (int i = 0; i <= MAX_SLICES; i++) cudaEventDestroy(h->slice_ev[i]);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->init_stream) cudaStreamDestroy(h->init_stream);
-    for (int i = 0; i < 2; i++) cudaEventDestroy(h->ev_init[i]);
+    for (int i = 0; i < 3; i++) cudaEventDestroy(h->ev_init[i]);
 #ifdef DBG_EMU
     if (h->pin) free(h->pin);
 #else

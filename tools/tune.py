@@ -16,7 +16,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, 'py-debruijn_b200')]
 
-STAGES = ('ms_pack', 'ms_estimate', 'ms_table_init', 'ms_insert', 'ms_chunk_insert', 'ms_expand_sketch', 'ms_expand', 'ms_region_order', 'ms_region_order',
+STAGES = ('ms_pack', 'ms_estimate', 'ms_table_init', 'ms_insert', 'ms_chunk_insert', 'ms_expand_sketch', 'ms_expand', 'ms_region_order',
           'ms_finalize', 'ms_order', 'ms_lists', 'ms_tips', 'ms_pull_reads', 'ms_build_total', 'ms_walk_rank',
           'ms_walk_emit', 'ms_walk_total')
 
