@@ -517,6 +517,44 @@ def e2e_api(R, args):
     return out
 
 
+def n3_concat(R, args):
+    """III_concatenateOutpus.py:53-146: the whole k = 20..6 loop + substring dedup on the GPU
+    (dbg_concat_*: one persistent kernel per k, Python's Mersenne Twister on the device) next to the restatement of
+    the script on the same contigs, score table and seed; outputs and printed lines compared."""
+    import random
+    from dbg_b200.concat import concatenate_outputs
+    r = random.Random(5)
+    aa = 'ACDEFGHIKLMNPQRSTVWY'
+    protein = ''.join(r.choice(aa) for _ in range(2400))
+    contigs, table = [], {}
+    for _ in range(300):
+        ln = r.choice([4, 7, 12, 18, 22, 25, 30, 40, 55])
+        p = r.randrange(0, len(protein) - ln + 1)
+        s = list(protein[p:p + ln])
+        if ln >= 8 and r.random() < 0.2:
+            j = r.randrange(0, 5) if r.random() < 0.5 else ln - 2 - r.randrange(0, 5)
+            s[j], s[j + 1] = s[j + 1], s[j]
+        contigs.append(''.join(s))
+    for _ in range(1800):
+        ln = r.randrange(5, 11)
+        p = r.randrange(0, len(protein) - ln + 1)
+        table[protein[p:p + ln]] = table.get(protein[p:p + ln], 0) + r.choice([0.85, 0.9, 0.99])
+    a, b = [], []
+    concatenate_outputs(contigs[:40], table, rng=random.Random(0), out=b.append)       # warm-up
+    b.clear()
+    t0 = time.perf_counter()
+    got = concatenate_outputs(contigs, table, rng=random.Random(1), out=b.append)
+    ms = (time.perf_counter() - t0) * 1e3
+    from oracle import concat_oracle                                # the CPU restatement, timed beside it
+    t0 = time.perf_counter()
+    exp = concat_oracle.concatenate_outputs(contigs, table, random.Random(1), out=a.append)
+    ms_port = (time.perf_counter() - t0) * 1e3
+    return {'workload': '%d peptide contigs cut from one 2400-letter sequence (adjacent swaps near the ends in 20 %%), '
+                        'k = 20..6, random.seed(1)' % len(contigs),
+            'outputs': len(got), 'ms': ms, 'python_port_ms': ms_port,
+            'equal_port': bool(got == exp and a == b)}
+
+
 def run_dbg(args, cfg, rank, local_rank, world):
     import torch
     import torch.distributed as dist
@@ -779,6 +817,7 @@ def run_dbg(args, cfg, rank, local_rank, world):
                           'nodes': int(res.n_nodes), 'contigs': int(len(res.contigs)), 'mode': mode}
         if not args.no_extras:
             line['e2e_api'] = e2e_api(R, args)
+            line['n3_concat'] = n3_concat(R, args)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -795,7 +834,7 @@ def main():
     ap.add_argument('--cpu-sample-bp', type=int, default=42_000)     # ~10 s of pure-Python work (the walk is super-linear)
     ap.add_argument('--ref-sample-bp', type=int, default=0)          # --impl reference: 0 = the full N=1 workload per step
     ap.add_argument('--min-count', type=int, default=1)              # EXTENSION (no reference oracle): abundance filter, configs[2] (ii)
-    ap.add_argument('--no-extras', action='store_true')              # skip strong_c5 / c4_batched / e2e_api
+    ap.add_argument('--no-extras', action='store_true')              # skip strong_c5 / c4_batched / e2e_api / n3_concat
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))

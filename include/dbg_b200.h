@@ -277,6 +277,49 @@ int dbg_materialize(dbg_t *h, const uint64_t *idx, uint64_t n, char *buf, const 
  * the path                                                                                  */
 int dbg_contig_scores(dbg_t *h, const uint64_t *idx, uint64_t n, uint64_t *scores);
 
+/* ---- contig concatenation, III_concatenateOutpus.py:57-142 ----
+ * The reference's randomised greedy merge (`for k in 20..6: up to 100000 times: current = random.choice(...)`,
+ * :57-137) as ONE persistent kernel per k: the contigs live in a byte arena in HBM, Python's Mersenne Twister runs
+ * on the device, no host round trip between iterations.  The handle only lends its device, stream and error text.
+ *   dbg_concat_begin    contigs (any bytes) = concatenated bytes + n + 1 offsets, HOST pointers; slot i = contig i.
+ *   dbg_concat_run      one k (:58-138).  mt_state = the 625 words of random.Random.getstate()[1] (624 state words +
+ *                       position), read and written back: the draws are exactly those of `random.choice` (:65) on
+ *                       that generator.  Returns with status
+ *                         DBG_CONCAT_DONE         the k is finished; n_alive = len(contigs), max_len = the longest
+ *                         DBG_CONCAT_NEED_CHOICE  the iteration in flight met swap-tolerant matches (:85-131), which
+ *                                                 the reference decides by findSupportReadScore of two candidate
+ *                                                 strings: read the matches with dbg_concat_pending (slot order =
+ *                                                 the reference's print order; `current` = the slot drawn), the
+ *                                                 strings with dbg_concat_lengths / dbg_concat_strings, answer with
+ *                                                 dbg_concat_choose and call dbg_concat_run(resume = 1).
+ *   dbg_concat_pending  the n_pending matched slots of that iteration, ascending, with their codes
+ *                       (1 head-on-tail :76, 2 tail-on-head :80, 3 swapped head-on-tail :85, 4 swapped tail-on-head :108).
+ *   dbg_concat_choose   one byte per pending match; for codes 3 / 4: 1 = result_1, 2 = result_2 (:91-98, :114-121).
+ *   dbg_concat_lengths  length of every slot's current string and whether the slot is still in the list.
+ *   dbg_concat_strings  strings of the given slots back to back at bytes + off[j] (off[j+1] - off[j] = its length).
+ *   dbg_concat_dedup    :139-142: keep[i] = 1 iff slot i is in the list and no earlier slot's string contains it.
+ */
+#define DBG_CONCAT_DONE 1u
+#define DBG_CONCAT_NEED_CHOICE 2u
+typedef struct {
+    uint32_t status;         /* DBG_CONCAT_*                                                            */
+    uint32_t current;        /* NEED_CHOICE: the slot random.choice drew                                */
+    uint64_t iterations;     /* iterations of this k finished so far                                    */
+    uint32_t n_alive;        /* len(contigs)                                                            */
+    uint32_t max_len;        /* len(max(contigs, key=len))                                              */
+    uint32_t n_pending;      /* NEED_CHOICE: matches of the iteration in flight                         */
+    uint32_t pad;
+    uint64_t arena_bytes;    /* bytes of string storage in use                                          */
+} dbg_concat_status_t;
+int dbg_concat_begin(dbg_t *h, const uint8_t *contigs, const uint64_t *contig_off, uint64_t n_contigs);
+int dbg_concat_run(dbg_t *h, int k, uint64_t max_iter, uint32_t *mt_state /* 625 */, int resume, dbg_concat_status_t *out);
+int dbg_concat_pending(dbg_t *h, uint32_t *slots, uint8_t *codes);
+int dbg_concat_choose(dbg_t *h, const uint8_t *choice);
+int dbg_concat_lengths(dbg_t *h, uint32_t *len, uint8_t *alive);
+int dbg_concat_strings(dbg_t *h, const uint32_t *slots, uint64_t n, uint8_t *bytes, const uint64_t *off);
+int dbg_concat_dedup(dbg_t *h, uint8_t *keep);
+int dbg_concat_end(dbg_t *h);
+
 #ifdef __cplusplus
 }
 #endif

@@ -45,6 +45,7 @@
 #include "dbg_shard.cuh"
 #include "dbg_generic.cuh"
 #include "dbg_support.cuh"
+#include "dbg_concat.cuh"
 
 #define DBG_ABI_VERSION 1
 #define DBG_RETRY_COLD 1                      // internal: a build sized from the handle's hint did not fit; redo it cold
@@ -156,7 +157,9 @@ struct dbg_handle {
     const dbg_shard_contig_t *sview = nullptr;  // what dbg_shard_contigs reads: the pinned records, or `scontigs` when some were dropped
     uint64_t n_sview = 0;
     int shard_stage = 0;                      // 0 none, 1 exits listed, 2 entries marked, 3 ranked locally, 4 reduced records out, 5 walked
+    struct ConcatSession *cc = nullptr;       // dbg_concat_* (III_concatenateOutpus.py:57-142; dbg_concat_host.cuh)
 };
+static void concat_free(dbg_t *h);
 
 static std::string g_create_error;
 static TGeom geom_of(const dbg_t *h);
@@ -2222,6 +2225,7 @@ DBG_API void dbg_destroy(dbg_t *h) {
                      &h->b_up, &h->b_codes, &h->b_etable, &h->b_earr, &h->b_earr2, &h->b_estart, &h->b_edeg, &h->b_enk, &h->b_lut,
                      &h->b_exitslot, &h->b_reqslot, &h->b_rvslot, &h->b_rvord, &h->b_link2, &h->b_scontig, &h->b_owneroff};
     for (DevBuf *b : all) if (b->p) cudaFree(b->p);
+    concat_free(h);
     for (int i = 0; i < EV_MAX; i++) cudaEventDestroy(h->ev[i]);
     for (int i = 0; i <= MAX_SLICES; i++) cudaEventDestroy(h->slice_ev[i]);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
@@ -3011,3 +3015,4 @@ DBG_API int dbg_contig_scores(dbg_t *h, const uint64_t *idx, uint64_t n, uint64_
     return DISPATCH(scores_impl, h, idx, n, scores);
 }
 
+#include "dbg_concat_host.cuh"

@@ -18,7 +18,8 @@ CSRC = os.path.join(PKG_DIR, 'csrc')
 LIB_DIR = os.path.join(PKG_DIR, 'lib')
 LIB_PATH = os.path.join(LIB_DIR, 'libdbg_b200.so')
 SOURCES = ('dbg_b200.cu',)
-HEADERS = ('dbg_common.cuh', 'dbg_kernels.cuh', 'dbg_chunks.cuh', 'dbg_shard.cuh', 'dbg_generic.cuh', 'dbg_support.cuh')
+HEADERS = ('dbg_common.cuh', 'dbg_kernels.cuh', 'dbg_chunks.cuh', 'dbg_shard.cuh', 'dbg_generic.cuh', 'dbg_support.cuh',
+           'dbg_concat.cuh', 'dbg_concat_host.cuh')
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-shared', '-Xcompiler', '-fPIC']
@@ -63,6 +64,14 @@ class ShardContig(C.Structure):
 
 class Segment(C.Structure):
     _fields_ = [('entry', C.c_uint32), ('n_nodes', C.c_uint32)]
+
+
+class ConcatStatus(C.Structure):
+    _fields_ = [('status', C.c_uint32), ('current', C.c_uint32), ('iterations', C.c_uint64), ('n_alive', C.c_uint32),
+                ('max_len', C.c_uint32), ('n_pending', C.c_uint32), ('pad', C.c_uint32), ('arena_bytes', C.c_uint64)]
+
+
+DBG_CONCAT_DONE, DBG_CONCAT_NEED_CHOICE = 1, 2
 
 
 # every symbol include/dbg_b200.h declares: name -> (restype, argtypes)
@@ -119,6 +128,14 @@ SYMBOLS = {
     'dbg_segments': (C.c_int, [_P, _P, C.POINTER(C.c_uint64)]),
     'dbg_materialize': (C.c_int, [_P, _P, C.c_uint64, _P, _P]),
     'dbg_contig_scores': (C.c_int, [_P, _P, C.c_uint64, _P]),
+    'dbg_concat_begin': (C.c_int, [_P, _P, _P, C.c_uint64]),
+    'dbg_concat_run': (C.c_int, [_P, C.c_int, C.c_uint64, _P, C.c_int, C.POINTER(ConcatStatus)]),
+    'dbg_concat_pending': (C.c_int, [_P, _P, _P]),
+    'dbg_concat_choose': (C.c_int, [_P, _P]),
+    'dbg_concat_lengths': (C.c_int, [_P, _P, _P]),
+    'dbg_concat_strings': (C.c_int, [_P, _P, C.c_uint64, _P, _P]),
+    'dbg_concat_dedup': (C.c_int, [_P, _P]),
+    'dbg_concat_end': (C.c_int, [_P]),
 }
 
 

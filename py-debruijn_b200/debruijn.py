@@ -24,7 +24,8 @@ import numpy as np
 from dbg_b200._native import AlphabetError
 from dbg_b200.graph import BatchGraph, EdgeCountTable, Edges, Graph, KmerList, Node, Vertices, pack_reads  # noqa: F401
 
-__all__ = ['Node', 'read_reads', 'construct_graph', 'construct_graph_batch', 'output_contigs', 'get_score']
+__all__ = ['Node', 'read_reads', 'construct_graph', 'construct_graph_batch', 'output_contigs', 'get_score',
+           'support_read_scores', 'findSupportReadScore', 'sort_by_support', 'concatenate_outputs']
 
 
 def read_reads(fname):
@@ -147,3 +148,12 @@ def sort_by_support(contigs, score_table):
     scores = support_read_scores(contigs, score_table)
     order = sorted(range(len(contigs)), key=lambda i: scores[i], reverse=True)
     return [contigs[i] for i in order], [scores[i] for i in order]
+
+
+def concatenate_outputs(contigs, sequences_scores, rng=None, out=print):
+    """III_concatenateOutpus.py:53-146 (the contig list read at :31 in, the list written at :148-149 out): the
+    randomised greedy merge for k = 20 .. 6 and the substring dedup, on the GPU (dbg_b200/concat.py).  Prints the
+    script's lines through `out`; draws from `rng` (default: the `random` module's generator, as the script does --
+    after `random.seed(s)` the result is the unmodified script's result after `random.seed(s)`)."""
+    from dbg_b200.concat import concatenate_outputs as _co
+    return _co(contigs, sequences_scores, rng=rng, out=out)
