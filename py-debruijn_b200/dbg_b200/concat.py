@@ -122,7 +122,7 @@ def concatenate(session, sequences_scores, rng=None, ks=None, out=print, max_ite
                     elif cd == 4:
                         cand += [current + contig[k:], current[:len(current) - k] + contig]       # :114-115
                         where.append(j)
-                scores = support_read_scores(cand, sequences_scores, device=session._g.device)
+                scores = support_read_scores(cand, sequences_scores, graph=session._g)
                 choice = np.zeros(len(slots), np.uint8)
                 for t, j in enumerate(where):
                     first = scores[2 * t] > scores[2 * t + 1]                                      # :95, :118

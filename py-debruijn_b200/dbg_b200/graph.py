@@ -768,7 +768,7 @@ def _pack_any(strings):
     return np.ascontiguousarray(data), off
 
 
-def support_read_scores(contigs, score_table, device=0):
+def support_read_scores(contigs, score_table, device=0, graph=None):
     """findSupportReadScore (IV_sortOutputs.py:10-15) for every contig of a list, on the GPU (include/dbg_b200.h,
     dbg_support_scores): float64 sums in the score_table's own key order, bit-identical with the reference's
     left-to-right `score +=`.  `score_table` is the reference's dict read -> score."""
@@ -783,11 +783,12 @@ def support_read_scores(contigs, score_table, device=0):
     rb, ro = _pack_any(reads)
     cb, co = _pack_any(contigs)
     sc = np.ascontiguousarray(np.fromiter((float(score_table[r]) for r in reads), dtype=np.float64, count=len(reads)))
-    g = Graph(1, device=device)
+    g = graph if graph is not None else Graph(1, device=device)     # `graph`: a handle to borrow (its k does not matter)
     try:
         g.lib.check(g.h, g.lib.dbg_support_scores(g.h, rb.ctypes.data if len(rb) else None, ro.ctypes.data, len(reads),
                                                   sc.ctypes.data if len(sc) else None, cb.ctypes.data if len(cb) else None,
                                                   co.ctypes.data, len(contigs), out.ctypes.data))
     finally:
-        g.close()
+        if graph is None:
+            g.close()
     return out
