@@ -256,6 +256,13 @@ int dbg_branch_nodes(dbg_t *h, uint32_t *node_id);   /* n_branch ids, reference 
 int dbg_pulled_nodes(dbg_t *h, uint32_t *node_id);   /* n_pulled ids, reference order        */
 int dbg_pull_reads(dbg_t *h, uint8_t *read_flags);   /* n_reads bytes, 1 = in pull_out_read  */
 int dbg_node_keys(dbg_t *h, const uint32_t *node_id, uint64_t n, uint64_t *key_lo, uint64_t *key_hi);
+/* EXTRA output, no reference line (north-star kernel 4 "in/out-degree and Eulerian balance"; SURVEY.md section 9
+ * delta 4): the reference keeps outdegree = distinct successors and a 0/1 first-seen indegree FLAG
+ * (debruijn.py:129-143, reported by dbg_export_nodes) and never a balance.  For the given nodes of the unpruned
+ * graph: indegree = distinct predecessors (distinct (k+1)-mers that end in the node), outdegree = distinct
+ * successors, balance = outdegree - indegree.  DNA handles holding the complete graph; any pointer may be NULL. */
+int dbg_degree_balance(dbg_t *h, const uint32_t *node_id, uint64_t n, uint8_t *indegree, uint8_t *outdegree,
+                       int8_t *balance);
 
 /* edge_count_table[(k+1)-mer] for n ASCII (k+1)-mers laid back to back; 0 = absent
  * (II_assembleFromReads.py:17 indexes it per contig window)                                 */

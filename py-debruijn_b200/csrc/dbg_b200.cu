@@ -2833,6 +2833,42 @@ DBG_API int dbg_node_keys(dbg_t *h, const uint32_t *node_id, uint64_t n, uint64_
 }
 
 template <int W>
+static int degree_impl(dbg_t *h, const uint32_t *node_id, uint64_t n, uint8_t *indeg, uint8_t *outdeg, int8_t *balance) {
+    DevBuf *s = h->b_scratch;
+    TRY(reserve(h, s[0], h->n_slots * 4));
+    TRY(reserve(h, s[1], n * 4));
+    TRY(reserve(h, s[2], n));
+    TRY(reserve(h, s[3], n));
+    TRY(reserve(h, s[4], n));
+    CK(cudaMemsetAsync(s[0].p, 0, h->n_slots * 4, h->stream));
+    CK(cudaMemcpyAsync(s[1].p, node_id, n * 4, cudaMemcpyHostToDevice, h->stream));
+    uint64_t grid = blocks_for(h->n_slots);
+    if (grid > 148 * 16) grid = 148 * 16;
+    LAUNCH(k_true_indegree<W>, grid, DBG_BLOCK, h->stream, ptr<const Slot<W>>(h->b_table), geom_of(h), h->k, ptr<u32>(s[0]));
+    CKK();
+    LAUNCH(k_degree_gather<W>, blocks_for(n), DBG_BLOCK, h->stream, ptr<const Slot<W>>(h->b_table), ptr<const u32>(s[0]),
+           ptr<const u32>(s[1]), n, ptr<u8>(s[2]), ptr<u8>(s[3]), ptr<signed char>(s[4]));
+    CKK();
+    if (indeg) CK(cudaMemcpyAsync(indeg, s[2].p, n, cudaMemcpyDeviceToHost, h->stream));
+    if (outdeg) CK(cudaMemcpyAsync(outdeg, s[3].p, n, cudaMemcpyDeviceToHost, h->stream));
+    if (balance) CK(cudaMemcpyAsync(balance, s[4].p, n, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return DBG_OK;
+}
+
+DBG_API int dbg_degree_balance(dbg_t *h, const uint32_t *node_id, uint64_t n, uint8_t *indeg, uint8_t *outdeg, int8_t *balance) {
+    NEED_BUILT();
+    if (n == 0) return DBG_OK;
+    if (!node_id) return fail(h, DBG_ERR_ARG, "NULL input");
+    if (h->sym_bits == GEN_BITS) return fail(h, DBG_ERR_STATE, "dbg_degree_balance: DNA handles only (a generic-alphabet handle lists its edges with dbg_export_edges)");
+    if (h->shard_n > 1) return fail(h, DBG_ERR_STATE, "dbg_degree_balance needs the complete graph, this handle holds a shard");
+    for (uint64_t i = 0; i < n; i++)
+        if (node_id[i] >= h->n_slots) return fail(h, DBG_ERR_ARG, "node id %u out of range", node_id[i]);
+    CK(cudaSetDevice(h->device));
+    return DISPATCH(degree_impl, h, node_id, n, indeg, outdeg, balance);
+}
+
+template <int W>
 static int lookup_impl(dbg_t *h, const uint8_t *q, const uint32_t *batch, uint64_t n, uint32_t *counts) {
     DevBuf *s = h->b_scratch;
     const uint64_t bytes = n * (uint64_t)(h->k + 1);

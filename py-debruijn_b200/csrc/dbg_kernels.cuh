@@ -1065,6 +1065,38 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_lookup_edges(const Slot<W> *__res
     out[i] = res;
 }
 
+// TRUE in-degree / out-degree / balance of the (unpruned) graph: in = distinct predecessors = distinct (k+1)-mers that end
+// in the node, out = distinct successors, balance = out - in.  An EXTRA output (north-star kernel 4, SURVEY.md 9
+// delta 4): the reference keeps only the 0/1 first-seen `indegree` flag (debruijn.py:137-143) and no balance.
+template <int W>
+__global__ void __launch_bounds__(DBG_BLOCK) k_true_indegree(const Slot<W> *__restrict__ table, TGeom tg, int k,
+                                                             u32 *__restrict__ indeg) {
+    typedef typename KeyOf<W>::type K;
+    const K mask = key_mask<W>(k);
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < tg.n_slots; i += (u64)gridDim.x * blockDim.x) {
+        const K key = load_key(&table[i]);
+        if (key == empty_key<W>()) continue;
+        for (u32 c = 0; c < 4; c++) {
+            if (!table[i].cnt[c]) continue;
+            const u64 fi = table_find<W>(table, tg, key_roll(key, c, mask));
+            if (fi != NONE64) atomicAdd(&indeg[fi], 1u);
+        }
+    }
+}
+template <int W>
+__global__ void __launch_bounds__(DBG_BLOCK) k_degree_gather(const Slot<W> *__restrict__ table, const u32 *__restrict__ indeg,
+                                                             const u32 *__restrict__ ids, u64 n, u8 *__restrict__ o_in,
+                                                             u8 *__restrict__ o_out, signed char *__restrict__ o_bal) {
+    const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const u32 i = ids[j];
+    u32 out = 0;
+    for (u32 c = 0; c < 4; c++) out += table[i].cnt[c] != 0u;
+    o_in[j] = (u8)indeg[i];
+    o_out[j] = (u8)out;
+    o_bal[j] = (signed char)((int)out - (int)indeg[i]);
+}
+
 template <int W>
 __global__ void __launch_bounds__(DBG_BLOCK) k_gather_keys(const Slot<W> *__restrict__ table,
                                                            const u32 *__restrict__ ids, u64 n,

@@ -121,6 +121,7 @@ SYMBOLS = {
     'dbg_pulled_nodes': (C.c_int, [_P, _P]),
     'dbg_pull_reads': (C.c_int, [_P, _P]),
     'dbg_node_keys': (C.c_int, [_P, _P, C.c_uint64, _P, _P]),
+    'dbg_degree_balance': (C.c_int, [_P, _P, C.c_uint64, _P, _P, _P]),
     'dbg_lookup_edges': (C.c_int, [_P, _P, C.c_uint64, _P]),
     'dbg_lookup_edges_batched': (C.c_int, [_P, _P, _P, C.c_uint64, _P]),
     'dbg_walk': (C.c_int, [_P, C.c_int, C.POINTER(C.c_uint64)]),

@@ -419,6 +419,24 @@ class Graph:
             self._edges = a
         return self._edges
 
+    def degree_balance(self):
+        """TRUE in-degree (distinct predecessors), out-degree (distinct successors) and balance = out - in of every
+        node of the unpruned graph, in nodes() order (dbg_degree_balance).  An extra output: the reference keeps only
+        `outdegree` and a 0/1 first-seen `indegree` flag (debruijn.py:129-143; SURVEY.md 9 delta 4)."""
+        nd = self.nodes()
+        n = len(nd['id'])
+        if self.alphabet is not None:                                   # generic-alphabet engine: from its edge list
+            e = self.edges()
+            ind = np.bincount(e['dst'], minlength=n).astype(np.uint8)
+            out = np.bincount(e['src'], minlength=n).astype(np.uint8)
+            return {'indegree': ind, 'outdegree': out, 'balance': out.astype(np.int8) - ind.astype(np.int8)}
+        ind, out, bal = np.zeros(n, np.uint8), np.zeros(n, np.uint8), np.zeros(n, np.int8)
+        if n:
+            ids = np.ascontiguousarray(nd['id'], dtype=np.uint32)
+            self.lib.check(self.h, self.lib.dbg_degree_balance(self.h, ids.ctypes.data, n, ind.ctypes.data, out.ctypes.data,
+                                                               bal.ctypes.data))
+        return {'indegree': ind, 'outdegree': out, 'balance': bal}
+
     def label_of_ids(self, ids):
         ids = np.ascontiguousarray(ids, dtype=np.uint32)
         n = len(ids)
