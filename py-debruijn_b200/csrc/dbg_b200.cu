@@ -157,6 +157,7 @@ struct dbg_handle {
     const dbg_shard_contig_t *sview = nullptr;  // what dbg_shard_contigs reads: the pinned records, or `scontigs` when some were dropped
     uint64_t n_sview = 0;
     int shard_stage = 0;                      // 0 none, 1 exits listed, 2 entries marked, 3 ranked locally, 4 reduced records out, 5 walked
+    bool avoid_regions = false;               // a build on this handle overflowed its regions (skewed minimizers): plain layout from then on
     struct ConcatSession *cc = nullptr;       // dbg_concat_* (III_concatenateOutpus.py:57-142; dbg_concat_host.cuh)
 };
 static void concat_free(dbg_t *h);
@@ -455,7 +456,7 @@ static uint32_t pass_count(dbg_t *h, uint64_t table_bytes) {
 static bool want_regions(const dbg_t *h) {
     // the region of a node is a hash of its minimizer (+ batch id): short minimizers take too few values to spread
     const ChunkGeom g = chunk_geom(h->k);
-    bool on = 2 * g.m + h->batch_bits >= 24 && h->sym_bits == 2;
+    bool on = 2 * g.m + h->batch_bits >= 24 && h->sym_bits == 2 && !h->avoid_regions;
     if (const char *e = getenv("DBG_B200_REGIONS")) on = atoi(e) != 0 && h->sym_bits == 2;    // tests / tuning: 0 = plain hash layout, 1 = force
     return on;
 }
@@ -695,12 +696,24 @@ static int expand_node_table(dbg_t *h) {
 template <int W>
 static int settle_node_table(dbg_t *h, bool fetched) {
     DevCounters *d_ctr = ptr<DevCounters>(h->b_ctr);
+    const uint64_t n_slots0 = h->n_slots;
     for (int attempt = 0;; attempt++) {
         if (!fetched) TRY(fetch_counters(h));
         fetched = false;
         tm_flush(h);
         if (!h->ctr.overflow) break;
-        if (attempt >= 6) return fail(h, DBG_ERR_NOMEM, "node table overflowed repeatedly");
+        if (attempt >= 8) return fail(h, DBG_ERR_NOMEM, "node table overflowed repeatedly");
+        if (attempt == 1 && geom_of(h).n_regions > 1) {
+            // Twice the slots did not help: the nodes are not short of slots, they crowd a few REGIONS -- reads that pile
+            // up on a few loci (amplicons, a high-copy repeat) put thousands of k-mer variants behind the same
+            // minimizers, and a larger table only adds regions nobody maps to.  Fall back to the plain hash layout
+            // (partition passes) for this build and for the following builds on the handle.
+            h->region_mode = false;
+            h->avoid_regions = true;
+            h->region_slots = 0;
+            h->have_hbytes = false;
+            h->n_slots = n_slots0;
+        }
         h->n_slots *= 2;                                               // estimate was low: rebuild larger
         CK(cudaMemsetAsync(&d_ctr->overflow, 0, 4, h->stream));
         if (h->n_ev >= h->expand_evs) h->n_ev -= h->expand_evs;                                // (the table may have been expanded by an earlier call)
@@ -1145,7 +1158,12 @@ static int graph_finalize(dbg_t *h) {
                ptr<u32>(h->b_link), d_ctr);
         CKK();
         if (geom_of(h).n_regions > 1) {
-            LAUNCH(k_finalize_far<W>, 148 * 4, DBG_BLOCK, h->stream, ptr<const S>(h->b_table), geom_of(h), h->k,
+            uint64_t far_grid = 148 * 16;                               // (measured 4 / 8 / 16 / 32 blocks an SM: finalize 0.278 / 0.268 / 0.265 / 0.266 ms at C2)
+            if (const char *e = getenv("DBG_B200_FAR_GRID")) {           // tuning: blocks per SM
+                const unsigned long long v = strtoull(e, nullptr, 10);
+                if (v >= 1) far_grid = 148 * v;
+            }
+            LAUNCH(k_finalize_far<W>, far_grid, DBG_BLOCK, h->stream, ptr<const S>(h->b_table), geom_of(h), h->k,
                    ptr<const u16>(h->b_kept), ptr<const u32>(h->b_link), ptr<u8>(h->b_flags), ptr<u32>(h->b_succ),
                    h->shard_n > 1 ? 1 : 0, d_ctr);
             CKK();
