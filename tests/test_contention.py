@@ -31,10 +31,10 @@ def _hot_reads(seed, G, L, n, err):
 @pytest.mark.parametrize('small_tables', [False, True])
 def test_hot_slots(backend_gpu, monkeypatch, k, small_tables):
     from dbg_b200 import Graph
-    if small_tables:
-        monkeypatch.setenv('DBG_B200_CHUNK_SLOTS', '64')
-        monkeypatch.setenv('DBG_B200_NODE_SLOTS', '256')
-    for seed, G, L, n, err in [(1, 300, 100, 300_000, 0.0), (2, 500, 150, 200_000, 0.002)]:
+    for seed, G, L, n, err, slots in [(1, 300, 100, 300_000, 0.0, 256), (2, 500, 150, 200_000, 0.002, 1 << 17)]:
+        if small_tables:                                           # a few doublings away from what the data need
+            monkeypatch.setenv('DBG_B200_CHUNK_SLOTS', '64')
+            monkeypatch.setenv('DBG_B200_NODE_SLOTS', str(slots))
         bases, off = _hot_reads(seed, G, L, n, err)
         g = Graph(k)
         try:
