@@ -36,6 +36,8 @@ CONFIGS = {
                name='configs[1]: synthetic 4.6 Mb genome, 150 bp reads 30x, k=31'),
     'c3': dict(G=4_600_000, L=150, cov=30, err=0.01, k=31, thr=2, seed=1002,
                name='configs[2]: 4.6 Mb genome, 1% substitution errors, k=31 (reference semantics, threshold 2)'),
+    'c3f': dict(G=50_000, L=150, cov=30, err=0.01, k=31, thr=2, seed=1002,
+                name='configs[2] on a 50 kb sub-sample (SURVEY 8 D2: the shape final=True is run on; use with --final)'),
     'c4': dict(T=10_000, Gmin=1000, Gmax=5000, L=100, cov=20, err=0.0, k=25, thr=2, seed=1004, G=30_000_000,
                name='configs[3]: 10k templates of 1-5 kb, 100 bp reads 20x, k=25, every template its own graph '
                     '(one batched pass)'),
@@ -254,7 +256,7 @@ def static_config(args, cfg, world):
     batched = 'T' in cfg
     return {'workload': wl, 'config_key': args.config, 'k': cfg['k'], 'threshold': cfg['thr'],
             'genome_bp': cfg['G'] * world, 'read_len': cfg['L'], 'coverage': cfg['cov'], 'error_rate': cfg['err'],
-            'final': False,
+            'final': bool(getattr(args, 'final', False)),
             'min_count': getattr(args, 'min_count', 1),
             'min_count_note': None if getattr(args, 'min_count', 1) <= 1 else
             'EXTENSION without a reference oracle (SURVEY.md section 9 delta 5): pinned by the two restatements only',
@@ -282,7 +284,7 @@ def run_reference(args, cfg, rank, world):
     nwin = n_windows_of(off, cfg['k'])
     times, last = [], None
     for i in range(args.warmup + args.steps):
-        last = cpu_c_port(cfg, bases, off)
+        last = cpu_c_port(cfg, bases, off, final=bool(getattr(args, 'final', False)))
         if i >= args.warmup:
             times.append(last['total_s'])
     t = float(np.mean(times))
@@ -571,9 +573,12 @@ def run_dbg(args, cfg, rank, local_rank, world):
         dist.init_process_group('nccl', device_id=dev)
 
     k, thr = cfg['k'], cfg['thr']
+    fin = bool(args.final)
     read_base = 0
     batched = 'T' in cfg
     sharded = world > 1 and not batched
+    if fin and (batched or sharded):
+        raise SystemExit('bench.py: --final runs on one GPU, one graph')
     read_batch = None
     if batched:
         # independent templates: shard by batch id, no collective; rank r builds its own T templates
@@ -609,9 +614,9 @@ def run_dbg(args, cfg, rank, local_rank, world):
             last['res'] = ddist.build_sharded(g, None, read_base, threshold=thr, final=False, stats=ex_stats,
                                               local_device=(d_bases.data_ptr(), d_off.data_ptr(), n_reads, n_bases))
         else:
-            g.build_device(d_bases.data_ptr(), d_off.data_ptr(), n_reads, n_bases, threshold=thr, final=False,
+            g.build_device(d_bases.data_ptr(), d_off.data_ptr(), n_reads, n_bases, threshold=thr, final=fin,
                            min_count=args.min_count)
-            g.walk(stop_at_branch=True)
+            g.walk(stop_at_branch=not fin)
 
     def step_host():
         if batched:
@@ -620,8 +625,8 @@ def run_dbg(args, cfg, rank, local_rank, world):
         elif sharded:
             last['res'] = ddist.build_sharded(g, (hb_np, ho_np), read_base, threshold=thr, final=False)
         else:
-            g.build(None, threshold=thr, final=False, packed=(hb_np, ho_np), min_count=args.min_count)
-            g.walk(stop_at_branch=True)
+            g.build(None, threshold=thr, final=fin, packed=(hb_np, ho_np), min_count=args.min_count)
+            g.walk(stop_at_branch=not fin)
 
     for _ in range(max(args.warmup, 3)):
         step_device()
@@ -788,7 +793,7 @@ def run_dbg(args, cfg, rank, local_rank, world):
     line.update(extras)
     if world == 1 and not args.no_cpu_baseline and not batched:
         py = cpu_python_port(cfg, args.cpu_sample_bp)
-        cp = cpu_c_port(cfg, bases, off)
+        cp = cpu_c_port(cfg, bases, off, final=fin)
         line['cpu_baseline'] = {
             'value': py['windows'] / (py['build_s'] + py['walk_s']), 'unit': 'k-mers/s', 'cores': 1, 'kind': 'port',
             'sample': 'pure-Python restatement of debruijn.py (oracle/dbg_oracle.py), construct_graph + '
@@ -807,11 +812,11 @@ def run_dbg(args, cfg, rank, local_rank, world):
         # parity at N = 1: the product's result of the timed workload against the C oracle, row by row
         from oracle import c_oracle, compare
         g.shard_config(0, 0)
-        g.build(None, threshold=thr, final=False, packed=(bases, off), min_count=args.min_count)
-        g.walk(stop_at_branch=True)
-        res = c_oracle.run(None, k, thr, False, strings=False, packed=(bases.tobytes(), off), min_count=args.min_count)
+        g.build(None, threshold=thr, final=fin, packed=(bases, off), min_count=args.min_count)
+        g.walk(stop_at_branch=not fin)
+        res = c_oracle.run(None, k, thr, fin, strings=False, packed=(bases.tobytes(), off), min_count=args.min_count)
         rows = []
-        bad = compare.compare_with_oracle(g, res, False, report=lambda name, ok: rows.append(name))
+        bad = compare.compare_with_oracle(g, res, fin, report=lambda name, ok: rows.append(name))
         line['parity'] = {'against': 'C oracle (oracle/dbg_oracle.c) on the FULL workload of this run',
                           'rows': rows, 'rows_differing': bad, 'equal': not bad,
                           'nodes': int(res.n_nodes), 'contigs': int(len(res.contigs)), 'mode': mode}
@@ -834,6 +839,7 @@ def main():
     ap.add_argument('--cpu-sample-bp', type=int, default=42_000)     # ~10 s of pure-Python work (the walk is super-linear)
     ap.add_argument('--ref-sample-bp', type=int, default=0)          # --impl reference: 0 = the full N=1 workload per step
     ap.add_argument('--min-count', type=int, default=1)              # EXTENSION (no reference oracle): abundance filter, configs[2] (ii)
+    ap.add_argument('--final', action='store_true')                  # construct_graph(final=True): all paths enumerated (single GPU, e.g. --config c3f)
     ap.add_argument('--no-extras', action='store_true')              # skip strong_c5 / c4_batched / e2e_api / n3_concat
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
