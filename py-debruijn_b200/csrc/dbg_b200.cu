@@ -1163,6 +1163,7 @@ static int graph_finalize(dbg_t *h) {
                 const unsigned long long v = strtoull(e, nullptr, 10);
                 if (v >= 1) far_grid = 148 * v;
             }
+            if (far_grid > blocks_for(n_slots)) far_grid = blocks_for(n_slots);   // (the far list is shorter than the table)
             LAUNCH(k_finalize_far<W>, far_grid, DBG_BLOCK, h->stream, ptr<const S>(h->b_table), geom_of(h), h->k,
                    ptr<const u16>(h->b_kept), ptr<const u32>(h->b_link), ptr<u8>(h->b_flags), ptr<u32>(h->b_succ),
                    h->shard_n > 1 ? 1 : 0, d_ctr);
