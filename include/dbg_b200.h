@@ -56,6 +56,14 @@ typedef enum {
 #define DBG_CHUNKS_ONLY 16u  /* stop after phase 1 of the chunk build (the distinct super-k-mers of the
                                 reads): the multi-GPU build exchanges CHUNK records, before any node table */
 
+#define DBG_BOTH_STRANDS 32u /* EXTENSION without a reference line (north-star "canonical k-mers"; the reference has no reverse
+                                complement anywhere, SURVEY.md section 9 delta 1): build from the reads FOLLOWED BY THEIR REVERSE
+                                COMPLEMENTS (read n_reads + i = reverse complement of read i), i.e. exactly what the reference
+                                computes on that longer read list -- which is its oracle.  The graph then holds every k-mer
+                                next to its reverse complement (twin nodes, dbg_twin_nodes): the canonical graph, unfolded.
+                                dbg_build / dbg_build_device, DNA handles, read_idx_base 0; dbg_stats / dbg_pull_reads count
+                                2 x n_reads reads.                                                                         */
+
 /* node flag bits (dbg_export_nodes) */
 #define DBG_NODE_START   0x02u  /* reference indegree == 0 (debruijn.py:137-143 quirk)       */
 #define DBG_NODE_BRANCH  0x04u  /* > 1 successor survives pruningEdges (debruijn.py:230-236) */
@@ -263,6 +271,10 @@ int dbg_node_keys(dbg_t *h, const uint32_t *node_id, uint64_t n, uint64_t *key_l
  * successors, balance = outdegree - indegree.  DNA handles holding the complete graph; any pointer may be NULL. */
 int dbg_degree_balance(dbg_t *h, const uint32_t *node_id, uint64_t n, uint8_t *indegree, uint8_t *outdegree,
                        int8_t *balance);
+/* twin_id[j] = node id of the reverse complement of node node_id[j], 0xFFFFFFFF if the graph does not hold it (it always
+ * does after a DBG_BOTH_STRANDS build); canonical[j] = 1 iff the node's k-mer <= its reverse complement (the canonical
+ * representative of the pair; both 1 for a palindrome, which is its own twin).  DNA handles, unbatched builds.        */
+int dbg_twin_nodes(dbg_t *h, const uint32_t *node_id, uint64_t n, uint32_t *twin_id, uint8_t *canonical);
 
 /* edge_count_table[(k+1)-mer] for n ASCII (k+1)-mers laid back to back; 0 = absent
  * (II_assembleFromReads.py:17 indexes it per contig window)                                 */

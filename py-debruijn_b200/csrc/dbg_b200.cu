@@ -157,6 +157,7 @@ struct dbg_handle {
     const dbg_shard_contig_t *sview = nullptr;  // what dbg_shard_contigs reads: the pinned records, or `scontigs` when some were dropped
     uint64_t n_sview = 0;
     int shard_stage = 0;                      // 0 none, 1 exits listed, 2 entries marked, 3 ranked locally, 4 reduced records out, 5 walked
+    DevBuf b_bases2, b_off2;                  // DBG_BOTH_STRANDS: the reads followed by their reverse complements
     bool avoid_regions = false;               // a build on this handle overflowed its regions (skewed minimizers): plain layout from then on
     struct ConcatSession *cc = nullptr;       // dbg_concat_* (III_concatenateOutpus.py:57-142; dbg_concat_host.cuh)
 };
@@ -2244,6 +2245,8 @@ DBG_API void dbg_destroy(dbg_t *h) {
                      &h->b_up, &h->b_codes, &h->b_etable, &h->b_earr, &h->b_earr2, &h->b_estart, &h->b_edeg, &h->b_enk, &h->b_lut,
                      &h->b_exitslot, &h->b_reqslot, &h->b_rvslot, &h->b_rvord, &h->b_link2, &h->b_scontig, &h->b_owneroff};
     for (DevBuf *b : all) if (b->p) cudaFree(b->p);
+    if (h->b_bases2.p) cudaFree(h->b_bases2.p);
+    if (h->b_off2.p) cudaFree(h->b_off2.p);
     concat_free(h);
     for (int i = 0; i < EV_MAX; i++) cudaEventDestroy(h->ev[i]);
     for (int i = 0; i <= MAX_SLICES; i++) cudaEventDestroy(h->slice_ev[i]);
@@ -2481,8 +2484,16 @@ static int build_device_common(dbg_t *h, const uint8_t *d_bases, const uint64_t 
     return DBG_OK;
 }
 
+static int build_both_strands(dbg_t *h, const uint8_t *d_bases, const uint64_t *d_read_off, uint64_t n_reads, uint64_t n_bases,
+                              uint64_t read_idx_base, double threshold, uint32_t flags);
+
 DBG_API int dbg_build_device(dbg_t *h, const uint8_t *d_bases, const uint64_t *d_read_off, uint64_t n_reads,
                      uint64_t n_bases, uint64_t read_idx_base, double threshold, uint32_t flags) {
+    if (h && (flags & DBG_BOTH_STRANDS)) {
+        if ((n_bases && !d_bases) || !d_read_off) return fail(h, DBG_ERR_ARG, "dbg_build_device: NULL input");
+        CK(cudaSetDevice(h->device));
+        return build_both_strands(h, d_bases, d_read_off, n_reads, n_bases, read_idx_base, threshold, flags);
+    }
     return build_device_common(h, d_bases, d_read_off, n_reads, n_bases, read_idx_base, threshold, flags, nullptr, 0);
 }
 
@@ -2537,6 +2548,24 @@ DBG_API int dbg_build_batched_device(dbg_t *h, const uint8_t *d_bases, const uin
     return build_device_common(h, d_bases, d_read_off, n_reads, n_bases, 0, threshold, flags, d_read_batch, n_batches);
 }
 
+// DBG_BOTH_STRANDS: build from the reads on the device followed by their reverse complements (read n + i = rc of read i)
+static int build_both_strands(dbg_t *h, const uint8_t *d_bases, const uint64_t *d_read_off, uint64_t n_reads, uint64_t n_bases,
+                              uint64_t read_idx_base, double threshold, uint32_t flags) {
+    if (h->sym_bits != 2) return fail(h, DBG_ERR_ARG, "DBG_BOTH_STRANDS exists for the DNA engine only");
+    if (read_idx_base || (flags & (DBG_TABLE_ONLY | DBG_CHUNKS_ONLY)))
+        return fail(h, DBG_ERR_ARG, "DBG_BOTH_STRANDS is a single-handle build (read_idx_base 0, no DBG_TABLE_ONLY / DBG_CHUNKS_ONLY)");
+    if (2 * n_reads >= 0xFFFFFFFFull) return fail(h, DBG_ERR_OVERFLOW, "read index exceeds 32 bits");
+    TRY(reserve(h, h->b_bases2, 2 * n_bases + 32));
+    TRY(reserve(h, h->b_off2, (2 * n_reads + 1) * 8));
+    uint64_t grid = cdiv(n_reads, DBG_WARPS);
+    if (grid > 148 * 16) grid = 148 * 16;
+    if (grid < 1) grid = 1;
+    LAUNCH(k_strand_reads, grid, DBG_BLOCK, h->stream, (const u8 *)d_bases, (const u64 *)d_read_off, (u64)n_reads, (u64)n_bases, ptr<u8>(h->b_bases2), ptr<u64>(h->b_off2));
+    CKK();
+    return build_device_common(h, ptr<const uint8_t>(h->b_bases2), ptr<const uint64_t>(h->b_off2), 2 * n_reads, 2 * n_bases, 0,
+                               threshold, flags & ~DBG_BOTH_STRANDS, nullptr, 0);
+}
+
 DBG_API int dbg_build(dbg_t *h, const uint8_t *bases, const uint64_t *read_off, uint64_t n_reads,
               uint64_t read_idx_base, double threshold, uint32_t flags) {
     if (!h) return DBG_ERR_ARG;
@@ -2544,6 +2573,17 @@ DBG_API int dbg_build(dbg_t *h, const uint8_t *bases, const uint64_t *read_off, 
     const uint64_t n_bases = read_off[n_reads];
     if (n_bases && !bases) return fail(h, DBG_ERR_ARG, "dbg_build: bases is NULL");
     CK(cudaSetDevice(h->device));
+    if (flags & DBG_BOTH_STRANDS) {                                      // (no slice streaming in this mode: everything over first)
+        TRY(reserve(h, h->b_bases, n_bases + 32));
+        TRY(reserve(h, h->b_off, (n_reads + 1) * 8));
+        CK(cudaMemcpyAsync(h->b_off.p, read_off, (n_reads + 1) * 8, cudaMemcpyHostToDevice, h->stream));
+        if (n_bases) CK(cudaMemcpyAsync(h->b_bases.p, bases, n_bases, cudaMemcpyHostToDevice, h->stream));
+        h->host_bases = nullptr;
+        const int rc2 = build_both_strands(h, ptr<const uint8_t>(h->b_bases), ptr<const uint64_t>(h->b_off), n_reads, n_bases,
+                                           read_idx_base, threshold, flags);
+        if (rc2 != DBG_OK) cudaStreamSynchronize(h->stream);             // the caller's buffers are its own again
+        return rc2;
+    }
     TRY(stage_host_reads(h, bases, read_off, n_reads, n_bases));
     const int rc = build_device_common(h, ptr<const uint8_t>(h->b_bases), ptr<const uint64_t>(h->b_off), n_reads, n_bases,
                                        read_idx_base, threshold, flags, nullptr, 0);
@@ -2849,6 +2889,33 @@ DBG_API int dbg_node_keys(dbg_t *h, const uint32_t *node_id, uint64_t n, uint64_
         if (node_id[i] >= h->n_slots) return fail(h, DBG_ERR_ARG, "node id %u out of range", node_id[i]);
     CK(cudaSetDevice(h->device));
     return DISPATCH(node_keys_impl, h, node_id, n, key_lo, key_hi);
+}
+
+template <int W>
+static int twin_impl(dbg_t *h, const uint32_t *node_id, uint64_t n, uint32_t *twin, uint8_t *canonical) {
+    DevBuf *s = h->b_scratch;
+    TRY(reserve(h, s[0], n * 4));
+    TRY(reserve(h, s[1], n * 4));
+    TRY(reserve(h, s[2], n));
+    CK(cudaMemcpyAsync(s[0].p, node_id, n * 4, cudaMemcpyHostToDevice, h->stream));
+    LAUNCH(k_twin_nodes<W>, blocks_for(n), DBG_BLOCK, h->stream, ptr<const Slot<W>>(h->b_table), geom_of(h), h->k,
+           ptr<const u32>(s[0]), n, ptr<u32>(s[1]), ptr<u8>(s[2]));
+    CKK();
+    if (twin) CK(cudaMemcpyAsync(twin, s[1].p, n * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (canonical) CK(cudaMemcpyAsync(canonical, s[2].p, n, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return DBG_OK;
+}
+
+DBG_API int dbg_twin_nodes(dbg_t *h, const uint32_t *node_id, uint64_t n, uint32_t *twin_id, uint8_t *canonical) {
+    NEED_BUILT();
+    if (n == 0) return DBG_OK;
+    if (!node_id) return fail(h, DBG_ERR_ARG, "NULL input");
+    if (h->sym_bits == GEN_BITS || h->batch_bits) return fail(h, DBG_ERR_STATE, "dbg_twin_nodes: DNA handles, unbatched builds");
+    for (uint64_t i = 0; i < n; i++)
+        if (node_id[i] >= h->n_slots) return fail(h, DBG_ERR_ARG, "node id %u out of range", node_id[i]);
+    CK(cudaSetDevice(h->device));
+    return DISPATCH(twin_impl, h, node_id, n, twin_id, canonical);
 }
 
 template <int W>

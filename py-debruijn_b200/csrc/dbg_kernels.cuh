@@ -1065,6 +1065,60 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_lookup_edges(const Slot<W> *__res
     out[i] = res;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Both strands (DBG_BOTH_STRANDS): the reads followed by their reverse complements, as a forward-strand assembler is
+// usually fed -- an EXTENSION (north-star "canonical k-mers"; the reference has no reverse complement anywhere,
+// SURVEY.md 9 delta 1).  The graph then holds every k-mer next to its reverse complement ("twin nodes"), which is the
+// canonical graph unfolded: counts of e and rc(e) are equal, and the nodes with key <= rc(key) are the canonical ones.
+// ---------------------------------------------------------------------------------------------
+DBG_D u8 comp_base(u8 c) { return c == 'A' ? 'T' : c == 'C' ? 'G' : c == 'G' ? 'C' : c == 'T' ? 'A' : c; }
+__global__ void __launch_bounds__(DBG_BLOCK) k_strand_reads(const u8 *__restrict__ src, const u64 *__restrict__ off, u64 n_reads,
+                                                            u64 n_bases, u8 *__restrict__ dst, u64 *__restrict__ off2) {
+    const u32 lane = threadIdx.x & 31;
+    const u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((u64)gridDim.x * blockDim.x) >> 5;
+    for (u64 r = warp; r < n_reads; r += n_warps) {
+        const u64 a = off[r], L = off[r + 1] - a;
+        for (u64 j = lane; j < L; j += 32) {
+            dst[a + j] = src[a + j];
+            dst[n_bases + a + j] = comp_base(src[a + L - 1 - j]);
+        }
+        if (lane == 0) { off2[r] = a; off2[n_reads + r] = n_bases + a; }
+    }
+    if (warp == 0 && lane == 0) off2[2 * n_reads] = 2 * n_bases;
+}
+DBG_HD u64 rev2bit64(u64 x) {                               // the 32 two-bit groups of a word in reverse order
+    x = ((x >> 2) & 0x3333333333333333ULL) | ((x & 0x3333333333333333ULL) << 2);
+    x = ((x >> 4) & 0x0F0F0F0F0F0F0F0FULL) | ((x & 0x0F0F0F0F0F0F0F0FULL) << 4);
+    x = ((x >> 8) & 0x00FF00FF00FF00FFULL) | ((x & 0x00FF00FF00FF00FFULL) << 8);
+    x = ((x >> 16) & 0x0000FFFF0000FFFFULL) | ((x & 0x0000FFFF0000FFFFULL) << 16);
+    return (x >> 32) | (x << 32);
+}
+DBG_HD u64 key_revcomp(u64 key, int k) { return rev2bit64(~key) >> (64 - 2 * k); }
+DBG_HD K128 key_revcomp(K128 key, int k) {
+    const u64 hi = rev2bit64(~key.lo), lo = rev2bit64(~key.hi);       // 128 bits reversed, left-aligned
+    const int sh = 128 - 2 * k;                                       // 2 <= sh <= 126 (a handle with 128-bit keys may hold k <= 31 too)
+    K128 r;
+    if (sh >= 64) { r.hi = 0; r.lo = sh == 64 ? hi : hi >> (sh - 64); }
+    else { r.hi = hi >> sh; r.lo = (lo >> sh) | (hi << (64 - sh)); }
+    return r;
+}
+DBG_HD bool key_le(u64 a, u64 b) { return a <= b; }
+DBG_HD bool key_le(K128 a, K128 b) { return a.hi < b.hi || (a.hi == b.hi && a.lo <= b.lo); }
+// twin[j] = node id of the reverse complement of node ids[j] (NONE32 if the graph does not hold it), canonical[j] = key <= rc(key)
+template <int W>
+__global__ void __launch_bounds__(DBG_BLOCK) k_twin_nodes(const Slot<W> *__restrict__ table, TGeom tg, int k,
+                                                          const u32 *__restrict__ ids, u64 n, u32 *__restrict__ twin,
+                                                          u8 *__restrict__ canonical) {
+    typedef typename KeyOf<W>::type K;
+    const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const K key = load_key(&table[ids[j]]);
+    const K rc = key_revcomp(key, k);
+    const u64 fi = table_find<W>(table, tg, rc);
+    twin[j] = fi == NONE64 ? NONE32 : (u32)fi;
+    canonical[j] = key_le(key, rc) ? 1 : 0;
+}
+
 // TRUE in-degree / out-degree / balance of the (unpruned) graph: in = distinct predecessors = distinct (k+1)-mers that end
 // in the node, out = distinct successors, balance = out - in.  An EXTRA output (north-star kernel 4, SURVEY.md 9
 // delta 4): the reference keeps only the 0/1 first-seen `indegree` flag (debruijn.py:137-143) and no balance.

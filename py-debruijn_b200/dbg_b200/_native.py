@@ -29,7 +29,7 @@ DBG_OK = 0
 DBG_ERR_CUDA, DBG_ERR_ARG, DBG_ERR_ALPHABET, DBG_ERR_NOMEM = -1, -2, -3, -4
 DBG_ERR_STATE, DBG_ERR_ZERODIV, DBG_ERR_OVERFLOW = -5, -6, -7
 # build flags
-DBG_FINAL, DBG_EXACT_ORDER, DBG_NO_PULL_READS, DBG_TABLE_ONLY, DBG_CHUNKS_ONLY = 1, 2, 4, 8, 16
+DBG_FINAL, DBG_EXACT_ORDER, DBG_NO_PULL_READS, DBG_TABLE_ONLY, DBG_CHUNKS_ONLY, DBG_BOTH_STRANDS = 1, 2, 4, 8, 16, 32
 # node flags
 NODE_START, NODE_BRANCH, NODE_DEADEND, NODE_PULLED, NODE_MULTI = 0x02, 0x04, 0x08, 0x10, 0x20
 # terminal kinds
@@ -122,6 +122,7 @@ SYMBOLS = {
     'dbg_pull_reads': (C.c_int, [_P, _P]),
     'dbg_node_keys': (C.c_int, [_P, _P, C.c_uint64, _P, _P]),
     'dbg_degree_balance': (C.c_int, [_P, _P, C.c_uint64, _P, _P, _P]),
+    'dbg_twin_nodes': (C.c_int, [_P, _P, C.c_uint64, _P, _P]),
     'dbg_lookup_edges': (C.c_int, [_P, _P, C.c_uint64, _P]),
     'dbg_lookup_edges_batched': (C.c_int, [_P, _P, _P, C.c_uint64, _P]),
     'dbg_walk': (C.c_int, [_P, C.c_int, C.POINTER(C.c_uint64)]),

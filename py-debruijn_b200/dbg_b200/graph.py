@@ -125,20 +125,23 @@ class Graph:
         return self
 
     def build(self, reads, threshold=3, final=False, exact_order=True, pull_reads=True,
-              packed=None, read_idx_base=0, min_count=1):
-        """Host entry: `reads` is a list[str] (or pass packed=(uint8 bases, uint64 offsets))."""
+              packed=None, read_idx_base=0, min_count=1, both_strands=False):
+        """Host entry: `reads` is a list[str] (or pass packed=(uint8 bases, uint64 offsets)).  `both_strands`: an
+        extension (DBG_BOTH_STRANDS) -- the graph of the reads followed by their reverse complements."""
         self.set_min_count(min_count)
         bases, off = packed if packed is not None else pack_reads(reads)
         self.reads = reads
         self.final = bool(final)
         self._reset_cache()
         flags = (N.DBG_FINAL if final else 0) | (N.DBG_EXACT_ORDER if exact_order else 0) | \
-                (0 if pull_reads else N.DBG_NO_PULL_READS)
+                (0 if pull_reads else N.DBG_NO_PULL_READS) | (N.DBG_BOTH_STRANDS if both_strands else 0)
         self._keep = (bases, off)                      # keep the buffers alive during the call
         self.n_reads = len(off) - 1
         rc = self.lib.dbg_build(self.h, bases.ctypes.data if len(bases) else None, off.ctypes.data,
                                 self.n_reads, int(read_idx_base), float(threshold), flags)
         self.lib.check(self.h, rc)
+        if both_strands:
+            self.n_reads *= 2                          # read n + i = reverse complement of read i
         return self
 
     def build_batched(self, batches, threshold=3, final=False, exact_order=True, pull_reads=True):
@@ -436,6 +439,21 @@ class Graph:
             self.lib.check(self.h, self.lib.dbg_degree_balance(self.h, ids.ctypes.data, n, ind.ctypes.data, out.ctypes.data,
                                                                bal.ctypes.data))
         return {'indegree': ind, 'outdegree': out, 'balance': bal}
+
+    def twin_nodes(self):
+        """Per node, in nodes() order: position (in nodes() order) of the node that is its reverse complement, -1 if the
+        graph does not hold it, and whether the node is the canonical one of the pair (k-mer <= its reverse complement).
+        After a both_strands build every node has its twin (dbg_twin_nodes)."""
+        nd = self.nodes()
+        n = len(nd['id'])
+        twin, canon = np.zeros(n, np.uint32), np.zeros(n, np.uint8)
+        if n:
+            ids = np.ascontiguousarray(nd['id'], dtype=np.uint32)
+            self.lib.check(self.h, self.lib.dbg_twin_nodes(self.h, ids.ctypes.data, n, twin.ctypes.data, canon.ctypes.data))
+        slot_to_idx = np.full(int(self.stats().table_slots) + 1, -1, np.int64)
+        slot_to_idx[nd['id']] = np.arange(n)
+        pos = np.where(twin == 0xFFFFFFFF, -1, slot_to_idx[np.minimum(twin, len(slot_to_idx) - 1)])
+        return {'twin': pos, 'canonical': canon.astype(bool)}
 
     def label_of_ids(self, ids):
         ids = np.ascontiguousarray(ids, dtype=np.uint32)

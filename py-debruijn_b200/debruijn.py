@@ -38,15 +38,24 @@ def read_reads(fname):
     return reads
 
 
-def _graph_for(reads, k, threshold, final, min_count=1):
+_COMP = str.maketrans('ACGT', 'TGCA')
+
+
+def reverse_complement(read):
+    return read.translate(_COMP)[::-1]
+
+
+def _graph_for(reads, k, threshold, final, min_count=1, both_strands=False):
     """Build on the DNA engine; reads over another alphabet (the reference's real inputs are peptides,
     II_assembleFromReads.py:43-47) go to the generic-alphabet engine with the symbols they use."""
     packed = pack_reads(reads)
     g = Graph(k)
     try:
-        return g.build(reads, threshold=threshold, final=final, packed=packed, min_count=min_count)
+        return g.build(reads, threshold=threshold, final=final, packed=packed, min_count=min_count, both_strands=both_strands)
     except AlphabetError:
         g.close()
+    if both_strands:
+        raise ValueError('dbg_b200: both_strands needs DNA reads (ACGT)')
     symbols = np.flatnonzero(np.bincount(packed[0], minlength=256)).astype(np.uint8)
     if len(symbols) > 32:
         raise ValueError('dbg_b200: the reads use %d distinct characters; the GPU path handles alphabets of up to 32'
@@ -55,11 +64,15 @@ def _graph_for(reads, k, threshold, final, min_count=1):
     return g.build(reads, threshold=threshold, final=final, packed=packed, min_count=min_count)
 
 
-def construct_graph(reads, k, threshold=3, final=False, min_count=1):
+def construct_graph(reads, k, threshold=3, final=False, min_count=1, both_strands=False):
     """debruijn.py:206-285 on the GPU.  `min_count` > 1 is an extension the reference does not have (an absolute
     abundance filter on the (k+1)-mers before the window loop, dbg_set_min_count in include/dbg_b200.h);
-    the default is the reference."""
-    g = _graph_for(reads, k, threshold, final, min_count)
+    `both_strands=True` is another (DBG_BOTH_STRANDS): the result is exactly
+    construct_graph(reads + [reverse_complement(r) for r in reads], ...), made on the device -- every k-mer next to its
+    reverse complement (Graph.twin_nodes), the canonical graph unfolded.  The defaults are the reference."""
+    g = _graph_for(reads, k, threshold, final, min_count, both_strands)
+    if both_strands:
+        reads = _BothStrands(reads)
     st = g.stats()
     print('number of {}mer: '.format(k), st.n_nodes)                      # debruijn.py:224
     print('branch number: ', st.n_branch)                                 # debruijn.py:236
@@ -71,6 +84,21 @@ def construct_graph(reads, k, threshold=3, final=False, min_count=1):
         branch_kmer = KmerList(g.label_of_ids(g.branch_ids()), g)
     already_pull_out = KmerList(g.label_of_ids(g.pulled_ids()), g)
     return (Vertices(g), Edges(g)), pull_out_read, branch_kmer, already_pull_out, EdgeCountTable(g)
+
+
+class _BothStrands:
+    """reads + their reverse complements as a sequence (the second half made on demand)."""
+
+    def __init__(self, reads):
+        self.reads = reads
+
+    def __len__(self):
+        return 2 * len(self.reads)
+
+    def __iter__(self):
+        yield from self.reads
+        for r in self.reads:
+            yield reverse_complement(r)
 
 
 def construct_graph_batch(batches, k, threshold=3, final=False, min_count=1):
