@@ -224,10 +224,21 @@ def build_sharded(graph: Graph, local_packed, read_idx_base, threshold=3, final=
     if clock:
         clock.sub('graph.stage0_ms')
     st = graph.stats()
-    tot = torch.tensor([st.n_nodes, st.n_edges, st.n_multi, st.n_branch, st.n_starts, st.n_windows],
-                       dtype=torch.int64, device=dev)
-    dist.all_reduce(tot, group=group)
-    totals = dict(zip(('n_nodes', 'n_edges', 'n_multi', 'n_branch', 'n_starts', 'n_windows'), (int(x) for x in tot.tolist())))
+    names = ('n_nodes', 'n_edges', 'n_multi', 'n_branch', 'n_starts', 'n_windows')
+    counts = np.zeros(world, np.uint64)
+    if st.n_branch == 0:
+        # no branch node on this shard: finish the graph stages and list the exits now, so that ONE collective carries
+        # the global counters AND everybody's exit counts (a rank that does have branch nodes sends zeros; then some
+        # rank reports n_branch > 0 and all of them take the replicated path below)
+        if exact_order and st.n_multi:
+            graph.graph_stage(1, threshold, final, exact_order, False)
+        graph.graph_stage(2, threshold, final, exact_order, False)
+        counts = graph.shard_exit_counts(world)
+    vec = torch.tensor([int(getattr(st, f)) for f in names] + [int(c) for c in counts], dtype=torch.int64, device=dev)
+    allv = torch.empty(world * (len(names) + world), dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(allv, vec, group=group)
+    m = allv.view(world, len(names) + world).tolist()
+    totals = {f: sum(m[r][i] for r in range(world)) for i, f in enumerate(names)}
     if totals['n_branch']:
         # ordered tip pruning needs whole neighbourhoods on one rank: complete graph everywhere
         flags = _replicate(graph, threshold, final, exact_order, True, group, clock)
@@ -236,21 +247,17 @@ def build_sharded(graph: Graph, local_packed, read_idx_base, threshold=3, final=
             clock.tick('walk_ms')
         del keep
         return ShardedResult(graph, 'replicated', None, totals, rank, world, pull_flags=flags)
-    if exact_order and st.n_multi:
-        graph.graph_stage(1, threshold, final, exact_order, False)
-    graph.graph_stage(2, threshold, final, exact_order, False)
     del keep
     if clock:
         clock.tick('graph_ms')
     # ---- contig walk: exits -> owners, local ranking, reduced list ----
-    W = graph.stats().key_words
-    counts = graph.shard_exit_counts(world)
+    W = int(st.key_words)
     n_exit = int(counts.sum())
     exit_keys = torch.empty((n_exit, W), dtype=torch.int64, device=dev)
     graph.shard_exit_keys(exit_keys.data_ptr())
     if clock:
         clock.sub('walk.exit_keys_ms')
-    rc = _exchange_counts(counts, dev, group)
+    rc = [int(m[r][len(names) + rank]) for r in range(world)]           # what every rank sends to this one
     sc = [int(c) for c in counts]
     req = torch.empty((sum(rc), W), dtype=torch.int64, device=dev)
     dist.all_to_all_single(req, exit_keys, output_split_sizes=rc, input_split_sizes=sc, group=group)
