@@ -39,7 +39,7 @@ def test_product_vs_golden(backend):
     from dbg_b200.concat import concatenate_outputs
     cases = _golden()
     swaps = 0
-    for c in cases[::2] if backend == 'emu' else cases:
+    for c in cases:
         lines = []
         outs = concatenate_outputs(c['contigs'], dict(c['score_items']), rng=random.Random(c['seed']), out=lines.append)
         assert '\n'.join(lines) + '\n' == c['stdout'], c['seed']
@@ -51,7 +51,7 @@ def test_product_vs_golden(backend):
 def test_product_vs_oracle_random(backend):
     """Fresh cases, the module-level generator (as the script uses it), and the generator state afterwards."""
     from dbg_b200.concat import concatenate_outputs
-    for seed in ([11, 12] if backend == 'emu' else [11, 12, 13, 14, 15, 16]):
+    for seed in [11, 12, 13, 14, 15, 16]:
         contigs, rows = make_case(seed, 20 + 10 * (seed % 3), 90 + 40 * (seed % 4), 0.3, 0.15)
         table = score_table(rows, 0.8)
         a, b = [], []

@@ -23,8 +23,6 @@ def test_golden_fuzz_corpus(backend):
     """Outputs of /root/reference/debruijn.py itself: the DNA cases run on the 2-bit engine, the others
     (peptides, 2- and 3-letter alphabets count as DNA subsets) on the generic-alphabet engine."""
     cases = util.load_golden('fuzz.json.gz')
-    if backend == 'emu':
-        cases = cases[::2]                         # the emulator is slow; the GPU run takes the whole corpus
     n_dna = n_other = 0
     for i, case in enumerate(cases):
         got = util.product_snapshot(case['reads'], case['k'], case['threshold'], case['final'])
@@ -33,7 +31,7 @@ def test_golden_fuzz_corpus(backend):
             n_dna += 1
         else:
             n_other += 1
-    assert (n_dna > 400 and n_other >= 75) if backend == 'gpu' else (n_dna > 200 and n_other >= 35)
+    assert n_dna > 400 and n_other >= 75
 
 
 def test_kat1_peptides_of_the_reference(backend):
@@ -426,7 +424,7 @@ def test_region_layout(backend, monkeypatch, region_slots):
         monkeypatch.setenv('DBG_B200_VB_BITS', '3')                  # 8 buckets of 16: the order array is nearly all spill
     r = random.Random(4242)
     n = 0
-    while n < (40 if backend == 'gpu' else 24):
+    while n < 40:
         reads, k, thr, final = util.random_dna_case(r, big=(n % 4 == 3))
         try:
             exp = dbg_oracle.snapshot(reads, k, thr, final, max_paths=200)
