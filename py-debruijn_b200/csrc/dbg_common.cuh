@@ -214,6 +214,7 @@ DBG_D u64 cas_key(u64 *addr, u64 expect, u64 val) { return atomicCAS(addr, expec
 DBG_D K128 cas_key(K128 *addr, K128 expect, K128 val) {
     K128 old;
 #ifdef DBG_EMU
+    emu::chaos_point();
     old = *addr;
     if (old == expect) *addr = val;
 #else

@@ -12,6 +12,13 @@
  * round-robin, switching only at __syncthreads / warp collectives, so atomics are trivially
  * atomic and "device memory" is the host heap.  No tensor cores, TMA, clusters or streams
  * (everything is synchronous).  Timing APIs return wall-clock time.
+ *
+ * Chaos mode (DBG_EMU_CHAOS=seed[:permille], read at every launch): a fiber ALSO gives way, with that probability,
+ * in front of every atomic, every __ldcg / __ldcv / __stcg and the 128-bit CAS, and each scheduler pass starts at a
+ * random thread.  The threads of a block then interleave at exactly the points where the lock-free protocols of the
+ * product (CAS on the first key half, plain store of the second, retry rings, min / add on a slot another lane is
+ * still publishing) can observe each other half-way, which the serial schedule never shows.  Single operations
+ * stay atomic.  tests/test_emu_chaos.py runs the parity cases under several seeds.
  */
 #pragma once
 #include <stdint.h>
@@ -93,6 +100,9 @@ struct State {
     int n_threads = 0;
     const std::function<void()> *body = nullptr;
     char *dyn_smem = nullptr;
+    uint64_t chaos_rng = 0;                         /* 0 = chaos mode off */
+    uint32_t chaos_permille = 0;
+    uint64_t chaos_yields = 0;                      /* how often chaos mode switched fibers (emu_chaos_yields()) */
 };
 inline State &S() { static State s; return s; }
 static const size_t STACK = 256 * 1024;
@@ -105,6 +115,26 @@ inline void yield() {
 #else
     swapcontext(&s.fibers[me].ctx, &s.sched);
 #endif
+}
+/* chaos mode: give way here with probability chaos_permille / 1000 (xorshift64*, seeded per launch) */
+inline void chaos_point() {
+    State &s = S();
+    if (!s.chaos_rng || s.cur < 0) return;
+    uint64_t x = s.chaos_rng;
+    x ^= x >> 12; x ^= x << 25; x ^= x >> 27;
+    s.chaos_rng = x;
+    if ((uint32_t)((x * 0x2545F4914F6CDD1DULL) >> 40) % 1000u < s.chaos_permille) { s.chaos_yields++; yield(); }
+}
+inline void chaos_setup() {
+    State &s = S();
+    static uint64_t launches = 0;
+    const char *e = getenv("DBG_EMU_CHAOS");
+    s.chaos_rng = 0; s.chaos_permille = 0;
+    if (!e || !*e) return;
+    char *end = nullptr;
+    unsigned long long seed = strtoull(e, &end, 10);
+    s.chaos_permille = (end && *end == ':') ? (uint32_t)strtoul(end + 1, nullptr, 10) : 250u;
+    s.chaos_rng = (seed * 0x9E3779B97F4A7C15ULL + (++launches) * 0xD1B54A32D192ED03ULL) | 1ULL;
 }
 inline void trampoline() {
     State &s = S();
@@ -122,6 +152,7 @@ inline void launch(dim3 grid, dim3 block, size_t smem, const std::function<void(
     int nt = (int)(block.x * block.y * block.z);
     s.n_threads = nt;
     s.blockDim = block; s.gridDim = grid; s.body = &body;
+    chaos_setup();
     if (s.stacks.size() < (size_t)nt * STACK) s.stacks.resize((size_t)nt * STACK);
     std::vector<char> dyn(smem ? smem : 1);
     s.dyn_smem = dyn.data();
@@ -155,7 +186,10 @@ inline void launch(dim3 grid, dim3 block, size_t smem, const std::function<void(
         int remaining = nt;
         while (remaining > 0) {
             int progressed = 0, waiting = 0;
-            for (int t = 0; t < nt; t++) {
+            int t0 = 0;
+            if (s.chaos_rng) { s.chaos_rng ^= s.chaos_rng << 13; s.chaos_rng ^= s.chaos_rng >> 7; s.chaos_rng ^= s.chaos_rng << 17; t0 = (int)((s.chaos_rng >> 20) % (uint64_t)nt); }
+            for (int tt = 0; tt < nt; tt++) {
+                const int t = tt + t0 < nt ? tt + t0 : tt + t0 - nt;
                 Fiber &f = s.fibers[t];
                 if (f.done) continue;
                 if (f.at_barrier) { waiting++; continue; }
@@ -199,6 +233,7 @@ inline const uint64_t *collective(uint32_t mask, uint64_t v, uint32_t *out_mask)
 }
 }  // namespace emu
 
+extern "C" __attribute__((used, visibility("default"))) unsigned long long emu_chaos_yields() { return emu::S().chaos_yields; }
 #define threadIdx (emu::S().threadIdx)
 #define blockIdx (emu::S().blockIdx)
 #define blockDim (emu::S().blockDim)
@@ -267,15 +302,15 @@ static inline unsigned emu_reduce(uint32_t mask, unsigned v, int op) {
 static inline unsigned __reduce_add_sync(uint32_t mask, unsigned v) { return emu_reduce(mask, v, 0); }
 static inline unsigned __reduce_min_sync(uint32_t mask, unsigned v) { return emu_reduce(mask, v, 1); }
 
-/* ---- atomics (fibers never preempt, so plain code is atomic) ---- */
-template <typename T> static inline T atomicAdd(T *p, T v) { T o = *p; *p = o + v; return o; }
-template <typename T> static inline T atomicSub(T *p, T v) { T o = *p; *p = o - v; return o; }
-template <typename T> static inline T atomicMin(T *p, T v) { T o = *p; if (v < o) *p = v; return o; }
-template <typename T> static inline T atomicMax(T *p, T v) { T o = *p; if (v > o) *p = v; return o; }
-template <typename T> static inline T atomicOr(T *p, T v) { T o = *p; *p = o | v; return o; }
-template <typename T> static inline T atomicAnd(T *p, T v) { T o = *p; *p = o & v; return o; }
-template <typename T> static inline T atomicExch(T *p, T v) { T o = *p; *p = v; return o; }
-template <typename T> static inline T atomicCAS(T *p, T c, T v) { T o = *p; if (o == c) *p = v; return o; }
+/* ---- atomics (fibers never preempt, so plain code is atomic; chaos mode gives way BEFORE the operation) ---- */
+template <typename T> static inline T atomicAdd(T *p, T v) { emu::chaos_point(); T o = *p; *p = o + v; return o; }
+template <typename T> static inline T atomicSub(T *p, T v) { emu::chaos_point(); T o = *p; *p = o - v; return o; }
+template <typename T> static inline T atomicMin(T *p, T v) { emu::chaos_point(); T o = *p; if (v < o) *p = v; return o; }
+template <typename T> static inline T atomicMax(T *p, T v) { emu::chaos_point(); T o = *p; if (v > o) *p = v; return o; }
+template <typename T> static inline T atomicOr(T *p, T v) { emu::chaos_point(); T o = *p; *p = o | v; return o; }
+template <typename T> static inline T atomicAnd(T *p, T v) { emu::chaos_point(); T o = *p; *p = o & v; return o; }
+template <typename T> static inline T atomicExch(T *p, T v) { emu::chaos_point(); T o = *p; *p = v; return o; }
+template <typename T> static inline T atomicCAS(T *p, T c, T v) { emu::chaos_point(); T o = *p; if (o == c) *p = v; return o; }
 
 /* ---- intrinsics ---- */
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
@@ -304,10 +339,10 @@ static inline unsigned __funnelshift_l(unsigned lo, unsigned hi, unsigned s) {
     s &= 31; return s ? (hi << s) | (lo >> (32 - s)) : hi;
 }
 template <typename T> static inline T __ldg(const T *p) { return *p; }
-template <typename T> static inline T __ldcg(const T *p) { return *p; }
+template <typename T> static inline T __ldcg(const T *p) { emu::chaos_point(); return *p; }
 template <typename T> static inline T __ldcs(const T *p) { return *p; }
-template <typename T> static inline T __ldcv(const T *p) { return *p; }
-template <typename T> static inline void __stcg(T *p, T v) { *p = v; }
+template <typename T> static inline T __ldcv(const T *p) { emu::chaos_point(); return *p; }
+template <typename T> static inline void __stcg(T *p, T v) { emu::chaos_point(); *p = v; }
 template <typename T> static inline void __stcs(T *p, T v) { *p = v; }
 static inline void __threadfence() {}
 static inline void __threadfence_block() {}
