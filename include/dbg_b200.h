@@ -15,8 +15,10 @@
  *   - alphabet: dbg_create / dbg_create_ex handles take DNA, exactly the bytes 'A','C','G','T' (2-bit codes
  *     0..3 in that order): k-mers ("nodes", debruijn.py:127) are 2k-bit integers, first base most
  *     significant; k <= 31 uses 64-bit keys, k <= 63 uses 128-bit keys (key_hi is 0 for k <= 31).
- *     dbg_create_alpha handles take ANY alphabet of up to 32 byte values (the reference's real inputs are
- *     peptides, II_assembleFromReads.py:43-47): 5-bit codes = position in the symbol list, k <= 24, 128-bit keys
+ *     dbg_create_alpha handles take ANY alphabet of up to 255 byte values (the reference's real inputs are
+ *     peptides, II_assembleFromReads.py:43-47; debruijn.py itself works on any characters): codes = position in the
+ *     symbol list, b = ceil(log2(n_symbols)) bits each (at least 1), 128-bit keys, b (k + 1) <= 125 and k <= 63 --
+ *     peptides (5 bits) k <= 24, ACGT + N (3 bits) k <= 40, 8-bit codes k <= 14
  *   - a tag is (global read index << 32 | position in read) of a node's FIRST occurrence
  *     in the reference's iteration order (debruijn.py:123-126); sorting by tag reproduces
  *     the reference's dict order
@@ -127,8 +129,8 @@ int  dbg_create(dbg_t **out, int device, int k);
 /* key_words: 0 = by k (1 for k <= 31, else 2); 2 forces 128-bit keys for a small k, which leaves
  * room for many batch ids above the k-mer (dbg_build_batched)                               */
 int  dbg_create_ex(dbg_t **out, int device, int k, int key_words);
-/* generic-alphabet engine: `symbols` = the n_symbols <= 32 distinct byte values the reads may hold; a node key is
- * k x 5 bits (symbol codes, first symbol most significant).  Same calls as a DNA handle except the batched and
+/* generic-alphabet engine: `symbols` = the n_symbols <= 255 distinct byte values the reads may hold; a node key is
+ * k x b bits (symbol codes, first symbol most significant; b as above).  Same calls as a DNA handle except the batched and
  * multi-GPU ones; successors are reported by dbg_export_edges instead of 4 counters per node.                */
 int  dbg_create_alpha(dbg_t **out, int device, int k, const uint8_t *symbols, int n_symbols);
 void dbg_destroy(dbg_t *h);

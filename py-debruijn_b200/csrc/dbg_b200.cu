@@ -121,9 +121,10 @@ struct dbg_handle {
     bool tags_local = false;                  // every tag in the table comes from this handle's own reads
     bool chunks_streamed = false;             // phase 1 already ran, slice by slice, while the reads were arriving
     uint64_t n_cslots = 0, n_clist = 0, ex_grid = 1;
-    // generic-alphabet engine (dbg_generic.cuh): sym_bits == 5; 2 = the DNA engine
+    // generic-alphabet engine (dbg_generic.cuh): generic, sym_bits = 1 .. 8 by the number of symbols; the DNA engine has 2
+    bool generic = false;
     int sym_bits = 2, n_symbols = 4;
-    uint8_t sym_of_code[GEN_MAX_SYMBOLS] = {'A', 'C', 'G', 'T'}, code_of_byte[256];
+    uint8_t sym_of_code[256 + 1] = {'A', 'C', 'G', 'T'}, code_of_byte[256];   // [256] = sym_bits (the device copy's layout)
     uint64_t n_eslots = 0, n_earr = 0;
     // Table sizes remembered from the last successful build on this handle (like the grow-only buffers): a build of
     // a similar read set sizes its chunk and node table from them at once -- no sketch round trips, no sketch pass,
@@ -357,7 +358,7 @@ static int tip_prune(dbg_t *h) {
     if (nb == 0) return DBG_OK;
     TRY(reserve(h, h->b_cnt32, nb * 4));
     TRY(reserve(h, h->b_off64, (nb + 1) * 8));
-    if (h->sym_bits == GEN_BITS)
+    if (h->generic)
         LAUNCH(k_g_tip_paths, blocks_for(nb), DBG_BLOCK, h->stream, ptr<const u8>(h->b_flags), ptr<const u32>(h->b_enk),
                ptr<const u32>(h->b_estart), ptr<const GEdge>(h->b_earr), ptr<const u32>(h->b_branch), nb, 0,
                ptr<u32>(h->b_cnt32), (const u64 *)nullptr, (u32 *)nullptr);
@@ -376,7 +377,7 @@ static int tip_prune(dbg_t *h) {
     if (total == 0) return DBG_OK;
     TRY(reserve(h, h->b_recs, total * 6 * 4));
     CK(cudaMemcpyAsync(h->b_off64.p, offs.data(), (nb + 1) * 8, cudaMemcpyHostToDevice, h->stream));
-    if (h->sym_bits == GEN_BITS)
+    if (h->generic)
         LAUNCH(k_g_tip_paths, blocks_for(nb), DBG_BLOCK, h->stream, ptr<const u8>(h->b_flags), ptr<const u32>(h->b_enk),
                ptr<const u32>(h->b_estart), ptr<const GEdge>(h->b_earr), ptr<const u32>(h->b_branch), nb, 1,
                ptr<u32>(h->b_cnt32), ptr<const u64>(h->b_off64), ptr<u32>(h->b_recs));
@@ -457,8 +458,8 @@ static uint32_t pass_count(dbg_t *h, uint64_t table_bytes) {
 static bool want_regions(const dbg_t *h) {
     // the region of a node is a hash of its minimizer (+ batch id): short minimizers take too few values to spread
     const ChunkGeom g = chunk_geom(h->k);
-    bool on = 2 * g.m + h->batch_bits >= 24 && h->sym_bits == 2 && !h->avoid_regions;
-    if (const char *e = getenv("DBG_B200_REGIONS")) on = atoi(e) != 0 && h->sym_bits == 2;    // tests / tuning: 0 = plain hash layout, 1 = force
+    bool on = 2 * g.m + h->batch_bits >= 24 && !h->generic && !h->avoid_regions;
+    if (const char *e = getenv("DBG_B200_REGIONS")) on = atoi(e) != 0 && !h->generic;    // tests / tuning: 0 = plain hash layout, 1 = force
     return on;
 }
 #define VB_BITS_MAX 21
@@ -1527,7 +1528,7 @@ static int order_merge_impl(dbg_t *h, const uint64_t *d_records, uint64_t n) {
 }
 
 // -------------------------------------------------------------------------------------------------
-// generic-alphabet engine (dbg_generic.cuh): construct_graph for reads over up to 32 symbols
+// generic-alphabet engine (dbg_generic.cuh): construct_graph for reads over any single-byte alphabet
 // -------------------------------------------------------------------------------------------------
 static int gen_sort_edges(dbg_t *h, uint64_t n) {
     // edge array -> sorted by (source slot, count descending, first appearance): b_earr holds the result
@@ -1577,10 +1578,10 @@ static int gen_build(dbg_t *h, const u8 *d_bases, const u64 *d_off) {
     const int e0 = ev_mark(h);
     if (h->host_bases && h->n_bases)
         CK(cudaMemcpyAsync((u8 *)d_bases, h->host_bases, h->n_bases, cudaMemcpyHostToDevice, h->stream));
-    // ---- symbols -> 5-bit codes; window count ----
-    TRY(reserve(h, h->b_lut, 256 + GEN_MAX_SYMBOLS));
+    // ---- symbols -> codes; window count ----
+    TRY(reserve(h, h->b_lut, GEN_LUT_BYTES));
     CK(cudaMemcpyAsync(h->b_lut.p, h->code_of_byte, 256, cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpyAsync(ptr<u8>(h->b_lut) + 256, h->sym_of_code, GEN_MAX_SYMBOLS, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(ptr<u8>(h->b_lut) + 256, h->sym_of_code, 257, cudaMemcpyHostToDevice, h->stream));
     TRY(reserve(h, h->b_codes, h->n_bases + 64));
     if (h->n_bases) {
         LAUNCH(k_g_encode, blocks_for(h->n_bases), DBG_BLOCK, h->stream, d_bases, h->n_bases, ptr<const u8>(h->b_lut),
@@ -1611,14 +1612,14 @@ static int gen_build(dbg_t *h, const u8 *d_bases, const u64 *d_off) {
     CKK();
     if (st.n_windows) {
         LAUNCH(k_g_insert, blocks_for(h->n_bases), DBG_BLOCK, h->stream, ptr<const u8>(h->b_codes), d_off, h->n_reads,
-               h->n_bases, k, ptr<S>(h->b_table), n_nslots, ptr<S>(h->b_etable), n_eslots, h->read_idx_base, d_ctr);
+               h->n_bases, k, h->sym_bits, ptr<S>(h->b_table), n_nslots, ptr<S>(h->b_etable), n_eslots, h->read_idx_base, d_ctr);
         CKK();
     }
     // ---- edge array in E order, CSR ----
     TRY(reserve(h, h->b_earr, (st.n_windows + 1) * sizeof(GEdge)));
     CK(cudaMemsetAsync(&d_ctr->n_list_a, 0, 8, h->stream));
     LAUNCH(k_g_edges, blocks_for(n_eslots), DBG_BLOCK, h->stream, ptr<const S>(h->b_etable), n_eslots, ptr<const S>(h->b_table),
-           n_nslots, k, ptr<GEdge>(h->b_earr), &d_ctr->n_list_a, d_ctr);
+           n_nslots, k, h->sym_bits, ptr<GEdge>(h->b_earr), &d_ctr->n_list_a, d_ctr);
     CKK();
     TRY(check_fault(h, "the generic table build"));
     if (h->ctr.overflow) return fail(h, DBG_ERR_STATE, "internal consistency fault: a table sized by its upper bound overflowed");
@@ -1682,7 +1683,7 @@ static int gen_build(dbg_t *h, const u8 *d_bases, const u64 *d_off) {
             TRY(reserve(h, h->b_readflags, h->n_reads));
             CK(cudaMemsetAsync(h->b_readflags.p, 0, h->n_reads, h->stream));
             LAUNCH(k_g_pull_reads, blocks_for(h->n_bases), DBG_BLOCK, h->stream, ptr<const u8>(h->b_codes), d_off, h->n_reads,
-                   h->n_bases, k, ptr<const S>(h->b_table), n_nslots, ptr<const u8>(h->b_flags), ptr<u8>(h->b_readflags));
+                   h->n_bases, k, h->sym_bits, ptr<const S>(h->b_table), n_nslots, ptr<const u8>(h->b_flags), ptr<u8>(h->b_readflags));
             CKK();
             CK(cudaMemcpyAsync(h->read_flags.data(), h->b_readflags.p, h->n_reads, cudaMemcpyDeviceToHost, h->stream));
             CK(cudaStreamSynchronize(h->stream));
@@ -1804,7 +1805,7 @@ static int walk_impl(dbg_t *h, int stop_at_branch) {
     std::vector<std::pair<u32, u32>> jindex;           // (slot, index in branch list), sorted by slot
     if (enumerate) {
         joff.assign(nb + 1, 0);
-        if (h->sym_bits == GEN_BITS) {                 // any number of kept successors: their counts first
+        if (h->generic) {                 // any number of kept successors: their counts first
             std::vector<u32> nk(nb);
             TRY(reserve(h, h->b_cnt32, nb * 4));
             LAUNCH(k_g_gather_u32, blocks_for(nb), DBG_BLOCK, h->stream, ptr<const u32>(h->b_enk), ptr<const u32>(h->b_branch),
@@ -2213,22 +2214,26 @@ DBG_API int dbg_create_alpha(dbg_t **out, int device, int k, const uint8_t *symb
     *out = nullptr;
     if (!symbols || n_symbols < 1 || n_symbols > GEN_MAX_SYMBOLS)
         return fail(nullptr, DBG_ERR_ARG, "an alphabet has 1 .. %d symbols (got %d)", GEN_MAX_SYMBOLS, n_symbols);
-    if (k < 1 || k > GEN_MAX_K)
-        return fail(nullptr, DBG_ERR_ARG, "k = %d out of range for 5-bit symbols (1..%d)", k, GEN_MAX_K);
+    const int gb = gen_bits_for(n_symbols);
+    if (k < 1 || k > gen_max_k(gb))
+        return fail(nullptr, DBG_ERR_ARG, "k = %d out of range for an alphabet of %d symbols (%d-bit codes: 1..%d)", k, n_symbols,
+                    gb, gen_max_k(gb));
     uint8_t code_of[256];
     memset(code_of, 0xFF, sizeof code_of);
     for (int i = 0; i < n_symbols; i++) {
         if (code_of[symbols[i]] != 0xFF) return fail(nullptr, DBG_ERR_ARG, "symbol %d appears twice in the alphabet", (int)symbols[i]);
         code_of[symbols[i]] = (uint8_t)i;
     }
-    const int rc = dbg_create_ex(out, device, 1, 2);                   // 128-bit keys; k is set below (5 bits a symbol)
+    const int rc = dbg_create_ex(out, device, 1, 2);                   // 128-bit keys; k is set below (gb bits a symbol)
     if (rc != DBG_OK) return rc;
     dbg_t *h = *out;
     h->k = k;
-    h->sym_bits = GEN_BITS;
+    h->generic = true;
+    h->sym_bits = gb;
     h->n_symbols = n_symbols;
     memset(h->sym_of_code, '?', sizeof h->sym_of_code);
     memcpy(h->sym_of_code, symbols, (size_t)n_symbols);
+    h->sym_of_code[256] = (uint8_t)gb;
     memcpy(h->code_of_byte, code_of, sizeof code_of);
     return DBG_OK;
 }
@@ -2373,7 +2378,7 @@ DBG_API int dbg_support_scores(dbg_t *h, const uint8_t *reads, const uint64_t *r
 
 DBG_API int dbg_set_min_count(dbg_t *h, uint32_t min_count) {
     if (!h) return DBG_ERR_ARG;
-    if (h->sym_bits != 2 && min_count > 1) return fail(h, DBG_ERR_ARG, "min_count exists for the DNA engine only");
+    if (h->generic && min_count > 1) return fail(h, DBG_ERR_ARG, "min_count exists for the DNA engine only");
     h->min_count = min_count < 1 ? 1 : min_count;
     return DBG_OK;
 }
@@ -2433,7 +2438,7 @@ static int build_device_common(dbg_t *h, const uint8_t *d_bases, const uint64_t 
     h->segments.clear();
     CK(cudaMemsetAsync(h->b_ctr.p, 0, sizeof(DevCounters), h->stream));
     h->table_ready = false;
-    if (h->sym_bits == GEN_BITS) {
+    if (h->generic) {
         if (d_read_batch || (flags & (DBG_TABLE_ONLY | DBG_CHUNKS_ONLY)))
             return fail(h, DBG_ERR_ARG, "batched and multi-GPU builds exist for the DNA engine only");
         return gen_build(h, (const u8 *)d_bases, (const u64 *)d_read_off);
@@ -2551,7 +2556,7 @@ DBG_API int dbg_build_batched_device(dbg_t *h, const uint8_t *d_bases, const uin
 // DBG_BOTH_STRANDS: build from the reads on the device followed by their reverse complements (read n + i = rc of read i)
 static int build_both_strands(dbg_t *h, const uint8_t *d_bases, const uint64_t *d_read_off, uint64_t n_reads, uint64_t n_bases,
                               uint64_t read_idx_base, double threshold, uint32_t flags) {
-    if (h->sym_bits != 2) return fail(h, DBG_ERR_ARG, "DBG_BOTH_STRANDS exists for the DNA engine only");
+    if (h->generic) return fail(h, DBG_ERR_ARG, "DBG_BOTH_STRANDS exists for the DNA engine only");
     if (read_idx_base || (flags & (DBG_TABLE_ONLY | DBG_CHUNKS_ONLY)))
         return fail(h, DBG_ERR_ARG, "DBG_BOTH_STRANDS is a single-handle build (read_idx_base 0, no DBG_TABLE_ONLY / DBG_CHUNKS_ONLY)");
     if (2 * n_reads >= 0xFFFFFFFFull) return fail(h, DBG_ERR_OVERFLOW, "read index exceeds 32 bits");
@@ -2591,7 +2596,7 @@ DBG_API int dbg_build(dbg_t *h, const uint8_t *bases, const uint64_t *read_off, 
     return rc;
 }
 
-#define NEED_TABLE() do { if (!h) return DBG_ERR_ARG; if (h->sym_bits != 2) return fail(h, DBG_ERR_STATE, "%s exists for the DNA engine only", __func__); if (!h->table_ready) return fail(h, DBG_ERR_STATE, "%s needs a node table (dbg_build* or dbg_table_reset first)", __func__); } while (0)
+#define NEED_TABLE() do { if (!h) return DBG_ERR_ARG; if (h->generic) return fail(h, DBG_ERR_STATE, "%s exists for the DNA engine only", __func__); if (!h->table_ready) return fail(h, DBG_ERR_STATE, "%s needs a node table (dbg_build* or dbg_table_reset first)", __func__); } while (0)
 
 DBG_API int dbg_graph_stage(dbg_t *h, int stage, double threshold, uint32_t flags) {
     NEED_TABLE();
@@ -2630,7 +2635,7 @@ DBG_API int dbg_export_records(dbg_t *h, uint32_t n_parts, const uint64_t *count
 
 DBG_API int dbg_table_reset(dbg_t *h, uint64_t expected_nodes) {
     if (!h) return DBG_ERR_ARG;
-    if (h->sym_bits != 2) return fail(h, DBG_ERR_STATE, "dbg_table_reset exists for the DNA engine only");
+    if (h->generic) return fail(h, DBG_ERR_STATE, "dbg_table_reset exists for the DNA engine only");
     CK(cudaSetDevice(h->device));
     return DISPATCH(table_reset_impl, h, expected_nodes);
 }
@@ -2655,7 +2660,7 @@ DBG_API int dbg_order_merge(dbg_t *h, const uint64_t *d_records, uint64_t n) {
     return DISPATCH(order_merge_impl, h, d_records, n);
 }
 
-#define NEED_CHUNKS() do { if (!h) return DBG_ERR_ARG; if (h->sym_bits != 2) return fail(h, DBG_ERR_STATE, "%s exists for the DNA engine only", __func__); if (!h->chunks_valid) return fail(h, DBG_ERR_STATE, "%s needs a chunk table (dbg_build* with DBG_CHUNKS_ONLY, or dbg_chunk_table_reset, first)", __func__); } while (0)
+#define NEED_CHUNKS() do { if (!h) return DBG_ERR_ARG; if (h->generic) return fail(h, DBG_ERR_STATE, "%s exists for the DNA engine only", __func__); if (!h->chunks_valid) return fail(h, DBG_ERR_STATE, "%s needs a chunk table (dbg_build* with DBG_CHUNKS_ONLY, or dbg_chunk_table_reset, first)", __func__); } while (0)
 
 DBG_API int dbg_chunk_record_words(const dbg_t *h) { return h ? (h->W == 1 ? 4 : 8) : 0; }
 
@@ -2675,7 +2680,7 @@ DBG_API int dbg_chunk_export_records(dbg_t *h, uint32_t n_parts, const uint64_t 
 
 DBG_API int dbg_chunk_table_reset(dbg_t *h, uint64_t expected_chunks) {
     if (!h) return DBG_ERR_ARG;
-    if (h->sym_bits != 2) return fail(h, DBG_ERR_STATE, "dbg_chunk_table_reset exists for the DNA engine only");
+    if (h->generic) return fail(h, DBG_ERR_STATE, "dbg_chunk_table_reset exists for the DNA engine only");
     CK(cudaSetDevice(h->device));
     return DISPATCH(chunk_table_reset_impl, h, expected_chunks);
 }
@@ -2746,7 +2751,7 @@ DBG_API int dbg_export_nodes(dbg_t *h, uint32_t *node_id, uint64_t *key_lo, uint
 
 DBG_API int dbg_export_edges(dbg_t *h, uint32_t *src_id, uint32_t *dst_id, uint8_t *symbol, uint32_t *count, uint8_t *kept) {
     NEED_BUILT();
-    if (h->sym_bits != GEN_BITS) return fail(h, DBG_ERR_STATE, "dbg_export_edges is the generic-alphabet engine's export; the DNA engine "
+    if (!h->generic) return fail(h, DBG_ERR_STATE, "dbg_export_edges is the generic-alphabet engine's export; the DNA engine "
                                              "reports successor counts per node (dbg_export_nodes)");
     const uint64_t n = h->n_earr;
     if (n == 0) return DBG_OK;
@@ -2911,7 +2916,7 @@ DBG_API int dbg_twin_nodes(dbg_t *h, const uint32_t *node_id, uint64_t n, uint32
     NEED_BUILT();
     if (n == 0) return DBG_OK;
     if (!node_id) return fail(h, DBG_ERR_ARG, "NULL input");
-    if (h->sym_bits == GEN_BITS || h->batch_bits) return fail(h, DBG_ERR_STATE, "dbg_twin_nodes: DNA handles, unbatched builds");
+    if (h->generic || h->batch_bits) return fail(h, DBG_ERR_STATE, "dbg_twin_nodes: DNA handles, unbatched builds");
     for (uint64_t i = 0; i < n; i++)
         if (node_id[i] >= h->n_slots) return fail(h, DBG_ERR_ARG, "node id %u out of range", node_id[i]);
     CK(cudaSetDevice(h->device));
@@ -2946,7 +2951,7 @@ DBG_API int dbg_degree_balance(dbg_t *h, const uint32_t *node_id, uint64_t n, ui
     NEED_BUILT();
     if (n == 0) return DBG_OK;
     if (!node_id) return fail(h, DBG_ERR_ARG, "NULL input");
-    if (h->sym_bits == GEN_BITS) return fail(h, DBG_ERR_STATE, "dbg_degree_balance: DNA handles only (a generic-alphabet handle lists its edges with dbg_export_edges)");
+    if (h->generic) return fail(h, DBG_ERR_STATE, "dbg_degree_balance: DNA handles only (a generic-alphabet handle lists its edges with dbg_export_edges)");
     if (h->shard_n > 1) return fail(h, DBG_ERR_STATE, "dbg_degree_balance needs the complete graph, this handle holds a shard");
     for (uint64_t i = 0; i < n; i++)
         if (node_id[i] >= h->n_slots) return fail(h, DBG_ERR_ARG, "node id %u out of range", node_id[i]);
@@ -2963,9 +2968,9 @@ static int lookup_impl(dbg_t *h, const uint8_t *q, const uint32_t *batch, uint64
     TRY(reserve(h, s[2], n * 4));
     CK(cudaMemcpyAsync(s[0].p, q, bytes, cudaMemcpyHostToDevice, h->stream));
     if (batch) CK(cudaMemcpyAsync(s[2].p, batch, n * 4, cudaMemcpyHostToDevice, h->stream));
-    if (h->sym_bits == GEN_BITS)
+    if (h->generic)
         LAUNCH(k_g_lookup_edges, blocks_for(n), DBG_BLOCK, h->stream, ptr<const Slot<2>>(h->b_etable), h->n_eslots, h->k,
-               ptr<const u8>(h->b_lut), ptr<const u8>(s[0]), n, ptr<u32>(s[1]));
+               h->sym_bits, ptr<const u8>(h->b_lut), ptr<const u8>(s[0]), n, ptr<u32>(s[1]));
     else
     LAUNCH(k_lookup_edges<W>, blocks_for(n), DBG_BLOCK, h->stream, ptr<const Slot<W>>(h->b_table), geom_of(h), h->k,
            ptr<const u8>(s[0]), batch ? ptr<const u32>(s[2]) : (const u32 *)nullptr, n, ptr<u32>(s[1]));
@@ -2988,7 +2993,7 @@ DBG_API int dbg_lookup_edges_batched(dbg_t *h, const uint8_t *kplus1mers, const 
     NEED_BUILT();
     if (n == 0) return DBG_OK;
     if (!kplus1mers || !counts || !batch) return fail(h, DBG_ERR_ARG, "NULL argument");
-    if (h->sym_bits != 2 || (!h->batch_bits && h->n_batches == 0)) return fail(h, DBG_ERR_STATE, "the graph was not built by dbg_build_batched");
+    if (h->generic || (!h->batch_bits && h->n_batches == 0)) return fail(h, DBG_ERR_STATE, "the graph was not built by dbg_build_batched");
     for (uint64_t i = 0; i < n; i++)
         if (batch[i] >= h->n_batches) return fail(h, DBG_ERR_ARG, "batch id %u out of range", batch[i]);
     CK(cudaSetDevice(h->device));
@@ -3074,7 +3079,7 @@ static int materialize_impl(dbg_t *h, const uint64_t *idx, uint64_t n, char *buf
     TRY(ensure_lift(h));
     LAUNCH((k_materialize<W>), jobs.size(), LIFT_BLOCK, h->stream, ptr<const Slot<W>>(h->b_table), h->n_slots, h->k,
            ptr<const u32>(h->b_succ), ptr<const u32>(h->b_up),
-           h->sym_bits == GEN_BITS ? ptr<const u8>(h->b_lut) + 256 : (const u8 *)nullptr, ptr<const SegJob>(s[0]), ptr<char>(s[1]));
+           h->generic ? ptr<const u8>(h->b_lut) + 256 : (const u8 *)nullptr, ptr<const SegJob>(s[0]), ptr<char>(s[1]));
     CKK();
     // strings may be requested with gaps between them: copy each back to where the caller wants it
     uint64_t lo = off[0], hi = 0;
@@ -3116,7 +3121,7 @@ static int scores_impl(dbg_t *h, const uint64_t *idx, uint64_t n, uint64_t *scor
     CK(cudaMemcpyAsync(s[1].p, nodes.data(), nodes.size() * 4, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(s[2].p, jobs.data(), n * sizeof(ScoreJob), cudaMemcpyHostToDevice, h->stream));
     TRY(ensure_lift(h));
-    const bool gen = h->sym_bits == GEN_BITS;
+    const bool gen = h->generic;
     LAUNCH((k_scores<W>), n, LIFT_BLOCK, h->stream, ptr<const Slot<W>>(h->b_table), h->n_slots, ptr<const u16>(h->b_kept),
            ptr<const u32>(h->b_succ), ptr<const u32>(h->b_up), gen ? ptr<const GEdge>(h->b_earr) : (const GEdge *)nullptr,
            gen ? ptr<const u32>(h->b_estart) : (const u32 *)nullptr, gen ? ptr<const u32>(h->b_edeg) : (const u32 *)nullptr,

@@ -1,12 +1,13 @@
-// dbg_generic.cuh -- the same hot path for ANY alphabet of up to 32 symbols (5-bit codes).
+// dbg_generic.cuh -- the same hot path for ANY single-byte alphabet (up to 255 symbols, codes of 1 .. 8 bits).
 //
 // The reference treats reads as opaque strings (debruijn.py works on any characters) and its real inputs
 // are de-novo PEPTIDES (II_assembleFromReads.py:43-47, :55), so the drop-in must take them.  The 2-bit
 // engine (dbg_chunks.cuh / dbg_kernels.cuh) is built around four successor counters per node; with 20+
 // letters a node can have 20+ distinct successors, so this engine keeps the graph edge-centric:
 //
-//   node table   Slot<2>: key = k symbols x 5 bits (k <= 24, 120 bits), tag = first occurrence
-//   edge table   Slot<2>: key = the (k+1)-mer (<= 125 bits), tag = first appearance of the edge
+//   node table   Slot<2>: key = k symbols x b bits, b = ceil(log2(symbols)) chosen per handle (peptides: 5 bits,
+//                k <= 24; ACGT + N: 3 bits, k <= 40; 8 bits: k <= 14), tag = first occurrence
+//   edge table   Slot<2>: key = the (k+1)-mer (b (k + 1) <= 125 bits), tag = first appearance of the edge
 //                (Counter.most_common tie order, debruijn.py:159-164), cnt[0] = multiplicity
 //                = edge_count_table[(k+1)-mer] (debruijn.py:213-222)
 //   edge array   occupied edge slots compacted and sorted by (source node, count desc, first appearance):
@@ -20,39 +21,39 @@
 #pragma once
 #include "dbg_kernels.cuh"
 
-#define GEN_BITS 5
-#define GEN_MAX_SYMBOLS 32
-#define GEN_MAX_K 24                       // 5 (k + 1) <= 125: the edge key keeps the all-ones pattern free
+#define GEN_MAX_SYMBOLS 255                // code 0xFF = "not a symbol of this alphabet"
+#define GEN_KEY_BITS 125                   // b (k + 1) <= 125: the edge key keeps the all-ones pattern free
+#define GEN_LUT_BYTES (256 + 256 + 1)      // byte -> code | code -> byte | b  (device copy of the handle's alphabet)
 
-DBG_HD K128 gkey_push(K128 key, u32 code) {
+DBG_HD int gen_bits_for(int n_symbols) {   // smallest code width that tells n_symbols apart
+    int b = 1;
+    while ((1 << b) < n_symbols) b++;
+    return b;
+}
+DBG_HD int gen_max_k(int gb) { const int m = GEN_KEY_BITS / gb - 1; return m < 63 ? m : 63; }   // (63: what the contig / label buffers of the ABI are sized for)
+
+DBG_HD K128 gkey_push(K128 key, u32 code, int gb) {
     K128 r;
-    r.hi = (key.hi << GEN_BITS) | (key.lo >> (64 - GEN_BITS));
-    r.lo = (key.lo << GEN_BITS) | (u64)code;
+    r.hi = (key.hi << gb) | (key.lo >> (64 - gb));
+    r.lo = (key.lo << gb) | (u64)code;
     return r;
 }
-DBG_HD K128 gkey_mask(int n) {             // low 5 n bits, n <= 25
+DBG_HD K128 gkey_mask(int n, int gb) {     // low gb n bits (<= 125)
     K128 r;
-    const int b = GEN_BITS * n;
+    const int b = gb * n;
     if (b >= 64) { r.lo = ~0ULL; r.hi = b == 64 ? 0ULL : ((1ULL << (b - 64)) - 1); }
     else { r.lo = (1ULL << b) - 1; r.hi = 0; }
     return r;
 }
 DBG_HD K128 gkey_and(K128 a, K128 m) { K128 r; r.lo = a.lo & m.lo; r.hi = a.hi & m.hi; return r; }
-DBG_HD K128 gkey_drop_last(K128 key) {     // (k+1)-mer -> its first k symbols
+DBG_HD K128 gkey_drop_last(K128 key, int gb) {     // (k+1)-mer -> its first k symbols
     K128 r;
-    r.lo = (key.lo >> GEN_BITS) | (key.hi << (64 - GEN_BITS));
-    r.hi = key.hi >> GEN_BITS;
+    r.lo = (key.lo >> gb) | (key.hi << (64 - gb));
+    r.hi = key.hi >> gb;
     return r;
 }
-DBG_HD u32 gkey_symbol(K128 key, int n, int j) {      // symbol j (0 = first) of an n-symbol key
-    const int sh = GEN_BITS * (n - 1 - j);
-    if (sh >= 64) return (u32)(key.hi >> (sh - 64)) & 31u;
-    u64 v = key.lo >> sh;
-    if (sh + GEN_BITS > 64) v |= key.hi << (64 - sh);
-    return (u32)v & 31u;
-}
 
-// ASCII -> 5-bit codes through the handle's table (0xFF = not a symbol of this alphabet)
+// bytes -> symbol codes through the handle's table (0xFF = not a symbol of this alphabet)
 __global__ void __launch_bounds__(DBG_BLOCK) k_g_encode(const u8 *__restrict__ bases, u64 n_bases,
                                                         const u8 *__restrict__ lut, u8 *__restrict__ codes,
                                                         DevCounters *ctr) {
@@ -75,8 +76,8 @@ DBG_D u64 g_read_of(const u64 *__restrict__ off, u64 n_reads, u64 p) {
 
 // the window loop, debruijn.py:123-144: one thread per stream position
 __global__ void __launch_bounds__(DBG_BLOCK) k_g_insert(const u8 *__restrict__ codes, const u64 *__restrict__ off,
-                                                        u64 n_reads, u64 n_bases, int k, Slot<2> *nodes, u64 n_nslots,
-                                                        Slot<2> *edges, u64 n_eslots, u64 read_idx_base,
+                                                        u64 n_reads, u64 n_bases, int k, int gb, Slot<2> *nodes,
+                                                        u64 n_nslots, Slot<2> *edges, u64 n_eslots, u64 read_idx_base,
                                                         DevCounters *ctr) {
     const u64 p = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (p < n_bases) {
@@ -85,14 +86,14 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_g_insert(const u8 *__restrict__ c
         const u64 len = re - rs, pos = p - rs;
         if (len > (u64)k && pos <= len - (u64)k) {                      // a node occurrence (debruijn.py:126-127)
             K128 key = zero_key<2>();
-            for (int j = 0; j < k; j++) key = gkey_push(key, codes[p + j]);
+            for (int j = 0; j < k; j++) key = gkey_push(key, codes[p + j], gb);
             const u64 tag = ((read_idx_base + r) << 32) | pos;
             u64 seen;
             const u64 idx = table_upsert_tag<2>(nodes, n_nslots, slot_home(hash32_key(key), n_nslots), key, &seen);
             if (idx == NONE64) ctr->overflow = 1;
             else if (tag < seen) atomicMin(&nodes[idx].tag, tag);
             if (pos < len - (u64)k) {                                    // ... with a successor (debruijn.py:128-136)
-                const K128 ekey = gkey_push(key, codes[p + k]);
+                const K128 ekey = gkey_push(key, codes[p + k], gb);
                 const u64 e = table_upsert_tag<2>(edges, n_eslots, slot_home(hash32_key(ekey), n_eslots), ekey, &seen);
                 if (e == NONE64) ctr->overflow = 1;
                 else {
@@ -106,7 +107,7 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_g_insert(const u8 *__restrict__ c
 
 // occupied edge slots -> edge array (unordered)
 __global__ void __launch_bounds__(DBG_BLOCK) k_g_edges(const Slot<2> *__restrict__ etable, u64 n_eslots,
-                                                       const Slot<2> *__restrict__ nodes, u64 n_nslots, int k,
+                                                       const Slot<2> *__restrict__ nodes, u64 n_nslots, int k, int gb,
                                                        GEdge *__restrict__ out, u64 *cursor, DevCounters *ctr) {
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     K128 ekey = empty_key<2>();
@@ -120,12 +121,12 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_g_edges(const Slot<2> *__restrict
     base = __shfl_sync(0xFFFFFFFFu, base, 0);
     if (!have) return;
     GEdge e;
-    const u64 s = table_find<2>(nodes, n_nslots, gkey_drop_last(ekey));
-    const u64 d = table_find<2>(nodes, n_nslots, gkey_and(ekey, gkey_mask(k)));
+    const u64 s = table_find<2>(nodes, n_nslots, gkey_drop_last(ekey, gb));
+    const u64 d = table_find<2>(nodes, n_nslots, gkey_and(ekey, gkey_mask(k, gb)));
     if (s == NONE64 || d == NONE64) raise_fault(ctr, FAULT_SUCC_MISSING, (u32)i);
     e.src = (u32)s; e.dst = (u32)d;
     e.cnt = etable[i].cnt[0];
-    e.sym = (u32)(ekey.lo & 31u);
+    e.sym = (u32)ekey.lo & ((1u << gb) - 1u);
     e.first = etable[i].tag;
     out[base + __popc(b & ((1u << lane) - 1))] = e;
 }
@@ -232,7 +233,7 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_g_tip_paths(const u8 *__restrict_
 
 // pull_out_read (debruijn.py:274-278): a read is pulled iff one of its k-mers is a branch node
 __global__ void __launch_bounds__(DBG_BLOCK) k_g_pull_reads(const u8 *__restrict__ codes, const u64 *__restrict__ off,
-                                                            u64 n_reads, u64 n_bases, int k,
+                                                            u64 n_reads, u64 n_bases, int k, int gb,
                                                             const Slot<2> *__restrict__ nodes, u64 n_nslots,
                                                             const u8 *__restrict__ flags, u8 *read_flags) {
     const u64 p = (u64)blockIdx.x * blockDim.x + threadIdx.x;
@@ -241,7 +242,7 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_g_pull_reads(const u8 *__restrict
     const u64 rs = __ldg(off + r), re = __ldg(off + r + 1);
     if (re - rs < (u64)k || p - rs > re - rs - (u64)k) return;
     K128 key = zero_key<2>();
-    for (int j = 0; j < k; j++) key = gkey_push(key, codes[p + j]);
+    for (int j = 0; j < k; j++) key = gkey_push(key, codes[p + j], gb);
     const u64 idx = table_find<2>(nodes, n_nslots, key);
     if (idx != NONE64 && (flags[idx] & F_BRANCH)) read_flags[r] = 1;
 }
@@ -277,7 +278,7 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_g_junctions(const u8 *__restrict_
 
 // edge_count_table[(k+1)-mer] for ASCII queries laid back to back; 0 = absent
 __global__ void __launch_bounds__(DBG_BLOCK) k_g_lookup_edges(const Slot<2> *__restrict__ etable, u64 n_eslots, int k,
-                                                              const u8 *__restrict__ lut, const u8 *__restrict__ q, u64 n,
+                                                              int gb, const u8 *__restrict__ lut, const u8 *__restrict__ q, u64 n,
                                                               u32 *__restrict__ out) {
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -287,7 +288,7 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_g_lookup_edges(const Slot<2> *__r
     for (int j = 0; j <= k; j++) {
         const u8 c = lut[s[j]];
         bad |= c == 0xFFu;
-        key = gkey_push(key, c & 31u);
+        key = gkey_push(key, bad ? 0u : (u32)c, gb);
     }
     u32 res = 0;
     if (!bad) {

@@ -935,21 +935,23 @@ DBG_D u32 lift_to(const u32 *__restrict__ succ, const u32 *__restrict__ up, u64 
     return v;
 }
 
-// last symbol / symbol i of a node label as a character: 2-bit DNA keys or 5-bit generic keys (lut = code -> byte)
+// last symbol / symbol i of a node label as a character: 2-bit DNA keys, or generic keys of lut[256] bits a symbol
+// (lut = the generic engine's code -> byte table followed by its code width, dbg_generic.cuh GEN_LUT_BYTES)
 template <int W> DBG_D char label_last_char(typename KeyOf<W>::type key, const u8 *__restrict__ lut) {
-    if (lut) return (char)lut[(u32)key_lo64(key) & 31u];
+    if (lut) return (char)lut[(u32)key_lo64(key) & ((1u << lut[256]) - 1u)];
     return (char)((0x54474341u >> (8 * key_last_base(key))) & 0xFFu);
 }
-DBG_D u32 key_symbol5(u64, int, int) { return 0; }                   // 64-bit keys are DNA only
-DBG_D u32 key_symbol5(K128 key, int n, int j) {
-    const int sh = 5 * (n - 1 - j);
-    if (sh >= 64) return (u32)(key.hi >> (sh - 64)) & 31u;
+DBG_D u32 key_symbol_g(u64, int, int, int) { return 0; }             // 64-bit keys are DNA only
+DBG_D u32 key_symbol_g(K128 key, int n, int j, int gb) {
+    const int sh = gb * (n - 1 - j);
+    const u32 mask = (1u << gb) - 1u;
+    if (sh >= 64) return (u32)(key.hi >> (sh - 64)) & mask;
     u64 x = key.lo >> sh;
-    if (sh + 5 > 64) x |= key.hi << (64 - sh);
-    return (u32)x & 31u;
+    if (sh + gb > 64) x |= key.hi << (64 - sh);
+    return (u32)x & mask;
 }
 template <int W> DBG_D char label_char(typename KeyOf<W>::type key, int k, int i, const u8 *__restrict__ lut) {
-    if (lut) return (char)lut[key_symbol5(key, k, i)];
+    if (lut) return (char)lut[key_symbol_g(key, k, i, (int)lut[256])];
     return (char)((0x54474341u >> (8 * key_base(key, k, i))) & 0xFFu);
 }
 

@@ -59,11 +59,14 @@ def decode_keys(key_lo, key_hi, k, bits=2, symbols=_ALPHA):
     codes[:, low] = ((lo >> shifts[low].astype(np.uint64)) & mask).astype(np.uint8)
     if high.any():
         codes[:, high] = ((hi >> (shifts[high] - 64).astype(np.uint64)) & mask).astype(np.uint8)
-    for j in np.nonzero(~low & ~high)[0]:           # straddles the two words (5-bit symbols only)
+    for j in np.nonzero(~low & ~high)[0]:           # straddles the two words (generic-alphabet keys only)
         sh = int(shifts[j])
         codes[:, j] = (((lo[:, 0] >> np.uint64(sh)) | (hi[:, 0] << np.uint64(64 - sh))) & mask).astype(np.uint8)
     chars = np.asarray(symbols, dtype=np.uint8)[codes]
-    return chars.view('S%d' % k).ravel().astype('U%d' % k).tolist()
+    if symbols is _ALPHA:
+        return chars.view('S%d' % k).ravel().astype('U%d' % k).tolist()
+    text = chars.tobytes().decode('latin-1')        # any byte values: NUL, blanks and 0x80 .. 0xFF are symbols like the others
+    return [text[i:i + k] for i in range(0, n * k, k)]
 
 
 def _default_device():
@@ -79,12 +82,14 @@ class Graph:
     called again with new reads and keeps its HBM."""
 
     def __init__(self, k, device=None, lib=None, key_words=0, alphabet=None):
-        """`alphabet` = bytes of up to 32 distinct symbols: the generic-alphabet engine (peptides; k <= 24).
+        """`alphabet` = bytes of up to 255 distinct symbols: the generic-alphabet engine, b = ceil(log2(symbols)) bits a
+        symbol and b (k + 1) <= 125 (peptides: 5 bits, k <= 24; ACGT + N: 3 bits, k <= 40; 8 bits: k <= 14).
         None = the DNA engine (ACGT, k <= 63)."""
         self.lib = lib or N.get()
         self.k = int(k)
         self.device = _default_device() if device is None else int(device)
         self.alphabet = bytes(alphabet) if alphabet is not None else None
+        self.sym_bits = max(1, (len(self.alphabet) - 1).bit_length()) if self.alphabet is not None else 2
         h = C.c_void_p()
         if self.alphabet is not None:
             rc = self.lib.dbg_create_alpha(C.byref(h), self.device, self.k, self.alphabet, len(self.alphabet))
@@ -396,7 +401,7 @@ class Graph:
 
     def _decode(self, lo, hi):
         if self.alphabet is not None:
-            return decode_keys(lo, hi, self.k, 5, np.frombuffer(self.alphabet.ljust(32, b'?'), dtype=np.uint8))
+            return decode_keys(lo, hi, self.k, self.sym_bits, np.frombuffer(self.alphabet.ljust(256, b'?'), dtype=np.uint8))
         return decode_keys(lo, hi, self.k)
 
     def labels(self):
@@ -533,7 +538,7 @@ class Graph:
         buf = np.empty(total, np.uint8)
         self.lib.check(self.h, self.lib.dbg_materialize(self.h, idx.ctypes.data, len(idx), buf.ctypes.data,
                                                         off.ctypes.data))
-        raw = buf.tobytes().decode('ascii')
+        raw = buf.tobytes().decode('latin-1')
         o = off.tolist()
         return [raw[o[i]:o[i + 1]] for i in range(len(idx))]
 

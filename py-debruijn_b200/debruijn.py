@@ -14,8 +14,9 @@ only packs the read list, calls the library and wraps the results.  ``vertices``
 ``edge_count_table`` are lazy mappings backed by the graph in HBM (II never inspects the first
 two and only indexes the third); they compare equal to the reference's dicts when materialised.
 There is no CPU path: without the built library or a CUDA device these calls raise.  DNA reads
-(ACGT) run on the 2-bit engine, 1 <= k <= 63; reads over any other alphabet of up to 32 characters
-(peptides) on the 5-bit generic engine, 1 <= k <= 24.
+(ACGT) run on the 2-bit engine, 1 <= k <= 63; reads over any other alphabet of single-byte characters (peptides,
+DNA with N / IUPAC codes, text) on the generic engine, b = ceil(log2(distinct characters)) bits a symbol and
+b (k + 1) <= 125: peptides k <= 24, ACGT + N k <= 40, 255 distinct characters k <= 14.
 """
 from __future__ import annotations
 
@@ -57,9 +58,8 @@ def _graph_for(reads, k, threshold, final, min_count=1, both_strands=False):
     if both_strands:
         raise ValueError('dbg_b200: both_strands needs DNA reads (ACGT)')
     symbols = np.flatnonzero(np.bincount(packed[0], minlength=256)).astype(np.uint8)
-    if len(symbols) > 32:
-        raise ValueError('dbg_b200: the reads use %d distinct characters; the GPU path handles alphabets of up to 32'
-                         % len(symbols))
+    if len(symbols) > 255:
+        raise ValueError('dbg_b200: the reads use all 256 byte values; the GPU path handles alphabets of up to 255')
     g = Graph(k, alphabet=symbols.tobytes())
     return g.build(reads, threshold=threshold, final=final, packed=packed, min_count=min_count)
 

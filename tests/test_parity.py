@@ -102,15 +102,15 @@ def test_generic_alphabet_vs_oracle(backend):
 
 
 def test_invalid_input_raises(backend):
-    """No CPU fallback and no silent truncation: more than 32 distinct characters, or k beyond what the
-    engine's keys hold, raise."""
+    """No CPU fallback and no silent truncation: characters that are not single bytes, all 256 byte values at once, or
+    k beyond what the engine's keys hold, raise (tests/test_alphabets.py has the alphabets that do work)."""
     import debruijn as db
-    import string
-    many = string.ascii_letters + string.digits                      # 62 distinct characters
     with pytest.raises(ValueError):
-        db.construct_graph([many, many[::-1]], 3, 2)
+        db.construct_graph(['\u65e5\u672c\u8a9e\u306e\u30c6\u30ad\u30b9\u30c8'], 3, 2)
     with pytest.raises(ValueError):
-        db.construct_graph(['EVQLVESGGALVQPGGSLRLSCAASGFTFS' * 2], 25, 2)     # 5-bit symbols: k <= 24
+        db.construct_graph(['EVQLVESGGALVQPGGSLRLSCAASGFTFS' * 3], 31, 2)     # 12 letters, 4-bit codes: k <= 30
+    with pytest.raises(ValueError):
+        db.construct_graph(['ACDEFGHIKLMNPQRSTVWY' * 3], 25, 2)               # 20 letters, 5-bit codes: k <= 24
     with pytest.raises(ValueError):
         db.construct_graph(['ACGT' * 40], 64, 2)
 
