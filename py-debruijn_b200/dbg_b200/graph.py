@@ -30,6 +30,10 @@ class Node:
         self.outdegree = 0
 
 
+class NotSingleByteError(ValueError):
+    """The reads hold characters beyond latin-1 (debruijn._graph_for then gives every character a private byte)."""
+
+
 def pack_reads(reads):
     """list[str] -> (uint8[n_bases] ASCII, uint64[n+1] offsets); II hands over a plain list."""
     n = len(reads)
@@ -39,7 +43,7 @@ def pack_reads(reads):
     try:
         data = ''.join(reads).encode('latin-1')
     except UnicodeEncodeError as e:
-        raise ValueError('dbg_b200: reads must be strings of single-byte characters') from e
+        raise NotSingleByteError('dbg_b200: reads must be strings of single-byte characters') from e
     bases = np.frombuffer(data, dtype=np.uint8)
     return bases, off
 
@@ -81,13 +85,21 @@ class Graph:
     """One de Bruijn graph resident on one GPU (one ``dbg_t``).  Re-usable: ``build`` may be
     called again with new reads and keeps its HBM."""
 
-    def __init__(self, k, device=None, lib=None, key_words=0, alphabet=None):
+    def __init__(self, k, device=None, lib=None, key_words=0, alphabet=None, charset=None):
         """`alphabet` = bytes of up to 255 distinct symbols: the generic-alphabet engine, b = ceil(log2(symbols)) bits a
         symbol and b (k + 1) <= 125 (peptides: 5 bits, k <= 24; ACGT + N: 3 bits, k <= 40; 8 bits: k <= 14).
-        None = the DNA engine (ACGT, k <= 63)."""
+        None = the DNA engine (ACGT, k <= 63).  `charset` = a list of up to 255 characters for reads that are not
+        latin-1 (any Unicode text, as the reference takes): character i travels as byte value i, the alphabet is
+        bytes(range(len(charset))) and every string that comes back (labels, contigs, edge keys) is mapped back."""
         self.lib = lib or N.get()
         self.k = int(k)
         self.device = _default_device() if device is None else int(device)
+        self._chars_in = self._chars_out = None
+        if charset is not None:
+            charset = list(charset)
+            alphabet = bytes(range(len(charset)))
+            self._chars_in = {ord(c): i for i, c in enumerate(charset)}
+            self._chars_out = {i: c for i, c in enumerate(charset)}
         self.alphabet = bytes(alphabet) if alphabet is not None else None
         self.sym_bits = max(1, (len(self.alphabet) - 1).bit_length()) if self.alphabet is not None else 2
         h = C.c_void_p()
@@ -399,9 +411,21 @@ class Graph:
             b = (lo >> np.uint64(sh)) | (hi << np.uint64(64 - sh))
         return (b & np.uint64(0xFFFFFFFF)).astype(np.uint32)
 
+    def text_in(self, s):
+        """A caller's string as the graph holds it (identity unless the handle was made with `charset`); a character
+        outside the charset becomes byte 0xFF, which is never a symbol."""
+        if self._chars_in is None:
+            return s
+        m = self._chars_in
+        return ''.join(chr(m.get(ord(c), 0xFF)) for c in s)
+
+    def text_out(self, s):
+        return s if self._chars_out is None else s.translate(self._chars_out)
+
     def _decode(self, lo, hi):
         if self.alphabet is not None:
-            return decode_keys(lo, hi, self.k, self.sym_bits, np.frombuffer(self.alphabet.ljust(256, b'?'), dtype=np.uint8))
+            out = decode_keys(lo, hi, self.k, self.sym_bits, np.frombuffer(self.alphabet.ljust(256, b'?'), dtype=np.uint8))
+            return out if self._chars_out is None else [x.translate(self._chars_out) for x in out]
         return decode_keys(lo, hi, self.k)
 
     def labels(self):
@@ -493,6 +517,8 @@ class Graph:
         out = np.zeros(n, np.uint32)
         if n == 0:
             return out
+        if self._chars_in is not None:
+            kplus1mers = [self.text_in(x) for x in kplus1mers]
         buf = ''.join(kplus1mers).encode('latin-1', 'replace')
         if len(buf) != n * (self.k + 1):
             raise ValueError('every query must have length k+1')
@@ -538,7 +564,7 @@ class Graph:
         buf = np.empty(total, np.uint8)
         self.lib.check(self.h, self.lib.dbg_materialize(self.h, idx.ctypes.data, len(idx), buf.ctypes.data,
                                                         off.ctypes.data))
-        raw = buf.tobytes().decode('latin-1')
+        raw = self.text_out(buf.tobytes().decode('latin-1'))
         o = off.tolist()
         return [raw[o[i]:o[i + 1]] for i in range(len(idx))]
 
@@ -757,7 +783,7 @@ class EdgeCountTable(Mapping):
             d = {}
             if getattr(g, 'alphabet', None) is not None:
                 e = g.edges()
-                for s_, sym, c in zip(e['src'].tolist(), e['symbol'].tobytes().decode('latin-1'), e['count'].tolist()):
+                for s_, sym, c in zip(e['src'].tolist(), g.text_out(e['symbol'].tobytes().decode('latin-1')), e['count'].tolist()):
                     d[labels[s_] + sym] = c
                 self._d = d
                 return d

@@ -16,14 +16,16 @@ two and only indexes the third); they compare equal to the reference's dicts whe
 There is no CPU path: without the built library or a CUDA device these calls raise.  DNA reads
 (ACGT) run on the 2-bit engine, 1 <= k <= 63; reads over any other alphabet of single-byte characters (peptides,
 DNA with N / IUPAC codes, text) on the generic engine, b = ceil(log2(distinct characters)) bits a symbol and
-b (k + 1) <= 125: peptides k <= 24, ACGT + N k <= 40, 255 distinct characters k <= 14.
+b (k + 1) <= 125: peptides k <= 24, ACGT + N k <= 40, 255 distinct characters k <= 14.  Reads with characters beyond
+latin-1 (any Unicode text) travel as one private byte per distinct character (up to 255) and come back as they were.
 """
 from __future__ import annotations
 
 import numpy as np
 
 from dbg_b200._native import AlphabetError
-from dbg_b200.graph import BatchGraph, EdgeCountTable, Edges, Graph, KmerList, Node, Vertices, pack_reads  # noqa: F401
+from dbg_b200.graph import (BatchGraph, EdgeCountTable, Edges, Graph, KmerList, Node, NotSingleByteError, Vertices,  # noqa: F401
+                            pack_reads)
 
 __all__ = ['Node', 'read_reads', 'construct_graph', 'construct_graph_batch', 'output_contigs', 'get_score',
            'support_read_scores', 'findSupportReadScore', 'sort_by_support', 'concatenate_outputs']
@@ -49,7 +51,18 @@ def reverse_complement(read):
 def _graph_for(reads, k, threshold, final, min_count=1, both_strands=False):
     """Build on the DNA engine; reads over another alphabet (the reference's real inputs are peptides,
     II_assembleFromReads.py:43-47) go to the generic-alphabet engine with the symbols they use."""
-    packed = pack_reads(reads)
+    try:
+        packed = pack_reads(reads)
+    except NotSingleByteError:                                                 # characters beyond latin-1: a private byte per character
+        if both_strands:
+            raise ValueError('dbg_b200: both_strands needs DNA reads (ACGT)') from None
+        if min_count != 1:
+            raise ValueError('dbg_b200: min_count exists for the DNA engine only') from None
+        charset = sorted(set(''.join(reads)))
+        if len(charset) > 255:
+            raise ValueError('dbg_b200: the reads use %d distinct characters; the GPU path handles up to 255' % len(charset)) from None
+        g = Graph(k, charset=charset)
+        return g.build(reads, threshold=threshold, final=final, packed=pack_reads([g.text_in(r) for r in reads]))
     g = Graph(k)
     try:
         return g.build(reads, threshold=threshold, final=final, packed=packed, min_count=min_count, both_strands=both_strands)
@@ -112,7 +125,7 @@ def construct_graph_batch(batches, k, threshold=3, final=False, min_count=1):
     try:
         g.set_min_count(min_count)
         g.build_batched(batches, threshold=threshold, final=final)
-    except AlphabetError:                                                # not DNA: one generic-alphabet build per batch
+    except (AlphabetError, NotSingleByteError):                          # not DNA: one generic-alphabet build per batch
         g.close()
         return [construct_graph(b, k, threshold, final, min_count) for b in batches]
     flags = g.pull_read_flags().tolist() if (not final and g.stats().n_pull_reads) else None

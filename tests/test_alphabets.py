@@ -59,8 +59,8 @@ def test_restatement_equals_the_literal_reference_on_these_alphabets():
 def test_limits_are_reported(backend):
     with pytest.raises(ValueError, match='3-bit codes: 1..40'):
         util.product_snapshot(['ACGTN' * 20], 41, 2, False)
-    with pytest.raises(ValueError, match='single-byte'):
-        util.product_snapshot(['日本語のテキスト'], 2, 2, False)
+    with pytest.raises(ValueError, match='distinct characters'):
+        util.product_snapshot([''.join(chr(0x4E00 + c) for c in range(300))], 2, 2, False)
     with pytest.raises(ValueError, match='256 byte values'):
         util.product_snapshot([''.join(chr(c) for c in range(256)) * 2], 2, 2, False)
 
@@ -85,6 +85,32 @@ def test_lookups_on_a_wide_alphabet(backend):
         ect[keys[-1]]
     scores = [db.get_score(ect, c, k) for c in contigs]
     assert scores == [sum(want[c[i:i + k + 1]] for i in range(len(c) - k)) for c in contigs]
+
+
+def test_unicode_reads_travel_as_private_bytes(backend):
+    """Characters beyond latin-1 (the reference takes any str): one private byte per distinct character, every string
+    that comes back (labels, branch / pulled lists, edge keys, contigs) is mapped back; lookups translate their query."""
+    import contextlib
+    import io
+    import debruijn as db
+    r = random.Random(5)
+    al = '\u65e5\u672c\u8a9e\u306e\u30c6\u30ad\u30b9\u30c8\u03b1\u03b2\u03b3\u03b4\u20ac\xe9A'
+    G = ''.join(r.choice(al) for _ in range(200))
+    G = G[:100] + G[10:25] + G[100:]
+    reads = [G[p:p + r.randrange(8, 30)] for p in (r.randrange(0, len(G) - 8) for _ in range(60))]
+    for k, thr, final in ((3, 2, False), (5, 2, True), (7, 1, False)):
+        exp = dbg_oracle.snapshot(reads, k, thr, final, max_paths=500)
+        util.assert_same(util.product_snapshot(reads, k, thr, final), exp, 'unicode k = %d' % k)
+    with contextlib.redirect_stdout(io.StringIO()):
+        g, pull, branch, pulled, ect = db.construct_graph(reads, 3, 2, False)
+        contigs = db.output_contigs(g, branch, pulled)
+        per_batch = db.construct_graph_batch([reads, reads[:20]], 3, 2, False)
+    want = dict(map(tuple, dbg_oracle.snapshot(reads, 3, 2, False)['ect']))
+    assert dict(ect) == want and dict(per_batch[0][4]) == want
+    assert ect._graph.lookup_edges(list(want)[:20]).tolist() == [want[e] for e in list(want)[:20]]
+    assert all(db.get_score(ect, c, 3) == sum(want[c[i:i + 4]] for i in range(len(c) - 3)) for c in contigs)
+    with pytest.raises(KeyError):
+        ect['ZZZZ']
 
 
 def keys_absent(reads, k):
