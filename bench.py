@@ -648,6 +648,14 @@ def run_dbg(args, cfg, rank, local_rank, world):
 
     ms_total = R.timed(step_device, args.steps, collect)
     st = g.stats()
+    # probe lengths of the two hash tables the timed step left (north-star evidence; outside every timed region)
+    probe = None
+    if not sharded:
+        try:
+            probe = {w: {f: v for f, v in g.probe_stats(w).items() if f != 'hist'} for w in ('nodes', 'chunks')}
+            probe['what'] = 'slots a lookup of an entry touches (linear probing from its home slot); dbg_probe_stats'
+        except Exception as e:                                           # e.g. a build that did not go through chunks
+            probe = {'error': str(e)[:200]}
     launches = int(st.n_launches)
     mode = last['res'].mode if sharded else ('batched' if batched else 'single')
     n_contigs_local = len(last['res'].contigs) if sharded and last['res'].mode == 'sharded' else int(st.n_contigs)
@@ -780,6 +788,7 @@ def run_dbg(args, cfg, rank, local_rank, world):
                 cold, roofline_frac=nwin * b_build / (cold['table_build_ms'] * 1e-3) / 1e9 / peak,
                 note='every build sizes its tables from HyperLogLog sketches first (DBG_B200_NO_HINT=1), as the first '
                      'build on a handle does')},
+        'probe_length': probe,
         'gpu_launches': launches * args.steps,
         'gpu_launches_per_step': launches,
         'clocks': clocks,

@@ -273,6 +273,12 @@ int dbg_node_keys(dbg_t *h, const uint32_t *node_id, uint64_t n, uint64_t *key_l
  * successors, balance = outdegree - indegree.  DNA handles holding the complete graph; any pointer may be NULL. */
 int dbg_degree_balance(dbg_t *h, const uint32_t *node_id, uint64_t n, uint8_t *indegree, uint8_t *outdegree,
                        int8_t *balance);
+/* Measurement aid (north-star: "probe length" as evidence for the hash-table design; bench.py reports it): probe-length
+ * statistics of the node table (which = 0) or the chunk table (which = 1) the last build left.  Both tables probe
+ * linearly from a home slot; an entry's probe length is the number of slots a lookup of its key touches.
+ * hist64[j] = entries of length j + 1 (hist64[63]: everything longer); any pointer may be NULL.  DNA handles.        */
+int dbg_probe_stats(dbg_t *h, int which, uint64_t *hist64, uint64_t *n_entries, uint64_t *sum_len, uint64_t *max_len,
+                    uint64_t *n_slots);
 /* twin_id[j] = node id of the reverse complement of node node_id[j], 0xFFFFFFFF if the graph does not hold it (it always
  * does after a DBG_BOTH_STRANDS build); canonical[j] = 1 iff the node's k-mer <= its reverse complement (the canonical
  * representative of the pair; both 1 for a palindrome, which is its own twin).  DNA handles, unbatched builds.        */

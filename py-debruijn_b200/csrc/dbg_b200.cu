@@ -2960,6 +2960,44 @@ DBG_API int dbg_degree_balance(dbg_t *h, const uint32_t *node_id, uint64_t n, ui
 }
 
 template <int W>
+static int probe_stats_impl(dbg_t *h, int which, uint64_t *hist, uint64_t *n_entries, uint64_t *sum_len, uint64_t *max_len,
+                            uint64_t *n_slots_out) {
+    DevBuf *s = h->b_scratch;
+    TRY(reserve(h, s[0], (PROBE_HIST + 3) * 8));
+    CK(cudaMemsetAsync(s[0].p, 0, (PROBE_HIST + 3) * 8, h->stream));
+    u64 *d_hist = ptr<u64>(s[0]), *d_acc = ptr<u64>(s[0]) + PROBE_HIST;
+    const uint64_t n_slots = which == 0 ? h->n_slots : h->n_cslots;
+    uint64_t grid = blocks_for(n_slots);
+    if (grid > 148 * 8) grid = 148 * 8;
+    if (which == 0)
+        LAUNCH(k_probe_stats_nodes<W>, grid, DBG_BLOCK, h->stream, ptr<const Slot<W>>(h->b_table), geom_of(h), d_hist, d_acc);
+    else
+        LAUNCH(k_probe_stats_chunks<W>, grid, DBG_BLOCK, h->stream, ptr<const ChunkSlot<W>>(h->b_ctable), n_slots, d_hist, d_acc);
+    CKK();
+    uint64_t host[PROBE_HIST + 3];
+    CK(cudaMemcpyAsync(host, s[0].p, sizeof host, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (hist) memcpy(hist, host, PROBE_HIST * 8);
+    if (n_entries) *n_entries = host[PROBE_HIST];
+    if (sum_len) *sum_len = host[PROBE_HIST + 1];
+    if (max_len) *max_len = host[PROBE_HIST + 2];
+    if (n_slots_out) *n_slots_out = n_slots;
+    return DBG_OK;
+}
+
+DBG_API int dbg_probe_stats(dbg_t *h, int which, uint64_t *hist64, uint64_t *n_entries, uint64_t *sum_len, uint64_t *max_len,
+                            uint64_t *n_slots) {
+    NEED_BUILT();
+    if (which != 0 && which != 1) return fail(h, DBG_ERR_ARG, "dbg_probe_stats: which = 0 (node table) or 1 (chunk table)");
+    if (h->generic) return fail(h, DBG_ERR_STATE, "dbg_probe_stats exists for the DNA engine only");
+    if (which == 0 && !h->table_ready) return fail(h, DBG_ERR_STATE, "dbg_probe_stats: no node table on this handle");
+    if (which == 1 && (!h->chunks_valid || !h->n_cslots))
+        return fail(h, DBG_ERR_STATE, "dbg_probe_stats: no chunk table on this handle (the build did not go through chunks)");
+    CK(cudaSetDevice(h->device));
+    return DISPATCH(probe_stats_impl, h, which, hist64, n_entries, sum_len, max_len, n_slots);
+}
+
+template <int W>
 static int lookup_impl(dbg_t *h, const uint8_t *q, const uint32_t *batch, uint64_t n, uint32_t *counts) {
     DevBuf *s = h->b_scratch;
     const uint64_t bytes = n * (uint64_t)(h->k + 1);

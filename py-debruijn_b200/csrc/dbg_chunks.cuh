@@ -332,6 +332,64 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_chunk_rehash(const ChunkSlot<W> *
     cc->chunk_overflow = 1;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Probe-length statistics (dbg_probe_stats; north-star "probe length" evidence, reported by bench.py): both tables
+// probe linearly from a home slot, so an entry's probe length = 1 + the cyclic distance from its home to the slot it
+// lives in = the number of slots a lookup of that key touches.  hist[j] counts lengths j + 1 (the last bucket takes
+// everything longer); acc[0] = entries, acc[1] = sum of lengths, acc[2] = longest.
+// ---------------------------------------------------------------------------------------------
+#define PROBE_HIST 64
+DBG_D void probe_stats_tally(u32 *sh_hist, bool have, u64 len, u64 *acc) {
+    if (have) {
+        atomicAdd(&sh_hist[len <= PROBE_HIST ? (u32)len - 1u : PROBE_HIST - 1u], 1u);
+        atomicAdd(&acc[1], len);
+        atomicMax(&acc[2], len);
+    }
+}
+template <int W>
+__global__ void __launch_bounds__(DBG_BLOCK) k_probe_stats_nodes(const Slot<W> *__restrict__ table, TGeom g, u64 *hist, u64 *acc) {
+    __shared__ u32 sh_hist[PROBE_HIST];
+    for (u32 j = threadIdx.x; j < PROBE_HIST; j += blockDim.x) sh_hist[j] = 0;
+    __syncthreads();
+    typedef typename KeyOf<W>::type K;
+    const K EMPTY = empty_key<W>();
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < g.n_slots; i += (u64)gridDim.x * blockDim.x) {
+        const K key = load_key(&table[i]);
+        const bool have = key != EMPTY;
+        u64 len = 0;
+        if (have) {
+            const u64 home = node_home(g, key);
+            len = (i >= home ? i - home : i + g.n_slots - home) + 1;
+        }
+        probe_stats_tally(sh_hist, have, len, acc);
+    }
+    __syncthreads();
+    for (u32 j = threadIdx.x; j < PROBE_HIST; j += blockDim.x)
+        if (sh_hist[j]) { atomicAdd(&hist[j], (u64)sh_hist[j]); atomicAdd(&acc[0], (u64)sh_hist[j]); }
+}
+template <int W>
+__global__ void __launch_bounds__(DBG_BLOCK) k_probe_stats_chunks(const ChunkSlot<W> *__restrict__ table, u64 n_slots, u64 *hist,
+                                                                 u64 *acc) {
+    __shared__ u32 sh_hist[PROBE_HIST];
+    for (u32 j = threadIdx.x; j < PROBE_HIST; j += blockDim.x) sh_hist[j] = 0;
+    __syncthreads();
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += (u64)gridDim.x * blockDim.x) {
+        ChunkKey<W> key;
+#pragma unroll
+        for (int hh = 0; hh < W; hh++) key.h[hh] = load_k128(&table[i].h[hh]);
+        const bool have = key.h[0] != k128_ones();
+        u64 len = 0;
+        if (have) {
+            const u64 home = slot_home(chunk_hash<W>(key), n_slots);
+            len = (i >= home ? i - home : i + n_slots - home) + 1;
+        }
+        probe_stats_tally(sh_hist, have, len, acc);
+    }
+    __syncthreads();
+    for (u32 j = threadIdx.x; j < PROBE_HIST; j += blockDim.x)
+        if (sh_hist[j]) { atomicAdd(&hist[j], (u64)sh_hist[j]); atomicAdd(&acc[0], (u64)sh_hist[j]); }
+}
+
 #ifndef DBG_CHUNK_MIN_BLOCKS
 #define DBG_CHUNK_MIN_BLOCKS 4
 #endif

@@ -122,6 +122,7 @@ SYMBOLS = {
     'dbg_pull_reads': (C.c_int, [_P, _P]),
     'dbg_node_keys': (C.c_int, [_P, _P, C.c_uint64, _P, _P]),
     'dbg_degree_balance': (C.c_int, [_P, _P, C.c_uint64, _P, _P, _P]),
+    'dbg_probe_stats': (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P]),
     'dbg_twin_nodes': (C.c_int, [_P, _P, C.c_uint64, _P, _P]),
     'dbg_lookup_edges': (C.c_int, [_P, _P, C.c_uint64, _P]),
     'dbg_lookup_edges_batched': (C.c_int, [_P, _P, _P, C.c_uint64, _P]),

@@ -451,6 +451,19 @@ class Graph:
             self._edges = a
         return self._edges
 
+    def probe_stats(self, which='nodes'):
+        """Probe-length statistics of the node table ('nodes') or the chunk table ('chunks') of the last build
+        (dbg_probe_stats): the number of slots a lookup of an entry's key touches (linear probing from its home slot)."""
+        hist = np.zeros(64, np.uint64)
+        n, total, longest, slots = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self.lib.check(self.h, self.lib.dbg_probe_stats(self.h, {'nodes': 0, 'chunks': 1}[which], hist.ctypes.data, C.byref(n),
+                                                        C.byref(total), C.byref(longest), C.byref(slots)))
+        cum = np.cumsum(hist)
+        q = lambda f: int(np.searchsorted(cum, f * n.value) + 1) if n.value else 0       # noqa: E731
+        return {'entries': int(n.value), 'slots': int(slots.value), 'load': n.value / max(1, slots.value),
+                'mean': total.value / max(1, n.value), 'p50': q(0.5), 'p99': q(0.99), 'max': int(longest.value),
+                'hist': hist.astype(np.int64).tolist()}
+
     def degree_balance(self):
         """TRUE in-degree (distinct predecessors), out-degree (distinct successors) and balance = out - in of every
         node of the unpruned graph, in nodes() order (dbg_degree_balance).  An extra output: the reference keeps only

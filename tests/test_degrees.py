@@ -45,3 +45,30 @@ def test_degree_balance(backend):
         assert d['outdegree'].tolist() == [len(succ[v]) for v in order]
         assert d['balance'].tolist() == [len(succ[v]) - len(pred[v]) for v in order]
         g.close()
+
+
+def test_probe_stats(backend):
+    """dbg_probe_stats: every entry counted once, lengths consistent, and the mean where linear probing puts it
+    for the table's load (successful search: (1 + 1 / (1 - load)) / 2), for one- and two-word keys."""
+    import util
+    from dbg_b200 import Graph
+    _, reads = util.synth_reads(9, 20000, 100, 12, err=0.01)
+    for k in (21, 47):
+        g = Graph(k)
+        g.build(reads, threshold=2)
+        st = g.stats()
+        p = g.probe_stats('nodes')
+        assert p['entries'] == st.n_nodes == sum(p['hist']) and p['slots'] == st.table_slots
+        assert p['p50'] <= p['p99'] <= min(p['max'], 64) and p['max'] < p['slots']
+        theory = (1 + 1 / (1 - p['load'])) / 2
+        assert 1.0 <= p['mean'] < 1.5 * theory + 0.5
+        c = g.probe_stats('chunks')
+        assert c['entries'] == sum(c['hist']) > 0 and c['entries'] <= st.chunk_slots and 1.0 <= c['mean'] < 4
+        g.close()
+    import pytest
+    from dbg_b200._native import DbgError
+    g = Graph(5, alphabet=b'ACDEFGHIKLMNPQRSTVWY')
+    g.build(['ACDEFGHIKLMNPQRSTVWY'], threshold=2)
+    with pytest.raises(DbgError):
+        g.probe_stats('nodes')
+    g.close()
