@@ -251,7 +251,8 @@ int dbg_shard_reduced_records(dbg_t *h, const uint32_t *d_replies, const uint64_
 int dbg_shard_walk(dbg_t *h, const uint64_t *d_all_records, uint64_t n_total, uint64_t my_base, uint64_t *n_contigs);
 int dbg_shard_contigs(dbg_t *h, dbg_shard_contig_t *out);            /* n_contigs entries            */
 
-/* nodes, unordered (sort by first_tag for the reference's dict order).  Any pointer may be
+/* nodes in first-occurrence order (ascending first_tag = the reference's dict order, debruijn.py:121-143; sorted
+ * on the device).  Any pointer may be
  * NULL.  succ_cnt: 4 per node = edge_count_table[node + "ACGT"[c]]; kept: low 8 bits = kept
  * successor bases in E order (2 bits each, first in bits 0-1), bits 8-10 = how many are kept
  * (pruningEdges result, debruijn.py:150-166).                                               */

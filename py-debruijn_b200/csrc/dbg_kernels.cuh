@@ -1164,26 +1164,17 @@ __global__ void __launch_bounds__(DBG_BLOCK) k_gather_keys(const Slot<W> *__rest
     hi[i] = key_hi64(key);
 }
 
-// export: compact occupied slots (unordered)
+// export: the fields of the given slots (dbg_export_nodes: the occupied slots in first-occurrence order)
 template <int W>
-__global__ void __launch_bounds__(DBG_BLOCK) k_export(const Slot<W> *__restrict__ table, u64 n_slots,
-                                                      const u8 *__restrict__ flags, const u16 *__restrict__ kept,
-                                                      u64 *cursor, u32 *__restrict__ o_id, u64 *__restrict__ o_lo,
-                                                      u64 *__restrict__ o_hi, u64 *__restrict__ o_tag,
-                                                      u32 *__restrict__ o_cnt, u8 *__restrict__ o_flags,
-                                                      u16 *__restrict__ o_kept) {
-    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    bool occ = i < n_slots && (flags[i] & F_OCC);
-    u32 b = __ballot_sync(0xFFFFFFFFu, occ);
-    if (!b) return;
-    u32 lane = threadIdx.x & 31;
-    u64 base = 0;
-    if (lane == 0) base = atomicAdd(cursor, (u64)__popc(b));
-    base = __shfl_sync(0xFFFFFFFFu, base, 0);
-    if (!occ) return;
-    u64 o = base + __popc(b & ((1u << lane) - 1));
+__global__ void __launch_bounds__(DBG_BLOCK) k_export_gather(const Slot<W> *__restrict__ table, const u8 *__restrict__ flags,
+                                                             const u16 *__restrict__ kept, const u32 *__restrict__ ids, u64 n,
+                                                             u64 *__restrict__ o_lo, u64 *__restrict__ o_hi,
+                                                             u64 *__restrict__ o_tag, u32 *__restrict__ o_cnt,
+                                                             u8 *__restrict__ o_flags, u16 *__restrict__ o_kept) {
+    const u64 o = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= n) return;
+    const u32 i = ids[o];
     typename KeyOf<W>::type key = table[i].key;
-    o_id[o] = (u32)i;
     o_lo[o] = key_lo64(key);
     o_hi[o] = key_hi64(key);
     o_tag[o] = table[i].tag;

@@ -37,7 +37,7 @@ class NotSingleByteError(ValueError):
 def pack_reads(reads):
     """list[str] -> (uint8[n_bases] ASCII, uint64[n+1] offsets); II hands over a plain list."""
     n = len(reads)
-    lens = np.fromiter((len(r) for r in reads), dtype=np.uint64, count=n)
+    lens = np.fromiter(map(len, reads), dtype=np.uint64, count=n)
     off = np.zeros(n + 1, dtype=np.uint64)
     np.cumsum(lens, out=off[1:])
     try:
@@ -395,10 +395,24 @@ class Graph:
             rc = self.lib.dbg_export_nodes(self.h, *(a[f].ctypes.data for f in
                                                      ('id', 'key_lo', 'key_hi', 'tag', 'cnt', 'flags', 'kept')))
             self.lib.check(self.h, rc)
-            order = np.argsort(a['tag'], kind='stable')
-            self._nodes = {f: v[order] for f, v in a.items()}
+            t = a['tag']
+            if len(t) > 1 and not bool((t[1:] > t[:-1]).all()):     # the library exports in tag order; an older one did not
+                order = np.argsort(t, kind='stable')
+                a = {f: v[order] for f, v in a.items()}
+            self._nodes = a
             self._nodes['batch'] = self.batch_of_keys(self._nodes['key_lo'], self._nodes['key_hi'])
         return self._nodes
+
+    def _batch_bounds(self, name, batch_fn):
+        """First position of every batch id in a batch-major list (n_batches + 1 entries), computed once per list."""
+        if self._batch_cache is None:
+            self._batch_cache = {}
+        key = ('bounds', name)
+        if key not in self._batch_cache:
+            batch = np.asarray(batch_fn())
+            nb = int(getattr(self, 'n_batches', 0) or (int(batch.max()) + 1 if len(batch) else 0))
+            self._batch_cache[key] = np.searchsorted(batch, np.arange(nb + 2, dtype=batch.dtype))
+        return self._batch_cache[key]
 
     def batch_of_keys(self, key_lo, key_hi):
         """Batch id of node keys (the bits above the 2k key bits; 0 for a graph built without batches)."""
@@ -605,9 +619,8 @@ class BatchGraph:
     def __init__(self, parent, b):
         self.parent, self.b = parent, int(b)
         self.k, self.device = parent.k, parent.device
-        nd = parent.nodes()
-        lo, hi = np.searchsorted(nd['batch'], [self.b, self.b + 1])      # nodes are sorted by tag = batch-major
-        self._lo, self._hi = int(lo), int(hi)
+        bounds = parent._batch_bounds('nodes', lambda: parent.nodes()['batch'])   # nodes are sorted by tag = batch-major
+        self._lo, self._hi = int(bounds[self.b]), int(bounds[self.b + 1])
         self._nodes = None
         self._labels = None
 
@@ -649,8 +662,8 @@ class BatchGraph:
                 p.lib.check(p.h, p.lib.dbg_node_keys(p.h, ids.ctypes.data, len(ids), lo_k.ctypes.data, hi_k.ctypes.data))
             p._batch_cache[name] = (ids, p.batch_of_keys(lo_k, hi_k))
         ids, batch = p._batch_cache[name]
-        a, z = np.searchsorted(batch, [self.b, self.b + 1])
-        return ids, int(a), int(z)
+        bounds = p._batch_bounds(name, lambda: batch)
+        return ids, int(bounds[self.b]), int(bounds[self.b + 1])
 
     def branch_ids(self):
         ids, a, z = self._split('branch', self.parent.branch_ids)
@@ -682,16 +695,31 @@ class BatchGraph:
             self._strings = p.contig_strings(np.arange(a, z, dtype=np.uint64))
             if p._batch_cache:
                 p._batch_cache.pop('contigs', None)                      # the handle no longer holds the default walk
+                p._batch_cache.pop(('bounds', 'contigs'), None)
+                p._batch_cache.pop('strings', None)
             return p.contig_descriptors()[a:z]
         _, a, z = self._split('contigs', lambda: p.walk(stop_at_branch=default)['start'])
         self._contig_range = (a, z)                                    # contigs come in start order = batch-major
         return p.contig_descriptors()[a:z]
 
+    STRINGS_AT_ONCE = 1 << 28            # characters: below this the strings of ALL batches come over in one call
+
     def contig_strings(self):
         if getattr(self, '_strings', None) is not None:
             return self._strings
         a, z = self._contig_range
-        return self.parent.contig_strings(np.arange(a, z, dtype=np.uint64))
+        p = self.parent
+        cache = p._batch_cache
+        if cache is not None and 'contigs' in cache:
+            # the handle holds the default walk of the whole graph (_split('contigs')): one dbg_materialize for every
+            # batch instead of one per batch (a call costs ~0.5 ms of copies and synchronisation whatever its size)
+            if 'strings' not in cache:
+                d = p.contig_descriptors()
+                total = int(d['n_nodes'].sum()) + (self.k - 1) * len(d)
+                cache['strings'] = p.contig_strings() if total <= self.STRINGS_AT_ONCE else None
+            if cache['strings'] is not None:
+                return cache['strings'][a:z]
+        return p.contig_strings(np.arange(a, z, dtype=np.uint64))
 
 
 # ---------------------------------------------------------------------------------------------
