@@ -9,6 +9,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import threading
 from collections.abc import Mapping
 
 import numpy as np
@@ -73,6 +74,32 @@ def decode_keys(key_lo, key_hi, k, bits=2, symbols=_ALPHA):
     return [text[i:i + k] for i in range(0, n * k, k)]
 
 
+# Handles of finished construct_graph calls, kept for the next call with the same k / alphabet / device (debruijn.py's API
+# has no state to hang a handle on, and dbg_create + dbg_destroy cost 1.7 ms -- more than building a small graph; a reused
+# handle also keeps its buffers and remembers its table sizes).  Only handles whose last build was small and that never
+# reported an error are kept; DBG_B200_HANDLE_POOL=0 switches the pool off.
+_POOL = {}
+_POOL_LOCK = threading.Lock()
+POOL_PER_KEY, POOL_TOTAL, POOL_MAX_BASES = 2, 8, 32 << 20
+
+
+def _pool_take(key):
+    with _POOL_LOCK:
+        lst = _POOL.get(key)
+        return lst.pop() if lst else None
+
+
+def _pool_put(key, h):
+    if os.environ.get('DBG_B200_HANDLE_POOL', '1') == '0':
+        return False
+    with _POOL_LOCK:
+        lst = _POOL.setdefault(key, [])
+        if len(lst) >= POOL_PER_KEY or sum(map(len, _POOL.values())) >= POOL_TOTAL:
+            return False
+        lst.append(h)
+        return True
+
+
 def _default_device():
     for var in ('DBG_B200_DEVICE', 'LOCAL_RANK'):
         v = os.environ.get(var)
@@ -85,12 +112,14 @@ class Graph:
     """One de Bruijn graph resident on one GPU (one ``dbg_t``).  Re-usable: ``build`` may be
     called again with new reads and keeps its HBM."""
 
-    def __init__(self, k, device=None, lib=None, key_words=0, alphabet=None, charset=None):
+    def __init__(self, k, device=None, lib=None, key_words=0, alphabet=None, charset=None, pooled=False):
         """`alphabet` = bytes of up to 255 distinct symbols: the generic-alphabet engine, b = ceil(log2(symbols)) bits a
         symbol and b (k + 1) <= 125 (peptides: 5 bits, k <= 24; ACGT + N: 3 bits, k <= 40; 8 bits: k <= 14).
         None = the DNA engine (ACGT, k <= 63).  `charset` = a list of up to 255 characters for reads that are not
         latin-1 (any Unicode text, as the reference takes): character i travels as byte value i, the alphabet is
-        bytes(range(len(charset))) and every string that comes back (labels, contigs, edge keys) is mapped back."""
+        bytes(range(len(charset))) and every string that comes back (labels, contigs, edge keys) is mapped back.
+        `pooled`: take the handle of an earlier, closed Graph of the same shape if there is one, and hand this one's
+        on when it is closed (what debruijn.construct_graph does)."""
         self.lib = lib or N.get()
         self.k = int(k)
         self.device = _default_device() if device is None else int(device)
@@ -102,14 +131,18 @@ class Graph:
             self._chars_out = {i: c for i, c in enumerate(charset)}
         self.alphabet = bytes(alphabet) if alphabet is not None else None
         self.sym_bits = max(1, (len(self.alphabet) - 1).bit_length()) if self.alphabet is not None else 2
-        h = C.c_void_p()
-        if self.alphabet is not None:
-            rc = self.lib.dbg_create_alpha(C.byref(h), self.device, self.k, self.alphabet, len(self.alphabet))
-        else:
-            rc = self.lib.dbg_create_ex(C.byref(h), self.device, self.k, int(key_words))
-        if rc != N.DBG_OK:
-            msg = self.lib.dbg_last_error(None)
-            N._raise(rc, msg.decode() if msg else '')
+        self._pool_key = (self.lib.path, self.device, self.k, int(key_words), self.alphabet) if pooled else None
+        self._pool_ok = False
+        h = _pool_take(self._pool_key) if pooled else None
+        if h is None:
+            h = C.c_void_p()
+            if self.alphabet is not None:
+                rc = self.lib.dbg_create_alpha(C.byref(h), self.device, self.k, self.alphabet, len(self.alphabet))
+            else:
+                rc = self.lib.dbg_create_ex(C.byref(h), self.device, self.k, int(key_words))
+            if rc != N.DBG_OK:
+                msg = self.lib.dbg_last_error(None)
+                N._raise(rc, msg.decode() if msg else '')
         self.h = h
         self.reads = None
         self.final = False
@@ -124,9 +157,13 @@ class Graph:
         self._stats = None
 
     def close(self):
-        if getattr(self, 'h', None):
-            self.lib.dbg_destroy(self.h)
+        h = getattr(self, 'h', None)
+        if h:
             self.h = None
+            if getattr(self, '_pool_key', None) is not None and self._pool_ok and not self.lib.dbg_last_error(h) \
+                    and _pool_put(self._pool_key, h):
+                return
+            self.lib.dbg_destroy(h)
 
     def __del__(self):
         try:
@@ -145,6 +182,7 @@ class Graph:
               packed=None, read_idx_base=0, min_count=1, both_strands=False):
         """Host entry: `reads` is a list[str] (or pass packed=(uint8 bases, uint64 offsets)).  `both_strands`: an
         extension (DBG_BOTH_STRANDS) -- the graph of the reads followed by their reverse complements."""
+        self._pool_ok = False
         self.set_min_count(min_count)
         bases, off = packed if packed is not None else pack_reads(reads)
         self.reads = reads
@@ -157,6 +195,7 @@ class Graph:
         rc = self.lib.dbg_build(self.h, bases.ctypes.data if len(bases) else None, off.ctypes.data,
                                 self.n_reads, int(read_idx_base), float(threshold), flags)
         self.lib.check(self.h, rc)
+        self._pool_ok = len(bases) <= POOL_MAX_BASES   # (a handle that held a big graph keeps gigabytes of HBM: not kept)
         if both_strands:
             self.n_reads *= 2                          # read n + i = reverse complement of read i
         return self
@@ -330,6 +369,7 @@ class Graph:
                                    ('n_nodes', np.uint32), ('kind', np.uint32)])
 
     def shard_config(self, rank, n_ranks):
+        self._pool_key = None
         self.lib.check(self.h, self.lib.dbg_shard_config(self.h, int(rank), int(n_ranks)))
 
     def shard_exit_counts(self, n_ranks):
@@ -366,6 +406,7 @@ class Graph:
         """Run on the caller's stream.  0 / None is CUDA's legacy default stream (what
         torch.cuda.current_stream().cuda_stream returns by default), passed as cudaStreamLegacy;
         use own_stream() to go back to the handle's private stream."""
+        self._pool_key = None
         self.lib.check(self.h, self.lib.dbg_set_stream(self.h, cuda_stream_ptr or 1))
         self._stream = int(cuda_stream_ptr or 0)
 

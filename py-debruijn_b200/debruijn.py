@@ -61,9 +61,9 @@ def _graph_for(reads, k, threshold, final, min_count=1, both_strands=False):
         charset = sorted(set(''.join(reads)))
         if len(charset) > 255:
             raise ValueError('dbg_b200: the reads use %d distinct characters; the GPU path handles up to 255' % len(charset)) from None
-        g = Graph(k, charset=charset)
+        g = Graph(k, charset=charset, pooled=True)
         return g.build(reads, threshold=threshold, final=final, packed=pack_reads([g.text_in(r) for r in reads]))
-    g = Graph(k)
+    g = Graph(k, pooled=True)
     try:
         return g.build(reads, threshold=threshold, final=final, packed=packed, min_count=min_count, both_strands=both_strands)
     except AlphabetError:
@@ -73,7 +73,7 @@ def _graph_for(reads, k, threshold, final, min_count=1, both_strands=False):
     symbols = np.flatnonzero(np.bincount(packed[0], minlength=256)).astype(np.uint8)
     if len(symbols) > 255:
         raise ValueError('dbg_b200: the reads use all 256 byte values; the GPU path handles alphabets of up to 255')
-    g = Graph(k, alphabet=symbols.tobytes())
+    g = Graph(k, alphabet=symbols.tobytes(), pooled=True)
     return g.build(reads, threshold=threshold, final=final, packed=packed, min_count=min_count)
 
 

@@ -446,3 +446,39 @@ def test_region_layout(backend, monkeypatch, region_slots):
         qs = list(ect)[:50] + ['A' * (k + 1)]
         assert g.lookup_edges(qs).tolist() == [ect.get(q, 0) for q in qs]
         g.close()
+
+
+def test_handle_pool_reuses_handles_between_calls(backend, monkeypatch):
+    """debruijn.construct_graph keeps the handle of a finished (garbage-collected) call for the next call with the same
+    k and alphabet (dbg_create + dbg_destroy cost more than a small build).  A reused handle remembers buffers and table
+    sizes of an unrelated read set: results must not depend on what it held before."""
+    import gc
+    import debruijn as db
+    from dbg_b200 import graph as G
+    r = random.Random(99)
+    sizes = [200, 4000, 150, 30000, 300, 300, 12000, 100]
+    created = []
+    lib = G.N.get()
+    real = lib.dbg_create_ex
+    monkeypatch.setattr(lib, 'dbg_create_ex', lambda *a: (created.append(1), real(*a))[1])
+    with G._POOL_LOCK:
+        G._POOL.clear()
+    for i, gsize in enumerate(sizes):
+        _, reads = util.synth_reads(100 + i, gsize, 60, 12, err=r.choice([0.0, 0.02]))
+        exp = dbg_oracle.snapshot(reads, 21, 2, False)
+        got = util.product_snapshot(reads, 21, 2, False)
+        util.assert_same(got, exp, 'pooled handle, call %d' % i)
+        gc.collect()
+    assert len(created) <= 2, 'every call created a handle: the pool is not used'
+    pep = ['EVQLVESGGALVQPGG', 'VQLVESGGGLVQ', 'LVESGGALVQPGGSLR', 'ESGGGLVQPGGSLRLS']
+    for _ in range(3):
+        util.assert_same(util.product_snapshot(pep, 5, 2, False), dbg_oracle.snapshot(pep, 5, 2, False), 'pooled generic handle')
+        gc.collect()
+    monkeypatch.setenv('DBG_B200_HANDLE_POOL', '0')
+    with G._POOL_LOCK:
+        G._POOL.clear()
+    n0 = len(created)
+    for i in range(3):
+        util.product_snapshot(['ACGTACGGTCA', 'CGTACGGTCAT'], 4, 2, False)
+        gc.collect()
+    assert len(created) == n0 + 3 and not any(G._POOL.values())
