@@ -483,12 +483,25 @@ def e2e_api(R, args):
     for _ in range(n):
         contigs = call()
     ms = (time.perf_counter() - t0) / n * 1e3
+    # the same call with a NEW handle every time (the module otherwise reuses the handle of the previous, finished call)
+    os.environ['DBG_B200_HANDLE_POOL'] = '0'
+    try:
+        call()
+        t0 = time.perf_counter()
+        for _ in range(n):
+            contigs = call()
+        ms_fresh = (time.perf_counter() - t0) / n * 1e3
+    finally:
+        del os.environ['DBG_B200_HANDLE_POOL']
     t0 = time.perf_counter()
     g, pull, branch, pulled, ect = dbg_oracle.construct_graph(reads, cfg['k'], cfg['thr'], False, verbose=False)
     exp = dbg_oracle.output_contigs(g, branch, pulled, verbose=False)
     ms_port = (time.perf_counter() - t0) * 1e3
     out['c1'] = {'workload': cfg['name'], 'reads': len(reads), 'contigs': len(contigs), 'chars': sum(map(len, contigs)),
-                 'ms_per_call': ms, 'windows': n_windows_of(off, cfg['k']),
+                 'ms_per_call': ms, 'ms_per_call_new_handle': ms_fresh,
+                 'handle': 'ms_per_call: repeated calls reuse the handle of the previous finished call (pool in dbg_b200/graph.py); '
+                           'ms_per_call_new_handle: DBG_B200_HANDLE_POOL=0',
+                 'windows': n_windows_of(off, cfg['k']),
                  'kmers_per_sec': n_windows_of(off, cfg['k']) / (ms * 1e-3),
                  'python_port_ms': ms_port, 'strings_equal_port': contigs == exp,
                  'literal_reference_note': 'the literal debruijn.py needs 48 s for this call (BASELINE.md section 2: '
