@@ -78,7 +78,8 @@ def decode_keys(key_lo, key_hi, k, bits=2, symbols=_ALPHA):
 # has no state to hang a handle on, and dbg_create + dbg_destroy cost 1.7 ms -- more than building a small graph; a reused
 # handle also keeps its buffers and remembers its table sizes).  Only handles whose last build was small and that never
 # reported an error are kept; DBG_B200_HANDLE_POOL=0 switches the pool off.
-_POOL = {}
+_POOL = {}                               # key -> [(handle, age, library)], oldest first
+_POOL_CLOCK = [0]
 _POOL_LOCK = threading.Lock()
 POOL_PER_KEY, POOL_TOTAL, POOL_MAX_BASES = 2, 8, 32 << 20
 
@@ -86,18 +87,27 @@ POOL_PER_KEY, POOL_TOTAL, POOL_MAX_BASES = 2, 8, 32 << 20
 def _pool_take(key):
     with _POOL_LOCK:
         lst = _POOL.get(key)
-        return lst.pop() if lst else None
+        return lst.pop()[0] if lst else None
 
 
-def _pool_put(key, h):
+def _pool_put(key, h, lib):
+    """Keep handle h for the next Graph of this shape; the oldest kept handle makes room when the pool is full (a
+    caller that changes k with every call, as II's loop does, would otherwise fill it with handles nobody takes)."""
     if os.environ.get('DBG_B200_HANDLE_POOL', '1') == '0':
         return False
+    evict = None
     with _POOL_LOCK:
+        _POOL_CLOCK[0] += 1
         lst = _POOL.setdefault(key, [])
-        if len(lst) >= POOL_PER_KEY or sum(map(len, _POOL.values())) >= POOL_TOTAL:
-            return False
-        lst.append(h)
-        return True
+        if len(lst) >= POOL_PER_KEY:
+            evict = lst.pop(0)
+        elif sum(map(len, _POOL.values())) >= POOL_TOTAL:
+            k_old = min((k for k, v in _POOL.items() if v), key=lambda k: _POOL[k][0][1])
+            evict = _POOL[k_old].pop(0)
+        lst.append((h, _POOL_CLOCK[0], lib))
+    if evict is not None:
+        evict[2].dbg_destroy(evict[0])
+    return True
 
 
 def _default_device():
@@ -161,7 +171,7 @@ class Graph:
         if h:
             self.h = None
             if getattr(self, '_pool_key', None) is not None and self._pool_ok and not self.lib.dbg_last_error(h) \
-                    and _pool_put(self._pool_key, h):
+                    and _pool_put(self._pool_key, h, self.lib):
                 return
             self.lib.dbg_destroy(h)
 
