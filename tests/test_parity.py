@@ -474,6 +474,13 @@ def test_handle_pool_reuses_handles_between_calls(backend, monkeypatch):
     for _ in range(3):
         util.assert_same(util.product_snapshot(pep, 5, 2, False), dbg_oracle.snapshot(pep, 5, 2, False), 'pooled generic handle')
         gc.collect()
+    # a caller that changes k with every call (II's loop): the pool never holds more than POOL_TOTAL handles, the oldest go
+    _, reads = util.synth_reads(5, 2000, 60, 10)
+    for k in list(range(30, 18, -1)) + [20, 20]:
+        util.assert_same(util.product_snapshot(reads, k, 2, False), dbg_oracle.snapshot(reads, k, 2, False), 'k = %d' % k)
+        gc.collect()
+    assert sum(map(len, G._POOL.values())) <= G.POOL_TOTAL
+    assert any(key[2] == 20 for key, v in G._POOL.items() if v) and not any(key[2] == 30 for key, v in G._POOL.items() if v)
     monkeypatch.setenv('DBG_B200_HANDLE_POOL', '0')
     with G._POOL_LOCK:
         G._POOL.clear()
