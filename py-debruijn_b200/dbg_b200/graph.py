@@ -144,6 +144,7 @@ class Graph:
         self._pool_key = (self.lib.path, self.device, self.k, int(key_words), self.alphabet) if pooled else None
         self._pool_ok = False
         h = _pool_take(self._pool_key) if pooled else None
+        self.from_pool = h is not None
         if h is None:
             h = C.c_void_p()
             if self.alphabet is not None:

@@ -23,7 +23,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from dbg_b200._native import AlphabetError
+from dbg_b200._native import AlphabetError, DbgError
 from dbg_b200.graph import (BatchGraph, EdgeCountTable, Edges, Graph, KmerList, Node, NotSingleByteError, Vertices,  # noqa: F401
                             pack_reads)
 
@@ -48,6 +48,23 @@ def reverse_complement(read):
     return read.translate(_COMP)[::-1]
 
 
+def _build_pooled(make, **kw):
+    """Graph.build on a handle from the pool; an internal error on a REUSED handle (never seen; the handle then
+    carries an error and is destroyed, not kept) is answered with one more try on a new handle."""
+    g = make(True)
+    try:
+        return g.build(**kw)
+    except (DbgError, MemoryError):
+        reused = g.from_pool
+        g.close()
+        if not reused:
+            raise
+    except BaseException:
+        g.close()
+        raise
+    return make(False).build(**kw)
+
+
 def _graph_for(reads, k, threshold, final, min_count=1, both_strands=False):
     """Build on the DNA engine; reads over another alphabet (the reference's real inputs are peptides,
     II_assembleFromReads.py:43-47) go to the generic-alphabet engine with the symbols they use."""
@@ -61,20 +78,22 @@ def _graph_for(reads, k, threshold, final, min_count=1, both_strands=False):
         charset = sorted(set(''.join(reads)))
         if len(charset) > 255:
             raise ValueError('dbg_b200: the reads use %d distinct characters; the GPU path handles up to 255' % len(charset)) from None
-        g = Graph(k, charset=charset, pooled=True)
-        return g.build(reads, threshold=threshold, final=final, packed=pack_reads([g.text_in(r) for r in reads]))
-    g = Graph(k, pooled=True)
+        fwd = {ord(c): i for i, c in enumerate(charset)}
+        packed = pack_reads([r.translate(fwd) for r in reads])
+        return _build_pooled(lambda pooled: Graph(k, charset=charset, pooled=pooled), reads=reads, threshold=threshold,
+                             final=final, packed=packed)
     try:
-        return g.build(reads, threshold=threshold, final=final, packed=packed, min_count=min_count, both_strands=both_strands)
+        return _build_pooled(lambda pooled: Graph(k, pooled=pooled), reads=reads, threshold=threshold, final=final,
+                             packed=packed, min_count=min_count, both_strands=both_strands)
     except AlphabetError:
-        g.close()
+        pass
     if both_strands:
         raise ValueError('dbg_b200: both_strands needs DNA reads (ACGT)')
     symbols = np.flatnonzero(np.bincount(packed[0], minlength=256)).astype(np.uint8)
     if len(symbols) > 255:
         raise ValueError('dbg_b200: the reads use all 256 byte values; the GPU path handles alphabets of up to 255')
-    g = Graph(k, alphabet=symbols.tobytes(), pooled=True)
-    return g.build(reads, threshold=threshold, final=final, packed=packed, min_count=min_count)
+    return _build_pooled(lambda pooled: Graph(k, alphabet=symbols.tobytes(), pooled=pooled), reads=reads, threshold=threshold,
+                         final=final, packed=packed, min_count=min_count)
 
 
 def construct_graph(reads, k, threshold=3, final=False, min_count=1, both_strands=False):

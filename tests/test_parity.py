@@ -489,3 +489,27 @@ def test_handle_pool_reuses_handles_between_calls(backend, monkeypatch):
         util.product_snapshot(['ACGTACGGTCA', 'CGTACGGTCAT'], 4, 2, False)
         gc.collect()
     assert len(created) == n0 + 3 and not any(G._POOL.values())
+
+
+def test_reused_handle_that_fails_is_replaced(backend, monkeypatch):
+    """An internal error on a handle taken from the pool is answered with one more try on a new handle."""
+    import gc
+    import debruijn as db
+    from dbg_b200 import graph as G
+    from dbg_b200._native import DbgError
+    reads = ['ACGTACGGTCATTGCA', 'CGTACGGTCATTGCAG', 'GTACGGTCATTGCAGT']
+    exp = dbg_oracle.snapshot(reads, 5, 2, False)
+    util.assert_same(util.product_snapshot(reads, 5, 2, False), exp, 'first call')
+    gc.collect()
+    assert any(key[2] == 5 for key, v in G._POOL.items() if v)
+    real = G.Graph.build
+    failed = []
+
+    def build(self, *a, **kw):
+        if self.from_pool and not failed:
+            failed.append(1)
+            raise DbgError(-5, 'injected')
+        return real(self, *a, **kw)
+    monkeypatch.setattr(G.Graph, 'build', build)
+    util.assert_same(util.product_snapshot(reads, 5, 2, False), exp, 'call whose pooled handle failed')
+    assert failed
